@@ -1,0 +1,578 @@
+// C-ABI implementation (include/microclimc_b200.h): context, static column split over GPUs, kernel launches.
+// One host thread + one stream per GPU, no collective, no CPU fallback.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+#include <functional>
+#include "../../include/microclimc_b200.h"
+#include "mc_driver.cuh"
+#include "mc_steady.cuh"
+
+using namespace mc;
+
+// ---------------------------------------------------------------------------------------------------
+// kernels: one column per thread; the column index is the fastest-varying index of every array, so each
+// warp-wide load/store touches 32 consecutive doubles (two full 128-B lines).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kBlock = 128;
+
+template <int MM, int MS>
+__global__ void __launch_bounds__(kBlock) k_transient(TransientArgs a) {
+  long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (c < a.ncol) run_column<MM, MS>(a, c);
+}
+template <int MM, int MS>
+__global__ void __launch_bounds__(kBlock) k_onestep(OneStepArgs a) {
+  long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (c < a.ncol) onestep_column<MM, MS>(a, c);
+}
+template <int MM, int MS>
+__global__ void __launch_bounds__(kBlock) k_paraminit(long long ncol, int m, int sm, const double* args, double* state) {
+  long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (c < ncol) paraminit_column<MM, MS>(ncol, m, sm, args, state, c);
+}
+template <int MM>
+__global__ void __launch_bounds__(kBlock) k_steady(SteadyArgs a) {
+  long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (c < a.ncol) steady_column<MM>(a, c, blockIdx.y, gridDim.y);
+}
+__global__ void k_steady_reduce(long long ncol, int nchunk, long long T, const double* part, double* stats) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncol) return;
+  double s0 = 0, mn0 = 1e300, mx0 = -1e300, s1 = 0, mn1 = 1e300, mx1 = -1e300;
+  for (int k = 0; k < nchunk; ++k) {
+    const double* p = part + (long long)k * 6 * ncol;
+    s0 += p[0 * ncol + c]; mn0 = dmin(mn0, p[1 * ncol + c]); mx0 = dmax(mx0, p[2 * ncol + c]);
+    s1 += p[3 * ncol + c]; mn1 = dmin(mn1, p[4 * ncol + c]); mx1 = dmax(mx1, p[5 * ncol + c]);
+  }
+  stats[0 * ncol + c] = s0 / (double)T; stats[1 * ncol + c] = mn0; stats[2 * ncol + c] = mx0;
+  stats[3 * ncol + c] = s1 / (double)T; stats[4 * ncol + c] = mn1; stats[5 * ncol + c] = mx1;
+}
+
+// FP64 pipe peak probe: 8 independent DFMA chains per thread (the roofline denominator for this FP64-bound path;
+// MEASURED_PEAKS.json has no FP64 entry).
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+std::string g_create_err;
+
+struct DBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t need(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+struct Shard {
+  int dev = 0; long long c0 = 0, nc = 0;
+  cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  DBuf vegp, soilp, lat, lon, state, state_bak, fscale, foffset, forcing, season, tsoil, stats, series, full, samp_of, flags,
+      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart;
+  bool has_pert = false, has_season = false, has_state = false;
+  float ms = 0; long long launches = 0;
+  // replay info for mc_bench_resident
+  int last_kind = 0;   // 0 none, 1 transient, 2 steady
+  TransientArgs last_t; SteadyArgs last_s; int last_nchunk = 1;
+  std::string err;
+};
+
+}  // namespace
+
+struct mc_ctx {
+  int m = 0, sm = 0;
+  long long ncol = 0, T = 0;
+  std::vector<Shard> shards;
+  double cfg[MC_C_N_];
+  bool has_cfg = false;
+  std::string err;
+  double last_ms = 0; long long last_launches = 0;
+};
+
+namespace {
+
+int fail(mc_ctx* ctx, int code, const std::string& msg) { if (ctx) ctx->err = msg; return code; }
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { s.err = std::string(#call) + ": " + cudaGetErrorString(e_); return MC_ERR_CUDA; } } while (0)
+
+// run fn on every shard, one host thread per GPU, joined before return
+int for_shards(mc_ctx* ctx, const std::function<int(Shard&)>& fn) {
+  std::vector<int> rc(ctx->shards.size(), 0);
+  if (ctx->shards.size() == 1) {
+    cudaSetDevice(ctx->shards[0].dev);
+    rc[0] = fn(ctx->shards[0]);
+  } else {
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < ctx->shards.size(); ++i)
+      th.emplace_back([&, i] { cudaSetDevice(ctx->shards[i].dev); rc[i] = fn(ctx->shards[i]); });
+    for (auto& t : th) t.join();
+  }
+  for (size_t i = 0; i < rc.size(); ++i)
+    if (rc[i]) { ctx->err = "gpu " + std::to_string(ctx->shards[i].dev) + ": " + ctx->shards[i].err; return rc[i]; }
+  return 0;
+}
+
+// copy rows x [c0, c0+nc) of a host [rows][ncol] array to a dense device [rows][nc] array (and back)
+cudaError_t h2d_rows(double* dst, const double* src, long long rows, long long ncol, long long c0, long long nc, cudaStream_t st) {
+  return cudaMemcpy2DAsync(dst, nc * sizeof(double), src + c0, ncol * sizeof(double), nc * sizeof(double), rows,
+                           cudaMemcpyHostToDevice, st);
+}
+cudaError_t d2h_rows(double* dst, const double* src, long long rows, long long ncol, long long c0, long long nc, cudaStream_t st) {
+  return cudaMemcpy2DAsync(dst + c0, ncol * sizeof(double), src, nc * sizeof(double), nc * sizeof(double), rows,
+                           cudaMemcpyDeviceToHost, st);
+}
+
+RunCfg mk_cfg(const double* c) {
+  RunCfg r;
+  r.timestep = c[MC_C_TIMESTEP]; r.edgedist = c[MC_C_EDGEDIST]; r.reqhgt = c[MC_C_REQHGT]; r.zu = c[MC_C_ZU];
+  r.merid = c[MC_C_MERID]; r.dst = c[MC_C_DST]; r.n = c[MC_C_N]; r.metopen = c[MC_C_METOPEN] != 0; r.windhgt = c[MC_C_WINDHGT];
+  r.zlafact = c[MC_C_ZLAFACT]; r.surfwet = c[MC_C_SURFWET];
+  return r;
+}
+
+template <class F> int dispatch_ms(int m, int sm, F&& f) {
+  if (m <= 20 && sm <= 10) return f(std::integral_constant<int, 20>(), std::integral_constant<int, 10>());
+  return f(std::integral_constant<int, 64>(), std::integral_constant<int, 32>());
+}
+inline unsigned nblocks(long long n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+int launch_transient(Shard& s, const TransientArgs& a) {
+  return dispatch_ms(a.m, a.sm, [&](auto MM, auto MS) {
+    k_transient<decltype(MM)::value, decltype(MS)::value><<<nblocks(a.ncol), kBlock, 0, s.st>>>(a);
+    s.launches++;
+    return 0;
+  });
+}
+int launch_steady(Shard& s, const SteadyArgs& a, int nchunk) {
+  dim3 grid(nblocks(a.ncol), nchunk);
+  if (a.m <= 20) k_steady<20><<<grid, kBlock, 0, s.st>>>(a);
+  else k_steady<64><<<grid, kBlock, 0, s.st>>>(a);
+  s.launches++;
+  if (a.part) {
+    k_steady_reduce<<<nblocks(a.ncol), kBlock, 0, s.st>>>(a.ncol, nchunk, a.T, a.part, a.stats);
+    s.launches++;
+  }
+  return 0;
+}
+void collect_timing(mc_ctx* ctx) {
+  double ms = 0; long long l = 0;
+  for (auto& s : ctx->shards) { if (s.ms > ms) ms = s.ms; l += s.launches; }
+  ctx->last_ms = ms; ctx->last_launches = l;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mc_version(void) { return MC_ABI_VERSION; }
+int mc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+int mc_nveg(int m) { return MC_V_NSCAL + 4 * m; }
+int mc_nsoil(int sm) { return MC_S_NSCAL + sm; }
+int mc_nstate(int m, int sm) { return nstate_rows(m, sm); }
+const char* mc_last_error(const mc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+mc_ctx* mc_create(int m, int sm, int n_gpus, const int* gpu_ids) {
+  if (m < 3) { g_create_err = "At least three canopy layers must be provided"; return nullptr; }
+  if (m > 64 || sm > 32 || sm < 2) { g_create_err = "supported sizes: 3 <= m <= 64, 2 <= sm <= 32"; return nullptr; }
+  int ndev = mc_device_count();
+  if (ndev <= 0) { g_create_err = "no CUDA device visible: microclimc_b200 has no CPU fallback"; return nullptr; }
+  if (n_gpus <= 0) n_gpus = 1;
+  if (n_gpus > ndev) { g_create_err = "requested " + std::to_string(n_gpus) + " GPUs but only " + std::to_string(ndev) + " visible"; return nullptr; }
+  mc_ctx* ctx = new mc_ctx();
+  ctx->m = m; ctx->sm = sm;
+  ctx->shards.resize(n_gpus);
+  for (int i = 0; i < n_gpus; ++i) {
+    Shard& s = ctx->shards[i];
+    s.dev = gpu_ids ? gpu_ids[i] : i;
+    if (cudaSetDevice(s.dev) != cudaSuccess || cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&s.e0) != cudaSuccess || cudaEventCreate(&s.e1) != cudaSuccess) {
+      g_create_err = std::string("CUDA init failed on device ") + std::to_string(s.dev) + ": " + cudaGetErrorString(cudaGetLastError());
+      delete ctx; return nullptr;
+    }
+  }
+  std::memset(ctx->cfg, 0, sizeof(ctx->cfg));
+  return ctx;
+}
+void mc_destroy(mc_ctx* ctx) {
+  if (!ctx) return;
+  for (auto& s : ctx->shards) {
+    cudaSetDevice(s.dev);
+    DBuf* bufs[] = {&s.vegp, &s.soilp, &s.lat, &s.lon, &s.state, &s.state_bak, &s.fscale, &s.foffset, &s.forcing, &s.season, &s.tsoil,
+                    &s.stats, &s.series, &s.full, &s.samp_of, &s.flags, &s.args6, &s.clim8, &s.theta, &s.thetap, &s.nmerged,
+                    &s.sclim, &s.snmr, &s.sseason, &s.sout, &s.spart};
+    for (DBuf* b : bufs) b->release();
+    if (s.e0) cudaEventDestroy(s.e0);
+    if (s.e1) cudaEventDestroy(s.e1);
+    if (s.st) cudaStreamDestroy(s.st);
+  }
+  delete ctx;
+}
+
+int mc_set_columns(mc_ctx* ctx, int64_t ncol, const double* vegp, const double* soilp, const double* lat, const double* lon) {
+  if (!ctx || ncol <= 0 || !vegp || !soilp || !lat || !lon) return fail(ctx, MC_ERR_ARG, "mc_set_columns: bad argument");
+  ctx->ncol = ncol;
+  const int G = (int)ctx->shards.size();
+  const long long per = (ncol + G - 1) / G;
+  for (int i = 0; i < G; ++i) {
+    Shard& s = ctx->shards[i];
+    s.c0 = std::min<long long>((long long)i * per, ncol);
+    s.nc = std::min<long long>(per, ncol - s.c0);
+    s.has_state = false; s.has_pert = false; s.last_kind = 0;
+  }
+  const int NV = mc_nveg(ctx->m), NSo = mc_nsoil(ctx->sm), NSt = mc_nstate(ctx->m, ctx->sm);
+  return for_shards(ctx, [&](Shard& s) -> int {
+    if (s.nc == 0) return 0;
+    CU(s.vegp.need(sizeof(double) * NV * s.nc)); CU(s.soilp.need(sizeof(double) * NSo * s.nc));
+    CU(s.lat.need(sizeof(double) * s.nc)); CU(s.lon.need(sizeof(double) * s.nc));
+    CU(s.state.need(sizeof(double) * NSt * s.nc));
+    CU(h2d_rows(s.vegp.as<double>(), vegp, NV, ncol, s.c0, s.nc, s.st));
+    CU(h2d_rows(s.soilp.as<double>(), soilp, NSo, ncol, s.c0, s.nc, s.st));
+    CU(h2d_rows(s.lat.as<double>(), lat, 1, ncol, s.c0, s.nc, s.st));
+    CU(h2d_rows(s.lon.as<double>(), lon, 1, ncol, s.c0, s.nc, s.st));
+    CU(cudaStreamSynchronize(s.st));
+    return 0;
+  });
+}
+
+int mc_set_forcing(mc_ctx* ctx, int64_t T, const double* forcing, const double* fscale, const double* foffset, const double* pai_season) {
+  if (!ctx || T <= 0 || !forcing || ctx->ncol <= 0) return fail(ctx, MC_ERR_ARG, "mc_set_forcing: bad argument (set columns first)");
+  if ((fscale == nullptr) != (foffset == nullptr)) return fail(ctx, MC_ERR_ARG, "mc_set_forcing: fscale and foffset must both be given");
+  ctx->T = T;
+  const long long ncol = ctx->ncol;
+  return for_shards(ctx, [&](Shard& s) -> int {
+    if (s.nc == 0) return 0;
+    CU(s.forcing.need(sizeof(double) * T * MC_F_N));
+    CU(cudaMemcpyAsync(s.forcing.p, forcing, sizeof(double) * T * MC_F_N, cudaMemcpyHostToDevice, s.st));
+    s.has_pert = fscale != nullptr;
+    if (fscale) {
+      CU(s.fscale.need(sizeof(double) * MC_NPERT * s.nc)); CU(s.foffset.need(sizeof(double) * MC_NPERT * s.nc));
+      CU(h2d_rows(s.fscale.as<double>(), fscale, MC_NPERT, ncol, s.c0, s.nc, s.st));
+      CU(h2d_rows(s.foffset.as<double>(), foffset, MC_NPERT, ncol, s.c0, s.nc, s.st));
+    }
+    s.has_season = pai_season != nullptr;
+    if (pai_season) {
+      CU(s.season.need(sizeof(double) * T));
+      CU(cudaMemcpyAsync(s.season.p, pai_season, sizeof(double) * T, cudaMemcpyHostToDevice, s.st));
+    }
+    CU(cudaStreamSynchronize(s.st));
+    return 0;
+  });
+}
+
+int mc_set_config(mc_ctx* ctx, const double* cfg) {
+  if (!ctx || !cfg) return fail(ctx, MC_ERR_ARG, "mc_set_config: bad argument");
+  std::memcpy(ctx->cfg, cfg, sizeof(ctx->cfg));
+  ctx->has_cfg = true;
+  return 0;
+}
+
+int mc_set_state(mc_ctx* ctx, const double* state) {
+  if (!ctx || !state || ctx->ncol <= 0) return fail(ctx, MC_ERR_ARG, "mc_set_state: bad argument (set columns first)");
+  const int NSt = mc_nstate(ctx->m, ctx->sm);
+  const long long ncol = ctx->ncol;
+  return for_shards(ctx, [&](Shard& s) -> int {
+    if (s.nc == 0) return 0;
+    CU(h2d_rows(s.state.as<double>(), state, NSt, ncol, s.c0, s.nc, s.st));
+    CU(cudaStreamSynchronize(s.st));
+    s.has_state = true;
+    return 0;
+  });
+}
+int mc_get_state(mc_ctx* ctx, double* state) {
+  if (!ctx || !state || ctx->ncol <= 0) return fail(ctx, MC_ERR_ARG, "mc_get_state: bad argument");
+  for (auto& s : ctx->shards) if (s.nc && !s.has_state) return fail(ctx, MC_ERR_STATE, "mc_get_state: no state on the device yet");
+  const int NSt = mc_nstate(ctx->m, ctx->sm);
+  const long long ncol = ctx->ncol;
+  return for_shards(ctx, [&](Shard& s) -> int {
+    if (s.nc == 0) return 0;
+    CU(d2h_rows(state, s.state.as<double>(), NSt, ncol, s.c0, s.nc, s.st));
+    CU(cudaStreamSynchronize(s.st));
+    return 0;
+  });
+}
+
+int mc_paraminit(mc_ctx* ctx, const double* args) {
+  if (!ctx || !args || ctx->ncol <= 0) return fail(ctx, MC_ERR_ARG, "mc_paraminit: bad argument (set columns first)");
+  const long long ncol = ctx->ncol;
+  const int m = ctx->m, sm = ctx->sm;
+  int rc = for_shards(ctx, [&](Shard& s) -> int {
+    s.ms = 0; s.launches = 0;
+    if (s.nc == 0) return 0;
+    CU(s.args6.need(sizeof(double) * 6 * s.nc));
+    CU(h2d_rows(s.args6.as<double>(), args, 6, ncol, s.c0, s.nc, s.st));
+    CU(cudaEventRecord(s.e0, s.st));
+    dispatch_ms(m, sm, [&](auto MM, auto MS) {
+      k_paraminit<decltype(MM)::value, decltype(MS)::value><<<nblocks(s.nc), kBlock, 0, s.st>>>(s.nc, m, sm, s.args6.as<double>(), s.state.as<double>());
+      return 0;
+    });
+    s.launches++;
+    CU(cudaEventRecord(s.e1, s.st));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s.st));
+    CU(cudaEventElapsedTime(&s.ms, s.e0, s.e1));
+    s.has_state = true;
+    return 0;
+  });
+  collect_timing(ctx);
+  return rc;
+}
+
+int mc_run_onestep(mc_ctx* ctx, const double* climvars, double jd, double lt, const double* theta, const double* thetap, int32_t* nmerged) {
+  if (!ctx || !climvars || !theta || !thetap || ctx->ncol <= 0) return fail(ctx, MC_ERR_ARG, "mc_run_onestep: bad argument");
+  if (!ctx->has_cfg) return fail(ctx, MC_ERR_ARG, "mc_run_onestep: mc_set_config first");
+  for (auto& s : ctx->shards) if (s.nc && !s.has_state) return fail(ctx, MC_ERR_STATE, "mc_run_onestep: no state (mc_paraminit / mc_set_state first)");
+  const long long ncol = ctx->ncol;
+  const int m = ctx->m, sm = ctx->sm;
+  RunCfg cfg = mk_cfg(ctx->cfg);
+  int rc = for_shards(ctx, [&](Shard& s) -> int {
+    s.ms = 0; s.launches = 0;
+    if (s.nc == 0) return 0;
+    CU(s.clim8.need(sizeof(double) * 8 * s.nc)); CU(s.theta.need(sizeof(double) * s.nc)); CU(s.thetap.need(sizeof(double) * s.nc));
+    CU(s.nmerged.need(sizeof(int) * s.nc));
+    CU(h2d_rows(s.clim8.as<double>(), climvars, 8, ncol, s.c0, s.nc, s.st));
+    CU(h2d_rows(s.theta.as<double>(), theta, 1, ncol, s.c0, s.nc, s.st));
+    CU(h2d_rows(s.thetap.as<double>(), thetap, 1, ncol, s.c0, s.nc, s.st));
+    OneStepArgs a{};
+    a.ncol = s.nc; a.m = m; a.sm = sm; a.vegp = s.vegp.as<double>(); a.soilp = s.soilp.as<double>(); a.lat = s.lat.as<double>();
+    a.lon = s.lon.as<double>(); a.climvars = s.clim8.as<double>(); a.theta = s.theta.as<double>(); a.thetap = s.thetap.as<double>();
+    a.jd = jd; a.lt = lt; a.state = s.state.as<double>(); a.nmerged = s.nmerged.as<int>(); a.cfg = cfg;
+    CU(cudaEventRecord(s.e0, s.st));
+    dispatch_ms(m, sm, [&](auto MM, auto MS) {
+      k_onestep<decltype(MM)::value, decltype(MS)::value><<<nblocks(s.nc), kBlock, 0, s.st>>>(a);
+      return 0;
+    });
+    s.launches++;
+    CU(cudaEventRecord(s.e1, s.st));
+    CU(cudaGetLastError());
+    if (nmerged) CU(cudaMemcpyAsync(nmerged + s.c0, s.nmerged.p, sizeof(int) * s.nc, cudaMemcpyDeviceToHost, s.st));
+    CU(cudaStreamSynchronize(s.st));
+    CU(cudaEventElapsedTime(&s.ms, s.e0, s.e1));
+    return 0;
+  });
+  collect_timing(ctx);
+  return rc;
+}
+
+static int run_transient_impl(mc_ctx* ctx, int64_t t0, int64_t t1, int spin_steps, const double* tsoil, const int64_t* samp_idx,
+                              int64_t nsamp, double* series, double* fullseries, double* stats, int32_t* flags) {
+  if (!ctx || ctx->ncol <= 0 || ctx->T <= 0) return fail(ctx, MC_ERR_ARG, "mc_run_transient: set columns and forcing first");
+  if (!ctx->has_cfg) return fail(ctx, MC_ERR_ARG, "mc_run_transient: mc_set_config first");
+  if (t0 < 0 || t1 < t0 || t1 > ctx->T) return fail(ctx, MC_ERR_ARG, "mc_run_transient: bad step range");
+  if ((series || fullseries) && (!samp_idx || nsamp <= 0)) return fail(ctx, MC_ERR_ARG, "mc_run_transient: series requested without samp_idx");
+  if (!ctx->cfg[MC_C_METOPEN]) {   // code.R:1141-1143 — checked per column on the host mirror; here a cheap global guard is not possible
+  }
+  if (spin_steps <= 0) for (auto& s : ctx->shards) if (s.nc && !s.has_state)
+    return fail(ctx, MC_ERR_STATE, "mc_run_transient: no state on the device (spin-up disabled and no mc_set_state / mc_paraminit)");
+  for (int64_t j = 0; j < nsamp; ++j) if (samp_idx[j] < 0 || samp_idx[j] >= ctx->ncol) return fail(ctx, MC_ERR_ARG, "mc_run_transient: samp_idx out of range");
+  const long long ncol = ctx->ncol;
+  const int m = ctx->m, sm = ctx->sm, NSt = mc_nstate(m, sm);
+  const long long nt = t1 - t0;
+  RunCfg cfg = mk_cfg(ctx->cfg);
+  const int charmode = ctx->cfg[MC_C_HARVEST_CHAR] != 0;
+  int rc = for_shards(ctx, [&](Shard& s) -> int {
+    s.ms = 0; s.launches = 0;
+    if (s.nc == 0) return 0;
+    // sample slots owned by this shard
+    std::vector<long long> samp_of; std::vector<int64_t> slots;
+    if (nsamp > 0 && (series || fullseries)) {
+      samp_of.assign(s.nc, -1);
+      for (int64_t j = 0; j < nsamp; ++j) {
+        long long c = samp_idx[j] - s.c0;
+        if (c >= 0 && c < s.nc) { samp_of[c] = (long long)slots.size(); slots.push_back(j); }
+      }
+    }
+    const long long ns = (long long)slots.size();
+    TransientArgs a{};
+    a.ncol = s.nc; a.m = m; a.sm = sm; a.T = ctx->T; a.t0 = t0; a.t1 = t1;
+    a.vegp = s.vegp.as<double>(); a.soilp = s.soilp.as<double>(); a.lat = s.lat.as<double>(); a.lon = s.lon.as<double>();
+    a.forcing = s.forcing.as<double>();
+    a.fscale = s.has_pert ? s.fscale.as<double>() : nullptr; a.foffset = s.has_pert ? s.foffset.as<double>() : nullptr;
+    a.season = s.has_season ? s.season.as<double>() : nullptr;
+    a.state = s.state.as<double>(); a.cfg = cfg; a.spin_steps = spin_steps; a.charmode = charmode;
+    if (tsoil) {
+      CU(s.tsoil.need(sizeof(double) * s.nc));
+      CU(h2d_rows(s.tsoil.as<double>(), tsoil, 1, ncol, s.c0, s.nc, s.st));
+      a.tsoil = s.tsoil.as<double>();
+    }
+    if (ns > 0) {
+      CU(s.samp_of.need(sizeof(long long) * s.nc));
+      CU(cudaMemcpyAsync(s.samp_of.p, samp_of.data(), sizeof(long long) * s.nc, cudaMemcpyHostToDevice, s.st));
+      a.samp_of = s.samp_of.as<long long>(); a.nsamp = ns;
+      if (series) { CU(s.series.need(sizeof(double) * nt * MC_O_N * ns)); a.series = s.series.as<double>(); }
+      if (fullseries) { CU(s.full.need(sizeof(double) * nt * NSt * ns)); a.full = s.full.as<double>(); }
+    }
+    if (stats) { CU(s.stats.need(sizeof(double) * 6 * s.nc)); a.stats = s.stats.as<double>(); }
+    if (flags) { CU(s.flags.need(sizeof(int) * s.nc)); a.flags = s.flags.as<int>(); }
+    if (spin_steps <= 0) {   // keep a copy so mc_bench_resident can replay from the same state
+      CU(s.state_bak.need(sizeof(double) * NSt * s.nc));
+      CU(cudaMemcpyAsync(s.state_bak.p, s.state.p, sizeof(double) * NSt * s.nc, cudaMemcpyDeviceToDevice, s.st));
+    }
+    CU(cudaEventRecord(s.e0, s.st));
+    launch_transient(s, a);
+    CU(cudaEventRecord(s.e1, s.st));
+    CU(cudaGetLastError());
+    s.last_kind = 1; s.last_t = a;
+    if (stats) CU(d2h_rows(stats, s.stats.as<double>(), 6, ncol, s.c0, s.nc, s.st));
+    if (flags) CU(cudaMemcpyAsync(flags + s.c0, s.flags.p, sizeof(int) * s.nc, cudaMemcpyDeviceToHost, s.st));
+    std::vector<double> hser, hfull;
+    if (ns > 0 && series) { hser.resize((size_t)nt * MC_O_N * ns); CU(cudaMemcpyAsync(hser.data(), s.series.p, sizeof(double) * hser.size(), cudaMemcpyDeviceToHost, s.st)); }
+    if (ns > 0 && fullseries) { hfull.resize((size_t)nt * NSt * ns); CU(cudaMemcpyAsync(hfull.data(), s.full.p, sizeof(double) * hfull.size(), cudaMemcpyDeviceToHost, s.st)); }
+    CU(cudaStreamSynchronize(s.st));
+    CU(cudaEventElapsedTime(&s.ms, s.e0, s.e1));
+    s.has_state = true;
+    // scatter this shard's sample slots into the caller's arrays (disjoint slots per shard)
+    for (long long k = 0; k < ns; ++k) {
+      const int64_t j = slots[k];
+      if (series) for (long long r = 0; r < nt * MC_O_N; ++r) series[r * nsamp + j] = hser[r * ns + k];
+      if (fullseries) for (long long r = 0; r < nt * NSt; ++r) fullseries[r * nsamp + j] = hfull[r * ns + k];
+    }
+    return 0;
+  });
+  collect_timing(ctx);
+  return rc;
+}
+
+int mc_run_transient(mc_ctx* ctx, int64_t t0, int64_t t1, const double* tsoil, const int64_t* samp_idx, int64_t nsamp,
+                     double* series, double* fullseries, double* stats, int32_t* flags) {
+  if (!ctx) return MC_ERR_ARG;
+  int spin = (t0 == 0) ? (int)ctx->cfg[MC_C_SPINSTEPS] : 0;
+  return run_transient_impl(ctx, t0, t1, spin, tsoil, samp_idx, nsamp, series, fullseries, stats, flags);
+}
+int mc_spinup(mc_ctx* ctx, int steps) {
+  if (!ctx || steps <= 0) return fail(ctx, MC_ERR_ARG, "mc_spinup: steps must be positive");
+  return run_transient_impl(ctx, 0, 0, steps, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+}
+
+int mc_run_steady(mc_ctx* ctx, int64_t T, const double* clim, const double* nmr, int nmr_percol, const double* scfg,
+                  const double* pai_season, double* out, double* stats) {
+  if (!ctx || ctx->ncol <= 0 || T <= 0 || !clim || !nmr || !scfg) return fail(ctx, MC_ERR_ARG, "mc_run_steady: bad argument (set columns first)");
+  const long long ncol = ctx->ncol;
+  const int m = ctx->m, sm = ctx->sm;
+  // snow-layer lookup guard (.snowtempf, NMR.R:495-508): the below-snow branch needs 0.025 <= reqhgt < 3
+  const double reqhgt = scfg[MC_SG_REQHGT];
+  int rc = for_shards(ctx, [&](Shard& s) -> int {
+    s.ms = 0; s.launches = 0;
+    if (s.nc == 0) return 0;
+    CU(s.sclim.need(sizeof(double) * T * MC_SC_N));
+    CU(cudaMemcpyAsync(s.sclim.p, clim, sizeof(double) * T * MC_SC_N, cudaMemcpyHostToDevice, s.st));
+    if (nmr_percol) {
+      CU(s.snmr.need(sizeof(double) * T * MC_SN_N * s.nc));
+      CU(h2d_rows(s.snmr.as<double>(), nmr, T * MC_SN_N, ncol, s.c0, s.nc, s.st));
+    } else {
+      CU(s.snmr.need(sizeof(double) * T * MC_SN_N));
+      CU(cudaMemcpyAsync(s.snmr.p, nmr, sizeof(double) * T * MC_SN_N, cudaMemcpyHostToDevice, s.st));
+    }
+    if (pai_season) {
+      CU(s.sseason.need(sizeof(double) * T));
+      CU(cudaMemcpyAsync(s.sseason.p, pai_season, sizeof(double) * T, cudaMemcpyHostToDevice, s.st));
+    }
+    // split time so that the grid has enough threads to fill the GPU when there are few columns
+    int nchunk = 1;
+    const long long want_threads = 148LL * 2048;
+    if (s.nc < want_threads) nchunk = (int)std::min<long long>((want_threads + s.nc - 1) / s.nc, std::max<long long>(1, T / 64));
+    if (nchunk > 65535) nchunk = 65535;
+    if (nchunk < 1) nchunk = 1;
+    SteadyArgs a{};
+    a.ncol = s.nc; a.m = m; a.sm = sm; a.T = T; a.vegp = s.vegp.as<double>(); a.soilp = s.soilp.as<double>();
+    a.lat = s.lat.as<double>(); a.lon = s.lon.as<double>(); a.clim = s.sclim.as<double>(); a.nmr = s.snmr.as<double>();
+    a.nmr_percol = nmr_percol; a.season = pai_season ? s.sseason.as<double>() : nullptr;
+    a.reqhgt = reqhgt; a.metopen = scfg[MC_SG_METOPEN] != 0; a.windhgt = scfg[MC_SG_WINDHGT]; a.surfwet = scfg[MC_SG_SURFWET];
+    if (out) { CU(s.sout.need(sizeof(double) * T * MC_SO_N * s.nc)); a.out = s.sout.as<double>(); }
+    if (stats) {
+      CU(s.stats.need(sizeof(double) * 6 * s.nc)); a.stats = s.stats.as<double>();
+      CU(s.spart.need(sizeof(double) * 6 * s.nc * nchunk)); a.part = s.spart.as<double>();
+    }
+    CU(s.flags.need(sizeof(int) * s.nc)); a.flags = s.flags.as<int>();
+    CU(cudaMemsetAsync(s.flags.p, 0, sizeof(int) * s.nc, s.st));
+    CU(cudaEventRecord(s.e0, s.st));
+    launch_steady(s, a, nchunk);
+    CU(cudaEventRecord(s.e1, s.st));
+    CU(cudaGetLastError());
+    s.last_kind = 2; s.last_s = a; s.last_nchunk = nchunk;
+    if (out) CU(d2h_rows(out, s.sout.as<double>(), T * MC_SO_N, ncol, s.c0, s.nc, s.st));
+    if (stats) CU(d2h_rows(stats, s.stats.as<double>(), 6, ncol, s.c0, s.nc, s.st));
+    std::vector<int> hflags(s.nc);
+    CU(cudaMemcpyAsync(hflags.data(), s.flags.p, sizeof(int) * s.nc, cudaMemcpyDeviceToHost, s.st));
+    CU(cudaStreamSynchronize(s.st));
+    CU(cudaEventElapsedTime(&s.ms, s.e0, s.e1));
+    for (int f : hflags) if (f & 4) { s.err = "snow-layer lookup out of range (.snowtempf needs 0.025 <= reqhgt < 3 m under snow)"; return MC_ERR_SNOWLAYER; }
+    return 0;
+  });
+  collect_timing(ctx);
+  return rc;
+}
+
+double mc_fp64_peak_tflops(mc_ctx* ctx) {
+  if (!ctx || ctx->shards.empty()) return -1.0;
+  Shard& s = ctx->shards[0];
+  cudaSetDevice(s.dev);
+  const int blocks = 148 * 16, threads = 256, iters = 20000;
+  double* buf = nullptr;
+  if (cudaMalloc(&buf, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
+  float best = 1e30f;
+  for (int r = 0; r < 4; ++r) {
+    cudaEventRecord(s.e0, s.st);
+    k_dfma_peak<<<blocks, threads, 0, s.st>>>(buf, iters, 0.999999, 1e-9);
+    cudaEventRecord(s.e1, s.st);
+    cudaStreamSynchronize(s.st);
+    float ms = 0; cudaEventElapsedTime(&ms, s.e0, s.e1);
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaFree(buf);
+  if (cudaGetLastError() != cudaSuccess) return -1.0;
+  double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+  return flops / (best * 1e-3) / 1e12;
+}
+
+double mc_last_kernel_ms(const mc_ctx* ctx) { return ctx ? ctx->last_ms : -1.0; }
+int64_t mc_last_kernel_launches(const mc_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+double mc_bench_resident(mc_ctx* ctx, int reps) {
+  if (!ctx || reps <= 0) return -1.0;
+  const int NSt = mc_nstate(ctx->m, ctx->sm);
+  int rc = for_shards(ctx, [&](Shard& s) -> int {
+    s.ms = 0; s.launches = 0;
+    if (s.nc == 0 || s.last_kind == 0) return 0;
+    float total = 0;
+    for (int r = 0; r < reps; ++r) {
+      if (s.last_kind == 1 && s.last_t.spin_steps <= 0)
+        CU(cudaMemcpyAsync(s.state.p, s.state_bak.p, sizeof(double) * NSt * s.nc, cudaMemcpyDeviceToDevice, s.st));
+      CU(cudaEventRecord(s.e0, s.st));
+      if (s.last_kind == 1) launch_transient(s, s.last_t); else launch_steady(s, s.last_s, s.last_nchunk);
+      CU(cudaEventRecord(s.e1, s.st));
+      CU(cudaGetLastError());
+      CU(cudaStreamSynchronize(s.st));
+      float ms = 0; CU(cudaEventElapsedTime(&ms, s.e0, s.e1));
+      total += ms;
+    }
+    s.ms = total / reps;
+    return 0;
+  });
+  collect_timing(ctx);
+  if (rc) return -1.0;
+  return ctx->last_ms;
+}
+
+}  // extern "C"

@@ -1,0 +1,164 @@
+// Device-side physics primitives for the microclimc hot path (FP64, sm_100a).
+//
+// These are the worker functions the reference obtains from `microctools` (absent from the reference
+// tree; SURVEY.md Appendix A gives every call site) plus the inline Tetens / latent-heat expressions of
+// R/code.R.  They are written for the GPU: functions are split into a column-invariant part (evaluated
+// once per column, `*_base`) and a per-step part, pow(x, 0.25) / pow(x, 1.75) are built from square
+// roots, and nothing allocates.  Semantics are those documented in DESIGN.md §"compat layer".
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define MC_HD __host__ __device__ __forceinline__
+#else
+#define MC_HD inline
+#endif
+
+namespace mc {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kSb = 5.67 * 1e-8;
+
+MC_HD double dmin(double a, double b) { return a < b ? a : b; }
+MC_HD double dmax(double a, double b) { return a > b ? a : b; }
+MC_HD double sq(double x) { return x * x; }
+MC_HD double pow4(double x) { double x2 = x * x; return x2 * x2; }
+MC_HD double qroot(double x) { return sqrt(sqrt(x)); }           // x^0.25
+MC_HD double pow175(double x) { double r = sqrt(x); return x * r * sqrt(r); }   // x^1.75
+
+// ---- thermodynamics ---------------------------------------------------------------------------
+MC_HD double phair(double tc, double pk) { return 44.6 * (pk / 101.3) * (273.15 / (tc + 273.15)); }
+MC_HD double cpair(double tc) { return 2e-05 * tc * tc + 0.0002 * tc + 29.119; }
+MC_HD double tetens(double tc) { return 0.6108 * exp(17.27 * tc / (tc + 237.3)); }   // code.R:156,382,410,...
+MC_HD double satvap(double tc) {                                   // ice = TRUE
+  double e0, L;
+  if (tc < 0) { e0 = 610.78 / 1000; L = 2.834e6; } else { e0 = 611.2 / 1000; L = 2.501e6 - 2340 * tc; }
+  return e0 * exp((L / 461.5) * (1 / 273.15 - 1 / (tc + 273.15)));
+}
+MC_HD double dewpoint(double ea, double tc) {
+  double e0, L;
+  if (tc < 0) { e0 = 610.78 / 1000; L = 2.834e6; } else { e0 = 611.2 / 1000; L = 2.501e6 - 2340 * tc; }
+  double it = 1 / 273.15 - (461.5 / L) * log(ea / e0);
+  return 1 / it - 273.15;
+}
+
+// ---- aerodynamics -----------------------------------------------------------------------------
+MC_HD double zeroplanedis(double hgt, double PAI) {                // NMR.R:103-107
+  if (PAI < 0.001) PAI = 0.001;
+  double s = sqrt(7.5 * PAI);
+  return (1 - (1 - exp(-s)) / s) * hgt;
+}
+MC_HD double roughlength_d(double hgt, double PAI, double d, double zm0) {   // NMR.R:109-113 (+ floor)
+  double Be = sqrt(0.003 + (0.2 * PAI) / 2);
+  double zm = (hgt - d) * exp(-0.4 / Be);
+  return zm < zm0 ? zm0 : zm;
+}
+MC_HD double roughlength(double hgt, double PAI, double zm0) { return roughlength_d(hgt, PAI, zeroplanedis(hgt, PAI), zm0); }
+MC_HD double mixinglength(double hgt, double PAI) {
+  double d = zeroplanedis(hgt, PAI);
+  double zm = roughlength_d(hgt, PAI, d, 0.003);
+  return (0.32 * (hgt - d)) / log((hgt - d) / zm);
+}
+// attencoef = attencoef_base * sqrt(phi_m); the base is column- and layer-invariant in time
+MC_HD double attencoef_base(double hgt, double PAI, double cd, double iw, double l_m) {
+  return sqrt((cd * PAI * hgt) / (2 * l_m * iw));
+}
+MC_HD void diabatic_cor(double tc, double pk, double H, double uf, double zi, double d, double& psi_m, double& psi_h) {
+  double Tk = tc + 273.15;
+  double st = -(0.4 * 9.81 * (zi - d) * H) / (phair(tc, pk) * cpair(tc) * Tk * (uf * uf * uf));
+  if (st < 0) { psi_h = -2 * log((1 + sqrt(1 - 16 * st)) / 2); psi_m = 0.6 * psi_h; }
+  else { psi_h = 6 * log(1 + st); psi_m = psi_h; }
+  if (psi_m > 4) psi_m = 4;
+  if (psi_h > 4) psi_h = 4;
+  if (psi_m < -1.5) psi_m = -1.5;
+  if (psi_h < -2.5) psi_h = -2.5;
+}
+// within-canopy conductance given precomputed mixing length and attenuation coefficient `a`
+MC_HD double gcanopy_a(double uh, double z1, double z0, double tc1, double tc0, double hgt, double l_m, double a,
+                       double iw, double phi_m, double pk) {
+  double ph = phair((tc1 + tc0) / 2, pk);
+  double e0 = exp(-a * (z0 / hgt - 1));
+  double e1 = exp(-a * (z1 / hgt - 1));
+  double g = (l_m * iw * ph * uh * a) / (hgt * (e0 - e1) * phi_m);
+  double gfree = 0.0012 * ph * qroot(fabs(tc1 - tc0) / fabs(z1 - z0));
+  return (g > gfree) ? g : gfree;
+}
+MC_HD double gcanopy(double uh, double z1, double z0, double tc1, double tc0, double hgt, double PAI, double cd,
+                     double iw, double phi_m, double pk) {
+  double l_m = mixinglength(hgt, PAI);
+  double a = attencoef_base(hgt, PAI, cd, iw, l_m) * sqrt(phi_m);
+  return gcanopy_a(uh, z1, z0, tc1, tc0, hgt, l_m, a, iw, phi_m, pk);
+}
+MC_HD double gturb(double u, double zu, double z1, double z0, double hgt, double PAI, double tc, double psi_m,
+                   double psi_h, double zm0, double pk) {
+  double d = zeroplanedis(hgt, PAI);
+  double zm = roughlength_d(hgt, PAI, d, zm0);
+  double zh = 0.2 * zm;
+  double ln = log((zu - d) / zm) + psi_m;
+  if (!(ln >= 0.55)) ln = 0.55;
+  double uf = (0.4 * u) / ln;
+  double lo = z0 - d;
+  if (!(lo > zh)) lo = zh;
+  double lnh = log((z1 - d) / lo);
+  double den = lnh + psi_h;
+  if (den < 0.25 * lnh) den = 0.25 * lnh;
+  return (0.4 * phair(tc, pk) * uf) / den;
+}
+MC_HD double gforcedfree(double d, double u, double tc, double dtc, double pk, double dtmin) {
+  double Tk = tc + 273.15;
+  double ph = phair(tc, pk);
+  double sc = pow175(Tk / 273.15) * (101.3 / pk);
+  double Dh = 18.9e-6 * sc;
+  double nu = 13.3e-6 * sc;
+  double adt = fabs(dtc);
+  if (adt < dtmin) adt = dtmin;
+  double Re = (u * d) / nu;
+  double Pr = nu / Dh;
+  double Gr = (9.81 * (d * d * d) * adt) / (Tk * (nu * nu));
+  double gforced = (0.664 * Dh * ph * sqrt(Re) * cbrt(Pr)) / d;
+  double gfree = (0.54 * Dh * ph * qroot(Gr * Pr)) / d;
+  return (gforced > gfree) ? gforced : gfree;
+}
+MC_HD double layercond(double Rsw, double gsmax, double q50) { double Qa = 4.6 * Rsw; return (gsmax * Qa) / (Qa + q50); }
+MC_HD double soilrh(double theta, double b, double Psie, double Smax, double tc) {
+  double matric = -Psie * pow(theta / Smax, -b);
+  return exp((0.018 * matric) / (8.31 * (tc + 273.15)));
+}
+
+// ---- sun / radiation --------------------------------------------------------------------------
+MC_HD double solalt(double lt, double lat, double lon, double jd, double merid, double dst) {
+  double mm = 6.24004077 + 0.01720197 * (jd - 2451545);
+  double eot = -7.659 * sin(mm) + 9.863 * sin(2 * mm + 3.5932);
+  double st = lt + (4 * (lon - merid) + eot) / 60 - dst;
+  double tt = 0.261799 * (st - 12);
+  double declin = (kPi * 23.5 / 180) * cos(2 * kPi * ((jd - 159.5) / 365.25));
+  double latr = lat * kPi / 180;
+  double sh = sin(declin) * sin(latr) + cos(declin) * cos(latr) * cos(tt);
+  return (180 * atan(sh / sqrt(1 - sh * sh))) / kPi;
+}
+MC_HD double difprop(double Rsw, double sa) {
+  if (!(sa > 0) || !(Rsw > 0)) return 1.0;
+  double kt = Rsw / (1352.0 * sin(sa * kPi / 180));
+  if (kt > 1) kt = 1;
+  if (kt <= 0.22) return 1 - 0.09 * kt;
+  if (kt <= 0.8) return 0.9511 - 0.1604 * kt + 4.388 * kt * kt - 16.638 * kt * kt * kt + 12.336 * kt * kt * kt * kt;
+  return 0.165;
+}
+MC_HD double cank_den(double x) { return x + 1.774 * pow(x + 1.182, -0.733); }   // column-invariant
+MC_HD double cank(double x, double sa, double den) {
+  double t = tan((90 - sa) * kPi / 180);
+  return sqrt(x * x + t * t) / den;
+}
+MC_HD double clumptr(double tr, double clump) { return clump + (1 - clump) * tr; }
+// shortwave under plant area l: `s` = sqrt(1 - ref), `trd` = clumped diffuse transmission exp(-s*l),
+// `K` = beam extinction (unused when sa <= 0)
+MC_HD double cansw_k(double globrad, double dp, double sa, double l, double s, double trd, double K, double clump) {
+  double trb = (sa > 0) ? clumptr(exp(-s * K * l), clump) : clumptr(0.0, clump);
+  return globrad * (dp * trd + (1 - dp) * trb);
+}
+MC_HD double psunlit_k(double l, double sa, double K, double clump) {
+  if (!(sa > 0)) return clumptr(0.0, clump);
+  return clumptr(exp(-K * l), clump);
+}
+
+}  // namespace mc

@@ -1,0 +1,449 @@
+// Steady-state path on the device: runmodelS + .runmodelsnow + tleafS + .leafabs2 + .windprofile + .snowtempf
+// (R/NicheMapRcode.R:717-885, 514-677, 432-493, 361-376, 378-404, 495-512), one thread per column looping over a
+// slice of the hours.  There is no time recurrence on this path, so the (column, hour) points are
+// independent; the time axis is split over blockIdx.y when there are too few columns to fill the GPU.
+// Everything that depends only on the column (and the seasonal PAI factor) — displacement/roughness lengths, the
+// log-law ratios, attenuation coefficient, canopy-conductance integrals, diffuse transmissions — is hoisted into
+// `prep()`; the hourly part keeps only the forcing-dependent transcendentals.
+#pragma once
+#include "mc_step.cuh"
+
+namespace mc {
+
+struct SteadyArgs {
+  long long ncol; int m, sm; long long T;
+  const double *vegp, *soilp, *lat, *lon;
+  const double* clim;        // [T][9]  temp, relhum, pres, windspeed, swrad, difrad, skyem, jd, lt
+  const double* nmr;         // [T][11] or [T][11][ncol]: D0cm, WC0cm, SNOWDEP(cm), SN1..SN8
+  int nmr_percol;
+  const double* season;      // [T] or null
+  double reqhgt; int metopen; double windhgt, surfwet;
+  double* out;               // [T][7][ncol] or null
+  double* stats;             // [6][ncol] (written by the reduce kernel)
+  double* part;              // [nchunk][6][ncol] partial sums/min/max, or null
+  int* flags;                // [ncol]; bit 2: snow-layer lookup out of range
+};
+
+template <int MM>
+struct SteadyCol {
+  int m;
+  double hgt, x, lw, cd, refls, refw, refg, vegem, gsmax, q50, clump, iwmean, soilb, psi_e, Smax, lat, lon;
+  double PAIb[MM + 2], pLAIb[MM + 2];
+  // prepared (column + season)
+  double PAIt, LAI, PAIu, d, zm3, zm4, lnuf, lnh3, a, l_m, La, leafdens;
+  double wA, wB, wE;            // .windprofile factors: ln(zi), ln(zo or hgt), exp term
+  double gt_lnu, gt_lnh, gtc_lnh;   // gturb pieces for z1 = hgt+2 and z1 = reqhgt
+  double gc_top_den, gc_c_den, gc_0_den;   // hgt*(e0-e1) of the three gcanopy calls
+  double ref, sref, kden, emv, slw, trd_u, trd_t, trlw_u;
+  double s02, trd02, sls, trdls, cdif;     // PAR (ref 0.2) and Rsw (ref refls) transmissions, cantransdif
+  double merid_def;
+  // snow variants
+  double a1, a2, PAIt_s, pLAI_s, zm3_s, d_s, wA1, wB1, wE1, wB2, leafdens_s, gts_lnu, gts_lnh, gtcs_lnh, gcs_top_den, gcs_c_den,
+      gcs_0_den, l_m_s, trds_u, trds_t, s06, trd06, s95, trd95, cdif95, trlw85_u, sref_s, ref_s;
+
+  MC_HD void load(const SteadyArgs& a, long long c) {
+    m = a.m;
+    auto V = [&](int r) { return a.vegp[(long long)r * a.ncol + c]; };
+    hgt = V(V_HGT); x = V(V_X); lw = V(V_LW); cd = V(V_CD); refls = V(V_REFLS); refg = V(V_REFG); refw = V(V_REFW);
+    vegem = V(V_VEGEM); gsmax = V(V_GSMAX); q50 = V(V_Q50); clump = V(V_CLUMP);
+    double s = 0;
+    for (int i = 1; i <= m; ++i) { PAIb[i] = V(V_NSCAL + i - 1); pLAIb[i] = V(V_NSCAL + m + i - 1); s += V(V_NSCAL + 2 * m + i - 1); }
+    iwmean = s / m;
+    auto S = [&](int r) { return a.soilp[(long long)r * a.ncol + c]; };
+    Smax = S(S_SMAX); soilb = S(S_B); psi_e = S(S_PSIE);
+    lat = a.lat[c]; lon = a.lon[c];
+  }
+  // hgt*(e0-e1) of gcanopy between z0 < z1 for attenuation a (phi_m = 1)
+  MC_HD double gc_den(double z1, double z0, double av) const {
+    return hgt * (exp(-av * (z0 / hgt - 1)) - exp(-av * (z1 / hgt - 1)));
+  }
+  MC_HD void prep(const SteadyArgs& A, double season) {
+    const double reqhgt = A.reqhgt;
+    // vegetation reductions (NMR.R:730-760)
+    double cs = 0, ls = 0, pu = 0;
+    int first = 0, nsel = 0;
+    for (int i = 1; i <= m; ++i) if ((i - 0.5) / m * hgt > reqhgt) { if (!first) first = i; ++nsel; }
+    double ptop = 0;
+    for (int i = 1; i <= m; ++i) {
+      double p = PAIb[i] * season; if (p < 0.0001) p = 0.0001;
+      cs += p; ls += pLAIb[i] * p;
+      if (nsel > 1 && i >= first) pu += p;
+      if (i == m) ptop = p;
+    }
+    PAIt = cs; LAI = ls / m;
+    if (reqhgt < hgt) {
+      if (nsel > 1) PAIu = pu;
+      else { double zu = (m - 0.5) / m * hgt; PAIu = ((hgt - reqhgt) / (hgt - zu)) * ptop; }
+    } else PAIu = 0;
+    La = log(67.8 * (hgt + 2) - 5.42);
+    d = zeroplanedis(hgt, PAIt);
+    zm3 = roughlength_d(hgt, PAIt, d, 0.003);
+    zm4 = roughlength_d(hgt, PAIt, d, 0.004);
+    lnuf = log((2 + hgt - d) / zm3);
+    lnh3 = log((hgt - d) / zm3); if (lnh3 < 0.55) lnh3 = 0.55;
+    l_m = mixinglength(hgt, PAIt);
+    a = attencoef_base(hgt, PAIt, cd, iwmean, l_m) * sqrt(1.0);
+    leafdens = PAIt / hgt;
+    wind_factors(hgt + 2, reqhgt, a, hgt, d, zm4, wA, wB, wE);
+    gturb_factors(hgt + 2, hgt + 2, hgt, d, zm4, gt_lnu, gt_lnh);
+    { double dum; gturb_factors(hgt + 2, reqhgt, hgt, d, zm4, dum, gtc_lnh); }
+    gc_top_den = gc_den(hgt, 0, a);
+    gc_c_den = gc_den(hgt, reqhgt, a);
+    gc_0_den = gc_den(reqhgt, 0, a);
+    // radiation
+    double pl = LAI / PAIt;
+    ref = pl * refls + (1 - pl) * refw;
+    sref = sqrt(1 - ref);
+    kden = cank_den(x);
+    emv = 1 - (1 - vegem);
+    slw = sqrt(emv);
+    trd_u = clumptr(exp(-sref * PAIu), 0.0);            // Q15: clump lands in `merid`; cansw/canlw see clump = 0
+    trd_t = clumptr(exp(-sref * PAIt), 0.0);
+    trlw_u = clumptr(exp(-slw * PAIu), 0.0);
+    s02 = sqrt(1 - 0.2); trd02 = exp(-s02 * PAIu);
+    sls = sqrt(1 - refls); trdls = exp(-sls * PAIu);
+    cdif = exp(-sqrt(1 - refls) * PAIu);
+    merid_def = nearbyint(lon / 15) * 15;
+    // ---- snow-surface variants (.runmodelsnow, NMR.R:514-677) ----
+    PAIt_s = PAIt < 0.001 ? 0.001 : PAIt;
+    pLAI_s = LAI / PAIt_s; if (pLAI_s != pLAI_s) pLAI_s = 0.8;
+    zm3_s = roughlength(hgt, PAIt_s, 0.003);
+    d_s = zeroplanedis(hgt, PAIt_s);
+    l_m_s = mixinglength(hgt, PAIt_s);
+    a1 = attencoef_base(hgt, PAIt_s, cd, iwmean, l_m_s) * sqrt(1.0);
+    { double lm0 = mixinglength(hgt, 0.0); a2 = attencoef_base(hgt, 0.0, cd, iwmean, lm0) * sqrt(1.0); }
+    { double zm4s = roughlength_d(hgt, PAIt_s, d_s, 0.004);
+      wind_factors(hgt + 2, reqhgt, a1, hgt, d_s, zm4s, wA1, wB1, wE1);
+      gturb_factors(hgt + 2, hgt + 2, hgt, d_s, zm4s, gts_lnu, gts_lnh);
+      double dum; gturb_factors(hgt + 2, reqhgt, hgt, d_s, zm4s, dum, gtcs_lnh); }
+    { double l2 = log((reqhgt - 0.0) / 0.004); if (l2 < 0.55) l2 = 0.55; wB2 = l2; }
+    leafdens_s = (PAIt_s / hgt) * 1.2;
+    gcs_top_den = gc_den(hgt, 0, a1); gcs_c_den = gc_den(hgt, reqhgt, a1); gcs_0_den = gc_den(reqhgt, 0, a1);
+    ref_s = pLAI_s * 0.95 + (1 - pLAI_s) * 0.95;
+    sref_s = sqrt(1 - ref_s);
+    trds_u = exp(-sref_s * PAIu); trds_t = exp(-sref_s * PAIt_s);
+    s06 = sqrt(1 - 0.6); trd06 = exp(-s06 * PAIu);
+    s95 = sqrt(1 - 0.95); trd95 = exp(-s95 * PAIu);
+    cdif95 = exp(-sqrt(1 - 0.95) * PAIu);
+    trlw85_u = clumptr(exp(-sqrt(1 - 0.85) * PAIu), clump);
+  }
+  // .windprofile (NMR.R:378-404) split into u-independent factors: uo = ((0.4*ui)/wA / 0.4) * wB [* wE]
+  MC_HD static void wind_factors(double zi, double zo, double av, double h, double dd, double zmm, double& fA, double& fB, double& fE) {
+    double l = log((zi - dd) / zmm); if (l < 0.55) l = 0.55;
+    fA = l;
+    if (zo >= h) { double l2 = log((zo - dd) / zmm); if (l2 < 0.55) l2 = 0.55; fB = l2; fE = -1.0; }
+    else { double l2 = log((h - dd) / zmm); if (l2 < 0.55) l2 = 0.55; fB = l2; fE = exp(av * (zo / h) - 1); }   // Q14
+  }
+  MC_HD static double wind_apply(double ui, double fA, double fB, double fE) {
+    double uf = (0.4 * ui) / fA;
+    double uo = (uf / 0.4) * fB;
+    return fE < 0 ? uo : uo * fE;
+  }
+  MC_HD static void gturb_factors(double zu, double z1, double z0, double dd, double zmm, double& lnu, double& lnh) {
+    double zh = 0.2 * zmm;
+    lnu = log((zu - dd) / zmm);
+    double lo = z0 - dd; if (!(lo > zh)) lo = zh;
+    lnh = log((z1 - dd) / lo);
+  }
+  MC_HD static double gturb_apply(double u, double lnu, double lnh, double ph, double psi_m, double psi_h) {
+    double ln = lnu + psi_m; if (!(ln >= 0.55)) ln = 0.55;
+    double uf = (0.4 * u) / ln;
+    double den = lnh + psi_h; if (den < 0.25 * lnh) den = 0.25 * lnh;
+    return (0.4 * ph * uf) / den;
+  }
+  // gcanopy with tc1 == tc0 (free-convection floor is exactly 0)
+  MC_HD static double gcan_apply(double lmix, double iw, double ph, double uh, double av, double den) {
+    double g = (lmix * iw * ph * uh * av) / (den * 1.0);
+    return (g > 0.0) ? g : 0.0;
+  }
+  // .leafabs2 (NMR.R:361-376) with merid <- clump (Q15), clump = 0
+  MC_HD double leafabs2(double Rsw, double sa, double K, double mul, double tair, double PAIt_, double PAIu_, double refv, double srefv,
+                        double trdu, double trdt, double refgv, double emvv, double trlwu, double skyem, double dp) const {
+    double sunl = psunlit_k(PAIu_, sa, K, 0.0);
+    double aRsw = (1 - refv) * cansw_k(Rsw, dp, sa, PAIu_, srefv, trdu, K, 0.0);
+    double aGround = refgv * cansw_k(Rsw, dp, sa, PAIt_, srefv, trdt, K, 0.0);
+    aGround = (1 - refv) * cansw_k(aGround, dp, sa, PAIt_, srefv, trdt, K, 0.0);
+    aRsw = sunl * mul * aRsw + (1 - sunl) * aRsw + aGround;
+    double lwout = kSb * pow4(tair + 273.15);
+    double lwin = trlwu * skyem * lwout + (1 - trlwu) * emvv * lwout;
+    return aRsw + emvv * lwin;
+  }
+  // tleafS (NMR.R:432-493)
+  MC_HD static void tleafS(double tair, double tground, double relhum, double pk, double theta, double gtt, double gt0, double gha,
+                           double gv, double gL, double Rabs, double vegemv, double soilbv, double Psie, double Smaxv, double surfwet,
+                           double leafd, double& tleaf, double& tn, double& rh) {
+    double cp = cpair(tair);
+    double gs = gtt + gt0;
+    double aL = (gtt * (tair + 273.15) + gt0 * (tground + 273.15)) / gs;
+    double bL = (leafd * gL) / gs;
+    double es = satvap(tair);
+    double eref = (relhum / 100) * es;
+    double esoil = soilrh(theta, soilbv, Psie, Smaxv, tground) * satvap(tground);
+    double tk = tair + 273.15;
+    double Rnet = Rabs - 0.97 * kSb * pow4(tk);
+    double tle = tair + (0.5 * Rnet) / (cp * gha);
+    double wgt1 = leafd < 1 ? leafd / 2 : 1 - 0.5 / leafd;
+    double tapprox = wgt1 * tle + (1 - wgt1) * tair;
+    double delta = 4098 * tetens(tapprox) / sq(tapprox + 237.3);
+    double g3 = gs + gv;
+    double ae = (gtt * eref + gt0 * esoil + gv * es) / g3;
+    double be = (gv * delta) / g3;
+    double bH = gha * cp;
+    double lg = ((-42.575 * tair + 44994) * gv) / pk;
+    double aX = lg * (surfwet * es - ae);
+    double bX = lg * (surfwet * delta - be);
+    if (aX < 0) aX = 0;
+    if (bX < 0) bX = 0;
+    double aR = kSb * vegemv * pow4(aL);
+    double bR = 4 * vegemv * kSb * ((aL * aL * aL) * bL + (tk * tk * tk));
+    double dTL = (Rabs - aR - aX) / (1 + bR + bX + bH);
+    tn = aL - 273.15 + bL * dTL;
+    tleaf = tn + dTL;
+    double eanew = ae + be * dTL;
+    if (eanew < 0.01) eanew = 0.01;
+    double tmin = dewpoint(eanew, tn);
+    double esnew = satvap(tn);
+    if (eanew > esnew) eanew = esnew;
+    rh = (eanew / esnew) * 100;
+    if (tleaf < tmin) tleaf = tmin;
+    if (tn < tmin) tn = tmin;
+    double tmax = (tn + 20 < 80) ? tn + 20 : 80;
+    if (tleaf > tmax) tleaf = tmax;
+    double tmx = dmax(tground + 5, tair + 5);
+    if (tn > tmx) tn = tmx;
+    tmx = dmax(tground + 20, tair + 20);
+    if (tleaf > tmx) tleaf = tmx;
+    if (tn < tair - 7) tn = tair - 7;
+    if (tleaf < tair - 20) tleaf = tair - 20;
+  }
+  MC_HD double wind2m(const SteadyArgs& A, double u, double PAIv) const {
+    double u2;
+    if (A.metopen) {
+      if (A.windhgt != 2) u = u * 4.87 / log(67.8 * A.windhgt - 5.42);
+      u2 = u * La / log(67.8 * 2 - 5.42);
+    } else {
+      u2 = u;
+      if (A.windhgt != (2 + hgt)) u2 = Column<3, 2>::windprofile(u, A.windhgt, hgt + 2, 2, PAIv, hgt, 0, 0.05 * hgt, 0.004);
+    }
+    if (u2 < 0.5) u2 = 0.5;
+    return u2;
+  }
+
+  // one hour without snow (runmodelS body, NMR.R:761-865); o[7] = Tloc, tleaf, RHloc, RSWloc, RLWloc, windspeed, dp
+  MC_HD void point(const SteadyArgs& A, const double* cr, double tground, double theta, double* o) const {
+    const double reqhgt = A.reqhgt;
+    const double tair = cr[0], relhum = cr[1], pk = cr[2], swrad = cr[4], skyem = cr[6];
+    const double u2 = wind2m(A, cr[3], PAIt);
+    const double uf = (0.4 * u2) / lnuf;
+    const double tk = tair + 273.15;
+    double Rlw = (1 - skyem) * kSb * vegem * pow4(tk);
+    const double Hh = 0.2 * ((1 - 0.23) * swrad - Rlw);
+    double psi_m, psi_h;
+    diabatic_cor(tair, pk, Hh, uf, hgt + 2, d, psi_m, psi_h);
+    if (psi_m > 2.5) psi_m = 2.5;
+    if (psi_h > 2.5) psi_h = 2.5;
+    if (psi_m < -2.5) psi_m = -2.5;
+    if (psi_h < -2.5) psi_h = -2.5;
+    const double uz = wind_apply(u2, wA, wB, wE);
+    const double uh = (uf / 0.4) * lnh3;
+    double dp = cr[5] / swrad;
+    if (dp != dp) dp = 0.5;
+    if (isinf(dp)) dp = 0.5;
+    if (dp > 1) dp = 1;
+    const double ph = phair(tair, pk);
+    double gtt = gturb_apply(u2, gt_lnu, gt_lnh, ph, psi_m, psi_h);
+    const double pl = LAI / PAIt;
+    const double sa_l = solalt(cr[8], lat, lon, cr[7], /*merid <- clump (Q15)*/ clump, 0);
+    const double K_l = (sa_l > 0) ? cank(x, sa_l, kden) : 0.0;
+    const double mul = cank(x, sa_l < 5 ? 5.0 : sa_l, kden);
+    const double ph0 = phair(tair, 101.3);
+    double tz, tleaf, rh, Rsw;
+    (void)pl;
+    if (reqhgt >= hgt) {
+      double gt0 = gcan_apply(l_m, iwmean, ph, uh, a, gc_top_den);
+      double gha = 1.41 * gforcedfree(lw * 0.71, uh, tair, 5, pk, 5);
+      double gC = layercond(swrad, gsmax, q50);
+      double gv = 1 / (1 / gC + 1 / gha);
+      double gL = 1 / (1 / gha + 1 / (ph0 * uh));
+      double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt, 0.0, ref, sref, 1.0, trd_t, refg, emv, 1.0, skyem, dp);
+      double tn, rhn;
+      tleafS(tair, tground, relhum, pk, theta, gtt, gt0, gha, gv, gL, Rabs, vegem, soilb, psi_e, Smax, A.surfwet, leafdens, tleaf, tn, rhn);
+      if (reqhgt == hgt) { tz = tn; rh = rhn; }
+      else {
+        double gtc = gturb_apply(u2, gt_lnu, gtc_lnh, ph, psi_m, psi_h);
+        double gt2 = 1 / (1 / gtt - 1 / gtc);
+        double eref = (relhum / 100) * satvap(tair);
+        double ecan = (rhn / 100) * satvap(tn);
+        double ea = (gt2 * eref + gtc * ecan) / (gt2 + gtc);
+        tz = (gt2 * tair + gtc * tn) / (gt2 + gtc);
+        rh = (ea / satvap(tz)) * 100;
+      }
+      if (rh > 100) rh = 100;
+      Rsw = swrad;
+    } else {
+      double gtc = gcan_apply(l_m, iwmean, ph, uh, a, gc_c_den);
+      gtt = 1 / (1 / gtt + 1 / gtc);
+      double gt0 = gcan_apply(l_m, iwmean, ph, uh, a, gc_0_den);
+      double gha = 1.41 * gforcedfree(lw * 0.71, uz, tair, 5, pk, 5);
+      double sa = solalt(cr[8], lat, lon, cr[7], merid_def, 0);
+      double K = (sa > 0) ? cank(x, sa, kden) : 0.0;
+      double PAR = cansw_k(swrad, dp, sa, PAIu, s02, trd02, K, 0.0);
+      double gC = layercond(PAR, gsmax, q50);
+      double gv = 1 / (1 / gC + 1 / gha);
+      double gL = 1 / (1 / gha + 1 / (ph0 * uz));
+      double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt, PAIu, ref, sref, trd_u, trd_t, refg, emv, trlw_u, skyem, dp);
+      tleafS(tair, tground, relhum, pk, theta, gtt, gt0, gha, gv, gL, Rabs, vegem, soilb, psi_e, Smax, A.surfwet, leafdens, tleaf, tz, rh);
+      Rsw = cansw_k(swrad, dp, sa, PAIu, sls, trdls, K, 0.0);
+      double Rdif = cdif * swrad * dp;
+      dp = Rdif / Rsw;
+      if (dp != dp) dp = 1;
+      if (isinf(dp)) dp = 1;
+      if (dp < 0) dp = 0;
+      if (dp > 1) dp = 1;
+      double tr = clumptr(exp(-slw * PAIu), clump);
+      double lwout = kSb * pow4(tk);
+      Rlw = tr * skyem * lwout + (1 - tr) * emv * lwout;
+    }
+    o[0] = tz; o[1] = tleaf; o[2] = rh; o[3] = Rsw; o[4] = Rlw; o[5] = uz; o[6] = dp;
+  }
+
+  // .snowtempf (NMR.R:495-512); false when the SN column lookup is out of range
+  MC_HD static bool snowtempf(double snowdepth, const double* SN, double reqhgt, double& stemp) {
+    const double nd[9] = {3.0, 2.0, 1.0, 0.5, 0.2, 0.1, 0.05, 0.025, 0.0};
+    int selb = 0;
+    for (int i = 1; i <= 9; ++i) if (nd[i - 1] - reqhgt <= 0) { selb = i; break; }
+    int sela = selb - 1;
+    if (sela < 1 || selb > 8) return false;
+    double smm = fabs(reqhgt - nd[sela - 1]) + fabs(reqhgt - nd[selb - 1]);
+    double wgt1 = 1 - fabs(reqhgt - nd[sela - 1]) / smm;
+    double wgt2 = 1 - fabs(reqhgt - nd[selb - 1]) / smm;
+    if (nd[sela - 1] > (snowdepth / 100)) { wgt1 = 0; wgt2 = 1; }
+    stemp = wgt1 * SN[sela - 1] + wgt2 * SN[selb - 1];
+    if (snowdepth < reqhgt) stemp = 0;
+    return true;
+  }
+  // one hour with snow on the ground (.runmodelsnow body, NMR.R:514-677)
+  MC_HD bool point_snow(const SteadyArgs& A, const double* cr, double snowdep_cm, const double* SN, double* o) const {
+    const double reqhgt = A.reqhgt;
+    const double snowtemp = SN[0];
+    const double snowdep = snowdep_cm / 100;
+    const double tair = cr[0], relhum = cr[1], pk = cr[2], swrad = cr[4], skyem = cr[6];
+    const double u2 = wind2m(A, cr[3], PAIt_s);
+    const bool above = hgt > snowdep;
+    const double zm = above ? zm3_s : 0.003;
+    const double dd = above ? d_s : snowdep - 0.003;
+    double hgt2 = above ? hgt : snowdep;
+    double uz;
+    if (above) uz = wind_apply(u2, wA1, wB1, wE1);
+    else {
+      double l = log((snowdep + 2 - 0.0) / 0.004); if (l < 0.55) l = 0.55;
+      uz = wind_apply(u2, l, wB2, -1.0);
+    }
+    double uf = (0.4 * u2) / log((hgt2 + 2 - dd) / zm);
+    if (uf < 0.065) uf = 0.065;
+    hgt2 = hgt < snowdep ? snowdep : hgt;
+    double uh = (uf / 0.4) * log((hgt2 - dd) / zm);
+    if (uh < uf) uh = uf;
+    const bool below = reqhgt < snowdep;
+    double tz2 = 0;
+    if (below && !snowtempf(snowdep, SN, reqhgt, tz2)) return false;
+    double dp = cr[5] / swrad;
+    if (dp != dp) dp = 0.5;
+    if (isinf(dp)) dp = 0.5;
+    if (dp > 1) dp = 1;
+    const double ph = phair(tair, pk), ph0 = phair(tair, 101.3);
+    double gtt = gturb_apply(u2, gts_lnu, gts_lnh, ph, 0, 0);
+    const double sa_l = solalt(cr[8], lat, lon, cr[7], clump, 0);
+    const double K_l = (sa_l > 0) ? cank(x, sa_l, kden) : 0.0;
+    const double mul = cank(x, sa_l < 5 ? 5.0 : sa_l, kden);
+    const double emv85 = 1 - (1 - 0.85);
+    const double tk = tair + 273.15;
+    double tz, tleaf, rh, Rsw, Rlw;
+    if (reqhgt >= hgt) {
+      double gt0 = gcan_apply(l_m_s, iwmean, ph, uh, a1, gcs_top_den);
+      double gha = 1.41 * gforcedfree(lw * 2 * 0.71, uh, tair, 5, pk, 5);
+      double gC = layercond(swrad, gsmax, q50);
+      double gv = 1 / (1 / gC + 1 / gha);
+      double gL = 1 / (1 / gha + 1 / (ph0 * uh));
+      double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt_s, 0.0, ref_s, sref_s, 1.0, trds_t, 0.95, emv85, 1.0, skyem, dp);
+      double tn, rhn;
+      tleafS(tair, snowtemp, relhum, pk, 0.5, gtt, gt0, gha, gv, gL, Rabs, 0.85, soilb, psi_e, Smax, 1, leafdens_s, tleaf, tn, rhn);
+      if (reqhgt == hgt) { tz = tn; rh = rhn; }
+      else {
+        double gtc = gturb_apply(u2, gts_lnu, gtcs_lnh, ph, 0, 0);
+        double gt2 = 1 / (1 / gtt - 1 / gtc);
+        double eref = (relhum / 100) * satvap(tair);
+        double ecan = (rhn / 100) * satvap(tn);
+        double ea = (gt2 * eref + gtc * ecan) / (gt2 + gtc);
+        tz = (gt2 * tair + gtc * tn) / (gt2 + gtc);
+        rh = (ea / satvap(tz)) * 100;
+      }
+      if (rh > 100) rh = 100;
+      Rsw = swrad;
+      Rlw = (1 - skyem) * 0.85 * kSb * pow4(tz + 273.15);
+    } else {
+      double gtc = gcan_apply(l_m_s, iwmean, ph, uh, a1, gcs_c_den);
+      gtt = 1 / (1 / gtt + 1 / gtc);
+      double gt0 = gcan_apply(l_m_s, iwmean, ph, uh, a1, gcs_0_den);
+      double gha = 1.41 * gforcedfree(lw * 0.71 * 2, uz, tair, 5, pk, 5);
+      double sa = solalt(cr[8], lat, lon, cr[7], merid_def, 0);
+      double K = (sa > 0) ? cank(x, sa, kden) : 0.0;
+      double PAR = cansw_k(swrad, dp, sa, PAIu, s06, trd06, K, 0.0);
+      double gC = layercond(PAR, gsmax, q50);
+      double gv = 1 / (1 / gC + 1 / gha);
+      double gL = 1 / (1 / gha + 1 / (ph0 * uz));
+      double trlw = clumptr(exp(-sqrt(emv85) * PAIu), 0.0);
+      double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt_s, PAIu, ref_s, sref_s, trds_u, trds_t, 0.95, emv85, trlw, skyem, dp);
+      tleafS(tair, snowtemp, relhum, pk, 0.5, gtt, gt0, gha, gv, gL, Rabs, vegem, soilb, psi_e, Smax, 1, leafdens_s, tleaf, tz, rh);
+      Rsw = cansw_k(swrad, dp, sa, PAIu, s95, trd95, K, 0.0);
+      double Rdif = cdif95 * swrad * dp;
+      dp = Rdif / Rsw;
+      if (dp != dp) dp = 1;
+      if (isinf(dp)) dp = 1;
+      if (dp < 0) dp = 0;
+      if (dp > 1) dp = 1;
+      double lwout = kSb * pow4(tk);
+      Rlw = trlw85_u * skyem * lwout + (1 - trlw85_u) * (1 - 0.85) * lwout;     // canlw(tair, PAIu, 0.85, ...): 0.85 passed as `ref`
+    }
+    if (below) { tz = tz2; tleaf = tz2; rh = 100; uz = 0; Rsw = 0; Rlw = kSb * 0.85 * pow4(tz2 + 273.15); }
+    o[0] = tz; o[1] = tleaf; o[2] = rh; o[3] = Rsw; o[4] = Rlw; o[5] = uz; o[6] = dp;
+    return true;
+  }
+};
+
+template <int MM>
+MC_HD void steady_column(const SteadyArgs& A, long long c, int chunk, int nchunk) {
+  SteadyCol<MM> col;
+  col.load(A, c);
+  if (!A.season) col.prep(A, 1.0);
+  const long long per = (A.T + nchunk - 1) / nchunk;
+  const long long tb = (long long)chunk * per;
+  const long long te = (tb + per < A.T) ? tb + per : A.T;
+  double st[6] = {0, 1e300, -1e300, 0, 1e300, -1e300};
+  int flag = 0;
+  for (long long t = tb; t < te; ++t) {
+    if (A.season) col.prep(A, A.season[t]);
+    const double* cr = A.clim + t * 9;
+    double nm[11];
+    if (A.nmr_percol) { for (int q = 0; q < 11; ++q) nm[q] = A.nmr[(t * 11 + q) * A.ncol + c]; }
+    else { for (int q = 0; q < 11; ++q) nm[q] = A.nmr[t * 11 + q]; }
+    double o[7];
+    if (nm[2] > 0) {                                             // NMR.R:873-883: snow rows come from .runmodelsnow
+      if (!col.point_snow(A, cr, nm[2], nm + 3, o)) { flag |= 4; for (int q = 0; q < 7; ++q) o[q] = NAN; }
+    } else col.point(A, cr, nm[0], nm[1], o);
+    if (A.out) for (int q = 0; q < 7; ++q) A.out[(t * 7 + q) * A.ncol + c] = o[q];
+    st[0] += o[0]; if (o[0] < st[1]) st[1] = o[0]; if (o[0] > st[2]) st[2] = o[0];
+    st[3] += o[1]; if (o[1] < st[4]) st[4] = o[1]; if (o[1] > st[5]) st[5] = o[1];
+  }
+  if (A.part) {
+    double* p = A.part + (long long)chunk * 6 * A.ncol;
+    for (int q = 0; q < 6; ++q) p[q * A.ncol + c] = st[q];
+  }
+#if defined(__CUDA_ARCH__)
+  if (flag && A.flags) atomicOr(&A.flags[c], flag);
+#else
+  if (flag && A.flags) A.flags[c] |= flag;
+#endif
+}
+
+}  // namespace mc

@@ -147,7 +147,7 @@ inline double gcanopy(double uh, double z1, double z0, double tc1, double tc0, d
   double e0 = std::exp(-a * (z0 / hgt - 1));
   double e1 = std::exp(-a * (z1 / hgt - 1));
   double g = (l_m * iw * ph * uh * a) / (hgt * (e0 - e1) * phi_m);
-  double gfree = 0.0012 * ph * std::pow(std::fabs(tc1 - tc0) / (z1 - z0), 0.25);
+  double gfree = 0.0012 * ph * std::pow(std::fabs(tc1 - tc0) / std::fabs(z1 - z0), 0.25);
   return (g > gfree) ? g : gfree;   // pmax; a NaN forced term falls through to gfree
 }
 // [R]+[V vig.md:491-517] leaf boundary-layer conductance, forced vs free (pmax).

@@ -1,0 +1,59 @@
+// TEST-ONLY host build of the device column code (microclimc_b200/csrc/mc_step.cuh, mc_driver.cuh).
+// Lets the CPU-only test suite check the product's fused step logic against the oracle without a GPU.
+// It is NOT part of the product library, is never loaded by microclimc_b200/, and is not a CPU fallback.
+#include <cmath>
+#include <cstdint>
+#include "../../microclimc_b200/csrc/mc_driver.cuh"
+#include "../../microclimc_b200/csrc/mc_steady.cuh"
+
+using namespace mc;
+static RunCfg mkcfg(const double* c) {
+  RunCfg r; r.timestep = c[0]; r.edgedist = c[1]; r.reqhgt = c[2]; r.zu = c[3]; r.merid = c[4]; r.dst = c[5]; r.n = c[6];
+  r.metopen = c[7] != 0; r.windhgt = c[8]; r.zlafact = c[9]; r.surfwet = c[10];
+  return r;
+}
+extern "C" int dbg_run_transient(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* forcing,
+                      const double* fscale, const double* foffset, const double* tsoil_in, const double* lat,
+                      const double* lon, const double* cfg, const double* pai_season, double* state, double* series,
+                      const int64_t* samp_idx, int64_t nsamp, double* stats, double* fullseries, int32_t* flags, int) {
+  TransientArgs a{};
+  a.ncol = ncol; a.m = m; a.sm = sm; a.T = T; a.t0 = 0; a.t1 = T; a.vegp = vegp; a.soilp = soilp; a.lat = lat; a.lon = lon;
+  a.forcing = forcing; a.fscale = fscale; a.foffset = foffset; a.tsoil = tsoil_in; a.season = pai_season; a.state = state;
+  a.series = series; a.full = fullseries; a.nsamp = nsamp; a.stats = stats; a.flags = flags; a.cfg = mkcfg(cfg);
+  a.spin_steps = (int)cfg[11]; a.charmode = (int)cfg[12];
+  long long* samp_of = new long long[ncol];
+  for (int64_t c = 0; c < ncol; ++c) samp_of[c] = -1;
+  for (int64_t j = 0; j < nsamp; ++j) samp_of[samp_idx[j]] = j;
+  a.samp_of = samp_of;
+  for (int64_t c = 0; c < ncol; ++c) {
+    if (m <= 20 && sm <= 10) run_column<20, 10>(a, c); else run_column<64, 32>(a, c);
+  }
+  delete[] samp_of;
+  return 0;
+}
+extern "C" int dbg_runonestep(int64_t ncol, int m, int sm, const double* vegp, const double* soilp, const double* climvars,
+                   const double* lat, const double* lon, const double* cfg, double jd, double lt, const double* theta,
+                   const double* thetap, double* state, int* nmerged) {
+  OneStepArgs a{}; a.ncol = ncol; a.m = m; a.sm = sm; a.vegp = vegp; a.soilp = soilp; a.lat = lat; a.lon = lon; a.climvars = climvars;
+  a.theta = theta; a.thetap = thetap; a.jd = jd; a.lt = lt; a.state = state; a.nmerged = nmerged; a.cfg = mkcfg(cfg);
+  for (int64_t c = 0; c < ncol; ++c) { if (m <= 20 && sm <= 10) onestep_column<20, 10>(a, c); else onestep_column<64, 32>(a, c); }
+  return 0;
+}
+
+extern "C" int dbg_run_steady(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* clim,
+                   const double* nmr, int nmr_percol, const double* lat, const double* lon, const double* scfg,
+                   const double* pai_season, double* out, double* stats, int) {
+  SteadyArgs a{}; a.ncol = ncol; a.m = m; a.sm = sm; a.T = T; a.vegp = vegp; a.soilp = soilp; a.lat = lat; a.lon = lon; a.clim = clim;
+  a.nmr = nmr; a.nmr_percol = nmr_percol; a.season = pai_season; a.reqhgt = scfg[0]; a.metopen = scfg[1] != 0; a.windhgt = scfg[2];
+  a.surfwet = scfg[3]; a.out = out;
+  int* flags = new int[ncol](); a.flags = flags;
+  double* part = new double[6 * ncol]; a.part = part;
+  int rc = 0;
+  for (int64_t c = 0; c < ncol; ++c) {
+    if (m <= 20) steady_column<20>(a, c, 0, 1); else steady_column<64>(a, c, 0, 1);
+    if (flags[c] & 4) rc = -2;
+    if (stats) { for (int q = 0; q < 6; ++q) stats[q * ncol + c] = part[q * ncol + c]; stats[0 * ncol + c] /= (double)T; stats[3 * ncol + c] /= (double)T; }
+  }
+  delete[] flags; delete[] part;
+  return rc;
+}

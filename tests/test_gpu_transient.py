@@ -1,0 +1,123 @@
+"""GPU parity proper: the CUDA path, called through the C-ABI (ctypes), against the CPU oracle on the same
+seeded inputs.  Tolerances are the north_star's: 1e-6 K on temperatures, 1e-8 relative on vapour / fluxes."""
+import numpy as np
+import pytest
+
+from tests.common import M, SM, make_cfg, transient_inputs, assert_state_close, assert_series_close, loam
+from microclimc_b200 import layout as L, synth as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(inp, cfg, n_gpus=1):
+    from microclimc_b200._lib import Context
+    ctx = Context(M, SM, n_gpus)
+    ctx.set_columns(inp["veg"], inp["soil"], inp["lat"], inp["lon"])
+    ctx.set_forcing(inp["f"], inp["fs"], inp["fo"])
+    ctx.set_config(cfg)
+    return ctx
+
+
+def test_paraminit_matches_oracle(oracle):
+    from microclimc_b200._lib import Context
+    ctx = Context(M, SM)
+    inp = transient_inputs(oracle, ncol=5, T=4)
+    ctx.set_columns(inp["veg"], inp["soil"], inp["lat"], inp["lon"])
+    args = np.array([[10, 15, 2, 80, 11, 500]] * 5, dtype=float).T.copy()
+    args[0] = [10, 12, 15, 3, 0.5]
+    ctx.paraminit(args)
+    got = ctx.get_state()
+    for c in range(5):
+        want = oracle.paraminit(M, SM, *args[:, c])[:, 0]
+        np.testing.assert_allclose(got[:, c], want, rtol=1e-14, atol=1e-14)
+
+
+@pytest.mark.parametrize("timestep,reqhgt", [(3600.0, np.nan), (60.0, np.nan), (600.0, 5.0), (3600.0, 0.5)])
+def test_single_step_parity_from_identical_state(oracle, timestep, reqhgt):
+    inp = transient_inputs(oracle, ncol=64, T=8)
+    cfg = make_cfg(timestep=timestep, reqhgt=reqhgt, spin_steps=0)
+    # identical start: oracle spin-up state
+    cfg_spin = make_cfg(timestep=timestep, reqhgt=reqhgt, spin_steps=20)
+    r0 = oracle.run_transient(inp["veg"], inp["soil"], inp["f"][:1], inp["lat"], inp["lon"], cfg_spin, M, SM,
+                              fscale=inp["fs"], foffset=inp["fo"])
+    st0 = r0["state"]
+    ncol = st0.shape[1]
+    rng = np.random.default_rng(5)
+    clim = np.stack([rng.uniform(-5, 25, ncol), rng.uniform(40, 100, ncol), rng.uniform(98, 103, ncol), rng.uniform(0, 12, ncol),
+                     rng.uniform(5, 12, ncol), rng.uniform(0.7, 1.0, ncol), rng.uniform(0, 900, ncol), rng.uniform(0.1, 1.0, ncol)])
+    theta = rng.uniform(0.15, 0.4, ncol); thetap = rng.uniform(0.15, 0.4, ncol)
+    jd, lt = 2449900.0, 13.0
+    want, nm_o = oracle.runonestep(inp["veg"], inp["soil"], clim, inp["lat"], inp["lon"], cfg, jd, lt, theta, thetap, st0, M, SM)
+    ctx = _ctx(inp, cfg)
+    ctx.set_state(st0)
+    nm_g = ctx.run_onestep(clim, jd, lt, theta, thetap)
+    got = ctx.get_state()
+    assert np.array_equal(nm_o, nm_g)
+    assert_state_close(got, want, what="one step dt=%g" % timestep)
+
+
+@pytest.mark.parametrize("timestep", [3600.0, 120.0])
+def test_trajectory_parity_with_spinup(oracle, timestep):
+    inp = transient_inputs(oracle, ncol=48, T=240)
+    cfg = make_cfg(timestep=timestep, spin_steps=200)
+    want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"],
+                                foffset=inp["fo"], want_full=True)
+    ctx = _ctx(inp, cfg)
+    got = ctx.run_transient(samp_idx=np.arange(48), want_full=True)
+    assert_series_close(got["series"], want["series"], "trajectory")
+    assert_state_close(ctx.get_state(), want["state"], what="final state")
+    np.testing.assert_allclose(got["stats"], want["stats"], rtol=0, atol=1e-6)
+    assert np.array_equal(got["flags"] & 1, want["flags"] & 1)
+    # full-state tables ("all"/"allclim" outputs)
+    for t in (0, 100, 239):
+        assert_state_close(got["full"][t], want["full"][t], what="full t=%d" % t)
+
+
+def test_chunked_run_equals_single_run(oracle):
+    inp = transient_inputs(oracle, ncol=32, T=96)
+    cfg = make_cfg(spin_steps=50)
+    ctx = _ctx(inp, cfg)
+    a = ctx.run_transient(samp_idx=np.arange(32))
+    sa = ctx.get_state()
+    ctx2 = _ctx(inp, cfg)
+    b1 = ctx2.run_transient(0, 40, samp_idx=np.arange(32))
+    b2 = ctx2.run_transient(40, 96, samp_idx=np.arange(32))
+    sb = ctx2.get_state()
+    np.testing.assert_array_equal(np.concatenate([b1["series"], b2["series"]]), a["series"])
+    np.testing.assert_array_equal(sa, sb)
+
+
+def test_columns_are_independent_and_order_invariant(oracle):
+    """Size-independent property: permuting the columns permutes the results bit-for-bit."""
+    inp = transient_inputs(oracle, ncol=200, T=48)
+    cfg = make_cfg(spin_steps=30)
+    ctx = _ctx(inp, cfg)
+    a = ctx.run_transient(want_series=False)
+    sa = ctx.get_state()
+    perm = np.random.default_rng(0).permutation(200)
+    inp2 = dict(inp, veg=inp["veg"][:, perm].copy(), soil=inp["soil"][:, perm].copy(), fs=inp["fs"][:, perm].copy(),
+                fo=inp["fo"][:, perm].copy())
+    ctx2 = _ctx(inp2, cfg)
+    b = ctx2.run_transient(want_series=False)
+    np.testing.assert_array_equal(ctx2.get_state(), sa[:, perm])
+    np.testing.assert_array_equal(b["stats"], a["stats"][:, perm])
+
+
+def test_too_few_layers_is_an_error():
+    from microclimc_b200._lib import Context
+    with pytest.raises(ValueError, match="three canopy layers"):
+        Context(2, 10)
+
+
+def test_seasonal_pai_and_full_year_single_column(oracle):
+    inp = transient_inputs(oracle, ncol=4, T=8760, perturb=False)
+    season = 0.6 + 0.4 * np.sin(np.pi * np.arange(8760) / 8760.0) ** 2
+    cfg = make_cfg(spin_steps=200)
+    want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, pai_season=season)
+    from microclimc_b200._lib import Context
+    ctx = Context(M, SM)
+    ctx.set_columns(inp["veg"], inp["soil"], inp["lat"], inp["lon"])
+    ctx.set_forcing(inp["f"], pai_season=season)
+    ctx.set_config(cfg)
+    got = ctx.run_transient(samp_idx=np.arange(4))
+    assert_series_close(got["series"], want["series"], "seasonal year")
