@@ -76,10 +76,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu_index, self.rows, self._stop = gpu_index, [], threading.Event()
+        self.gpu_index, self.rows, self._halt = gpu_index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -87,10 +87,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set(); self.join(timeout=6)
+        self._halt.set(); self.join(timeout=6)
         sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
         reasons = set()
