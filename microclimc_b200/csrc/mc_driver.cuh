@@ -35,6 +35,7 @@ struct TransientArgs {
   RunCfg cfg;
   int spin_steps;            // > 0: paraminit + spinup before the loop (state input ignored)
   int charmode;              // reqhgt "all"/"allclim"
+  int spin_standalone;       // spin-up called as spinup() itself: keeps reqhgt, zlafact, surfwet (no Q22 / spinhgt mapping)
 };
 
 MC_HD void forcing_at(const TransientArgs& a, long long t, long long c, double* f) {
@@ -78,7 +79,8 @@ MC_HD void run_column(const TransientArgs& a, long long c) {
   RunCfg cl = a.cfg;
   cl.reqhgt = a.charmode ? spinhgt : reqhgt;                                                              // reqhgt2, code.R:1199
   if (a.spin_steps > 0) {
-    RunCfg cs = a.cfg; cs.reqhgt = spinhgt; cs.zlafact = 1; cs.surfwet = 1;                               // Q22
+    RunCfg cs = a.cfg;
+    if (!a.spin_standalone) { cs.reqhgt = spinhgt; cs.zlafact = 1; cs.surfwet = 1; }                     // Q22
     col.precompute(cs, a.season ? a.season[0] : 1.0);
     col.paraminit(col.hgt, f0[F_TAIR], f0[F_U], f0[F_RELHUM], tmean, f0[F_RSW]);
     col.precompute_leafgeom(cs);

@@ -375,7 +375,7 @@ int mc_run_onestep(mc_ctx* ctx, const double* climvars, double jd, double lt, co
   return rc;
 }
 
-static int run_transient_impl(mc_ctx* ctx, int64_t t0, int64_t t1, int spin_steps, const double* tsoil, const int64_t* samp_idx,
+static int run_transient_impl(mc_ctx* ctx, int64_t t0, int64_t t1, int spin_steps, int standalone, const double* tsoil, const int64_t* samp_idx,
                               int64_t nsamp, double* series, double* fullseries, double* stats, int32_t* flags) {
   if (!ctx || ctx->ncol <= 0 || ctx->T <= 0) return fail(ctx, MC_ERR_ARG, "mc_run_transient: set columns and forcing first");
   if (!ctx->has_cfg) return fail(ctx, MC_ERR_ARG, "mc_run_transient: mc_set_config first");
@@ -410,7 +410,7 @@ static int run_transient_impl(mc_ctx* ctx, int64_t t0, int64_t t1, int spin_step
     a.forcing = s.forcing.as<double>();
     a.fscale = s.has_pert ? s.fscale.as<double>() : nullptr; a.foffset = s.has_pert ? s.foffset.as<double>() : nullptr;
     a.season = s.has_season ? s.season.as<double>() : nullptr;
-    a.state = s.state.as<double>(); a.cfg = cfg; a.spin_steps = spin_steps; a.charmode = charmode;
+    a.state = s.state.as<double>(); a.cfg = cfg; a.spin_steps = spin_steps; a.charmode = charmode; a.spin_standalone = standalone;
     if (tsoil) {
       CU(s.tsoil.need(sizeof(double) * s.nc));
       CU(h2d_rows(s.tsoil.as<double>(), tsoil, 1, ncol, s.c0, s.nc, s.st));
@@ -458,11 +458,11 @@ int mc_run_transient(mc_ctx* ctx, int64_t t0, int64_t t1, const double* tsoil, c
                      double* series, double* fullseries, double* stats, int32_t* flags) {
   if (!ctx) return MC_ERR_ARG;
   int spin = (t0 == 0) ? (int)ctx->cfg[MC_C_SPINSTEPS] : 0;
-  return run_transient_impl(ctx, t0, t1, spin, tsoil, samp_idx, nsamp, series, fullseries, stats, flags);
+  return run_transient_impl(ctx, t0, t1, spin, 0, tsoil, samp_idx, nsamp, series, fullseries, stats, flags);
 }
 int mc_spinup(mc_ctx* ctx, int steps) {
   if (!ctx || steps <= 0) return fail(ctx, MC_ERR_ARG, "mc_spinup: steps must be positive");
-  return run_transient_impl(ctx, 0, 0, steps, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+  return run_transient_impl(ctx, 0, 0, steps, 1, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
 }
 
 int mc_run_steady(mc_ctx* ctx, int64_t T, const double* clim, const double* nmr, int nmr_percol, const double* scfg,

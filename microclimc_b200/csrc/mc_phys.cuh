@@ -19,6 +19,64 @@ namespace mc {
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kSb = 5.67 * 1e-8;
 
+// ---- fast FP64 primitives ------------------------------------------------------------------------
+// Division and exp dominate the instruction stream of this path (profiles/README.md r01a: 1 445 IEEE divisions
+// per column-step at ~20 instructions each, plus ~350 exp calls whose polynomial constants are rebuilt with
+// move pairs).  On the device:
+//  * frcp/fdiv: MUFU.RCP64H seed (rcp.approx.ftz.f64) + 2 Newton steps + one residual correction, branch-free,
+//    <= 1 ulp from the correctly rounded quotient for normal, finite, non-zero operands. Sites whose operands can
+//    legitimately be 0 / Inf (stomatal conductance at night) keep the IEEE `/`.
+//  * fexp: Cody-Waite reduction + degree-13 polynomial with the coefficients in constant memory (DFMA takes them
+//    as constant-bank operands), exponent insertion by integer add; relative error < 2 ulp, flushes below -708.
+// The host build (tests) maps them to the libm / IEEE operations.
+#if defined(__CUDACC__)
+__constant__ double c_exp_poly[14] = {1.0, 1.0, 0.5, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.3333333333333332e-03,
+                                      1.3888888888888889e-03, 1.9841269841269841e-04, 2.4801587301587302e-05,
+                                      2.7557319223985893e-06, 2.7557319223985888e-07, 2.5052108385441720e-08,
+                                      2.0876756987868100e-09, 1.6059043836821613e-10};
+#endif
+MC_HD double frcp(double b) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+#else
+  return 1.0 / b;
+#endif
+}
+MC_HD double fdiv(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  double r = frcp(b);
+  double q = a * r;
+  return fma(fma(-q, b, a), r, q);
+#else
+  return a / b;
+#endif
+}
+MC_HD double fexp(double x) {
+#if defined(__CUDA_ARCH__)
+  double t = fma(x, 1.4426950408889634, 6755399441055744.0);          // round-to-nearest integer in the low word
+  int k = __double2loint(t);
+  double kd = t - 6755399441055744.0;
+  double r = fma(kd, -6.93147180369123816490e-01, x);
+  r = fma(kd, -1.90821492927058770002e-10, r);
+  double p = c_exp_poly[13];
+#pragma unroll
+  for (int j = 12; j >= 0; --j) p = fma(p, r, c_exp_poly[j]);
+  double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  if (x < -708.0) res = 0.0;
+  if (x > 709.0) res = __longlong_as_double(0x7ff0000000000000LL);
+  if (x != x) res = x;
+  return res;
+#else
+  return exp(x);
+#endif
+}
+
 MC_HD double dmin(double a, double b) { return a < b ? a : b; }
 MC_HD double dmax(double a, double b) { return a > b ? a : b; }
 MC_HD double sq(double x) { return x * x; }
@@ -29,17 +87,18 @@ MC_HD double pow175(double x) { double r = sqrt(x); return x * r * sqrt(r); }   
 // ---- thermodynamics ---------------------------------------------------------------------------
 MC_HD double phair(double tc, double pk) { return 44.6 * (pk / 101.3) * (273.15 / (tc + 273.15)); }
 MC_HD double cpair(double tc) { return 2e-05 * tc * tc + 0.0002 * tc + 29.119; }
-MC_HD double tetens(double tc) { return 0.6108 * exp(17.27 * tc / (tc + 237.3)); }   // code.R:156,382,410,...
+MC_HD double tetens(double tc) { return 0.6108 * fexp(fdiv(17.27 * tc, tc + 237.3)); }   // code.R:156,382,410,...
+MC_HD double phair_c(double c, double tc) { return c * fdiv(273.15, tc + 273.15); }     // c = 44.6 * (pk / 101.3)
 MC_HD double satvap(double tc) {                                   // ice = TRUE
   double e0, L;
   if (tc < 0) { e0 = 610.78 / 1000; L = 2.834e6; } else { e0 = 611.2 / 1000; L = 2.501e6 - 2340 * tc; }
-  return e0 * exp((L / 461.5) * (1 / 273.15 - 1 / (tc + 273.15)));
+  return e0 * fexp((L * (1 / 461.5)) * (1 / 273.15 - frcp(tc + 273.15)));
 }
 MC_HD double dewpoint(double ea, double tc) {
   double e0, L;
   if (tc < 0) { e0 = 610.78 / 1000; L = 2.834e6; } else { e0 = 611.2 / 1000; L = 2.501e6 - 2340 * tc; }
-  double it = 1 / 273.15 - (461.5 / L) * log(ea / e0);
-  return 1 / it - 273.15;
+  double it = 1 / 273.15 - fdiv(461.5, L) * log(fdiv(ea, e0));
+  return frcp(it) - 273.15;
 }
 
 // ---- aerodynamics -----------------------------------------------------------------------------
