@@ -168,6 +168,9 @@ double orc_gforcedfree(double d, double u, double tc, double dtc, double pk, dou
 double orc_windprofile(double ui, double zi, double zo, double a, double PAI, double hgt, double psi_m, double hgtg, double zm0) {
   return windprofile(ui, zi, zo, a, PAI, hgt, psi_m, hgtg, zm0);
 }
+double orc_windprofile2(double ui, double zi, double zo, double a, double hgt, double PAI, double psi_m) {   // .windprofile, NMR.R:378-404
+  return windprofile2(ui, zi, zo, a, hgt, PAI, psi_m);
+}
 double orc_windcanopy(double uh, double z, double hgt, double PAI, double cd, double iw, double phi_m, double edgedist, double uref, double zref) {
   return windcanopy(uh, z, hgt, PAI, cd, iw, phi_m, edgedist, uref, zref);
 }

@@ -33,7 +33,7 @@ def lib():
         sig("orc_attencoef", D, [D] * 5); sig("orc_solalt", D, [D] * 6); sig("orc_jday", D, [C.c_int] * 3)
         sig("orc_gcanopy", D, [D] * 11); sig("orc_gturb", D, [D] * 11); sig("orc_gforcedfree", D, [D] * 6)
         sig("orc_windprofile", D, [D] * 9); sig("orc_windcanopy", D, [D] * 10); sig("orc_abovecanopytemp", D, [D] * 10)
-        sig("orc_leafem", D, [D, D])
+        sig("orc_leafem", D, [D, D]); sig("orc_windprofile2", D, [D] * 7)
         sig("orc_thomas", None, [C.c_int, PD, D, D, PD, PD, C.c_int, D, PD, C.c_int, PD])
         sig("orc_paraminit", None, [C.c_int, C.c_int, D, D, D, D, D, D, PD])
         sig("orc_soilinit_z", None, [C.c_int, D, D, PD])

@@ -37,6 +37,8 @@ def assert_state_close(a, b, m=M, sm=SM, what=""):
     """a, b: [NSTATE][ncol]. Temperatures to TOL_T absolute, everything else to TOL_REL relative (+ tiny abs floor)."""
     rows = L.state_rows(m, sm)
     temp_keys = ["tabove", "tair", "tsoil", "tc", "tleaf", "soiltc"]
+    # flux densities are differences of O(100 W m-2) terms (H = Rnet - G - L): relative to max(|ref|, 1 W m-2)
+    flux_keys = ["H", "G", "L", "Rabs", "Rswin", "Rlwin"]
     for k, sl in rows.items():
         x, y = a[sl], b[sl]
         assert np.array_equal(np.isnan(x), np.isnan(y)), "%s NaN pattern differs in %s" % (what, k)
@@ -45,7 +47,8 @@ def assert_state_close(a, b, m=M, sm=SM, what=""):
             err = np.max(np.abs(x - y)) if x.size else 0
             assert err <= TOL_T, "%s %s abs err %g" % (what, k, err)
         else:
-            err = np.max(np.abs(x - y) / (np.abs(y) + 1e-6)) if x.size else 0
+            floor = 1.0 if k in flux_keys else 1e-6
+            err = np.max(np.abs(x - y) / np.maximum(np.abs(y), floor)) if x.size else 0
             assert err <= TOL_REL, "%s %s rel err %g" % (what, k, err)
 
 
@@ -57,5 +60,6 @@ def assert_series_close(a, b, what=""):
         err = np.max(np.abs(a[:, k] - b[:, k]))
         assert err <= TOL_T, "%s series %s abs err %g" % (what, L.SERIES[k], err)
     for k in range(2, 8):
-        err = np.max(np.abs(a[:, k] - b[:, k]) / (np.abs(b[:, k]) + 1e-3))
-        assert err <= TOL_REL * 10, "%s series %s rel err %g" % (what, L.SERIES[k], err)
+        floor = 1e-3 if k == 2 else 1.0              # relhum (%) ; flux densities relative to max(|ref|, 1 W m-2)
+        err = np.max(np.abs(a[:, k] - b[:, k]) / np.maximum(np.abs(b[:, k]), floor))
+        assert err <= TOL_REL, "%s series %s rel err %g" % (what, L.SERIES[k], err)

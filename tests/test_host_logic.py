@@ -1,0 +1,183 @@
+"""CPU-only checks of the product's fused column code.
+
+tests/hostdbg/dbg_host.cpp compiles the DEVICE headers (mc_step.cuh, mc_driver.cuh, mc_steady.cuh) for the host
+with g++ (test-only build, never shipped or loaded by the package) so that the logic of the fused step — hoisted
+geometry, fused leaftemp loop, two-array Thomas, layer merge / average / interpolation, snow overlay — is compared
+with the literal oracle here, without a GPU.  The GPU parity tests proper are tests/test_gpu_*.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.common import M, SM, make_cfg, transient_inputs, assert_state_close, assert_series_close, loam
+from microclimc_b200 import layout as L, synth as S
+
+PD = C.POINTER(C.c_double)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(PD)
+
+
+def _f(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def dbg_run_transient(lib, inp, cfg, m=M, sm=SM, state=None, pai_season=None, want_full=False):
+    veg, soil, f, lat, lon, fs, fo = map(_f, (inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], inp["fs"], inp["fo"]))
+    ncol, T = veg.shape[1], f.shape[0]
+    NS = L.nstate(m, sm)
+    st = np.zeros((NS, ncol)) if state is None else np.array(state, dtype=np.float64, order="C", copy=True)
+    samp = np.arange(ncol, dtype=np.int64)
+    series = np.zeros((T, 8, ncol)); stats = np.zeros((6, ncol)); flags = np.zeros(ncol, dtype=np.int32)
+    full = np.zeros((T, NS, ncol)) if want_full else None
+    lib.dbg_run_transient.restype = C.c_int
+    rc = lib.dbg_run_transient(C.c_int64(ncol), m, sm, C.c_int64(T), _p(veg), _p(soil), _p(f), _p(fs), _p(fo), None, _p(lat), _p(lon),
+                               _p(_f(cfg)), _p(_f(pai_season)), _p(st), _p(series), samp.ctypes.data_as(C.POINTER(C.c_int64)),
+                               C.c_int64(ncol), _p(stats), _p(full), flags.ctypes.data_as(C.POINTER(C.c_int32)), 0)
+    assert rc == 0
+    return dict(state=st, series=series, stats=stats, flags=flags, full=full)
+
+
+def dbg_runonestep(lib, inp, clim, cfg, jd, lt, theta, thetap, state, m=M, sm=SM):
+    veg, soil, lat, lon, clim, theta, thetap = map(_f, (inp["veg"], inp["soil"], inp["lat"], inp["lon"], clim, theta, thetap))
+    st = np.array(state, dtype=np.float64, order="C", copy=True)
+    ncol = st.shape[1]
+    nm = np.zeros(ncol, dtype=np.int32)
+    rc = lib.dbg_runonestep(C.c_int64(ncol), m, sm, _p(veg), _p(soil), _p(clim), _p(lat), _p(lon), _p(_f(cfg)), C.c_double(jd),
+                            C.c_double(lt), _p(theta), _p(thetap), _p(st), nm.ctypes.data_as(C.POINTER(C.c_int)))
+    assert rc == 0
+    return st, nm
+
+
+def _random_climvars(ncol, seed=5):
+    rng = np.random.default_rng(seed)
+    clim = np.stack([rng.uniform(-5, 25, ncol), rng.uniform(40, 100, ncol), rng.uniform(98, 103, ncol), rng.uniform(0, 12, ncol),
+                     rng.uniform(5, 12, ncol), rng.uniform(0.7, 1.0, ncol), rng.uniform(0, 900, ncol), rng.uniform(0.1, 1.0, ncol)])
+    return clim, rng.uniform(0.15, 0.4, ncol), rng.uniform(0.15, 0.4, ncol)
+
+
+@pytest.mark.parametrize("timestep,reqhgt,edgedist,metopen", [(3600.0, np.nan, 100.0, 1), (60.0, np.nan, 100.0, 1), (600.0, 5.0, np.nan, 1),
+                                                             (3600.0, 0.5, 30.0, 0), (20.0, 17.0, 100.0, 1)])
+def test_fused_step_equals_literal_oracle(oracle, hostdbg, timestep, reqhgt, edgedist, metopen):
+    inp = transient_inputs(oracle, ncol=24, T=4)
+    windhgt = 2.0 if metopen else 19.0
+    cfg_spin = make_cfg(timestep=timestep, reqhgt=reqhgt, edgedist=edgedist, metopen=metopen, windhgt=windhgt, spin_steps=15)
+    st0 = oracle.run_transient(inp["veg"], inp["soil"], inp["f"][:1], inp["lat"], inp["lon"], cfg_spin, M, SM, fscale=inp["fs"],
+                               foffset=inp["fo"])["state"]
+    cfg = make_cfg(timestep=timestep, reqhgt=reqhgt, edgedist=edgedist, metopen=metopen, windhgt=windhgt, spin_steps=0)
+    clim, theta, thetap = _random_climvars(24)
+    want, nm_o = oracle.runonestep(inp["veg"], inp["soil"], clim, inp["lat"], inp["lon"], cfg, 2449900.0, 13.0, theta, thetap, st0, M, SM)
+    got, nm_d = dbg_runonestep(hostdbg, inp, clim, cfg, 2449900.0, 13.0, theta, thetap, st0)
+    assert np.array_equal(nm_o, nm_d)
+    assert_state_close(got, want, what="dt=%g" % timestep)
+
+
+def test_merged_layer_branch_is_exercised(oracle, hostdbg):
+    """Short time steps give several merged air layers (code.R:813-852); hourly steps give one (code.R:854-867)."""
+    inp = transient_inputs(oracle, ncol=8, T=2)
+    counts = {}
+    for ts in (3600.0, 120.0, 5.0):
+        cfg_spin = make_cfg(timestep=ts, spin_steps=10)
+        st0 = oracle.run_transient(inp["veg"], inp["soil"], inp["f"][:1], inp["lat"], inp["lon"], cfg_spin, M, SM)["state"]
+        clim, theta, thetap = _random_climvars(8, seed=9)
+        _, nm = oracle.runonestep(inp["veg"], inp["soil"], clim, inp["lat"], inp["lon"], make_cfg(timestep=ts, spin_steps=0), 2449900.0, 11.0,
+                                  theta, thetap, st0, M, SM)
+        counts[ts] = nm
+    assert np.all(counts[3600.0] == 1)
+    assert np.any(counts[120.0] > 1) and np.all(counts[5.0] >= counts[120.0]) and np.all(counts[5.0] > 1) and counts[5.0].max() <= M
+
+
+@pytest.mark.parametrize("timestep,charmode,reqhgt", [(3600.0, 0, np.nan), (300.0, 1, np.nan), (3600.0, 0, 7.3), (3600.0, 0, -0.3)])
+def test_trajectory_with_spinup_equals_oracle(oracle, hostdbg, timestep, charmode, reqhgt):
+    inp = transient_inputs(oracle, ncol=6, T=72)
+    cfg = make_cfg(timestep=timestep, reqhgt=reqhgt, spin_steps=60, harvest_char=charmode)
+    want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"],
+                                want_full=True)
+    got = dbg_run_transient(hostdbg, inp, cfg, want_full=True)
+    assert_series_close(got["series"], want["series"], "trajectory")
+    assert_state_close(got["state"], want["state"], what="final state")
+    np.testing.assert_allclose(got["stats"], want["stats"], rtol=0, atol=1e-6)
+    assert np.array_equal(got["flags"] & 1, want["flags"] & 1)
+    assert_state_close(got["full"][40], want["full"][40], what="full table row")
+
+
+def test_other_layer_counts(oracle, hostdbg):
+    """m = 7 / sm = 5 (small template) and m = 33 / sm = 12 (large template)."""
+    for m, sm in [(7, 5), (33, 12)]:
+        soil = loam(oracle); soil["z"] = oracle.soilinit_z(sm)
+        veg, so = S.ensemble(S.vegp_deciduous(m=m), soil, 5, m, sm, seed=3)
+        f, ts = S.forcing_from_climdata(S.load_weather()); f = np.ascontiguousarray(f[4000:4030])
+        inp = dict(veg=veg, soil=so, f=f, lat=np.full(5, 50.0), lon=np.full(5, -5.0), fs=None, fo=None)
+        cfg = make_cfg(spin_steps=25)
+        want = oracle.run_transient(veg, so, f, inp["lat"], inp["lon"], cfg, m, sm)
+        got = dbg_run_transient(hostdbg, inp, cfg, m=m, sm=sm)
+        assert_state_close(got["state"], want["state"], m=m, sm=sm, what="m=%d" % m)
+
+
+def test_zero_pai_layers_are_floored(oracle, hostdbg):
+    """PAI == 0 -> 1e-4 (code.R:691-696)."""
+    inp = transient_inputs(oracle, ncol=3, T=24, perturb=False)
+    inp["veg"][L.veg_rows(M)["PAI"]][3:6, :] = 0.0
+    cfg = make_cfg(spin_steps=20)
+    want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM)
+    got = dbg_run_transient(hostdbg, inp, cfg)
+    assert np.all(np.isfinite(want["state"]))
+    assert_state_close(got["state"], want["state"], what="zero PAI")
+
+
+# ---- steady path ----------------------------------------------------------------------------------------------------
+def _steady_inputs(oracle, ncol, T, t0=0, snow=False, percol=False, seed=2):
+    veg, soil = S.ensemble(S.vegp_deciduous(), loam(oracle), ncol, M, SM, seed=seed)
+    clim = S.steady_clim_from_climdata(S.load_weather())[t0:t0 + T]
+    rng = np.random.default_rng(seed)
+    shape = (T, 11, ncol) if percol else (T, 11)
+    nmr = np.zeros(shape)
+    tair = clim[:, 0]
+    bt = (lambda a: a[:, None]) if percol else (lambda a: a)
+    nmr[:, 0] = bt(tair) + rng.normal(0.5, 1.0, nmr[:, 0].shape)
+    nmr[:, 1] = rng.uniform(0.12, 0.4, nmr[:, 1].shape)
+    if snow:
+        sd = np.clip(rng.normal(20, 40, nmr[:, 2].shape), 0, None)       # cm; about a third of the hours snow-free
+        nmr[:, 2] = sd
+        nmr[:, 3:] = rng.uniform(-10, 0, nmr[:, 3:].shape)
+    return veg, soil, clim, nmr
+
+
+def dbg_run_steady(lib, veg, soil, clim, nmr, lat, lon, scfg, m=M, sm=SM, pai_season=None):
+    veg, soil, clim, nmr, lat, lon, scfg = map(_f, (veg, soil, clim, nmr, lat, lon, scfg))
+    ncol, T = veg.shape[1], clim.shape[0]
+    out = np.zeros((T, 7, ncol)); stats = np.zeros((6, ncol))
+    rc = lib.dbg_run_steady(C.c_int64(ncol), m, sm, C.c_int64(T), _p(veg), _p(soil), _p(clim), _p(nmr), 1 if nmr.ndim == 3 else 0, _p(lat),
+                            _p(lon), _p(scfg), _p(_f(pai_season)), _p(out), _p(stats), 0)
+    return dict(out=out, stats=stats, rc=rc)
+
+
+@pytest.mark.parametrize("reqhgt,snow,percol", [(1.0, False, False), (15.5, False, False), (22.0, False, True), (1.0, True, True),
+                                                (0.3, True, False), (18.0, True, False)])
+def test_steady_series_equals_oracle(oracle, hostdbg, reqhgt, snow, percol):
+    ncol, T = 7, 96
+    veg, soil, clim, nmr = _steady_inputs(oracle, ncol, T, t0=600, snow=snow, percol=percol)
+    lat = np.full(ncol, 50.0); lon = np.full(ncol, -5.0)
+    scfg = np.array([reqhgt, 1, 2, 1, 0.95])
+    want = oracle.run_steady(veg, soil, clim, nmr, lat, lon, scfg, M, SM)
+    got = dbg_run_steady(hostdbg, veg, soil, clim, nmr, lat, lon, scfg)
+    assert want["rc"] == 0 and got["rc"] == 0
+    assert np.array_equal(np.isnan(got["out"]), np.isnan(want["out"]))
+    np.testing.assert_allclose(np.nan_to_num(got["out"]), np.nan_to_num(want["out"]), rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(got["stats"], want["stats"], rtol=0, atol=1e-6)
+    if snow:
+        buried = reqhgt < nmr[:, 2] / 100.0
+        if buried.any():     # under the snow pack: wind 0, RH 100, SW 0 (NMR.R:668-675)
+            o = want["out"] if not percol else want["out"]
+            sel = np.broadcast_to(buried if percol else buried[:, None], (T, ncol))
+            assert np.all(want["out"][:, 5][sel] == 0) and np.all(want["out"][:, 2][sel] == 100) and np.all(want["out"][:, 3][sel] == 0)
+
+
+def test_steady_snow_lookup_error_is_reported(oracle, hostdbg):
+    veg, soil, clim, nmr = _steady_inputs(oracle, 3, 24, snow=True)
+    nmr[:, 2] = 50.0
+    lat = np.full(3, 50.0); lon = np.full(3, -5.0)
+    scfg = np.array([0.01, 1, 2, 1, 0.95])           # below the lowest snow node: R indexes snow[, 11]
+    assert oracle.run_steady(veg, soil, clim, nmr, lat, lon, scfg, M, SM)["rc"] != 0
+    assert dbg_run_steady(hostdbg, veg, soil, clim, nmr, lat, lon, scfg)["rc"] != 0
