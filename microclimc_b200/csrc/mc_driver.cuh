@@ -55,8 +55,10 @@ MC_HD void forcing_at(const TransientArgs& a, long long t, long long c, double* 
   }
 }
 
+// `live` is false for the padding threads of the last block: they shadow the last column through every barrier and
+// write nothing.
 template <int MM, int MS>
-MC_HD void run_column(const TransientArgs& a, long long c) {
+MC_HD void run_column(const TransientArgs& a, long long c, bool live = true) {
   Column<MM, MS> col;
   col.load_params(a.vegp, a.soilp, a.lat, a.lon, a.ncol, c, a.m, a.sm);
   const int m = a.m;
@@ -88,6 +90,7 @@ MC_HD void run_column(const TransientArgs& a, long long c) {
                   f0[F_THETA], f0[F_THETA]};
     double Hsum = 0;
     for (int i = 1; i <= a.spin_steps; ++i) {
+      MC_CTA_SYNC();
       col.step(fc, cs);
       Hsum += col.H;
       col.H = Hsum / i;                                                                                   // previn$H <- mean(H)
@@ -105,6 +108,7 @@ MC_HD void run_column(const TransientArgs& a, long long c) {
   const long long slot = (a.nsamp > 0 && a.samp_of) ? a.samp_of[c] : -1;
   const int NS = nstate_rows(m, a.sm);
   for (long long t = a.t0; t < a.t1; ++t) {
+    MC_CTA_SYNC();
     forcing_at(a, t, c, f);
     if (a.season && t > a.t0) { col.precompute(cl, a.season[t]); col.precompute_leafgeom(cl); }
     Forcing fc = {f[F_TAIR], f[F_RELHUM], f[F_PK], f[F_U], tsoil, f[F_SKYEM], f[F_RSW], f[F_DP], f[F_JD], f[F_LT], f[F_THETA],
@@ -116,11 +120,12 @@ MC_HD void run_column(const TransientArgs& a, long long c) {
     st[0] += o[0]; if (o[0] < st[1]) st[1] = o[0]; if (o[0] > st[2]) st[2] = o[0];
     st[3] += o[1]; if (o[1] < st[4]) st[4] = o[1]; if (o[1] > st[5]) st[5] = o[1];
     if (!isfinite(o[0]) || !isfinite(o[1])) flag |= 1;
-    if (slot >= 0) {
+    if (slot >= 0 && live) {
       if (a.series) for (int q = 0; q < 8; ++q) a.series[((t - a.t0) * 8 + q) * a.nsamp + slot] = o[q];
       if (a.full) col.store_state(a.full + (t - a.t0) * NS * a.nsamp, a.nsamp, slot);
     }
   }
+  if (!live) return;
   if (a.stats) {
     const double n = (double)(a.t1 - a.t0);
     a.stats[0 * a.ncol + c] = st[0] / n; a.stats[1 * a.ncol + c] = st[1]; a.stats[2 * a.ncol + c] = st[2];

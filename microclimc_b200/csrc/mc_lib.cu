@@ -22,7 +22,8 @@ constexpr int kBlock = 128;
 template <int MM, int MS>
 __global__ void __launch_bounds__(kBlock) k_transient(TransientArgs a) {
   long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (c < a.ncol) run_column<MM, MS>(a, c);
+  const bool live = c < a.ncol;
+  run_column<MM, MS>(a, live ? c : a.ncol - 1, live);
 }
 template <int MM, int MS>
 __global__ void __launch_bounds__(kBlock) k_onestep(OneStepArgs a) {

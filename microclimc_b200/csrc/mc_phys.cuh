@@ -10,8 +10,17 @@
 
 #if defined(__CUDACC__)
 #define MC_HD __host__ __device__ __forceinline__
+#define MC_NI __host__ __device__ __noinline__      // large bodies: one copy in the instruction stream (I-cache)
 #else
 #define MC_HD inline
+#define MC_NI inline
+#endif
+// CTA-wide rendezvous that keeps the warps of a block on the same stretch of code, so that one instruction-cache
+// fill serves all of them (the hot loop is larger than the 32 KB L1.5 I-cache). No-op in the host (test) build.
+#if defined(__CUDA_ARCH__)
+#define MC_CTA_SYNC() __syncthreads()
+#else
+#define MC_CTA_SYNC() ((void)0)
 #endif
 
 namespace mc {

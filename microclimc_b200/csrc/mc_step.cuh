@@ -81,7 +81,7 @@ struct Column {
     lat = latp[c]; lon = lonp[c];
     th_cache = -1e300;
   }
-  MC_HD void load_state(const double* __restrict__ st, long long ncol, long long c) {
+  MC_NI void load_state(const double* __restrict__ st, long long ncol, long long c) {
     auto P = [&](int r) { return st[(long long)r * ncol + c]; };
     tabove = P(P_TABOVE); relhum = P(P_RELHUM); tair = P(P_TAIR); tsoil = P(P_TSOIL); pk = P(P_PK); H = P(P_H); psi_m = P(P_PSIM);
     zabove = P(P_ZABOVE); G = P(P_G);
@@ -100,7 +100,7 @@ struct Column {
     r += m; for (int i = 1; i <= m + 1; ++i) gt[i] = P(r + i - 1);
     r += m + 1; for (int i = 1; i <= sm; ++i) soiltc[i] = P(r + i - 1);
   }
-  MC_HD void store_state(double* __restrict__ st, long long ncol, long long c) const {
+  MC_NI void store_state(double* __restrict__ st, long long ncol, long long c) const {
     auto W = [&](int r, double v) { st[(long long)r * ncol + c] = v; };
     W(P_TABOVE, tabove); W(P_ZABOVE, zabove); W(P_RELHUM, relhum); W(P_TAIR, tair); W(P_TSOIL, tsoil); W(P_PK, pk);
     W(P_H, H); W(P_G, G); W(P_PSIM, psi_m);
@@ -161,7 +161,7 @@ struct Column {
     return !(zq < 0.12);
   }
   // generic windprofile (code.R:191-221) for one height
-  MC_HD static double windprofile(double ui, double zi, double zo, double a, double PAI_, double hgt_, double psi, double hgtg_,
+  MC_NI static double windprofile(double ui, double zi, double zo, double a, double PAI_, double hgt_, double psi, double hgtg_,
                                   double zm0_) {
     double dd = zeroplanedis(hgt_, PAI_);
     double zmm = roughlength_d(hgt_, PAI_, dd, zm0_);
@@ -197,7 +197,7 @@ struct Column {
   }
 
   // ---- time-invariant geometry (recomputed each step only when PAI varies in time) -------------
-  MC_HD void precompute(const RunCfg& cfg, double season) {
+  MC_NI void precompute(const RunCfg& cfg, double season) {
     for (int i = 1; i <= m; ++i) { double p = PAIbase[i] * season; PAI[i] = (p == 0) ? 0.0001 : p; }   // code.R:691-696
     const double reqhgt = cfg.reqhgt;
     for (int i = 1; i <= m; ++i) z[i] = (i - 0.5) / m * hgt;
@@ -282,7 +282,7 @@ struct Column {
     trlw_sum = clumptr(exp(-slw * sumPAI), 0.0);
   }
   // leaftemp's layer geometry depends on previn$z (code.R:387-392)
-  MC_HD void precompute_leafgeom(const RunCfg& cfg) {
+  MC_NI void precompute_leafgeom(const RunCfg& cfg) {
     for (int i = 1; i <= m - 1; ++i) zthp[i] = zprev[i + 1] - zprev[i];
     zthp[m] = hgt - (zprev[m] + zprev[m - 1]) / 2;
     for (int i = 1; i <= m; ++i) zla[i] = mixinglength(zthp[i], PAI[i]) * 0.5 * cfg.zlafact;
@@ -290,7 +290,7 @@ struct Column {
     for (int i = 1; i <= m; ++i) if (zprev[i] != z[i]) zprev_is_z = false;
   }
 
-  MC_HD void soilk(double timestep, double theta) {
+  MC_NI void soilk(double timestep, double theta) {
     if (theta == th_cache) return;
     th_cache = theta;
     double A = 0.65 - 0.78 * rho + 0.6 * rho * rho;
@@ -310,7 +310,7 @@ struct Column {
   }
 
   // Thomas (code.R:94-125) on 1-based local arrays: tcv[N+2] (modified), k[N+1], cdv[N], Xv[N] -> tn[N+2].
-  MC_HD static void thomas(int N, double* tcv, double tmsoil, double tairv, const double* k, const double* cdv, double f,
+  MC_NI static void thomas(int N, double* tcv, double tmsoil, double tairv, const double* k, const double* cdv, double f,
                            const double* Xv, double* tn, double* cc, double* dd) {
     const double g = 1 - f;
     tn[N + 2] = tmsoil; tn[1] = tairv;
@@ -342,7 +342,7 @@ struct Column {
 
   // ---- one time step (runonestep, code.R:687-902) ---------------------------------------------
   // returns the number of merged air layers used by the diffusion solve
-  MC_HD int step(const Forcing& fc, const RunCfg& cfg) {
+  MC_NI int step(const Forcing& fc, const RunCfg& cfg) {
     const double timestep = cfg.timestep;
     const double tairn = fc.tair, pkn = fc.pk, skyem = fc.skyem, Rsw = fc.Rsw;
     double relhumn = fc.relhum, u = fc.u;
@@ -417,6 +417,7 @@ struct Column {
       gtn[m] = (g > gfree) ? g : gfree;
     }
     for (int i = m - 1; i >= 1; --i) {
+      MC_CTA_SYNC();
       bool fast = zi_[i] != 0.0;
       double zt = z[i + 1] - z[i];
       double zi = z[i + 1] + 0.5 * zt, zo = z[i + 1] - 0.5 * zt;
@@ -462,6 +463,7 @@ struct Column {
     double aRsw1 = 0, ref_m = 0;
     double Rabsn[MM + 2], gvn[MM + 2], ghan[MM + 2];
     for (int i = 1; i <= m; ++i) {
+      MC_CTA_SYNC();
       double ref = pLAI[i] * refls + (1 - pLAI[i]) * refw;
       double pc = PAIg[m + 1 - i];
       double sunl = psunlit_k(pc, sa, K, clump);
@@ -496,6 +498,7 @@ struct Column {
     const double eamn = (relhumn / 100) * tet_tcan;
     double tnl[MM + 2], tleafn[MM + 2], eal[MM + 2];
     for (int i = 1; i <= m; ++i) {
+      MC_CTA_SYNC();
       const double ptc = tc[i], ptl = tleaf[i];
       const double zp = zprev[i], zth = zthp[i], zl = zla[i];
       const double zrf = (hgt + 2) - zp;
@@ -589,6 +592,7 @@ struct Column {
       L[i] = (aX + bX * dTL) * PAI[i];                                                         // code.R:880 (Q1)
     }
     // ---- soil conductances and surface forcing (code.R:789-811) ----
+    MC_CTA_SYNC();
     soilk(timestep, fc.theta);
     double TT[MM + 2];
     { double s = 0; for (int i = 1; i <= m; ++i) { s += (phair(tc[i], ppk) / gtn[i]) * (z[i] - (i > 1 ? z[i - 1] : 0.0)); TT[i] = s; } }
@@ -717,6 +721,7 @@ struct Column {
       }
     }
     // ---- limits, humidity, fluxes (code.R:868-897) ----
+    MC_CTA_SYNC();
     if (tnsoil[1] < tfrost) tnsoil[1] = tfrost;
     if (tnsoil[1] > tairn + 30) tnsoil[1] = tairn + 30;
     double Lt = 0;
@@ -742,6 +747,7 @@ struct Column {
     const double Hn = net - Gn - Lt;
     // ---- commit the new state ----
     for (int i = 1; i <= m; ++i) {
+      MC_CTA_SYNC();
       double tn = tnn[i];
       double es = tetens(tn);
       double r = (ean2[i] / es) * 100;
@@ -762,7 +768,7 @@ struct Column {
   }
 
   // runmodel's per-step output harvest (code.R:1222-1265): tout, tleaf, rh, Rswin, Rlwin, L, H, G
-  MC_HD void harvest(double reqhgt, int charmode, double temp_i, double relhum0, double rsw0, double skyem0, double* o) const {
+  MC_NI void harvest(double reqhgt, int charmode, double temp_i, double relhum0, double rsw0, double skyem0, double* o) const {
     double stc = 0, stl = 0, srh = 0, ssw = 0, slw = 0, sL = 0;
     for (int i = 1; i <= m; ++i) { stc += tc[i]; stl += tleaf[i]; srh += rh[i]; ssw += Rswin[i]; slw += Rlwin[i]; sL += L[i]; }
     o[6] = H; o[7] = G;
