@@ -60,6 +60,7 @@ MC_HD void forcing_at(const TransientArgs& a, long long t, long long c, double* 
 template <int MM, int MS>
 MC_HD void run_column(const TransientArgs& a, long long c, bool live = true) {
   Column<MM, MS> col;
+  col.cta_sync = true;
   col.load_params(a.vegp, a.soilp, a.lat, a.lon, a.ncol, c, a.m, a.sm);
   const int m = a.m;
   double f0[F_N], f[F_N];

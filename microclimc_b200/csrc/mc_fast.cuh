@@ -1,0 +1,1005 @@
+// Streaming form of the transient step (runonestep, R/code.R:687-902) for the configuration the BASELINE workloads run:
+// time-invariant PAI, at most kNG merged canopy air layers (hourly steps give 1-5), regular wind edge profile.
+// Columns that leave that envelope at some step (many merged layers at very short time steps, state whose node
+// heights differ from the current geometry) take that step through the general `Column::step` (mc_step.cuh).
+//
+// Why a second form: the general column keeps ~16 KB of thread-private state + hoisted geometry + work arrays and is
+// bound by local-memory latency (profiles/README.md r01b: long_scoreboard 64 % of stalls, FP64 pipe 13 % busy).
+// Here nothing per-layer lives in thread-private memory:
+//   * a geometry kernel writes every time-invariant per-layer constant once per launch into a tile-major workspace
+//     P[tile][row][128 columns];  state S and the few inter-pass work rows W use the same tiling;
+//   * the step is three sweeps over the layers — A: top -> bottom (wind, turbulent conductances, code.R:747-770),
+//     B: bottom -> top (leafabs + leaftemp, code.R:776-785, with the layermerge / layeraverage sums accumulated on
+//     the way), then the Thomas / ThomasV solves on the few merged nodes (code.R:813-860), C: bottom -> top
+//     (layerinterp or the equilibrium blend, humidity, limits, code.R:846-897) — and each (sweep, layer) is one
+//     pipeline stage whose rows (2-27 KB per 128-column tile) are
+//     fetched by TMA 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx) into a double-buffered shared-memory
+//     stage while the previous layer is being computed; results go back with coalesced 8-byte stores;
+//   * the block's four warps advance stage by stage together, so one instruction-cache fill serves all of them.
+// The same code builds for the host (tests/hostdbg) with a direct-memory accessor, which is how its arithmetic is
+// checked against the CPU oracle without a GPU.
+#pragma once
+#include "mc_driver.cuh"
+
+namespace mc {
+
+constexpr int kTile = 128;   // columns per CTA == columns per workspace tile
+#if !defined(__CUDACC__)
+static long long g_mc_general_steps = 0;
+#endif
+
+// ---- workspace rows -----------------------------------------------------------------------------------------------
+enum { P0_HGT, P0_LA, P0_LNREF, P0_LZU, P0_LZUH, P0_LZOH, P0_LNHD, P0_D, P0_GLNH, P0_DZTB, P0_SUMPAI, P0_WL1, P0_WL2,
+       P0_A0CAP, P0_GXC0, P0_CGCAP, P0_RDZCAP, P0_A0G, P0_GXG1, P0_CGG, P0_RZG,
+       P0_X, P0_KDEN, P0_CLUMP, P0_REFG, P0_SM, P0_TRDM, P0_EMV, P0_VEGEM, P0_TRLWSUM, P0_REFM, P0_LAT, P0_LON,
+       P0_GSMAX, P0_Q50, P0_LWD, P0_SMAX, P0_SOILB, P0_PSIE, P0_SKA, P0_SKB, P0_SKC, P0_SKAD, P0_CVDRY, P0_Z1,
+       P0_SELG, P0_SELH, P0_SELS, P0_ZABOVE, P0_FAST, P0_NFIX };          // then DZK[sm], DZC[sm], Z[m]
+enum { PA_A0I, PA_A0O, PA_EX1, PA_EX2, PA_GLO, PA_GLI, PA_EDO, PA_EDI, PA_GX0, PA_GX1, PA_CG, PA_RDZ, PA_DZ, PA_N };
+enum { PB_REF, PB_PC, PB_SPC, PB_SGC, PB_TRDC, PB_TRDG, PB_TRLW, PB_PAI, PB_IZTH, PB_IZL, PB_IZRF, PB_IZP, PB_MAC, PB_MZ,
+       PB_VDEN, PB_DZ, PB_N };
+enum { S0_TABOVE, S0_RELHUM, S0_TAIR, S0_TSOIL, S0_PK, S0_H, S0_PSIM, S0_G, S0_TCSUM, S0_GTCAP, S0_N };   // then soiltc[sm]
+enum { SL_TC, SL_TLEAF, SL_RH, SL_RABS, SL_GV, SL_GHA, SL_N };
+enum { WL_RG, WL_SFX, WL_GTN, WL_UZN, WL_PHZ, WL_TT, WL_EAL, WL_L, WL_RSWIN, WL_RLWIN, WL_N };
+constexpr int kWLiveB = 5;                        // W rows sweep B reads back from sweep A (RG .. PHZ)
+constexpr int kWLiveC = 2;                        // W rows sweep C reads back from sweep B (TT, EAL)
+constexpr int kStageRows = PB_N + SL_N + kWLiveB; // 27 rows of 128 doubles = 27 KB per stage buffer
+constexpr int kNG = 6;                            // merged air layers handled in the streaming form (more: general path)
+
+struct FastLayout {
+  int m, sm;
+  MC_HD int np0() const { return P0_NFIX + 2 * sm + m; }
+  MC_HD int pz(int i) const { return P0_NFIX + 2 * sm + (i - 1); }
+  MC_HD int pa(int i, int r) const { return np0() + (i - 1) * PA_N + r; }
+  MC_HD int pb(int i, int r) const { return np0() + m * PA_N + (i - 1) * PB_N + r; }
+  MC_HD int nP() const { return np0() + m * (PA_N + PB_N); }
+  MC_HD int soiltc(int j) const { return S0_N + (j - 1); }
+  MC_HD int sl(int i, int r) const { return S0_N + sm + (i - 1) * SL_N + r; }
+  MC_HD int uz(int i) const { return S0_N + sm + m * SL_N + (i - 1); }
+  MC_HD int gt(int i) const { return S0_N + sm + m * SL_N + m + (i - 1); }          // i = 1..m+1
+  MC_HD int nS() const { return S0_N + sm + m * SL_N + m + (m + 1); }
+  MC_HD int wl(int i, int r) const { return (i - 1) * WL_N + r; }
+  MC_HD int nW() const { return m * WL_N; }
+};
+
+struct FastArgs {
+  TransientArgs t;          // the ABI-layout arrays and run description (mc_driver.cuh)
+  double* P;                // [ntile][nP][128]  geometry, written by geom_column
+  double* S;                // [ntile][nS][128]  working state
+  double* W;                // [ntile][nW][128]  inter-pass work rows
+  int spin_mode;            // 1: paraminit + t.spin_steps steps on forcing row 0 with the running mean of H (spinup, code.R:982-1013)
+};
+
+// ---- geometry: one thread per column, once per launch (uses the general column's precompute) -------------------------
+template <int MM, int MS>
+MC_HD void geom_column(const FastArgs& a, const RunCfg& cfg, long long c, long long cl /* clamped source column */) {
+  Column<MM, MS> col;
+  const TransientArgs& t = a.t;
+  col.load_params(t.vegp, t.soilp, t.lat, t.lon, t.ncol, cl, t.m, t.sm);
+  col.precompute(cfg, 1.0);
+  const int m = t.m, sm = t.sm;
+  for (int i = 1; i <= m; ++i) col.zprev[i] = col.z[i];
+  col.precompute_leafgeom(cfg);
+  FastLayout L{m, sm};
+  double* P = a.P + (c / kTile) * (long long)L.nP() * kTile + (c % kTile);
+  auto put = [&](int row, double v) { P[(long long)row * kTile] = v; };
+  const double hgt = col.hgt;
+  put(P0_HGT, hgt); put(P0_LA, col.La); put(P0_LNREF, col.lnref); put(P0_LZU, col.lzu); put(P0_LZUH, col.lzuh); put(P0_LZOH, col.lzoh);
+  put(P0_LNHD, col.lnhd); put(P0_D, col.d); put(P0_GLNH, col.g_lnh); put(P0_DZTB, col.z[m] - col.z[1]); put(P0_SUMPAI, col.sumPAI);
+  {
+    const double zm4 = roughlength_d(hgt, col.sumPAI, col.d, 0.004);
+    put(P0_WL1, log((cfg.windhgt - col.d) / zm4)); put(P0_WL2, log(((hgt + 2) - col.d) / zm4));
+  }
+  put(P0_A0CAP, col.a0_cap); put(P0_GXC0, col.gxc0); put(P0_CGCAP, (col.lm_cap * col.iw[m]) / hgt); put(P0_RDZCAP, 1 / fabs(hgt - col.z[m]));
+  put(P0_A0G, col.a0_g); put(P0_GXG1, col.gxg1); put(P0_CGG, (col.lm_g * col.iwmean) / hgt); put(P0_RZG, 1 / fabs(col.zg - 0));
+  put(P0_X, col.x); put(P0_KDEN, col.kden); put(P0_CLUMP, col.clump); put(P0_REFG, col.refg); put(P0_SM, col.s_m); put(P0_TRDM, col.trd_m);
+  put(P0_EMV, col.emv); put(P0_VEGEM, col.vegem); put(P0_TRLWSUM, col.trlw_sum);
+  put(P0_REFM, col.pLAI[m] * col.refls + (1 - col.pLAI[m]) * col.refw); put(P0_LAT, col.lat); put(P0_LON, col.lon);
+  put(P0_GSMAX, col.gsmax); put(P0_Q50, col.q50); put(P0_LWD, col.lw * 0.71); put(P0_SMAX, col.Smax); put(P0_SOILB, col.soilb);
+  put(P0_PSIE, col.psi_e);
+  {                                                                  // soilk (see Column::soilk): theta-independent pieces
+    const double rho = col.rho;
+    const double A = 0.65 - 0.78 * rho + 0.6 * rho * rho, B = 1.06 * rho, C = 1 + 2.6 / sqrt(col.Mc), D = 0.03 + 0.1 * rho * rho;
+    put(P0_SKA, A); put(P0_SKB, B); put(P0_SKC, C); put(P0_SKAD, A - D);
+    put(P0_CVDRY, 2.128 * col.Vq + 2.385 * col.Vm + 2.496 * col.Vo_s);
+    for (int j = 1; j <= sm; ++j) {
+      const double dzk = (j < sm) ? (col.zs[j + 1] - col.zs[j]) : (col.zs[sm] - col.zs[sm - 1]);
+      const double zlo = (j > 1) ? col.zs[j - 1] : 0.0;
+      const double zhi = (j < sm) ? col.zs[j + 1] : (col.zs[sm] + (col.zs[sm] - col.zs[sm - 1]));
+      put(P0_NFIX + (j - 1), dzk); put(P0_NFIX + sm + (j - 1), zhi - zlo);
+    }
+  }
+  put(P0_Z1, col.z[1]); put(P0_SELG, (double)col.selG);
+  for (int i = 1; i <= m; ++i) put(L.pz(i), col.z[i]);
+  {                                                                  // output node selection of runmodel (code.R:1241-1263)
+    int selh = 0;
+    if (cfg.reqhgt == cfg.reqhgt) for (int i = 1; i <= m; ++i) if (col.z[i] == cfg.reqhgt) { selh = i; break; }
+    int sels = 1; double mn = 1e300;
+    if (cfg.reqhgt == cfg.reqhgt) for (int j = 1; j <= sm; ++j) { double dd = fabs(col.zs[j] + cfg.reqhgt); if (dd < mn) { mn = dd; sels = j; } }
+    put(P0_SELH, (double)selh); put(P0_SELS, (double)sels);
+  }
+  put(P0_ZABOVE, col.zabove_g);
+  bool fast = true;
+  if (cfg.edgedist == cfg.edgedist) for (int i = 1; i <= m; ++i) if (col.zi_[i] == 0.0) fast = false;
+  put(P0_FAST, fast ? 1.0 : 0.0);
+  // sweep A rows: layer m (canopy top, code.R:749-753) then the recurrence layers (code.R:756-767)
+  put(L.pa(m, PA_A0I), col.a0_top); put(L.pa(m, PA_A0O), col.a0_top); put(L.pa(m, PA_EX1), col.ex_top); put(L.pa(m, PA_EX2), col.ex_top);
+  put(L.pa(m, PA_GLO), col.gl_top); put(L.pa(m, PA_GLI), col.gl_top); put(L.pa(m, PA_EDO), col.ed_top); put(L.pa(m, PA_EDI), col.ed_top);
+  put(L.pa(m, PA_GX0), col.gx0_top); put(L.pa(m, PA_GX1), col.gx1_top); put(L.pa(m, PA_CG), (col.lm_top * col.iw[m]) / hgt);
+  put(L.pa(m, PA_RDZ), 1 / fabs(col.z[m] - col.z[m - 1])); put(L.pa(m, PA_DZ), col.z[m] - col.z[m - 1]);
+  for (int i = m - 1; i >= 1; --i) {
+    const double zt = col.z[i + 1] - col.z[i], zi = col.z[i + 1] + 0.5 * zt;
+    const double z0 = (i > 1) ? col.z[i - 1] : 0;
+    put(L.pa(i, PA_A0I), col.a0i[i]); put(L.pa(i, PA_A0O), col.a0o[i]); put(L.pa(i, PA_EX1), col.ex1[i]); put(L.pa(i, PA_EX2), col.ex2[i]);
+    put(L.pa(i, PA_GLO), col.gl_o[i]); put(L.pa(i, PA_GLI), col.gl_i[i]); put(L.pa(i, PA_EDO), col.ed_o[i]); put(L.pa(i, PA_EDI), col.ed_i[i]);
+    put(L.pa(i, PA_GX0), col.gx0[i]); put(L.pa(i, PA_GX1), col.gx1[i]); put(L.pa(i, PA_CG), (col.lmi[i] * col.iw[i]) / zi);
+    put(L.pa(i, PA_RDZ), 1 / fabs(col.z[i] - z0)); put(L.pa(i, PA_DZ), col.z[i] - z0);
+  }
+  // sweep B rows: leafabs (code.R:31-49) and leaftemp (code.R:378-512) constants of the layer
+  for (int i = 1; i <= m; ++i) {
+    const double ref = col.pLAI[i] * col.refls + (1 - col.pLAI[i]) * col.refw;
+    const double pc = col.PAIg[m + 1 - i];
+    const double zth = col.zthp[i], zl = col.zla[i];
+    const double PAIm = 2 * col.PAI[i] / zth;
+    const double vden = col.thickw[i] * col.PAI[i];
+    put(L.pb(i, PB_REF), ref); put(L.pb(i, PB_PC), pc); put(L.pb(i, PB_SPC), col.sref[i] * pc); put(L.pb(i, PB_SGC), col.sref[i] * col.PAIg[i]);
+    put(L.pb(i, PB_TRDC), col.trdc[i]); put(L.pb(i, PB_TRDG), col.trdg[i]); put(L.pb(i, PB_TRLW), col.trlw[i]); put(L.pb(i, PB_PAI), col.PAI[i]);
+    put(L.pb(i, PB_IZTH), 1 / zth); put(L.pb(i, PB_IZL), 1 / zl); put(L.pb(i, PB_IZRF), 1 / ((hgt + 2) - col.z[i]));
+    put(L.pb(i, PB_IZP), 1 / col.z[i]); put(L.pb(i, PB_MAC), (cfg.timestep * PAIm * 2) / (1 - vden));
+    put(L.pb(i, PB_MZ), ((cfg.timestep * PAIm) / (vden * col.cpw * col.phw)) / zl); put(L.pb(i, PB_VDEN), vden);
+    put(L.pb(i, PB_DZ), col.z[i] - (i > 1 ? col.z[i - 1] : 0.0));
+  }
+}
+
+// ---- memory accessors ------------------------------------------------------------------------------------------------
+// DirectMem: host build and the device's non-pipelined reads. Every accessor addresses this thread's lane of a tile.
+struct DirectMem {
+  const double* P; double* S; double* W;      // lane-adjusted tile bases
+  FastLayout L;
+  int ia, ib;
+  MC_HD void step_begin() {}
+  MC_HD void sweepB_begin() {}
+  MC_HD void sweepC_begin() {}
+  MC_HD void stageA(int i) { ia = i; }
+  MC_HD void stageB(int i) { ib = i; }
+  MC_HD void stageC(int i) { ib = i; }
+  MC_HD double c_w(int r) const { return W[(long long)L.wl(ib, WL_TT + r) * kTile]; }
+  MC_HD double a_p(int r) const { return P[(long long)L.pa(ia, r) * kTile]; }
+  MC_HD double a_tcl() const { return S[(long long)L.sl(ia - 1, SL_TC) * kTile]; }          // only for ia > 1
+  MC_HD double a_gto() const { return S[(long long)L.gt(ia) * kTile]; }
+  MC_HD double b_p(int r) const { return P[(long long)L.pb(ib, r) * kTile]; }
+  MC_HD double b_s(int r) const { return S[(long long)L.sl(ib, r) * kTile]; }
+  MC_HD double b_w(int r) const { return W[(long long)L.wl(ib, r) * kTile]; }
+};
+
+#if defined(__CUDACC__)
+#define MC_D __device__ __forceinline__
+// PipeMem: per-stage rows arrive in shared memory through TMA bulk copies; two buffers, one mbarrier each.
+MC_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+MC_D void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+MC_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+MC_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+MC_D void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+MC_D void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+struct PipeMem {
+  const double* P; double* S; double* W;      // lane-adjusted tile bases (for stores and the few direct reads)
+  const double* Pt; const double* St; const double* Wt;   // tile bases (lane 0), for the bulk copies
+  FastLayout L;
+  double* buf;                                 // [2][kStageRows][kTile] in shared memory
+  unsigned long long* bar;                     // [2]
+  int lane;                                    // threadIdx.x
+  unsigned k;                                  // stages issued so far (uniform over the block)
+  const double* cur;                           // current stage buffer + lane
+  MC_D void issueA(int i, unsigned kk) {
+    double* b = buf + (kk & 1) * (kStageRows * kTile);
+    unsigned long long* mb = bar + (kk & 1);
+    const unsigned bytes = (PA_N + (i > 1 ? 1 : 0) + 1) * kTile * 8;
+    mbar_expect_tx(mb, bytes);
+    bulk_g2s(b, Pt + (long long)L.pa(i, 0) * kTile, PA_N * kTile * 8, mb);
+    if (i > 1) bulk_g2s(b + PA_N * kTile, St + (long long)L.sl(i - 1, SL_TC) * kTile, kTile * 8, mb);
+    bulk_g2s(b + (PA_N + 1) * kTile, St + (long long)L.gt(i) * kTile, kTile * 8, mb);
+  }
+  MC_D void issueB(int i, unsigned kk) {
+    double* b = buf + (kk & 1) * (kStageRows * kTile);
+    unsigned long long* mb = bar + (kk & 1);
+    mbar_expect_tx(mb, kStageRows * kTile * 8);
+    bulk_g2s(b, Pt + (long long)L.pb(i, 0) * kTile, PB_N * kTile * 8, mb);
+    bulk_g2s(b + PB_N * kTile, St + (long long)L.sl(i, 0) * kTile, SL_N * kTile * 8, mb);
+    bulk_g2s(b + (PB_N + SL_N) * kTile, Wt + (long long)L.wl(i, 0) * kTile, kWLiveB * kTile * 8, mb);
+  }
+  MC_D void issueC(int i, unsigned kk) {
+    double* b = buf + (kk & 1) * (kStageRows * kTile);
+    unsigned long long* mb = bar + (kk & 1);
+    mbar_expect_tx(mb, kWLiveC * kTile * 8);
+    bulk_g2s(b, Wt + (long long)L.wl(i, WL_TT) * kTile, kWLiveC * kTile * 8, mb);
+  }
+  // generic-proxy stores of the previous sweep -> visible to the async proxy, block-wide; then start the next sweep
+  MC_D void step_begin() {
+    fence_proxy_async();
+    __syncthreads();
+    if (lane == 0) issueA(L.m, k);
+  }
+  MC_D void sweepB_begin() {
+    fence_proxy_async();
+    __syncthreads();
+    if (lane == 0) issueB(1, k);
+  }
+  MC_D void sweepC_begin() {
+    fence_proxy_async();
+    __syncthreads();
+    if (lane == 0) issueC(1, k);
+  }
+  MC_D void stageC(int i) {
+    __syncthreads();
+    if (lane == 0 && i < L.m) issueC(i + 1, k + 1);
+    mbar_wait(bar + (k & 1), (k >> 1) & 1);
+    cur = buf + (k & 1) * (kStageRows * kTile) + lane;
+    ++k;
+  }
+  MC_D void stageA(int i) {
+    __syncthreads();                                   // everybody has left the buffer the next stage will fill
+    if (lane == 0 && i > 1) issueA(i - 1, k + 1);
+    mbar_wait(bar + (k & 1), (k >> 1) & 1);
+    cur = buf + (k & 1) * (kStageRows * kTile) + lane;
+    ++k;
+  }
+  MC_D void stageB(int i) {
+    __syncthreads();
+    if (lane == 0 && i < L.m) issueB(i + 1, k + 1);
+    mbar_wait(bar + (k & 1), (k >> 1) & 1);
+    cur = buf + (k & 1) * (kStageRows * kTile) + lane;
+    ++k;
+  }
+  MC_D double a_p(int r) const { return cur[r * kTile]; }
+  MC_D double a_tcl() const { return cur[PA_N * kTile]; }
+  MC_D double a_gto() const { return cur[(PA_N + 1) * kTile]; }
+  MC_D double b_p(int r) const { return cur[r * kTile]; }
+  MC_D double b_s(int r) const { return cur[(PB_N + r) * kTile]; }
+  MC_D double b_w(int r) const { return cur[(PB_N + SL_N + r) * kTile]; }
+  MC_D double c_w(int r) const { return cur[r * kTile]; }
+};
+#endif
+
+// windcanopy (code.R:279-294) with hoisted pieces: uzv = uh * exp(a*ex); edge term ur * exp(a*ed), ur = ugr * gl
+MC_HD double wc_fast(double uh, double a, double ex, double gl, double ed, double ugr, bool edge) {
+  double uzv = uh * fexp(a * ex);
+  if (edge) {
+    double uhr = (ugr * gl) * fexp(a * ed);
+    if (uzv != uzv) uzv = uhr;
+    else if (uhr == uhr && uhr > uzv) uzv = uhr;
+  }
+  return uzv;
+}
+
+struct StepOut { double o[8]; int ng; };
+
+// One time step of one column in streaming form.  `run` false: the thread only keeps the block's barriers company
+// (padding lane, or a column that takes this step through the general path).  Returns false when the column left the
+// fast envelope after sweep A (nothing of the state has been modified then).
+template <class Mem, int MS>
+MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, bool emit, double reqhgt, int charmode,
+                     double relhum0, double rsw0, double skyem0, StepOut& out) {
+  const FastLayout L = mem.L;
+  const int m = L.m, sm = L.sm;
+  const double* P = mem.P; double* S = mem.S; double* W = mem.W;
+  auto p0 = [&](int r) { return P[(long long)r * kTile]; };
+  auto s0 = [&](int r) { return S[(long long)r * kTile]; };
+  auto sput = [&](int r, double v) { S[(long long)r * kTile] = v; };
+  auto wput = [&](int i, int r, double v) { W[(long long)L.wl(i, r) * kTile] = v; };
+  auto wget = [&](int i, int r) { return W[(long long)L.wl(i, r) * kTile]; };
+  mem.step_begin();
+  const double timestep = cfg.timestep;
+  // ---------------- scalars of the step (code.R:700-745) ----------------
+  const double tairn = fc.tair, pkn = fc.pk, skyem = fc.skyem, Rsw = fc.Rsw;
+  double relhumn = fc.relhum, u = fc.u;
+  const double ppk = s0(S0_PK), Hprev = s0(S0_H), ps1 = s0(L.soiltc(1)), tairp = s0(S0_TAIR), relhump = s0(S0_RELHUM),
+               tsoilp = s0(S0_TSOIL), tabove = s0(S0_TABOVE);
+  const double hgt = p0(P0_HGT), dpl = p0(P0_D);
+  const double cpk = 44.6 * (pkn / 101.3), cppk = 44.6 * (ppk / 101.3);      // phair(t, pk) = c * 273.15 / (t + 273.15)
+  const double pha = phair(tairn, pkn);
+  double u2;
+  if (cfg.metopen) {
+    if (cfg.windhgt != 2) u = u * 4.87 / log(67.8 * cfg.windhgt - 5.42);
+    u2 = u * p0(P0_LA) / log(67.8 * 2 - 5.42);
+  } else {
+    u2 = u;
+    if (cfg.windhgt != (2 + hgt)) {                                          // windprofile(u, windhgt, hgt+2, ...) with zo above the canopy
+      const double psi = s0(S0_PSIM);
+      double ln2 = p0(P0_WL2) + psi;
+      if (ln2 < 0.55) ln2 = 0.55;
+      u2 = ((0.4 * (u / (p0(P0_WL1) + psi))) / 0.4) * ln2;
+    }
+  }
+  if (u2 < 0.5) u2 = 0.5;
+  const double lnref = p0(P0_LNREF);
+  const double uf = (0.4 * u2) / lnref;
+  double psi_mn, psi_h;
+  diabatic_cor(tairn, pkn, Hprev, uf, hgt + 2, dpl, psi_mn, psi_h);
+  const double tcm = s0(L.sl(m, SL_TC)), tc1 = s0(L.sl(1, SL_TC));
+  double phi_m;
+  {
+    const double dz = p0(P0_DZTB);
+    const double dtdz = (tcm - tc1) / dz;
+    double dudz = (s0(L.uz(m)) - s0(L.uz(1))) / dz;
+    if (fabs(dudz) < 0.01) dudz = 0.01;
+    const double Tk = s0(S0_TCSUM) / m + 273.15;
+    double Ri = (9.81 / Tk) * dtdz / (dudz * dudz);
+    if (Ri > 0.15) Ri = 0.15;
+    if (Ri < -1) Ri = -1;
+    if (Ri < 0) { double phh = 1 / sqrt(1 - 16 * Ri); phi_m = sqrt(phh); }
+    else { double st = Ri / (1 - 5 * Ri); phi_m = 1 + (6 * st) / (1 + st); }
+  }
+  double tcan;
+  {
+    const double ufh = (0.4 * u2) / (p0(P0_LZU) + psi_h);
+    const double mm = Hprev / (0.4 * pha * cpair(tairn) * ufh);
+    const double tref = tairn + mm * (p0(P0_LZUH) + psi_h);
+    tcan = tref - mm * (p0(P0_LZOH) + psi_h);
+  }
+  const double tfrost = dewpoint((relhumn / 100) * satvap(tairn), tairn);
+  if (tcan < tfrost) tcan = tfrost;
+  if (tcan > (tairn + 15)) tcan = tairn + 15;
+  if (tcan < (tairn - 4.5)) tcan = tairn - 4.5;
+  const double tet_tair = tetens(tairn), tet_tcan = tetens(tcan);
+  {
+    const double ea = tet_tair * (relhumn / 100);
+    relhumn = (ea / tet_tcan) * 100;
+    if (relhumn > 100) relhumn = 100;
+  }
+  const double sqphi = sqrt(phi_m), iphi = 1 / phi_m;
+  const bool edge = cfg.edgedist == cfg.edgedist;
+  const double ugr = (0.4 * (u / p0(P0_GLNH))) / 0.4;                        // grass-profile ur = ugr * gl (uref = u, zref = zu)
+  double uh;
+  {
+    const double ufw = 0.4 * (u2 / (lnref + psi_mn));
+    double ln2 = p0(P0_LNHD) + psi_mn;
+    if (ln2 < 0.55) ln2 = 0.55;
+    uh = (ufw / 0.4) * ln2;
+  }
+  // ---------------- sweep A: wind and turbulent conductances, top -> bottom (code.R:747-770) ----------------
+  double sfx = 0, Rtot = 0, Ctot = 0, cs = 0, tcu = tcm;
+  const int half = (int)nearbyint(m / 2.0);
+  for (int i = m; i >= 1; --i) {
+    mem.stageA(i);
+    if (!run) continue;
+    const double tcl = (i > 1) ? mem.a_tcl() : ps1;
+    const double ai = mem.a_p(PA_A0I) * sqphi;
+    double uzn;
+    if (i == m) uzn = wc_fast(uh, ai, mem.a_p(PA_EX1), mem.a_p(PA_GLO), mem.a_p(PA_EDO), ugr, edge);
+    else {
+      uh = wc_fast(uh, ai, mem.a_p(PA_EX1), mem.a_p(PA_GLO), mem.a_p(PA_EDO), ugr, edge);
+      uzn = wc_fast(uh, mem.a_p(PA_A0O) * sqphi, mem.a_p(PA_EX2), mem.a_p(PA_GLI), mem.a_p(PA_EDI), ugr, edge);        // Q9
+    }
+    const double ph = phair_c(cpk, (tcu + tcl) / 2);
+    const double e0 = fexp(-ai * mem.a_p(PA_GX0)), e1 = fexp(-ai * mem.a_p(PA_GX1));
+    const double g = fdiv(mem.a_p(PA_CG) * ph * uh * ai, e0 - e1) * iphi;
+    const double gfree = 0.0012 * ph * qroot(fabs(tcu - tcl) * mem.a_p(PA_RDZ));
+    const double gtn = (g > gfree) ? g : gfree;
+    const double rn = frcp(gtn);
+    const double rg = frcp(0.5 * gtn + 0.5 * mem.a_gto());
+    const double phz = phair_c(cppk, tcu) * mem.a_p(PA_DZ);
+    wput(i, WL_RG, rg); wput(i, WL_SFX, sfx); wput(i, WL_GTN, gtn); wput(i, WL_UZN, uzn); wput(i, WL_PHZ, phz);
+    sfx += rg; Rtot += rn; Ctot += phz;
+    if (i <= half) cs += rn;
+    tcu = tcl;
+  }
+  bool fastok = run;
+  double gtncap = 0, rgcap = 0;
+  if (run) {
+    {                                                                         // canopy top <-> reference (code.R:769), Q8
+      const double a = p0(P0_A0CAP) * sqphi;
+      const double ph = phair_c(cpk, (tcan + tc1) / 2);
+      const double e0 = fexp(-a * p0(P0_GXC0));
+      const double g = fdiv(p0(P0_CGCAP) * ph * uh * a, e0 - 1.0) * iphi;
+      const double gfree = 0.0012 * ph * qroot(fabs(tcan - tc1) * p0(P0_RDZCAP));
+      gtncap = (g > gfree) ? g : gfree;
+      rgcap = frcp(0.5 * gtncap + 0.5 * s0(S0_GTCAP));
+    }
+    // layermerge (code.R:772) closes a group when timestep / sum(1/gt) <= sum(ph*zth); k closed groups need
+    // sum(1/gt) * sum(ph*zth) >= k^2 * timestep (Cauchy-Schwarz), so below (kNG+1)^2 * timestep at most kNG groups exist.
+    if (!(Rtot * Ctot < (double)((kNG + 1) * (kNG + 1)) * timestep * (1 - 1e-9))) fastok = false;
+  }
+  mem.sweepB_begin();
+  // ---------------- scalars of sweep B: radiation geometry, reference vapour (code.R:776-785) ----------------
+  const double clump = p0(P0_CLUMP), refg = p0(P0_REFG), emv = p0(P0_EMV), vegem = p0(P0_VEGEM);
+  double dp = fc.dp;
+  const double sa = solalt(fc.lt, p0(P0_LAT), p0(P0_LON), fc.jd, cfg.merid, cfg.dst);
+  if (dp != dp) dp = difprop(Rsw, sa);
+  const double xx = p0(P0_X), kden = p0(P0_KDEN);
+  const double K = (sa > 0) ? cank(xx, sa, kden) : 0.0;
+  const double mul = cank(xx, sa < 5 ? 5.0 : sa, kden);
+  const double aG0 = refg * cansw_k(Rsw, dp, sa, p0(P0_SUMPAI), p0(P0_SM), p0(P0_TRDM), K, clump);
+  const double lwout = kSb * pow4(tairn + 273.15);
+  const double lambda_l = (-42.575 * tcan + 44994) * cfg.surfwet;
+  const double mtref = 0.5 * tcan + 0.5 * tairp;
+  const double mrh = 0.5 * relhumn + 0.5 * relhump;
+  const double mpk = 0.5 * ppk + 0.5 * pkn;
+  const double impk = frcp(mpk);
+  const double eref = (mrh / 100) * satvap(mtref);
+  const double esoil = soilrh(fc.theta, p0(P0_SOILB), -p0(P0_PSIE), p0(P0_SMAX), ps1) * satvap(ps1);     // Q7
+  const double eamn = (relhumn / 100) * tet_tcan;
+  const double gsmax = p0(P0_GSMAX), q50 = p0(P0_Q50), lwd = p0(P0_LWD);
+  // soilk (microctools; Column::soilk) for this step's theta
+  double cd1, lam, Cv;
+  {
+    const double ct = p0(P0_SKC) * fc.theta;
+    lam = p0(P0_SKA) + p0(P0_SKB) * fc.theta - p0(P0_SKAD) * exp(-((ct * ct) * (ct * ct)));
+    Cv = (p0(P0_CVDRY) + 4.18 * fc.theta) * 1e6;
+    cd1 = (Cv * p0(P0_NFIX + sm)) / (2 * timestep);
+  }
+  // ---------------- sweep B: leafabs + leaftemp, bottom -> top, with the merged-layer sums ----------------
+  double acc2 = 0, TT = 0, Lt = 0, stl = 0, ssw = 0;
+  double Xs = 0, cp1 = 0;
+  double hv[6] = {0, 0, 0, 0, 0, 0};
+  // layermerge / layeraverage bookkeeping (code.R:772, 814): closed groups 1..ng and the open one
+  int ng = 0, glo[kNG + 2], ghi[kNG + 2], olo = 1;
+  double gw[kNG + 2], gtc[kNG + 2], gVo[kNG + 2], gea[kNG + 2], gX[kNG + 2], gvd[kNG + 2];
+  double oR = 0, oC = 0, ow = 0, otc = 0, oVo = 0, oea = 0, oX = 0, ovd = 0;
+  bool open = false;
+  const bool runB = run && fastok;
+  for (int i = 1; i <= m; ++i) {
+    mem.stageB(i);
+    if (!runB) continue;
+    const double ptc = mem.b_s(SL_TC), ptl = mem.b_s(SL_TLEAF);
+    const double uzn = mem.b_w(WL_UZN), gtn = mem.b_w(WL_GTN);
+    // leafabs (code.R:31-49) of this layer
+    const double ref = mem.b_p(PB_REF), omr = 1 - ref, pc = mem.b_p(PB_PC);
+    double aRsw, rsw;
+    {
+      const double trbc = (sa > 0) ? clumptr(fexp(-(mem.b_p(PB_SPC) * K)), clump) : clumptr(0.0, clump);
+      const double trbg = (sa > 0) ? clumptr(fexp(-(mem.b_p(PB_SGC) * K)), clump) : clumptr(0.0, clump);
+      const double sunl = (sa > 0) ? clumptr(fexp(-K * pc), clump) : clumptr(0.0, clump);
+      const double aR = omr * (Rsw * (dp * mem.b_p(PB_TRDC) + (1 - dp) * trbc));
+      const double aGr = omr * (aG0 * (dp * mem.b_p(PB_TRDG) + (1 - dp) * trbg));
+      aRsw = sunl * mul * aR + (1 - sunl) * aR + aGr;
+      rsw = aRsw / omr;
+    }
+    const double trl = mem.b_p(PB_TRLW);
+    const double aRlw = emv * (trl * skyem * lwout + (1 - trl) * emv * lwout);
+    const double Rabsn = aRsw + aRlw;
+    const double gvn = layercond(rsw, gsmax, q50);
+    const double ghan = 1.41 * gforcedfree(lwd, uzn, ptc, ptl - ptc, pkn, 1.0);
+    // leaftemp (code.R:378-512)
+    const double rg = mem.b_w(WL_RG);
+    const double gtt = frcp(rgcap + mem.b_w(WL_SFX));
+    acc2 += rg;
+    const double gtt2 = frcp(acc2);
+    const double izl = mem.b_p(PB_IZL), izrf = mem.b_p(PB_IZRF), izp = mem.b_p(PB_IZP), izth = mem.b_p(PB_IZTH), PAIi = mem.b_p(PB_PAI);
+    const double PAIm = 2 * PAIi * izth;
+    const double esj = tetens(ptc);
+    const double eaj = (mem.b_s(SL_RH) / 100) * esj;
+    const double estl = satvap(ptl);
+    const double delta = 4098 * tetens(ptl) / sq(ptl + 237.3);
+    const double gvo = mem.b_s(SL_GV), ghao = mem.b_s(SL_GHA);
+    const double gvp = 1 / ((1 / gvo) + (1 / ghao));
+    const double gvc = 1 / ((1 / gvn) + (1 / ghan));
+    const double gvm = 0.5 * gvp + 0.5 * gvc;
+    const double gham = 0.5 * ghan + 0.5 * ghao;
+    const double g1 = gtt * izrf, g2 = gtt2 * izp, g3 = gvm * izl, g3h = gham * izl;
+    double ae, be;
+    if (timestep * dmax(dmax(g1, g3), g2) > 1) {
+      const double gv2b = (PAIm * izth) * gvm;                                // Q21
+      const double iden = frcp(gtt + gtt2 + gv2b);
+      ae = (gtt * eref + gtt2 * esoil + gv2b * estl) * iden;
+      be = (0.5 * delta) * iden;
+    } else {
+      const double ibtm = frcp((1 / timestep) + 0.5 * (g1 + g2 + g3));
+      const double sat = eaj > esj ? 0.0 : 1.0;                               // edf(), code.R:380-386
+      const double e1 = (eref > eaj ? eref - eaj : 0.0) * sat;
+      const double e2 = (esoil > eaj ? esoil - eaj : 0.0) * sat;
+      const double e3 = (estl > eaj ? estl - eaj : 0.0) * sat;
+      ae = eaj + 0.5 * (g1 * e1 + g2 * e2 + g3 * e3) * ibtm;
+      be = (0.25 * gvm * delta) * ibtm;
+    }
+    const double cp = cpair(ptc);
+    const double phc = phair_c(cppk, ptc);
+    double aL, bL;
+    if (timestep * dmax(dmax(g1, g3h), g2) > 1) {
+      const double K1 = gtt * cp, K2 = gtt2 * cp, K3 = gham * cp;
+      const double iden = frcp(K1 + K2 + K3);
+      aL = (K1 * mtref + K2 * ps1 + K3 * ptl) * iden;
+      bL = (0.5 * K3) * iden;
+    } else {
+      const double ma = fdiv(mem.b_p(PB_MAC), cp * phc);
+      const double K1 = g1 * cp, K2 = g2 * cp, K3 = g3h * cp * PAIm;
+      const double ibtm = frcp(1 + 0.5 * ma * (K1 + K2 + K3));
+      aL = (ptc + 0.5 * ma * (K1 * mtref + K2 * ps1 + K3 * ptl)) * ibtm;
+      bL = (0.25 * ma * K3) * ibtm;
+    }
+    if (bL < 0) bL = 0;
+    const double aH = cp * gham * (ptl - aL);
+    double bH = cp * gham * (0.5 - 0.5 * bL);
+    if (bH < 0) bH = 0;
+    const double lg = lambda_l * gvm * impk;
+    double edf_l = (estl > ae ? estl - ae : 0.0);
+    if (ae > esj) edf_l = 0;
+    const double aX = lg * edf_l;
+    double bX = lg * (delta - be);
+    if (bX < 0) bX = 0;
+    const double Ra = 0.5 * Rabsn + 0.5 * mem.b_s(SL_RABS);
+    const double tk = ptl + 273.15;
+    const double aRe = vegem * kSb * pow4(tk);
+    const double bRe = vegem * kSb * 2 * (tk * tk * tk);
+    const double mz = mem.b_p(PB_MZ);                                          // ml / zla
+    const double num = Ra - aRe - aX - aH, bsum = bRe + bX + bH;
+    double dTL = fdiv(mz * num, 1 + mz * bsum);                                // (ml*num) / (zla + ml*bsum)
+    const double dTL2 = fdiv(num, bsum);
+    if (fabs(dTL2) < fabs(dTL)) dTL = dTL2;
+    double tnl = aL + bL * dTL;
+    double tlf = ptl + dTL;
+    if (tlf > tnl) { const double tmx = dmax(tcan + 15, tlf); if (tnl > tmx) tnl = tmx; }
+    if (tlf < tnl) { const double tmn = dmin(tcan - 5, tlf); if (tnl < tmn) tnl = tmn; }
+    const double eam = ae + be * dTL;
+    double ean = eaj + 2 * (eam - eaj);
+    const double es = tetens(tnl);
+    if (ean > es) ean = es;
+    if (ean < eamn) ean = eamn;
+    const double al = log(ean / 0.6108);
+    const double Tdew = -(237.3 * al) / (al - 17.27);
+    double dT1 = -(ptl + dTL - Tdew);
+    if (dT1 < 0) dT1 = 0;
+    const double Lc = lambda_l * gvm * (tetens(tlf) - ean) * impk;
+    double dT2 = -mz * Lc;
+    if (dT2 < 0) dT2 = 0;
+    tlf = tlf + dmin(dT1, dT2);
+    dTL = tlf - ptl;
+    const double dTmx = ptc + 20.2 - ptl, dTmn = ptc - 4.5 - ptl;
+    if (dTL > dTmx) dTL = dTmx;
+    if (dTL < dTmn) dTL = dTmn;
+    tnl = aL + bL * dTL;
+    const double tleafn = ptl + dTL;
+    const double Lp = (aX + bX * dTL) * PAIi;                                   // code.R:880 (Q1)
+    if (i == 1) {                                                               // soil-surface forcing (code.R:799-811)
+      cp1 = cp;
+      const double a1 = (1 - refg) * (aRsw / cd1);
+      if (esoil - ean > 0) {
+        const double mm = ((-42.575 * ptc + 44994) * phc * p0(P0_Z1)) / pkn;
+        const double dl = 4098 * tetens(ps1) / sq(ps1 + 237.3);
+        const double btm = 1 + 0.5 * (mm / cd1) * dl;
+        Xs = (a1 - (mm / cd1) * (esoil - ean)) / btm;
+      } else Xs = a1;
+      const double sgn = Xs < 0 ? -1.0 : 1.0;
+      const double Xsmx = ((1 - refg) * aRsw) / (ghan * cp) + (tnl - ps1);
+      if (fabs(Xs) > fabs(Xsmx)) Xs = Xsmx;
+      Xs = fabs(Xs) * sgn;
+    }
+    // layermerge (code.R:772) greedy grouping with the layeraverage sums (code.R:814) of the open group
+    {
+      const double wi = mem.b_p(PB_DZ), phz = mem.b_w(WL_PHZ), rn = frcp(gtn);
+      TT += phz * rn;                                                           // cumsum((ph/gt) * dz), code.R:797
+      oR += rn; oC += phz; open = true;
+      ow += wi; otc += wi * ptc; oVo += wi * (eaj / ppk); oea += wi * ean; oX += wi * (tnl - ptc); ovd += wi * mem.b_p(PB_VDEN);
+      if (timestep / oR <= oC) {
+        if (ng < kNG + 1) {
+          ++ng;
+          glo[ng] = olo; ghi[ng] = i; gw[ng] = ow; gtc[ng] = otc; gVo[ng] = oVo; gea[ng] = oea; gX[ng] = oX; gvd[ng] = ovd;
+        }
+        olo = i + 1; oR = 0; oC = 0; ow = 0; otc = 0; oVo = 0; oea = 0; oX = 0; ovd = 0; open = false;
+      }
+    }
+    auto slput = [&](int rr, double v) { S[(long long)L.sl(i, rr) * kTile] = v; };
+    slput(SL_TLEAF, tleafn); slput(SL_RABS, Rabsn); slput(SL_GV, gvn); slput(SL_GHA, ghan);
+    sput(L.uz(i), uzn); sput(L.gt(i), gtn);
+    wput(i, WL_TT, TT); wput(i, WL_EAL, ean);
+    if (emit) { wput(i, WL_L, Lp); wput(i, WL_RSWIN, rsw); }
+    Lt += Lp; stl += tleafn; ssw += rsw;
+    if ((int)p0(P0_SELH) == i) { hv[1] = tleafn; hv[3] = rsw; hv[5] = Lp; }
+  }
+  // ---------------- heat and vapour exchange on the merged nodes (code.R:813-867) ----------------
+  double tnsoil[MS + 2];
+  double T2[kNG + 3], Yt[kNG + 3], Ye[kNG + 3];     // interpolation nodes (cumulative resistance, temperature, vapour pressure)
+  int nn = 2;
+  const double TX = TT + (pha / gtncap) * 2;
+  if (runB) {
+    if (open) {                                     // trailing group joins the last closed one
+      if (ng > 0) { ghi[ng] = m; gw[ng] += ow; gtc[ng] += otc; gVo[ng] += oVo; gea[ng] += oea; gX[ng] += oX; gvd[ng] += ovd; }
+      else { ng = 1; glo[1] = 1; ghi[1] = m; }
+    }
+    double k[kNG + MS + 3], cdv[kNG + MS + 2], XX[kNG + MS + 2], tc2[kNG + MS + 4], tn2[kNG + MS + 4], cc[kNG + MS + 4], dd[kNG + MS + 4];
+    if (ng > 1) {
+      const int mg = ng, N = mg + sm;
+      double ltc[kNG + 2], lgt[kNG + 3], lz[kNG + 4], lVo[kNG + 2], lea[kNG + 2], lph[kNG + 2], lTT[kNG + 2];
+      int cprev = 0;
+      lz[1] = 0;
+      for (int g = 1; g <= mg; ++g) {
+        const double iw = 1 / gw[g];
+        ltc[g] = gtc[g] * iw; lVo[g] = gVo[g] * iw; lea[g] = gea[g] * iw;
+        const double lX = gX[g] * iw, lvd = gvd[g] * iw;
+        const double lcp = cpair(ltc[g]);
+        lph[g] = phair(ltc[g], ppk);
+        const int c = (glo[g] + ghi[g] + 1) / 2;
+        lz[g + 1] = P[(long long)L.pz(c) * kTile]; lTT[g] = wget(c, WL_TT);
+        if (c - cprev == 1) lgt[g] = wget(c, WL_GTN);
+        else { double R = 0; for (int j = cprev + 1; j <= c; ++j) R += 1 / wget(j, WL_GTN); lgt[g] = 1 / R; }
+        cprev = c;
+        // stash what the Thomas set-up needs in the solver arrays (filled in reverse order below)
+        XX[mg + 1 - g] = lX; tc2[1 + mg + 1 - g] = ltc[g]; cc[g] = lcp; dd[g] = lvd;
+      }
+      if (m + 1 - cprev == 1) lgt[mg + 1] = gtncap;
+      else { double R = 0; for (int j = cprev + 1; j <= m; ++j) R += 1 / wget(j, WL_GTN); R += 1 / gtncap; lgt[mg + 1] = 1 / R; }
+      lz[mg + 2] = hgt;
+      for (int g = 1; g <= mg; ++g) {
+        const double cda = cc[g] * lph[g] * (1 - dd[g]) * (lz[g + 2] - lz[g]) / 2 * timestep;       // Q10
+        double ka = lgt[g] * cc[g];
+        if (ka > cda) ka = cda;
+        k[mg + 2 - g] = ka; cdv[mg + 1 - g] = cda;
+      }
+      k[1] = lgt[mg + 1] * cpair(tabove);
+      for (int j = 1; j <= sm; ++j) {
+        k[mg + 1 + j] = lam / p0(P0_NFIX + (j - 1)); cdv[mg + j] = (Cv * p0(P0_NFIX + sm + (j - 1))) / (2 * timestep);
+        XX[mg + j] = 0; tc2[1 + mg + j] = s0(L.soiltc(j));
+      }
+      XX[mg + 1] = Xs;
+      tc2[1] = tabove; tc2[N + 2] = tsoilp;
+      Column<4, kNG + MS>::thomas(N, tc2, fc.tsoil, tcan, k, cdv, cfg.n, XX, tn2, cc, dd);
+      for (int j = 1; j <= sm; ++j) tnsoil[j] = tn2[mg + 1 + j];
+      // tnair = rev(tn2[1:(mg+2)]) = (soil 1, air bottom..top, tcan)
+      nn = mg + 2;
+      for (int g = 1; g <= mg + 2; ++g) Yt[g] = tn2[mg + 3 - g];
+      {                                               // ThomasV (code.R:153-169) on reversed arrays
+        double rhs = soilrh(fc.theta, p0(P0_SOILB), p0(P0_PSIE), p0(P0_SMAX), tnsoil[1]); if (rhs > 1) rhs = 1;
+        double rhsp = soilrh(fc.thetap, p0(P0_SOILB), p0(P0_PSIE), p0(P0_SMAX), ps1); if (rhsp > 1) rhsp = 1;
+        const double Vair = (tet_tcan * (relhumn / 100)) / pkn;
+        const double eap = tetens(tairp) * (relhump / 100);
+        const double Vsoil = (tetens(tnsoil[1]) * rhs) / pkn;
+        const double easp = tetens(tsoilp) * rhsp;                               // Q5
+        double vt[kNG + 4], vk[kNG + 3], vcd[kNG + 2], vX[kNG + 2], vn[kNG + 4];
+        vt[1] = eap / ppk; vt[mg + 2] = easp / ppk;
+        for (int g = 1; g <= mg; ++g) vt[1 + g] = lVo[mg + 1 - g];
+        for (int g = 1; g <= mg + 1; ++g) {
+          double gt2 = lgt[g];
+          if (g <= mg) { const double gtmx = lph[g] / (lz[g + 1] - lz[g]) * (2 * timestep); if (gt2 > gtmx) gt2 = gtmx; }
+          vk[mg + 2 - g] = gt2;
+        }
+        for (int g = 1; g <= mg; ++g) {
+          vcd[mg + 1 - g] = phair(Yt[g + 1], pkn);
+          double vf = (lea[g] / pkn) - lVo[g]; if (vf < 0) vf = 0;
+          vX[g] = vf;                                                            // Q6: not reversed
+        }
+        Column<4, kNG + MS>::thomas(mg, vt, Vsoil, Vair, vk, vcd, cfg.n, vX, vn, cc, dd);
+        for (int g = 1; g <= mg + 2; ++g) Ye[g] = vn[mg + 3 - g];                   // mole fractions; scaled by pk after the interpolation
+      }
+      T2[1] = 0; for (int g = 1; g <= mg; ++g) T2[g + 1] = lTT[g];
+      T2[mg + 2] = TX;
+    } else {
+      // canopy air in equilibrium with the air above: soil solve with one lumped canopy conductance (code.R:854-867)
+      k[1] = (1 / cs) * cpair(tabove);
+      for (int j = 1; j <= sm; ++j) {
+        k[1 + j] = lam / p0(P0_NFIX + (j - 1)); cdv[j] = (Cv * p0(P0_NFIX + sm + (j - 1))) / (2 * timestep);
+        XX[j] = 0; tc2[1 + j] = s0(L.soiltc(j));
+      }
+      XX[1] = Xs;
+      tc2[1] = tabove; tc2[sm + 2] = tsoilp;
+      Column<4, kNG + MS>::thomas(sm, tc2, fc.tsoil, tcan, k, cdv, cfg.n, XX, tn2, cc, dd);
+      for (int j = 1; j <= sm; ++j) tnsoil[j] = tn2[1 + j];
+      T2[1] = 0; T2[2] = TX; Yt[1] = tnsoil[1]; Yt[2] = tcan; Ye[1] = esoil; Ye[2] = eamn;       // eair = (relhum/100)*tetens(tcan)
+    }
+  }
+  mem.sweepC_begin();
+  // ---------------- sweep C: back to the m nodes, humidity, limits (code.R:846-874, 893-897) ----------------
+  const double trlw_sum = p0(P0_TRLWSUM);
+  const int selG = (int)p0(P0_SELG), selH = (int)p0(P0_SELH);
+  const double iTX = 1 / TX;
+  double stc = 0, srh = 0, slw = 0, tnselG = 0;
+  for (int i = 1; i <= m; ++i) {
+    mem.stageC(i);
+    if (!runB) continue;
+    const double v = mem.c_w(0), ean = mem.c_w(1);
+    double tnn, ea2;
+    if (nn == 2) {
+      const double wgt = v * iTX;
+      tnn = (1 - wgt) * Yt[1] + wgt * Yt[2];
+      ea2 = (1 - wgt) * Ye[1] + wgt * Ye[2];
+    } else if (!(v >= 0.0) || !(v <= TX)) { tnn = NAN; ea2 = NAN; }
+    else {                                            // layerinterp: R approx(), bisection + linear (code.R:846-847)
+      int a = 1, b = nn;
+      while (a < b - 1) { const int ab = (a + b) / 2; if (v < T2[ab]) b = ab; else a = ab; }
+      if (v == T2[b]) { tnn = Yt[b]; ea2 = Ye[b] * pkn; }
+      else if (v == T2[a]) { tnn = Yt[a]; ea2 = Ye[a] * pkn; }
+      else {
+        const double w = (v - T2[a]) / (T2[b] - T2[a]);
+        tnn = Yt[a] + (Yt[b] - Yt[a]) * w;
+        ea2 = (Ye[a] + (Ye[b] - Ye[a]) * w) * pkn;                               // ea <- vn * pk (code.R:852)
+      }
+    }
+    double r = fdiv(ea2, tetens(tnn)) * 100;
+    if (r > 100) r = 100;
+    if (r < 0) r = 0;
+    const double tdws = dewpoint(ean, tnn);                                    // Q12
+    const double tn = (tnn < tdws) ? tdws : tnn;
+    const double lwt = kSb * pow4(tn + 273.15);
+    const double Rlwin = trlw_sum * skyem * lwt + (1 - trlw_sum) * emv * lwt;
+    if (i == selG) tnselG = tnn;
+    S[(long long)L.sl(i, SL_TC) * kTile] = tn; S[(long long)L.sl(i, SL_RH) * kTile] = r;
+    if (emit) wput(i, WL_RLWIN, Rlwin);
+    stc += tn; srh += r; slw += Rlwin;
+    if (i == selH) { hv[0] = tn; hv[2] = r; hv[4] = Rlwin; }
+  }
+  if (!runB) return !run || fastok;
+  // ---------------- soil limits and fluxes (code.R:868-891) ----------------
+  if (tnsoil[1] < tfrost) tnsoil[1] = tfrost;
+  if (tnsoil[1] > tairn + 30) tnsoil[1] = tairn + 30;
+  const double refm = p0(P0_REFM);
+  const double shade = (1 - exp(-refm * p0(P0_SUMPAI)));
+  const double alb = shade * refm + (1 - shade) * refg;
+  const double Rlw = kSb * 0.97 * pow4(0.5 * tnsoil[1] + 0.5 * ps1 + 273.15);
+  double Gn;
+  {
+    const double a = p0(P0_A0G) * sqphi;
+    const double t1 = tnselG, t0 = tnsoil[1];
+    const double ph = phair((t1 + t0) / 2, pkn);
+    const double e0 = exp(-a * (-1.0)), e1 = exp(-a * p0(P0_GXG1));
+    const double g = (p0(P0_CGG) * ph * uh * a) / ((e0 - e1) * phi_m);
+    const double gfree = 0.0012 * ph * qroot(fabs(t1 - t0) * p0(P0_RZG));
+    const double gt2 = (g > gfree) ? g : gfree;
+    Gn = gt2 * cp1 * (t1 - t0);
+  }
+  const double net = (1 - alb) * Rsw - Rlw;
+  const double Gmx = fabs(net - Lt);
+  if (Gn > Gmx) Gn = Gmx;
+  if (Gn < -Gmx) Gn = -Gmx;
+  const double Hn = net - Gn - Lt;
+  for (int j = 1; j <= sm; ++j) sput(L.soiltc(j), tnsoil[j]);
+  sput(S0_TABOVE, tcan); sput(S0_RELHUM, relhumn); sput(S0_TAIR, tairn); sput(S0_TSOIL, fc.tsoil); sput(S0_PK, pkn); sput(S0_H, Hn);
+  sput(S0_PSIM, psi_mn); sput(S0_G, Gn); sput(S0_TCSUM, stc); sput(S0_GTCAP, gtncap);
+  // ---------------- runmodel's output harvest (code.R:1222-1265) ----------------
+  double* o = out.o;
+  out.ng = ng;
+  o[6] = Hn; o[7] = Gn;
+  if (charmode || reqhgt != reqhgt) { o[0] = stc / m; o[1] = stl / m; o[2] = srh / m; o[3] = ssw / m; o[4] = slw / m; o[5] = Lt; return true; }
+  o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0;
+  if (reqhgt >= hgt) {                                                         // Q13
+    o[0] = tcan; o[1] = stl / m;
+    double r = (((relhum0 / 100) * tet_tair) / tet_tcan) * 100; if (r > 100) r = 100;
+    o[2] = r; o[3] = rsw0; o[4] = skyem0 * 5.67 * 1e-8 * pow4(tcan + 273.15); o[5] = Lt;
+  }
+  if (reqhgt >= 0 && reqhgt < hgt) {
+    if (selH) { for (int q = 0; q < 6; ++q) o[q] = hv[q]; }
+    else { for (int q = 0; q < 6; ++q) o[q] = NAN; }
+  }
+  if (reqhgt <= 0) { o[0] = tnsoil[(int)p0(P0_SELS)]; o[1] = stl / m; o[2] = srh / m; o[3] = ssw / m; o[4] = slw / m; o[5] = Lt; }
+  return true;
+}
+
+// ---- moving one column between the ABI state array and the working rows ------------------------------------------------
+template <int MM, int MS>
+MC_HD void ws_from_column(const Column<MM, MS>& col, const FastLayout& L, double* S) {
+  auto put = [&](int r, double v) { S[(long long)r * kTile] = v; };
+  const int m = L.m, sm = L.sm;
+  put(S0_TABOVE, col.tabove); put(S0_RELHUM, col.relhum); put(S0_TAIR, col.tair); put(S0_TSOIL, col.tsoil); put(S0_PK, col.pk);
+  put(S0_H, col.H); put(S0_PSIM, col.psi_m); put(S0_G, col.G);
+  double s = 0;
+  for (int i = 1; i <= m; ++i) {
+    s += col.tc[i];
+    put(L.sl(i, SL_TC), col.tc[i]); put(L.sl(i, SL_TLEAF), col.tleaf[i]); put(L.sl(i, SL_RH), col.rh[i]); put(L.sl(i, SL_RABS), col.Rabs[i]);
+    put(L.sl(i, SL_GV), col.gv[i]); put(L.sl(i, SL_GHA), col.gha[i]); put(L.uz(i), col.uz[i]); put(L.gt(i), col.gt[i]);
+  }
+  put(S0_TCSUM, s); put(S0_GTCAP, col.gt[m + 1]); put(L.gt(m + 1), col.gt[m + 1]);
+  for (int j = 1; j <= sm; ++j) put(L.soiltc(j), col.soiltc[j]);
+}
+template <int MM, int MS>
+MC_HD void column_from_ws(Column<MM, MS>& col, const FastLayout& L, const double* S) {
+  auto get = [&](int r) { return S[(long long)r * kTile]; };
+  const int m = L.m, sm = L.sm;
+  col.tabove = get(S0_TABOVE); col.relhum = get(S0_RELHUM); col.tair = get(S0_TAIR); col.tsoil = get(S0_TSOIL); col.pk = get(S0_PK);
+  col.H = get(S0_H); col.psi_m = get(S0_PSIM); col.G = get(S0_G);
+  for (int i = 1; i <= m; ++i) {
+    col.tc[i] = get(L.sl(i, SL_TC)); col.tleaf[i] = get(L.sl(i, SL_TLEAF)); col.rh[i] = get(L.sl(i, SL_RH)); col.Rabs[i] = get(L.sl(i, SL_RABS));
+    col.gv[i] = get(L.sl(i, SL_GV)); col.gha[i] = get(L.sl(i, SL_GHA)); col.uz[i] = get(L.uz(i)); col.gt[i] = get(L.gt(i));
+  }
+  col.gt[m + 1] = get(S0_GTCAP);
+  for (int j = 1; j <= sm; ++j) col.soiltc[j] = get(L.soiltc(j));
+}
+
+// One step of one column through the general path (several merged air layers, or node heights of the incoming state that
+// differ from the current geometry).  `zprev` null: previous heights equal the current ones.
+template <int MM, int MS>
+MC_NI void general_step(const FastArgs& a, const RunCfg& cfg, const FastLayout& L, long long c, double* S, double* W, const double* zprev,
+                        long long zld, const Forcing& fc, bool emit, double reqhgt, int charmode, double temp_i, double relhum0, double rsw0,
+                        double skyem0, StepOut& out) {
+#if !defined(__CUDACC__)
+  ++g_mc_general_steps;                     // host (test) build only: how often columns leave the streaming envelope
+#endif
+  Column<MM, MS> col;
+  const TransientArgs& t = a.t;
+  col.load_params(t.vegp, t.soilp, t.lat, t.lon, t.ncol, c, t.m, t.sm);
+  col.precompute(cfg, 1.0);
+  column_from_ws(col, L, S);
+  for (int i = 1; i <= L.m; ++i) { col.zprev[i] = zprev ? zprev[(long long)(i - 1) * zld] : col.z[i]; col.L[i] = 0; col.Rswin[i] = 0; col.Rlwin[i] = 0; }
+  col.zabove = col.zabove_g;
+  col.precompute_leafgeom(cfg);
+  out.ng = col.step(fc, cfg);
+  ws_from_column(col, L, S);
+  if (emit) for (int i = 1; i <= L.m; ++i) {
+    W[(long long)L.wl(i, WL_L) * kTile] = col.L[i]; W[(long long)L.wl(i, WL_RSWIN) * kTile] = col.Rswin[i]; W[(long long)L.wl(i, WL_RLWIN) * kTile] = col.Rlwin[i];
+  }
+  col.harvest(reqhgt, charmode, temp_i, relhum0, rsw0, skyem0, out.o);
+}
+
+// ABI state rows of one column from the working rows (state layout of include/microclimc_b200.h)
+MC_HD void abi_state_from_ws(const FastLayout& L, const double* P, const double* S, const double* W, const double* soilz /* soilp z rows */,
+                             long long soil_ld, double* st, long long ld) {
+  const int m = L.m, sm = L.sm;
+  auto g = [&](int r) { return S[(long long)r * kTile]; };
+  auto w = [&](int r, double v) { st[(long long)r * ld] = v; };
+  w(P_TABOVE, g(S0_TABOVE)); w(P_ZABOVE, P[(long long)P0_ZABOVE * kTile]); w(P_RELHUM, g(S0_RELHUM)); w(P_TAIR, g(S0_TAIR)); w(P_TSOIL, g(S0_TSOIL));
+  w(P_PK, g(S0_PK)); w(P_H, g(S0_H)); w(P_G, g(S0_G)); w(P_PSIM, g(S0_PSIM));
+  int r = P_NSCAL;
+  for (int i = 1; i <= m; ++i) w(r + i - 1, g(L.sl(i, SL_TC)));
+  r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, g(L.sl(i, SL_TLEAF)));
+  r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, g(L.uz(i)));
+  r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, P[(long long)L.pz(i) * kTile]);
+  r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, g(L.sl(i, SL_RH)));
+  r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, g(L.sl(i, SL_RABS)));
+  r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, g(L.sl(i, SL_GV)));
+  r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, g(L.sl(i, SL_GHA)));
+  r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, W[(long long)L.wl(i, WL_L) * kTile]);
+  r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, W[(long long)L.wl(i, WL_RSWIN) * kTile]);
+  r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, W[(long long)L.wl(i, WL_RLWIN) * kTile]);
+  r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, g(L.gt(i)));
+  w(r + m, g(S0_GTCAP));
+  r += m + 1; for (int j = 1; j <= sm; ++j) w(r + j - 1, g(L.soiltc(j)));
+  r += sm; for (int j = 1; j <= sm; ++j) w(r + j - 1, soilz[(long long)(j - 1) * soil_ld]);
+}
+
+// ---- per-column configuration of a launch ---------------------------------------------------------------------------------
+// runmodel maps reqhgt to the spin-up height and to reqhgt2 (code.R:1136-1140, 1199); spinup from runmodel drops zlafact /
+// surfwet (Q22).  `spin` selects the spin-up variant.
+MC_HD RunCfg effective_cfg(const TransientArgs& t, double hgt, bool spin) {
+  const double reqhgt = t.cfg.reqhgt;
+  const double spinhgt = t.charmode ? hgt / 2 : ((reqhgt == reqhgt && reqhgt > 0) ? reqhgt : NAN);
+  RunCfg c = t.cfg;
+  if (spin) { if (!t.spin_standalone) { c.reqhgt = spinhgt; c.zlafact = 1; c.surfwet = 1; } }
+  else c.reqhgt = t.charmode ? spinhgt : reqhgt;
+  return c;
+}
+
+// mean(climdata$temp) of one column (code.R:992, 1165), summed in time order
+MC_HD double column_tmean(const TransientArgs& a, long long c) {
+  double s = 0;
+  if (a.fscale && a.foffset) {
+    const double sc = a.fscale[(long long)F_TAIR * a.ncol + c], of = a.foffset[(long long)F_TAIR * a.ncol + c];
+    for (long long t = 0; t < a.T; ++t) s += a.forcing[t * F_N + F_TAIR] * sc + of;
+  } else {
+    for (long long t = 0; t < a.T; ++t) s += a.forcing[t * F_N + F_TAIR];
+  }
+  return s / (double)a.T;
+}
+
+// The whole launch for one column: spin_mode 1 = paraminit + spin-up steps on forcing row 0 (code.R:982-1013);
+// spin_mode 0 = steps [t0, t1) of runmodel's loop with the output harvest (code.R:1193-1266).
+// `c` is the source column (clamped for padding lanes), `live` false for padding lanes.
+template <class Mem, int MM, int MS>
+MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) {
+  const TransientArgs& t = a.t;
+  const FastLayout L = mem.L;
+  const int m = L.m, sm = L.sm;
+  double* S = mem.S; double* W = mem.W; const double* P = mem.P;
+  auto sput = [&](int r, double v) { S[(long long)r * kTile] = v; };
+  const double hgt = P[(long long)P0_HGT * kTile];
+  const RunCfg cfg = effective_cfg(t, hgt, a.spin_mode != 0);
+  const bool fastcol = P[(long long)P0_FAST * kTile] != 0.0;
+  double f0[F_N], f[F_N];
+  forcing_at(t, 0, c, f0);
+  const bool have_tsoil = t.tsoil && t.tsoil[c] == t.tsoil[c];
+  const double tmean = (a.spin_mode || !have_tsoil) ? column_tmean(t, c) : 0.0;
+  const int NS = nstate_rows(m, sm);
+  bool zdiff = false;
+  if (a.spin_mode) {
+    // paraminit (code.R:566-585) straight into the working rows
+    const double tair_ = f0[F_TAIR], u_ = f0[F_U], relhum_ = f0[F_RELHUM], tsoil_ = tmean, Rsw_ = f0[F_RSW];
+    auto lin2 = [](double y1, double y2, int i, int n) { double xx = 1 + (double)(i - 1) / (double)(n - 1); return y1 + (y2 - y1) * (xx - 1); };
+    double tcs = 0;
+    const double g0 = 50.0 * ((double)m / hgt) * (2.0 / m);
+    for (int i = 1; i <= m; ++i) {
+      const double tci = lin2(tsoil_, tair_, sm + i, m + sm), Ra = lin2(0.2 * Rsw_ + 20, Rsw_ + 20, i, m);
+      tcs += tci;
+      sput(L.sl(i, SL_TC), tci); sput(L.sl(i, SL_TLEAF), tci + 0.01 * Ra); sput(L.sl(i, SL_RH), relhum_); sput(L.sl(i, SL_RABS), Ra);
+      sput(L.sl(i, SL_GV), lin2(0.25, 0.32, i, m)); sput(L.sl(i, SL_GHA), lin2(0.13, 0.19, i, m)); sput(L.uz(i), ((double)i / m) * u_);
+      sput(L.gt(i), i == 1 ? 2 * g0 : g0);
+    }
+    const double gcap = g0 * (hgt / m) * 0.5;
+    sput(L.gt(m + 1), gcap); sput(S0_GTCAP, gcap); sput(S0_TCSUM, tcs);
+    for (int j = 1; j <= sm; ++j) sput(L.soiltc(j), lin2(tsoil_, tair_, sm + 1 - j, m + sm));
+    sput(S0_TABOVE, tair_); sput(S0_RELHUM, relhum_); sput(S0_TAIR, tair_); sput(S0_TSOIL, tsoil_); sput(S0_PK, 101.3); sput(S0_H, 0.0);
+    sput(S0_PSIM, 0.0); sput(S0_G, 0.0);
+    // paraminit's z is the regular grid; a snapped node (reqhgt) makes the first step's previn$z differ (code.R:573, 719)
+    for (int i = 1; i <= m; ++i) if ((i - 0.5) / m * hgt != P[(long long)L.pz(i) * kTile]) zdiff = true;
+  } else {
+    auto st = [&](int r) { return t.state[(long long)r * t.ncol + c]; };
+    sput(S0_TABOVE, st(P_TABOVE)); sput(S0_RELHUM, st(P_RELHUM)); sput(S0_TAIR, st(P_TAIR)); sput(S0_TSOIL, st(P_TSOIL)); sput(S0_PK, st(P_PK));
+    sput(S0_H, st(P_H)); sput(S0_PSIM, st(P_PSIM)); sput(S0_G, st(P_G));
+    double tcs = 0;
+    for (int i = 1; i <= m; ++i) {
+      const double tci = st(P_NSCAL + i - 1);
+      tcs += tci;
+      sput(L.sl(i, SL_TC), tci); sput(L.sl(i, SL_TLEAF), st(P_NSCAL + m + i - 1)); sput(L.uz(i), st(P_NSCAL + 2 * m + i - 1));
+      if (st(P_NSCAL + 3 * m + i - 1) != P[(long long)L.pz(i) * kTile]) zdiff = true;
+      sput(L.sl(i, SL_RH), st(P_NSCAL + 4 * m + i - 1)); sput(L.sl(i, SL_RABS), st(P_NSCAL + 5 * m + i - 1));
+      sput(L.sl(i, SL_GV), st(P_NSCAL + 6 * m + i - 1)); sput(L.sl(i, SL_GHA), st(P_NSCAL + 7 * m + i - 1));
+      sput(L.gt(i), st(P_NSCAL + 11 * m + i - 1));
+      W[(long long)L.wl(i, WL_L) * kTile] = st(P_NSCAL + 8 * m + i - 1); W[(long long)L.wl(i, WL_RSWIN) * kTile] = st(P_NSCAL + 9 * m + i - 1);
+      W[(long long)L.wl(i, WL_RLWIN) * kTile] = st(P_NSCAL + 10 * m + i - 1);
+    }
+    sput(S0_TCSUM, tcs); sput(S0_GTCAP, st(P_NSCAL + 12 * m)); sput(L.gt(m + 1), st(P_NSCAL + 12 * m));
+    for (int j = 1; j <= sm; ++j) sput(L.soiltc(j), st(P_NSCAL + 12 * m + 1 + j - 1));
+  }
+  const double reqhgt = t.cfg.reqhgt;
+  StepOut so;
+  if (a.spin_mode) {
+    const Forcing fc = {f0[F_TAIR], f0[F_RELHUM], f0[F_PK], f0[F_U], tmean, f0[F_SKYEM], f0[F_RSW], f0[F_DP], f0[F_JD], f0[F_LT],
+                        f0[F_THETA], f0[F_THETA]};
+    double Hsum = 0;
+    // previn$z of paraminit (regular grid) as an array for the general path
+    for (int i = 1; i <= t.spin_steps; ++i) {
+      const bool emit = live && i == t.spin_steps;
+      const bool gen_first = zdiff && i == 1;
+      const bool runf = live && fastcol && !gen_first;
+      const bool ok = fast_step<Mem, MS>(mem, fc, cfg, runf, emit, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
+      if (live && (!runf || !ok)) {
+        double zreg[MM + 1];
+        for (int q = 1; q <= m; ++q) zreg[q - 1] = (q - 0.5) / m * hgt;
+        general_step<MM, MS>(a, cfg, L, c, S, W, gen_first ? zreg : nullptr, 1, fc, emit, reqhgt, t.charmode, fc.tair, f0[F_RELHUM], f0[F_RSW],
+                             f0[F_SKYEM], so);
+      }
+      if (live) { Hsum += S[(long long)S0_H * kTile]; sput(S0_H, Hsum / i); }                  // previn$H <- mean(H)
+    }
+  } else {
+    const double tsoil = have_tsoil ? t.tsoil[c] : tmean;
+    double stt[6] = {0, 1e300, -1e300, 0, 1e300, -1e300};
+    int flag = 0;
+    const long long slot = (t.nsamp > 0 && t.samp_of) ? t.samp_of[c] : -1;
+    for (long long tt = t.t0; tt < t.t1; ++tt) {
+      forcing_at(t, tt, c, f);
+      const Forcing fc = {f[F_TAIR], f[F_RELHUM], f[F_PK], f[F_U], tsoil, f[F_SKYEM], f[F_RSW], f[F_DP], f[F_JD], f[F_LT], f[F_THETA],
+                          /*Q2*/ f0[F_THETA]};
+      const bool emit = live && (tt == t.t1 - 1 || (slot >= 0 && t.full));
+      const bool gen_first = zdiff && tt == t.t0;
+      const bool runf = live && fastcol && !gen_first;
+      const bool ok = fast_step<Mem, MS>(mem, fc, cfg, runf, emit, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
+      if (live && (!runf || !ok))
+        general_step<MM, MS>(a, cfg, L, c, S, W, gen_first ? t.state + (long long)(P_NSCAL + 3 * m) * t.ncol + c : nullptr, t.ncol, fc, emit,
+                             reqhgt, t.charmode, fc.tair, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
+      if (!live) continue;
+      if (so.ng > 1) flag |= 2;
+      const double* o = so.o;
+      stt[0] += o[0]; if (o[0] < stt[1]) stt[1] = o[0]; if (o[0] > stt[2]) stt[2] = o[0];
+      stt[3] += o[1]; if (o[1] < stt[4]) stt[4] = o[1]; if (o[1] > stt[5]) stt[5] = o[1];
+      if (!isfinite(o[0]) || !isfinite(o[1])) flag |= 1;
+      if (slot >= 0) {
+        if (t.series) for (int q = 0; q < 8; ++q) t.series[((tt - t.t0) * 8 + q) * t.nsamp + slot] = o[q];
+        if (t.full) abi_state_from_ws(L, P, S, W, t.soilp + (long long)S_NSCAL * t.ncol + c, t.ncol,
+                                      t.full + (tt - t.t0) * NS * t.nsamp + slot, t.nsamp);
+      }
+    }
+    if (live) {
+      if (t.stats) {
+        const double n = (double)(t.t1 - t.t0);
+        t.stats[0 * t.ncol + c] = stt[0] / n; t.stats[1 * t.ncol + c] = stt[1]; t.stats[2 * t.ncol + c] = stt[2];
+        t.stats[3 * t.ncol + c] = stt[3] / n; t.stats[4 * t.ncol + c] = stt[4]; t.stats[5 * t.ncol + c] = stt[5];
+      }
+      if (t.flags) t.flags[c] = flag;
+    }
+  }
+  if (live) abi_state_from_ws(L, P, S, W, t.soilp + (long long)S_NSCAL * t.ncol + c, t.ncol, t.state + c, t.ncol);
+}
+
+}  // namespace mc

@@ -2,6 +2,7 @@
 // One host thread + one stream per GPU, no collective, no CPU fallback.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -9,6 +10,7 @@
 #include <functional>
 #include "../../include/microclimc_b200.h"
 #include "mc_driver.cuh"
+#include "mc_fast.cuh"
 #include "mc_steady.cuh"
 
 using namespace mc;
@@ -24,6 +26,37 @@ __global__ void __launch_bounds__(kBlock) k_transient(TransientArgs a) {
   long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const bool live = c < a.ncol;
   run_column<MM, MS>(a, live ? c : a.ncol - 1, live);
+}
+// Streaming form of the transient run (mc_fast.cuh): geometry once per launch, then the time loop with TMA-staged layers.
+template <int MM, int MS>
+__global__ void __launch_bounds__(kTile) k_geom(FastArgs a) {
+  const long long c = (long long)blockIdx.x * kTile + threadIdx.x;
+  const long long cl = c < a.t.ncol ? c : a.t.ncol - 1;
+  const double hgt = a.t.vegp[(long long)V_HGT * a.t.ncol + cl];
+  geom_column<MM, MS>(a, effective_cfg(a.t, hgt, a.spin_mode != 0), c, cl);
+}
+constexpr int kFastSmem = 2 * kStageRows * kTile * 8 + 64;
+template <int MM, int MS>
+__global__ void __launch_bounds__(kTile, 4) k_transient_fast(FastArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* buf = reinterpret_cast<double*>(smem_raw);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + 2 * kStageRows * kTile * 8);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1); mbar_init(bar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_proxy_async();
+  __syncthreads();
+  const long long c = (long long)blockIdx.x * kTile + threadIdx.x;
+  const bool live = c < a.t.ncol;
+  FastLayout L{a.t.m, a.t.sm};
+  PipeMem mem;
+  mem.L = L;
+  mem.Pt = a.P + (long long)blockIdx.x * L.nP() * kTile; mem.St = a.S + (long long)blockIdx.x * L.nS() * kTile;
+  mem.Wt = a.W + (long long)blockIdx.x * L.nW() * kTile;
+  mem.P = mem.Pt + threadIdx.x; mem.S = const_cast<double*>(mem.St) + threadIdx.x; mem.W = const_cast<double*>(mem.Wt) + threadIdx.x;
+  mem.buf = buf; mem.bar = bar; mem.lane = threadIdx.x; mem.k = 0; mem.cur = buf;
+  fast_run_column<PipeMem, MM, MS>(a, mem, live ? c : a.t.ncol - 1, live);
 }
 template <int MM, int MS>
 __global__ void __launch_bounds__(kBlock) k_onestep(OneStepArgs a) {
@@ -87,7 +120,8 @@ struct Shard {
   int dev = 0; long long c0 = 0, nc = 0;
   cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
   DBuf vegp, soilp, lat, lon, state, state_bak, fscale, foffset, forcing, season, tsoil, stats, series, full, samp_of, flags,
-      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart;
+      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, fP, fS, fW;
+  bool fast_attr = false;
   bool has_pert = false, has_season = false, has_state = false;
   float ms = 0; long long launches = 0;
   // replay info for mc_bench_resident
@@ -155,12 +189,36 @@ template <class F> int dispatch_ms(int m, int sm, F&& f) {
 }
 inline unsigned nblocks(long long n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
+// The streaming kernels cover time-invariant PAI and the small template (m <= 20, sm <= 10); everything else, or
+// MC_FORCE_GENERAL=1 in the environment (A/B tests), runs the general one-column-per-thread kernel.
+bool fast_eligible(const TransientArgs& a) {
+  const char* e = getenv("MC_FORCE_GENERAL");
+  return !a.season && a.m <= 20 && a.m > kNG && a.sm <= 10 && !(e && e[0] == '1');
+}
 int launch_transient(Shard& s, const TransientArgs& a) {
-  return dispatch_ms(a.m, a.sm, [&](auto MM, auto MS) {
-    k_transient<decltype(MM)::value, decltype(MS)::value><<<nblocks(a.ncol), kBlock, 0, s.st>>>(a);
-    s.launches++;
-    return 0;
-  });
+  if (!fast_eligible(a))
+    return dispatch_ms(a.m, a.sm, [&](auto MM, auto MS) {
+      k_transient<decltype(MM)::value, decltype(MS)::value><<<nblocks(a.ncol), kBlock, 0, s.st>>>(a);
+      s.launches++;
+      return 0;
+    });
+  const FastLayout L{a.m, a.sm};
+  const long long ntile = (a.ncol + kTile - 1) / kTile;
+  CU(s.fP.need(sizeof(double) * ntile * L.nP() * kTile)); CU(s.fS.need(sizeof(double) * ntile * L.nS() * kTile));
+  CU(s.fW.need(sizeof(double) * ntile * L.nW() * kTile));
+  if (!s.fast_attr) {
+    CU(cudaFuncSetAttribute(k_transient_fast<20, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
+    s.fast_attr = true;
+  }
+  FastArgs fa{a, s.fP.as<double>(), s.fS.as<double>(), s.fW.as<double>(), 0};
+  for (int spin = 1; spin >= 0; --spin) {
+    if (spin ? a.spin_steps <= 0 : a.t1 <= a.t0) continue;
+    fa.spin_mode = spin;
+    k_geom<20, 10><<<(unsigned)ntile, kTile, 0, s.st>>>(fa);
+    k_transient_fast<20, 10><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
+    s.launches += 2;
+  }
+  return 0;
 }
 int launch_steady(Shard& s, const SteadyArgs& a, int nchunk) {
   dim3 grid(nblocks(a.ncol), nchunk);
@@ -222,7 +280,7 @@ void mc_destroy(mc_ctx* ctx) {
     cudaSetDevice(s.dev);
     DBuf* bufs[] = {&s.vegp, &s.soilp, &s.lat, &s.lon, &s.state, &s.state_bak, &s.fscale, &s.foffset, &s.forcing, &s.season, &s.tsoil,
                     &s.stats, &s.series, &s.full, &s.samp_of, &s.flags, &s.args6, &s.clim8, &s.theta, &s.thetap, &s.nmerged,
-                    &s.sclim, &s.snmr, &s.sseason, &s.sout, &s.spart};
+                    &s.sclim, &s.snmr, &s.sseason, &s.sout, &s.spart, &s.fP, &s.fS, &s.fW};
     for (DBuf* b : bufs) b->release();
     if (s.e0) cudaEventDestroy(s.e0);
     if (s.e1) cudaEventDestroy(s.e1);

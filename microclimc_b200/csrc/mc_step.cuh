@@ -58,6 +58,9 @@ struct Column {
   double mref, s_m, trd_m, kden, emv, trlw_sum;
   double zla[MM + 2], zthp[MM + 2];
   bool zprev_is_z;
+  // true only when every thread of the block runs step() together (general kernel): block-wide rendezvous per layer keeps the
+  // warps on the same instructions (I-cache). Must stay false when single threads call step() (streaming kernel's fallback).
+  bool cta_sync = false;
   // soil conductance cache (soilk depends on theta only)
   double th_cache, ksoil[MS + 2], cdsoil[MS + 2];
   // grass-reference constants of windcanopy's edge profile (code.R:286)
@@ -417,7 +420,7 @@ struct Column {
       gtn[m] = (g > gfree) ? g : gfree;
     }
     for (int i = m - 1; i >= 1; --i) {
-      MC_CTA_SYNC();
+      if (cta_sync) MC_CTA_SYNC();
       bool fast = zi_[i] != 0.0;
       double zt = z[i + 1] - z[i];
       double zi = z[i + 1] + 0.5 * zt, zo = z[i + 1] - 0.5 * zt;
@@ -463,7 +466,7 @@ struct Column {
     double aRsw1 = 0, ref_m = 0;
     double Rabsn[MM + 2], gvn[MM + 2], ghan[MM + 2];
     for (int i = 1; i <= m; ++i) {
-      MC_CTA_SYNC();
+      if (cta_sync) MC_CTA_SYNC();
       double ref = pLAI[i] * refls + (1 - pLAI[i]) * refw;
       double pc = PAIg[m + 1 - i];
       double sunl = psunlit_k(pc, sa, K, clump);
@@ -498,7 +501,7 @@ struct Column {
     const double eamn = (relhumn / 100) * tet_tcan;
     double tnl[MM + 2], tleafn[MM + 2], eal[MM + 2];
     for (int i = 1; i <= m; ++i) {
-      MC_CTA_SYNC();
+      if (cta_sync) MC_CTA_SYNC();
       const double ptc = tc[i], ptl = tleaf[i];
       const double zp = zprev[i], zth = zthp[i], zl = zla[i];
       const double zrf = (hgt + 2) - zp;
@@ -592,7 +595,7 @@ struct Column {
       L[i] = (aX + bX * dTL) * PAI[i];                                                         // code.R:880 (Q1)
     }
     // ---- soil conductances and surface forcing (code.R:789-811) ----
-    MC_CTA_SYNC();
+    if (cta_sync) MC_CTA_SYNC();
     soilk(timestep, fc.theta);
     double TT[MM + 2];
     { double s = 0; for (int i = 1; i <= m; ++i) { s += (phair(tc[i], ppk) / gtn[i]) * (z[i] - (i > 1 ? z[i - 1] : 0.0)); TT[i] = s; } }
@@ -721,7 +724,7 @@ struct Column {
       }
     }
     // ---- limits, humidity, fluxes (code.R:868-897) ----
-    MC_CTA_SYNC();
+    if (cta_sync) MC_CTA_SYNC();
     if (tnsoil[1] < tfrost) tnsoil[1] = tfrost;
     if (tnsoil[1] > tairn + 30) tnsoil[1] = tairn + 30;
     double Lt = 0;
@@ -747,7 +750,7 @@ struct Column {
     const double Hn = net - Gn - Lt;
     // ---- commit the new state ----
     for (int i = 1; i <= m; ++i) {
-      MC_CTA_SYNC();
+      if (cta_sync) MC_CTA_SYNC();
       double tn = tnn[i];
       double es = tetens(tn);
       double r = (ean2[i] / es) * 100;

@@ -4,7 +4,9 @@
 #include <cmath>
 #include <cstdint>
 #include "../../microclimc_b200/csrc/mc_driver.cuh"
+#include "../../microclimc_b200/csrc/mc_fast.cuh"
 #include "../../microclimc_b200/csrc/mc_steady.cuh"
+#include <vector>
 
 using namespace mc;
 static RunCfg mkcfg(const double* c) {
@@ -31,6 +33,45 @@ extern "C" int dbg_run_transient(int64_t ncol, int m, int sm, int64_t T, const d
   delete[] samp_of;
   return 0;
 }
+// Streaming form (mc_fast.cuh) with the direct-memory accessor: geometry pass, then every column through
+// fast_run_column — spin-up launch first, then the hourly loop, exactly as mc_lib.cu sequences the two kernels.
+extern "C" int dbg_run_transient_fast(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* forcing,
+                      const double* fscale, const double* foffset, const double* tsoil_in, const double* lat,
+                      const double* lon, const double* cfg, const double* pai_season, double* state, double* series,
+                      const int64_t* samp_idx, int64_t nsamp, double* stats, double* fullseries, int32_t* flags, int) {
+  if (pai_season || m > 20 || m <= kNG || sm > 10) return -9;
+  TransientArgs t{};
+  t.ncol = ncol; t.m = m; t.sm = sm; t.T = T; t.t0 = 0; t.t1 = T; t.vegp = vegp; t.soilp = soilp; t.lat = lat; t.lon = lon;
+  t.forcing = forcing; t.fscale = fscale; t.foffset = foffset; t.tsoil = tsoil_in; t.season = nullptr; t.state = state;
+  t.series = series; t.full = fullseries; t.nsamp = nsamp; t.stats = stats; t.flags = flags; t.cfg = mkcfg(cfg);
+  t.spin_steps = (int)cfg[11]; t.charmode = (int)cfg[12];
+  std::vector<long long> samp_of(ncol, -1);
+  for (int64_t j = 0; j < nsamp; ++j) samp_of[samp_idx[j]] = j;
+  t.samp_of = samp_of.data();
+  FastLayout L{m, sm};
+  const long long ntile = (ncol + kTile - 1) / kTile;
+  std::vector<double> P(ntile * L.nP() * kTile), S(ntile * L.nS() * kTile), W(ntile * L.nW() * kTile);
+  FastArgs a{t, P.data(), S.data(), W.data(), 0};
+  for (int spin = 1; spin >= 0; --spin) {
+    if (spin ? t.spin_steps <= 0 : T <= 0) continue;
+    a.spin_mode = spin;
+    for (long long c = 0; c < ntile * kTile; ++c) {
+      const long long cl = c < ncol ? c : ncol - 1;
+      geom_column<20, 10>(a, effective_cfg(t, vegp[(long long)V_HGT * ncol + cl], spin != 0), c, cl);
+    }
+    for (long long c = 0; c < ncol; ++c) {
+      DirectMem mem;
+      mem.L = L;
+      mem.P = P.data() + (c / kTile) * L.nP() * kTile + (c % kTile);
+      mem.S = S.data() + (c / kTile) * L.nS() * kTile + (c % kTile);
+      mem.W = W.data() + (c / kTile) * L.nW() * kTile + (c % kTile);
+      mem.ia = mem.ib = 1;
+      fast_run_column<DirectMem, 20, 10>(a, mem, c, true);
+    }
+  }
+  return 0;
+}
+extern "C" long long dbg_general_steps(int reset) { long long v = g_mc_general_steps; if (reset) g_mc_general_steps = 0; return v; }
 extern "C" int dbg_runonestep(int64_t ncol, int m, int sm, const double* vegp, const double* soilp, const double* climvars,
                    const double* lat, const double* lon, const double* cfg, double jd, double lt, const double* theta,
                    const double* thetap, double* state, int* nmerged) {
