@@ -33,7 +33,7 @@ enum { P0_HGT, P0_LA, P0_LNREF, P0_LZU, P0_LZUH, P0_LZOH, P0_LNHD, P0_D, P0_GLNH
        P0_A0CAP, P0_GXC0, P0_CGCAP, P0_RDZCAP, P0_A0G, P0_GXG1, P0_CGG, P0_RZG,
        P0_X, P0_KDEN, P0_CLUMP, P0_REFG, P0_SM, P0_TRDM, P0_EMV, P0_VEGEM, P0_TRLWSUM, P0_REFM, P0_LAT, P0_LON,
        P0_GSMAX, P0_Q50, P0_LWD, P0_SMAX, P0_SOILB, P0_PSIE, P0_SKA, P0_SKB, P0_SKC, P0_SKAD, P0_CVDRY, P0_Z1,
-       P0_SELG, P0_SELH, P0_SELS, P0_ZABOVE, P0_FAST, P0_NFIX };          // then DZK[sm], DZC[sm], Z[m]
+       P0_SELG, P0_SELH, P0_SELS, P0_ZABOVE, P0_FAST, P0_NFIX };          // then 1/DZK[sm], DZC[sm], Z[m]
 enum { PA_A0I, PA_A0O, PA_EX1, PA_EX2, PA_GLO, PA_GLI, PA_EDO, PA_EDI, PA_GX0, PA_GX1, PA_CG, PA_RDZ, PA_DZ, PA_N };
 enum { PB_REF, PB_PC, PB_SPC, PB_SGC, PB_TRDC, PB_TRDG, PB_TRLW, PB_PAI, PB_IZTH, PB_IZL, PB_IZRF, PB_IZP, PB_MAC, PB_MZ,
        PB_VDEN, PB_DZ, PB_N };
@@ -105,7 +105,7 @@ MC_HD void geom_column(const FastArgs& a, const RunCfg& cfg, long long c, long l
       const double dzk = (j < sm) ? (col.zs[j + 1] - col.zs[j]) : (col.zs[sm] - col.zs[sm - 1]);
       const double zlo = (j > 1) ? col.zs[j - 1] : 0.0;
       const double zhi = (j < sm) ? col.zs[j + 1] : (col.zs[sm] + (col.zs[sm] - col.zs[sm - 1]));
-      put(P0_NFIX + (j - 1), dzk); put(P0_NFIX + sm + (j - 1), zhi - zlo);
+      put(P0_NFIX + (j - 1), 1 / dzk); put(P0_NFIX + sm + (j - 1), zhi - zlo);
     }
   }
   put(P0_Z1, col.z[1]); put(P0_SELG, (double)col.selG);
@@ -289,6 +289,54 @@ MC_HD double wc_fast(double uh, double a, double ex, double gl, double ed, doubl
   return uzv;
 }
 
+// 1.41 * gforcedfree(d, u, tc, dtc, pk, dtmin = 1) (microctools; mc_phys.cuh gforcedfree) with the reciprocals shared:
+// iTk = 1/(tc+273.15), c101 = 101.3/pk, ph = phair(tc, pk), id = 1/d, d3 = 9.81*d^3.  Pr = nu/Dh = 13.3/18.9 exactly.
+MC_HD double gha_fast(double d, double id, double d3, double u, double Tk, double iTk, double ph, double dtc, double c101) {
+  const double kPr = 0.7037037037037037, kCbrtPr = 0.8894672162406483;
+  const double sc = pow175(Tk * (1 / 273.15)) * c101;
+  const double Dh = 18.9e-6 * sc, nu = 13.3e-6 * sc;
+  const double inu = frcp(nu);
+  double adt = fabs(dtc);
+  if (adt < 1.0) adt = 1.0;
+  const double Re = (u * d) * inu;
+  const double Gr = (d3 * adt) * iTk * (inu * inu);
+  const double gforced = (0.664 * Dh * ph * fsqrt(Re) * kCbrtPr) * id;
+  const double gfree = (0.54 * Dh * ph * qroot(Gr * kPr)) * id;
+  return 1.41 * ((gforced > gfree) ? gforced : gfree);
+}
+
+// Thomas (code.R:94-125; same recurrences as Column::thomas) with one reciprocal per eliminated node.
+MC_HD void thomas_f(int N, double* tcv, double tmsoil, double tairv, const double* k, const double* cdv, double f, const double* Xv,
+                    double* tn, double* cc, double* dd) {
+  const double g = 1 - f;
+  tn[N + 2] = tmsoil; tn[1] = tairv;
+  for (int xx = 2; xx <= N + 1; ++xx) tcv[xx] = tcv[xx] + g * Xv[xx - 1];
+  for (int xx = 2; xx <= N + 1; ++xx)
+    dd[xx] = g * k[xx - 1] * tcv[xx - 1] + (cdv[xx - 1] - g * (k[xx] + k[xx - 1])) * tcv[xx] + g * k[xx] * tcv[xx + 1];
+  dd[2] = dd[2] + k[1] * tn[1] * f;
+  dd[N + 1] = dd[N + 1] + k[N + 1] * f * tn[N + 2];
+  double b = f * (k[2] + k[1]) + cdv[1];
+  for (int i = 2; i <= N; ++i) {
+    const double ib = frcp(b);
+    const double a1 = -k[i] * f;
+    const double ci = a1 * ib;
+    cc[i] = ci;
+    dd[i] = dd[i] * ib;
+    b = (f * (k[i + 1] + k[i]) + cdv[i]) - a1 * ci;
+    dd[i + 1] = dd[i + 1] - a1 * dd[i];
+  }
+  tn[N + 1] = fdiv(dd[N + 1], b);
+  for (int i = N; i >= 2; --i) tn[i] = dd[i] - cc[i] * tn[i + 1];
+  for (int xx = 2; xx <= N + 1; ++xx) {
+    const double xmn = dmin(dmin(tcv[xx], tcv[xx - 1]), tcv[xx + 1]);
+    const double xmx = dmax(dmax(tcv[xx], tcv[xx - 1]), tcv[xx + 1]);
+    double v = tn[xx];
+    if (v < xmn) v = xmn;
+    if (v > xmx) v = xmx;
+    tn[xx] = v + f * Xv[xx - 1];
+  }
+}
+
 struct StepOut { double o[8]; int ng; };
 
 // One time step of one column in streaming form.  `run` false: the thread only keeps the block's barriers company
@@ -437,13 +485,16 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
   const double esoil = soilrh(fc.theta, p0(P0_SOILB), -p0(P0_PSIE), p0(P0_SMAX), ps1) * satvap(ps1);     // Q7
   const double eamn = (relhumn / 100) * tet_tcan;
   const double gsmax = p0(P0_GSMAX), q50 = p0(P0_Q50), lwd = p0(P0_LWD);
+  const double ilwd = 1 / lwd, lwd3 = 9.81 * (lwd * lwd * lwd), c101 = 101.3 / pkn, ippk = 1 / ppk;
+  const int selHb = (int)p0(P0_SELH);
   // soilk (microctools; Column::soilk) for this step's theta
   double cd1, lam, Cv;
+  const double i2ts = 1 / (2 * timestep);
   {
     const double ct = p0(P0_SKC) * fc.theta;
     lam = p0(P0_SKA) + p0(P0_SKB) * fc.theta - p0(P0_SKAD) * exp(-((ct * ct) * (ct * ct)));
     Cv = (p0(P0_CVDRY) + 4.18 * fc.theta) * 1e6;
-    cd1 = (Cv * p0(P0_NFIX + sm)) / (2 * timestep);
+    cd1 = (Cv * p0(P0_NFIX + sm)) * i2ts;
   }
   // ---------------- sweep B: leafabs + leaftemp, bottom -> top, with the merged-layer sums ----------------
   double acc2 = 0, TT = 0, Lt = 0, stl = 0, ssw = 0;
@@ -467,16 +518,19 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
       const double trbc = (sa > 0) ? clumptr(fexp(-(mem.b_p(PB_SPC) * K)), clump) : clumptr(0.0, clump);
       const double trbg = (sa > 0) ? clumptr(fexp(-(mem.b_p(PB_SGC) * K)), clump) : clumptr(0.0, clump);
       const double sunl = (sa > 0) ? clumptr(fexp(-K * pc), clump) : clumptr(0.0, clump);
-      const double aR = omr * (Rsw * (dp * mem.b_p(PB_TRDC) + (1 - dp) * trbc));
-      const double aGr = omr * (aG0 * (dp * mem.b_p(PB_TRDG) + (1 - dp) * trbg));
-      aRsw = sunl * mul * aR + (1 - sunl) * aR + aGr;
-      rsw = aRsw / omr;
+      // code.R:43-46 per unit (1 - ref): Rswin = aRsw / (1 - ref) (code.R:895) is formed first, aRsw = (1 - ref) * Rswin
+      const double xR = Rsw * (dp * mem.b_p(PB_TRDC) + (1 - dp) * trbc);
+      const double xG = aG0 * (dp * mem.b_p(PB_TRDG) + (1 - dp) * trbg);
+      rsw = sunl * mul * xR + (1 - sunl) * xR + xG;
+      aRsw = omr * rsw;
     }
     const double trl = mem.b_p(PB_TRLW);
     const double aRlw = emv * (trl * skyem * lwout + (1 - trl) * emv * lwout);
     const double Rabsn = aRsw + aRlw;
-    const double gvn = layercond(rsw, gsmax, q50);
-    const double ghan = 1.41 * gforcedfree(lwd, uzn, ptc, ptl - ptc, pkn, 1.0);
+    const double Qa = 4.6 * rsw;
+    const double gvn = fdiv(gsmax * Qa, Qa + q50);                            // layercond
+    const double Tkc = ptc + 273.15, iTkc = frcp(Tkc);
+    const double ghan = gha_fast(lwd, ilwd, lwd3, uzn, Tkc, iTkc, (cpk * 273.15) * iTkc, ptl - ptc, c101);
     // leaftemp (code.R:378-512)
     const double rg = mem.b_w(WL_RG);
     const double gtt = frcp(rgcap + mem.b_w(WL_SFX));
@@ -484,13 +538,16 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     const double gtt2 = frcp(acc2);
     const double izl = mem.b_p(PB_IZL), izrf = mem.b_p(PB_IZRF), izp = mem.b_p(PB_IZP), izth = mem.b_p(PB_IZTH), PAIi = mem.b_p(PB_PAI);
     const double PAIm = 2 * PAIi * izth;
-    const double esj = tetens(ptc);
-    const double eaj = (mem.b_s(SL_RH) / 100) * esj;
+    const double esj = 0.6108 * fexp((17.27 * ptc) * frcp(ptc + 237.3));      // Tetens, code.R:410
+    const double eaj = (mem.b_s(SL_RH) * 0.01) * esj;
     const double estl = satvap(ptl);
-    const double delta = 4098 * tetens(ptl) / sq(ptl + 237.3);
+    const double r237l = frcp(ptl + 237.3);
+    const double tetl = 0.6108 * fexp((17.27 * ptl) * r237l);
+    const double delta = (4098 * tetl) * (r237l * r237l);                      // code.R:415
     const double gvo = mem.b_s(SL_GV), ghao = mem.b_s(SL_GHA);
-    const double gvp = 1 / ((1 / gvo) + (1 / ghao));
-    const double gvc = 1 / ((1 / gvn) + (1 / ghan));
+    // 1/(1/a + 1/b) = a*b/(a+b): one division; a = 0 (closed stomata at night) still gives 0
+    const double gvp = fdiv(gvo * ghao, gvo + ghao);
+    const double gvc = fdiv(gvn * ghan, gvn + ghan);
     const double gvm = 0.5 * gvp + 0.5 * gvc;
     const double gham = 0.5 * ghan + 0.5 * ghao;
     const double g1 = gtt * izrf, g2 = gtt2 * izp, g3 = gvm * izl, g3h = gham * izl;
@@ -510,7 +567,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
       be = (0.25 * gvm * delta) * ibtm;
     }
     const double cp = cpair(ptc);
-    const double phc = phair_c(cppk, ptc);
+    const double phc = (cppk * 273.15) * iTkc;
     double aL, bL;
     if (timestep * dmax(dmax(g1, g3h), g2) > 1) {
       const double K1 = gtt * cp, K2 = gtt2 * cp, K3 = gham * cp;
@@ -552,8 +609,8 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     const double es = tetens(tnl);
     if (ean > es) ean = es;
     if (ean < eamn) ean = eamn;
-    const double al = log(ean / 0.6108);
-    const double Tdew = -(237.3 * al) / (al - 17.27);
+    const double al = log(ean * (1 / 0.6108));
+    const double Tdew = -fdiv(237.3 * al, al - 17.27);
     double dT1 = -(ptl + dTL - Tdew);
     if (dT1 < 0) dT1 = 0;
     const double Lc = lambda_l * gvm * (tetens(tlf) - ean) * impk;
@@ -569,15 +626,16 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     const double Lp = (aX + bX * dTL) * PAIi;                                   // code.R:880 (Q1)
     if (i == 1) {                                                               // soil-surface forcing (code.R:799-811)
       cp1 = cp;
-      const double a1 = (1 - refg) * (aRsw / cd1);
+      const double icd1 = frcp(cd1);
+      const double a1 = (1 - refg) * (aRsw * icd1);
       if (esoil - ean > 0) {
-        const double mm = ((-42.575 * ptc + 44994) * phc * p0(P0_Z1)) / pkn;
+        const double mm = fdiv((-42.575 * ptc + 44994) * phc * p0(P0_Z1), pkn);
         const double dl = 4098 * tetens(ps1) / sq(ps1 + 237.3);
-        const double btm = 1 + 0.5 * (mm / cd1) * dl;
-        Xs = (a1 - (mm / cd1) * (esoil - ean)) / btm;
+        const double btm = 1 + 0.5 * (mm * icd1) * dl;
+        Xs = fdiv(a1 - (mm * icd1) * (esoil - ean), btm);
       } else Xs = a1;
       const double sgn = Xs < 0 ? -1.0 : 1.0;
-      const double Xsmx = ((1 - refg) * aRsw) / (ghan * cp) + (tnl - ps1);
+      const double Xsmx = fdiv((1 - refg) * aRsw, ghan * cp) + (tnl - ps1);
       if (fabs(Xs) > fabs(Xsmx)) Xs = Xsmx;
       Xs = fabs(Xs) * sgn;
     }
@@ -586,8 +644,8 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
       const double wi = mem.b_p(PB_DZ), phz = mem.b_w(WL_PHZ), rn = frcp(gtn);
       TT += phz * rn;                                                           // cumsum((ph/gt) * dz), code.R:797
       oR += rn; oC += phz; open = true;
-      ow += wi; otc += wi * ptc; oVo += wi * (eaj / ppk); oea += wi * ean; oX += wi * (tnl - ptc); ovd += wi * mem.b_p(PB_VDEN);
-      if (timestep / oR <= oC) {
+      ow += wi; otc += wi * ptc; oVo += wi * (eaj * ippk); oea += wi * ean; oX += wi * (tnl - ptc); ovd += wi * mem.b_p(PB_VDEN);
+      if (timestep <= oC * oR) {                                               // timestep / sum(1/gt) <= sum(ph*zth)
         if (ng < kNG + 1) {
           ++ng;
           glo[ng] = olo; ghi[ng] = i; gw[ng] = ow; gtc[ng] = otc; gVo[ng] = oVo; gea[ng] = oea; gX[ng] = oX; gvd[ng] = ovd;
@@ -601,7 +659,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     wput(i, WL_TT, TT); wput(i, WL_EAL, ean);
     if (emit) { wput(i, WL_L, Lp); wput(i, WL_RSWIN, rsw); }
     Lt += Lp; stl += tleafn; ssw += rsw;
-    if ((int)p0(P0_SELH) == i) { hv[1] = tleafn; hv[3] = rsw; hv[5] = Lp; }
+    if (selHb == i) { hv[1] = tleafn; hv[3] = rsw; hv[5] = Lp; }
   }
   // ---------------- heat and vapour exchange on the merged nodes (code.R:813-867) ----------------
   double tnsoil[MS + 2];
@@ -644,12 +702,12 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
       }
       k[1] = lgt[mg + 1] * cpair(tabove);
       for (int j = 1; j <= sm; ++j) {
-        k[mg + 1 + j] = lam / p0(P0_NFIX + (j - 1)); cdv[mg + j] = (Cv * p0(P0_NFIX + sm + (j - 1))) / (2 * timestep);
+        k[mg + 1 + j] = lam * p0(P0_NFIX + (j - 1)); cdv[mg + j] = (Cv * p0(P0_NFIX + sm + (j - 1))) * i2ts;
         XX[mg + j] = 0; tc2[1 + mg + j] = s0(L.soiltc(j));
       }
       XX[mg + 1] = Xs;
       tc2[1] = tabove; tc2[N + 2] = tsoilp;
-      Column<4, kNG + MS>::thomas(N, tc2, fc.tsoil, tcan, k, cdv, cfg.n, XX, tn2, cc, dd);
+      thomas_f(N, tc2, fc.tsoil, tcan, k, cdv, cfg.n, XX, tn2, cc, dd);
       for (int j = 1; j <= sm; ++j) tnsoil[j] = tn2[mg + 1 + j];
       // tnair = rev(tn2[1:(mg+2)]) = (soil 1, air bottom..top, tcan)
       nn = mg + 2;
@@ -674,7 +732,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
           double vf = (lea[g] / pkn) - lVo[g]; if (vf < 0) vf = 0;
           vX[g] = vf;                                                            // Q6: not reversed
         }
-        Column<4, kNG + MS>::thomas(mg, vt, Vsoil, Vair, vk, vcd, cfg.n, vX, vn, cc, dd);
+        thomas_f(mg, vt, Vsoil, Vair, vk, vcd, cfg.n, vX, vn, cc, dd);
         for (int g = 1; g <= mg + 2; ++g) Ye[g] = vn[mg + 3 - g];                   // mole fractions; scaled by pk after the interpolation
       }
       T2[1] = 0; for (int g = 1; g <= mg; ++g) T2[g + 1] = lTT[g];
@@ -683,12 +741,12 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
       // canopy air in equilibrium with the air above: soil solve with one lumped canopy conductance (code.R:854-867)
       k[1] = (1 / cs) * cpair(tabove);
       for (int j = 1; j <= sm; ++j) {
-        k[1 + j] = lam / p0(P0_NFIX + (j - 1)); cdv[j] = (Cv * p0(P0_NFIX + sm + (j - 1))) / (2 * timestep);
+        k[1 + j] = lam * p0(P0_NFIX + (j - 1)); cdv[j] = (Cv * p0(P0_NFIX + sm + (j - 1))) * i2ts;
         XX[j] = 0; tc2[1 + j] = s0(L.soiltc(j));
       }
       XX[1] = Xs;
       tc2[1] = tabove; tc2[sm + 2] = tsoilp;
-      Column<4, kNG + MS>::thomas(sm, tc2, fc.tsoil, tcan, k, cdv, cfg.n, XX, tn2, cc, dd);
+      thomas_f(sm, tc2, fc.tsoil, tcan, k, cdv, cfg.n, XX, tn2, cc, dd);
       for (int j = 1; j <= sm; ++j) tnsoil[j] = tn2[1 + j];
       T2[1] = 0; T2[2] = TX; Yt[1] = tnsoil[1]; Yt[2] = tcan; Ye[1] = esoil; Ye[2] = eamn;       // eair = (relhum/100)*tetens(tcan)
     }
@@ -720,10 +778,16 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
         ea2 = (Ye[a] + (Ye[b] - Ye[a]) * w) * pkn;                               // ea <- vn * pk (code.R:852)
       }
     }
-    double r = fdiv(ea2, tetens(tnn)) * 100;
+    double r = fdiv(ea2, 0.6108 * fexp((17.27 * tnn) * frcp(tnn + 237.3))) * 100;
     if (r > 100) r = 100;
     if (r < 0) r = 0;
-    const double tdws = dewpoint(ean, tnn);                                    // Q12
+    double tdws;                                                               // dewpoint(tln$ea, tn), Q12
+    {
+      const bool ice = tnn < 0;
+      const double ie0 = ice ? (1 / (610.78 / 1000)) : (1 / (611.2 / 1000));
+      const double iLv = ice ? (461.5 / 2.834e6) : fdiv(461.5, 2.501e6 - 2340 * tnn);
+      tdws = frcp(1 / 273.15 - iLv * log(ean * ie0)) - 273.15;
+    }
     const double tn = (tnn < tdws) ? tdws : tnn;
     const double lwt = kSb * pow4(tn + 273.15);
     const double Rlwin = trlw_sum * skyem * lwt + (1 - trlw_sum) * emv * lwt;
