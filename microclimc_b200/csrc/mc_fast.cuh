@@ -197,6 +197,18 @@ MC_D void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long lon
                "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// streamed rows (geometry, state) are read once per step with a reuse distance far beyond L2: mark them evict-first so
+// that the short-lived work rows and the threads' local scratch stay resident
+MC_D unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+MC_D void bulk_g2s_stream(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
 MC_D void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 struct PipeMem {
@@ -208,21 +220,22 @@ struct PipeMem {
   int lane;                                    // threadIdx.x
   unsigned k;                                  // stages issued so far (uniform over the block)
   const double* cur;                           // current stage buffer + lane
+  unsigned long long pol;                      // L2 evict-first policy for the streamed rows
   MC_D void issueA(int i, unsigned kk) {
     double* b = buf + (kk & 1) * (kStageRows * kTile);
     unsigned long long* mb = bar + (kk & 1);
     const unsigned bytes = (PA_N + (i > 1 ? 1 : 0) + 1) * kTile * 8;
     mbar_expect_tx(mb, bytes);
-    bulk_g2s(b, Pt + (long long)L.pa(i, 0) * kTile, PA_N * kTile * 8, mb);
-    if (i > 1) bulk_g2s(b + PA_N * kTile, St + (long long)L.sl(i - 1, SL_TC) * kTile, kTile * 8, mb);
-    bulk_g2s(b + (PA_N + 1) * kTile, St + (long long)L.gt(i) * kTile, kTile * 8, mb);
+    bulk_g2s_stream(b, Pt + (long long)L.pa(i, 0) * kTile, PA_N * kTile * 8, mb, pol);
+    if (i > 1) bulk_g2s_stream(b + PA_N * kTile, St + (long long)L.sl(i - 1, SL_TC) * kTile, kTile * 8, mb, pol);
+    bulk_g2s_stream(b + (PA_N + 1) * kTile, St + (long long)L.gt(i) * kTile, kTile * 8, mb, pol);
   }
   MC_D void issueB(int i, unsigned kk) {
     double* b = buf + (kk & 1) * (kStageRows * kTile);
     unsigned long long* mb = bar + (kk & 1);
     mbar_expect_tx(mb, kStageRows * kTile * 8);
-    bulk_g2s(b, Pt + (long long)L.pb(i, 0) * kTile, PB_N * kTile * 8, mb);
-    bulk_g2s(b + PB_N * kTile, St + (long long)L.sl(i, 0) * kTile, SL_N * kTile * 8, mb);
+    bulk_g2s_stream(b, Pt + (long long)L.pb(i, 0) * kTile, PB_N * kTile * 8, mb, pol);
+    bulk_g2s_stream(b + PB_N * kTile, St + (long long)L.sl(i, 0) * kTile, SL_N * kTile * 8, mb, pol);
     bulk_g2s(b + (PB_N + SL_N) * kTile, Wt + (long long)L.wl(i, 0) * kTile, kWLiveB * kTile * 8, mb);
   }
   MC_D void issueC(int i, unsigned kk) {
@@ -348,11 +361,11 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
   const FastLayout L = mem.L;
   const int m = L.m, sm = L.sm;
   const double* P = mem.P; double* S = mem.S; double* W = mem.W;
-  auto p0 = [&](int r) { return P[(long long)r * kTile]; };
-  auto s0 = [&](int r) { return S[(long long)r * kTile]; };
-  auto sput = [&](int r, double v) { S[(long long)r * kTile] = v; };
-  auto wput = [&](int i, int r, double v) { W[(long long)L.wl(i, r) * kTile] = v; };
-  auto wget = [&](int i, int r) { return W[(long long)L.wl(i, r) * kTile]; };
+  auto p0 = [=](int r) { return P[(long long)r * kTile]; };
+  auto s0 = [=](int r) { return S[(long long)r * kTile]; };
+  auto sput = [=](int r, double v) { S[(long long)r * kTile] = v; };
+  auto wput = [=](int i, int r, double v) { W[(long long)L.wl(i, r) * kTile] = v; };
+  auto wget = [=](int i, int r) { return W[(long long)L.wl(i, r) * kTile]; };
   mem.step_begin();
   const double timestep = cfg.timestep;
   // ---------------- scalars of the step (code.R:700-745) ----------------
@@ -427,7 +440,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
   const int half = (int)nearbyint(m / 2.0);
   for (int i = m; i >= 1; --i) {
     mem.stageA(i);
-    if (!run) continue;
+    if (!run || (cfg.dbg & 1)) continue;
     const double tcl = (i > 1) ? mem.a_tcl() : ps1;
     const double ai = mem.a_p(PA_A0I) * sqphi;
     double uzn;
@@ -499,7 +512,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
   // ---------------- sweep B: leafabs + leaftemp, bottom -> top, with the merged-layer sums ----------------
   double acc2 = 0, TT = 0, Lt = 0, stl = 0, ssw = 0;
   double Xs = 0, cp1 = 0;
-  double hv[6] = {0, 0, 0, 0, 0, 0};
+  double hv0 = 0, hv1 = 0, hv2 = 0, hv3 = 0, hv4 = 0, hv5 = 0;
   // layermerge / layeraverage bookkeeping (code.R:772, 814): closed groups 1..ng and the open one
   int ng = 0, glo[kNG + 2], ghi[kNG + 2], olo = 1;
   double gw[kNG + 2], gtc[kNG + 2], gVo[kNG + 2], gea[kNG + 2], gX[kNG + 2], gvd[kNG + 2];
@@ -508,7 +521,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
   const bool runB = run && fastok;
   for (int i = 1; i <= m; ++i) {
     mem.stageB(i);
-    if (!runB) continue;
+    if (!runB || (cfg.dbg & 2)) continue;
     const double ptc = mem.b_s(SL_TC), ptl = mem.b_s(SL_TLEAF);
     const double uzn = mem.b_w(WL_UZN), gtn = mem.b_w(WL_GTN);
     // leafabs (code.R:31-49) of this layer
@@ -653,20 +666,20 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
         olo = i + 1; oR = 0; oC = 0; ow = 0; otc = 0; oVo = 0; oea = 0; oX = 0; ovd = 0; open = false;
       }
     }
-    auto slput = [&](int rr, double v) { S[(long long)L.sl(i, rr) * kTile] = v; };
+    auto slput = [=](int rr, double v) { S[(long long)L.sl(i, rr) * kTile] = v; };
     slput(SL_TLEAF, tleafn); slput(SL_RABS, Rabsn); slput(SL_GV, gvn); slput(SL_GHA, ghan);
     sput(L.uz(i), uzn); sput(L.gt(i), gtn);
     wput(i, WL_TT, TT); wput(i, WL_EAL, ean);
     if (emit) { wput(i, WL_L, Lp); wput(i, WL_RSWIN, rsw); }
     Lt += Lp; stl += tleafn; ssw += rsw;
-    if (selHb == i) { hv[1] = tleafn; hv[3] = rsw; hv[5] = Lp; }
+    if (selHb == i) { hv1 = tleafn; hv3 = rsw; hv5 = Lp; }
   }
   // ---------------- heat and vapour exchange on the merged nodes (code.R:813-867) ----------------
   double tnsoil[MS + 2];
   double T2[kNG + 3], Yt[kNG + 3], Ye[kNG + 3];     // interpolation nodes (cumulative resistance, temperature, vapour pressure)
   int nn = 2;
   const double TX = TT + (pha / gtncap) * 2;
-  if (runB) {
+  if (runB && !(cfg.dbg & 4)) {
     if (open) {                                     // trailing group joins the last closed one
       if (ng > 0) { ghi[ng] = m; gw[ng] += ow; gtc[ng] += otc; gVo[ng] += oVo; gea[ng] += oea; gX[ng] += oX; gvd[ng] += ovd; }
       else { ng = 1; glo[1] = 1; ghi[1] = m; }
@@ -756,16 +769,17 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
   const double trlw_sum = p0(P0_TRLWSUM);
   const int selG = (int)p0(P0_SELG), selH = (int)p0(P0_SELH);
   const double iTX = 1 / TX;
+  const double y1t = Yt[1], y2t = Yt[2], y1e = Ye[1], y2e = Ye[2];             // the common two-node case stays in registers
   double stc = 0, srh = 0, slw = 0, tnselG = 0;
   for (int i = 1; i <= m; ++i) {
     mem.stageC(i);
-    if (!runB) continue;
+    if (!runB || (cfg.dbg & 8)) continue;
     const double v = mem.c_w(0), ean = mem.c_w(1);
     double tnn, ea2;
     if (nn == 2) {
       const double wgt = v * iTX;
-      tnn = (1 - wgt) * Yt[1] + wgt * Yt[2];
-      ea2 = (1 - wgt) * Ye[1] + wgt * Ye[2];
+      tnn = (1 - wgt) * y1t + wgt * y2t;
+      ea2 = (1 - wgt) * y1e + wgt * y2e;
     } else if (!(v >= 0.0) || !(v <= TX)) { tnn = NAN; ea2 = NAN; }
     else {                                            // layerinterp: R approx(), bisection + linear (code.R:846-847)
       int a = 1, b = nn;
@@ -795,7 +809,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     S[(long long)L.sl(i, SL_TC) * kTile] = tn; S[(long long)L.sl(i, SL_RH) * kTile] = r;
     if (emit) wput(i, WL_RLWIN, Rlwin);
     stc += tn; srh += r; slw += Rlwin;
-    if (i == selH) { hv[0] = tn; hv[2] = r; hv[4] = Rlwin; }
+    if (i == selH) { hv0 = tn; hv2 = r; hv4 = Rlwin; }
   }
   if (!runB) return !run || fastok;
   // ---------------- soil limits and fluxes (code.R:868-891) ----------------
@@ -836,7 +850,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     o[2] = r; o[3] = rsw0; o[4] = skyem0 * 5.67 * 1e-8 * pow4(tcan + 273.15); o[5] = Lt;
   }
   if (reqhgt >= 0 && reqhgt < hgt) {
-    if (selH) { for (int q = 0; q < 6; ++q) o[q] = hv[q]; }
+    if (selH) { o[0] = hv0; o[1] = hv1; o[2] = hv2; o[3] = hv3; o[4] = hv4; o[5] = hv5; }
     else { for (int q = 0; q < 6; ++q) o[q] = NAN; }
   }
   if (reqhgt <= 0) { o[0] = tnsoil[(int)p0(P0_SELS)]; o[1] = stl / m; o[2] = srh / m; o[3] = ssw / m; o[4] = slw / m; o[5] = Lt; }
@@ -957,7 +971,7 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
   const FastLayout L = mem.L;
   const int m = L.m, sm = L.sm;
   double* S = mem.S; double* W = mem.W; const double* P = mem.P;
-  auto sput = [&](int r, double v) { S[(long long)r * kTile] = v; };
+  auto sput = [=](int r, double v) { S[(long long)r * kTile] = v; };
   const double hgt = P[(long long)P0_HGT * kTile];
   const RunCfg cfg = effective_cfg(t, hgt, a.spin_mode != 0);
   const bool fastcol = P[(long long)P0_FAST * kTile] != 0.0;

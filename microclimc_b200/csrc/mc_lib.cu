@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kTile, 4) k_transient_fast(FastArgs a) {
   mem.Pt = a.P + (long long)blockIdx.x * L.nP() * kTile; mem.St = a.S + (long long)blockIdx.x * L.nS() * kTile;
   mem.Wt = a.W + (long long)blockIdx.x * L.nW() * kTile;
   mem.P = mem.Pt + threadIdx.x; mem.S = const_cast<double*>(mem.St) + threadIdx.x; mem.W = const_cast<double*>(mem.Wt) + threadIdx.x;
-  mem.buf = buf; mem.bar = bar; mem.lane = threadIdx.x; mem.k = 0; mem.cur = buf;
+  mem.buf = buf; mem.bar = bar; mem.lane = threadIdx.x; mem.k = 0; mem.cur = buf; mem.pol = l2_evict_first_policy();
   fast_run_column<PipeMem, MM, MS>(a, mem, live ? c : a.t.ncol - 1, live);
 }
 template <int MM, int MS>
@@ -180,6 +180,8 @@ RunCfg mk_cfg(const double* c) {
   r.timestep = c[MC_C_TIMESTEP]; r.edgedist = c[MC_C_EDGEDIST]; r.reqhgt = c[MC_C_REQHGT]; r.zu = c[MC_C_ZU];
   r.merid = c[MC_C_MERID]; r.dst = c[MC_C_DST]; r.n = c[MC_C_N]; r.metopen = c[MC_C_METOPEN] != 0; r.windhgt = c[MC_C_WINDHGT];
   r.zlafact = c[MC_C_ZLAFACT]; r.surfwet = c[MC_C_SURFWET];
+  const char* e = getenv("MC_DBG_SKIP");
+  r.dbg = e ? atoi(e) : 0;
   return r;
 }
 

@@ -22,6 +22,7 @@ namespace mc {
 struct RunCfg {          // runonestep / runmodel scalar arguments (code.R:687-689, 1125-1129)
   double timestep, edgedist, reqhgt, zu, merid, dst, n, windhgt, zlafact, surfwet;
   int metopen;
+  int dbg;                 // timing ablations of the streaming kernel (MC_DBG_SKIP; results are meaningless when non-zero)
 };
 struct Forcing { double tair, relhum, pk, u, tsoil, skyem, Rsw, dp, jd, lt, theta, thetap; };
 

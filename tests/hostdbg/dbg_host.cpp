@@ -11,7 +11,7 @@
 using namespace mc;
 static RunCfg mkcfg(const double* c) {
   RunCfg r; r.timestep = c[0]; r.edgedist = c[1]; r.reqhgt = c[2]; r.zu = c[3]; r.merid = c[4]; r.dst = c[5]; r.n = c[6];
-  r.metopen = c[7] != 0; r.windhgt = c[8]; r.zlafact = c[9]; r.surfwet = c[10];
+  r.metopen = c[7] != 0; r.windhgt = c[8]; r.zlafact = c[9]; r.surfwet = c[10]; r.dbg = 0;
   return r;
 }
 extern "C" int dbg_run_transient(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* forcing,
@@ -57,7 +57,7 @@ extern "C" int dbg_run_transient_fast(int64_t ncol, int m, int sm, int64_t T, co
     a.spin_mode = spin;
     for (long long c = 0; c < ntile * kTile; ++c) {
       const long long cl = c < ncol ? c : ncol - 1;
-      geom_column<20, 10>(a, effective_cfg(t, vegp[(long long)V_HGT * ncol + cl], spin != 0), c, cl);
+      geom_column<20, 10>(a, effective_cfg(t, vegp[(long long)mc::V_HGT * ncol + cl], spin != 0), c, cl);
     }
     for (long long c = 0; c < ncol; ++c) {
       DirectMem mem;

@@ -65,7 +65,7 @@ def main():
     out = {"_about": "FP64 operator census per column-timestep; tools/opcount/run_opcount.py", "weights_fp64_slots": WEIGHT,
            "workload": "C3 sample: %d columns, hourly, m=20, sm=10, state after 200-step spin-up, steps %d..%d of the synthetic year" % (ncol, T1, T2),
            "algorithmic_bytes_per_colstep": 152.0}
-    for name, fn in (("oracle_literal", "orc_run_transient"), ("shipped_fused", "dbg_run_transient")):
+    for name, fn in (("oracle_literal", "orc_run_transient"), ("general_fused", "dbg_run_transient"), ("shipped_streaming", "dbg_run_transient_fast")):
         _, st0 = run(lib, fn, w, cfg_spin, 1, np.zeros((bench.M * 12 + 10 + 2 * bench.SM, ncol)))
         c1, _ = run(lib, fn, w, cfg, T1, st0)
         c2, _ = run(lib, fn, w, cfg, T2, st0)
@@ -76,8 +76,8 @@ def main():
                      "one_off_ops_per_column": dict(zip(KINDS, [float(x) for x in (c1 - per * ncol * T1) / ncol]))}
         print(name, json.dumps(out[name]["ops_per_colstep"]), "slots", slots)
     # the roofline uses the SHIPPED algorithm's count (hoisting removes work the literal restatement repeats every step)
-    out["fp64_flop_per_colstep"] = out["shipped_fused"]["fp64_flop_per_colstep"]
-    out["fp64_slots_per_colstep"] = out["shipped_fused"]["fp64_slots_per_colstep"]
+    out["fp64_flop_per_colstep"] = out["shipped_streaming"]["fp64_flop_per_colstep"]
+    out["fp64_slots_per_colstep"] = out["shipped_streaming"]["fp64_slots_per_colstep"]
     prev = {}
     path = os.path.join(ROOT, "profiles", "cost_per_colstep.json")
     if os.path.exists(path):
