@@ -156,6 +156,11 @@ struct DirectMem {
   const double* P; double* S; double* W;      // lane-adjusted tile bases
   FastLayout L;
   int ia, ib;
+  double parked[64];                            // stands in for the device's tensor-memory scratch (PipeMem::park)
+  MC_HD void park(int slot, double v) { parked[slot] = v; }
+  MC_HD void park_done() {}
+  MC_HD void unpark8(int slot0, double* v) { for (int q = 0; q < 8; ++q) v[q] = parked[slot0 + q]; }
+  MC_HD double unpark(int slot) { return parked[slot]; }
   MC_HD void step_begin() {}
   MC_HD void sweepB_begin() {}
   MC_HD void sweepC_begin() {}
@@ -221,6 +226,33 @@ struct PipeMem {
   unsigned k;                                  // stages issued so far (uniform over the block)
   const double* cur;                           // current stage buffer + lane
   unsigned long long pol;                      // L2 evict-first policy for the streamed rows
+  // Tensor memory as a per-thread scratchpad: the CTA owns 128 columns x 128 lanes x 32 bit, i.e. 64 doubles per thread
+  // (thread t of warp w <-> lane 32*(w%4) + t%32).  Step scalars that are only needed once per layer are parked there instead
+  // of being spilled to local memory (12-cycle LDTM vs an L2 round trip).  All 32 lanes must execute these together.
+  unsigned tbase;                              // TMEM address of this warp's lane quarter, column 0 of the allocation
+  MC_D void park(int slot, double v) {
+    __syncwarp();
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(tbase + 2 * slot), "r"(__double2loint(v)), "r"(__double2hiint(v)));
+  }
+  MC_D void park_done() { asm volatile("tcgen05.wait::st.sync.aligned;"); }
+  MC_D double unpark(int slot) {
+    unsigned lo, hi;
+    __syncwarp();
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(tbase + 2 * slot));
+    asm volatile("tcgen05.wait::ld.sync.aligned;");
+    return __hiloint2double(hi, lo);
+  }
+  MC_D void unpark8(int slot0, double* v) {
+    unsigned r[16];
+    __syncwarp();
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(tbase + 2 * slot0));
+    asm volatile("tcgen05.wait::ld.sync.aligned;");
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = __hiloint2double(r[2 * q + 1], r[2 * q]);
+  }
   MC_D void issueA(int i, unsigned kk) {
     double* b = buf + (kk & 1) * (kStageRows * kTile);
     unsigned long long* mb = bar + (kk & 1);
@@ -352,467 +384,540 @@ MC_HD void thomas_f(int N, double* tcv, double tmsoil, double tairv, const doubl
 
 struct StepOut { double o[8]; int ng; };
 
-// One time step of one column in streaming form.  `run` false: the thread only keeps the block's barriers company
-// (padding lane, or a column that takes this step through the general path).  Returns false when the column left the
-// fast envelope after sweep A (nothing of the state has been modified then).
+// Step context: per-thread scalars handed from one phase of the step to the next.  On the device they live in tensor
+// memory (PipeMem::park / unpark), so that no phase has to keep another phase's values in registers (or spill them to
+// local memory, which is an L2 round trip here); the host build keeps them in a plain array.
+enum { X_TAIRN, X_PKN, X_SKYEM, X_RSW, X_RELHUMN, X_TCAN, X_TAIRP, X_RELHUMP,
+       X_PPK, X_PS1, X_TET_TAIR, X_TET_TCAN, X_TFROST, X_PSIM, X_PHIM, X_TABOVE,
+       X_TSOILP, X_PHA, X_TC1, X_UH, X_SQPHI, X_CS, X_GTNCAP, X_RGCAP,
+       X_XS, X_CP1, X_TT, X_LT, X_STL, X_SSW, X_LAM, X_CV,
+       // sweep-B invariants, 8 per group, one LDTM each
+       KR_K, KR_MUL, KR_DP, KR_RSW, KR_AG0, KR_CLUMP, KR_SKLW, KR_EMLW,
+       KG_EMV, KG_GSMAX, KG_Q50, KG_LWD, KG_ILWD, KG_LWD3, KG_C101, KG_CPK,
+       KT_EREF, KT_ESOIL, KT_MTREF, KT_PS1, KT_RGCAP, KT_TS, KT_ITS, KT_CPPK,
+       KU_LAMBDA, KU_IMPK, KU_VSB, KU_TCAN, KU_EAMN, KU_IPPK, KU_PKN, KU_REFG, K_NPARK };
+static_assert(K_NPARK <= 64, "64 doubles of tensor-memory scratch per thread");
+
+// One time step of one column in streaming form.  Every lane computes (tensor-memory accesses are warp-collective);
+// `run` false (a column that takes this step through the general path) only suppresses the stores into the state rows.
+// Returns false when the column left the fast envelope (nothing of the state has been modified then).
 template <class Mem, int MS>
 MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, bool emit, double reqhgt, int charmode,
                      double relhum0, double rsw0, double skyem0, StepOut& out) {
   const FastLayout L = mem.L;
   const int m = L.m, sm = L.sm;
-  const double* P = mem.P; double* S = mem.S; double* W = mem.W;
+  const double* const P = mem.P; double* const S = mem.S; double* const W = mem.W;
   auto p0 = [=](int r) { return P[(long long)r * kTile]; };
   auto s0 = [=](int r) { return S[(long long)r * kTile]; };
   auto sput = [=](int r, double v) { S[(long long)r * kTile] = v; };
   auto wput = [=](int i, int r, double v) { W[(long long)L.wl(i, r) * kTile] = v; };
   auto wget = [=](int i, int r) { return W[(long long)L.wl(i, r) * kTile]; };
   mem.step_begin();
-  const double timestep = cfg.timestep;
-  // ---------------- scalars of the step (code.R:700-745) ----------------
-  const double tairn = fc.tair, pkn = fc.pk, skyem = fc.skyem, Rsw = fc.Rsw;
-  double relhumn = fc.relhum, u = fc.u;
-  const double ppk = s0(S0_PK), Hprev = s0(S0_H), ps1 = s0(L.soiltc(1)), tairp = s0(S0_TAIR), relhump = s0(S0_RELHUM),
-               tsoilp = s0(S0_TSOIL), tabove = s0(S0_TABOVE);
-  const double hgt = p0(P0_HGT), dpl = p0(P0_D);
-  const double cpk = 44.6 * (pkn / 101.3), cppk = 44.6 * (ppk / 101.3);      // phair(t, pk) = c * 273.15 / (t + 273.15)
-  const double pha = phair(tairn, pkn);
-  double u2;
-  if (cfg.metopen) {
-    if (cfg.windhgt != 2) u = u * 4.87 / log(67.8 * cfg.windhgt - 5.42);
-    u2 = u * p0(P0_LA) / log(67.8 * 2 - 5.42);
-  } else {
-    u2 = u;
-    if (cfg.windhgt != (2 + hgt)) {                                          // windprofile(u, windhgt, hgt+2, ...) with zo above the canopy
-      const double psi = s0(S0_PSIM);
-      double ln2 = p0(P0_WL2) + psi;
-      if (ln2 < 0.55) ln2 = 0.55;
-      u2 = ((0.4 * (u / (p0(P0_WL1) + psi))) / 0.4) * ln2;
-    }
-  }
-  if (u2 < 0.5) u2 = 0.5;
-  const double lnref = p0(P0_LNREF);
-  const double uf = (0.4 * u2) / lnref;
-  double psi_mn, psi_h;
-  diabatic_cor(tairn, pkn, Hprev, uf, hgt + 2, dpl, psi_mn, psi_h);
-  const double tcm = s0(L.sl(m, SL_TC)), tc1 = s0(L.sl(1, SL_TC));
-  double phi_m;
-  {
-    const double dz = p0(P0_DZTB);
-    const double dtdz = (tcm - tc1) / dz;
-    double dudz = (s0(L.uz(m)) - s0(L.uz(1))) / dz;
-    if (fabs(dudz) < 0.01) dudz = 0.01;
-    const double Tk = s0(S0_TCSUM) / m + 273.15;
-    double Ri = (9.81 / Tk) * dtdz / (dudz * dudz);
-    if (Ri > 0.15) Ri = 0.15;
-    if (Ri < -1) Ri = -1;
-    if (Ri < 0) { double phh = 1 / sqrt(1 - 16 * Ri); phi_m = sqrt(phh); }
-    else { double st = Ri / (1 - 5 * Ri); phi_m = 1 + (6 * st) / (1 + st); }
-  }
-  double tcan;
-  {
-    const double ufh = (0.4 * u2) / (p0(P0_LZU) + psi_h);
-    const double mm = Hprev / (0.4 * pha * cpair(tairn) * ufh);
-    const double tref = tairn + mm * (p0(P0_LZUH) + psi_h);
-    tcan = tref - mm * (p0(P0_LZOH) + psi_h);
-  }
-  const double tfrost = dewpoint((relhumn / 100) * satvap(tairn), tairn);
-  if (tcan < tfrost) tcan = tfrost;
-  if (tcan > (tairn + 15)) tcan = tairn + 15;
-  if (tcan < (tairn - 4.5)) tcan = tairn - 4.5;
-  const double tet_tair = tetens(tairn), tet_tcan = tetens(tcan);
-  {
-    const double ea = tet_tair * (relhumn / 100);
-    relhumn = (ea / tet_tcan) * 100;
-    if (relhumn > 100) relhumn = 100;
-  }
-  const double sqphi = sqrt(phi_m), iphi = 1 / phi_m;
-  const bool edge = cfg.edgedist == cfg.edgedist;
-  const double ugr = (0.4 * (u / p0(P0_GLNH))) / 0.4;                        // grass-profile ur = ugr * gl (uref = u, zref = zu)
-  double uh;
-  {
-    const double ufw = 0.4 * (u2 / (lnref + psi_mn));
-    double ln2 = p0(P0_LNHD) + psi_mn;
-    if (ln2 < 0.55) ln2 = 0.55;
-    uh = (ufw / 0.4) * ln2;
-  }
-  // ---------------- sweep A: wind and turbulent conductances, top -> bottom (code.R:747-770) ----------------
-  double sfx = 0, Rtot = 0, Ctot = 0, cs = 0, tcu = tcm;
-  const int half = (int)nearbyint(m / 2.0);
-  for (int i = m; i >= 1; --i) {
-    mem.stageA(i);
-    if (!run || (cfg.dbg & 1)) continue;
-    const double tcl = (i > 1) ? mem.a_tcl() : ps1;
-    const double ai = mem.a_p(PA_A0I) * sqphi;
-    double uzn;
-    if (i == m) uzn = wc_fast(uh, ai, mem.a_p(PA_EX1), mem.a_p(PA_GLO), mem.a_p(PA_EDO), ugr, edge);
-    else {
-      uh = wc_fast(uh, ai, mem.a_p(PA_EX1), mem.a_p(PA_GLO), mem.a_p(PA_EDO), ugr, edge);
-      uzn = wc_fast(uh, mem.a_p(PA_A0O) * sqphi, mem.a_p(PA_EX2), mem.a_p(PA_GLI), mem.a_p(PA_EDI), ugr, edge);        // Q9
-    }
-    const double ph = phair_c(cpk, (tcu + tcl) / 2);
-    const double e0 = fexp(-ai * mem.a_p(PA_GX0)), e1 = fexp(-ai * mem.a_p(PA_GX1));
-    const double g = fdiv(mem.a_p(PA_CG) * ph * uh * ai, e0 - e1) * iphi;
-    const double gfree = 0.0012 * ph * qroot(fabs(tcu - tcl) * mem.a_p(PA_RDZ));
-    const double gtn = (g > gfree) ? g : gfree;
-    const double rn = frcp(gtn);
-    const double rg = frcp(0.5 * gtn + 0.5 * mem.a_gto());
-    const double phz = phair_c(cppk, tcu) * mem.a_p(PA_DZ);
-    wput(i, WL_RG, rg); wput(i, WL_SFX, sfx); wput(i, WL_GTN, gtn); wput(i, WL_UZN, uzn); wput(i, WL_PHZ, phz);
-    sfx += rg; Rtot += rn; Ctot += phz;
-    if (i <= half) cs += rn;
-    tcu = tcl;
-  }
   bool fastok = run;
-  double gtncap = 0, rgcap = 0;
-  if (run) {
-    {                                                                         // canopy top <-> reference (code.R:769), Q8
-      const double a = p0(P0_A0CAP) * sqphi;
-      const double ph = phair_c(cpk, (tcan + tc1) / 2);
-      const double e0 = fexp(-a * p0(P0_GXC0));
-      const double g = fdiv(p0(P0_CGCAP) * ph * uh * a, e0 - 1.0) * iphi;
-      const double gfree = 0.0012 * ph * qroot(fabs(tcan - tc1) * p0(P0_RDZCAP));
-      gtncap = (g > gfree) ? g : gfree;
-      rgcap = frcp(0.5 * gtncap + 0.5 * s0(S0_GTCAP));
-    }
-    // layermerge (code.R:772) closes a group when timestep / sum(1/gt) <= sum(ph*zth); k closed groups need
-    // sum(1/gt) * sum(ph*zth) >= k^2 * timestep (Cauchy-Schwarz), so below (kNG+1)^2 * timestep at most kNG groups exist.
-    if (!(Rtot * Ctot < (double)((kNG + 1) * (kNG + 1)) * timestep * (1 - 1e-9))) fastok = false;
-  }
-  mem.sweepB_begin();
-  // ---------------- scalars of sweep B: radiation geometry, reference vapour (code.R:776-785) ----------------
-  const double clump = p0(P0_CLUMP), refg = p0(P0_REFG), emv = p0(P0_EMV), vegem = p0(P0_VEGEM);
-  double dp = fc.dp;
-  const double sa = solalt(fc.lt, p0(P0_LAT), p0(P0_LON), fc.jd, cfg.merid, cfg.dst);
-  if (dp != dp) dp = difprop(Rsw, sa);
-  const double xx = p0(P0_X), kden = p0(P0_KDEN);
-  const double K = (sa > 0) ? cank(xx, sa, kden) : 0.0;
-  const double mul = cank(xx, sa < 5 ? 5.0 : sa, kden);
-  const double aG0 = refg * cansw_k(Rsw, dp, sa, p0(P0_SUMPAI), p0(P0_SM), p0(P0_TRDM), K, clump);
-  const double lwout = kSb * pow4(tairn + 273.15);
-  const double lambda_l = (-42.575 * tcan + 44994) * cfg.surfwet;
-  const double mtref = 0.5 * tcan + 0.5 * tairp;
-  const double mrh = 0.5 * relhumn + 0.5 * relhump;
-  const double mpk = 0.5 * ppk + 0.5 * pkn;
-  const double impk = frcp(mpk);
-  const double eref = (mrh / 100) * satvap(mtref);
-  const double esoil = soilrh(fc.theta, p0(P0_SOILB), -p0(P0_PSIE), p0(P0_SMAX), ps1) * satvap(ps1);     // Q7
-  const double eamn = (relhumn / 100) * tet_tcan;
-  const double gsmax = p0(P0_GSMAX), q50 = p0(P0_Q50), lwd = p0(P0_LWD);
-  const double ilwd = 1 / lwd, lwd3 = 9.81 * (lwd * lwd * lwd), c101 = 101.3 / pkn, ippk = 1 / ppk;
-  const int selHb = (int)p0(P0_SELH);
-  // soilk (microctools; Column::soilk) for this step's theta
-  double cd1, lam, Cv;
-  const double i2ts = 1 / (2 * timestep);
+  // ======================= phase 0: scalars of the step (code.R:700-745) =======================
+  double uh, sqphi, iphi, ugr, cpk, cppk, ps1a, tcu;
+  const bool edge = cfg.edgedist == cfg.edgedist;
   {
-    const double ct = p0(P0_SKC) * fc.theta;
-    lam = p0(P0_SKA) + p0(P0_SKB) * fc.theta - p0(P0_SKAD) * exp(-((ct * ct) * (ct * ct)));
-    Cv = (p0(P0_CVDRY) + 4.18 * fc.theta) * 1e6;
-    cd1 = (Cv * p0(P0_NFIX + sm)) * i2ts;
-  }
-  // ---------------- sweep B: leafabs + leaftemp, bottom -> top, with the merged-layer sums ----------------
-  double acc2 = 0, TT = 0, Lt = 0, stl = 0, ssw = 0;
-  double Xs = 0, cp1 = 0;
-  double hv0 = 0, hv1 = 0, hv2 = 0, hv3 = 0, hv4 = 0, hv5 = 0;
-  // layermerge / layeraverage bookkeeping (code.R:772, 814): closed groups 1..ng and the open one
-  int ng = 0, glo[kNG + 2], ghi[kNG + 2], olo = 1;
-  double gw[kNG + 2], gtc[kNG + 2], gVo[kNG + 2], gea[kNG + 2], gX[kNG + 2], gvd[kNG + 2];
-  double oR = 0, oC = 0, ow = 0, otc = 0, oVo = 0, oea = 0, oX = 0, ovd = 0;
-  bool open = false;
-  const bool runB = run && fastok;
-  for (int i = 1; i <= m; ++i) {
-    mem.stageB(i);
-    if (!runB || (cfg.dbg & 2)) continue;
-    const double ptc = mem.b_s(SL_TC), ptl = mem.b_s(SL_TLEAF);
-    const double uzn = mem.b_w(WL_UZN), gtn = mem.b_w(WL_GTN);
-    // leafabs (code.R:31-49) of this layer
-    const double ref = mem.b_p(PB_REF), omr = 1 - ref, pc = mem.b_p(PB_PC);
-    double aRsw, rsw;
-    {
-      const double trbc = (sa > 0) ? clumptr(fexp(-(mem.b_p(PB_SPC) * K)), clump) : clumptr(0.0, clump);
-      const double trbg = (sa > 0) ? clumptr(fexp(-(mem.b_p(PB_SGC) * K)), clump) : clumptr(0.0, clump);
-      const double sunl = (sa > 0) ? clumptr(fexp(-K * pc), clump) : clumptr(0.0, clump);
-      // code.R:43-46 per unit (1 - ref): Rswin = aRsw / (1 - ref) (code.R:895) is formed first, aRsw = (1 - ref) * Rswin
-      const double xR = Rsw * (dp * mem.b_p(PB_TRDC) + (1 - dp) * trbc);
-      const double xG = aG0 * (dp * mem.b_p(PB_TRDG) + (1 - dp) * trbg);
-      rsw = sunl * mul * xR + (1 - sunl) * xR + xG;
-      aRsw = omr * rsw;
-    }
-    const double trl = mem.b_p(PB_TRLW);
-    const double aRlw = emv * (trl * skyem * lwout + (1 - trl) * emv * lwout);
-    const double Rabsn = aRsw + aRlw;
-    const double Qa = 4.6 * rsw;
-    const double gvn = fdiv(gsmax * Qa, Qa + q50);                            // layercond
-    const double Tkc = ptc + 273.15, iTkc = frcp(Tkc);
-    const double ghan = gha_fast(lwd, ilwd, lwd3, uzn, Tkc, iTkc, (cpk * 273.15) * iTkc, ptl - ptc, c101);
-    // leaftemp (code.R:378-512)
-    const double rg = mem.b_w(WL_RG);
-    const double gtt = frcp(rgcap + mem.b_w(WL_SFX));
-    acc2 += rg;
-    const double gtt2 = frcp(acc2);
-    const double izl = mem.b_p(PB_IZL), izrf = mem.b_p(PB_IZRF), izp = mem.b_p(PB_IZP), izth = mem.b_p(PB_IZTH), PAIi = mem.b_p(PB_PAI);
-    const double PAIm = 2 * PAIi * izth;
-    const double esj = 0.6108 * fexp((17.27 * ptc) * frcp(ptc + 237.3));      // Tetens, code.R:410
-    const double eaj = (mem.b_s(SL_RH) * 0.01) * esj;
-    const double estl = satvap(ptl);
-    const double r237l = frcp(ptl + 237.3);
-    const double tetl = 0.6108 * fexp((17.27 * ptl) * r237l);
-    const double delta = (4098 * tetl) * (r237l * r237l);                      // code.R:415
-    const double gvo = mem.b_s(SL_GV), ghao = mem.b_s(SL_GHA);
-    // 1/(1/a + 1/b) = a*b/(a+b): one division; a = 0 (closed stomata at night) still gives 0
-    const double gvp = fdiv(gvo * ghao, gvo + ghao);
-    const double gvc = fdiv(gvn * ghan, gvn + ghan);
-    const double gvm = 0.5 * gvp + 0.5 * gvc;
-    const double gham = 0.5 * ghan + 0.5 * ghao;
-    const double g1 = gtt * izrf, g2 = gtt2 * izp, g3 = gvm * izl, g3h = gham * izl;
-    double ae, be;
-    if (timestep * dmax(dmax(g1, g3), g2) > 1) {
-      const double gv2b = (PAIm * izth) * gvm;                                // Q21
-      const double iden = frcp(gtt + gtt2 + gv2b);
-      ae = (gtt * eref + gtt2 * esoil + gv2b * estl) * iden;
-      be = (0.5 * delta) * iden;
+    const double tairn = fc.tair, pkn = fc.pk;
+    double relhumn = fc.relhum, u = fc.u;
+    const double ppk = s0(S0_PK), Hprev = s0(S0_H), ps1 = s0(L.soiltc(1));
+    const double hgt = p0(P0_HGT);
+    cpk = 44.6 * (pkn / 101.3); cppk = 44.6 * (ppk / 101.3);                  // phair(t, pk) = c * 273.15 / (t + 273.15)
+    const double pha = phair(tairn, pkn);
+    double u2;
+    if (cfg.metopen) {
+      if (cfg.windhgt != 2) u = u * 4.87 / log(67.8 * cfg.windhgt - 5.42);
+      u2 = u * p0(P0_LA) / log(67.8 * 2 - 5.42);
     } else {
-      const double ibtm = frcp((1 / timestep) + 0.5 * (g1 + g2 + g3));
-      const double sat = eaj > esj ? 0.0 : 1.0;                               // edf(), code.R:380-386
-      const double e1 = (eref > eaj ? eref - eaj : 0.0) * sat;
-      const double e2 = (esoil > eaj ? esoil - eaj : 0.0) * sat;
-      const double e3 = (estl > eaj ? estl - eaj : 0.0) * sat;
-      ae = eaj + 0.5 * (g1 * e1 + g2 * e2 + g3 * e3) * ibtm;
-      be = (0.25 * gvm * delta) * ibtm;
-    }
-    const double cp = cpair(ptc);
-    const double phc = (cppk * 273.15) * iTkc;
-    double aL, bL;
-    if (timestep * dmax(dmax(g1, g3h), g2) > 1) {
-      const double K1 = gtt * cp, K2 = gtt2 * cp, K3 = gham * cp;
-      const double iden = frcp(K1 + K2 + K3);
-      aL = (K1 * mtref + K2 * ps1 + K3 * ptl) * iden;
-      bL = (0.5 * K3) * iden;
-    } else {
-      const double ma = fdiv(mem.b_p(PB_MAC), cp * phc);
-      const double K1 = g1 * cp, K2 = g2 * cp, K3 = g3h * cp * PAIm;
-      const double ibtm = frcp(1 + 0.5 * ma * (K1 + K2 + K3));
-      aL = (ptc + 0.5 * ma * (K1 * mtref + K2 * ps1 + K3 * ptl)) * ibtm;
-      bL = (0.25 * ma * K3) * ibtm;
-    }
-    if (bL < 0) bL = 0;
-    const double aH = cp * gham * (ptl - aL);
-    double bH = cp * gham * (0.5 - 0.5 * bL);
-    if (bH < 0) bH = 0;
-    const double lg = lambda_l * gvm * impk;
-    double edf_l = (estl > ae ? estl - ae : 0.0);
-    if (ae > esj) edf_l = 0;
-    const double aX = lg * edf_l;
-    double bX = lg * (delta - be);
-    if (bX < 0) bX = 0;
-    const double Ra = 0.5 * Rabsn + 0.5 * mem.b_s(SL_RABS);
-    const double tk = ptl + 273.15;
-    const double aRe = vegem * kSb * pow4(tk);
-    const double bRe = vegem * kSb * 2 * (tk * tk * tk);
-    const double mz = mem.b_p(PB_MZ);                                          // ml / zla
-    const double num = Ra - aRe - aX - aH, bsum = bRe + bX + bH;
-    double dTL = fdiv(mz * num, 1 + mz * bsum);                                // (ml*num) / (zla + ml*bsum)
-    const double dTL2 = fdiv(num, bsum);
-    if (fabs(dTL2) < fabs(dTL)) dTL = dTL2;
-    double tnl = aL + bL * dTL;
-    double tlf = ptl + dTL;
-    if (tlf > tnl) { const double tmx = dmax(tcan + 15, tlf); if (tnl > tmx) tnl = tmx; }
-    if (tlf < tnl) { const double tmn = dmin(tcan - 5, tlf); if (tnl < tmn) tnl = tmn; }
-    const double eam = ae + be * dTL;
-    double ean = eaj + 2 * (eam - eaj);
-    const double es = tetens(tnl);
-    if (ean > es) ean = es;
-    if (ean < eamn) ean = eamn;
-    const double al = log(ean * (1 / 0.6108));
-    const double Tdew = -fdiv(237.3 * al, al - 17.27);
-    double dT1 = -(ptl + dTL - Tdew);
-    if (dT1 < 0) dT1 = 0;
-    const double Lc = lambda_l * gvm * (tetens(tlf) - ean) * impk;
-    double dT2 = -mz * Lc;
-    if (dT2 < 0) dT2 = 0;
-    tlf = tlf + dmin(dT1, dT2);
-    dTL = tlf - ptl;
-    const double dTmx = ptc + 20.2 - ptl, dTmn = ptc - 4.5 - ptl;
-    if (dTL > dTmx) dTL = dTmx;
-    if (dTL < dTmn) dTL = dTmn;
-    tnl = aL + bL * dTL;
-    const double tleafn = ptl + dTL;
-    const double Lp = (aX + bX * dTL) * PAIi;                                   // code.R:880 (Q1)
-    if (i == 1) {                                                               // soil-surface forcing (code.R:799-811)
-      cp1 = cp;
-      const double icd1 = frcp(cd1);
-      const double a1 = (1 - refg) * (aRsw * icd1);
-      if (esoil - ean > 0) {
-        const double mm = fdiv((-42.575 * ptc + 44994) * phc * p0(P0_Z1), pkn);
-        const double dl = 4098 * tetens(ps1) / sq(ps1 + 237.3);
-        const double btm = 1 + 0.5 * (mm * icd1) * dl;
-        Xs = fdiv(a1 - (mm * icd1) * (esoil - ean), btm);
-      } else Xs = a1;
-      const double sgn = Xs < 0 ? -1.0 : 1.0;
-      const double Xsmx = fdiv((1 - refg) * aRsw, ghan * cp) + (tnl - ps1);
-      if (fabs(Xs) > fabs(Xsmx)) Xs = Xsmx;
-      Xs = fabs(Xs) * sgn;
-    }
-    // layermerge (code.R:772) greedy grouping with the layeraverage sums (code.R:814) of the open group
-    {
-      const double wi = mem.b_p(PB_DZ), phz = mem.b_w(WL_PHZ), rn = frcp(gtn);
-      TT += phz * rn;                                                           // cumsum((ph/gt) * dz), code.R:797
-      oR += rn; oC += phz; open = true;
-      ow += wi; otc += wi * ptc; oVo += wi * (eaj * ippk); oea += wi * ean; oX += wi * (tnl - ptc); ovd += wi * mem.b_p(PB_VDEN);
-      if (timestep <= oC * oR) {                                               // timestep / sum(1/gt) <= sum(ph*zth)
-        if (ng < kNG + 1) {
-          ++ng;
-          glo[ng] = olo; ghi[ng] = i; gw[ng] = ow; gtc[ng] = otc; gVo[ng] = oVo; gea[ng] = oea; gX[ng] = oX; gvd[ng] = ovd;
-        }
-        olo = i + 1; oR = 0; oC = 0; ow = 0; otc = 0; oVo = 0; oea = 0; oX = 0; ovd = 0; open = false;
+      u2 = u;
+      if (cfg.windhgt != (2 + hgt)) {                                        // windprofile(u, windhgt, hgt+2, ...) with zo above the canopy
+        const double psi = s0(S0_PSIM);
+        double ln2 = p0(P0_WL2) + psi;
+        if (ln2 < 0.55) ln2 = 0.55;
+        u2 = ((0.4 * (u / (p0(P0_WL1) + psi))) / 0.4) * ln2;
       }
     }
-    auto slput = [=](int rr, double v) { S[(long long)L.sl(i, rr) * kTile] = v; };
-    slput(SL_TLEAF, tleafn); slput(SL_RABS, Rabsn); slput(SL_GV, gvn); slput(SL_GHA, ghan);
-    sput(L.uz(i), uzn); sput(L.gt(i), gtn);
-    wput(i, WL_TT, TT); wput(i, WL_EAL, ean);
-    if (emit) { wput(i, WL_L, Lp); wput(i, WL_RSWIN, rsw); }
-    Lt += Lp; stl += tleafn; ssw += rsw;
-    if (selHb == i) { hv1 = tleafn; hv3 = rsw; hv5 = Lp; }
+    if (u2 < 0.5) u2 = 0.5;
+    const double lnref = p0(P0_LNREF);
+    const double uf = (0.4 * u2) / lnref;
+    double psi_mn, psi_h;
+    diabatic_cor(tairn, pkn, Hprev, uf, hgt + 2, p0(P0_D), psi_mn, psi_h);
+    const double tcm = s0(L.sl(m, SL_TC)), tc1 = s0(L.sl(1, SL_TC));
+    double phi_m;
+    {
+      const double dz = p0(P0_DZTB);
+      const double dtdz = (tcm - tc1) / dz;
+      double dudz = (s0(L.uz(m)) - s0(L.uz(1))) / dz;
+      if (fabs(dudz) < 0.01) dudz = 0.01;
+      const double Tk = s0(S0_TCSUM) / m + 273.15;
+      double Ri = (9.81 / Tk) * dtdz / (dudz * dudz);
+      if (Ri > 0.15) Ri = 0.15;
+      if (Ri < -1) Ri = -1;
+      if (Ri < 0) { double phh = 1 / sqrt(1 - 16 * Ri); phi_m = sqrt(phh); }
+      else { double st = Ri / (1 - 5 * Ri); phi_m = 1 + (6 * st) / (1 + st); }
+    }
+    double tcan;
+    {
+      const double ufh = (0.4 * u2) / (p0(P0_LZU) + psi_h);
+      const double mm = Hprev / (0.4 * pha * cpair(tairn) * ufh);
+      const double tref = tairn + mm * (p0(P0_LZUH) + psi_h);
+      tcan = tref - mm * (p0(P0_LZOH) + psi_h);
+    }
+    const double tfrost = dewpoint((relhumn / 100) * satvap(tairn), tairn);
+    if (tcan < tfrost) tcan = tfrost;
+    if (tcan > (tairn + 15)) tcan = tairn + 15;
+    if (tcan < (tairn - 4.5)) tcan = tairn - 4.5;
+    const double tet_tair = tetens(tairn), tet_tcan = tetens(tcan);
+    {
+      const double ea = tet_tair * (relhumn / 100);
+      relhumn = (ea / tet_tcan) * 100;
+      if (relhumn > 100) relhumn = 100;
+    }
+    sqphi = sqrt(phi_m); iphi = 1 / phi_m;
+    ugr = (0.4 * (u / p0(P0_GLNH))) / 0.4;                                    // grass-profile ur = ugr * gl (uref = u, zref = zu)
+    {
+      const double ufw = 0.4 * (u2 / (lnref + psi_mn));
+      double ln2 = p0(P0_LNHD) + psi_mn;
+      if (ln2 < 0.55) ln2 = 0.55;
+      uh = (ufw / 0.4) * ln2;
+    }
+    ps1a = ps1; tcu = tcm;
+    mem.park(X_TAIRN, tairn); mem.park(X_PKN, pkn); mem.park(X_SKYEM, fc.skyem); mem.park(X_RSW, fc.Rsw); mem.park(X_RELHUMN, relhumn);
+    mem.park(X_TCAN, tcan); mem.park(X_TAIRP, s0(S0_TAIR)); mem.park(X_RELHUMP, s0(S0_RELHUM));
+    mem.park(X_PPK, ppk); mem.park(X_PS1, ps1); mem.park(X_TET_TAIR, tet_tair); mem.park(X_TET_TCAN, tet_tcan); mem.park(X_TFROST, tfrost);
+    mem.park(X_PSIM, psi_mn); mem.park(X_PHIM, phi_m); mem.park(X_TABOVE, s0(S0_TABOVE));
+    mem.park(X_TSOILP, s0(S0_TSOIL)); mem.park(X_PHA, pha); mem.park(X_TC1, tc1);
+    mem.park_done();
   }
-  // ---------------- heat and vapour exchange on the merged nodes (code.R:813-867) ----------------
-  double tnsoil[MS + 2];
-  double T2[kNG + 3], Yt[kNG + 3], Ye[kNG + 3];     // interpolation nodes (cumulative resistance, temperature, vapour pressure)
-  int nn = 2;
-  const double TX = TT + (pha / gtncap) * 2;
-  if (runB && !(cfg.dbg & 4)) {
+  // ======================= sweep A: wind and turbulent conductances, top -> bottom (code.R:747-770) =======================
+  {
+    double sfx = 0, Rtot = 0, Ctot = 0, cs = 0;
+    const int half = (int)nearbyint(m / 2.0);
+    for (int i = m; i >= 1; --i) {
+      mem.stageA(i);
+      if (cfg.dbg & 1) continue;
+      const double tcl = (i > 1) ? mem.a_tcl() : ps1a;
+      const double ai = mem.a_p(PA_A0I) * sqphi;
+      double uzn;
+      if (i == m) uzn = wc_fast(uh, ai, mem.a_p(PA_EX1), mem.a_p(PA_GLO), mem.a_p(PA_EDO), ugr, edge);
+      else {
+        uh = wc_fast(uh, ai, mem.a_p(PA_EX1), mem.a_p(PA_GLO), mem.a_p(PA_EDO), ugr, edge);
+        uzn = wc_fast(uh, mem.a_p(PA_A0O) * sqphi, mem.a_p(PA_EX2), mem.a_p(PA_GLI), mem.a_p(PA_EDI), ugr, edge);      // Q9
+      }
+      const double ph = phair_c(cpk, (tcu + tcl) / 2);
+      const double e0 = fexp(-ai * mem.a_p(PA_GX0)), e1 = fexp(-ai * mem.a_p(PA_GX1));
+      const double g = fdiv(mem.a_p(PA_CG) * ph * uh * ai, e0 - e1) * iphi;
+      const double gfree = 0.0012 * ph * qroot(fabs(tcu - tcl) * mem.a_p(PA_RDZ));
+      const double gtn = (g > gfree) ? g : gfree;
+      const double rn = frcp(gtn);
+      const double rg = frcp(0.5 * gtn + 0.5 * mem.a_gto());
+      const double phz = phair_c(cppk, tcu) * mem.a_p(PA_DZ);
+      double* Wl = W + (long long)L.wl(i, 0) * kTile;
+      Wl[WL_RG * kTile] = rg; Wl[WL_SFX * kTile] = sfx; Wl[WL_GTN * kTile] = gtn; Wl[WL_UZN * kTile] = uzn; Wl[WL_PHZ * kTile] = phz;
+      sfx += rg; Rtot += rn; Ctot += phz;
+      if (i <= half) cs += rn;
+      tcu = tcl;
+    }
+    // canopy top <-> reference (code.R:769), Q8: leftover uh, lowest air node
+    const double tcan = mem.unpark(X_TCAN), tc1 = mem.unpark(X_TC1);
+    const double a = p0(P0_A0CAP) * sqphi;
+    const double ph = phair_c(cpk, (tcan + tc1) / 2);
+    const double e0 = fexp(-a * p0(P0_GXC0));
+    const double g = fdiv(p0(P0_CGCAP) * ph * uh * a, e0 - 1.0) * iphi;
+    const double gfree = 0.0012 * ph * qroot(fabs(tcan - tc1) * p0(P0_RDZCAP));
+    const double gtncap = (g > gfree) ? g : gfree;
+    const double rgcap = frcp(0.5 * gtncap + 0.5 * s0(S0_GTCAP));
+    // layermerge (code.R:772) closes a group when timestep / sum(1/gt) <= sum(ph*zth); k closed groups need
+    // sum(1/gt) * sum(ph*zth) >= k^2 * timestep (Cauchy-Schwarz), so below (kNG+1)^2 * timestep at most kNG groups exist.
+    if (!(Rtot * Ctot < (double)((kNG + 1) * (kNG + 1)) * cfg.timestep * (1 - 1e-9))) fastok = false;
+    mem.park(X_UH, uh); mem.park(X_SQPHI, sqphi); mem.park(X_CS, cs); mem.park(X_GTNCAP, gtncap); mem.park(X_RGCAP, rgcap);
+  }
+  mem.sweepB_begin();
+  // ======================= scalars of sweep B: radiation geometry, reference vapour (code.R:776-785) =======================
+  bool day;
+  {
+    double x0[8], x1[8];
+    mem.park_done();
+    mem.unpark8(X_TAIRN, x0); mem.unpark8(X_PPK, x1);
+    const double tairn = x0[X_TAIRN], pkn = x0[X_PKN], skyem = x0[X_SKYEM], Rsw = x0[X_RSW], relhumn = x0[X_RELHUMN], tcan = x0[X_TCAN];
+    const double ppk = x1[X_PPK - X_PPK], ps1 = x1[X_PS1 - X_PPK], tet_tcan = x1[X_TET_TCAN - X_PPK];
+    const double clump = p0(P0_CLUMP), refg = p0(P0_REFG), emv = p0(P0_EMV);
+    double dp = fc.dp;
+    const double sa = solalt(fc.lt, p0(P0_LAT), p0(P0_LON), fc.jd, cfg.merid, cfg.dst);
+    if (dp != dp) dp = difprop(Rsw, sa);
+    const double xx = p0(P0_X), kden = p0(P0_KDEN);
+    const double K = (sa > 0) ? cank(xx, sa, kden) : 0.0;
+    const double mul = cank(xx, sa < 5 ? 5.0 : sa, kden);
+    const double aG0 = refg * cansw_k(Rsw, dp, sa, p0(P0_SUMPAI), p0(P0_SM), p0(P0_TRDM), K, clump);
+    const double lwout = kSb * pow4(tairn + 273.15);
+    day = sa > 0;
+    mem.park(KR_K, K); mem.park(KR_MUL, mul); mem.park(KR_DP, dp); mem.park(KR_RSW, Rsw); mem.park(KR_AG0, aG0); mem.park(KR_CLUMP, clump);
+    mem.park(KR_SKLW, skyem * lwout); mem.park(KR_EMLW, emv * lwout);
+    const double lwd = p0(P0_LWD);
+    mem.park(KG_EMV, emv); mem.park(KG_GSMAX, p0(P0_GSMAX)); mem.park(KG_Q50, p0(P0_Q50)); mem.park(KG_LWD, lwd); mem.park(KG_ILWD, 1 / lwd);
+    mem.park(KG_LWD3, 9.81 * (lwd * lwd * lwd)); mem.park(KG_C101, 101.3 / pkn); mem.park(KG_CPK, (44.6 * (pkn / 101.3)) * 273.15);
+    const double mtref = 0.5 * tcan + 0.5 * x0[X_TAIRP];
+    const double mrh = 0.5 * relhumn + 0.5 * x0[X_RELHUMP];
+    const double mpk = 0.5 * ppk + 0.5 * pkn;
+    const double eref = (mrh / 100) * satvap(mtref);
+    const double esoil = soilrh(fc.theta, p0(P0_SOILB), -p0(P0_PSIE), p0(P0_SMAX), ps1) * satvap(ps1);     // Q7
+    const double eamn = (relhumn / 100) * tet_tcan;
+    mem.park(KT_EREF, eref); mem.park(KT_ESOIL, esoil); mem.park(KT_MTREF, mtref); mem.park(KT_PS1, ps1); mem.park(KT_RGCAP, mem.unpark(X_RGCAP));
+    mem.park(KT_TS, cfg.timestep); mem.park(KT_ITS, 1 / cfg.timestep); mem.park(KT_CPPK, (44.6 * (ppk / 101.3)) * 273.15);
+    mem.park(KU_LAMBDA, (-42.575 * tcan + 44994) * cfg.surfwet); mem.park(KU_IMPK, frcp(mpk)); mem.park(KU_VSB, p0(P0_VEGEM) * kSb);
+    mem.park(KU_TCAN, tcan); mem.park(KU_EAMN, eamn); mem.park(KU_IPPK, 1 / ppk); mem.park(KU_PKN, pkn); mem.park(KU_REFG, refg);
+    // soilk (microctools; Column::soilk) for this step's theta
+    const double ct = p0(P0_SKC) * fc.theta;
+    mem.park(X_LAM, p0(P0_SKA) + p0(P0_SKB) * fc.theta - p0(P0_SKAD) * exp(-((ct * ct) * (ct * ct))));
+    mem.park(X_CV, (p0(P0_CVDRY) + 4.18 * fc.theta) * 1e6);
+    mem.park_done();
+  }
+  // ======================= sweep B: leafabs + leaftemp, bottom -> top, with the merged-layer sums =======================
+  // layermerge / layeraverage bookkeeping (code.R:772, 814): closed groups 1..ng and the open one
+  int ng = 0, glo[kNG + 2], ghi[kNG + 2];
+  double gw[kNG + 2], gtc[kNG + 2], gVo[kNG + 2], gea[kNG + 2], gX[kNG + 2], gvd[kNG + 2];
+  const bool runB = run && fastok;
+  {
+    const int selHb = (int)p0(P0_SELH);
+    double acc2 = 0, TT = 0, Lt = 0, stl = 0, ssw = 0, Xs = 0, cp1 = 0;
+    double oR = 0, oC = 0, ow = 0, otc = 0, oVo = 0, oea = 0, oX = 0, ovd = 0;
+    int olo = 1;
+    bool open = false;
+    for (int i = 1; i <= m; ++i) {
+      mem.stageB(i);
+      if (cfg.dbg & 2) continue;
+      const double ptc = mem.b_s(SL_TC), ptl = mem.b_s(SL_TLEAF);
+      const double uzn = mem.b_w(WL_UZN), gtn = mem.b_w(WL_GTN);
+      // leafabs (code.R:31-49) of this layer
+      const double omr = 1 - mem.b_p(PB_REF);
+      double aRsw, rsw, Rabsn, gvn, ghan;
+      const double Tkc = ptc + 273.15, iTkc = frcp(Tkc);
+      {
+        double kr[8];
+        mem.unpark8(KR_K, kr);
+        const double K = kr[KR_K - KR_K], clump = kr[KR_CLUMP - KR_K], dp = kr[KR_DP - KR_K];
+        const double trbc = day ? clumptr(fexp(-(mem.b_p(PB_SPC) * K)), clump) : clumptr(0.0, clump);
+        const double trbg = day ? clumptr(fexp(-(mem.b_p(PB_SGC) * K)), clump) : clumptr(0.0, clump);
+        const double sunl = day ? clumptr(fexp(-K * mem.b_p(PB_PC)), clump) : clumptr(0.0, clump);
+        // code.R:43-46 per unit (1 - ref): Rswin = aRsw / (1 - ref) (code.R:895) is formed first, aRsw = (1 - ref) * Rswin
+        const double xR = kr[KR_RSW - KR_K] * (dp * mem.b_p(PB_TRDC) + (1 - dp) * trbc);
+        const double xG = kr[KR_AG0 - KR_K] * (dp * mem.b_p(PB_TRDG) + (1 - dp) * trbg);
+        rsw = sunl * kr[KR_MUL - KR_K] * xR + (1 - sunl) * xR + xG;
+        aRsw = omr * rsw;
+        const double trl = mem.b_p(PB_TRLW);
+        double kg[8];
+        mem.unpark8(KG_EMV, kg);
+        const double aRlw = kg[KG_EMV - KG_EMV] * (trl * kr[KR_SKLW - KR_K] + (1 - trl) * kr[KR_EMLW - KR_K]);       // canlw()$lwabs, code.R:47
+        Rabsn = aRsw + aRlw;
+        const double Qa = 4.6 * rsw;
+        gvn = fdiv(kg[KG_GSMAX - KG_EMV] * Qa, Qa + kg[KG_Q50 - KG_EMV]);       // layercond
+        ghan = gha_fast(kg[KG_LWD - KG_EMV], kg[KG_ILWD - KG_EMV], kg[KG_LWD3 - KG_EMV], uzn, Tkc, iTkc, kg[KG_CPK - KG_EMV] * iTkc, ptl - ptc,
+                        kg[KG_C101 - KG_EMV]);
+      }
+      double kt[8], ku[8];
+      mem.unpark8(KT_EREF, kt);
+      mem.unpark8(KU_LAMBDA, ku);
+      const double eref = kt[KT_EREF - KT_EREF], esoil = kt[KT_ESOIL - KT_EREF], mtref = kt[KT_MTREF - KT_EREF], ps1 = kt[KT_PS1 - KT_EREF];
+      const double timestep = kt[KT_TS - KT_EREF];
+      const double lambda_l = ku[KU_LAMBDA - KU_LAMBDA], impk = ku[KU_IMPK - KU_LAMBDA], tcan = ku[KU_TCAN - KU_LAMBDA], eamn = ku[KU_EAMN - KU_LAMBDA];
+      // leaftemp (code.R:378-512)
+      const double rg = mem.b_w(WL_RG);
+      const double gtt = frcp(kt[KT_RGCAP - KT_EREF] + mem.b_w(WL_SFX));
+      acc2 += rg;
+      const double gtt2 = frcp(acc2);
+      const double izl = mem.b_p(PB_IZL), izrf = mem.b_p(PB_IZRF), izp = mem.b_p(PB_IZP), izth = mem.b_p(PB_IZTH), PAIi = mem.b_p(PB_PAI);
+      const double PAIm = 2 * PAIi * izth;
+      const double esj = 0.6108 * fexp((17.27 * ptc) * frcp(ptc + 237.3));      // Tetens, code.R:410
+      const double eaj = (mem.b_s(SL_RH) * 0.01) * esj;
+      const double estl = satvap(ptl);
+      const double r237l = frcp(ptl + 237.3);
+      const double tetl = 0.6108 * fexp((17.27 * ptl) * r237l);
+      const double delta = (4098 * tetl) * (r237l * r237l);                      // code.R:415
+      const double gvo = mem.b_s(SL_GV), ghao = mem.b_s(SL_GHA);
+      // 1/(1/a + 1/b) = a*b/(a+b): one division; a = 0 (closed stomata at night) still gives 0
+      const double gvp = fdiv(gvo * ghao, gvo + ghao);
+      const double gvc = fdiv(gvn * ghan, gvn + ghan);
+      const double gvm = 0.5 * gvp + 0.5 * gvc;
+      const double gham = 0.5 * ghan + 0.5 * ghao;
+      const double g1 = gtt * izrf, g2 = gtt2 * izp, g3 = gvm * izl, g3h = gham * izl;
+      double ae, be;
+      if (timestep * dmax(dmax(g1, g3), g2) > 1) {
+        const double gv2b = (PAIm * izth) * gvm;                                // Q21
+        const double iden = frcp(gtt + gtt2 + gv2b);
+        ae = (gtt * eref + gtt2 * esoil + gv2b * estl) * iden;
+        be = (0.5 * delta) * iden;
+      } else {
+        const double ibtm = frcp(kt[KT_ITS - KT_EREF] + 0.5 * (g1 + g2 + g3));
+        const double sat = eaj > esj ? 0.0 : 1.0;                               // edf(), code.R:380-386
+        const double e1 = (eref > eaj ? eref - eaj : 0.0) * sat;
+        const double e2 = (esoil > eaj ? esoil - eaj : 0.0) * sat;
+        const double e3 = (estl > eaj ? estl - eaj : 0.0) * sat;
+        ae = eaj + 0.5 * (g1 * e1 + g2 * e2 + g3 * e3) * ibtm;
+        be = (0.25 * gvm * delta) * ibtm;
+      }
+      const double cp = cpair(ptc);
+      const double phc = kt[KT_CPPK - KT_EREF] * iTkc;
+      double aL, bL;
+      if (timestep * dmax(dmax(g1, g3h), g2) > 1) {
+        const double K1 = gtt * cp, K2 = gtt2 * cp, K3 = gham * cp;
+        const double iden = frcp(K1 + K2 + K3);
+        aL = (K1 * mtref + K2 * ps1 + K3 * ptl) * iden;
+        bL = (0.5 * K3) * iden;
+      } else {
+        const double ma = fdiv(mem.b_p(PB_MAC), cp * phc);
+        const double K1 = g1 * cp, K2 = g2 * cp, K3 = g3h * cp * PAIm;
+        const double ibtm = frcp(1 + 0.5 * ma * (K1 + K2 + K3));
+        aL = (ptc + 0.5 * ma * (K1 * mtref + K2 * ps1 + K3 * ptl)) * ibtm;
+        bL = (0.25 * ma * K3) * ibtm;
+      }
+      if (bL < 0) bL = 0;
+      const double aH = cp * gham * (ptl - aL);
+      double bH = cp * gham * (0.5 - 0.5 * bL);
+      if (bH < 0) bH = 0;
+      const double lg = lambda_l * gvm * impk;
+      double edf_l = (estl > ae ? estl - ae : 0.0);
+      if (ae > esj) edf_l = 0;
+      const double aX = lg * edf_l;
+      double bX = lg * (delta - be);
+      if (bX < 0) bX = 0;
+      const double Ra = 0.5 * Rabsn + 0.5 * mem.b_s(SL_RABS);
+      const double tk = ptl + 273.15;
+      const double aRe = ku[KU_VSB - KU_LAMBDA] * pow4(tk);
+      const double bRe = ku[KU_VSB - KU_LAMBDA] * 2 * (tk * tk * tk);
+      const double mz = mem.b_p(PB_MZ);                                          // ml / zla
+      const double num = Ra - aRe - aX - aH, bsum = bRe + bX + bH;
+      double dTL = fdiv(mz * num, 1 + mz * bsum);                                // (ml*num) / (zla + ml*bsum)
+      const double dTL2 = fdiv(num, bsum);
+      if (fabs(dTL2) < fabs(dTL)) dTL = dTL2;
+      double tnl = aL + bL * dTL;
+      double tlf = ptl + dTL;
+      if (tlf > tnl) { const double tmx = dmax(tcan + 15, tlf); if (tnl > tmx) tnl = tmx; }
+      if (tlf < tnl) { const double tmn = dmin(tcan - 5, tlf); if (tnl < tmn) tnl = tmn; }
+      const double eam = ae + be * dTL;
+      double ean = eaj + 2 * (eam - eaj);
+      const double es = tetens(tnl);
+      if (ean > es) ean = es;
+      if (ean < eamn) ean = eamn;
+      const double al = log(ean * (1 / 0.6108));
+      const double Tdew = -fdiv(237.3 * al, al - 17.27);
+      double dT1 = -(ptl + dTL - Tdew);
+      if (dT1 < 0) dT1 = 0;
+      const double Lc = lambda_l * gvm * (tetens(tlf) - ean) * impk;
+      double dT2 = -mz * Lc;
+      if (dT2 < 0) dT2 = 0;
+      tlf = tlf + dmin(dT1, dT2);
+      dTL = tlf - ptl;
+      const double dTmx = ptc + 20.2 - ptl, dTmn = ptc - 4.5 - ptl;
+      if (dTL > dTmx) dTL = dTmx;
+      if (dTL < dTmn) dTL = dTmn;
+      tnl = aL + bL * dTL;
+      const double tleafn = ptl + dTL;
+      const double Lp = (aX + bX * dTL) * PAIi;                                   // code.R:880 (Q1)
+      if (i == 1) {                                                               // soil-surface forcing (code.R:799-811)
+        const double refg = ku[KU_REFG - KU_LAMBDA], pkn = ku[KU_PKN - KU_LAMBDA];
+        cp1 = cp;
+        const double cd1 = (mem.unpark(X_CV) * p0(P0_NFIX + sm)) * (0.5 * kt[KT_ITS - KT_EREF]);
+        const double icd1 = frcp(cd1);
+        const double a1 = (1 - refg) * (aRsw * icd1);
+        if (esoil - ean > 0) {
+          const double mm = fdiv((-42.575 * ptc + 44994) * phc * p0(P0_Z1), pkn);
+          const double dl = 4098 * tetens(ps1) / sq(ps1 + 237.3);
+          const double btm = 1 + 0.5 * (mm * icd1) * dl;
+          Xs = fdiv(a1 - (mm * icd1) * (esoil - ean), btm);
+        } else Xs = a1;
+        const double sgn = Xs < 0 ? -1.0 : 1.0;
+        const double Xsmx = fdiv((1 - refg) * aRsw, ghan * cp) + (tnl - ps1);
+        if (fabs(Xs) > fabs(Xsmx)) Xs = Xsmx;
+        Xs = fabs(Xs) * sgn;
+      }
+      // layermerge (code.R:772) greedy grouping with the layeraverage sums (code.R:814) of the open group
+      {
+        const double wi = mem.b_p(PB_DZ), phz = mem.b_w(WL_PHZ), rn = frcp(gtn);
+        TT += phz * rn;                                                           // cumsum((ph/gt) * dz), code.R:797
+        oR += rn; oC += phz; open = true;
+        ow += wi; otc += wi * ptc; oVo += wi * (eaj * ku[KU_IPPK - KU_LAMBDA]); oea += wi * ean; oX += wi * (tnl - ptc); ovd += wi * mem.b_p(PB_VDEN);
+        if (timestep <= oC * oR) {                                               // timestep / sum(1/gt) <= sum(ph*zth)
+          if (ng < kNG + 1) {
+            ++ng;
+            glo[ng] = olo; ghi[ng] = i; gw[ng] = ow; gtc[ng] = otc; gVo[ng] = oVo; gea[ng] = oea; gX[ng] = oX; gvd[ng] = ovd;
+          }
+          olo = i + 1; oR = 0; oC = 0; ow = 0; otc = 0; oVo = 0; oea = 0; oX = 0; ovd = 0; open = false;
+        }
+      }
+      if (runB) {
+        double* Sl = S + (long long)L.sl(i, 0) * kTile;
+        Sl[SL_TLEAF * kTile] = tleafn; Sl[SL_RABS * kTile] = Rabsn; Sl[SL_GV * kTile] = gvn; Sl[SL_GHA * kTile] = ghan;
+        sput(L.uz(i), uzn); sput(L.gt(i), gtn);
+      }
+      double* Wl = W + (long long)L.wl(i, 0) * kTile;
+      Wl[WL_TT * kTile] = TT; Wl[WL_EAL * kTile] = ean;
+      if (emit || i == selHb) { Wl[WL_L * kTile] = Lp; Wl[WL_RSWIN * kTile] = rsw; }
+      Lt += Lp; stl += tleafn; ssw += rsw;
+    }
     if (open) {                                     // trailing group joins the last closed one
       if (ng > 0) { ghi[ng] = m; gw[ng] += ow; gtc[ng] += otc; gVo[ng] += oVo; gea[ng] += oea; gX[ng] += oX; gvd[ng] += ovd; }
       else { ng = 1; glo[1] = 1; ghi[1] = m; }
     }
-    double k[kNG + MS + 3], cdv[kNG + MS + 2], XX[kNG + MS + 2], tc2[kNG + MS + 4], tn2[kNG + MS + 4], cc[kNG + MS + 4], dd[kNG + MS + 4];
-    if (ng > 1) {
-      const int mg = ng, N = mg + sm;
-      double ltc[kNG + 2], lgt[kNG + 3], lz[kNG + 4], lVo[kNG + 2], lea[kNG + 2], lph[kNG + 2], lTT[kNG + 2];
-      int cprev = 0;
-      lz[1] = 0;
-      for (int g = 1; g <= mg; ++g) {
-        const double iw = 1 / gw[g];
-        ltc[g] = gtc[g] * iw; lVo[g] = gVo[g] * iw; lea[g] = gea[g] * iw;
-        const double lX = gX[g] * iw, lvd = gvd[g] * iw;
-        const double lcp = cpair(ltc[g]);
-        lph[g] = phair(ltc[g], ppk);
-        const int c = (glo[g] + ghi[g] + 1) / 2;
-        lz[g + 1] = P[(long long)L.pz(c) * kTile]; lTT[g] = wget(c, WL_TT);
-        if (c - cprev == 1) lgt[g] = wget(c, WL_GTN);
-        else { double R = 0; for (int j = cprev + 1; j <= c; ++j) R += 1 / wget(j, WL_GTN); lgt[g] = 1 / R; }
-        cprev = c;
-        // stash what the Thomas set-up needs in the solver arrays (filled in reverse order below)
-        XX[mg + 1 - g] = lX; tc2[1 + mg + 1 - g] = ltc[g]; cc[g] = lcp; dd[g] = lvd;
-      }
-      if (m + 1 - cprev == 1) lgt[mg + 1] = gtncap;
-      else { double R = 0; for (int j = cprev + 1; j <= m; ++j) R += 1 / wget(j, WL_GTN); R += 1 / gtncap; lgt[mg + 1] = 1 / R; }
-      lz[mg + 2] = hgt;
-      for (int g = 1; g <= mg; ++g) {
-        const double cda = cc[g] * lph[g] * (1 - dd[g]) * (lz[g + 2] - lz[g]) / 2 * timestep;       // Q10
-        double ka = lgt[g] * cc[g];
-        if (ka > cda) ka = cda;
-        k[mg + 2 - g] = ka; cdv[mg + 1 - g] = cda;
-      }
-      k[1] = lgt[mg + 1] * cpair(tabove);
-      for (int j = 1; j <= sm; ++j) {
-        k[mg + 1 + j] = lam * p0(P0_NFIX + (j - 1)); cdv[mg + j] = (Cv * p0(P0_NFIX + sm + (j - 1))) * i2ts;
-        XX[mg + j] = 0; tc2[1 + mg + j] = s0(L.soiltc(j));
-      }
-      XX[mg + 1] = Xs;
-      tc2[1] = tabove; tc2[N + 2] = tsoilp;
-      thomas_f(N, tc2, fc.tsoil, tcan, k, cdv, cfg.n, XX, tn2, cc, dd);
-      for (int j = 1; j <= sm; ++j) tnsoil[j] = tn2[mg + 1 + j];
-      // tnair = rev(tn2[1:(mg+2)]) = (soil 1, air bottom..top, tcan)
-      nn = mg + 2;
-      for (int g = 1; g <= mg + 2; ++g) Yt[g] = tn2[mg + 3 - g];
-      {                                               // ThomasV (code.R:153-169) on reversed arrays
-        double rhs = soilrh(fc.theta, p0(P0_SOILB), p0(P0_PSIE), p0(P0_SMAX), tnsoil[1]); if (rhs > 1) rhs = 1;
-        double rhsp = soilrh(fc.thetap, p0(P0_SOILB), p0(P0_PSIE), p0(P0_SMAX), ps1); if (rhsp > 1) rhsp = 1;
-        const double Vair = (tet_tcan * (relhumn / 100)) / pkn;
-        const double eap = tetens(tairp) * (relhump / 100);
-        const double Vsoil = (tetens(tnsoil[1]) * rhs) / pkn;
-        const double easp = tetens(tsoilp) * rhsp;                               // Q5
-        double vt[kNG + 4], vk[kNG + 3], vcd[kNG + 2], vX[kNG + 2], vn[kNG + 4];
-        vt[1] = eap / ppk; vt[mg + 2] = easp / ppk;
-        for (int g = 1; g <= mg; ++g) vt[1 + g] = lVo[mg + 1 - g];
-        for (int g = 1; g <= mg + 1; ++g) {
-          double gt2 = lgt[g];
-          if (g <= mg) { const double gtmx = lph[g] / (lz[g + 1] - lz[g]) * (2 * timestep); if (gt2 > gtmx) gt2 = gtmx; }
-          vk[mg + 2 - g] = gt2;
-        }
+    mem.park(X_XS, Xs); mem.park(X_CP1, cp1); mem.park(X_TT, TT); mem.park(X_LT, Lt); mem.park(X_STL, stl); mem.park(X_SSW, ssw);
+    mem.park_done();
+  }
+  // ======================= heat and vapour exchange on the merged nodes (code.R:813-867) =======================
+  double tnsoil[MS + 2];
+  double T2[kNG + 3], Yt[kNG + 3], Ye[kNG + 3];     // interpolation nodes (cumulative resistance, temperature, vapour pressure)
+  int nn = 2;
+  double TX;
+  {
+    double x0[8], x1[8], x2[8];
+    mem.unpark8(X_TAIRN, x0); mem.unpark8(X_PPK, x1); mem.unpark8(X_TSOILP, x2);
+    const double pkn = x0[X_PKN], relhumn = x0[X_RELHUMN], tcan = x0[X_TCAN], tairp = x0[X_TAIRP], relhump = x0[X_RELHUMP];
+    const double ppk = x1[X_PPK - X_PPK], ps1 = x1[X_PS1 - X_PPK], tet_tcan = x1[X_TET_TCAN - X_PPK], tabove = x1[X_TABOVE - X_PPK];
+    const double tsoilp = x2[X_TSOILP - X_TSOILP], pha = x2[X_PHA - X_TSOILP], cs = x2[X_CS - X_TSOILP], gtncap = x2[X_GTNCAP - X_TSOILP];
+    const double Xs = mem.unpark(X_XS), TT = mem.unpark(X_TT), lam = mem.unpark(X_LAM), Cv = mem.unpark(X_CV);
+    const double esoil = mem.unpark(KT_ESOIL), eamn = mem.unpark(KU_EAMN);          // (all tensor-memory reads before lanes diverge)
+    const double timestep = cfg.timestep, i2ts = 1 / (2 * timestep);
+    TX = TT + (pha / gtncap) * 2;
+    if (!(cfg.dbg & 4)) {
+      double k[kNG + MS + 3], cdv[kNG + MS + 2], XX[kNG + MS + 2], tc2[kNG + MS + 4], tn2[kNG + MS + 4], cc[kNG + MS + 4], dd[kNG + MS + 4];
+      if (ng > 1) {
+        const int mg = ng, N = mg + sm;
+        double ltc[kNG + 2], lgt[kNG + 3], lz[kNG + 4], lVo[kNG + 2], lea[kNG + 2], lph[kNG + 2], lTT[kNG + 2];
+        int cprev = 0;
+        lz[1] = 0;
         for (int g = 1; g <= mg; ++g) {
-          vcd[mg + 1 - g] = phair(Yt[g + 1], pkn);
-          double vf = (lea[g] / pkn) - lVo[g]; if (vf < 0) vf = 0;
-          vX[g] = vf;                                                            // Q6: not reversed
+          const double iw = 1 / gw[g];
+          ltc[g] = gtc[g] * iw; lVo[g] = gVo[g] * iw; lea[g] = gea[g] * iw;
+          const double lX = gX[g] * iw, lvd = gvd[g] * iw;
+          const double lcp = cpair(ltc[g]);
+          lph[g] = phair(ltc[g], ppk);
+          const int c = (glo[g] + ghi[g] + 1) / 2;
+          lz[g + 1] = P[(long long)L.pz(c) * kTile]; lTT[g] = wget(c, WL_TT);
+          if (c - cprev == 1) lgt[g] = wget(c, WL_GTN);
+          else { double R = 0; for (int j = cprev + 1; j <= c; ++j) R += 1 / wget(j, WL_GTN); lgt[g] = 1 / R; }
+          cprev = c;
+          // stash what the Thomas set-up needs in the solver arrays (filled in reverse order below)
+          XX[mg + 1 - g] = lX; tc2[1 + mg + 1 - g] = ltc[g]; cc[g] = lcp; dd[g] = lvd;
         }
-        thomas_f(mg, vt, Vsoil, Vair, vk, vcd, cfg.n, vX, vn, cc, dd);
-        for (int g = 1; g <= mg + 2; ++g) Ye[g] = vn[mg + 3 - g];                   // mole fractions; scaled by pk after the interpolation
+        if (m + 1 - cprev == 1) lgt[mg + 1] = gtncap;
+        else { double R = 0; for (int j = cprev + 1; j <= m; ++j) R += 1 / wget(j, WL_GTN); R += 1 / gtncap; lgt[mg + 1] = 1 / R; }
+        lz[mg + 2] = p0(P0_HGT);
+        for (int g = 1; g <= mg; ++g) {
+          const double cda = cc[g] * lph[g] * (1 - dd[g]) * (lz[g + 2] - lz[g]) / 2 * timestep;       // Q10
+          double ka = lgt[g] * cc[g];
+          if (ka > cda) ka = cda;
+          k[mg + 2 - g] = ka; cdv[mg + 1 - g] = cda;
+        }
+        k[1] = lgt[mg + 1] * cpair(tabove);
+        for (int j = 1; j <= sm; ++j) {
+          k[mg + 1 + j] = lam * p0(P0_NFIX + (j - 1)); cdv[mg + j] = (Cv * p0(P0_NFIX + sm + (j - 1))) * i2ts;
+          XX[mg + j] = 0; tc2[1 + mg + j] = s0(L.soiltc(j));
+        }
+        XX[mg + 1] = Xs;
+        tc2[1] = tabove; tc2[N + 2] = tsoilp;
+        thomas_f(N, tc2, fc.tsoil, tcan, k, cdv, cfg.n, XX, tn2, cc, dd);
+        for (int j = 1; j <= sm; ++j) tnsoil[j] = tn2[mg + 1 + j];
+        // tnair = rev(tn2[1:(mg+2)]) = (soil 1, air bottom..top, tcan)
+        nn = mg + 2;
+        for (int g = 1; g <= mg + 2; ++g) Yt[g] = tn2[mg + 3 - g];
+        {                                               // ThomasV (code.R:153-169) on reversed arrays
+          double rhs = soilrh(fc.theta, p0(P0_SOILB), p0(P0_PSIE), p0(P0_SMAX), tnsoil[1]); if (rhs > 1) rhs = 1;
+          double rhsp = soilrh(fc.thetap, p0(P0_SOILB), p0(P0_PSIE), p0(P0_SMAX), ps1); if (rhsp > 1) rhsp = 1;
+          const double Vair = (tet_tcan * (relhumn / 100)) / pkn;
+          const double eap = tetens(tairp) * (relhump / 100);
+          const double Vsoil = (tetens(tnsoil[1]) * rhs) / pkn;
+          const double easp = tetens(tsoilp) * rhsp;                               // Q5
+          double vt[kNG + 4], vk[kNG + 3], vcd[kNG + 2], vX[kNG + 2], vn[kNG + 4];
+          vt[1] = eap / ppk; vt[mg + 2] = easp / ppk;
+          for (int g = 1; g <= mg; ++g) vt[1 + g] = lVo[mg + 1 - g];
+          for (int g = 1; g <= mg + 1; ++g) {
+            double gt2 = lgt[g];
+            if (g <= mg) { const double gtmx = lph[g] / (lz[g + 1] - lz[g]) * (2 * timestep); if (gt2 > gtmx) gt2 = gtmx; }
+            vk[mg + 2 - g] = gt2;
+          }
+          for (int g = 1; g <= mg; ++g) {
+            vcd[mg + 1 - g] = phair(Yt[g + 1], pkn);
+            double vf = (lea[g] / pkn) - lVo[g]; if (vf < 0) vf = 0;
+            vX[g] = vf;                                                            // Q6: not reversed
+          }
+          thomas_f(mg, vt, Vsoil, Vair, vk, vcd, cfg.n, vX, vn, cc, dd);
+          for (int g = 1; g <= mg + 2; ++g) Ye[g] = vn[mg + 3 - g];                   // mole fractions; scaled by pk after the interpolation
+        }
+        T2[1] = 0; for (int g = 1; g <= mg; ++g) T2[g + 1] = lTT[g];
+        T2[mg + 2] = TX;
+      } else {
+        // canopy air in equilibrium with the air above: soil solve with one lumped canopy conductance (code.R:854-867)
+        k[1] = (1 / cs) * cpair(tabove);
+        for (int j = 1; j <= sm; ++j) {
+          k[1 + j] = lam * p0(P0_NFIX + (j - 1)); cdv[j] = (Cv * p0(P0_NFIX + sm + (j - 1))) * i2ts;
+          XX[j] = 0; tc2[1 + j] = s0(L.soiltc(j));
+        }
+        XX[1] = Xs;
+        tc2[1] = tabove; tc2[sm + 2] = tsoilp;
+        thomas_f(sm, tc2, fc.tsoil, tcan, k, cdv, cfg.n, XX, tn2, cc, dd);
+        for (int j = 1; j <= sm; ++j) tnsoil[j] = tn2[1 + j];
+        T2[1] = 0; T2[2] = TX; Yt[1] = tnsoil[1]; Yt[2] = tcan;
+        Ye[1] = esoil; Ye[2] = eamn;                                                 // eair = (relhum/100)*tetens(tcan), code.R:863
       }
-      T2[1] = 0; for (int g = 1; g <= mg; ++g) T2[g + 1] = lTT[g];
-      T2[mg + 2] = TX;
-    } else {
-      // canopy air in equilibrium with the air above: soil solve with one lumped canopy conductance (code.R:854-867)
-      k[1] = (1 / cs) * cpair(tabove);
-      for (int j = 1; j <= sm; ++j) {
-        k[1 + j] = lam * p0(P0_NFIX + (j - 1)); cdv[j] = (Cv * p0(P0_NFIX + sm + (j - 1))) * i2ts;
-        XX[j] = 0; tc2[1 + j] = s0(L.soiltc(j));
-      }
-      XX[1] = Xs;
-      tc2[1] = tabove; tc2[sm + 2] = tsoilp;
-      thomas_f(sm, tc2, fc.tsoil, tcan, k, cdv, cfg.n, XX, tn2, cc, dd);
-      for (int j = 1; j <= sm; ++j) tnsoil[j] = tn2[1 + j];
-      T2[1] = 0; T2[2] = TX; Yt[1] = tnsoil[1]; Yt[2] = tcan; Ye[1] = esoil; Ye[2] = eamn;       // eair = (relhum/100)*tetens(tcan)
     }
   }
   mem.sweepC_begin();
-  // ---------------- sweep C: back to the m nodes, humidity, limits (code.R:846-874, 893-897) ----------------
-  const double trlw_sum = p0(P0_TRLWSUM);
-  const int selG = (int)p0(P0_SELG), selH = (int)p0(P0_SELH);
-  const double iTX = 1 / TX;
-  const double y1t = Yt[1], y2t = Yt[2], y1e = Ye[1], y2e = Ye[2];             // the common two-node case stays in registers
+  // ======================= sweep C: back to the m nodes, humidity, limits (code.R:846-874, 893-897) =======================
   double stc = 0, srh = 0, slw = 0, tnselG = 0;
-  for (int i = 1; i <= m; ++i) {
-    mem.stageC(i);
-    if (!runB || (cfg.dbg & 8)) continue;
-    const double v = mem.c_w(0), ean = mem.c_w(1);
-    double tnn, ea2;
-    if (nn == 2) {
-      const double wgt = v * iTX;
-      tnn = (1 - wgt) * y1t + wgt * y2t;
-      ea2 = (1 - wgt) * y1e + wgt * y2e;
-    } else if (!(v >= 0.0) || !(v <= TX)) { tnn = NAN; ea2 = NAN; }
-    else {                                            // layerinterp: R approx(), bisection + linear (code.R:846-847)
-      int a = 1, b = nn;
-      while (a < b - 1) { const int ab = (a + b) / 2; if (v < T2[ab]) b = ab; else a = ab; }
-      if (v == T2[b]) { tnn = Yt[b]; ea2 = Ye[b] * pkn; }
-      else if (v == T2[a]) { tnn = Yt[a]; ea2 = Ye[a] * pkn; }
-      else {
-        const double w = (v - T2[a]) / (T2[b] - T2[a]);
-        tnn = Yt[a] + (Yt[b] - Yt[a]) * w;
-        ea2 = (Ye[a] + (Ye[b] - Ye[a]) * w) * pkn;                               // ea <- vn * pk (code.R:852)
+  {
+    const double trlw_sum = p0(P0_TRLWSUM), emv = p0(P0_EMV);
+    const double skyem = mem.unpark(X_SKYEM), pkn = mem.unpark(X_PKN);
+    const int selG = (int)p0(P0_SELG), selH = (int)p0(P0_SELH);
+    const double iTX = 1 / TX;
+    const double y1t = Yt[1], y2t = Yt[2], y1e = Ye[1], y2e = Ye[2];             // the common two-node case stays in registers
+    for (int i = 1; i <= m; ++i) {
+      mem.stageC(i);
+      if (cfg.dbg & 8) continue;
+      const double v = mem.c_w(0), ean = mem.c_w(1);
+      double tnn, ea2;
+      if (nn == 2) {
+        const double wgt = v * iTX;
+        tnn = (1 - wgt) * y1t + wgt * y2t;
+        ea2 = (1 - wgt) * y1e + wgt * y2e;
+      } else if (!(v >= 0.0) || !(v <= TX)) { tnn = NAN; ea2 = NAN; }
+      else {                                            // layerinterp: R approx(), bisection + linear (code.R:846-847)
+        int a = 1, b = nn;
+        while (a < b - 1) { const int ab = (a + b) / 2; if (v < T2[ab]) b = ab; else a = ab; }
+        if (v == T2[b]) { tnn = Yt[b]; ea2 = Ye[b] * pkn; }
+        else if (v == T2[a]) { tnn = Yt[a]; ea2 = Ye[a] * pkn; }
+        else {
+          const double w = (v - T2[a]) / (T2[b] - T2[a]);
+          tnn = Yt[a] + (Yt[b] - Yt[a]) * w;
+          ea2 = (Ye[a] + (Ye[b] - Ye[a]) * w) * pkn;                               // ea <- vn * pk (code.R:852)
+        }
       }
+      double r = fdiv(ea2, 0.6108 * fexp((17.27 * tnn) * frcp(tnn + 237.3))) * 100;
+      if (r > 100) r = 100;
+      if (r < 0) r = 0;
+      double tdws;                                                               // dewpoint(tln$ea, tn), Q12
+      {
+        const bool ice = tnn < 0;
+        const double ie0 = ice ? (1 / (610.78 / 1000)) : (1 / (611.2 / 1000));
+        const double iLv = ice ? (461.5 / 2.834e6) : fdiv(461.5, 2.501e6 - 2340 * tnn);
+        tdws = frcp(1 / 273.15 - iLv * log(ean * ie0)) - 273.15;
+      }
+      const double tn = (tnn < tdws) ? tdws : tnn;
+      const double lwt = kSb * pow4(tn + 273.15);
+      const double Rlwin = trlw_sum * skyem * lwt + (1 - trlw_sum) * emv * lwt;
+      if (i == selG) tnselG = tnn;
+      if (runB) { S[(long long)L.sl(i, SL_TC) * kTile] = tn; S[(long long)L.sl(i, SL_RH) * kTile] = r; }
+      if (emit || i == selH) wput(i, WL_RLWIN, Rlwin);
+      stc += tn; srh += r; slw += Rlwin;
     }
-    double r = fdiv(ea2, 0.6108 * fexp((17.27 * tnn) * frcp(tnn + 237.3))) * 100;
-    if (r > 100) r = 100;
-    if (r < 0) r = 0;
-    double tdws;                                                               // dewpoint(tln$ea, tn), Q12
-    {
-      const bool ice = tnn < 0;
-      const double ie0 = ice ? (1 / (610.78 / 1000)) : (1 / (611.2 / 1000));
-      const double iLv = ice ? (461.5 / 2.834e6) : fdiv(461.5, 2.501e6 - 2340 * tnn);
-      tdws = frcp(1 / 273.15 - iLv * log(ean * ie0)) - 273.15;
-    }
-    const double tn = (tnn < tdws) ? tdws : tnn;
-    const double lwt = kSb * pow4(tn + 273.15);
-    const double Rlwin = trlw_sum * skyem * lwt + (1 - trlw_sum) * emv * lwt;
-    if (i == selG) tnselG = tnn;
-    S[(long long)L.sl(i, SL_TC) * kTile] = tn; S[(long long)L.sl(i, SL_RH) * kTile] = r;
-    if (emit) wput(i, WL_RLWIN, Rlwin);
-    stc += tn; srh += r; slw += Rlwin;
-    if (i == selH) { hv0 = tn; hv2 = r; hv4 = Rlwin; }
   }
-  if (!runB) return !run || fastok;
-  // ---------------- soil limits and fluxes (code.R:868-891) ----------------
+  // ======================= soil limits and fluxes (code.R:868-891), output harvest (code.R:1222-1265) =======================
+  double x0[8], x1[8];
+  mem.unpark8(X_TAIRN, x0); mem.unpark8(X_PPK, x1);
+  const double Lt = mem.unpark(X_LT), stl = mem.unpark(X_STL), ssw = mem.unpark(X_SSW);
+  const double sqphi_e = mem.unpark(X_SQPHI), uh_e = mem.unpark(X_UH), cp1_e = mem.unpark(X_CP1), gtncap_e = mem.unpark(X_GTNCAP);
+  if (!runB) return !run || fastok;               // (after the last warp-collective tensor-memory access of the step)
+  const double tairn = x0[X_TAIRN], pkn = x0[X_PKN], Rsw = x0[X_RSW], tcan = x0[X_TCAN];
+  const double ps1 = x1[X_PS1 - X_PPK], tet_tair = x1[X_TET_TAIR - X_PPK], tet_tcan = x1[X_TET_TCAN - X_PPK], tfrost = x1[X_TFROST - X_PPK];
+  const double phi_m = x1[X_PHIM - X_PPK];
+  const double hgt = p0(P0_HGT), refg = p0(P0_REFG);
   if (tnsoil[1] < tfrost) tnsoil[1] = tfrost;
   if (tnsoil[1] > tairn + 30) tnsoil[1] = tairn + 30;
   const double refm = p0(P0_REFM);
@@ -821,14 +926,14 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
   const double Rlw = kSb * 0.97 * pow4(0.5 * tnsoil[1] + 0.5 * ps1 + 273.15);
   double Gn;
   {
-    const double a = p0(P0_A0G) * sqphi;
+    const double a = p0(P0_A0G) * sqphi_e;
     const double t1 = tnselG, t0 = tnsoil[1];
     const double ph = phair((t1 + t0) / 2, pkn);
     const double e0 = exp(-a * (-1.0)), e1 = exp(-a * p0(P0_GXG1));
-    const double g = (p0(P0_CGG) * ph * uh * a) / ((e0 - e1) * phi_m);
+    const double g = (p0(P0_CGG) * ph * uh_e * a) / ((e0 - e1) * phi_m);
     const double gfree = 0.0012 * ph * qroot(fabs(t1 - t0) * p0(P0_RZG));
     const double gt2 = (g > gfree) ? g : gfree;
-    Gn = gt2 * cp1 * (t1 - t0);
+    Gn = gt2 * cp1_e * (t1 - t0);
   }
   const double net = (1 - alb) * Rsw - Rlw;
   const double Gmx = fabs(net - Lt);
@@ -836,9 +941,8 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
   if (Gn < -Gmx) Gn = -Gmx;
   const double Hn = net - Gn - Lt;
   for (int j = 1; j <= sm; ++j) sput(L.soiltc(j), tnsoil[j]);
-  sput(S0_TABOVE, tcan); sput(S0_RELHUM, relhumn); sput(S0_TAIR, tairn); sput(S0_TSOIL, fc.tsoil); sput(S0_PK, pkn); sput(S0_H, Hn);
-  sput(S0_PSIM, psi_mn); sput(S0_G, Gn); sput(S0_TCSUM, stc); sput(S0_GTCAP, gtncap);
-  // ---------------- runmodel's output harvest (code.R:1222-1265) ----------------
+  sput(S0_TABOVE, tcan); sput(S0_RELHUM, x0[X_RELHUMN]); sput(S0_TAIR, tairn); sput(S0_TSOIL, fc.tsoil); sput(S0_PK, pkn); sput(S0_H, Hn);
+  sput(S0_PSIM, x1[X_PSIM - X_PPK]); sput(S0_G, Gn); sput(S0_TCSUM, stc); sput(S0_GTCAP, gtncap_e);
   double* o = out.o;
   out.ng = ng;
   o[6] = Hn; o[7] = Gn;
@@ -850,8 +954,11 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     o[2] = r; o[3] = rsw0; o[4] = skyem0 * 5.67 * 1e-8 * pow4(tcan + 273.15); o[5] = Lt;
   }
   if (reqhgt >= 0 && reqhgt < hgt) {
-    if (selH) { o[0] = hv0; o[1] = hv1; o[2] = hv2; o[3] = hv3; o[4] = hv4; o[5] = hv5; }
-    else { for (int q = 0; q < 6; ++q) o[q] = NAN; }
+    const int selH = (int)p0(P0_SELH);
+    if (selH) {
+      o[0] = s0(L.sl(selH, SL_TC)); o[1] = s0(L.sl(selH, SL_TLEAF)); o[2] = s0(L.sl(selH, SL_RH)); o[3] = wget(selH, WL_RSWIN);
+      o[4] = wget(selH, WL_RLWIN); o[5] = wget(selH, WL_L);
+    } else { for (int q = 0; q < 6; ++q) o[q] = NAN; }
   }
   if (reqhgt <= 0) { o[0] = tnsoil[(int)p0(P0_SELS)]; o[1] = stl / m; o[2] = srh / m; o[3] = ssw / m; o[4] = slw / m; o[5] = Lt; }
   return true;

@@ -41,12 +41,19 @@ __global__ void __launch_bounds__(kTile, 4) k_transient_fast(FastArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* buf = reinterpret_cast<double*>(smem_raw);
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + 2 * kStageRows * kTile * 8);
+  unsigned* tmem_base_s = reinterpret_cast<unsigned*>(bar + 2);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1); mbar_init(bar + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x < 32) {         // one warp allocates the block's 128 tensor-memory columns (64 doubles per thread of scratch)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "n"(128) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   fence_proxy_async();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const long long c = (long long)blockIdx.x * kTile + threadIdx.x;
   const bool live = c < a.t.ncol;
   FastLayout L{a.t.m, a.t.sm};
@@ -56,7 +63,11 @@ __global__ void __launch_bounds__(kTile, 4) k_transient_fast(FastArgs a) {
   mem.Wt = a.W + (long long)blockIdx.x * L.nW() * kTile;
   mem.P = mem.Pt + threadIdx.x; mem.S = const_cast<double*>(mem.St) + threadIdx.x; mem.W = const_cast<double*>(mem.Wt) + threadIdx.x;
   mem.buf = buf; mem.bar = bar; mem.lane = threadIdx.x; mem.k = 0; mem.cur = buf; mem.pol = l2_evict_first_policy();
+  mem.tbase = *tmem_base_s + ((unsigned)((threadIdx.x >> 5) * 32) << 16);
   fast_run_column<PipeMem, MM, MS>(a, mem, live ? c : a.t.ncol - 1, live);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_base_s), "n"(128) : "memory");
 }
 template <int MM, int MS>
 __global__ void __launch_bounds__(kBlock) k_onestep(OneStepArgs a) {
