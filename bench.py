@@ -143,8 +143,9 @@ def run_reference(args):
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": "C3 (bounded sample)", "columns": ncol_s, "hours_per_step": args.hours, "m": M, "sm": SM,
-                       "mode": "transient"},
+            "config": {"workload": "C3", "columns_per_gpu": args.columns, "hours_per_step": args.hours, "m": M, "sm": SM,
+                       "mode": "transient", "spin_steps": args.spin,
+                       "sample": "bounded: %d columns of the C3 workload per step (the reference path is CPU-only)" % ncol_s},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d columns x %d hourly steps per bench step, OpenMP over columns; C++ restatement of the R "
                                        "path (R and microctools are not installable here)" % (ncol_s, args.hours)},
@@ -261,25 +262,32 @@ def main():
         except Exception:
             pass
         per_gpu_rate = value / world
+        # Roofline of the dominant kernel (k_transient_fast): this path is FP64-pipe bound (DESIGN.md "Measurement").
+        #  achieved = algorithmic FP64 work per column-timestep (operator census of the shipped algorithm, 2 flop per FP64 issue slot,
+        #             profiles/cost_per_colstep.json) x column-timesteps of the timed launches / their CUDA-event time;
+        #  peak     = DFMA probe measured in this run (MEASURED_PEAKS.json carries HBM and bf16 only, no FP64 figure).
+        # The HBM view is reported next to it: measured DRAM traffic per column-timestep (ncu) x rate against the measured copy peak.
         flop_per = cost.get("fp64_flop_per_colstep")
         bytes_per = cost.get("algorithmic_bytes_per_colstep", 152.0)
         traffic_per = cost.get("dram_bytes_per_colstep")
-        roof = {"bound": "fp64", "unit": "TFLOP/s",
-                "achieved": (flop_per * per_gpu_rate / 1e12) if flop_per else None,
-                "peak": peak_fp64, "peak_source": "mc_fp64_peak_tflops DFMA probe, this run (MEASURED_PEAKS.json has no FP64 entry)",
-                "frac": (flop_per * per_gpu_rate / 1e12 / peak_fp64) if (flop_per and peak_fp64 > 0) else None,
+        ach = (flop_per * per_gpu_rate / 1e12) if flop_per else None
+        roof = {"bound": "fp64", "unit": "TFLOP/s", "achieved": ach, "peak": peak_fp64,
+                "peak_source": "of measured: mc_fp64_peak_tflops DFMA probe in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "frac": (ach / peak_fp64) if (ach and peak_fp64 > 0) else None,
                 "traffic": (traffic_per * ncol * hours) if traffic_per else None,
-                "flop_per_colstep": flop_per,
-                "hbm": {"achieved": bytes_per * per_gpu_rate / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": bytes_per * per_gpu_rate / 1e9 / hbm_peak,
-                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
-                        "algorithmic_bytes_per_colstep": bytes_per}}
+                "flop_per_colstep": flop_per, "flop_source": "tools/opcount: shipped streaming algorithm, 2 x FP64 issue slots",
+                "hbm": {"achieved": (traffic_per or bytes_per) * per_gpu_rate / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": (traffic_per or bytes_per) * per_gpu_rate / 1e9 / hbm_peak,
+                        "peak_source": "of measured: MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "of fallback 6650",
+                        "bytes_per_colstep_measured": traffic_per, "algorithmic_bytes_per_colstep": bytes_per}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": dev_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": "C3", "columns_per_gpu": ncol, "hours_per_step": hours, "m": M, "sm": SM, "mode": "transient",
                            "spin_steps": args.spin, "forcing": "shared synthetic hourly series + per-column affine perturbation",
-                           "outputs": "per-column mean/min/max of tout,tleaf + flags", "l2": "state 2.2 KB/column > L2, no flush"},
+                           "outputs": "per-column mean/min/max of tout,tleaf + flags",
+                           "l2": "per-launch working set (state + geometry + work rows, 7.4 KB/column = 7.4 GB per 10^6 columns) >> 126 MB L2, no flush",
+                           "kernel": "k_geom + k_transient_fast per launch (TMA-staged streaming form)"},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_total / K * 1e3},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "nonfinite_columns": nonfinite}

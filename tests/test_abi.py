@@ -82,3 +82,19 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dp, f)).read()
                 assert "pyoracle" not in src and "mc_oracle" not in src and "oracle/" not in src, os.path.join(dp, f)
+
+
+def test_r_shim_compiles_against_stub_headers_and_binds_only_declared_symbols():
+    """r-package/src/shim.c is the .Call binding a maintainer adds. R is not installed here, so it is
+    syntax-checked against minimal stand-in R headers (tests/rstub) and every mc_* call must be a declared ABI symbol."""
+    import subprocess
+    shim = os.path.join(ROOT, "r-package", "src", "shim.c")
+    subprocess.check_call(["gcc", "-std=c11", "-fsyntax-only", "-I" + os.path.join(ROOT, "tests", "rstub"), "-I" + os.path.join(ROOT, "include"), shim])
+    used = set(re.findall(r"\b(mc_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", open(shim).read(), flags=re.S)))
+    assert used and used <= set(_declared_functions()), used - set(_declared_functions())
+    rsrc = open(os.path.join(ROOT, "r-package", "R", "microclimc_b200.R")).read()
+    for fn in ("paraminit", "soilinit", "runonestep", "spinup", "runmodel", "runmodelS", "runmodel_batch", "runmodelS_batch"):
+        assert re.search(r"^%s <- function\(" % fn, rsrc, flags=re.M), fn
+    # reference signatures kept verbatim (R/code.R:687-689, 1125-1129)
+    assert "runonestep <- function(climvars, previn, vegp, soilp, timestep, tme, lat, long, edgedist = 1000, sdepth = 2, reqhgt = NA, zu = 2," in rsrc
+    assert "runmodel <- function(climdata, vegp, soilp, lat, long, edgedist = 100, reqhgt = NA, sdepth = 2, zu = 2, theta = 0.3, merid = 0," in rsrc
