@@ -66,6 +66,7 @@ struct FastArgs {
   double* P;                // [ntile][nP][128]  geometry, written by geom_column
   double* S;                // [ntile][nS][128]  working state
   double* W;                // [ntile][nW][128]  inter-pass work rows
+  unsigned long long* dbgbuf;   // [8] phase cycle counters (MC_DBG_SKIP bit 16) or null
   int spin_mode;            // 1: paraminit + t.spin_steps steps on forcing row 0 with the running mean of H (spinup, code.R:982-1013)
 };
 
@@ -161,6 +162,12 @@ struct DirectMem {
   MC_HD void park_done() {}
   MC_HD void unpark8(int slot0, double* v) { for (int q = 0; q < 8; ++q) v[q] = parked[slot0 + q]; }
   MC_HD double unpark(int slot) { return parked[slot]; }
+  MC_HD void park2(int slot, double a, double b) { parked[slot] = a; parked[slot + 1] = b; }
+  MC_HD void unpark2(int slot, double& a, double& b) { a = parked[slot]; b = parked[slot + 1]; }
+  double scratch[2 * kStageRows];               // stands in for the idle stage buffers (PipeMem::scr_*)
+  MC_HD double scr_get(int idx) const { return scratch[idx]; }
+  MC_HD void scr_put(int idx, double v) { scratch[idx] = v; }
+  MC_HD int warp_max(int v) const { return v; }
   MC_HD void step_begin() {}
   MC_HD void sweepB_begin() {}
   MC_HD void sweepC_begin() {}
@@ -230,11 +237,28 @@ struct PipeMem {
   // (thread t of warp w <-> lane 32*(w%4) + t%32).  Step scalars that are only needed once per layer are parked there instead
   // of being spilled to local memory (12-cycle LDTM vs an L2 round trip).  All 32 lanes must execute these together.
   unsigned tbase;                              // TMEM address of this warp's lane quarter, column 0 of the allocation
+  long long tcyc[8], tlast;                    // phase timing (MC_DBG_SKIP bit 16)
   MC_D void park(int slot, double v) {
     __syncwarp();
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(tbase + 2 * slot), "r"(__double2loint(v)), "r"(__double2hiint(v)));
   }
   MC_D void park_done() { asm volatile("tcgen05.wait::st.sync.aligned;"); }
+  MC_D void park2(int slot, double a, double b) {
+    __syncwarp();
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tbase + 2 * slot), "r"(__double2loint(a)),
+                 "r"(__double2hiint(a)), "r"(__double2loint(b)), "r"(__double2hiint(b)));
+  }
+  MC_D void unpark2(int slot, double& a, double& b) {
+    unsigned r0, r1, r2, r3;
+    __syncwarp();
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(tbase + 2 * slot));
+    asm volatile("tcgen05.wait::ld.sync.aligned;");
+    a = __hiloint2double(r1, r0); b = __hiloint2double(r3, r2);
+  }
+  // per-thread scratch in the stage buffers while no stage is in flight (54 doubles: row idx of the two buffers, own lane)
+  MC_D double scr_get(int idx) const { return buf[idx * kTile + lane]; }
+  MC_D void scr_put(int idx, double v) { buf[idx * kTile + lane] = v; }
+  MC_D int warp_max(int v) const { __syncwarp(); return __reduce_max_sync(0xffffffffu, v); }
   MC_D double unpark(int slot) {
     unsigned lo, hi;
     __syncwarp();
@@ -382,7 +406,75 @@ MC_HD void thomas_f(int N, double* tcv, double tmsoil, double tairv, const doubl
   }
 }
 
+// Scratch map of the solves (indices into Mem::scr_*; the C stages later overwrite rows 0, 1, 27, 28 only):
+//   heat   : K(i) at SK0+i (i = 1..17), CD(i) at SCD0+i (1..16), TC(i) at STC0+i (1..18; holds the solution afterwards)
+//   vapour : K, CD, TC in the (then dead) heat K/CD rows;  node arrays for sweep C: T2, Yt, Ye (1..8 each)
+enum { SK0 = 0, SCD0 = 17, STC0 = 33, VK0 = 0, VCD0 = 8, VTC0 = 15, NT20 = 1, NYT0 = 9, NYE0 = 17, KS_CC = 32 };
+static_assert(STC0 + kNG + 10 + 2 < 2 * kStageRows, "solver scratch exceeds the two stage buffers");
+
+// Thomas (code.R:94-125) in fused form: one forward pass forms the right-hand side on the fly and eliminates, one backward
+// pass substitutes and applies the old-stencil limits (quirk Q11).  Coefficients come from the scratch rows, the elimination
+// factors (cc, dd) go through tensor memory.  Same operations in the same order as Column::thomas.  Warp-collective: every lane
+// calls it (N may differ per lane; N = 0 lanes only keep the tensor-memory accesses aligned).
+template <class Mem>
+MC_HD void thomas_s(Mem& mem, int k0, int cd0, int tc0, int N, double tmsoil, double tairv, double f, const double* xv, int nx) {
+  const int Nw = mem.warp_max(N);
+  const double g = 1 - f;
+  double t_lo = 0, t_mid = 0, k_lo = 0, a1p = 0, ccp = 0, dnp = 0, tnN1 = 0;
+  if (N >= 1) {
+    t_lo = mem.scr_get(tc0 + 1);
+    t_mid = mem.scr_get(tc0 + 2) + g * (nx >= 1 ? xv[1] : 0.0);
+    k_lo = mem.scr_get(k0 + 1);
+  }
+  for (int x = 2; x <= Nw + 1; ++x) {
+    double c = 0, dn = 0;
+    if (x <= N + 1) {
+      const double k_mid = mem.scr_get(k0 + x), cd = mem.scr_get(cd0 + x - 1);
+      double t_hi = mem.scr_get(tc0 + x + 1);
+      if (x + 1 <= N + 1) t_hi = t_hi + g * (x <= nx ? xv[x] : 0.0);
+      double d = g * k_lo * t_lo + (cd - g * (k_mid + k_lo)) * t_mid + g * k_mid * t_hi;
+      if (x == 2) d = d + k_lo * tairv * f;
+      if (x == N + 1) d = d + k_mid * f * tmsoil;
+      double b = f * (k_mid + k_lo) + cd;
+      if (x > 2) { d = d - a1p * dnp; b = b - a1p * ccp; }
+      mem.scr_put(tc0 + x, t_mid);                     // tcv' = tcv + (1-f) X, needed again for the limits
+      if (x <= N) {
+        const double ib = frcp(b);
+        const double a1 = -k_mid * f;
+        c = a1 * ib; dn = d * ib;
+        a1p = a1; ccp = c; dnp = dn;
+      } else tnN1 = fdiv(d, b);
+      t_lo = t_mid; t_mid = t_hi; k_lo = k_mid;
+    }
+    mem.park2(KS_CC + 2 * (x - 2), c, dn);
+  }
+  mem.park_done();
+  double tu = tnN1, t_up = 0, t_c = 0;
+  for (int x = Nw + 1; x >= 2; --x) {
+    double c, dn;
+    mem.unpark2(KS_CC + 2 * (x - 2), c, dn);
+    if (x <= N + 1) {
+      if (x == N + 1) { t_up = mem.scr_get(tc0 + N + 2); t_c = mem.scr_get(tc0 + N + 1); }
+      else tu = dn - c * tu;
+      const double t_dn = mem.scr_get(tc0 + x - 1);
+      const double xmn = dmin(dmin(t_c, t_dn), t_up), xmx = dmax(dmax(t_c, t_dn), t_up);
+      double v = tu;
+      if (v < xmn) v = xmn;
+      if (v > xmx) v = xmx;
+      mem.scr_put(tc0 + x, v + f * ((x - 1) <= nx ? xv[x - 1] : 0.0));
+      t_up = t_c; t_c = t_dn;
+    }
+  }
+}
+
 struct StepOut { double o[8]; int ng; };
+
+// wall-clock per phase of the step (MC_DBG_SKIP bit 16): one lane per block accumulates clock64() deltas
+#if defined(__CUDA_ARCH__)
+#define MC_TICK(slot) do { if (cfg.dbg & 16) { long long t_ = clock64(); mem.tcyc[slot] += t_ - mem.tlast; mem.tlast = t_; } } while (0)
+#else
+#define MC_TICK(slot) ((void)0)
+#endif
 
 // Step context: per-thread scalars handed from one phase of the step to the next.  On the device they live in tensor
 // memory (PipeMem::park / unpark), so that no phase has to keep another phase's values in registers (or spill them to
@@ -412,6 +504,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
   auto sput = [=](int r, double v) { S[(long long)r * kTile] = v; };
   auto wput = [=](int i, int r, double v) { W[(long long)L.wl(i, r) * kTile] = v; };
   auto wget = [=](int i, int r) { return W[(long long)L.wl(i, r) * kTile]; };
+  MC_TICK(7);
   mem.step_begin();
   bool fastok = run;
   // ======================= phase 0: scalars of the step (code.R:700-745) =======================
@@ -489,6 +582,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     mem.park(X_TSOILP, s0(S0_TSOIL)); mem.park(X_PHA, pha); mem.park(X_TC1, tc1);
     mem.park_done();
   }
+  MC_TICK(0);
   // ======================= sweep A: wind and turbulent conductances, top -> bottom (code.R:747-770) =======================
   {
     double sfx = 0, Rtot = 0, Ctot = 0, cs = 0;
@@ -532,6 +626,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     if (!(Rtot * Ctot < (double)((kNG + 1) * (kNG + 1)) * cfg.timestep * (1 - 1e-9))) fastok = false;
     mem.park(X_UH, uh); mem.park(X_SQPHI, sqphi); mem.park(X_CS, cs); mem.park(X_GTNCAP, gtncap); mem.park(X_RGCAP, rgcap);
   }
+  MC_TICK(1);
   mem.sweepB_begin();
   // ======================= scalars of sweep B: radiation geometry, reference vapour (code.R:776-785) =======================
   bool day;
@@ -572,6 +667,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     mem.park(X_CV, (p0(P0_CVDRY) + 4.18 * fc.theta) * 1e6);
     mem.park_done();
   }
+  MC_TICK(2);
   // ======================= sweep B: leafabs + leaftemp, bottom -> top, with the merged-layer sums =======================
   // layermerge / layeraverage bookkeeping (code.R:772, 814): closed groups 1..ng and the open one
   int ng = 0, glo[kNG + 2], ghi[kNG + 2];
@@ -761,11 +857,12 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     mem.park(X_XS, Xs); mem.park(X_CP1, cp1); mem.park(X_TT, TT); mem.park(X_LT, Lt); mem.park(X_STL, stl); mem.park(X_SSW, ssw);
     mem.park_done();
   }
+  MC_TICK(3);
   // ======================= heat and vapour exchange on the merged nodes (code.R:813-867) =======================
-  double tnsoil[MS + 2];
-  double T2[kNG + 3], Yt[kNG + 3], Ye[kNG + 3];     // interpolation nodes (cumulative resistance, temperature, vapour pressure)
-  int nn = 2;
-  double TX;
+  // Solver storage: coefficients in the block's idle stage buffers, elimination factors in tensor memory; ONE Thomas call site
+  // per solve for both branches (equilibrium = no merged air node), so warps with mixed lanes do not run the solves twice.
+  int nn = 2, mgx = 0;
+  double TX, y1t = 0, y2t = 0, y1e = 0, y2e = 0;
   {
     double x0[8], x1[8], x2[8];
     mem.unpark8(X_TAIRN, x0); mem.unpark8(X_PPK, x1); mem.unpark8(X_TSOILP, x2);
@@ -777,88 +874,89 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     const double timestep = cfg.timestep, i2ts = 1 / (2 * timestep);
     TX = TT + (pha / gtncap) * 2;
     if (!(cfg.dbg & 4)) {
-      double k[kNG + MS + 3], cdv[kNG + MS + 2], XX[kNG + MS + 2], tc2[kNG + MS + 4], tn2[kNG + MS + 4], cc[kNG + MS + 4], dd[kNG + MS + 4];
-      if (ng > 1) {
-        const int mg = ng, N = mg + sm;
-        double ltc[kNG + 2], lgt[kNG + 3], lz[kNG + 4], lVo[kNG + 2], lea[kNG + 2], lph[kNG + 2], lTT[kNG + 2];
+      mgx = (ng > 1) ? ng : 0;
+      const int mg = mgx, N = mg + sm;
+      double ltc[kNG + 2], lgt[kNG + 3], lz[kNG + 4], lVo[kNG + 2], lea[kNG + 2], lph[kNG + 2], lTT[kNG + 2], xv[kNG + 3], vX[kNG + 2], Yt[kNG + 3];
+      if (mg > 0) {                                   // layeraverage (code.R:814) and the air part of the system (code.R:815-826)
         int cprev = 0;
         lz[1] = 0;
         for (int g = 1; g <= mg; ++g) {
           const double iw = 1 / gw[g];
           ltc[g] = gtc[g] * iw; lVo[g] = gVo[g] * iw; lea[g] = gea[g] * iw;
-          const double lX = gX[g] * iw, lvd = gvd[g] * iw;
-          const double lcp = cpair(ltc[g]);
           lph[g] = phair(ltc[g], ppk);
           const int c = (glo[g] + ghi[g] + 1) / 2;
           lz[g + 1] = P[(long long)L.pz(c) * kTile]; lTT[g] = wget(c, WL_TT);
           if (c - cprev == 1) lgt[g] = wget(c, WL_GTN);
           else { double R = 0; for (int j = cprev + 1; j <= c; ++j) R += 1 / wget(j, WL_GTN); lgt[g] = 1 / R; }
           cprev = c;
-          // stash what the Thomas set-up needs in the solver arrays (filled in reverse order below)
-          XX[mg + 1 - g] = lX; tc2[1 + mg + 1 - g] = ltc[g]; cc[g] = lcp; dd[g] = lvd;
+          xv[mg + 1 - g] = gX[g] * iw;
         }
         if (m + 1 - cprev == 1) lgt[mg + 1] = gtncap;
         else { double R = 0; for (int j = cprev + 1; j <= m; ++j) R += 1 / wget(j, WL_GTN); R += 1 / gtncap; lgt[mg + 1] = 1 / R; }
         lz[mg + 2] = p0(P0_HGT);
         for (int g = 1; g <= mg; ++g) {
-          const double cda = cc[g] * lph[g] * (1 - dd[g]) * (lz[g + 2] - lz[g]) / 2 * timestep;       // Q10
-          double ka = lgt[g] * cc[g];
+          const double lcp = cpair(ltc[g]), lvd = gvd[g] * (1 / gw[g]);
+          const double cda = lcp * lph[g] * (1 - lvd) * (lz[g + 2] - lz[g]) / 2 * timestep;       // Q10
+          double ka = lgt[g] * lcp;
           if (ka > cda) ka = cda;
-          k[mg + 2 - g] = ka; cdv[mg + 1 - g] = cda;
+          mem.scr_put(SK0 + mg + 2 - g, ka); mem.scr_put(SCD0 + mg + 1 - g, cda); mem.scr_put(STC0 + 1 + mg + 1 - g, ltc[g]);
         }
-        k[1] = lgt[mg + 1] * cpair(tabove);
-        for (int j = 1; j <= sm; ++j) {
-          k[mg + 1 + j] = lam * p0(P0_NFIX + (j - 1)); cdv[mg + j] = (Cv * p0(P0_NFIX + sm + (j - 1))) * i2ts;
-          XX[mg + j] = 0; tc2[1 + mg + j] = s0(L.soiltc(j));
-        }
-        XX[mg + 1] = Xs;
-        tc2[1] = tabove; tc2[N + 2] = tsoilp;
-        thomas_f(N, tc2, fc.tsoil, tcan, k, cdv, cfg.n, XX, tn2, cc, dd);
-        for (int j = 1; j <= sm; ++j) tnsoil[j] = tn2[mg + 1 + j];
-        // tnair = rev(tn2[1:(mg+2)]) = (soil 1, air bottom..top, tcan)
-        nn = mg + 2;
-        for (int g = 1; g <= mg + 2; ++g) Yt[g] = tn2[mg + 3 - g];
-        {                                               // ThomasV (code.R:153-169) on reversed arrays
-          double rhs = soilrh(fc.theta, p0(P0_SOILB), p0(P0_PSIE), p0(P0_SMAX), tnsoil[1]); if (rhs > 1) rhs = 1;
-          double rhsp = soilrh(fc.thetap, p0(P0_SOILB), p0(P0_PSIE), p0(P0_SMAX), ps1); if (rhsp > 1) rhsp = 1;
-          const double Vair = (tet_tcan * (relhumn / 100)) / pkn;
-          const double eap = tetens(tairp) * (relhump / 100);
-          const double Vsoil = (tetens(tnsoil[1]) * rhs) / pkn;
-          const double easp = tetens(tsoilp) * rhsp;                               // Q5
-          double vt[kNG + 4], vk[kNG + 3], vcd[kNG + 2], vX[kNG + 2], vn[kNG + 4];
-          vt[1] = eap / ppk; vt[mg + 2] = easp / ppk;
-          for (int g = 1; g <= mg; ++g) vt[1 + g] = lVo[mg + 1 - g];
-          for (int g = 1; g <= mg + 1; ++g) {
-            double gt2 = lgt[g];
-            if (g <= mg) { const double gtmx = lph[g] / (lz[g + 1] - lz[g]) * (2 * timestep); if (gt2 > gtmx) gt2 = gtmx; }
-            vk[mg + 2 - g] = gt2;
-          }
-          for (int g = 1; g <= mg; ++g) {
-            vcd[mg + 1 - g] = phair(Yt[g + 1], pkn);
-            double vf = (lea[g] / pkn) - lVo[g]; if (vf < 0) vf = 0;
-            vX[g] = vf;                                                            // Q6: not reversed
-          }
-          thomas_f(mg, vt, Vsoil, Vair, vk, vcd, cfg.n, vX, vn, cc, dd);
-          for (int g = 1; g <= mg + 2; ++g) Ye[g] = vn[mg + 3 - g];                   // mole fractions; scaled by pk after the interpolation
-        }
-        T2[1] = 0; for (int g = 1; g <= mg; ++g) T2[g + 1] = lTT[g];
-        T2[mg + 2] = TX;
+        mem.scr_put(SK0 + 1, lgt[mg + 1] * cpair(tabove));
       } else {
-        // canopy air in equilibrium with the air above: soil solve with one lumped canopy conductance (code.R:854-867)
-        k[1] = (1 / cs) * cpair(tabove);
-        for (int j = 1; j <= sm; ++j) {
-          k[1 + j] = lam * p0(P0_NFIX + (j - 1)); cdv[j] = (Cv * p0(P0_NFIX + sm + (j - 1))) * i2ts;
-          XX[j] = 0; tc2[1 + j] = s0(L.soiltc(j));
+        mem.scr_put(SK0 + 1, (1 / cs) * cpair(tabove));   // one lumped conductance for the lower half of the canopy (code.R:856-857)
+      }
+      xv[mg + 1] = Xs;
+#pragma unroll
+      for (int j = 1; j <= MS; ++j) if (j <= sm) {       // soil nodes (unrolled: the row loads are issued together)
+        mem.scr_put(SK0 + mg + 1 + j, lam * p0(P0_NFIX + (j - 1))); mem.scr_put(SCD0 + mg + j, (Cv * p0(P0_NFIX + sm + (j - 1))) * i2ts);
+        mem.scr_put(STC0 + 1 + mg + j, s0(L.soiltc(j)));
+      }
+      mem.scr_put(STC0 + 1, tabove); mem.scr_put(STC0 + N + 2, tsoilp);
+      thomas_s(mem, SK0, SCD0, STC0, N, fc.tsoil, tcan, cfg.n, xv, mg + 1);
+      // STC(2..N+1) now holds tn2 (code.R:829); tnsoil[j] = tn2[mg+1+j]
+      const double tns1 = mem.scr_get(STC0 + mg + 2);
+      double Vsoil = 0, Vair = 0;
+      if (mg > 0) {
+        // tnair = rev(tn2[1:(mg+2)]) = (soil 1, air bottom..top, tcan); ThomasV (code.R:153-169) on reversed arrays
+        nn = mg + 2;
+        Yt[mg + 2] = tcan;
+        for (int g = 1; g <= mg + 1; ++g) Yt[g] = mem.scr_get(STC0 + mg + 3 - g);
+        double rhs = soilrh(fc.theta, p0(P0_SOILB), p0(P0_PSIE), p0(P0_SMAX), tns1); if (rhs > 1) rhs = 1;
+        double rhsp = soilrh(fc.thetap, p0(P0_SOILB), p0(P0_PSIE), p0(P0_SMAX), ps1); if (rhsp > 1) rhsp = 1;
+        Vair = (tet_tcan * (relhumn / 100)) / pkn;
+        const double eap = tetens(tairp) * (relhump / 100);
+        Vsoil = (tetens(tns1) * rhs) / pkn;
+        const double easp = tetens(tsoilp) * rhsp;                               // Q5
+        mem.scr_put(VTC0 + 1, eap / ppk); mem.scr_put(VTC0 + mg + 2, easp / ppk);
+        for (int g = 1; g <= mg; ++g) mem.scr_put(VTC0 + 1 + g, lVo[mg + 1 - g]);
+        for (int g = 1; g <= mg + 1; ++g) {
+          double gt2 = lgt[g];
+          if (g <= mg) { const double gtmx = lph[g] / (lz[g + 1] - lz[g]) * (2 * timestep); if (gt2 > gtmx) gt2 = gtmx; }
+          mem.scr_put(VK0 + mg + 2 - g, gt2);
         }
-        XX[1] = Xs;
-        tc2[1] = tabove; tc2[sm + 2] = tsoilp;
-        thomas_f(sm, tc2, fc.tsoil, tcan, k, cdv, cfg.n, XX, tn2, cc, dd);
-        for (int j = 1; j <= sm; ++j) tnsoil[j] = tn2[1 + j];
-        T2[1] = 0; T2[2] = TX; Yt[1] = tnsoil[1]; Yt[2] = tcan;
-        Ye[1] = esoil; Ye[2] = eamn;                                                 // eair = (relhum/100)*tetens(tcan), code.R:863
+        for (int g = 1; g <= mg; ++g) {
+          mem.scr_put(VCD0 + mg + 1 - g, phair(Yt[g + 1], pkn));
+          double vf = (lea[g] / pkn) - lVo[g]; if (vf < 0) vf = 0;
+          vX[g] = vf;                                                            // Q6: not reversed
+        }
+      }
+      thomas_s(mem, VK0, VCD0, VTC0, mg, Vsoil, Vair, cfg.n, vX, mg);           // (lanes without merged layers idle through it)
+      if (mg > 0) {
+        // Vn = rev(vn): Ye[g] = vn[mg+3-g] with vn[1] = Vair, vn[mg+2] = Vsoil; mole fractions, scaled by pk after the interpolation
+        double Ye[kNG + 3];
+        Ye[1] = Vsoil; Ye[mg + 2] = Vair;
+        for (int g = 2; g <= mg + 1; ++g) Ye[g] = mem.scr_get(VTC0 + mg + 3 - g);
+        // node arrays for sweep C, in scratch rows the C stages do not touch
+        for (int g = 1; g <= mg + 2; ++g) { mem.scr_put(NYT0 + g, Yt[g]); mem.scr_put(NYE0 + g, Ye[g]); }
+        mem.scr_put(NT20 + 1, 0.0);
+        for (int g = 1; g <= mg; ++g) mem.scr_put(NT20 + g + 1, lTT[g]);
+        mem.scr_put(NT20 + mg + 2, TX);
+      } else {
+        y1t = tns1; y2t = tcan; y1e = esoil; y2e = eamn;                           // eair = (relhum/100)*tetens(tcan), code.R:863
       }
     }
   }
+  MC_TICK(4);
   mem.sweepC_begin();
   // ======================= sweep C: back to the m nodes, humidity, limits (code.R:846-874, 893-897) =======================
   double stc = 0, srh = 0, slw = 0, tnselG = 0;
@@ -867,7 +965,6 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     const double skyem = mem.unpark(X_SKYEM), pkn = mem.unpark(X_PKN);
     const int selG = (int)p0(P0_SELG), selH = (int)p0(P0_SELH);
     const double iTX = 1 / TX;
-    const double y1t = Yt[1], y2t = Yt[2], y1e = Ye[1], y2e = Ye[2];             // the common two-node case stays in registers
     for (int i = 1; i <= m; ++i) {
       mem.stageC(i);
       if (cfg.dbg & 8) continue;
@@ -880,13 +977,15 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
       } else if (!(v >= 0.0) || !(v <= TX)) { tnn = NAN; ea2 = NAN; }
       else {                                            // layerinterp: R approx(), bisection + linear (code.R:846-847)
         int a = 1, b = nn;
-        while (a < b - 1) { const int ab = (a + b) / 2; if (v < T2[ab]) b = ab; else a = ab; }
-        if (v == T2[b]) { tnn = Yt[b]; ea2 = Ye[b] * pkn; }
-        else if (v == T2[a]) { tnn = Yt[a]; ea2 = Ye[a] * pkn; }
+        while (a < b - 1) { const int ab = (a + b) / 2; if (v < mem.scr_get(NT20 + ab)) b = ab; else a = ab; }
+        const double T2a = mem.scr_get(NT20 + a), T2b = mem.scr_get(NT20 + b);
+        const double Yta = mem.scr_get(NYT0 + a), Ytb = mem.scr_get(NYT0 + b), Yea = mem.scr_get(NYE0 + a), Yeb = mem.scr_get(NYE0 + b);
+        if (v == T2b) { tnn = Ytb; ea2 = Yeb * pkn; }
+        else if (v == T2a) { tnn = Yta; ea2 = Yea * pkn; }
         else {
-          const double w = (v - T2[a]) / (T2[b] - T2[a]);
-          tnn = Yt[a] + (Yt[b] - Yt[a]) * w;
-          ea2 = (Ye[a] + (Ye[b] - Ye[a]) * w) * pkn;                               // ea <- vn * pk (code.R:852)
+          const double w = (v - T2a) / (T2b - T2a);
+          tnn = Yta + (Ytb - Yta) * w;
+          ea2 = (Yea + (Yeb - Yea) * w) * pkn;                                     // ea <- vn * pk (code.R:852)
         }
       }
       double r = fdiv(ea2, 0.6108 * fexp((17.27 * tnn) * frcp(tnn + 237.3))) * 100;
@@ -908,6 +1007,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
       stc += tn; srh += r; slw += Rlwin;
     }
   }
+  MC_TICK(5);
   // ======================= soil limits and fluxes (code.R:868-891), output harvest (code.R:1222-1265) =======================
   double x0[8], x1[8];
   mem.unpark8(X_TAIRN, x0); mem.unpark8(X_PPK, x1);
@@ -918,16 +1018,17 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
   const double ps1 = x1[X_PS1 - X_PPK], tet_tair = x1[X_TET_TAIR - X_PPK], tet_tcan = x1[X_TET_TCAN - X_PPK], tfrost = x1[X_TFROST - X_PPK];
   const double phi_m = x1[X_PHIM - X_PPK];
   const double hgt = p0(P0_HGT), refg = p0(P0_REFG);
-  if (tnsoil[1] < tfrost) tnsoil[1] = tfrost;
-  if (tnsoil[1] > tairn + 30) tnsoil[1] = tairn + 30;
+  double tns1 = mem.scr_get(STC0 + mgx + 2);                                   // tnsoil[1] = tn2[mg+2] (code.R:830, 859)
+  if (tns1 < tfrost) tns1 = tfrost;
+  if (tns1 > tairn + 30) tns1 = tairn + 30;
   const double refm = p0(P0_REFM);
   const double shade = (1 - exp(-refm * p0(P0_SUMPAI)));
   const double alb = shade * refm + (1 - shade) * refg;
-  const double Rlw = kSb * 0.97 * pow4(0.5 * tnsoil[1] + 0.5 * ps1 + 273.15);
+  const double Rlw = kSb * 0.97 * pow4(0.5 * tns1 + 0.5 * ps1 + 273.15);
   double Gn;
   {
     const double a = p0(P0_A0G) * sqphi_e;
-    const double t1 = tnselG, t0 = tnsoil[1];
+    const double t1 = tnselG, t0 = tns1;
     const double ph = phair((t1 + t0) / 2, pkn);
     const double e0 = exp(-a * (-1.0)), e1 = exp(-a * p0(P0_GXG1));
     const double g = (p0(P0_CGG) * ph * uh_e * a) / ((e0 - e1) * phi_m);
@@ -940,9 +1041,11 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
   if (Gn > Gmx) Gn = Gmx;
   if (Gn < -Gmx) Gn = -Gmx;
   const double Hn = net - Gn - Lt;
-  for (int j = 1; j <= sm; ++j) sput(L.soiltc(j), tnsoil[j]);
+  sput(L.soiltc(1), tns1);
+  for (int j = 2; j <= sm; ++j) sput(L.soiltc(j), mem.scr_get(STC0 + mgx + 1 + j));
   sput(S0_TABOVE, tcan); sput(S0_RELHUM, x0[X_RELHUMN]); sput(S0_TAIR, tairn); sput(S0_TSOIL, fc.tsoil); sput(S0_PK, pkn); sput(S0_H, Hn);
   sput(S0_PSIM, x1[X_PSIM - X_PPK]); sput(S0_G, Gn); sput(S0_TCSUM, stc); sput(S0_GTCAP, gtncap_e);
+  MC_TICK(6);
   double* o = out.o;
   out.ng = ng;
   o[6] = Hn; o[7] = Gn;
@@ -960,7 +1063,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
       o[4] = wget(selH, WL_RLWIN); o[5] = wget(selH, WL_L);
     } else { for (int q = 0; q < 6; ++q) o[q] = NAN; }
   }
-  if (reqhgt <= 0) { o[0] = tnsoil[(int)p0(P0_SELS)]; o[1] = stl / m; o[2] = srh / m; o[3] = ssw / m; o[4] = slw / m; o[5] = Lt; }
+  if (reqhgt <= 0) { const int ss = (int)p0(P0_SELS); o[0] = (ss == 1) ? tns1 : mem.scr_get(STC0 + mgx + 1 + ss); o[1] = stl / m; o[2] = srh / m; o[3] = ssw / m; o[4] = slw / m; o[5] = Lt; }
   return true;
 }
 

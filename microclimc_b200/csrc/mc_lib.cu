@@ -64,7 +64,10 @@ __global__ void __launch_bounds__(kTile, 4) k_transient_fast(FastArgs a) {
   mem.P = mem.Pt + threadIdx.x; mem.S = const_cast<double*>(mem.St) + threadIdx.x; mem.W = const_cast<double*>(mem.Wt) + threadIdx.x;
   mem.buf = buf; mem.bar = bar; mem.lane = threadIdx.x; mem.k = 0; mem.cur = buf; mem.pol = l2_evict_first_policy();
   mem.tbase = *tmem_base_s + ((unsigned)((threadIdx.x >> 5) * 32) << 16);
+  for (int q = 0; q < 8; ++q) mem.tcyc[q] = 0;
+  mem.tlast = clock64();
   fast_run_column<PipeMem, MM, MS>(a, mem, live ? c : a.t.ncol - 1, live);
+  if (a.dbgbuf && threadIdx.x == 0) for (int q = 0; q < 8; ++q) atomicAdd(a.dbgbuf + q, (unsigned long long)mem.tcyc[q]);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_base_s), "n"(128) : "memory");
@@ -131,7 +134,7 @@ struct Shard {
   int dev = 0; long long c0 = 0, nc = 0;
   cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
   DBuf vegp, soilp, lat, lon, state, state_bak, fscale, foffset, forcing, season, tsoil, stats, series, full, samp_of, flags,
-      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, fP, fS, fW;
+      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, fP, fS, fW, dbg;
   bool fast_attr = false;
   bool has_pert = false, has_season = false, has_state = false;
   float ms = 0; long long launches = 0;
@@ -223,13 +226,26 @@ int launch_transient(Shard& s, const TransientArgs& a) {
     CU(cudaFuncSetAttribute(k_transient_fast<20, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
     s.fast_attr = true;
   }
-  FastArgs fa{a, s.fP.as<double>(), s.fS.as<double>(), s.fW.as<double>(), 0};
+  FastArgs fa{a, s.fP.as<double>(), s.fS.as<double>(), s.fW.as<double>(), nullptr, 0};
+  if (a.cfg.dbg & 16) {
+    CU(s.dbg.need(sizeof(unsigned long long) * 8));
+    CU(cudaMemsetAsync(s.dbg.p, 0, sizeof(unsigned long long) * 8, s.st));
+    fa.dbgbuf = s.dbg.as<unsigned long long>();
+  }
   for (int spin = 1; spin >= 0; --spin) {
     if (spin ? a.spin_steps <= 0 : a.t1 <= a.t0) continue;
     fa.spin_mode = spin;
     k_geom<20, 10><<<(unsigned)ntile, kTile, 0, s.st>>>(fa);
     k_transient_fast<20, 10><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
     s.launches += 2;
+  }
+  if (fa.dbgbuf) {
+    unsigned long long h[8];
+    CU(cudaMemcpyAsync(h, fa.dbgbuf, sizeof(h), cudaMemcpyDeviceToHost, s.st));
+    CU(cudaStreamSynchronize(s.st));
+    unsigned long long tot = 0; for (int q = 0; q < 8; ++q) tot += h[q];
+    const char* nm[8] = {"phase0", "sweepA+cap", "Bprep", "sweepB", "solve", "sweepC", "end", "between-steps"};
+    for (int q = 0; q < 8; ++q) fprintf(stderr, "[mc phase] %-14s %6.2f %%\n", nm[q], 100.0 * (double)h[q] / (double)(tot ? tot : 1));
   }
   return 0;
 }
@@ -293,7 +309,7 @@ void mc_destroy(mc_ctx* ctx) {
     cudaSetDevice(s.dev);
     DBuf* bufs[] = {&s.vegp, &s.soilp, &s.lat, &s.lon, &s.state, &s.state_bak, &s.fscale, &s.foffset, &s.forcing, &s.season, &s.tsoil,
                     &s.stats, &s.series, &s.full, &s.samp_of, &s.flags, &s.args6, &s.clim8, &s.theta, &s.thetap, &s.nmerged,
-                    &s.sclim, &s.snmr, &s.sseason, &s.sout, &s.spart, &s.fP, &s.fS, &s.fW};
+                    &s.sclim, &s.snmr, &s.sseason, &s.sout, &s.spart, &s.fP, &s.fS, &s.fW, &s.dbg};
     for (DBuf* b : bufs) b->release();
     if (s.e0) cudaEventDestroy(s.e0);
     if (s.e1) cudaEventDestroy(s.e1);
