@@ -190,10 +190,10 @@ MC_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_share
 MC_D void mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-MC_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+MC_D void mbar_expect_tx(unsigned bar32, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar32), "r"(bytes) : "memory");
 }
-MC_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+MC_D void mbar_wait(unsigned bar32, unsigned parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -202,11 +202,11 @@ MC_D void mbar_wait(unsigned long long* bar, unsigned parity) {
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "}\n" ::"r"(bar32), "r"(parity) : "memory");
 }
-MC_D void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-               "r"(bytes), "r"(smem_u32(bar))
+MC_D void bulk_g2s(unsigned dst32, const void* src, unsigned bytes, unsigned bar32) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst32), "l"(src), "r"(bytes),
+               "r"(bar32)
                : "memory");
 }
 // streamed rows (geometry, state) are read once per step with a reuse distance far beyond L2: mark them evict-first so
@@ -216,9 +216,9 @@ MC_D unsigned long long l2_evict_first_policy() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-MC_D void bulk_g2s_stream(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long pol) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+MC_D void bulk_g2s_stream(unsigned dst32, const void* src, unsigned bytes, unsigned bar32, unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst32), "l"(src),
+               "r"(bytes), "r"(bar32), "l"(pol)
                : "memory");
 }
 MC_D void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -229,6 +229,7 @@ struct PipeMem {
   FastLayout L;
   double* buf;                                 // [2][kStageRows][kTile] in shared memory
   unsigned long long* bar;                     // [2]
+  unsigned bar32, buf32;                       // the same two as 32-bit shared-window addresses (no generic->shared conversion in the loops)
   int lane;                                    // threadIdx.x
   unsigned k;                                  // stages issued so far (uniform over the block)
   const double* cur;                           // current stage buffer + lane
@@ -278,25 +279,25 @@ struct PipeMem {
     for (int q = 0; q < 8; ++q) v[q] = __hiloint2double(r[2 * q + 1], r[2 * q]);
   }
   MC_D void issueA(int i, unsigned kk) {
-    double* b = buf + (kk & 1) * (kStageRows * kTile);
-    unsigned long long* mb = bar + (kk & 1);
+    const unsigned b = buf32 + (kk & 1) * (kStageRows * kTile * 8);
+    const unsigned mb = bar32 + (kk & 1) * 8;
     const unsigned bytes = (PA_N + (i > 1 ? 1 : 0) + 1) * kTile * 8;
     mbar_expect_tx(mb, bytes);
     bulk_g2s_stream(b, Pt + (long long)L.pa(i, 0) * kTile, PA_N * kTile * 8, mb, pol);
-    if (i > 1) bulk_g2s_stream(b + PA_N * kTile, St + (long long)L.sl(i - 1, SL_TC) * kTile, kTile * 8, mb, pol);
-    bulk_g2s_stream(b + (PA_N + 1) * kTile, St + (long long)L.gt(i) * kTile, kTile * 8, mb, pol);
+    if (i > 1) bulk_g2s_stream(b + PA_N * kTile * 8, St + (long long)L.sl(i - 1, SL_TC) * kTile, kTile * 8, mb, pol);
+    bulk_g2s_stream(b + (PA_N + 1) * kTile * 8, St + (long long)L.gt(i) * kTile, kTile * 8, mb, pol);
   }
   MC_D void issueB(int i, unsigned kk) {
-    double* b = buf + (kk & 1) * (kStageRows * kTile);
-    unsigned long long* mb = bar + (kk & 1);
+    const unsigned b = buf32 + (kk & 1) * (kStageRows * kTile * 8);
+    const unsigned mb = bar32 + (kk & 1) * 8;
     mbar_expect_tx(mb, kStageRows * kTile * 8);
     bulk_g2s_stream(b, Pt + (long long)L.pb(i, 0) * kTile, PB_N * kTile * 8, mb, pol);
-    bulk_g2s_stream(b + PB_N * kTile, St + (long long)L.sl(i, 0) * kTile, SL_N * kTile * 8, mb, pol);
-    bulk_g2s(b + (PB_N + SL_N) * kTile, Wt + (long long)L.wl(i, 0) * kTile, kWLiveB * kTile * 8, mb);
+    bulk_g2s_stream(b + PB_N * kTile * 8, St + (long long)L.sl(i, 0) * kTile, SL_N * kTile * 8, mb, pol);
+    bulk_g2s(b + (PB_N + SL_N) * kTile * 8, Wt + (long long)L.wl(i, 0) * kTile, kWLiveB * kTile * 8, mb);
   }
   MC_D void issueC(int i, unsigned kk) {
-    double* b = buf + (kk & 1) * (kStageRows * kTile);
-    unsigned long long* mb = bar + (kk & 1);
+    const unsigned b = buf32 + (kk & 1) * (kStageRows * kTile * 8);
+    const unsigned mb = bar32 + (kk & 1) * 8;
     mbar_expect_tx(mb, kWLiveC * kTile * 8);
     bulk_g2s(b, Wt + (long long)L.wl(i, WL_TT) * kTile, kWLiveC * kTile * 8, mb);
   }
@@ -319,21 +320,21 @@ struct PipeMem {
   MC_D void stageC(int i) {
     __syncthreads();
     if (lane == 0 && i < L.m) issueC(i + 1, k + 1);
-    mbar_wait(bar + (k & 1), (k >> 1) & 1);
+    mbar_wait(bar32 + (k & 1) * 8, (k >> 1) & 1);
     cur = buf + (k & 1) * (kStageRows * kTile) + lane;
     ++k;
   }
   MC_D void stageA(int i) {
     __syncthreads();                                   // everybody has left the buffer the next stage will fill
     if (lane == 0 && i > 1) issueA(i - 1, k + 1);
-    mbar_wait(bar + (k & 1), (k >> 1) & 1);
+    mbar_wait(bar32 + (k & 1) * 8, (k >> 1) & 1);
     cur = buf + (k & 1) * (kStageRows * kTile) + lane;
     ++k;
   }
   MC_D void stageB(int i) {
     __syncthreads();
     if (lane == 0 && i < L.m) issueB(i + 1, k + 1);
-    mbar_wait(bar + (k & 1), (k >> 1) & 1);
+    mbar_wait(bar32 + (k & 1) * 8, (k >> 1) & 1);
     cur = buf + (k & 1) * (kStageRows * kTile) + lane;
     ++k;
   }
@@ -794,7 +795,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
       const double es = tetens(tnl);
       if (ean > es) ean = es;
       if (ean < eamn) ean = eamn;
-      const double al = log(ean * (1 / 0.6108));
+      const double al = flog(ean * (1 / 0.6108));
       const double Tdew = -fdiv(237.3 * al, al - 17.27);
       double dT1 = -(ptl + dTL - Tdew);
       if (dT1 < 0) dT1 = 0;
@@ -833,7 +834,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
         oR += rn; oC += phz; open = true;
         ow += wi; otc += wi * ptc; oVo += wi * (eaj * ku[KU_IPPK - KU_LAMBDA]); oea += wi * ean; oX += wi * (tnl - ptc); ovd += wi * mem.b_p(PB_VDEN);
         if (timestep <= oC * oR) {                                               // timestep / sum(1/gt) <= sum(ph*zth)
-          if (ng < kNG + 1) {
+          if (ng < kNG) {            // (lanes outside the envelope compute too, but never beyond the solver's storage)
             ++ng;
             glo[ng] = olo; ghi[ng] = i; gw[ng] = ow; gtc[ng] = otc; gVo[ng] = oVo; gea[ng] = oea; gX[ng] = oX; gvd[ng] = ovd;
           }
@@ -906,10 +907,14 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
         mem.scr_put(SK0 + 1, (1 / cs) * cpair(tabove));   // one lumped conductance for the lower half of the canopy (code.R:856-857)
       }
       xv[mg + 1] = Xs;
+      {                                                  // soil nodes: all row loads first (one latency), then the scratch stores
+        double rk[MS], rc[MS], rt[MS];
 #pragma unroll
-      for (int j = 1; j <= MS; ++j) if (j <= sm) {       // soil nodes (unrolled: the row loads are issued together)
-        mem.scr_put(SK0 + mg + 1 + j, lam * p0(P0_NFIX + (j - 1))); mem.scr_put(SCD0 + mg + j, (Cv * p0(P0_NFIX + sm + (j - 1))) * i2ts);
-        mem.scr_put(STC0 + 1 + mg + j, s0(L.soiltc(j)));
+        for (int j = 1; j <= MS; ++j) if (j <= sm) { rk[j - 1] = p0(P0_NFIX + (j - 1)); rc[j - 1] = p0(P0_NFIX + sm + (j - 1)); rt[j - 1] = s0(L.soiltc(j)); }
+#pragma unroll
+        for (int j = 1; j <= MS; ++j) if (j <= sm) {
+          mem.scr_put(SK0 + mg + 1 + j, lam * rk[j - 1]); mem.scr_put(SCD0 + mg + j, (Cv * rc[j - 1]) * i2ts); mem.scr_put(STC0 + 1 + mg + j, rt[j - 1]);
+        }
       }
       mem.scr_put(STC0 + 1, tabove); mem.scr_put(STC0 + N + 2, tsoilp);
       thomas_s(mem, SK0, SCD0, STC0, N, fc.tsoil, tcan, cfg.n, xv, mg + 1);
@@ -996,7 +1001,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
         const bool ice = tnn < 0;
         const double ie0 = ice ? (1 / (610.78 / 1000)) : (1 / (611.2 / 1000));
         const double iLv = ice ? (461.5 / 2.834e6) : fdiv(461.5, 2.501e6 - 2340 * tnn);
-        tdws = frcp(1 / 273.15 - iLv * log(ean * ie0)) - 273.15;
+        tdws = frcp(1 / 273.15 - iLv * flog(ean * ie0)) - 273.15;
       }
       const double tn = (tnn < tdws) ? tdws : tnn;
       const double lwt = kSb * pow4(tn + 273.15);

@@ -93,6 +93,37 @@ MC_HD double fexp(double x) {
 #endif
 }
 
+// Natural logarithm for finite positive normal x (the vapour pressures and ratios of this path): x = 2^e * m with
+// m in [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1), log m = 2s + s^3 * P(s^2) (atanh series, degree 8 in s^2, Estrin),
+// result = e*ln2_hi + (2s + ... + e*ln2_lo); < 2 ulp. x <= 0, Inf, NaN, subnormals fall back to log().
+#if defined(__CUDACC__)
+__constant__ double c_log_poly[9] = {2.0 / 3, 2.0 / 5, 2.0 / 7, 2.0 / 9, 2.0 / 11, 2.0 / 13, 2.0 / 15, 2.0 / 17, 2.0 / 19};
+#endif
+MC_HD double flog(double x) {
+#if defined(__CUDA_ARCH__)
+  int hi = __double2hiint(x);
+  if (hi < 0x00100000 || hi >= 0x7ff00000) return log(x);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;
+  double m = __hiloint2double(hi, __double2loint(x));          // [1, 2)
+  if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+  const double sn = m - 1.0, sd = m + 1.0;
+  const double s1 = fdiv(sn, sd);
+  const double z = s1 * s1, z2 = z * z, z4 = z2 * z2;
+  const double p01 = fma(c_log_poly[1], z, c_log_poly[0]), p23 = fma(c_log_poly[3], z, c_log_poly[2]);
+  const double p45 = fma(c_log_poly[5], z, c_log_poly[4]), p67 = fma(c_log_poly[7], z, c_log_poly[6]);
+  const double q03 = fma(p23, z2, p01), q47 = fma(p67, z2, p45);
+  const double P = fma(fma(c_log_poly[8], z4, q47), z4, q03);
+  const double ed = (double)e;
+  // log m = 2 s1 + s1 * z * P, with the rounding error of s1 = sn/sd folded in: r = (sn - s1*sd)/sd
+  const double r = fma(-s1, sd, sn) * frcp(sd);
+  const double lo = fma(s1 * z, P, fma(ed, 1.90821492927058770002e-10, 2.0 * r));
+  return fma(ed, 6.93147180369123816490e-01, fma(2.0, s1, lo));
+#else
+  return log(x);
+#endif
+}
+
 MC_HD double dmin(double a, double b) { return a < b ? a : b; }
 MC_HD double dmax(double a, double b) { return a > b ? a : b; }
 MC_HD double sq(double x) { return x * x; }
