@@ -42,6 +42,7 @@ enum { SL_TC, SL_TLEAF, SL_RH, SL_RABS, SL_GV, SL_GHA, SL_N };
 enum { WL_RG, WL_SFX, WL_GTN, WL_UZN, WL_PHZ, WL_TT, WL_EAL, WL_L, WL_RSWIN, WL_RLWIN, WL_N };
 constexpr int kWLiveB = 5;                        // W rows sweep B reads back from sweep A (RG .. PHZ)
 constexpr int kWLiveC = 2;                        // W rows sweep C reads back from sweep B (TT, EAL)
+constexpr int kCL = 5;                            // layers per sweep-C stage (their TT/EAL rows are contiguous: 10 rows)
 constexpr int kStageRows = PB_N + SL_N + kWLiveB; // 27 rows of 128 doubles = 27 KB per stage buffer
 constexpr int kNG = 6;                            // merged air layers handled in the streaming form (more: general path)
 
@@ -57,7 +58,10 @@ struct FastLayout {
   MC_HD int uz(int i) const { return S0_N + sm + m * SL_N + (i - 1); }
   MC_HD int gt(int i) const { return S0_N + sm + m * SL_N + m + (i - 1); }          // i = 1..m+1
   MC_HD int nS() const { return S0_N + sm + m * SL_N + m + (m + 1); }
-  MC_HD int wl(int i, int r) const { return (i - 1) * WL_N + r; }
+  // per-layer blocks of 8 rows (RG..PHZ, L, RSWIN, RLWIN), then the sweep-C rows (TT, EAL) of all layers contiguously
+  MC_HD int wl(int i, int r) const {
+    return (r == WL_TT || r == WL_EAL) ? m * (WL_N - 2) + (i - 1) * 2 + (r - WL_TT) : (i - 1) * (WL_N - 2) + (r < WL_TT ? r : r - 2);
+  }
   MC_HD int nW() const { return m * WL_N; }
 };
 
@@ -233,6 +237,7 @@ struct PipeMem {
   int lane;                                    // threadIdx.x
   unsigned k;                                  // stages issued so far (uniform over the block)
   const double* cur;                           // current stage buffer + lane
+  const double* cbase;                         // sweep C: start of the current group's rows
   unsigned long long pol;                      // L2 evict-first policy for the streamed rows
   // Tensor memory as a per-thread scratchpad: the CTA owns 128 columns x 128 lanes x 32 bit, i.e. 64 doubles per thread
   // (thread t of warp w <-> lane 32*(w%4) + t%32).  Step scalars that are only needed once per layer are parked there instead
@@ -295,11 +300,12 @@ struct PipeMem {
     bulk_g2s_stream(b + PB_N * kTile * 8, St + (long long)L.sl(i, 0) * kTile, SL_N * kTile * 8, mb, pol);
     bulk_g2s(b + (PB_N + SL_N) * kTile * 8, Wt + (long long)L.wl(i, 0) * kTile, kWLiveB * kTile * 8, mb);
   }
-  MC_D void issueC(int i, unsigned kk) {
+  MC_D void issueC(int i, unsigned kk) {                  // rows of layers i .. i+kCL-1 (or up to m)
     const unsigned b = buf32 + (kk & 1) * (kStageRows * kTile * 8);
     const unsigned mb = bar32 + (kk & 1) * 8;
-    mbar_expect_tx(mb, kWLiveC * kTile * 8);
-    bulk_g2s(b, Wt + (long long)L.wl(i, WL_TT) * kTile, kWLiveC * kTile * 8, mb);
+    const int nl = (L.m - i + 1 < kCL) ? (L.m - i + 1) : kCL;
+    mbar_expect_tx(mb, nl * kWLiveC * kTile * 8);
+    bulk_g2s(b, Wt + (long long)L.wl(i, WL_TT) * kTile, nl * kWLiveC * kTile * 8, mb);
   }
   // generic-proxy stores of the previous sweep -> visible to the async proxy, block-wide; then start the next sweep
   MC_D void step_begin() {
@@ -318,11 +324,15 @@ struct PipeMem {
     if (lane == 0) issueC(1, k);
   }
   MC_D void stageC(int i) {
-    __syncthreads();
-    if (lane == 0 && i < L.m) issueC(i + 1, k + 1);
-    mbar_wait(bar32 + (k & 1) * 8, (k >> 1) & 1);
-    cur = buf + (k & 1) * (kStageRows * kTile) + lane;
-    ++k;
+    const int q = (i - 1) % kCL;
+    if (q == 0) {
+      __syncthreads();
+      if (lane == 0 && i + kCL <= L.m) issueC(i + kCL, k + 1);
+      mbar_wait(bar32 + (k & 1) * 8, (k >> 1) & 1);
+      cbase = buf + (k & 1) * (kStageRows * kTile) + lane;
+      ++k;
+    }
+    cur = cbase + q * kWLiveC * kTile;
   }
   MC_D void stageA(int i) {
     __syncthreads();                                   // everybody has left the buffer the next stage will fill
@@ -410,7 +420,10 @@ MC_HD void thomas_f(int N, double* tcv, double tmsoil, double tairv, const doubl
 // Scratch map of the solves (indices into Mem::scr_*; the C stages later overwrite rows 0, 1, 27, 28 only):
 //   heat   : K(i) at SK0+i (i = 1..17), CD(i) at SCD0+i (1..16), TC(i) at STC0+i (1..18; holds the solution afterwards)
 //   vapour : K, CD, TC in the (then dead) heat K/CD rows;  node arrays for sweep C: T2, Yt, Ye (1..8 each)
-enum { SK0 = 0, SCD0 = 17, STC0 = 33, VK0 = 0, VCD0 = 8, VTC0 = 15, NT20 = 1, NYT0 = 9, NYE0 = 17, KS_CC = 32 };
+// sweep C stages use rows 0..9 of both buffers: the node arrays sit in rows 10..25 of buffer 0 and 10..17 of buffer 1; the new
+// soil temperatures move to tensor memory (KS_TN + j) before sweep C starts.
+enum { SK0 = 0, SCD0 = 17, STC0 = 33, VK0 = 0, VCD0 = 8, VTC0 = 15, NT20 = 9, NYT0 = 17, NYE0 = 36, KS_CC = 32, KS_TN = 32 };
+static_assert(2 * kCL <= NT20 + 1 && NYE0 + 1 >= kStageRows + 2 * kCL, "sweep-C stage rows overlap the node arrays");
 static_assert(STC0 + kNG + 10 + 2 < 2 * kStageRows, "solver scratch exceeds the two stage buffers");
 
 // Thomas (code.R:94-125) in fused form: one forward pass forms the right-hand side on the fly and eliminates, one backward
@@ -846,9 +859,8 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
         Sl[SL_TLEAF * kTile] = tleafn; Sl[SL_RABS * kTile] = Rabsn; Sl[SL_GV * kTile] = gvn; Sl[SL_GHA * kTile] = ghan;
         sput(L.uz(i), uzn); sput(L.gt(i), gtn);
       }
-      double* Wl = W + (long long)L.wl(i, 0) * kTile;
-      Wl[WL_TT * kTile] = TT; Wl[WL_EAL * kTile] = ean;
-      if (emit || i == selHb) { Wl[WL_L * kTile] = Lp; Wl[WL_RSWIN * kTile] = rsw; }
+      wput(i, WL_TT, TT); wput(i, WL_EAL, ean);
+      if (emit || i == selHb) { wput(i, WL_L, Lp); wput(i, WL_RSWIN, rsw); }
       Lt += Lp; stl += tleafn; ssw += rsw;
     }
     if (open) {                                     // trailing group joins the last closed one
@@ -946,6 +958,9 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
         }
       }
       thomas_s(mem, VK0, VCD0, VTC0, mg, Vsoil, Vair, cfg.n, vX, mg);           // (lanes without merged layers idle through it)
+      // tnsoil (code.R:830, 859) -> tensor memory, before the node arrays below reuse its scratch rows
+      for (int j = 1; j <= sm; ++j) mem.park(KS_TN + j, mem.scr_get(STC0 + mg + 1 + j));
+      mem.park_done();
       if (mg > 0) {
         // Vn = rev(vn): Ye[g] = vn[mg+3-g] with vn[1] = Vair, vn[mg+2] = Vsoil; mole fractions, scaled by pk after the interpolation
         double Ye[kNG + 3];
@@ -1018,12 +1033,15 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
   mem.unpark8(X_TAIRN, x0); mem.unpark8(X_PPK, x1);
   const double Lt = mem.unpark(X_LT), stl = mem.unpark(X_STL), ssw = mem.unpark(X_SSW);
   const double sqphi_e = mem.unpark(X_SQPHI), uh_e = mem.unpark(X_UH), cp1_e = mem.unpark(X_CP1), gtncap_e = mem.unpark(X_GTNCAP);
+  double tnsoil[MS + 2];
+#pragma unroll
+  for (int j = 1; j <= MS; ++j) if (j <= sm) tnsoil[j] = mem.unpark(KS_TN + j);
   if (!runB) return !run || fastok;               // (after the last warp-collective tensor-memory access of the step)
   const double tairn = x0[X_TAIRN], pkn = x0[X_PKN], Rsw = x0[X_RSW], tcan = x0[X_TCAN];
   const double ps1 = x1[X_PS1 - X_PPK], tet_tair = x1[X_TET_TAIR - X_PPK], tet_tcan = x1[X_TET_TCAN - X_PPK], tfrost = x1[X_TFROST - X_PPK];
   const double phi_m = x1[X_PHIM - X_PPK];
   const double hgt = p0(P0_HGT), refg = p0(P0_REFG);
-  double tns1 = mem.scr_get(STC0 + mgx + 2);                                   // tnsoil[1] = tn2[mg+2] (code.R:830, 859)
+  double tns1 = tnsoil[1];
   if (tns1 < tfrost) tns1 = tfrost;
   if (tns1 > tairn + 30) tns1 = tairn + 30;
   const double refm = p0(P0_REFM);
@@ -1047,7 +1065,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
   if (Gn < -Gmx) Gn = -Gmx;
   const double Hn = net - Gn - Lt;
   sput(L.soiltc(1), tns1);
-  for (int j = 2; j <= sm; ++j) sput(L.soiltc(j), mem.scr_get(STC0 + mgx + 1 + j));
+  for (int j = 2; j <= sm; ++j) sput(L.soiltc(j), tnsoil[j]);
   sput(S0_TABOVE, tcan); sput(S0_RELHUM, x0[X_RELHUMN]); sput(S0_TAIR, tairn); sput(S0_TSOIL, fc.tsoil); sput(S0_PK, pkn); sput(S0_H, Hn);
   sput(S0_PSIM, x1[X_PSIM - X_PPK]); sput(S0_G, Gn); sput(S0_TCSUM, stc); sput(S0_GTCAP, gtncap_e);
   MC_TICK(6);
@@ -1068,7 +1086,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
       o[4] = wget(selH, WL_RLWIN); o[5] = wget(selH, WL_L);
     } else { for (int q = 0; q < 6; ++q) o[q] = NAN; }
   }
-  if (reqhgt <= 0) { const int ss = (int)p0(P0_SELS); o[0] = (ss == 1) ? tns1 : mem.scr_get(STC0 + mgx + 1 + ss); o[1] = stl / m; o[2] = srh / m; o[3] = ssw / m; o[4] = slw / m; o[5] = Lt; }
+  if (reqhgt <= 0) { const int ss = (int)p0(P0_SELS); o[0] = (ss == 1) ? tns1 : tnsoil[ss]; o[1] = stl / m; o[2] = srh / m; o[3] = ssw / m; o[4] = slw / m; o[5] = Lt; }
   return true;
 }
 

@@ -28,7 +28,7 @@ def hostdbg():
     src = os.path.join(ROOT, "tests", "hostdbg", "dbg_host.cpp")
     out = os.path.join(ROOT, "tests", "hostdbg", "libdbg_host.so")
     deps = [src] + [os.path.join(ROOT, "microclimc_b200", "csrc", f) for f in
-                    ("mc_step.cuh", "mc_driver.cuh", "mc_steady.cuh", "mc_phys.cuh")]
+                    ("mc_step.cuh", "mc_driver.cuh", "mc_steady.cuh", "mc_phys.cuh", "mc_fast.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-x", "c++", "-o", out, src])
