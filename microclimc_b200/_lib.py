@@ -5,7 +5,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmicroclimc_b200.so")
+# MC_B200_LIB: developer knob to A/B another build of the same CUDA library (never a CPU path)
+LIB_PATH = os.environ.get("MC_B200_LIB") or os.path.join(_HERE, "libmicroclimc_b200.so")
 _LIB = None
 D, PD, I64 = C.c_double, C.POINTER(C.c_double), C.c_int64
 PI32, PI64 = C.POINTER(C.c_int32), C.POINTER(C.c_int64)

@@ -484,10 +484,13 @@ MC_HD void thomas_s(Mem& mem, int k0, int cd0, int tc0, int N, double tmsoil, do
 struct StepOut { double o[8]; int ng; };
 
 // wall-clock per phase of the step (MC_DBG_SKIP bit 16): one lane per block accumulates clock64() deltas
-#if defined(__CUDA_ARCH__)
+// Both are compiled in only with -DMC_ABLATE (make ABLATE=1): the production kernel carries no debug tests in its loops.
+#if defined(__CUDA_ARCH__) && defined(MC_ABLATE)
 #define MC_TICK(slot) do { if (cfg.dbg & 16) { long long t_ = clock64(); mem.tcyc[slot] += t_ - mem.tlast; mem.tlast = t_; } } while (0)
+#define MC_SKIP(bit) (cfg.dbg & (bit))
 #else
 #define MC_TICK(slot) ((void)0)
+#define MC_SKIP(bit) false
 #endif
 
 // Step context: per-thread scalars handed from one phase of the step to the next.  On the device they live in tensor
@@ -508,7 +511,8 @@ static_assert(K_NPARK <= 64, "64 doubles of tensor-memory scratch per thread");
 // `run` false (a column that takes this step through the general path) only suppresses the stores into the state rows.
 // Returns false when the column left the fast envelope (nothing of the state has been modified then).
 template <class Mem, int MS>
-MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, bool emit, double reqhgt, int charmode,
+MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-uniform fields only */, double surfwet, bool run, bool emit,
+                     double reqhgt, int charmode,
                      double relhum0, double rsw0, double skyem0, StepOut& out) {
   const FastLayout L = mem.L;
   const int m = L.m, sm = L.sm;
@@ -603,7 +607,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     const int half = (int)nearbyint(m / 2.0);
     for (int i = m; i >= 1; --i) {
       mem.stageA(i);
-      if (cfg.dbg & 1) continue;
+      if (MC_SKIP(1)) continue;
       const double tcl = (i > 1) ? mem.a_tcl() : ps1a;
       const double ai = mem.a_p(PA_A0I) * sqphi;
       double uzn;
@@ -673,7 +677,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     const double eamn = (relhumn / 100) * tet_tcan;
     mem.park(KT_EREF, eref); mem.park(KT_ESOIL, esoil); mem.park(KT_MTREF, mtref); mem.park(KT_PS1, ps1); mem.park(KT_RGCAP, mem.unpark(X_RGCAP));
     mem.park(KT_TS, cfg.timestep); mem.park(KT_ITS, 1 / cfg.timestep); mem.park(KT_CPPK, (44.6 * (ppk / 101.3)) * 273.15);
-    mem.park(KU_LAMBDA, (-42.575 * tcan + 44994) * cfg.surfwet); mem.park(KU_IMPK, frcp(mpk)); mem.park(KU_VSB, p0(P0_VEGEM) * kSb);
+    mem.park(KU_LAMBDA, (-42.575 * tcan + 44994) * surfwet); mem.park(KU_IMPK, frcp(mpk)); mem.park(KU_VSB, p0(P0_VEGEM) * kSb);
     mem.park(KU_TCAN, tcan); mem.park(KU_EAMN, eamn); mem.park(KU_IPPK, 1 / ppk); mem.park(KU_PKN, pkn); mem.park(KU_REFG, refg);
     // soilk (microctools; Column::soilk) for this step's theta
     const double ct = p0(P0_SKC) * fc.theta;
@@ -695,7 +699,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     bool open = false;
     for (int i = 1; i <= m; ++i) {
       mem.stageB(i);
-      if (cfg.dbg & 2) continue;
+      if (MC_SKIP(2)) continue;
       const double ptc = mem.b_s(SL_TC), ptl = mem.b_s(SL_TLEAF);
       const double uzn = mem.b_w(WL_UZN), gtn = mem.b_w(WL_GTN);
       // leafabs (code.R:31-49) of this layer
@@ -886,7 +890,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     const double esoil = mem.unpark(KT_ESOIL), eamn = mem.unpark(KU_EAMN);          // (all tensor-memory reads before lanes diverge)
     const double timestep = cfg.timestep, i2ts = 1 / (2 * timestep);
     TX = TT + (pha / gtncap) * 2;
-    if (!(cfg.dbg & 4)) {
+    if (!MC_SKIP(4)) {
       mgx = (ng > 1) ? ng : 0;
       const int mg = mgx, N = mg + sm;
       double ltc[kNG + 2], lgt[kNG + 3], lz[kNG + 4], lVo[kNG + 2], lea[kNG + 2], lph[kNG + 2], lTT[kNG + 2], xv[kNG + 3], vX[kNG + 2], Yt[kNG + 3];
@@ -987,7 +991,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg, bool run, b
     const double iTX = 1 / TX;
     for (int i = 1; i <= m; ++i) {
       mem.stageC(i);
-      if (cfg.dbg & 8) continue;
+      if (MC_SKIP(8)) continue;
       const double v = mem.c_w(0), ean = mem.c_w(1);
       double tnn, ea2;
       if (nn == 2) {
@@ -1264,7 +1268,7 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
       const bool emit = live && i == t.spin_steps;
       const bool gen_first = zdiff && i == 1;
       const bool runf = live && fastcol && !gen_first;
-      const bool ok = fast_step<Mem, MS>(mem, fc, cfg, runf, emit, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
+      const bool ok = fast_step<Mem, MS>(mem, fc, t.cfg, cfg.surfwet, runf, emit, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
       if (live && (!runf || !ok)) {
         double zreg[MM + 1];
         for (int q = 1; q <= m; ++q) zreg[q - 1] = (q - 0.5) / m * hgt;
@@ -1285,7 +1289,7 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
       const bool emit = live && (tt == t.t1 - 1 || (slot >= 0 && t.full));
       const bool gen_first = zdiff && tt == t.t0;
       const bool runf = live && fastcol && !gen_first;
-      const bool ok = fast_step<Mem, MS>(mem, fc, cfg, runf, emit, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
+      const bool ok = fast_step<Mem, MS>(mem, fc, t.cfg, cfg.surfwet, runf, emit, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
       if (live && (!runf || !ok))
         general_step<MM, MS>(a, cfg, L, c, S, W, gen_first ? t.state + (long long)(P_NSCAL + 3 * m) * t.ncol + c : nullptr, t.ncol, fc, emit,
                              reqhgt, t.charmode, fc.tair, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(kBlock) k_transient(TransientArgs a) {
 }
 // Streaming form of the transient run (mc_fast.cuh): geometry once per launch, then the time loop with TMA-staged layers.
 template <int MM, int MS>
-__global__ void __launch_bounds__(kTile) k_geom(FastArgs a) {
+__global__ void __launch_bounds__(kTile) k_geom(const __grid_constant__ FastArgs a) {
   const long long c = (long long)blockIdx.x * kTile + threadIdx.x;
   const long long cl = c < a.t.ncol ? c : a.t.ncol - 1;
   const double hgt = a.t.vegp[(long long)V_HGT * a.t.ncol + cl];
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kTile) k_geom(FastArgs a) {
 }
 constexpr int kFastSmem = 2 * kStageRows * kTile * 8 + 64;
 template <int MM, int MS>
-__global__ void __launch_bounds__(kTile, 4) k_transient_fast(FastArgs a) {
+__global__ void __launch_bounds__(kTile, 4) k_transient_fast(const __grid_constant__ FastArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* buf = reinterpret_cast<double*>(smem_raw);
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + 2 * kStageRows * kTile * 8);
