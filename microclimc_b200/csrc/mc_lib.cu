@@ -36,7 +36,9 @@ __global__ void __launch_bounds__(kTile) k_geom(const __grid_constant__ FastArgs
   geom_column<MM, MS>(a, effective_cfg(a.t, hgt, a.spin_mode != 0), c, cl);
 }
 constexpr int kFastSmem = 2 * kStageRows * kTile * 8 + 64;
-template <int MM, int MS>
+// EXACT: the layer counts equal the template bounds (m = MM, sm = MS, all BASELINE configs), so every row offset is a
+// compile-time constant; otherwise they are read from the arguments (6 < m <= MM, sm <= MS).
+template <int MM, int MS, bool EXACT>
 __global__ void __launch_bounds__(kTile, 4) k_transient_fast(const __grid_constant__ FastArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* buf = reinterpret_cast<double*>(smem_raw);
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(kTile, 4) k_transient_fast(const __grid_consta
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const long long c = (long long)blockIdx.x * kTile + threadIdx.x;
   const bool live = c < a.t.ncol;
-  FastLayout L{a.t.m, a.t.sm};
+  FastLayout L{EXACT ? MM : a.t.m, EXACT ? MS : a.t.sm};
   PipeMem mem;
   mem.L = L;
   mem.Pt = a.P + (long long)blockIdx.x * L.nP() * kTile; mem.St = a.S + (long long)blockIdx.x * L.nS() * kTile;
@@ -223,7 +225,8 @@ int launch_transient(Shard& s, const TransientArgs& a) {
   CU(s.fP.need(sizeof(double) * ntile * L.nP() * kTile)); CU(s.fS.need(sizeof(double) * ntile * L.nS() * kTile));
   CU(s.fW.need(sizeof(double) * ntile * L.nW() * kTile));
   if (!s.fast_attr) {
-    CU(cudaFuncSetAttribute(k_transient_fast<20, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
+    CU(cudaFuncSetAttribute(k_transient_fast<20, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
+    CU(cudaFuncSetAttribute(k_transient_fast<20, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
     s.fast_attr = true;
   }
   FastArgs fa{a, s.fP.as<double>(), s.fS.as<double>(), s.fW.as<double>(), nullptr, 0};
@@ -236,7 +239,8 @@ int launch_transient(Shard& s, const TransientArgs& a) {
     if (spin ? a.spin_steps <= 0 : a.t1 <= a.t0) continue;
     fa.spin_mode = spin;
     k_geom<20, 10><<<(unsigned)ntile, kTile, 0, s.st>>>(fa);
-    k_transient_fast<20, 10><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
+    if (a.m == 20 && a.sm == 10) k_transient_fast<20, 10, true><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
+    else k_transient_fast<20, 10, false><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
     s.launches += 2;
   }
   if (fa.dbgbuf) {
