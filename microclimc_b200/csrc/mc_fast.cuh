@@ -488,6 +488,11 @@ struct StepOut { double o[8]; int ng; };
 #if defined(__CUDA_ARCH__) && defined(MC_ABLATE)
 #define MC_TICK(slot) do { if (cfg.dbg & 16) { long long t_ = clock64(); mem.tcyc[slot] += t_ - mem.tlast; mem.tlast = t_; } } while (0)
 #define MC_SKIP(bit) (cfg.dbg & (bit))
+#elif defined(__CUDA_ARCH__)
+// production build: one clock read per phase boundary and step, as a marker that splits a profile's SASS listing by phase
+// (tools/ncu_phase_split.py); the value is discarded
+#define MC_TICK(slot) do { unsigned t_; asm volatile("mov.u32 %0, %%clock;" : "=r"(t_)); } while (0)
+#define MC_SKIP(bit) false
 #else
 #define MC_TICK(slot) ((void)0)
 #define MC_SKIP(bit) false
@@ -1259,60 +1264,56 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
   }
   const double reqhgt = t.cfg.reqhgt;
   StepOut so;
-  if (a.spin_mode) {
-    const Forcing fc = {f0[F_TAIR], f0[F_RELHUM], f0[F_PK], f0[F_U], tmean, f0[F_SKYEM], f0[F_RSW], f0[F_DP], f0[F_JD], f0[F_LT],
-                        f0[F_THETA], f0[F_THETA]};
-    double Hsum = 0;
-    // previn$z of paraminit (regular grid) as an array for the general path
-    for (int i = 1; i <= t.spin_steps; ++i) {
-      const bool emit = live && i == t.spin_steps;
-      const bool gen_first = zdiff && i == 1;
-      const bool runf = live && fastcol && !gen_first;
-      const bool ok = fast_step<Mem, MS>(mem, fc, t.cfg, cfg.surfwet, runf, emit, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
-      if (live && (!runf || !ok)) {
-        double zreg[MM + 1];
+  // ONE loop (one inlined copy of the step) serves both modes; `spin` is launch-uniform.
+  //   spin-up (code.R:982-1013): t.spin_steps steps on forcing row 0, tsoil = mean air temperature, previn$H <- running mean of H;
+  //   runmodel (code.R:1193-1266): steps [t0, t1) with the output harvest.
+  const bool spin = a.spin_mode != 0;
+  const long long nsteps = spin ? (long long)t.spin_steps : t.t1 - t.t0;
+  const double tsoil = spin ? tmean : (have_tsoil ? t.tsoil[c] : tmean);
+  const double surfwet = cfg.surfwet;
+  double stt[6] = {0, 1e300, -1e300, 0, 1e300, -1e300};
+  double Hsum = 0;
+  int flag = 0;
+  const long long slot = (!spin && t.nsamp > 0 && t.samp_of) ? t.samp_of[c] : -1;
+  for (long long it = 0; it < nsteps; ++it) {
+    const long long tt = spin ? 0 : t.t0 + it;
+    forcing_at(t, tt, c, f);
+    const Forcing fc = {f[F_TAIR], f[F_RELHUM], f[F_PK], f[F_U], tsoil, f[F_SKYEM], f[F_RSW], f[F_DP], f[F_JD], f[F_LT], f[F_THETA],
+                        /*Q2*/ f0[F_THETA]};
+    const bool emit = live && (it == nsteps - 1 || (slot >= 0 && t.full));
+    const bool gen_first = zdiff && it == 0;
+    const bool runf = live && fastcol && !gen_first;
+    const bool ok = fast_step<Mem, MS>(mem, fc, t.cfg, surfwet, runf, emit, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
+    if (live && (!runf || !ok)) {
+      if (spin) {
+        double zreg[MM + 1];                                  // previn$z of paraminit (regular grid) for the general path
         for (int q = 1; q <= m; ++q) zreg[q - 1] = (q - 0.5) / m * hgt;
         general_step<MM, MS>(a, cfg, L, c, S, W, gen_first ? zreg : nullptr, 1, fc, emit, reqhgt, t.charmode, fc.tair, f0[F_RELHUM], f0[F_RSW],
                              f0[F_SKYEM], so);
-      }
-      if (live) { Hsum += S[(long long)S0_H * kTile]; sput(S0_H, Hsum / i); }                  // previn$H <- mean(H)
-    }
-  } else {
-    const double tsoil = have_tsoil ? t.tsoil[c] : tmean;
-    double stt[6] = {0, 1e300, -1e300, 0, 1e300, -1e300};
-    int flag = 0;
-    const long long slot = (t.nsamp > 0 && t.samp_of) ? t.samp_of[c] : -1;
-    for (long long tt = t.t0; tt < t.t1; ++tt) {
-      forcing_at(t, tt, c, f);
-      const Forcing fc = {f[F_TAIR], f[F_RELHUM], f[F_PK], f[F_U], tsoil, f[F_SKYEM], f[F_RSW], f[F_DP], f[F_JD], f[F_LT], f[F_THETA],
-                          /*Q2*/ f0[F_THETA]};
-      const bool emit = live && (tt == t.t1 - 1 || (slot >= 0 && t.full));
-      const bool gen_first = zdiff && tt == t.t0;
-      const bool runf = live && fastcol && !gen_first;
-      const bool ok = fast_step<Mem, MS>(mem, fc, t.cfg, cfg.surfwet, runf, emit, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
-      if (live && (!runf || !ok))
+      } else {
         general_step<MM, MS>(a, cfg, L, c, S, W, gen_first ? t.state + (long long)(P_NSCAL + 3 * m) * t.ncol + c : nullptr, t.ncol, fc, emit,
                              reqhgt, t.charmode, fc.tair, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
-      if (!live) continue;
-      if (so.ng > 1) flag |= 2;
-      const double* o = so.o;
-      stt[0] += o[0]; if (o[0] < stt[1]) stt[1] = o[0]; if (o[0] > stt[2]) stt[2] = o[0];
-      stt[3] += o[1]; if (o[1] < stt[4]) stt[4] = o[1]; if (o[1] > stt[5]) stt[5] = o[1];
-      if (!isfinite(o[0]) || !isfinite(o[1])) flag |= 1;
-      if (slot >= 0) {
-        if (t.series) for (int q = 0; q < 8; ++q) t.series[((tt - t.t0) * 8 + q) * t.nsamp + slot] = o[q];
-        if (t.full) abi_state_from_ws(L, P, S, W, t.soilp + (long long)S_NSCAL * t.ncol + c, t.ncol,
-                                      t.full + (tt - t.t0) * NS * t.nsamp + slot, t.nsamp);
       }
     }
-    if (live) {
-      if (t.stats) {
-        const double n = (double)(t.t1 - t.t0);
-        t.stats[0 * t.ncol + c] = stt[0] / n; t.stats[1 * t.ncol + c] = stt[1]; t.stats[2 * t.ncol + c] = stt[2];
-        t.stats[3 * t.ncol + c] = stt[3] / n; t.stats[4 * t.ncol + c] = stt[4]; t.stats[5 * t.ncol + c] = stt[5];
-      }
-      if (t.flags) t.flags[c] = flag;
+    if (!live) continue;
+    if (spin) { Hsum += S[(long long)S0_H * kTile]; sput(S0_H, Hsum / (double)(it + 1)); continue; }   // previn$H <- mean(H)
+    if (so.ng > 1) flag |= 2;
+    const double* o = so.o;
+    stt[0] += o[0]; if (o[0] < stt[1]) stt[1] = o[0]; if (o[0] > stt[2]) stt[2] = o[0];
+    stt[3] += o[1]; if (o[1] < stt[4]) stt[4] = o[1]; if (o[1] > stt[5]) stt[5] = o[1];
+    if (!isfinite(o[0]) || !isfinite(o[1])) flag |= 1;
+    if (slot >= 0) {
+      if (t.series) for (int q = 0; q < 8; ++q) t.series[(it * 8 + q) * t.nsamp + slot] = o[q];
+      if (t.full) abi_state_from_ws(L, P, S, W, t.soilp + (long long)S_NSCAL * t.ncol + c, t.ncol, t.full + it * NS * t.nsamp + slot, t.nsamp);
     }
+  }
+  if (live && !spin) {
+    if (t.stats) {
+      const double n = (double)(t.t1 - t.t0);
+      t.stats[0 * t.ncol + c] = stt[0] / n; t.stats[1 * t.ncol + c] = stt[1]; t.stats[2 * t.ncol + c] = stt[2];
+      t.stats[3 * t.ncol + c] = stt[3] / n; t.stats[4 * t.ncol + c] = stt[4]; t.stats[5 * t.ncol + c] = stt[5];
+    }
+    if (t.flags) t.flags[c] = flag;
   }
   if (live) abi_state_from_ws(L, P, S, W, t.soilp + (long long)S_NSCAL * t.ncol + c, t.ncol, t.state + c, t.ncol);
 }

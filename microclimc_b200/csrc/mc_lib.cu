@@ -23,6 +23,7 @@ constexpr int kBlock = 128;
 
 template <int MM, int MS>
 __global__ void __launch_bounds__(kBlock) k_transient(TransientArgs a) {
+  exp_tab_init();
   long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const bool live = c < a.ncol;
   run_column<MM, MS>(a, live ? c : a.ncol - 1, live);
@@ -30,6 +31,7 @@ __global__ void __launch_bounds__(kBlock) k_transient(TransientArgs a) {
 // Streaming form of the transient run (mc_fast.cuh): geometry once per launch, then the time loop with TMA-staged layers.
 template <int MM, int MS>
 __global__ void __launch_bounds__(kTile) k_geom(const __grid_constant__ FastArgs a) {
+  exp_tab_init();
   const long long c = (long long)blockIdx.x * kTile + threadIdx.x;
   const long long cl = c < a.t.ncol ? c : a.t.ncol - 1;
   const double hgt = a.t.vegp[(long long)V_HGT * a.t.ncol + cl];
@@ -40,6 +42,7 @@ constexpr int kFastSmem = 2 * kStageRows * kTile * 8 + 64;
 // compile-time constant; otherwise they are read from the arguments (6 < m <= MM, sm <= MS).
 template <int MM, int MS, bool EXACT>
 __global__ void __launch_bounds__(kTile, 4) k_transient_fast(const __grid_constant__ FastArgs a) {
+  exp_tab_init();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* buf = reinterpret_cast<double*>(smem_raw);
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + 2 * kStageRows * kTile * 8);
@@ -76,16 +79,19 @@ __global__ void __launch_bounds__(kTile, 4) k_transient_fast(const __grid_consta
 }
 template <int MM, int MS>
 __global__ void __launch_bounds__(kBlock) k_onestep(OneStepArgs a) {
+  exp_tab_init();
   long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   if (c < a.ncol) onestep_column<MM, MS>(a, c);
 }
 template <int MM, int MS>
 __global__ void __launch_bounds__(kBlock) k_paraminit(long long ncol, int m, int sm, const double* args, double* state) {
+  exp_tab_init();
   long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   if (c < ncol) paraminit_column<MM, MS>(ncol, m, sm, args, state, c);
 }
 template <int MM>
 __global__ void __launch_bounds__(kBlock) k_steady(SteadyArgs a) {
+  exp_tab_init();
   long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   if (c < a.ncol) steady_column<MM>(a, c, blockIdx.y, gridDim.y);
 }

@@ -35,14 +35,34 @@ constexpr double kSb = 5.67 * 1e-8;
 //  * frcp/fdiv: MUFU.RCP64H seed (rcp.approx.ftz.f64) + 2 Newton steps + one residual correction, branch-free,
 //    <= 1 ulp from the correctly rounded quotient for normal, finite, non-zero operands. Sites whose operands can
 //    legitimately be 0 / Inf (stomatal conductance at night) keep the IEEE `/`.
-//  * fexp: Cody-Waite reduction + degree-13 polynomial with the coefficients in constant memory (DFMA takes them
-//    as constant-bank operands), exponent insertion by integer add; relative error < 2 ulp, flushes below -708.
+//  * fexp: Cody-Waite reduction to |r| <= ln2/128 with a 64-entry table of 2^(j/64) in shared memory + degree-5
+//    polynomial, exponent insertion by integer add; relative error < 1.5 ulp, flushes below -708.
 // The host build (tests) maps them to the libm / IEEE operations.
 #if defined(__CUDACC__)
-__constant__ double c_exp_poly[14] = {1.0, 1.0, 0.5, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.3333333333333332e-03,
-                                      1.3888888888888889e-03, 1.9841269841269841e-04, 2.4801587301587302e-05,
-                                      2.7557319223985893e-06, 2.7557319223985888e-07, 2.5052108385441720e-08,
-                                      2.0876756987868100e-09, 1.6059043836821613e-10};
+// 2^(j/64), j = 0..63, correctly rounded.  Every kernel that evaluates fexp copies the table to shared memory first
+// (exp_tab_init): a per-lane index into constant memory would serialise, shared memory serves it in one or two wavefronts.
+__constant__ double c_exp_tab[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+__shared__ double s_exp_tab[64];
+__device__ __forceinline__ void exp_tab_init() {
+  if (threadIdx.x < 64) s_exp_tab[threadIdx.x] = c_exp_tab[threadIdx.x];
+  __syncthreads();
+}
 #endif
 MC_HD double frcp(double b) {
 #if defined(__CUDA_ARCH__)
@@ -68,22 +88,19 @@ MC_HD double fdiv(double a, double b) {
 }
 MC_HD double fexp(double x) {
 #if defined(__CUDA_ARCH__)
-  double t = fma(x, 1.4426950408889634, 6755399441055744.0);          // round-to-nearest integer in the low word
-  int k = __double2loint(t);
-  double kd = t - 6755399441055744.0;
-  double r = fma(kd, -6.93147180369123816490e-01, x);
-  r = fma(kd, -1.90821492927058770002e-10, r);
-  // degree-13 Taylor polynomial, Estrin scheme: dependent chain of 5 fused steps instead of 13 (the FP64 pipe is
-  // latency-bound on Horner chains with the few warps this register-heavy kernel keeps resident)
-  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-  const double q01 = fma(c_exp_poly[1], r, c_exp_poly[0]), q23 = fma(c_exp_poly[3], r, c_exp_poly[2]);
-  const double q45 = fma(c_exp_poly[5], r, c_exp_poly[4]), q67 = fma(c_exp_poly[7], r, c_exp_poly[6]);
-  const double q89 = fma(c_exp_poly[9], r, c_exp_poly[8]), qab = fma(c_exp_poly[11], r, c_exp_poly[10]);
-  const double qcd = fma(c_exp_poly[13], r, c_exp_poly[12]);
-  const double h03 = fma(q23, r2, q01), h47 = fma(q67, r2, q45), h8b = fma(qab, r2, q89);
-  const double lo = fma(h47, r4, h03), hi = fma(qcd, r4, h8b);
-  double p = fma(hi, r8, lo);
-  double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  // x = (64 k + j) ln2/64 + r, |r| <= ln2/128:  exp(x) = 2^k * 2^(j/64) * exp(r), exp(r) - 1 by a degree-5 polynomial
+  // (remainder r^6/720 < 4e-17).  10 FP64 operations on a dependent chain of 7 instead of 20 on a chain of 9.
+  double t = fma(x, 9.233248261689366e+01, 6755399441055744.0);        // 64/ln2; round-to-nearest integer in the low word
+  const int n = __double2loint(t);
+  const double kd = t - 6755399441055744.0;
+  double r = fma(kd, -0x1.62e42feep-7, x);                             // ln2/64, high part (trailing zeros: kd * hi is exact)
+  r = fma(kd, -0x1.a39ef35793c76p-39, r);                              // ln2/64, low part
+  const double T = s_exp_tab[n & 63];
+  const double r2 = r * r;
+  const double a = fma(8.3333333333333332e-03, r, 4.1666666666666664e-02), b = fma(1.6666666666666666e-01, r, 0.5);
+  const double d = fma(fma(a, r2, b), r2, r);                          // exp(r) - 1
+  const double p = fma(T, d, T);
+  double res = __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
   if (x < -708.0) res = 0.0;
   if (x > 709.0) res = __longlong_as_double(0x7ff0000000000000LL);
   if (x != x) res = x;
