@@ -421,63 +421,53 @@ MC_HD void thomas_f(int N, double* tcv, double tmsoil, double tairv, const doubl
 //   heat   : K(i) at SK0+i (i = 1..17), CD(i) at SCD0+i (1..16), TC(i) at STC0+i (1..18; holds the solution afterwards)
 //   vapour : K, CD, TC in the (then dead) heat K/CD rows;  node arrays for sweep C: T2, Yt, Ye (1..8 each)
 // sweep C stages use rows 0..9 of both buffers: the node arrays sit in rows 10..25 of buffer 0 and 10..17 of buffer 1; the new
-// soil temperatures move to tensor memory (KS_TN + j) before sweep C starts.
-enum { SK0 = 0, SCD0 = 17, STC0 = 33, VK0 = 0, VCD0 = 8, VTC0 = 15, NT20 = 9, NYT0 = 17, NYE0 = 36, KS_CC = 32, KS_TN = 32 };
+// soil temperatures are written to the state rows right after the heat solve.
+enum { SK0 = 0, SCD0 = 17, STC0 = 33, VK0 = 0, VCD0 = 8, VTC0 = 15, NT20 = 9, NYT0 = 17, NYE0 = 36 };
 static_assert(2 * kCL <= NT20 + 1 && NYE0 + 1 >= kStageRows + 2 * kCL, "sweep-C stage rows overlap the node arrays");
 static_assert(STC0 + kNG + 10 + 2 < 2 * kStageRows, "solver scratch exceeds the two stage buffers");
 
 // Thomas (code.R:94-125) in fused form: one forward pass forms the right-hand side on the fly and eliminates, one backward
-// pass substitutes and applies the old-stencil limits (quirk Q11).  Coefficients come from the scratch rows, the elimination
-// factors (cc, dd) go through tensor memory.  Same operations in the same order as Column::thomas.  Warp-collective: every lane
-// calls it (N may differ per lane; N = 0 lanes only keep the tensor-memory accesses aligned).
+// pass substitutes and applies the old-stencil limits (quirk Q11).  Coefficients come from the scratch rows and are replaced in
+// place by the elimination factors (cc, dd) as the forward pass consumes them.  Same operations in the same order as
+// Column::thomas.  N may differ per lane (N = 0: nothing to solve).
 template <class Mem>
 MC_HD void thomas_s(Mem& mem, int k0, int cd0, int tc0, int N, double tmsoil, double tairv, double f, const double* xv, int nx) {
-  const int Nw = mem.warp_max(N);
+  if (N < 1) return;
   const double g = 1 - f;
-  double t_lo = 0, t_mid = 0, k_lo = 0, a1p = 0, ccp = 0, dnp = 0, tnN1 = 0;
-  if (N >= 1) {
-    t_lo = mem.scr_get(tc0 + 1);
-    t_mid = mem.scr_get(tc0 + 2) + g * (nx >= 1 ? xv[1] : 0.0);
-    k_lo = mem.scr_get(k0 + 1);
+  double t_lo = mem.scr_get(tc0 + 1);
+  double t_mid = mem.scr_get(tc0 + 2) + g * (nx >= 1 ? xv[1] : 0.0);
+  double k_lo = mem.scr_get(k0 + 1);
+  double a1p = 0, ccp = 0, dnp = 0, tnN1 = 0;
+  for (int x = 2; x <= N + 1; ++x) {
+    const double k_mid = mem.scr_get(k0 + x), cd = mem.scr_get(cd0 + x - 1);
+    double t_hi = mem.scr_get(tc0 + x + 1);
+    if (x + 1 <= N + 1) t_hi = t_hi + g * (x <= nx ? xv[x] : 0.0);
+    double d = g * k_lo * t_lo + (cd - g * (k_mid + k_lo)) * t_mid + g * k_mid * t_hi;
+    if (x == 2) d = d + k_lo * tairv * f;
+    if (x == N + 1) d = d + k_mid * f * tmsoil;
+    double b = f * (k_mid + k_lo) + cd;
+    if (x > 2) { d = d - a1p * dnp; b = b - a1p * ccp; }
+    mem.scr_put(tc0 + x, t_mid);                       // tcv' = tcv + (1-f) X, needed again for the limits
+    if (x <= N) {
+      const double ib = frcp(b);
+      const double a1 = -k_mid * f;
+      const double c = a1 * ib, dn = d * ib;
+      mem.scr_put(k0 + x, c); mem.scr_put(cd0 + x - 1, dn);      // elimination factors replace the (now dead) coefficients
+      a1p = a1; ccp = c; dnp = dn;
+    } else tnN1 = fdiv(d, b);
+    t_lo = t_mid; t_mid = t_hi; k_lo = k_mid;
   }
-  for (int x = 2; x <= Nw + 1; ++x) {
-    double c = 0, dn = 0;
-    if (x <= N + 1) {
-      const double k_mid = mem.scr_get(k0 + x), cd = mem.scr_get(cd0 + x - 1);
-      double t_hi = mem.scr_get(tc0 + x + 1);
-      if (x + 1 <= N + 1) t_hi = t_hi + g * (x <= nx ? xv[x] : 0.0);
-      double d = g * k_lo * t_lo + (cd - g * (k_mid + k_lo)) * t_mid + g * k_mid * t_hi;
-      if (x == 2) d = d + k_lo * tairv * f;
-      if (x == N + 1) d = d + k_mid * f * tmsoil;
-      double b = f * (k_mid + k_lo) + cd;
-      if (x > 2) { d = d - a1p * dnp; b = b - a1p * ccp; }
-      mem.scr_put(tc0 + x, t_mid);                     // tcv' = tcv + (1-f) X, needed again for the limits
-      if (x <= N) {
-        const double ib = frcp(b);
-        const double a1 = -k_mid * f;
-        c = a1 * ib; dn = d * ib;
-        a1p = a1; ccp = c; dnp = dn;
-      } else tnN1 = fdiv(d, b);
-      t_lo = t_mid; t_mid = t_hi; k_lo = k_mid;
-    }
-    mem.park2(KS_CC + 2 * (x - 2), c, dn);
-  }
-  mem.park_done();
-  double tu = tnN1, t_up = 0, t_c = 0;
-  for (int x = Nw + 1; x >= 2; --x) {
-    double c, dn;
-    mem.unpark2(KS_CC + 2 * (x - 2), c, dn);
-    if (x <= N + 1) {
-      if (x == N + 1) { t_up = mem.scr_get(tc0 + N + 2); t_c = mem.scr_get(tc0 + N + 1); }
-      else tu = dn - c * tu;
-      const double t_dn = mem.scr_get(tc0 + x - 1);
-      const double xmn = dmin(dmin(t_c, t_dn), t_up), xmx = dmax(dmax(t_c, t_dn), t_up);
-      double v = tu;
-      if (v < xmn) v = xmn;
-      if (v > xmx) v = xmx;
-      mem.scr_put(tc0 + x, v + f * ((x - 1) <= nx ? xv[x - 1] : 0.0));
-      t_up = t_c; t_c = t_dn;
-    }
+  double tu = tnN1;
+  double t_up = mem.scr_get(tc0 + N + 2), t_c = mem.scr_get(tc0 + N + 1);
+  for (int x = N + 1; x >= 2; --x) {
+    if (x <= N) tu = mem.scr_get(cd0 + x - 1) - mem.scr_get(k0 + x) * tu;
+    const double t_dn = mem.scr_get(tc0 + x - 1);
+    const double xmn = dmin(dmin(t_c, t_dn), t_up), xmx = dmax(dmax(t_c, t_dn), t_up);
+    double v = tu;
+    if (v < xmn) v = xmn;
+    if (v > xmx) v = xmx;
+    mem.scr_put(tc0 + x, v + f * ((x - 1) <= nx ? xv[x - 1] : 0.0));
+    t_up = t_c; t_c = t_dn;
   }
 }
 
@@ -489,9 +479,9 @@ struct StepOut { double o[8]; int ng; };
 #define MC_TICK(slot) do { if (cfg.dbg & 16) { long long t_ = clock64(); mem.tcyc[slot] += t_ - mem.tlast; mem.tlast = t_; } } while (0)
 #define MC_SKIP(bit) (cfg.dbg & (bit))
 #elif defined(__CUDA_ARCH__)
-// production build: one clock read per phase boundary and step, as a marker that splits a profile's SASS listing by phase
-// (tools/ncu_phase_split.py); the value is discarded
-#define MC_TICK(slot) do { unsigned t_; asm volatile("mov.u32 %0, %%clock;" : "=r"(t_)); } while (0)
+// production build: one performance-monitor trigger (PMTRIG) per phase boundary and step, as a marker that splits a profile's
+// SASS listing by phase (tools/ncu_phase_split.py)
+#define MC_TICK(slot) asm volatile("pmevent %0;" ::"n"(slot))
 #define MC_SKIP(bit) false
 #else
 #define MC_TICK(slot) ((void)0)
@@ -508,9 +498,22 @@ enum { X_TAIRN, X_PKN, X_SKYEM, X_RSW, X_RELHUMN, X_TCAN, X_TAIRP, X_RELHUMP,
        // sweep-B invariants, 8 per group, one LDTM each
        KR_K, KR_MUL, KR_DP, KR_RSW, KR_AG0, KR_CLUMP, KR_SKLW, KR_EMLW,
        KG_EMV, KG_GSMAX, KG_Q50, KG_LWD, KG_ILWD, KG_LWD3, KG_C101, KG_CPK,
-       KT_EREF, KT_ESOIL, KT_MTREF, KT_PS1, KT_RGCAP, KT_TS, KT_ITS, KT_CPPK,
+       KT_EREF, KT_ESOIL, KT_MTREF, KT_PS1, KT_RGCAP, KT_TNS1, KT_TSEL, KT_CPPK,
        KU_LAMBDA, KU_IMPK, KU_VSB, KU_TCAN, KU_EAMN, KU_IPPK, KU_PKN, KU_REFG, K_NPARK };
 static_assert(K_NPARK <= 64, "64 doubles of tensor-memory scratch per thread");
+
+// Column constants of sweep B that live in tensor memory for the whole launch (nothing else writes these slots).
+template <class Mem>
+MC_HD void fast_park_constants(Mem& mem) {
+  const double* const P = mem.P;
+  auto p0 = [=](int r) { return P[(long long)r * kTile]; };
+  const double lwd = p0(P0_LWD);
+  mem.park(KR_CLUMP, p0(P0_CLUMP));
+  mem.park(KG_EMV, p0(P0_EMV)); mem.park(KG_GSMAX, p0(P0_GSMAX)); mem.park(KG_Q50, p0(P0_Q50)); mem.park(KG_LWD, lwd); mem.park(KG_ILWD, 1 / lwd);
+  mem.park(KG_LWD3, 9.81 * (lwd * lwd * lwd));
+  mem.park(KU_VSB, p0(P0_VEGEM) * kSb); mem.park(KU_REFG, p0(P0_REFG));
+  mem.park_done();
+}
 
 // One time step of one column in streaming form.  Every lane computes (tensor-memory accesses are warp-collective);
 // `run` false (a column that takes this step through the general path) only suppresses the stores into the state rows.
@@ -659,7 +662,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
     mem.unpark8(X_TAIRN, x0); mem.unpark8(X_PPK, x1);
     const double tairn = x0[X_TAIRN], pkn = x0[X_PKN], skyem = x0[X_SKYEM], Rsw = x0[X_RSW], relhumn = x0[X_RELHUMN], tcan = x0[X_TCAN];
     const double ppk = x1[X_PPK - X_PPK], ps1 = x1[X_PS1 - X_PPK], tet_tcan = x1[X_TET_TCAN - X_PPK];
-    const double clump = p0(P0_CLUMP), refg = p0(P0_REFG), emv = p0(P0_EMV);
+    const double clump = mem.unpark(KR_CLUMP), refg = mem.unpark(KU_REFG), emv = mem.unpark(KG_EMV);   // launch-resident (fast_park_constants)
     double dp = fc.dp;
     const double sa = solalt(fc.lt, p0(P0_LAT), p0(P0_LON), fc.jd, cfg.merid, cfg.dst);
     if (dp != dp) dp = difprop(Rsw, sa);
@@ -669,11 +672,9 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
     const double aG0 = refg * cansw_k(Rsw, dp, sa, p0(P0_SUMPAI), p0(P0_SM), p0(P0_TRDM), K, clump);
     const double lwout = kSb * pow4(tairn + 273.15);
     day = sa > 0;
-    mem.park(KR_K, K); mem.park(KR_MUL, mul); mem.park(KR_DP, dp); mem.park(KR_RSW, Rsw); mem.park(KR_AG0, aG0); mem.park(KR_CLUMP, clump);
+    mem.park(KR_K, K); mem.park(KR_MUL, mul); mem.park(KR_DP, dp); mem.park(KR_RSW, Rsw); mem.park(KR_AG0, aG0);
     mem.park(KR_SKLW, skyem * lwout); mem.park(KR_EMLW, emv * lwout);
-    const double lwd = p0(P0_LWD);
-    mem.park(KG_EMV, emv); mem.park(KG_GSMAX, p0(P0_GSMAX)); mem.park(KG_Q50, p0(P0_Q50)); mem.park(KG_LWD, lwd); mem.park(KG_ILWD, 1 / lwd);
-    mem.park(KG_LWD3, 9.81 * (lwd * lwd * lwd)); mem.park(KG_C101, 101.3 / pkn); mem.park(KG_CPK, (44.6 * (pkn / 101.3)) * 273.15);
+    mem.park(KG_C101, 101.3 / pkn); mem.park(KG_CPK, (44.6 * (pkn / 101.3)) * 273.15);
     const double mtref = 0.5 * tcan + 0.5 * x0[X_TAIRP];
     const double mrh = 0.5 * relhumn + 0.5 * x0[X_RELHUMP];
     const double mpk = 0.5 * ppk + 0.5 * pkn;
@@ -681,9 +682,9 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
     const double esoil = soilrh(fc.theta, p0(P0_SOILB), -p0(P0_PSIE), p0(P0_SMAX), ps1) * satvap(ps1);     // Q7
     const double eamn = (relhumn / 100) * tet_tcan;
     mem.park(KT_EREF, eref); mem.park(KT_ESOIL, esoil); mem.park(KT_MTREF, mtref); mem.park(KT_PS1, ps1); mem.park(KT_RGCAP, mem.unpark(X_RGCAP));
-    mem.park(KT_TS, cfg.timestep); mem.park(KT_ITS, 1 / cfg.timestep); mem.park(KT_CPPK, (44.6 * (ppk / 101.3)) * 273.15);
-    mem.park(KU_LAMBDA, (-42.575 * tcan + 44994) * surfwet); mem.park(KU_IMPK, frcp(mpk)); mem.park(KU_VSB, p0(P0_VEGEM) * kSb);
-    mem.park(KU_TCAN, tcan); mem.park(KU_EAMN, eamn); mem.park(KU_IPPK, 1 / ppk); mem.park(KU_PKN, pkn); mem.park(KU_REFG, refg);
+    mem.park(KT_CPPK, (44.6 * (ppk / 101.3)) * 273.15);
+    mem.park(KU_LAMBDA, (-42.575 * tcan + 44994) * surfwet); mem.park(KU_IMPK, frcp(mpk));
+    mem.park(KU_TCAN, tcan); mem.park(KU_EAMN, eamn); mem.park(KU_IPPK, 1 / ppk); mem.park(KU_PKN, pkn);
     // soilk (microctools; Column::soilk) for this step's theta
     const double ct = p0(P0_SKC) * fc.theta;
     mem.park(X_LAM, p0(P0_SKA) + p0(P0_SKB) * fc.theta - p0(P0_SKAD) * exp(-((ct * ct) * (ct * ct))));
@@ -698,6 +699,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
   const bool runB = run && fastok;
   {
     const int selHb = (int)p0(P0_SELH);
+    const double its = 1 / cfg.timestep;              // launch-uniform
     double acc2 = 0, TT = 0, Lt = 0, stl = 0, ssw = 0, Xs = 0, cp1 = 0;
     double oR = 0, oC = 0, ow = 0, otc = 0, oVo = 0, oea = 0, oX = 0, ovd = 0;
     int olo = 1;
@@ -737,7 +739,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
       mem.unpark8(KT_EREF, kt);
       mem.unpark8(KU_LAMBDA, ku);
       const double eref = kt[KT_EREF - KT_EREF], esoil = kt[KT_ESOIL - KT_EREF], mtref = kt[KT_MTREF - KT_EREF], ps1 = kt[KT_PS1 - KT_EREF];
-      const double timestep = kt[KT_TS - KT_EREF];
+      const double timestep = cfg.timestep;
       const double lambda_l = ku[KU_LAMBDA - KU_LAMBDA], impk = ku[KU_IMPK - KU_LAMBDA], tcan = ku[KU_TCAN - KU_LAMBDA], eamn = ku[KU_EAMN - KU_LAMBDA];
       // leaftemp (code.R:378-512)
       const double rg = mem.b_w(WL_RG);
@@ -766,7 +768,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
         ae = (gtt * eref + gtt2 * esoil + gv2b * estl) * iden;
         be = (0.5 * delta) * iden;
       } else {
-        const double ibtm = frcp(kt[KT_ITS - KT_EREF] + 0.5 * (g1 + g2 + g3));
+        const double ibtm = frcp(its + 0.5 * (g1 + g2 + g3));
         const double sat = eaj > esj ? 0.0 : 1.0;                               // edf(), code.R:380-386
         const double e1 = (eref > eaj ? eref - eaj : 0.0) * sat;
         const double e2 = (esoil > eaj ? esoil - eaj : 0.0) * sat;
@@ -835,7 +837,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
       if (i == 1) {                                                               // soil-surface forcing (code.R:799-811)
         const double refg = ku[KU_REFG - KU_LAMBDA], pkn = ku[KU_PKN - KU_LAMBDA];
         cp1 = cp;
-        const double cd1 = (mem.unpark(X_CV) * p0(P0_NFIX + sm)) * (0.5 * kt[KT_ITS - KT_EREF]);
+        const double cd1 = (mem.unpark(X_CV) * p0(P0_NFIX + sm)) * (0.5 * its);
         const double icd1 = frcp(cd1);
         const double a1 = (1 - refg) * (aRsw * icd1);
         if (esoil - ean > 0) {
@@ -884,7 +886,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
   // Solver storage: coefficients in the block's idle stage buffers, elimination factors in tensor memory; ONE Thomas call site
   // per solve for both branches (equilibrium = no merged air node), so warps with mixed lanes do not run the solves twice.
   int nn = 2, mgx = 0;
-  double TX, y1t = 0, y2t = 0, y1e = 0, y2e = 0;
+  double TX, y1t = 0, y2t = 0, y1e = 0, y2e = 0, tns1_raw = 0, tsel_raw = 0;
   {
     double x0[8], x1[8], x2[8];
     mem.unpark8(X_TAIRN, x0); mem.unpark8(X_PPK, x1); mem.unpark8(X_TSOILP, x2);
@@ -967,9 +969,18 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
         }
       }
       thomas_s(mem, VK0, VCD0, VTC0, mg, Vsoil, Vair, cfg.n, vX, mg);           // (lanes without merged layers idle through it)
-      // tnsoil (code.R:830, 859) -> tensor memory, before the node arrays below reuse its scratch rows
-      for (int j = 1; j <= sm; ++j) mem.park(KS_TN + j, mem.scr_get(STC0 + mg + 1 + j));
-      mem.park_done();
+      // tnsoil (code.R:830, 859): nodes 2..sm go straight to the state rows (before the node arrays below reuse their scratch
+      // rows); node 1 passes the limits at the end of the step first.  The node nearest to -reqhgt is kept for the harvest.
+      {
+        const int ss = (int)p0(P0_SELS);
+        double tsel = tns1;
+        for (int j = 2; j <= sm; ++j) {
+          const double v = mem.scr_get(STC0 + mg + 1 + j);
+          if (runB) sput(L.soiltc(j), v);
+          if (j == ss) tsel = v;
+        }
+        tns1_raw = tns1; tsel_raw = tsel;
+      }
       if (mg > 0) {
         // Vn = rev(vn): Ye[g] = vn[mg+3-g] with vn[1] = Vair, vn[mg+2] = Vsoil; mole fractions, scaled by pk after the interpolation
         double Ye[kNG + 3];
@@ -985,6 +996,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
       }
     }
   }
+  mem.park(KT_TNS1, tns1_raw); mem.park(KT_TSEL, tsel_raw); mem.park_done();
   MC_TICK(4);
   mem.sweepC_begin();
   // ======================= sweep C: back to the m nodes, humidity, limits (code.R:846-874, 893-897) =======================
@@ -1042,15 +1054,13 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
   mem.unpark8(X_TAIRN, x0); mem.unpark8(X_PPK, x1);
   const double Lt = mem.unpark(X_LT), stl = mem.unpark(X_STL), ssw = mem.unpark(X_SSW);
   const double sqphi_e = mem.unpark(X_SQPHI), uh_e = mem.unpark(X_UH), cp1_e = mem.unpark(X_CP1), gtncap_e = mem.unpark(X_GTNCAP);
-  double tnsoil[MS + 2];
-#pragma unroll
-  for (int j = 1; j <= MS; ++j) if (j <= sm) tnsoil[j] = mem.unpark(KS_TN + j);
+  const double tns1_in = mem.unpark(KT_TNS1), tsel_in = mem.unpark(KT_TSEL);
   if (!runB) return !run || fastok;               // (after the last warp-collective tensor-memory access of the step)
   const double tairn = x0[X_TAIRN], pkn = x0[X_PKN], Rsw = x0[X_RSW], tcan = x0[X_TCAN];
   const double ps1 = x1[X_PS1 - X_PPK], tet_tair = x1[X_TET_TAIR - X_PPK], tet_tcan = x1[X_TET_TCAN - X_PPK], tfrost = x1[X_TFROST - X_PPK];
   const double phi_m = x1[X_PHIM - X_PPK];
   const double hgt = p0(P0_HGT), refg = p0(P0_REFG);
-  double tns1 = tnsoil[1];
+  double tns1 = tns1_in;
   if (tns1 < tfrost) tns1 = tfrost;
   if (tns1 > tairn + 30) tns1 = tairn + 30;
   const double refm = p0(P0_REFM);
@@ -1074,7 +1084,6 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
   if (Gn < -Gmx) Gn = -Gmx;
   const double Hn = net - Gn - Lt;
   sput(L.soiltc(1), tns1);
-  for (int j = 2; j <= sm; ++j) sput(L.soiltc(j), tnsoil[j]);
   sput(S0_TABOVE, tcan); sput(S0_RELHUM, x0[X_RELHUMN]); sput(S0_TAIR, tairn); sput(S0_TSOIL, fc.tsoil); sput(S0_PK, pkn); sput(S0_H, Hn);
   sput(S0_PSIM, x1[X_PSIM - X_PPK]); sput(S0_G, Gn); sput(S0_TCSUM, stc); sput(S0_GTCAP, gtncap_e);
   MC_TICK(6);
@@ -1095,7 +1104,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
       o[4] = wget(selH, WL_RLWIN); o[5] = wget(selH, WL_L);
     } else { for (int q = 0; q < 6; ++q) o[q] = NAN; }
   }
-  if (reqhgt <= 0) { const int ss = (int)p0(P0_SELS); o[0] = (ss == 1) ? tns1 : tnsoil[ss]; o[1] = stl / m; o[2] = srh / m; o[3] = ssw / m; o[4] = slw / m; o[5] = Lt; }
+  if (reqhgt <= 0) { const int ss = (int)p0(P0_SELS); o[0] = (ss == 1) ? tns1 : tsel_in; o[1] = stl / m; o[2] = srh / m; o[3] = ssw / m; o[4] = slw / m; o[5] = Lt; }
   return true;
 }
 
@@ -1275,6 +1284,7 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
   double Hsum = 0;
   int flag = 0;
   const long long slot = (!spin && t.nsamp > 0 && t.samp_of) ? t.samp_of[c] : -1;
+  fast_park_constants(mem);
   for (long long it = 0; it < nsteps; ++it) {
     const long long tt = spin ? 0 : t.t0 + it;
     forcing_at(t, tt, c, f);

@@ -24,8 +24,8 @@ for r in rows:
     d = dict(zip(hdr, r))
     sass = d["Source"].strip()
     ex = int(d["Instructions Executed"] or 0); s = int(d["# Samples"] or 0)
-    if "SR_CLOCK" in sass:
-        cur = new("after clock #%d @%s" % (len(segs), r[0][-6:])); segs.append(cur)
+    if "SR_CLOCK" in sass or "PMTRIG" in sass:
+        cur = new("after %s @%s" % (sass.replace(";", "").strip()[:18], r[0][-6:])); segs.append(cur)
     cur["n"] += 1; cur["ex"] += ex; cur["samples"] += s
     op = sass.split()[0] if not sass.startswith("@") else sass.split()[1]
     if op.startswith(("DFMA", "DMUL", "DADD", "DSETP", "DMNMX")): cur["fp64"] += ex
