@@ -275,7 +275,7 @@ def main():
                 "peak_source": "of measured: mc_fp64_peak_tflops DFMA probe in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "frac": (ach / peak_fp64) if (ach and peak_fp64 > 0) else None,
                 "traffic": (traffic_per * ncol * hours) if traffic_per else None,
-                "flop_per_colstep": flop_per, "flop_source": "tools/opcount: shipped streaming algorithm, 2 x FP64 issue slots",
+                "flop_per_colstep": flop_per, "flop_source": cost.get("fp64_flop_source", "tools/opcount: shipped streaming algorithm, 2 x FP64 issue slots"),
                 "hbm": {"achieved": (traffic_per or bytes_per) * per_gpu_rate / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": (traffic_per or bytes_per) * per_gpu_rate / 1e9 / hbm_peak,
                         "peak_source": "of measured: MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "of fallback 6650",

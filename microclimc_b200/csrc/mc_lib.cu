@@ -112,7 +112,8 @@ __global__ void k_steady_reduce(long long ncol, int nchunk, long long T, const d
 // MEASURED_PEAKS.json has no FP64 entry).
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-  for (int i = 0; i < iters; ++i) {
+#pragma unroll 16
+  for (int i = 0; i < iters; ++i) {                  // unrolled: the loop bookkeeping would otherwise take 3 issue slots per 8 DFMA
     x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
     x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
   }
