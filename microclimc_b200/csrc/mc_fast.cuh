@@ -438,6 +438,7 @@ MC_HD void thomas_s(Mem& mem, int k0, int cd0, int tc0, int N, double tmsoil, do
   double t_mid = mem.scr_get(tc0 + 2) + g * (nx >= 1 ? xv[1] : 0.0);
   double k_lo = mem.scr_get(k0 + 1);
   double a1p = 0, ccp = 0, dnp = 0, tnN1 = 0;
+#pragma unroll 1
   for (int x = 2; x <= N + 1; ++x) {
     const double k_mid = mem.scr_get(k0 + x), cd = mem.scr_get(cd0 + x - 1);
     double t_hi = mem.scr_get(tc0 + x + 1);
@@ -459,6 +460,7 @@ MC_HD void thomas_s(Mem& mem, int k0, int cd0, int tc0, int N, double tmsoil, do
   }
   double tu = tnN1;
   double t_up = mem.scr_get(tc0 + N + 2), t_c = mem.scr_get(tc0 + N + 1);
+#pragma unroll 1
   for (int x = N + 1; x >= 2; --x) {
     if (x <= N) tu = mem.scr_get(cd0 + x - 1) - mem.scr_get(k0 + x) * tu;
     const double t_dn = mem.scr_get(tc0 + x - 1);
@@ -541,64 +543,65 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
     double relhumn = fc.relhum, u = fc.u;
     const double ppk = s0(S0_PK), Hprev = s0(S0_H), ps1 = s0(L.soiltc(1));
     const double hgt = p0(P0_HGT);
-    cpk = 44.6 * (pkn / 101.3); cppk = 44.6 * (ppk / 101.3);                  // phair(t, pk) = c * 273.15 / (t + 273.15)
+    cpk = 44.6 * fdiv(pkn, 101.3); cppk = 44.6 * fdiv(ppk, 101.3);                  // phair(t, pk) = c * 273.15 / (t + 273.15)
     const double pha = phair(tairn, pkn);
     double u2;
     if (cfg.metopen) {
-      if (cfg.windhgt != 2) u = u * 4.87 / log(67.8 * cfg.windhgt - 5.42);
-      u2 = u * p0(P0_LA) / log(67.8 * 2 - 5.42);
+      if (cfg.windhgt != 2) u = fdiv(u * 4.87, flog(67.8 * cfg.windhgt - 5.42));
+      u2 = fdiv(u * p0(P0_LA), log(67.8 * 2 - 5.42));
     } else {
       u2 = u;
       if (cfg.windhgt != (2 + hgt)) {                                        // windprofile(u, windhgt, hgt+2, ...) with zo above the canopy
         const double psi = s0(S0_PSIM);
         double ln2 = p0(P0_WL2) + psi;
         if (ln2 < 0.55) ln2 = 0.55;
-        u2 = ((0.4 * (u / (p0(P0_WL1) + psi))) / 0.4) * ln2;
+        u2 = fdiv(0.4 * fdiv(u, p0(P0_WL1) + psi), 0.4) * ln2;
       }
     }
     if (u2 < 0.5) u2 = 0.5;
     const double lnref = p0(P0_LNREF);
-    const double uf = (0.4 * u2) / lnref;
+    const double uf = fdiv(0.4 * u2, lnref);
     double psi_mn, psi_h;
     diabatic_cor(tairn, pkn, Hprev, uf, hgt + 2, p0(P0_D), psi_mn, psi_h);
     const double tcm = s0(L.sl(m, SL_TC)), tc1 = s0(L.sl(1, SL_TC));
     double phi_m;
     {
       const double dz = p0(P0_DZTB);
-      const double dtdz = (tcm - tc1) / dz;
-      double dudz = (s0(L.uz(m)) - s0(L.uz(1))) / dz;
+      const double idz = frcp(dz);
+      const double dtdz = (tcm - tc1) * idz;
+      double dudz = (s0(L.uz(m)) - s0(L.uz(1))) * idz;
       if (fabs(dudz) < 0.01) dudz = 0.01;
-      const double Tk = s0(S0_TCSUM) / m + 273.15;
-      double Ri = (9.81 / Tk) * dtdz / (dudz * dudz);
+      const double Tk = fdiv(s0(S0_TCSUM), (double)m) + 273.15;
+      double Ri = fdiv(fdiv(9.81, Tk) * dtdz, dudz * dudz);
       if (Ri > 0.15) Ri = 0.15;
       if (Ri < -1) Ri = -1;
-      if (Ri < 0) { double phh = 1 / sqrt(1 - 16 * Ri); phi_m = sqrt(phh); }
-      else { double st = Ri / (1 - 5 * Ri); phi_m = 1 + (6 * st) / (1 + st); }
+      if (Ri < 0) { double phh = frcp(fsqrt(1 - 16 * Ri)); phi_m = fsqrt(phh); }
+      else { double st = fdiv(Ri, 1 - 5 * Ri); phi_m = 1 + fdiv(6 * st, 1 + st); }
     }
     double tcan;
     {
-      const double ufh = (0.4 * u2) / (p0(P0_LZU) + psi_h);
-      const double mm = Hprev / (0.4 * pha * cpair(tairn) * ufh);
+      const double ufh = fdiv(0.4 * u2, p0(P0_LZU) + psi_h);
+      const double mm = fdiv(Hprev, 0.4 * pha * cpair(tairn) * ufh);
       const double tref = tairn + mm * (p0(P0_LZUH) + psi_h);
       tcan = tref - mm * (p0(P0_LZOH) + psi_h);
     }
-    const double tfrost = dewpoint((relhumn / 100) * satvap(tairn), tairn);
+    const double tfrost = dewpoint(fdiv(relhumn, 100) * satvap(tairn), tairn);
     if (tcan < tfrost) tcan = tfrost;
     if (tcan > (tairn + 15)) tcan = tairn + 15;
     if (tcan < (tairn - 4.5)) tcan = tairn - 4.5;
     const double tet_tair = tetens(tairn), tet_tcan = tetens(tcan);
     {
-      const double ea = tet_tair * (relhumn / 100);
-      relhumn = (ea / tet_tcan) * 100;
+      const double ea = tet_tair * fdiv(relhumn, 100);
+      relhumn = fdiv(ea, tet_tcan) * 100;
       if (relhumn > 100) relhumn = 100;
     }
-    sqphi = sqrt(phi_m); iphi = 1 / phi_m;
-    ugr = (0.4 * (u / p0(P0_GLNH))) / 0.4;                                    // grass-profile ur = ugr * gl (uref = u, zref = zu)
+    sqphi = fsqrt(phi_m); iphi = frcp(phi_m);
+    ugr = fdiv(0.4 * fdiv(u, p0(P0_GLNH)), 0.4);                                    // grass-profile ur = ugr * gl (uref = u, zref = zu)
     {
-      const double ufw = 0.4 * (u2 / (lnref + psi_mn));
+      const double ufw = 0.4 * fdiv(u2, lnref + psi_mn);
       double ln2 = p0(P0_LNHD) + psi_mn;
       if (ln2 < 0.55) ln2 = 0.55;
-      uh = (ufw / 0.4) * ln2;
+      uh = fdiv(ufw, 0.4) * ln2;
     }
     ps1a = ps1; tcu = tcm;
     mem.park(X_TAIRN, tairn); mem.park(X_PKN, pkn); mem.park(X_SKYEM, fc.skyem); mem.park(X_RSW, fc.Rsw); mem.park(X_RELHUMN, relhumn);
@@ -674,20 +677,20 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
     day = sa > 0;
     mem.park(KR_K, K); mem.park(KR_MUL, mul); mem.park(KR_DP, dp); mem.park(KR_RSW, Rsw); mem.park(KR_AG0, aG0);
     mem.park(KR_SKLW, skyem * lwout); mem.park(KR_EMLW, emv * lwout);
-    mem.park(KG_C101, 101.3 / pkn); mem.park(KG_CPK, (44.6 * (pkn / 101.3)) * 273.15);
+    mem.park(KG_C101, fdiv(101.3, pkn)); mem.park(KG_CPK, (44.6 * fdiv(pkn, 101.3)) * 273.15);
     const double mtref = 0.5 * tcan + 0.5 * x0[X_TAIRP];
     const double mrh = 0.5 * relhumn + 0.5 * x0[X_RELHUMP];
     const double mpk = 0.5 * ppk + 0.5 * pkn;
-    const double eref = (mrh / 100) * satvap(mtref);
+    const double eref = fdiv(mrh, 100) * satvap(mtref);
     const double esoil = soilrh(fc.theta, p0(P0_SOILB), -p0(P0_PSIE), p0(P0_SMAX), ps1) * satvap(ps1);     // Q7
-    const double eamn = (relhumn / 100) * tet_tcan;
+    const double eamn = fdiv(relhumn, 100) * tet_tcan;
     mem.park(KT_EREF, eref); mem.park(KT_ESOIL, esoil); mem.park(KT_MTREF, mtref); mem.park(KT_PS1, ps1); mem.park(KT_RGCAP, mem.unpark(X_RGCAP));
-    mem.park(KT_CPPK, (44.6 * (ppk / 101.3)) * 273.15);
+    mem.park(KT_CPPK, (44.6 * fdiv(ppk, 101.3)) * 273.15);
     mem.park(KU_LAMBDA, (-42.575 * tcan + 44994) * surfwet); mem.park(KU_IMPK, frcp(mpk));
-    mem.park(KU_TCAN, tcan); mem.park(KU_EAMN, eamn); mem.park(KU_IPPK, 1 / ppk); mem.park(KU_PKN, pkn);
+    mem.park(KU_TCAN, tcan); mem.park(KU_EAMN, eamn); mem.park(KU_IPPK, frcp(ppk)); mem.park(KU_PKN, pkn);
     // soilk (microctools; Column::soilk) for this step's theta
     const double ct = p0(P0_SKC) * fc.theta;
-    mem.park(X_LAM, p0(P0_SKA) + p0(P0_SKB) * fc.theta - p0(P0_SKAD) * exp(-((ct * ct) * (ct * ct))));
+    mem.park(X_LAM, p0(P0_SKA) + p0(P0_SKB) * fc.theta - p0(P0_SKAD) * fexp(-((ct * ct) * (ct * ct))));
     mem.park(X_CV, (p0(P0_CVDRY) + 4.18 * fc.theta) * 1e6);
     mem.park_done();
   }
@@ -896,7 +899,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
     const double Xs = mem.unpark(X_XS), TT = mem.unpark(X_TT), lam = mem.unpark(X_LAM), Cv = mem.unpark(X_CV);
     const double esoil = mem.unpark(KT_ESOIL), eamn = mem.unpark(KU_EAMN);          // (all tensor-memory reads before lanes diverge)
     const double timestep = cfg.timestep, i2ts = 1 / (2 * timestep);
-    TX = TT + (pha / gtncap) * 2;
+    TX = TT + fdiv(pha, gtncap) * 2;
     if (!MC_SKIP(4)) {
       mgx = (ng > 1) ? ng : 0;
       const int mg = mgx, N = mg + sm;
@@ -904,22 +907,34 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
       if (mg > 0) {                                   // layeraverage (code.R:814) and the air part of the system (code.R:815-826)
         int cprev = 0;
         lz[1] = 0;
+#pragma unroll 1
         for (int g = 1; g <= mg; ++g) {
-          const double iw = 1 / gw[g];
+          const double iw = frcp(gw[g]);
           ltc[g] = gtc[g] * iw; lVo[g] = gVo[g] * iw; lea[g] = gea[g] * iw;
           lph[g] = phair(ltc[g], ppk);
           const int c = (glo[g] + ghi[g] + 1) / 2;
           lz[g + 1] = P[(long long)L.pz(c) * kTile]; lTT[g] = wget(c, WL_TT);
           if (c - cprev == 1) lgt[g] = wget(c, WL_GTN);
-          else { double R = 0; for (int j = cprev + 1; j <= c; ++j) R += 1 / wget(j, WL_GTN); lgt[g] = 1 / R; }
+          else {
+            double R = 0;
+#pragma unroll 1
+            for (int j = cprev + 1; j <= c; ++j) R += frcp(wget(j, WL_GTN));
+            lgt[g] = frcp(R);
+          }
           cprev = c;
           xv[mg + 1 - g] = gX[g] * iw;
         }
         if (m + 1 - cprev == 1) lgt[mg + 1] = gtncap;
-        else { double R = 0; for (int j = cprev + 1; j <= m; ++j) R += 1 / wget(j, WL_GTN); R += 1 / gtncap; lgt[mg + 1] = 1 / R; }
+        else {
+          double R = 0;
+#pragma unroll 1
+          for (int j = cprev + 1; j <= m; ++j) R += frcp(wget(j, WL_GTN));
+          R += frcp(gtncap); lgt[mg + 1] = frcp(R);
+        }
         lz[mg + 2] = p0(P0_HGT);
+#pragma unroll 1
         for (int g = 1; g <= mg; ++g) {
-          const double lcp = cpair(ltc[g]), lvd = gvd[g] * (1 / gw[g]);
+          const double lcp = cpair(ltc[g]), lvd = gvd[g] * frcp(gw[g]);
           const double cda = lcp * lph[g] * (1 - lvd) * (lz[g + 2] - lz[g]) / 2 * timestep;       // Q10
           double ka = lgt[g] * lcp;
           if (ka > cda) ka = cda;
@@ -927,7 +942,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
         }
         mem.scr_put(SK0 + 1, lgt[mg + 1] * cpair(tabove));
       } else {
-        mem.scr_put(SK0 + 1, (1 / cs) * cpair(tabove));   // one lumped conductance for the lower half of the canopy (code.R:856-857)
+        mem.scr_put(SK0 + 1, frcp(cs) * cpair(tabove));   // one lumped conductance for the lower half of the canopy (code.R:856-857)
       }
       xv[mg + 1] = Xs;
       {                                                  // soil nodes: all row loads first (one latency), then the scratch stores
@@ -951,20 +966,21 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
         for (int g = 1; g <= mg + 1; ++g) Yt[g] = mem.scr_get(STC0 + mg + 3 - g);
         double rhs = soilrh(fc.theta, p0(P0_SOILB), p0(P0_PSIE), p0(P0_SMAX), tns1); if (rhs > 1) rhs = 1;
         double rhsp = soilrh(fc.thetap, p0(P0_SOILB), p0(P0_PSIE), p0(P0_SMAX), ps1); if (rhsp > 1) rhsp = 1;
-        Vair = (tet_tcan * (relhumn / 100)) / pkn;
-        const double eap = tetens(tairp) * (relhump / 100);
-        Vsoil = (tetens(tns1) * rhs) / pkn;
+        const double ipkn = frcp(pkn), ippk = frcp(ppk);
+        Vair = (tet_tcan * fdiv(relhumn, 100)) * ipkn;
+        const double eap = tetens(tairp) * fdiv(relhump, 100);
+        Vsoil = (tetens(tns1) * rhs) * ipkn;
         const double easp = tetens(tsoilp) * rhsp;                               // Q5
-        mem.scr_put(VTC0 + 1, eap / ppk); mem.scr_put(VTC0 + mg + 2, easp / ppk);
+        mem.scr_put(VTC0 + 1, eap * ippk); mem.scr_put(VTC0 + mg + 2, easp * ippk);
         for (int g = 1; g <= mg; ++g) mem.scr_put(VTC0 + 1 + g, lVo[mg + 1 - g]);
         for (int g = 1; g <= mg + 1; ++g) {
           double gt2 = lgt[g];
-          if (g <= mg) { const double gtmx = lph[g] / (lz[g + 1] - lz[g]) * (2 * timestep); if (gt2 > gtmx) gt2 = gtmx; }
+          if (g <= mg) { const double gtmx = fdiv(lph[g], lz[g + 1] - lz[g]) * (2 * timestep); if (gt2 > gtmx) gt2 = gtmx; }
           mem.scr_put(VK0 + mg + 2 - g, gt2);
         }
         for (int g = 1; g <= mg; ++g) {
           mem.scr_put(VCD0 + mg + 1 - g, phair(Yt[g + 1], pkn));
-          double vf = (lea[g] / pkn) - lVo[g]; if (vf < 0) vf = 0;
+          double vf = (lea[g] * ipkn) - lVo[g]; if (vf < 0) vf = 0;
           vX[g] = vf;                                                            // Q6: not reversed
         }
       }
@@ -1005,7 +1021,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
     const double trlw_sum = p0(P0_TRLWSUM), emv = p0(P0_EMV);
     const double skyem = mem.unpark(X_SKYEM), pkn = mem.unpark(X_PKN);
     const int selG = (int)p0(P0_SELG), selH = (int)p0(P0_SELH);
-    const double iTX = 1 / TX;
+    const double iTX = frcp(TX);
     for (int i = 1; i <= m; ++i) {
       mem.stageC(i);
       if (MC_SKIP(8)) continue;
@@ -1024,7 +1040,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
         if (v == T2b) { tnn = Ytb; ea2 = Yeb * pkn; }
         else if (v == T2a) { tnn = Yta; ea2 = Yea * pkn; }
         else {
-          const double w = (v - T2a) / (T2b - T2a);
+          const double w = fdiv(v - T2a, T2b - T2a);
           tnn = Yta + (Ytb - Yta) * w;
           ea2 = (Yea + (Yeb - Yea) * w) * pkn;                                     // ea <- vn * pk (code.R:852)
         }
@@ -1064,7 +1080,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
   if (tns1 < tfrost) tns1 = tfrost;
   if (tns1 > tairn + 30) tns1 = tairn + 30;
   const double refm = p0(P0_REFM);
-  const double shade = (1 - exp(-refm * p0(P0_SUMPAI)));
+  const double shade = (1 - fexp(-refm * p0(P0_SUMPAI)));
   const double alb = shade * refm + (1 - shade) * refg;
   const double Rlw = kSb * 0.97 * pow4(0.5 * tns1 + 0.5 * ps1 + 273.15);
   double Gn;
@@ -1072,8 +1088,8 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
     const double a = p0(P0_A0G) * sqphi_e;
     const double t1 = tnselG, t0 = tns1;
     const double ph = phair((t1 + t0) / 2, pkn);
-    const double e0 = exp(-a * (-1.0)), e1 = exp(-a * p0(P0_GXG1));
-    const double g = (p0(P0_CGG) * ph * uh_e * a) / ((e0 - e1) * phi_m);
+    const double e0 = fexp(-a * (-1.0)), e1 = fexp(-a * p0(P0_GXG1));
+    const double g = fdiv(p0(P0_CGG) * ph * uh_e * a, (e0 - e1) * phi_m);
     const double gfree = 0.0012 * ph * qroot(fabs(t1 - t0) * p0(P0_RZG));
     const double gt2 = (g > gfree) ? g : gfree;
     Gn = gt2 * cp1_e * (t1 - t0);

@@ -165,7 +165,7 @@ MC_HD double qroot(double x) { return fsqrt(fsqrt(x)); }           // x^0.25
 MC_HD double pow175(double x) { double r = fsqrt(x); return x * r * fsqrt(r); }   // x^1.75
 
 // ---- thermodynamics ---------------------------------------------------------------------------
-MC_HD double phair(double tc, double pk) { return 44.6 * (pk / 101.3) * (273.15 / (tc + 273.15)); }
+MC_HD double phair(double tc, double pk) { return 44.6 * fdiv(pk, 101.3) * fdiv(273.15, tc + 273.15); }
 MC_HD double cpair(double tc) { return 2e-05 * tc * tc + 0.0002 * tc + 29.119; }
 MC_HD double tetens(double tc) { return 0.6108 * fexp(fdiv(17.27 * tc, tc + 237.3)); }   // code.R:156,382,410,...
 MC_HD double phair_c(double c, double tc) { return c * fdiv(273.15, tc + 273.15); }     // c = 44.6 * (pk / 101.3)
@@ -177,7 +177,7 @@ MC_HD double satvap(double tc) {                                   // ice = TRUE
 MC_HD double dewpoint(double ea, double tc) {
   double e0, L;
   if (tc < 0) { e0 = 610.78 / 1000; L = 2.834e6; } else { e0 = 611.2 / 1000; L = 2.501e6 - 2340 * tc; }
-  double it = 1 / 273.15 - fdiv(461.5, L) * log(fdiv(ea, e0));
+  double it = 1 / 273.15 - fdiv(461.5, L) * flog(fdiv(ea, e0));
   return frcp(it) - 273.15;
 }
 
@@ -204,9 +204,9 @@ MC_HD double attencoef_base(double hgt, double PAI, double cd, double iw, double
 }
 MC_HD void diabatic_cor(double tc, double pk, double H, double uf, double zi, double d, double& psi_m, double& psi_h) {
   double Tk = tc + 273.15;
-  double st = -(0.4 * 9.81 * (zi - d) * H) / (phair(tc, pk) * cpair(tc) * Tk * (uf * uf * uf));
-  if (st < 0) { psi_h = -2 * log((1 + sqrt(1 - 16 * st)) / 2); psi_m = 0.6 * psi_h; }
-  else { psi_h = 6 * log(1 + st); psi_m = psi_h; }
+  double st = -fdiv(0.4 * 9.81 * (zi - d) * H, phair(tc, pk) * cpair(tc) * Tk * (uf * uf * uf));
+  if (st < 0) { psi_h = -2 * flog((1 + fsqrt(1 - 16 * st)) / 2); psi_m = 0.6 * psi_h; }
+  else { psi_h = 6 * flog(1 + st); psi_m = psi_h; }
   if (psi_m > 4) psi_m = 4;
   if (psi_h > 4) psi_h = 4;
   if (psi_m < -1.5) psi_m = -1.5;
@@ -216,10 +216,10 @@ MC_HD void diabatic_cor(double tc, double pk, double H, double uf, double zi, do
 MC_HD double gcanopy_a(double uh, double z1, double z0, double tc1, double tc0, double hgt, double l_m, double a,
                        double iw, double phi_m, double pk) {
   double ph = phair((tc1 + tc0) / 2, pk);
-  double e0 = exp(-a * (z0 / hgt - 1));
-  double e1 = exp(-a * (z1 / hgt - 1));
-  double g = (l_m * iw * ph * uh * a) / (hgt * (e0 - e1) * phi_m);
-  double gfree = 0.0012 * ph * qroot(fabs(tc1 - tc0) / fabs(z1 - z0));
+  double e0 = fexp(-a * (fdiv(z0, hgt) - 1));
+  double e1 = fexp(-a * (fdiv(z1, hgt) - 1));
+  double g = fdiv(l_m * iw * ph * uh * a, hgt * (e0 - e1) * phi_m);
+  double gfree = 0.0012 * ph * qroot(fdiv(fabs(tc1 - tc0), fabs(z1 - z0)));
   return (g > gfree) ? g : gfree;
 }
 MC_HD double gcanopy(double uh, double z1, double z0, double tc1, double tc0, double hgt, double PAI, double cd,
@@ -260,24 +260,28 @@ MC_HD double gforcedfree(double d, double u, double tc, double dtc, double pk, d
 }
 MC_HD double layercond(double Rsw, double gsmax, double q50) { double Qa = 4.6 * Rsw; return (gsmax * Qa) / (Qa + q50); }
 MC_HD double soilrh(double theta, double b, double Psie, double Smax, double tc) {
+#if defined(__CUDA_ARCH__)
+  double matric = -Psie * fexp(-b * flog(fdiv(theta, Smax)));          // (theta / Smax)^-b
+#else
   double matric = -Psie * pow(theta / Smax, -b);
-  return exp((0.018 * matric) / (8.31 * (tc + 273.15)));
+#endif
+  return fexp(fdiv(0.018 * matric, 8.31 * (tc + 273.15)));
 }
 
 // ---- sun / radiation --------------------------------------------------------------------------
 MC_HD double solalt(double lt, double lat, double lon, double jd, double merid, double dst) {
   double mm = 6.24004077 + 0.01720197 * (jd - 2451545);
   double eot = -7.659 * sin(mm) + 9.863 * sin(2 * mm + 3.5932);
-  double st = lt + (4 * (lon - merid) + eot) / 60 - dst;
+  double st = lt + fdiv(4 * (lon - merid) + eot, 60) - dst;
   double tt = 0.261799 * (st - 12);
-  double declin = (kPi * 23.5 / 180) * cos(2 * kPi * ((jd - 159.5) / 365.25));
-  double latr = lat * kPi / 180;
+  double declin = (kPi * 23.5 / 180) * cos(2 * kPi * fdiv(jd - 159.5, 365.25));
+  double latr = fdiv(lat * kPi, 180);
   double sh = sin(declin) * sin(latr) + cos(declin) * cos(latr) * cos(tt);
-  return (180 * atan(sh / sqrt(1 - sh * sh))) / kPi;
+  return fdiv(180 * atan(fdiv(sh, fsqrt(1 - sh * sh))), kPi);
 }
 MC_HD double difprop(double Rsw, double sa) {
   if (!(sa > 0) || !(Rsw > 0)) return 1.0;
-  double kt = Rsw / (1352.0 * sin(sa * kPi / 180));
+  double kt = fdiv(Rsw, 1352.0 * sin(fdiv(sa * kPi, 180)));
   if (kt > 1) kt = 1;
   if (kt <= 0.22) return 1 - 0.09 * kt;
   if (kt <= 0.8) return 0.9511 - 0.1604 * kt + 4.388 * kt * kt - 16.638 * kt * kt * kt + 12.336 * kt * kt * kt * kt;
@@ -285,19 +289,19 @@ MC_HD double difprop(double Rsw, double sa) {
 }
 MC_HD double cank_den(double x) { return x + 1.774 * pow(x + 1.182, -0.733); }   // column-invariant
 MC_HD double cank(double x, double sa, double den) {
-  double t = tan((90 - sa) * kPi / 180);
-  return sqrt(x * x + t * t) / den;
+  double t = tan(fdiv((90 - sa) * kPi, 180));
+  return fdiv(fsqrt(x * x + t * t), den);
 }
 MC_HD double clumptr(double tr, double clump) { return clump + (1 - clump) * tr; }
 // shortwave under plant area l: `s` = sqrt(1 - ref), `trd` = clumped diffuse transmission exp(-s*l),
 // `K` = beam extinction (unused when sa <= 0)
 MC_HD double cansw_k(double globrad, double dp, double sa, double l, double s, double trd, double K, double clump) {
-  double trb = (sa > 0) ? clumptr(exp(-s * K * l), clump) : clumptr(0.0, clump);
+  double trb = (sa > 0) ? clumptr(fexp(-s * K * l), clump) : clumptr(0.0, clump);
   return globrad * (dp * trd + (1 - dp) * trb);
 }
 MC_HD double psunlit_k(double l, double sa, double K, double clump) {
   if (!(sa > 0)) return clumptr(0.0, clump);
-  return clumptr(exp(-K * l), clump);
+  return clumptr(fexp(-K * l), clump);
 }
 
 }  // namespace mc
