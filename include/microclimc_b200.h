@@ -110,6 +110,12 @@ double mc_bench_resident(mc_ctx* ctx, int reps);
  * FP64-bound path (the driver's MEASURED_PEAKS.json carries no FP64 figure). */
 double mc_fp64_peak_tflops(mc_ctx* ctx);
 
+/* Diagnostic: evaluates the device's fast FP64 primitives (microclimc_b200/csrc/mc_phys.cuh) on n host values.
+ * op: 0 exp, 1 log, 2 1/x, 3 sqrt, 4 x/y (y = second operand array, may be null for the other ops).
+ * The kernels of this library replace IEEE division and the libm exp/log/sqrt by these; tests bound their error in ulp.
+ * Returns 0 or a negative MC_ERR_* code. */
+int mc_eval_primitive(mc_ctx* ctx, int op, int64_t n, const double* x, const double* y, double* out);
+
 #ifdef __cplusplus
 }
 #endif

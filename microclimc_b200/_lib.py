@@ -33,6 +33,7 @@ SYMBOLS = {
     "mc_last_kernel_launches": (I64, [C.c_void_p]),
     "mc_bench_resident": (D, [C.c_void_p, C.c_int]),
     "mc_fp64_peak_tflops": (D, [C.c_void_p]),
+    "mc_eval_primitive": (C.c_int, [C.c_void_p, C.c_int, I64, PD, PD, PD]),
 }
 
 
@@ -163,6 +164,15 @@ class Context:
 
     def fp64_peak_tflops(self):
         return lib().mc_fp64_peak_tflops(self._h)
+
+    def eval_primitive(self, op, x, y=None):
+        """Device fast-math primitive `op` ("exp", "log", "rcp", "sqrt", "div") on host arrays (diagnostic)."""
+        code = {"exp": 0, "log": 1, "rcp": 2, "sqrt": 3, "div": 4}[op]
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = None if y is None else np.ascontiguousarray(y, dtype=np.float64)
+        out = np.empty_like(x)
+        self._chk(lib().mc_eval_primitive(self._h, code, x.size, _p(x), _p(y), _p(out)))
+        return out
 
     def bench_resident(self, reps=1):
         ms = lib().mc_bench_resident(self._h, reps)

@@ -108,6 +108,23 @@ __global__ void k_steady_reduce(long long ncol, int nchunk, long long T, const d
   stats[3 * ncol + c] = s1 / (double)T; stats[4 * ncol + c] = mn1; stats[5 * ncol + c] = mx1;
 }
 
+// Diagnostic: the fast FP64 primitives of mc_phys.cuh on plain arrays (tests bound their error in ulp).
+__global__ void k_eval_primitive(int op, long long n, const double* x, const double* y, double* out) {
+  exp_tab_init();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = x[i];
+  double r;
+  switch (op) {
+    case 0: r = mc::fexp(a); break;
+    case 1: r = mc::flog(a); break;
+    case 2: r = mc::frcp(a); break;
+    case 3: r = mc::fsqrt(a); break;
+    default: r = mc::fdiv(a, y[i]); break;
+  }
+  out[i] = r;
+}
+
 // FP64 pipe peak probe: 8 independent DFMA chains per thread (the roofline denominator for this FP64-bound path;
 // MEASURED_PEAKS.json has no FP64 entry).
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
@@ -643,6 +660,29 @@ double mc_fp64_peak_tflops(mc_ctx* ctx) {
   if (cudaGetLastError() != cudaSuccess) return -1.0;
   double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
   return flops / (best * 1e-3) / 1e12;
+}
+
+int mc_eval_primitive(mc_ctx* ctx, int op, int64_t n, const double* x, const double* y, double* out) {
+  if (!ctx || ctx->shards.empty() || n < 0 || !x || !out || op < 0 || op > 4 || (op == 4 && !y))
+    return fail(ctx, MC_ERR_ARG, "mc_eval_primitive: bad argument");
+  if (n == 0) return 0;
+  Shard& s = ctx->shards[0];
+  cudaSetDevice(s.dev);
+  double *dx = nullptr, *dy = nullptr, *dout = nullptr;
+  const size_t bytes = sizeof(double) * (size_t)n;
+  cudaError_t e = cudaMalloc(&dx, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&dout, bytes);
+  if (e == cudaSuccess && y) e = cudaMalloc(&dy, bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dx, x, bytes, cudaMemcpyHostToDevice, s.st);
+  if (e == cudaSuccess && y) e = cudaMemcpyAsync(dy, y, bytes, cudaMemcpyHostToDevice, s.st);
+  if (e == cudaSuccess) {
+    k_eval_primitive<<<(unsigned)((n + 127) / 128), 128, 0, s.st>>>(op, n, dx, dy, dout);
+    e = cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, s.st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s.st);
+  cudaFree(dx); cudaFree(dy); cudaFree(dout);
+  if (e != cudaSuccess) return fail(ctx, MC_ERR_CUDA, std::string("mc_eval_primitive: ") + cudaGetErrorString(e));
+  return 0;
 }
 
 double mc_last_kernel_ms(const mc_ctx* ctx) { return ctx ? ctx->last_ms : -1.0; }

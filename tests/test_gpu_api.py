@@ -119,3 +119,29 @@ def test_full_size_properties_one_million_columns(oracle):
                                 make_cfg(spin_steps=30), M, SM, fscale=base["fs"][:, :16], foffset=base["fo"][:, :16])
     assert_series_close(r["series"][:, :, :16], want["series"], "1M grid sample")
     assert_series_close(r["series"][:, :, 16:], want["series"], "1M grid sample (far end)")
+
+
+def _ulp_err(got, want):
+    """|got - want| in units of the spacing of `want` (want computed in extended precision where available)."""
+    want = np.asarray(want, dtype=np.longdouble)
+    sp = np.spacing(np.abs(want.astype(np.float64))).astype(np.longdouble)
+    return np.max(np.abs(np.asarray(got, dtype=np.longdouble) - want) / sp)
+
+
+def test_fast_fp64_primitives_are_within_two_ulp():
+    """The kernels replace IEEE division and libm exp/log/sqrt by branch-free sequences (mc_phys.cuh); bound them in ulp
+    over the ranges this path uses, and check the special values the code relies on."""
+    from microclimc_b200._lib import Context
+    ctx = Context(20, 10, 1, [0])
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-700, 700, 200000), rng.uniform(-5, 5, 200000), rng.uniform(-1e-3, 1e-3, 50000)])
+    assert _ulp_err(ctx.eval_primitive("exp", x), np.exp(x.astype(np.longdouble))) <= 2.0
+    sp = ctx.eval_primitive("exp", np.array([-800.0, 800.0, np.nan, 0.0, -708.5]))
+    assert sp[0] == 0.0 and np.isinf(sp[1]) and np.isnan(sp[2]) and sp[3] == 1.0 and sp[4] == 0.0
+    p = np.concatenate([rng.uniform(1e-6, 1e6, 200000), np.exp(rng.uniform(-300, 300, 100000)), rng.uniform(0.5, 2.0, 100000)])
+    assert _ulp_err(ctx.eval_primitive("log", p), np.log(p.astype(np.longdouble))) <= 2.0
+    assert _ulp_err(ctx.eval_primitive("rcp", p), 1 / p.astype(np.longdouble)) <= 1.0
+    assert _ulp_err(ctx.eval_primitive("sqrt", p), np.sqrt(p.astype(np.longdouble))) <= 1.0
+    q = np.concatenate([rng.uniform(-1e3, 1e3, 300000), rng.uniform(-1, 1, 100000)])
+    assert _ulp_err(ctx.eval_primitive("div", q, p), q.astype(np.longdouble) / p.astype(np.longdouble)) <= 1.0
+    assert ctx.eval_primitive("sqrt", np.array([0.0]))[0] == 0.0
