@@ -39,11 +39,13 @@ enum { PB_REF, PB_PC, PB_SPC, PB_SGC, PB_TRDC, PB_TRDG, PB_TRLW, PB_PAI, PB_IZTH
        PB_VDEN, PB_DZ, PB_N };
 enum { S0_TABOVE, S0_RELHUM, S0_TAIR, S0_TSOIL, S0_PK, S0_H, S0_PSIM, S0_G, S0_TCSUM, S0_GTCAP, S0_N };   // then soiltc[sm]
 enum { SL_TC, SL_TLEAF, SL_RH, SL_RABS, SL_GV, SL_GHA, SL_N };
-enum { WL_RG, WL_SFX, WL_GTN, WL_UZN, WL_PHZ, WL_TT, WL_EAL, WL_L, WL_RSWIN, WL_RLWIN, WL_N };
-constexpr int kWLiveB = 5;                        // W rows sweep B reads back from sweep A (RG .. PHZ)
+enum { WL_GTN, WL_UZN, WL_PHZ, WL_TT, WL_EAL, WL_L, WL_RSWIN, WL_RLWIN, WL_N };
+constexpr int kWLiveB = 3;                        // W rows sweep B reads back from sweep A (GTN, UZN, PHZ)
 constexpr int kWLiveC = 2;                        // W rows sweep C reads back from sweep B (TT, EAL)
 constexpr int kCL = 5;                            // layers per sweep-C stage (their TT/EAL rows are contiguous: 10 rows)
-constexpr int kStageRows = PB_N + SL_N + kWLiveB; // 27 rows of 128 doubles = 27 KB per stage buffer
+constexpr int kStageRowsB = PB_N + SL_N + kWLiveB + 1;   // sweep-B stage: geometry, state, work rows and the old gt row = 26 rows
+constexpr int kStageRows = 27;                    // rows of 128 doubles per stage buffer (the solver scratch needs 2 x 27)
+static_assert(kStageRowsB <= kStageRows, "sweep-B stage exceeds the stage buffer");
 constexpr int kNG = 6;                            // merged air layers handled in the streaming form (more: general path)
 
 struct FastLayout {
@@ -58,7 +60,7 @@ struct FastLayout {
   MC_HD int uz(int i) const { return S0_N + sm + m * SL_N + (i - 1); }
   MC_HD int gt(int i) const { return S0_N + sm + m * SL_N + m + (i - 1); }          // i = 1..m+1
   MC_HD int nS() const { return S0_N + sm + m * SL_N + m + (m + 1); }
-  // per-layer blocks of 8 rows (RG..PHZ, L, RSWIN, RLWIN), then the sweep-C rows (TT, EAL) of all layers contiguously
+  // per-layer blocks of 6 rows (GTN, UZN, PHZ, L, RSWIN, RLWIN), then the sweep-C rows (TT, EAL) of all layers contiguously
   MC_HD int wl(int i, int r) const {
     return (r == WL_TT || r == WL_EAL) ? m * (WL_N - 2) + (i - 1) * 2 + (r - WL_TT) : (i - 1) * (WL_N - 2) + (r < WL_TT ? r : r - 2);
   }
@@ -185,6 +187,7 @@ struct DirectMem {
   MC_HD double b_p(int r) const { return P[(long long)L.pb(ib, r) * kTile]; }
   MC_HD double b_s(int r) const { return S[(long long)L.sl(ib, r) * kTile]; }
   MC_HD double b_w(int r) const { return W[(long long)L.wl(ib, r) * kTile]; }
+  MC_HD double b_gto() const { return S[(long long)L.gt(ib) * kTile]; }                     // read before the layer stores its new gt
 };
 
 #if defined(__CUDACC__)
@@ -295,10 +298,11 @@ struct PipeMem {
   MC_D void issueB(int i, unsigned kk) {
     const unsigned b = buf32 + (kk & 1) * (kStageRows * kTile * 8);
     const unsigned mb = bar32 + (kk & 1) * 8;
-    mbar_expect_tx(mb, kStageRows * kTile * 8);
+    mbar_expect_tx(mb, kStageRowsB * kTile * 8);
     bulk_g2s_stream(b, Pt + (long long)L.pb(i, 0) * kTile, PB_N * kTile * 8, mb, pol);
     bulk_g2s_stream(b + PB_N * kTile * 8, St + (long long)L.sl(i, 0) * kTile, SL_N * kTile * 8, mb, pol);
     bulk_g2s(b + (PB_N + SL_N) * kTile * 8, Wt + (long long)L.wl(i, 0) * kTile, kWLiveB * kTile * 8, mb);
+    bulk_g2s_stream(b + (PB_N + SL_N + kWLiveB) * kTile * 8, St + (long long)L.gt(i) * kTile, kTile * 8, mb, pol);
   }
   MC_D void issueC(int i, unsigned kk) {                  // rows of layers i .. i+kCL-1 (or up to m)
     const unsigned b = buf32 + (kk & 1) * (kStageRows * kTile * 8);
@@ -354,6 +358,7 @@ struct PipeMem {
   MC_D double b_p(int r) const { return cur[r * kTile]; }
   MC_D double b_s(int r) const { return cur[(PB_N + r) * kTile]; }
   MC_D double b_w(int r) const { return cur[(PB_N + SL_N + r) * kTile]; }
+  MC_D double b_gto() const { return cur[(PB_N + SL_N + kWLiveB) * kTile]; }
   MC_D double c_w(int r) const { return cur[r * kTile]; }
 };
 #endif
@@ -636,7 +641,9 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
       const double rg = frcp(0.5 * gtn + 0.5 * mem.a_gto());
       const double phz = phair_c(cppk, tcu) * mem.a_p(PA_DZ);
       double* Wl = W + (long long)L.wl(i, 0) * kTile;
-      Wl[WL_RG * kTile] = rg; Wl[WL_SFX * kTile] = sfx; Wl[WL_GTN * kTile] = gtn; Wl[WL_UZN * kTile] = uzn; Wl[WL_PHZ * kTile] = phz;
+      Wl[WL_GTN * kTile] = gtn; Wl[WL_UZN * kTile] = uzn; Wl[WL_PHZ * kTile] = phz;
+      // rg and its sum above each layer are not handed to sweep B through memory: B recomputes rg from gtn and the old gt row
+      // and rebuilds the sum above layer i as (total - sum up to i)
       sfx += rg; Rtot += rn; Ctot += phz;
       if (i <= half) cs += rn;
       tcu = tcl;
@@ -654,6 +661,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
     // sum(1/gt) * sum(ph*zth) >= k^2 * timestep (Cauchy-Schwarz), so below (kNG+1)^2 * timestep at most kNG groups exist.
     if (!(Rtot * Ctot < (double)((kNG + 1) * (kNG + 1)) * cfg.timestep * (1 - 1e-9))) fastok = false;
     mem.park(X_UH, uh); mem.park(X_SQPHI, sqphi); mem.park(X_CS, cs); mem.park(X_GTNCAP, gtncap); mem.park(X_RGCAP, rgcap);
+    mem.park(KT_TNS1, sfx);                            // sum of rg over all layers (the slot is free until the solve)
   }
   MC_TICK(1);
   mem.sweepB_begin();
@@ -745,9 +753,10 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
       const double timestep = cfg.timestep;
       const double lambda_l = ku[KU_LAMBDA - KU_LAMBDA], impk = ku[KU_IMPK - KU_LAMBDA], tcan = ku[KU_TCAN - KU_LAMBDA], eamn = ku[KU_EAMN - KU_LAMBDA];
       // leaftemp (code.R:378-512)
-      const double rg = mem.b_w(WL_RG);
-      const double gtt = frcp(kt[KT_RGCAP - KT_EREF] + mem.b_w(WL_SFX));
+      const double rg = frcp(0.5 * gtn + 0.5 * mem.b_gto());                     // as in sweep A
       acc2 += rg;
+      const double sfxi = (i == m) ? 0.0 : kt[KT_TNS1 - KT_EREF] - acc2;            // sum of rg above this layer
+      const double gtt = frcp(kt[KT_RGCAP - KT_EREF] + sfxi);
       const double gtt2 = frcp(acc2);
       const double izl = mem.b_p(PB_IZL), izrf = mem.b_p(PB_IZRF), izp = mem.b_p(PB_IZP), izth = mem.b_p(PB_IZTH), PAIi = mem.b_p(PB_PAI);
       const double PAIm = 2 * PAIi * izth;
@@ -871,7 +880,10 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
       if (runB) {
         double* Sl = S + (long long)L.sl(i, 0) * kTile;
         Sl[SL_TLEAF * kTile] = tleafn; Sl[SL_RABS * kTile] = Rabsn; Sl[SL_GV * kTile] = gvn; Sl[SL_GHA * kTile] = ghan;
-        sput(L.uz(i), uzn); sput(L.gt(i), gtn);
+        // previn$uz is only read at the lowest and highest node (code.R:731), so the other rows are written when the state is
+        // harvested (emit) and not on every step
+        if (emit || i == 1 || i == m) sput(L.uz(i), uzn);
+        sput(L.gt(i), gtn);
       }
       wput(i, WL_TT, TT); wput(i, WL_EAL, ean);
       if (emit || i == selHb) { wput(i, WL_L, Lp); wput(i, WL_RSWIN, rsw); }
