@@ -1,0 +1,61 @@
+"""Throughput of the steady-state path (runmodelS + .runmodelsnow, NMR.R:717-885) on the shapes of BASELINE configs 2 and 4.
+Prints one JSON line per configuration: column-hours/s of k_steady (+ reduce) timed with CUDA events inside the library.
+  C2: 10^4-column perturbed-parameter ensemble, the bundled year of hourly forcing (8760 h), reqhgt 1 m, no snow
+  C4: 4 x 10^6 columns from 4 habitat templates, `hours` hours of winter forcing with the snow branch active
+Usage: python tools/bench_steady.py [--c4-cols N] [--c4-hours H]"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from microclimc_b200 import synth as S, layout as L          # noqa: E402
+from microclimc_b200._lib import Context                      # noqa: E402
+
+M, SM = 20, 10
+
+
+def soil_loam():
+    sp = S.load_soilparams(); i = sp["Soil.type"].index("Loam")
+    soil = {k: sp[k][i] for k in L.SOIL_SCALARS}
+    soil["z"] = (2.0 / 10 ** 1.2) * np.arange(1, 11) ** 1.2
+    return soil
+
+
+def run(name, ncol, T, t0, snow, reqhgt, reps, habitats=1):
+    rng = np.random.default_rng(3)
+    veg, soil = S.ensemble(S.vegp_deciduous(), soil_loam(), ncol, M, SM, seed=11)
+    if habitats > 1:                      # habitat classes: scale height and plant area of the template per class
+        cls = rng.integers(0, habitats, ncol)
+        veg[L.VEG_SCALARS.index("hgt")] *= (0.4 + 0.4 * cls)
+        veg[len(L.VEG_SCALARS):len(L.VEG_SCALARS) + M] *= (0.5 + 0.35 * cls)
+    clim = S.steady_clim_from_climdata(S.load_weather())[t0:t0 + T]
+    nmr = np.zeros((T, 11))
+    nmr[:, 0] = clim[:, 0] + rng.normal(0.5, 1.0, T)
+    nmr[:, 1] = rng.uniform(0.12, 0.4, T)
+    if snow:
+        nmr[:, 2] = np.clip(rng.normal(20, 40, T), 0, None)
+        nmr[:, 3:] = rng.uniform(-10, 0, (T, 8))
+    ctx = Context(M, SM, 1, [0])
+    ctx.set_columns(veg, soil, np.full(ncol, 50.0), np.full(ncol, -5.0))
+    scfg = np.array([reqhgt, 1, 2, 1, 0.95])
+    ctx.run_steady(clim, nmr, scfg, want_out=False)
+    ms = min(ctx.bench_resident(1) for _ in range(reps))
+    r = ctx.run_steady(clim, nmr, scfg, want_out=False)
+    print(json.dumps({"config": name, "columns": ncol, "hours": T, "snow_hours": int((nmr[:, 2] > 0).sum()), "kernel_ms": ms,
+                      "column_hours_per_s": ncol * T / (ms * 1e-3), "finite": bool(np.isfinite(r["stats"]).all())}))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--c4-cols", type=int, default=4_000_000)
+    ap.add_argument("--c4-hours", type=int, default=48)
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    if a.only in ("", "c2"):
+        run("C2", 10_000, 8760, 0, False, 1.0, 3)
+    if a.only in ("", "c4"):
+        run("C4", a.c4_cols, a.c4_hours, 300, True, 1.0, 2, habitats=4)
