@@ -36,7 +36,7 @@ constexpr double kSb = 5.67 * 1e-8;
 //    <= 1 ulp from the correctly rounded quotient for normal, finite, non-zero operands. Sites whose operands can
 //    legitimately be 0 / Inf (stomatal conductance at night) keep the IEEE `/`.
 //  * fexp: Cody-Waite reduction to |r| <= ln2/128 with a 64-entry table of 2^(j/64) in shared memory + degree-5
-//    polynomial, exponent insertion by integer add; relative error < 1.5 ulp, flushes below -708.
+//    polynomial, exponent insertion by integer add; relative error < 1.5 ulp; below -708 it returns e^-708 = 3e-308.
 // The host build (tests) maps them to the libm / IEEE operations.
 #if defined(__CUDACC__)
 // 2^(j/64), j = 0..63, correctly rounded.  Every kernel that evaluates fexp copies the table to shared memory first
@@ -90,10 +90,13 @@ MC_HD double fexp(double x) {
 #if defined(__CUDA_ARCH__)
   // x = (64 k + j) ln2/64 + r, |r| <= ln2/128:  exp(x) = 2^k * 2^(j/64) * exp(r), exp(r) - 1 by a degree-5 polynomial
   // (remainder r^6/720 < 4e-17).  10 FP64 operations on a dependent chain of 7 instead of 20 on a chain of 9.
-  double t = fma(x, 9.233248261689366e+01, 6755399441055744.0);        // 64/ln2; round-to-nearest integer in the low word
+  // Arguments below -708 are clamped first (the result is then e^-708 = 3e-308 instead of 0: the exponent insertion below must not
+  // underflow); a NaN passes the clamp, gives n = 0 and comes out as NaN.  One compare + select here instead of three at the end.
+  const double xc = (x < -708.0) ? -708.0 : x;
+  double t = fma(xc, 9.233248261689366e+01, 6755399441055744.0);       // 64/ln2; round-to-nearest integer in the low word
   const int n = __double2loint(t);
   const double kd = t - 6755399441055744.0;
-  double r = fma(kd, -0x1.62e42feep-7, x);                             // ln2/64, high part (trailing zeros: kd * hi is exact)
+  double r = fma(kd, -0x1.62e42feep-7, xc);                            // ln2/64, high part (trailing zeros: kd * hi is exact)
   r = fma(kd, -0x1.a39ef35793c76p-39, r);                              // ln2/64, low part
   const double T = s_exp_tab[n & 63];
   const double r2 = r * r;
@@ -101,9 +104,7 @@ MC_HD double fexp(double x) {
   const double d = fma(fma(a, r2, b), r2, r);                          // exp(r) - 1
   const double p = fma(T, d, T);
   double res = __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
-  if (x < -708.0) res = 0.0;
   if (x > 709.0) res = __longlong_as_double(0x7ff0000000000000LL);
-  if (x != x) res = x;
   return res;
 #else
   return exp(x);
