@@ -121,3 +121,33 @@ def test_seasonal_pai_and_full_year_single_column(oracle):
     ctx.set_config(cfg)
     got = ctx.run_transient(samp_idx=np.arange(4))
     assert_series_close(got["series"], want["series"], "seasonal year")
+
+
+@pytest.mark.parametrize("m,sm", [(7, 5), (12, 8), (20, 7), (33, 12)])
+def test_other_layer_counts_on_the_gpu(oracle, m, sm):
+    """Layer counts other than the 20/10 of the BASELINE configs: m <= 20, sm <= 10 run the streaming kernel's run-time-sized
+    instantiation (EXACT = false), larger templates the general kernel."""
+    from microclimc_b200._lib import Context
+    ncol, T = 40, 72
+    soil = loam(oracle); soil["z"] = oracle.soilinit_z(sm)
+    veg, so = S.ensemble(S.vegp_deciduous(m=m), soil, ncol, m, sm, seed=3)
+    f, ts = S.forcing_from_climdata(S.load_weather()); f = np.ascontiguousarray(f[4000:4000 + T])
+    lat = np.full(ncol, 50.0); lon = np.full(ncol, -5.0)
+    cfg = make_cfg(spin_steps=60)
+    want = oracle.run_transient(veg, so, f, lat, lon, cfg, m, sm, samp_idx=np.arange(ncol))
+    ctx = Context(m, sm)
+    ctx.set_columns(veg, so, lat, lon); ctx.set_forcing(f, None, None); ctx.set_config(cfg)
+    got = ctx.run_transient(samp_idx=np.arange(ncol))
+    assert_series_close(got["series"], want["series"], "m=%d sm=%d" % (m, sm))
+    assert_state_close(ctx.get_state(), want["state"], m=m, sm=sm, what="m=%d sm=%d" % (m, sm))
+
+
+@pytest.mark.parametrize("ncol", [1, 31, 127, 129, 1000])
+def test_ragged_column_counts(oracle, ncol):
+    """Column counts that do not fill a 128-column tile (padding lanes compute but never store)."""
+    inp = transient_inputs(oracle, ncol=ncol, T=30)
+    cfg = make_cfg(spin_steps=30)
+    want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"])
+    ctx = _ctx(inp, cfg)
+    ctx.run_transient()
+    assert_state_close(ctx.get_state(), want["state"], what="ncol=%d" % ncol)
