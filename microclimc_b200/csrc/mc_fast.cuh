@@ -168,8 +168,6 @@ struct DirectMem {
   MC_HD void park_done() {}
   MC_HD void unpark8(int slot0, double* v) { for (int q = 0; q < 8; ++q) v[q] = parked[slot0 + q]; }
   MC_HD double unpark(int slot) { return parked[slot]; }
-  MC_HD void park2(int slot, double a, double b) { parked[slot] = a; parked[slot + 1] = b; }
-  MC_HD void unpark2(int slot, double& a, double& b) { a = parked[slot]; b = parked[slot + 1]; }
   double scratch[2 * kStageRows];               // stands in for the idle stage buffers (PipeMem::scr_*)
   MC_HD double scr_get(int idx) const { return scratch[idx]; }
   MC_HD void scr_put(int idx, double v) { scratch[idx] = v; }
@@ -252,18 +250,6 @@ struct PipeMem {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(tbase + 2 * slot), "r"(__double2loint(v)), "r"(__double2hiint(v)));
   }
   MC_D void park_done() { asm volatile("tcgen05.wait::st.sync.aligned;"); }
-  MC_D void park2(int slot, double a, double b) {
-    __syncwarp();
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tbase + 2 * slot), "r"(__double2loint(a)),
-                 "r"(__double2hiint(a)), "r"(__double2loint(b)), "r"(__double2hiint(b)));
-  }
-  MC_D void unpark2(int slot, double& a, double& b) {
-    unsigned r0, r1, r2, r3;
-    __syncwarp();
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(tbase + 2 * slot));
-    asm volatile("tcgen05.wait::ld.sync.aligned;");
-    a = __hiloint2double(r1, r0); b = __hiloint2double(r3, r2);
-  }
   // per-thread scratch in the stage buffers while no stage is in flight (54 doubles: row idx of the two buffers, own lane)
   MC_D double scr_get(int idx) const { return buf[idx * kTile + lane]; }
   MC_D void scr_put(int idx, double v) { buf[idx * kTile + lane] = v; }
@@ -388,38 +374,6 @@ MC_HD double gha_fast(double d, double id, double d3, double u, double Tk, doubl
   const double gforced = (0.664 * Dh * ph * fsqrt(Re) * kCbrtPr) * id;
   const double gfree = (0.54 * Dh * ph * qroot(Gr * kPr)) * id;
   return 1.41 * ((gforced > gfree) ? gforced : gfree);
-}
-
-// Thomas (code.R:94-125; same recurrences as Column::thomas) with one reciprocal per eliminated node.
-MC_HD void thomas_f(int N, double* tcv, double tmsoil, double tairv, const double* k, const double* cdv, double f, const double* Xv,
-                    double* tn, double* cc, double* dd) {
-  const double g = 1 - f;
-  tn[N + 2] = tmsoil; tn[1] = tairv;
-  for (int xx = 2; xx <= N + 1; ++xx) tcv[xx] = tcv[xx] + g * Xv[xx - 1];
-  for (int xx = 2; xx <= N + 1; ++xx)
-    dd[xx] = g * k[xx - 1] * tcv[xx - 1] + (cdv[xx - 1] - g * (k[xx] + k[xx - 1])) * tcv[xx] + g * k[xx] * tcv[xx + 1];
-  dd[2] = dd[2] + k[1] * tn[1] * f;
-  dd[N + 1] = dd[N + 1] + k[N + 1] * f * tn[N + 2];
-  double b = f * (k[2] + k[1]) + cdv[1];
-  for (int i = 2; i <= N; ++i) {
-    const double ib = frcp(b);
-    const double a1 = -k[i] * f;
-    const double ci = a1 * ib;
-    cc[i] = ci;
-    dd[i] = dd[i] * ib;
-    b = (f * (k[i + 1] + k[i]) + cdv[i]) - a1 * ci;
-    dd[i + 1] = dd[i + 1] - a1 * dd[i];
-  }
-  tn[N + 1] = fdiv(dd[N + 1], b);
-  for (int i = N; i >= 2; --i) tn[i] = dd[i] - cc[i] * tn[i + 1];
-  for (int xx = 2; xx <= N + 1; ++xx) {
-    const double xmn = dmin(dmin(tcv[xx], tcv[xx - 1]), tcv[xx + 1]);
-    const double xmx = dmax(dmax(tcv[xx], tcv[xx - 1]), tcv[xx + 1]);
-    double v = tn[xx];
-    if (v < xmn) v = xmn;
-    if (v > xmx) v = xmx;
-    tn[xx] = v + f * Xv[xx - 1];
-  }
 }
 
 // Scratch map of the solves (indices into Mem::scr_*; the C stages later overwrite rows 0, 1, 27, 28 only):
@@ -898,7 +852,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
   }
   MC_TICK(3);
   // ======================= heat and vapour exchange on the merged nodes (code.R:813-867) =======================
-  // Solver storage: coefficients in the block's idle stage buffers, elimination factors in tensor memory; ONE Thomas call site
+  // Solver storage: coefficients in the block's idle stage buffers, replaced in place by the elimination factors; ONE Thomas call site
   // per solve for both branches (equilibrium = no merged air node), so warps with mixed lanes do not run the solves twice.
   int nn = 2, mgx = 0;
   double TX, y1t = 0, y2t = 0, y1e = 0, y2e = 0, tns1_raw = 0, tsel_raw = 0;
