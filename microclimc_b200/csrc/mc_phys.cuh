@@ -247,19 +247,20 @@ MC_HD double gturb(double u, double zu, double z1, double z0, double hgt, double
 MC_HD double gforcedfree(double d, double u, double tc, double dtc, double pk, double dtmin) {
   double Tk = tc + 273.15;
   double ph = phair(tc, pk);
-  double sc = pow175(Tk / 273.15) * (101.3 / pk);
+  double sc = pow175(Tk * (1 / 273.15)) * fdiv(101.3, pk);
   double Dh = 18.9e-6 * sc;
   double nu = 13.3e-6 * sc;
   double adt = fabs(dtc);
   if (adt < dtmin) adt = dtmin;
-  double Re = (u * d) / nu;
-  double Pr = nu / Dh;
-  double Gr = (9.81 * (d * d * d) * adt) / (Tk * (nu * nu));
-  double gforced = (0.664 * Dh * ph * sqrt(Re) * cbrt(Pr)) / d;
-  double gfree = (0.54 * Dh * ph * qroot(Gr * Pr)) / d;
+  const double id = frcp(d);
+  double Re = fdiv(u * d, nu);
+  double Pr = fdiv(nu, Dh);
+  double Gr = fdiv(9.81 * (d * d * d) * adt, Tk * (nu * nu));
+  double gforced = (0.664 * Dh * ph * fsqrt(Re) * cbrt(Pr)) * id;
+  double gfree = (0.54 * Dh * ph * qroot(Gr * Pr)) * id;
   return (gforced > gfree) ? gforced : gfree;
 }
-MC_HD double layercond(double Rsw, double gsmax, double q50) { double Qa = 4.6 * Rsw; return (gsmax * Qa) / (Qa + q50); }
+MC_HD double layercond(double Rsw, double gsmax, double q50) { double Qa = 4.6 * Rsw; return fdiv(gsmax * Qa, Qa + q50); }
 MC_HD double soilrh(double theta, double b, double Psie, double Smax, double tc) {
 #if defined(__CUDA_ARCH__)
   double matric = -Psie * fexp(-b * flog(fdiv(theta, Smax)));          // (theta / Smax)^-b

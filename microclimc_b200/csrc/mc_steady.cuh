@@ -135,8 +135,8 @@ struct SteadyCol {
     else { double l2 = log((h - dd) / zmm); if (l2 < 0.55) l2 = 0.55; fB = l2; fE = exp(av * (zo / h) - 1); }   // Q14
   }
   MC_HD static double wind_apply(double ui, double fA, double fB, double fE) {
-    double uf = (0.4 * ui) / fA;
-    double uo = (uf / 0.4) * fB;
+    double uf = fdiv(0.4 * ui, fA);
+    double uo = fdiv(uf, 0.4) * fB;
     return fE < 0 ? uo : uo * fE;
   }
   MC_HD static void gturb_factors(double zu, double z1, double z0, double dd, double zmm, double& lnu, double& lnh) {
@@ -147,13 +147,13 @@ struct SteadyCol {
   }
   MC_HD static double gturb_apply(double u, double lnu, double lnh, double ph, double psi_m, double psi_h) {
     double ln = lnu + psi_m; if (!(ln >= 0.55)) ln = 0.55;
-    double uf = (0.4 * u) / ln;
+    double uf = fdiv(0.4 * u, ln);
     double den = lnh + psi_h; if (den < 0.25 * lnh) den = 0.25 * lnh;
-    return (0.4 * ph * uf) / den;
+    return fdiv(0.4 * ph * uf, den);
   }
   // gcanopy with tc1 == tc0 (free-convection floor is exactly 0)
   MC_HD static double gcan_apply(double lmix, double iw, double ph, double uh, double av, double den) {
-    double g = (lmix * iw * ph * uh * av) / (den * 1.0);
+    double g = fdiv(lmix * iw * ph * uh * av, den * 1.0);
     return (g > 0.0) ? g : 0.0;
   }
   // .leafabs2 (NMR.R:361-376) with merid <- clump (Q15), clump = 0
@@ -168,35 +168,39 @@ struct SteadyCol {
     double lwin = trlwu * skyem * lwout + (1 - trlwu) * emvv * lwout;
     return aRsw + emvv * lwin;
   }
+  // 1 / (1/a + 1/b) as a*b / (a+b): one division; a == 0 (closed stomata at night) still gives 0 as the IEEE form does
+  MC_HD static double hpar(double a, double b) { return fdiv(a * b, a + b); }
   // tleafS (NMR.R:432-493)
   MC_HD static void tleafS(double tair, double tground, double relhum, double pk, double theta, double gtt, double gt0, double gha,
                            double gv, double gL, double Rabs, double vegemv, double soilbv, double Psie, double Smaxv, double surfwet,
                            double leafd, double& tleaf, double& tn, double& rh) {
     double cp = cpair(tair);
     double gs = gtt + gt0;
-    double aL = (gtt * (tair + 273.15) + gt0 * (tground + 273.15)) / gs;
-    double bL = (leafd * gL) / gs;
+    const double igs = frcp(gs);
+    double aL = (gtt * (tair + 273.15) + gt0 * (tground + 273.15)) * igs;
+    double bL = (leafd * gL) * igs;
     double es = satvap(tair);
-    double eref = (relhum / 100) * es;
+    double eref = fdiv(relhum, 100) * es;
     double esoil = soilrh(theta, soilbv, Psie, Smaxv, tground) * satvap(tground);
     double tk = tair + 273.15;
     double Rnet = Rabs - 0.97 * kSb * pow4(tk);
-    double tle = tair + (0.5 * Rnet) / (cp * gha);
-    double wgt1 = leafd < 1 ? leafd / 2 : 1 - 0.5 / leafd;
+    double tle = tair + fdiv(0.5 * Rnet, cp * gha);
+    double wgt1 = leafd < 1 ? leafd / 2 : 1 - fdiv(0.5, leafd);
     double tapprox = wgt1 * tle + (1 - wgt1) * tair;
-    double delta = 4098 * tetens(tapprox) / sq(tapprox + 237.3);
+    double delta = fdiv(4098 * tetens(tapprox), sq(tapprox + 237.3));
     double g3 = gs + gv;
-    double ae = (gtt * eref + gt0 * esoil + gv * es) / g3;
-    double be = (gv * delta) / g3;
+    const double ig3 = frcp(g3);
+    double ae = (gtt * eref + gt0 * esoil + gv * es) * ig3;
+    double be = (gv * delta) * ig3;
     double bH = gha * cp;
-    double lg = ((-42.575 * tair + 44994) * gv) / pk;
+    double lg = fdiv((-42.575 * tair + 44994) * gv, pk);
     double aX = lg * (surfwet * es - ae);
     double bX = lg * (surfwet * delta - be);
     if (aX < 0) aX = 0;
     if (bX < 0) bX = 0;
     double aR = kSb * vegemv * pow4(aL);
     double bR = 4 * vegemv * kSb * ((aL * aL * aL) * bL + (tk * tk * tk));
-    double dTL = (Rabs - aR - aX) / (1 + bR + bX + bH);
+    double dTL = fdiv(Rabs - aR - aX, 1 + bR + bX + bH);
     tn = aL - 273.15 + bL * dTL;
     tleaf = tn + dTL;
     double eanew = ae + be * dTL;
@@ -204,7 +208,7 @@ struct SteadyCol {
     double tmin = dewpoint(eanew, tn);
     double esnew = satvap(tn);
     if (eanew > esnew) eanew = esnew;
-    rh = (eanew / esnew) * 100;
+    rh = fdiv(eanew, esnew) * 100;
     if (tleaf < tmin) tleaf = tmin;
     if (tn < tmin) tn = tmin;
     double tmax = (tn + 20 < 80) ? tn + 20 : 80;
@@ -219,8 +223,8 @@ struct SteadyCol {
   MC_HD double wind2m(const SteadyArgs& A, double u, double PAIv) const {
     double u2;
     if (A.metopen) {
-      if (A.windhgt != 2) u = u * 4.87 / log(67.8 * A.windhgt - 5.42);
-      u2 = u * La / log(67.8 * 2 - 5.42);
+      if (A.windhgt != 2) u = fdiv(u * 4.87, flog(67.8 * A.windhgt - 5.42));
+      u2 = fdiv(u * La, log(67.8 * 2 - 5.42));
     } else {
       u2 = u;
       if (A.windhgt != (2 + hgt)) u2 = Column<3, 2>::windprofile(u, A.windhgt, hgt + 2, 2, PAIv, hgt, 0, 0.05 * hgt, 0.004);
@@ -234,7 +238,7 @@ struct SteadyCol {
     const double reqhgt = A.reqhgt;
     const double tair = cr[0], relhum = cr[1], pk = cr[2], swrad = cr[4], skyem = cr[6];
     const double u2 = wind2m(A, cr[3], PAIt);
-    const double uf = (0.4 * u2) / lnuf;
+    const double uf = fdiv(0.4 * u2, lnuf);
     const double tk = tair + 273.15;
     double Rlw = (1 - skyem) * kSb * vegem * pow4(tk);
     const double Hh = 0.2 * ((1 - 0.23) * swrad - Rlw);
@@ -245,26 +249,24 @@ struct SteadyCol {
     if (psi_m < -2.5) psi_m = -2.5;
     if (psi_h < -2.5) psi_h = -2.5;
     const double uz = wind_apply(u2, wA, wB, wE);
-    const double uh = (uf / 0.4) * lnh3;
+    const double uh = fdiv(uf, 0.4) * lnh3;
     double dp = cr[5] / swrad;
     if (dp != dp) dp = 0.5;
     if (isinf(dp)) dp = 0.5;
     if (dp > 1) dp = 1;
     const double ph = phair(tair, pk);
     double gtt = gturb_apply(u2, gt_lnu, gt_lnh, ph, psi_m, psi_h);
-    const double pl = LAI / PAIt;
     const double sa_l = solalt(cr[8], lat, lon, cr[7], /*merid <- clump (Q15)*/ clump, 0);
     const double K_l = (sa_l > 0) ? cank(x, sa_l, kden) : 0.0;
     const double mul = cank(x, sa_l < 5 ? 5.0 : sa_l, kden);
     const double ph0 = phair(tair, 101.3);
     double tz, tleaf, rh, Rsw;
-    (void)pl;
     if (reqhgt >= hgt) {
       double gt0 = gcan_apply(l_m, iwmean, ph, uh, a, gc_top_den);
       double gha = 1.41 * gforcedfree(lw * 0.71, uh, tair, 5, pk, 5);
       double gC = layercond(swrad, gsmax, q50);
-      double gv = 1 / (1 / gC + 1 / gha);
-      double gL = 1 / (1 / gha + 1 / (ph0 * uh));
+      double gv = hpar(gC, gha);
+      double gL = hpar(gha, ph0 * uh);
       double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt, 0.0, ref, sref, 1.0, trd_t, refg, emv, 1.0, skyem, dp);
       double tn, rhn;
       tleafS(tair, tground, relhum, pk, theta, gtt, gt0, gha, gv, gL, Rabs, vegem, soilb, psi_e, Smax, A.surfwet, leafdens, tleaf, tn, rhn);
@@ -272,25 +274,25 @@ struct SteadyCol {
       else {
         double gtc = gturb_apply(u2, gt_lnu, gtc_lnh, ph, psi_m, psi_h);
         double gt2 = 1 / (1 / gtt - 1 / gtc);
-        double eref = (relhum / 100) * satvap(tair);
-        double ecan = (rhn / 100) * satvap(tn);
-        double ea = (gt2 * eref + gtc * ecan) / (gt2 + gtc);
+        double eref = fdiv(relhum, 100) * satvap(tair);
+        double ecan = fdiv(rhn, 100) * satvap(tn);
+        double ea = (gt2 * eref + gtc * ecan) / (gt2 + gtc);          // (gt2 may be +-Inf when gtt == gtc: IEEE division kept)
         tz = (gt2 * tair + gtc * tn) / (gt2 + gtc);
-        rh = (ea / satvap(tz)) * 100;
+        rh = fdiv(ea, satvap(tz)) * 100;
       }
       if (rh > 100) rh = 100;
       Rsw = swrad;
     } else {
       double gtc = gcan_apply(l_m, iwmean, ph, uh, a, gc_c_den);
-      gtt = 1 / (1 / gtt + 1 / gtc);
+      gtt = hpar(gtt, gtc);
       double gt0 = gcan_apply(l_m, iwmean, ph, uh, a, gc_0_den);
       double gha = 1.41 * gforcedfree(lw * 0.71, uz, tair, 5, pk, 5);
       double sa = solalt(cr[8], lat, lon, cr[7], merid_def, 0);
       double K = (sa > 0) ? cank(x, sa, kden) : 0.0;
       double PAR = cansw_k(swrad, dp, sa, PAIu, s02, trd02, K, 0.0);
       double gC = layercond(PAR, gsmax, q50);
-      double gv = 1 / (1 / gC + 1 / gha);
-      double gL = 1 / (1 / gha + 1 / (ph0 * uz));
+      double gv = hpar(gC, gha);
+      double gL = hpar(gha, ph0 * uz);
       double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt, PAIu, ref, sref, trd_u, trd_t, refg, emv, trlw_u, skyem, dp);
       tleafS(tair, tground, relhum, pk, theta, gtt, gt0, gha, gv, gL, Rabs, vegem, soilb, psi_e, Smax, A.surfwet, leafdens, tleaf, tz, rh);
       Rsw = cansw_k(swrad, dp, sa, PAIu, sls, trdls, K, 0.0);
@@ -300,7 +302,7 @@ struct SteadyCol {
       if (isinf(dp)) dp = 1;
       if (dp < 0) dp = 0;
       if (dp > 1) dp = 1;
-      double tr = clumptr(exp(-slw * PAIu), clump);
+      double tr = clumptr(fexp(-slw * PAIu), clump);
       double lwout = kSb * pow4(tk);
       Rlw = tr * skyem * lwout + (1 - tr) * emv * lwout;
     }
@@ -336,13 +338,13 @@ struct SteadyCol {
     double uz;
     if (above) uz = wind_apply(u2, wA1, wB1, wE1);
     else {
-      double l = log((snowdep + 2 - 0.0) / 0.004); if (l < 0.55) l = 0.55;
+      double l = flog(fdiv(snowdep + 2 - 0.0, 0.004)); if (l < 0.55) l = 0.55;
       uz = wind_apply(u2, l, wB2, -1.0);
     }
-    double uf = (0.4 * u2) / log((hgt2 + 2 - dd) / zm);
+    double uf = fdiv(0.4 * u2, flog(fdiv(hgt2 + 2 - dd, zm)));
     if (uf < 0.065) uf = 0.065;
     hgt2 = hgt < snowdep ? snowdep : hgt;
-    double uh = (uf / 0.4) * log((hgt2 - dd) / zm);
+    double uh = fdiv(uf, 0.4) * flog(fdiv(hgt2 - dd, zm));
     if (uh < uf) uh = uf;
     const bool below = reqhgt < snowdep;
     double tz2 = 0;
@@ -363,8 +365,8 @@ struct SteadyCol {
       double gt0 = gcan_apply(l_m_s, iwmean, ph, uh, a1, gcs_top_den);
       double gha = 1.41 * gforcedfree(lw * 2 * 0.71, uh, tair, 5, pk, 5);
       double gC = layercond(swrad, gsmax, q50);
-      double gv = 1 / (1 / gC + 1 / gha);
-      double gL = 1 / (1 / gha + 1 / (ph0 * uh));
+      double gv = hpar(gC, gha);
+      double gL = hpar(gha, ph0 * uh);
       double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt_s, 0.0, ref_s, sref_s, 1.0, trds_t, 0.95, emv85, 1.0, skyem, dp);
       double tn, rhn;
       tleafS(tair, snowtemp, relhum, pk, 0.5, gtt, gt0, gha, gv, gL, Rabs, 0.85, soilb, psi_e, Smax, 1, leafdens_s, tleaf, tn, rhn);
@@ -372,27 +374,27 @@ struct SteadyCol {
       else {
         double gtc = gturb_apply(u2, gts_lnu, gtcs_lnh, ph, 0, 0);
         double gt2 = 1 / (1 / gtt - 1 / gtc);
-        double eref = (relhum / 100) * satvap(tair);
-        double ecan = (rhn / 100) * satvap(tn);
-        double ea = (gt2 * eref + gtc * ecan) / (gt2 + gtc);
+        double eref = fdiv(relhum, 100) * satvap(tair);
+        double ecan = fdiv(rhn, 100) * satvap(tn);
+        double ea = (gt2 * eref + gtc * ecan) / (gt2 + gtc);          // (gt2 may be +-Inf when gtt == gtc: IEEE division kept)
         tz = (gt2 * tair + gtc * tn) / (gt2 + gtc);
-        rh = (ea / satvap(tz)) * 100;
+        rh = fdiv(ea, satvap(tz)) * 100;
       }
       if (rh > 100) rh = 100;
       Rsw = swrad;
       Rlw = (1 - skyem) * 0.85 * kSb * pow4(tz + 273.15);
     } else {
       double gtc = gcan_apply(l_m_s, iwmean, ph, uh, a1, gcs_c_den);
-      gtt = 1 / (1 / gtt + 1 / gtc);
+      gtt = hpar(gtt, gtc);
       double gt0 = gcan_apply(l_m_s, iwmean, ph, uh, a1, gcs_0_den);
       double gha = 1.41 * gforcedfree(lw * 0.71 * 2, uz, tair, 5, pk, 5);
       double sa = solalt(cr[8], lat, lon, cr[7], merid_def, 0);
       double K = (sa > 0) ? cank(x, sa, kden) : 0.0;
       double PAR = cansw_k(swrad, dp, sa, PAIu, s06, trd06, K, 0.0);
       double gC = layercond(PAR, gsmax, q50);
-      double gv = 1 / (1 / gC + 1 / gha);
-      double gL = 1 / (1 / gha + 1 / (ph0 * uz));
-      double trlw = clumptr(exp(-sqrt(emv85) * PAIu), 0.0);
+      double gv = hpar(gC, gha);
+      double gL = hpar(gha, ph0 * uz);
+      double trlw = clumptr(fexp(-fsqrt(emv85) * PAIu), 0.0);
       double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt_s, PAIu, ref_s, sref_s, trds_u, trds_t, 0.95, emv85, trlw, skyem, dp);
       tleafS(tair, snowtemp, relhum, pk, 0.5, gtt, gt0, gha, gv, gL, Rabs, vegem, soilb, psi_e, Smax, 1, leafdens_s, tleaf, tz, rh);
       Rsw = cansw_k(swrad, dp, sa, PAIu, s95, trd95, K, 0.0);
