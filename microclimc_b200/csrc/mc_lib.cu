@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kBlock) k_paraminit(long long ncol, int m, int
   if (c < ncol) paraminit_column<MM, MS>(ncol, m, sm, args, state, c);
 }
 template <int MM>
-__global__ void __launch_bounds__(kBlock) k_steady(SteadyArgs a) {
+__global__ void __launch_bounds__(kBlock, 5) k_steady(SteadyArgs a) {
   exp_tab_init();
   long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   if (c < a.ncol) steady_column<MM>(a, c, blockIdx.y, gridDim.y);
