@@ -1,0 +1,169 @@
+"""GPU parity over the run-description arguments of runmodel / runmodelS (code.R:1125-1129, NMR.R:717-718) and over
+vegetation / soil / site variants: every switch that selects a different branch of the step is driven once through the
+CUDA path (C-ABI) and compared with the CPU oracle.  Tolerances as everywhere: 1e-6 K / 1e-8 relative."""
+import numpy as np
+import pytest
+
+from tests.common import M, SM, make_cfg, assert_state_close, assert_series_close, loam
+from microclimc_b200 import layout as L, synth as S
+
+pytestmark = pytest.mark.gpu
+
+NCOL, T = 40, 96
+# Short spin-up on purpose: with the forcing frozen (spinup, code.R:982-1013) some run descriptions (no edge term, n = 0.5, ...)
+# put the reference's step into a period-3 oscillation in which rounding-level differences double every step (1e-12 after 25
+# steps, 1e-7 after 60: DESIGN.md section 2, "sensitivity") — any two evaluation orders, R's included, drift apart there.  Twenty
+# steps exercise the spin-up code without giving that growth time; the hourly run that follows is contracting.
+SPIN = 20
+
+
+def _soil(oracle, name):
+    sp = S.load_soilparams(); i = sp["Soil.type"].index(name)
+    soil = {k: sp[k][i] for k in L.SOIL_SCALARS}
+    soil["z"] = oracle.soilinit_z()
+    return soil
+
+
+def _inputs(oracle, vegp=None, soil="Loam", lat=50.0, lon=-5.0, t0=4000, dp=None, theta=None, seed=11):
+    vegp = S.vegp_deciduous() if vegp is None else vegp
+    veg, so = S.ensemble(vegp, _soil(oracle, soil), NCOL, M, SM, seed=seed)
+    f, ts = S.forcing_from_climdata(S.load_weather())
+    f = np.ascontiguousarray(f[t0:t0 + T])
+    if dp is not None:                                   # diffuse proportion given instead of derived (code.R:701, leafabs dp)
+        f[:, L.FORCING.index("dp")] = dp
+    if theta is not None:                                # time-varying soil moisture (code.R:1200-1202)
+        f[:, L.FORCING.index("theta")] = theta
+    fs, fo = S.forcing_perturbation(NCOL, seed=seed + 1)
+    return dict(veg=veg, soil=so, f=f, lat=np.full(NCOL, lat), lon=np.full(NCOL, lon), fs=fs, fo=fo)
+
+
+def _run_both(oracle, inp, cfg):
+    from microclimc_b200._lib import Context
+    want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"])
+    ctx = Context(M, SM)
+    ctx.set_columns(inp["veg"], inp["soil"], inp["lat"], inp["lon"]); ctx.set_forcing(inp["f"], inp["fs"], inp["fo"]); ctx.set_config(cfg)
+    got = ctx.run_transient(samp_idx=np.arange(NCOL))
+    return got, ctx.get_state(), want
+
+
+CFG_VARIANTS = {
+    "no_edge": dict(edgedist=np.nan),
+    "near_edge": dict(edgedist=8.0),
+    "met_station_above_canopy": dict(metopen=0, windhgt=19.0),
+    "open_station_10m": dict(metopen=1, windhgt=10.0),
+    "dry_surface": dict(surfwet=0.3),
+    "leaf_area_height_factor": dict(zlafact=1.6),
+    "crank_nicolson": dict(n=0.5),
+    "fully_implicit": dict(n=1.0),
+    "wind_ref_height_5m": dict(zu=5.0),
+    "meridian_and_dst": dict(merid=15.0, dst=1.0),
+    "output_at_node_height": dict(reqhgt=3.0),
+    "ten_minute_steps": dict(timestep=600.0),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CFG_VARIANTS))
+def test_run_description_variants(oracle, name):
+    kw = dict(spin_steps=SPIN); kw.update(CFG_VARIANTS[name])
+    cfg = make_cfg(**kw)
+    inp = _inputs(oracle)
+    got, st, want = _run_both(oracle, inp, cfg)
+    assert_series_close(got["series"], want["series"], name)
+    assert_state_close(st, want["state"], what=name)
+    assert np.array_equal(got["flags"] & 1, want["flags"] & 1)
+
+
+def test_negative_reqhgt_quirk_is_reproduced(oracle):
+    """Quirk Q18 (code.R:719, reached through code.R:1199-1202): a negative `reqhgt` moves the lowest canopy node below the
+    ground, so parts of the profile turn NaN and the rest follows a rounding-sensitive trajectory.  The CUDA path has to show the
+    same NaN pattern and stay on the same trajectory in the median (single columns drift by more than the parity tolerance there)."""
+    inp = _inputs(oracle)
+    got, st, want = _run_both(oracle, inp, make_cfg(spin_steps=SPIN, reqhgt=-0.1))
+    assert np.array_equal(np.isnan(got["series"]), np.isnan(want["series"]))
+    assert np.array_equal(np.isnan(st), np.isnan(want["state"]))
+    assert np.array_equal(got["flags"] & 1, want["flags"] & 1)
+    assert np.nanmedian(np.abs(got["series"][:, :2] - want["series"][:, :2])) < 1e-6
+
+
+def _grass():
+    v = S.vegp_deciduous(hgt=0.4, PAIt=1.5)
+    v.update(x=0.4, lw=0.01, gsmax=0.4, hgtg=0.02)
+    return v
+
+
+def _conifer():
+    v = S.vegp_deciduous(hgt=28.0, PAIt=6.5)
+    v.update(x=0.6, lw=0.002, clump=0.3, refls=0.25)
+    return v
+
+
+SITE_VARIANTS = {
+    "sand": dict(soil="Sand"),
+    "clay": dict(soil="Clay"),
+    "short_grass_general_path": dict(vegp=_grass),            # nodes below 0.12 m: every step goes through Column::step
+    "tall_clumped_conifer": dict(vegp=_conifer),
+    "southern_hemisphere_summer": dict(lat=-33.9, lon=151.2, t0=200),
+    "arctic_winter_no_sun": dict(lat=69.0, lon=18.0, t0=100),
+    "midwinter_night_frost": dict(t0=300),
+    "diffuse_fraction_given": dict(dp=0.45),
+    "soil_moisture_series": dict(theta=0.15 + 0.2 * np.abs(np.sin(np.arange(T) / 9.0))),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SITE_VARIANTS))
+def test_vegetation_soil_site_variants(oracle, name):
+    kw = dict(SITE_VARIANTS[name])
+    if callable(kw.get("vegp")):
+        kw["vegp"] = kw["vegp"]()
+    inp = _inputs(oracle, **kw)
+    got, st, want = _run_both(oracle, inp, make_cfg(spin_steps=SPIN))
+    assert np.all(np.isfinite(want["series"][:, :2]))
+    assert_series_close(got["series"], want["series"], name)
+    assert_state_close(st, want["state"], what=name)
+
+
+def test_zero_pai_layers_are_floored(oracle):
+    """code.R:694-697: zero plant area in a layer is raised to 0.0001 before the step."""
+    inp = _inputs(oracle)
+    r = L.veg_rows(M)["PAI"]
+    inp["veg"][r][:3, ::2] = 0.0
+    got, st, want = _run_both(oracle, inp, make_cfg(spin_steps=SPIN))
+    assert_series_close(got["series"], want["series"], "zero PAI")
+    assert_state_close(st, want["state"], what="zero PAI")
+
+
+STEADY_VARIANTS = {
+    "default": dict(),
+    "below_canopy_low": dict(reqhgt=0.1),
+    "above_canopy": dict(reqhgt=17.0),
+    "met_station_above_canopy": dict(metopen=0.0, windhgt=19.0),
+    "dry_surface_low_emissivity": dict(surfwet=0.2, groundem=0.9),
+}
+
+
+@pytest.mark.parametrize("name", sorted(STEADY_VARIANTS))
+@pytest.mark.parametrize("snow", [False, True])
+def test_steady_variants(oracle, name, snow):
+    from microclimc_b200._lib import Context
+    kw = dict(reqhgt=1.0, metopen=1.0, windhgt=2.0, surfwet=1.0, groundem=0.95); kw.update(STEADY_VARIANTS[name])
+    scfg = np.array([kw[k] for k in L.STEADY_CFG], float)
+    veg, so = S.ensemble(S.vegp_deciduous(), loam(oracle), NCOL, M, SM, seed=5)
+    w = S.load_weather()
+    clim = S.steady_clim_from_climdata(w)[:240]
+    rng = np.random.default_rng(2)
+    nmr = np.zeros((240, 11)); nmr[:, 0] = clim[:, 0] + rng.normal(0, 1.5, 240); nmr[:, 1] = rng.uniform(0.1, 0.4, 240)
+    if snow:
+        nmr[:, 2] = np.where(clim[:, 0] < 6, rng.uniform(1, 250, 240), 0.0)       # cm; some hours bury the output height
+        nmr[:, 3:] = rng.uniform(-9, 0, (240, 8))
+    lat = np.full(NCOL, 50.0); lon = np.full(NCOL, -5.0)
+    want = oracle.run_steady(veg, so, clim, nmr, lat, lon, scfg, M, SM)["out"]
+    ctx = Context(M, SM)
+    ctx.set_columns(veg, so, lat, lon)
+    got = ctx.run_steady(clim, nmr, scfg)["out"]
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    g = np.nan_to_num(got); w_ = np.nan_to_num(want)
+    for k, nm_ in enumerate(L.STEADY_OUT):
+        if nm_ in ("Tloc", "tleaf", "dp"):
+            assert np.max(np.abs(g[:, k] - w_[:, k])) <= 1e-6, (name, nm_)
+        else:
+            assert np.max(np.abs(g[:, k] - w_[:, k]) / np.maximum(np.abs(w_[:, k]), 1.0 if nm_ != "windspeed" else 1e-3)) <= 1e-8, (name, nm_)
