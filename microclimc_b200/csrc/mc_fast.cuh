@@ -39,11 +39,11 @@ enum { PB_REF, PB_PC, PB_SPC, PB_SGC, PB_TRDC, PB_TRDG, PB_TRLW, PB_PAI, PB_IZTH
        PB_VDEN, PB_DZ, PB_N };
 enum { S0_TABOVE, S0_RELHUM, S0_TAIR, S0_TSOIL, S0_PK, S0_H, S0_PSIM, S0_G, S0_TCSUM, S0_GTCAP, S0_N };   // then soiltc[sm]
 enum { SL_TC, SL_TLEAF, SL_RH, SL_RABS, SL_GV, SL_GHA, SL_N };
-enum { WL_GTN, WL_UZN, WL_PHZ, WL_TT, WL_EAL, WL_L, WL_RSWIN, WL_RLWIN, WL_N };
-constexpr int kWLiveB = 3;                        // W rows sweep B reads back from sweep A (GTN, UZN, PHZ)
+enum { WL_GTN, WL_UZN, WL_TT, WL_EAL, WL_L, WL_RSWIN, WL_RLWIN, WL_N };
+constexpr int kWLiveB = 2;                        // W rows sweep B reads back from sweep A (GTN, UZN)
 constexpr int kWLiveC = 2;                        // W rows sweep C reads back from sweep B (TT, EAL)
 constexpr int kCL = 5;                            // layers per sweep-C stage (their TT/EAL rows are contiguous: 10 rows)
-constexpr int kStageRowsB = PB_N + SL_N + kWLiveB + 1;   // sweep-B stage: geometry, state, work rows and the old gt row = 26 rows
+constexpr int kStageRowsB = PB_N + SL_N + kWLiveB + 1;   // sweep-B stage: geometry, state, work rows and the old gt row = 25 rows
 constexpr int kStageRows = 27;                    // rows of 128 doubles per stage buffer (the solver scratch needs 2 x 27)
 static_assert(kStageRowsB <= kStageRows, "sweep-B stage exceeds the stage buffer");
 constexpr int kNG = 6;                            // merged air layers handled in the streaming form (more: general path)
@@ -60,7 +60,7 @@ struct FastLayout {
   MC_HD int uz(int i) const { return S0_N + sm + m * SL_N + (i - 1); }
   MC_HD int gt(int i) const { return S0_N + sm + m * SL_N + m + (i - 1); }          // i = 1..m+1
   MC_HD int nS() const { return S0_N + sm + m * SL_N + m + (m + 1); }
-  // per-layer blocks of 6 rows (GTN, UZN, PHZ, L, RSWIN, RLWIN), then the sweep-C rows (TT, EAL) of all layers contiguously
+  // per-layer blocks of 5 rows (GTN, UZN, L, RSWIN, RLWIN), then the sweep-C rows (TT, EAL) of all layers contiguously
   MC_HD int wl(int i, int r) const {
     return (r == WL_TT || r == WL_EAL) ? m * (WL_N - 2) + (i - 1) * 2 + (r - WL_TT) : (i - 1) * (WL_N - 2) + (r < WL_TT ? r : r - 2);
   }
@@ -172,6 +172,10 @@ struct DirectMem {
   MC_HD double scr_get(int idx) const { return scratch[idx]; }
   MC_HD void scr_put(int idx, double v) { scratch[idx] = v; }
   MC_HD int warp_max(int v) const { return v; }
+  MC_HD void st_stream(double* p, double v) const { *p = v; }
+  MC_HD void st_keep(double* p, double v) const { *p = v; }
+  MC_HD void discard_AB() {}
+  MC_HD void discard_C() {}
   MC_HD void step_begin() {}
   MC_HD void sweepB_begin() {}
   MC_HD void sweepC_begin() {}
@@ -227,6 +231,21 @@ MC_D void bulk_g2s_stream(unsigned dst32, const void* src, unsigned bytes, unsig
                : "memory");
 }
 MC_D void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Work rows W are written in one sweep and read back once, half a step later, by the same CTA: keep them in L2 (evict-last) and drop
+// the dead lines after the read (discard.global.L2: no write-back of a dirty line nobody will read again).  MC_L2HINT: 0 none,
+// 1 hints only, 2 hints + discard.
+#ifndef MC_L2HINT
+#define MC_L2HINT 2
+#endif
+MC_D unsigned long long l2_evict_last_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+MC_D void st_hint(double* p, double v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+MC_D void discard_line(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
 
 struct PipeMem {
   const double* P; double* S; double* W;      // lane-adjusted tile bases (for stores and the few direct reads)
@@ -240,6 +259,31 @@ struct PipeMem {
   const double* cur;                           // current stage buffer + lane
   const double* cbase;                         // sweep C: start of the current group's rows
   unsigned long long pol;                      // L2 evict-first policy for the streamed rows
+  unsigned long long pol_keep;                 // L2 evict-last policy for the work rows
+#if MC_L2HINT
+  MC_D void st_stream(double* p, double v) const { st_hint(p, v, pol); }
+  MC_D void st_keep(double* p, double v) const { st_hint(p, v, pol_keep); }
+#else
+  MC_D void st_stream(double* p, double v) const { *p = v; }
+  MC_D void st_keep(double* p, double v) const { *p = v; }
+#endif
+  // all lines of the A->B rows (GTN, UZN of every layer) / of the B->C rows (TT, EAL, contiguous) of this tile
+  MC_D void discard_AB() {
+#if MC_L2HINT >= 2
+    const int nl = L.m * 2 * (kTile * 8 / 128);                        // 2 rows per layer, 8 lines per row
+    for (int q = lane; q < nl; q += kTile) {
+      const int i = q / 16, r = q % 16;                                // layer, line within its two (adjacent) rows
+      discard_line(reinterpret_cast<const char*>(Wt + (long long)L.wl(i + 1, WL_GTN) * kTile) + r * 128);
+    }
+#endif
+  }
+  MC_D void discard_C() {
+#if MC_L2HINT >= 2
+    const int nl = L.m * kWLiveC * (kTile * 8 / 128);
+    const char* base = reinterpret_cast<const char*>(Wt + (long long)L.wl(1, WL_TT) * kTile);
+    for (int q = lane; q < nl; q += kTile) discard_line(base + q * 128);
+#endif
+  }
   // Tensor memory as a per-thread scratchpad: the CTA owns 128 columns x 128 lanes x 32 bit, i.e. 64 doubles per thread
   // (thread t of warp w <-> lane 32*(w%4) + t%32).  Step scalars that are only needed once per layer are parked there instead
   // of being spilled to local memory (12-cycle LDTM vs an L2 round trip).  All 32 lanes must execute these together.
@@ -287,7 +331,11 @@ struct PipeMem {
     mbar_expect_tx(mb, kStageRowsB * kTile * 8);
     bulk_g2s_stream(b, Pt + (long long)L.pb(i, 0) * kTile, PB_N * kTile * 8, mb, pol);
     bulk_g2s_stream(b + PB_N * kTile * 8, St + (long long)L.sl(i, 0) * kTile, SL_N * kTile * 8, mb, pol);
+#if MC_L2HINT
+    bulk_g2s_stream(b + (PB_N + SL_N) * kTile * 8, Wt + (long long)L.wl(i, 0) * kTile, kWLiveB * kTile * 8, mb, pol_keep);
+#else
     bulk_g2s(b + (PB_N + SL_N) * kTile * 8, Wt + (long long)L.wl(i, 0) * kTile, kWLiveB * kTile * 8, mb);
+#endif
     bulk_g2s_stream(b + (PB_N + SL_N + kWLiveB) * kTile * 8, St + (long long)L.gt(i) * kTile, kTile * 8, mb, pol);
   }
   MC_D void issueC(int i, unsigned kk) {                  // rows of layers i .. i+kCL-1 (or up to m)
@@ -295,7 +343,11 @@ struct PipeMem {
     const unsigned mb = bar32 + (kk & 1) * 8;
     const int nl = (L.m - i + 1 < kCL) ? (L.m - i + 1) : kCL;
     mbar_expect_tx(mb, nl * kWLiveC * kTile * 8);
+#if MC_L2HINT
+    bulk_g2s_stream(b, Wt + (long long)L.wl(i, WL_TT) * kTile, nl * kWLiveC * kTile * 8, mb, pol_keep);
+#else
     bulk_g2s(b, Wt + (long long)L.wl(i, WL_TT) * kTile, nl * kWLiveC * kTile * 8, mb);
+#endif
   }
   // generic-proxy stores of the previous sweep -> visible to the async proxy, block-wide; then start the next sweep
   MC_D void step_begin() {
@@ -595,8 +647,8 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
       const double rg = frcp(0.5 * gtn + 0.5 * mem.a_gto());
       const double phz = phair_c(cppk, tcu) * mem.a_p(PA_DZ);
       double* Wl = W + (long long)L.wl(i, 0) * kTile;
-      Wl[WL_GTN * kTile] = gtn; Wl[WL_UZN * kTile] = uzn; Wl[WL_PHZ * kTile] = phz;
-      // rg and its sum above each layer are not handed to sweep B through memory: B recomputes rg from gtn and the old gt row
+      mem.st_keep(Wl + WL_GTN * kTile, gtn); mem.st_keep(Wl + WL_UZN * kTile, uzn);
+      // phz is rebuilt in sweep B from rows it stages anyway (old tc of the layer, dz); rg and its sum above each layer are not handed to sweep B through memory: B recomputes rg from gtn and the old gt row
       // and rebuilds the sum above layer i as (total - sum up to i)
       sfx += rg; Rtot += rn; Ctot += phz;
       if (i <= half) cs += rn;
@@ -819,7 +871,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
       }
       // layermerge (code.R:772) greedy grouping with the layeraverage sums (code.R:814) of the open group
       {
-        const double wi = mem.b_p(PB_DZ), phz = mem.b_w(WL_PHZ), rn = frcp(gtn);
+        const double wi = mem.b_p(PB_DZ), phz = phc * wi, rn = frcp(gtn);       // phair(previn$tc, previn$pk) * dz as in sweep A
         TT += phz * rn;                                                           // cumsum((ph/gt) * dz), code.R:797
         oR += rn; oC += phz; open = true;
         ow += wi; otc += wi * ptc; oVo += wi * (eaj * ku[KU_IPPK - KU_LAMBDA]); oea += wi * ean; oX += wi * (tnl - ptc); ovd += wi * mem.b_p(PB_VDEN);
@@ -833,13 +885,14 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
       }
       if (runB) {
         double* Sl = S + (long long)L.sl(i, 0) * kTile;
-        Sl[SL_TLEAF * kTile] = tleafn; Sl[SL_RABS * kTile] = Rabsn; Sl[SL_GV * kTile] = gvn; Sl[SL_GHA * kTile] = ghan;
+        mem.st_stream(Sl + SL_TLEAF * kTile, tleafn); mem.st_stream(Sl + SL_RABS * kTile, Rabsn); mem.st_stream(Sl + SL_GV * kTile, gvn);
+        mem.st_stream(Sl + SL_GHA * kTile, ghan);
         // previn$uz is only read at the lowest and highest node (code.R:731), so the other rows are written when the state is
         // harvested (emit) and not on every step
         if (emit || i == 1 || i == m) sput(L.uz(i), uzn);
-        sput(L.gt(i), gtn);
+        mem.st_stream(S + (long long)L.gt(i) * kTile, gtn);
       }
-      wput(i, WL_TT, TT); wput(i, WL_EAL, ean);
+      mem.st_keep(W + (long long)L.wl(i, WL_TT) * kTile, TT); mem.st_keep(W + (long long)L.wl(i, WL_EAL) * kTile, ean);
       if (emit || i == selHb) { wput(i, WL_L, Lp); wput(i, WL_RSWIN, rsw); }
       Lt += Lp; stl += tleafn; ssw += rsw;
     }
@@ -981,6 +1034,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
   mem.park(KT_TNS1, tns1_raw); mem.park(KT_TSEL, tsel_raw); mem.park_done();
   MC_TICK(4);
   mem.sweepC_begin();
+  mem.discard_AB();                                   // (after the barrier in sweepC_begin: every lane's solve has read its GTN rows)
   // ======================= sweep C: back to the m nodes, humidity, limits (code.R:846-874, 893-897) =======================
   double stc = 0, srh = 0, slw = 0, tnselG = 0;
   {
@@ -1025,12 +1079,13 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
       const double lwt = kSb * pow4(tn + 273.15);
       const double Rlwin = trlw_sum * skyem * lwt + (1 - trlw_sum) * emv * lwt;
       if (i == selG) tnselG = tnn;
-      if (runB) { S[(long long)L.sl(i, SL_TC) * kTile] = tn; S[(long long)L.sl(i, SL_RH) * kTile] = r; }
+      if (runB) { mem.st_stream(S + (long long)L.sl(i, SL_TC) * kTile, tn); mem.st_stream(S + (long long)L.sl(i, SL_RH) * kTile, r); }
       if (emit || i == selH) wput(i, WL_RLWIN, Rlwin);
       stc += tn; srh += r; slw += Rlwin;
     }
   }
   MC_TICK(5);
+  mem.discard_C();
   // ======================= soil limits and fluxes (code.R:868-891), output harvest (code.R:1222-1265) =======================
   double x0[8], x1[8];
   mem.unpark8(X_TAIRN, x0); mem.unpark8(X_PPK, x1);

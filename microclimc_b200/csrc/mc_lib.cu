@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kTile, 4) k_transient_fast(const __grid_consta
   mem.Pt = a.P + (long long)blockIdx.x * L.nP() * kTile; mem.St = a.S + (long long)blockIdx.x * L.nS() * kTile;
   mem.Wt = a.W + (long long)blockIdx.x * L.nW() * kTile;
   mem.P = mem.Pt + threadIdx.x; mem.S = const_cast<double*>(mem.St) + threadIdx.x; mem.W = const_cast<double*>(mem.Wt) + threadIdx.x;
-  mem.buf = buf; mem.bar = bar; mem.bar32 = smem_u32(bar); mem.buf32 = smem_u32(buf); mem.lane = threadIdx.x; mem.k = 0; mem.cur = buf; mem.pol = l2_evict_first_policy();
+  mem.buf = buf; mem.bar = bar; mem.bar32 = smem_u32(bar); mem.buf32 = smem_u32(buf); mem.lane = threadIdx.x; mem.k = 0; mem.cur = buf; mem.pol = l2_evict_first_policy(); mem.pol_keep = l2_evict_last_policy();
   mem.tbase = *tmem_base_s + ((unsigned)((threadIdx.x >> 5) * 32) << 16);
   for (int q = 0; q < 8; ++q) mem.tcyc[q] = 0;
   mem.tlast = clock64();
