@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--spin", type=int, default=200)
     ap.add_argument("--cpu-sample-cols", type=int, default=0, help="0 = auto (sized for ~10-20 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-steady", action="store_true", help="skip the extra steady-state (BASELINE config 2) measurement")
     return ap.parse_args()
 
 
@@ -298,6 +299,16 @@ def main():
             line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d columns x %d hourly steps x 2, OpenMP over columns; C++ restatement of the R path"
                                               % (ncs, hours)}
+        if not args.no_steady and world == 1:
+            # BASELINE config 2 beside the headline (not a bench line of its own): steady-state runmodelS, 10^4-column ensemble x the
+            # bundled year of hourly forcing, k_steady timed with CUDA events inside the library (tools/bench_steady.py)
+            try:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("bench_steady", os.path.join(ROOT, "tools", "bench_steady.py"))
+                bs = importlib.util.module_from_spec(spec); spec.loader.exec_module(bs)
+                line["other_workloads"] = {"C2_steady": bs.run("C2", 10_000, 8760, 0, False, 1.0, 3, gpu=local, quiet=True)}
+            except Exception as e:                                   # the headline must not depend on the side measurement
+                line["other_workloads"] = {"C2_steady": {"error": str(e)}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -112,6 +112,50 @@ def synthetic_forcing(T, seed=7, lat=50.0):
                 windspeed=wind, winddir=np.zeros(T))
 
 
+def theta_from_dailyprecip(dailyprecip, soil, temp, swrad, T=None, depth=0.1, theta0=None):
+    """Hourly volumetric water content of the top soil layer from daily precipitation — a host-side single-bucket recipe for
+    BASELINE config C4.  Soil moisture is an INPUT of the hot path: the reference has no soil-water model of its
+    own (vignette: `theta` is supplied; NicheMapR provides it in runwithNMR, NMR.R:796), so this stands in for that provider.
+
+    Bucket of `depth` m between Smin and Smax of `soil` (soilparams row): every hour
+      theta += (P/24 - ET - D) / (1000 * depth)   [P in mm/day, ET and D in mm/h]
+      ET = 0.0008 * max(swrad, 0) * max(temp, 0) / 15 * rel   (radiation- and temperature-scaled, rel = relative saturation)
+      D  = Ksat/24 * rel ** (2 * b + 3)                       (Campbell unit-gradient drainage, Ksat in mm/day)
+    clipped to [Smin, Smax] (excess runs off)."""
+    P = np.asarray(dailyprecip, float)
+    temp = np.asarray(temp, float); swrad = np.asarray(swrad, float)
+    T = temp.size if T is None else T
+    smin, smax, b, ksat = float(soil["Smin"]), float(soil["Smax"]), float(soil["b"]), float(soil["Ksat"])
+    th = np.empty(T)
+    cur = 0.5 * (smin + smax) if theta0 is None else float(theta0)
+    for t in range(T):
+        rel = (cur - smin) / (smax - smin)
+        et = 0.0008 * max(swrad[t], 0.0) * max(temp[t], 0.0) / 15.0 * rel
+        dr = ksat / 24.0 * rel ** (2 * b + 3)
+        cur = min(smax, max(smin, cur + (P[(t // 24) % P.size] / 24.0 - et - dr) / (1000.0 * depth)))
+        th[t] = cur
+    return th
+
+
+def snow_from_forcing(dailyprecip, temp, density=100.0, melt_per_degree_hour=0.2, seed=0):
+    """Synthetic NicheMapR-style snow outputs for config C4: snow depth (cm) accumulates from precipitation falling at temp < 0.5 C
+    (fresh-snow density `density` kg m-3) and melts by `melt_per_degree_hour` cm per degree-hour above 0 C; the eight snow-layer
+    temperatures SN1..SN8 grade from the (sub-zero) air temperature at the surface to -0.5 C at the base.  Returns (SNOWDEP[T],
+    SN[T][8])."""
+    P = np.asarray(dailyprecip, float); temp = np.asarray(temp, float)
+    T = temp.size
+    dep = np.zeros(T); cur = 0.0
+    for t in range(T):
+        if temp[t] < 0.5:
+            cur += P[(t // 24) % P.size] / 24.0 * (1000.0 / density) / 10.0       # mm water -> cm snow
+        else:
+            cur = max(0.0, cur - melt_per_degree_hour * temp[t])
+        dep[t] = cur
+    top = np.minimum(temp, -0.1)
+    w = np.linspace(1.0, 0.0, 8)[None, :]
+    return dep, top[:, None] * w + (-0.5) * (1 - w)
+
+
 def vegp_deciduous(m=20, hgt=15.0, PAIt=4.0):
     """Synthetic 'deciduous broadleaf forest' vegp (dict with the 21 reference field names)."""
     zz = (np.arange(1, m + 1) - 0.5) / m

@@ -87,3 +87,21 @@ def test_guards():
 def test_leafem_and_datasets():
     assert abs(api.leafem(11.0, 0.97) - 0.97 * 5.67e-8 * (284.15) ** 4) < 1e-9
     assert len(api.weather()["temp"]) == 8760 and api.dailyprecip().size == 365 and api.climvars()["tair"] == 16
+
+
+def test_c4_soil_moisture_bucket_and_snow_series():
+    """BASELINE config C4 inputs: theta(t) from the documented dailyprecip bucket, snow pack from the same
+    precipitation.  Host-side recipes (soil moisture and snow are inputs of the hot path): bounded, reproducible, responsive."""
+    w = S.load_weather(); sp = S.load_soilparams(); i = sp["Soil.type"].index("Loam")
+    loam = {k: sp[k][i] for k in L.SOIL_SCALARS}
+    P = S.load_dailyprecip()
+    th = S.theta_from_dailyprecip(P, loam, w["temp"], w["swrad"])
+    assert th.shape == (8760,) and th.min() >= loam["Smin"] and th.max() <= loam["Smax"]
+    assert np.array_equal(th, S.theta_from_dailyprecip(P, loam, w["temp"], w["swrad"]))
+    wet = S.theta_from_dailyprecip(P * 2, loam, w["temp"], w["swrad"]); dry = S.theta_from_dailyprecip(P * 0, loam, w["temp"], w["swrad"])
+    assert wet.mean() > th.mean() > dry.mean() and dry[-1] < dry[0]
+    dep, sn = S.snow_from_forcing(P * 4.0, w["temp"] - 6.0)
+    assert dep.shape == (8760,) and sn.shape == (8760, 8) and dep.min() >= 0 and dep.max() > 100 and np.all(sn <= 0)
+    assert np.all(np.diff(dep)[w["temp"][1:] - 6.0 >= 0.5] <= 0)                      # melts, never grows, above the threshold
+    d0, _ = S.snow_from_forcing(P * 4.0, w["temp"] + 20.0)
+    assert d0.max() == 0.0
