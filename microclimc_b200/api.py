@@ -245,13 +245,9 @@ def spinup(climdata, vegp, soilp, lat, long, edgedist=100, reqhgt=None, sdepth=2
     return _state_to_list(ctx.get_state(), m, sm)
 
 
-def runmodel_batch(climdata, vegp, soilp, lat, long, edgedist=100, reqhgt=None, sdepth=2, zu=2, theta=0.3, merid=0, dst=0, n=0.6,
-                   steps=200, tsoil=None, metopen=True, windhgt=2, zlafact=1, surfwet=1, previn=None, snow=None, fscale=None,
-                   foffset=None, sample=None, full=False, n_gpus=1):
-    """Batched `runmodel` (R/code.R:1125-1328) over stacked columns.
-
-    vegp / soilp: lists of the reference's lists (one per column) or packed [row][column] arrays.
-    Returns dict(series [T][8][nsample] (layout.SERIES), stats [6][ncol], flags, state [NSTATE][ncol], full, sample, obs_time)."""
+def _prepare_transient(climdata, vegp, soilp, lat, long, edgedist, reqhgt, zu, theta, merid, dst, n, steps, metopen, windhgt, zlafact,
+                       surfwet, previn, snow, fscale, foffset, n_gpus):
+    """Argument checks and input shaping of `runmodel` (R/code.R:1130-1192) for stacked columns; returns the loaded context."""
     char = isinstance(reqhgt, str)
     if char and reqhgt not in ("all", "allclim"):
         raise ValueError("input reqhgt no recognised\n")                                     # code.R:1136-1139
@@ -293,6 +289,19 @@ def runmodel_batch(climdata, vegp, soilp, lat, long, edgedist=100, reqhgt=None, 
         st = previn if isinstance(previn, np.ndarray) else np.concatenate([_list_to_state(p, m, sm) for p in
                                                                            (previn if isinstance(previn, (list, tuple)) else [previn])], axis=1)
         ctx.set_state(st)
+    return ctx, dict(m=m, sm=sm, ncol=ncol, T=T, char=char, timestep=ts)
+
+
+def runmodel_batch(climdata, vegp, soilp, lat, long, edgedist=100, reqhgt=None, sdepth=2, zu=2, theta=0.3, merid=0, dst=0, n=0.6,
+                   steps=200, tsoil=None, metopen=True, windhgt=2, zlafact=1, surfwet=1, previn=None, snow=None, fscale=None,
+                   foffset=None, sample=None, full=False, n_gpus=1):
+    """Batched `runmodel` (R/code.R:1125-1328) over stacked columns.
+
+    vegp / soilp: lists of the reference's lists (one per column) or packed [row][column] arrays.
+    Returns dict(series [T][8][nsample] (layout.SERIES), stats [6][ncol], flags, state [NSTATE][ncol], full, sample, obs_time)."""
+    ctx, info = _prepare_transient(climdata, vegp, soilp, lat, long, edgedist, reqhgt, zu, theta, merid, dst, n, steps, metopen, windhgt,
+                                   zlafact, surfwet, previn, snow, fscale, foffset, n_gpus)
+    m, sm, ncol, char = info["m"], info["sm"], info["ncol"], info["char"]
     ts_arr = None
     if not _isna(tsoil):
         ts_arr = np.broadcast_to(np.asarray(tsoil, float), (ncol,)).copy()
@@ -303,21 +312,10 @@ def runmodel_batch(climdata, vegp, soilp, lat, long, edgedist=100, reqhgt=None, 
     return r
 
 
-def runmodel(climdata, vegp, soilp, lat, long, edgedist=100, reqhgt=None, sdepth=2, zu=2, theta=0.3, merid=0, dst=0, n=0.6,
-             steps=200, plotout=False, plotsteps=100, tsoil=None, metopen=True, windhgt=2, zlafact=1, surfwet=1, previn=None,
-             snow=None):
-    """R/code.R:1125-1328 for one column. Returns a pandas DataFrame (obs_time, reftemp, tout, tleaf, relhum, SWin, LWin, H, L, G)
-    or, for reqhgt "all"/"allclim", a dict of DataFrames (Airtemp, Leaftemp, Soiltemp, Windspeed, Relhum[, Conductivity, Fluxes])."""
+def _all_tables(full, obs, m, sm, with_fluxes):
+    """The data.frames `runmodel` returns for reqhgt "allclim" / "all" (R/code.R:1267-1322) from the full-state rows [T][NSTATE]
+    of one column."""
     import pandas as pd
-    r = runmodel_batch(climdata, [vegp], [soilp], lat, long, edgedist, reqhgt, sdepth, zu, theta, merid, dst, n, steps, tsoil, metopen,
-                       windhgt, zlafact, surfwet, previn=None if previn is None else [previn], snow=snow)
-    m, sm = r["m"], r["sm"]
-    obs = r["obs_time"]
-    if not isinstance(reqhgt, str):
-        s = r["series"][:, :, 0]
-        return pd.DataFrame(dict(obs_time=obs, reftemp=np.asarray(climdata["temp"], float), tout=s[:, 0], tleaf=s[:, 1], relhum=s[:, 2],
-                                 SWin=s[:, 3], LWin=s[:, 4], H=s[:, 6], L=s[:, 5], G=s[:, 7]))
-    full = r["full"][:, :, 0]                                                               # [T][NSTATE]
     rows = L.state_rows(m, sm)
     z = full[-1, rows["z"]]; sz = full[-1, rows["sz"]]
     zab = full[-1, rows["zabove"]][0]
@@ -335,7 +333,7 @@ def runmodel(climdata, vegp, soilp, lat, long, edgedist=100, reqhgt=None, sdepth
         Soiltemp=df(full[:, rows["soiltc"]], ["Temp_%gm" % round(v, 3) for v in sz]),
         Windspeed=df(full[:, rows["uz"]], ["u_%s" % v for v in zn]),
         Relhum=df(full[:, rows["rh"]], ["relh_%s" % v for v in zn]))
-    if reqhgt == "all":
+    if with_fluxes:
         # code.R:1302-1310 binds gha, gt (m+1 columns), gv in that order; its name vector is one short, so plain names here
         out["Conductivity"] = df(np.column_stack([full[:, rows["gha"]], full[:, rows["gt"]], full[:, rows["gv"]]]),
                                  ["Leafbound_%s" % v for v in zn] + ["Air_%d" % i for i in range(m + 1)] + ["Leafvap_%s" % v for v in zn])
@@ -343,6 +341,23 @@ def runmodel(climdata, vegp, soilp, lat, long, edgedist=100, reqhgt=None, sdepth
                                             full[:, rows["G"]]]),
                            ["SWin_%s" % v for v in zn] + ["Lwin_%s" % v for v in zn] + ["Latent_%sW/m^2" % v for v in zn] + ["Sensible", "Ground"])
     return out
+
+
+def runmodel(climdata, vegp, soilp, lat, long, edgedist=100, reqhgt=None, sdepth=2, zu=2, theta=0.3, merid=0, dst=0, n=0.6,
+             steps=200, plotout=False, plotsteps=100, tsoil=None, metopen=True, windhgt=2, zlafact=1, surfwet=1, previn=None,
+             snow=None):
+    """R/code.R:1125-1328 for one column. Returns a pandas DataFrame (obs_time, reftemp, tout, tleaf, relhum, SWin, LWin, H, L, G)
+    or, for reqhgt "all"/"allclim", a dict of DataFrames (Airtemp, Leaftemp, Soiltemp, Windspeed, Relhum[, Conductivity, Fluxes])."""
+    import pandas as pd
+    r = runmodel_batch(climdata, [vegp], [soilp], lat, long, edgedist, reqhgt, sdepth, zu, theta, merid, dst, n, steps, tsoil, metopen,
+                       windhgt, zlafact, surfwet, previn=None if previn is None else [previn], snow=snow)
+    m, sm = r["m"], r["sm"]
+    obs = r["obs_time"]
+    if not isinstance(reqhgt, str):
+        s = r["series"][:, :, 0]
+        return pd.DataFrame(dict(obs_time=obs, reftemp=np.asarray(climdata["temp"], float), tout=s[:, 0], tleaf=s[:, 1], relhum=s[:, 2],
+                                 SWin=s[:, 3], LWin=s[:, 4], H=s[:, 6], L=s[:, 5], G=s[:, 7]))
+    return _all_tables(r["full"][:, :, 0], obs, m, sm, reqhgt == "all")
 
 
 # ---- steady state --------------------------------------------------------------------------------------------------

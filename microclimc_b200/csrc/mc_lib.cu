@@ -93,7 +93,8 @@ template <int MM>
 __global__ void __launch_bounds__(kBlock, 5) k_steady(SteadyArgs a) {
   exp_tab_init();
   long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (c < a.ncol) steady_column<MM>(a, c, blockIdx.y, gridDim.y);
+  const bool live = c < a.ncol;
+  steady_column<MM>(a, live ? c : a.ncol - 1, blockIdx.y, gridDim.y, live);
 }
 __global__ void k_steady_reduce(long long ncol, int nchunk, long long T, const double* part, double* stats) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;

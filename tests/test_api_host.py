@@ -105,3 +105,9 @@ def test_c4_soil_moisture_bucket_and_snow_series():
     assert np.all(np.diff(dep)[w["temp"][1:] - 6.0 >= 0.5] <= 0)                      # melts, never grows, above the threshold
     d0, _ = S.snow_from_forcing(P * 4.0, w["temp"] + 20.0)
     assert d0.max() == 0.0
+
+
+def test_gridrun_rejects_bad_chunking_before_touching_a_device(tmp_path):
+    from microclimc_b200 import gridrun
+    with pytest.raises(ValueError, match="chunk_hours"):
+        gridrun.runmodel_grid(S.load_weather(), [S.vegp_deciduous()], [api.soilinit("Loam")], 50, -5, str(tmp_path), chunk_hours=0)
