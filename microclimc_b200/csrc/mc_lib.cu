@@ -89,8 +89,11 @@ __global__ void __launch_bounds__(kBlock) k_paraminit(long long ncol, int m, int
   long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   if (c < ncol) paraminit_column<MM, MS>(ncol, m, sm, args, state, c);
 }
+#ifndef MC_STEADY_CTAS
+#define MC_STEADY_CTAS 5
+#endif
 template <int MM>
-__global__ void __launch_bounds__(kBlock, 5) k_steady(SteadyArgs a) {
+__global__ void __launch_bounds__(kBlock, MC_STEADY_CTAS) k_steady(SteadyArgs a) {
   exp_tab_init();
   long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const bool live = c < a.ncol;
