@@ -246,3 +246,38 @@ def test_streaming_restart_and_chunking(oracle, hostdbg):
     b2 = dbg_run_transient(hostdbg, dict(inp, f=inp["f"][1:2]), make_cfg(spin_steps=0), state=s0["state"])
     assert_state_close(b1["state"], b2["state"], what="restart fast vs general")
     assert np.all(np.isfinite(a["state"]))
+
+
+# ---- the variant tables of tests/test_gpu_variants.py through the host build of the streaming code -----------------------
+def _variant_cases():
+    import tests.test_gpu_variants as V
+    return [("cfg", k) for k in sorted(V.CFG_VARIANTS)] + [("site", k) for k in sorted(V.SITE_VARIANTS)]
+
+
+@pytest.mark.parametrize("kind,name", _variant_cases())
+def test_streaming_form_over_the_variant_tables(oracle, hostdbg, kind, name, monkeypatch):
+    """Every run-description / vegetation / soil / site variant the GPU test drives through the CUDA kernels, here through the
+    host build of the same source (DirectMem accessor) against the literal oracle — the CPU suite's view of those branches."""
+    import tests.test_gpu_variants as V
+    monkeypatch.setattr(V, "NCOL", 5)
+    if kind == "cfg":
+        kw = dict(spin_steps=V.SPIN); kw.update(V.CFG_VARIANTS[name])
+        inp = V._inputs(oracle)
+    else:
+        kw = dict(spin_steps=V.SPIN)
+        sk = dict(V.SITE_VARIANTS[name])
+        if callable(sk.get("vegp")):
+            sk["vegp"] = sk["vegp"]()
+        inp = V._inputs(oracle, **sk)
+    cfg = make_cfg(**kw)
+    want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"])
+    fl = _FastLib(hostdbg)
+    fl.dbg_general_steps(1)
+    got = dbg_run_transient(fl, inp, cfg)
+    ngen = fl.dbg_general_steps(1)
+    assert_series_close(got["series"], want["series"], name)
+    assert_state_close(got["state"], want["state"], what=name)
+    if name == "short_grass_general_path":
+        assert ngen >= 5 * (V.T + V.SPIN) - 5, "nodes under 0.12 m must take the general path (%d)" % ngen
+    elif kw.get("timestep", 3600.0) >= 3600.0 and "reqhgt" not in kw:
+        assert ngen <= 5, "hourly columns should stay in the streaming envelope (general steps: %d)" % ngen
