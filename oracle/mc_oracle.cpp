@@ -1,4 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+// PARITY UNPINNED vs real R: the reference ships no tests or golden vectors and neither R nor microctools can run here;
+// pinned only by SURVEY Appendix F known answers, the independent numpy transliteration goldens and the decoded datasets.
 //
 // extern "C" entry points (ctypes-callable) around the CPU restatement in mc_model.hpp / mc_steady.hpp,
 // plus the drivers spinup (code.R:982-1013) and the runmodel hot loop + output harvest (code.R:1193-1266),
