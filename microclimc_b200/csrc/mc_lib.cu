@@ -99,6 +99,13 @@ __global__ void __launch_bounds__(kBlock, MC_STEADY_CTAS) k_steady(SteadyArgs a)
   const bool live = c < a.ncol;
   steady_column<MM>(a, live ? c : a.ncol - 1, blockIdx.y, gridDim.y, live);
 }
+// date-only part of the solar geometry, once per hour of the series instead of once per (column, hour)
+__global__ void k_steady_sol(long long T, const double* clim, double* sol) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const SolDay d = sol_day(clim[t * 9 + 7]);
+  sol[t * 3] = d.eot; sol[t * 3 + 1] = d.sdec; sol[t * 3 + 2] = d.cdec;
+}
 __global__ void k_steady_reduce(long long ncol, int nchunk, long long T, const double* part, double* stats) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncol) return;
@@ -164,7 +171,7 @@ struct Shard {
   int dev = 0; long long c0 = 0, nc = 0;
   cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
   DBuf vegp, soilp, lat, lon, state, state_bak, fscale, foffset, forcing, season, tsoil, stats, series, full, samp_of, flags,
-      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, fP, fS, fW, dbg;
+      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fP, fS, fW, dbg;
   bool fast_attr = false;
   bool has_pert = false, has_season = false, has_state = false;
   float ms = 0; long long launches = 0;
@@ -282,6 +289,10 @@ int launch_transient(Shard& s, const TransientArgs& a) {
   return 0;
 }
 int launch_steady(Shard& s, const SteadyArgs& a, int nchunk) {
+  if (a.sol) {
+    k_steady_sol<<<nblocks(a.T), kBlock, 0, s.st>>>(a.T, a.clim, const_cast<double*>(a.sol));
+    s.launches++;
+  }
   dim3 grid(nblocks(a.ncol), nchunk);
   if (a.m <= 20) k_steady<20><<<grid, kBlock, 0, s.st>>>(a);
   else k_steady<64><<<grid, kBlock, 0, s.st>>>(a);
@@ -341,7 +352,7 @@ void mc_destroy(mc_ctx* ctx) {
     cudaSetDevice(s.dev);
     DBuf* bufs[] = {&s.vegp, &s.soilp, &s.lat, &s.lon, &s.state, &s.state_bak, &s.fscale, &s.foffset, &s.forcing, &s.season, &s.tsoil,
                     &s.stats, &s.series, &s.full, &s.samp_of, &s.flags, &s.args6, &s.clim8, &s.theta, &s.thetap, &s.nmerged,
-                    &s.sclim, &s.snmr, &s.sseason, &s.sout, &s.spart, &s.fP, &s.fS, &s.fW, &s.dbg};
+                    &s.sclim, &s.snmr, &s.sseason, &s.sout, &s.spart, &s.ssol, &s.fP, &s.fS, &s.fW, &s.dbg};
     for (DBuf* b : bufs) b->release();
     if (s.e0) cudaEventDestroy(s.e0);
     if (s.e1) cudaEventDestroy(s.e1);
@@ -626,6 +637,7 @@ int mc_run_steady(mc_ctx* ctx, int64_t T, const double* clim, const double* nmr,
     }
     CU(s.flags.need(sizeof(int) * s.nc)); a.flags = s.flags.as<int>();
     CU(cudaMemsetAsync(s.flags.p, 0, sizeof(int) * s.nc, s.st));
+    CU(s.ssol.need(sizeof(double) * T * 3)); a.sol = s.ssol.as<double>();
     CU(cudaEventRecord(s.e0, s.st));
     launch_steady(s, a, nchunk);
     CU(cudaEventRecord(s.e1, s.st));

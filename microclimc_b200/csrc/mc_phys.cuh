@@ -298,15 +298,33 @@ MC_HD double soilrh(double theta, double b, double Psie, double Smax, double tc)
 }
 
 // ---- sun / radiation --------------------------------------------------------------------------
-MC_HD double solalt(double lt, double lat, double lon, double jd, double merid, double dst) {
-  double mm = 6.24004077 + 0.01720197 * (jd - 2451545);
-  double eot = -7.659 * sin(mm) + 9.863 * sin(2 * mm + 3.5932);
-  double st = lt + fdiv(4 * (lon - merid) + eot, 60) - dst;
+// Solar altitude (microctools solalt; degrees).  Its nine trigonometric calls split three ways: five depend on the date only
+// (equation of time, declination), two on the latitude only, and only cos(hour angle) and the atan depend on both — the steady
+// kernel takes the date part from a per-hour table and the latitude part from the column's preparation (34 % of its stall samples
+// sat in these calls, profiles r01q), the streaming kernel likewise.  Same operations in the same order as the one-piece form.
+struct SolDay { double eot, sdec, cdec; };
+MC_HD SolDay sol_day(double jd) {
+  const double mm = 6.24004077 + 0.01720197 * (jd - 2451545);
+  SolDay d;
+  d.eot = -7.659 * sin(mm) + 9.863 * sin(2 * mm + 3.5932);
+  const double declin = (kPi * 23.5 / 180) * cos(2 * kPi * fdiv(jd - 159.5, 365.25));
+  d.sdec = sin(declin); d.cdec = cos(declin);
+  return d;
+}
+MC_HD void sol_site(double lat, double& slat, double& clat) {
+  const double latr = fdiv(lat * kPi, 180);
+  slat = sin(latr); clat = cos(latr);
+}
+MC_HD double solalt_pre(double lt, double lon, double merid, double dst, const SolDay& d, double slat, double clat) {
+  double st = lt + fdiv(4 * (lon - merid) + d.eot, 60) - dst;
   double tt = 0.261799 * (st - 12);
-  double declin = (kPi * 23.5 / 180) * cos(2 * kPi * fdiv(jd - 159.5, 365.25));
-  double latr = fdiv(lat * kPi, 180);
-  double sh = sin(declin) * sin(latr) + cos(declin) * cos(latr) * cos(tt);
+  double sh = d.sdec * slat + d.cdec * clat * cos(tt);
   return fdiv(180 * atan(fdiv(sh, fsqrt(1 - sh * sh))), kPi);
+}
+MC_HD double solalt(double lt, double lat, double lon, double jd, double merid, double dst) {
+  double sl, cl;
+  sol_site(lat, sl, cl);
+  return solalt_pre(lt, lon, merid, dst, sol_day(jd), sl, cl);
 }
 MC_HD double difprop(double Rsw, double sa) {
   if (!(sa > 0) || !(Rsw > 0)) return 1.0;

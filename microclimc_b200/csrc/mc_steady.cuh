@@ -20,6 +20,7 @@ struct SteadyArgs {
   const double* nmr;         // [T][11] or [T][11][ncol]: D0cm, WC0cm, SNOWDEP(cm), SN1..SN8
   int nmr_percol;
   const double* season;      // [T] or null
+  const double* sol;         // [T][3] eot, sin(declination), cos(declination) per hour (k_steady_sol), or null: computed in place
   double reqhgt; int metopen; double windhgt, surfwet;
   double* out;               // [T][7][ncol] or null
   double* stats;             // [6][ncol] (written by the reduce kernel)
@@ -30,7 +31,7 @@ struct SteadyArgs {
 template <int MM>
 struct SteadyCol {
   int m;
-  double hgt, x, lw, cd, refls, refw, refg, vegem, gsmax, q50, clump, iwmean, soilb, psi_e, Smax, lat, lon;
+  double hgt, x, lw, cd, refls, refw, refg, vegem, gsmax, q50, clump, iwmean, soilb, psi_e, Smax, lat, lon, slat, clat;
   double PAIb[MM + 2], pLAIb[MM + 2];
   // prepared (column + season)
   double PAIt, LAI, PAIu, d, zm3, zm4, lnuf, lnh3, a, l_m, La, leafdens;
@@ -55,6 +56,7 @@ struct SteadyCol {
     auto S = [&](int r) { return a.soilp[(long long)r * a.ncol + c]; };
     Smax = S(S_SMAX); soilb = S(S_B); psi_e = S(S_PSIE);
     lat = a.lat[c]; lon = a.lon[c];
+    sol_site(lat, slat, clat);
   }
   // hgt*(e0-e1) of gcanopy between z0 < z1 for attenuation a (phi_m = 1)
   MC_HD double gc_den(double z1, double z0, double av) const {
@@ -237,7 +239,7 @@ struct SteadyCol {
   }
 
   // one hour without snow (runmodelS body, NMR.R:761-865); o[7] = Tloc, tleaf, RHloc, RSWloc, RLWloc, windspeed, dp
-  MC_HD void point(const SteadyArgs& A, const double* cr, double tground, double theta, double* o) const {
+  MC_HD void point(const SteadyArgs& A, const double* cr, const SolDay& sd, double tground, double theta, double* o) const {
     const double reqhgt = A.reqhgt;
     const double tair = cr[0], relhum = cr[1], pk = cr[2], swrad = cr[4], skyem = cr[6];
     const double u2 = wind2m(A, cr[3], PAIt);
@@ -259,7 +261,7 @@ struct SteadyCol {
     if (dp > 1) dp = 1;
     const double ph = phair(tair, pk);
     double gtt = gturb_apply(u2, gt_lnu, gt_lnh, ph, psi_m, psi_h);
-    const double sa_l = solalt(cr[8], lat, lon, cr[7], /*merid <- clump (Q15)*/ clump, 0);
+    const double sa_l = solalt_pre(cr[8], lon, /*merid <- clump (Q15)*/ clump, 0, sd, slat, clat);
     const double K_l = (sa_l > 0) ? cank(x, sa_l, kden) : 0.0;
     const double mul = cank(x, sa_l < 5 ? 5.0 : sa_l, kden);
     const double ph0 = phair(tair, 101.3);
@@ -290,7 +292,7 @@ struct SteadyCol {
       gtt = hpar(gtt, gtc);
       double gt0 = gcan_apply(l_m, iwmean, ph, uh, a, gc_0_den);
       double gha = 1.41 * gforcedfree(lw * 0.71, uz, tair, 5, pk, 5);
-      double sa = solalt(cr[8], lat, lon, cr[7], merid_def, 0);
+      double sa = solalt_pre(cr[8], lon, merid_def, 0, sd, slat, clat);
       double K = (sa > 0) ? cank(x, sa, kden) : 0.0;
       double PAR = cansw_k(swrad, dp, sa, PAIu, s02, trd02, K, 0.0);
       double gC = layercond(PAR, gsmax, q50);
@@ -328,7 +330,7 @@ struct SteadyCol {
     return true;
   }
   // one hour with snow on the ground (.runmodelsnow body, NMR.R:514-677)
-  MC_HD bool point_snow(const SteadyArgs& A, const double* cr, double snowdep_cm, const double* SN, double* o) const {
+  MC_HD bool point_snow(const SteadyArgs& A, const double* cr, const SolDay& sd, double snowdep_cm, const double* SN, double* o) const {
     const double reqhgt = A.reqhgt;
     const double snowtemp = SN[0];
     const double snowdep = snowdep_cm / 100;
@@ -358,7 +360,7 @@ struct SteadyCol {
     if (dp > 1) dp = 1;
     const double ph = phair(tair, pk), ph0 = phair(tair, 101.3);
     double gtt = gturb_apply(u2, gts_lnu, gts_lnh, ph, 0, 0);
-    const double sa_l = solalt(cr[8], lat, lon, cr[7], clump, 0);
+    const double sa_l = solalt_pre(cr[8], lon, clump, 0, sd, slat, clat);
     const double K_l = (sa_l > 0) ? cank(x, sa_l, kden) : 0.0;
     const double mul = cank(x, sa_l < 5 ? 5.0 : sa_l, kden);
     const double emv85 = 1 - (1 - 0.85);
@@ -391,7 +393,7 @@ struct SteadyCol {
       gtt = hpar(gtt, gtc);
       double gt0 = gcan_apply(l_m_s, iwmean, ph, uh, a1, gcs_0_den);
       double gha = 1.41 * gforcedfree(lw * 0.71 * 2, uz, tair, 5, pk, 5);
-      double sa = solalt(cr[8], lat, lon, cr[7], merid_def, 0);
+      double sa = solalt_pre(cr[8], lon, merid_def, 0, sd, slat, clat);
       double K = (sa > 0) ? cank(x, sa, kden) : 0.0;
       double PAR = cansw_k(swrad, dp, sa, PAIu, s06, trd06, K, 0.0);
       double gC = layercond(PAR, gsmax, q50);
@@ -438,10 +440,13 @@ MC_HD void steady_column(const SteadyArgs& A, long long c, int chunk, int nchunk
     double nm[11];
     if (A.nmr_percol) { for (int q = 0; q < 11; ++q) nm[q] = A.nmr[(t * 11 + q) * A.ncol + c]; }
     else { for (int q = 0; q < 11; ++q) nm[q] = A.nmr[t * 11 + q]; }
+    SolDay sd;
+    if (A.sol) { sd.eot = A.sol[t * 3]; sd.sdec = A.sol[t * 3 + 1]; sd.cdec = A.sol[t * 3 + 2]; }
+    else sd = sol_day(cr[7]);
     double o[7];
     if (nm[2] > 0) {                                             // NMR.R:873-883: snow rows come from .runmodelsnow
-      if (!col.point_snow(A, cr, nm[2], nm + 3, o)) { flag |= 4; for (int q = 0; q < 7; ++q) o[q] = NAN; }
-    } else col.point(A, cr, nm[0], nm[1], o);
+      if (!col.point_snow(A, cr, sd, nm[2], nm + 3, o)) { flag |= 4; for (int q = 0; q < 7; ++q) o[q] = NAN; }
+    } else col.point(A, cr, sd, nm[0], nm[1], o);
     if (A.out && live) for (int q = 0; q < 7; ++q) A.out[(t * 7 + q) * A.ncol + c] = o[q];
     st[0] += o[0]; if (o[0] < st[1]) st[1] = o[0]; if (o[0] > st[2]) st[2] = o[0];
     st[3] += o[1]; if (o[1] < st[4]) st[4] = o[1]; if (o[1] > st[5]) st[5] = o[1];

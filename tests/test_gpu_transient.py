@@ -151,3 +151,36 @@ def test_ragged_column_counts(oracle, ncol):
     ctx = _ctx(inp, cfg)
     ctx.run_transient()
     assert_state_close(ctx.get_state(), want["state"], what="ncol=%d" % ncol)
+
+
+def test_empty_and_out_of_range_inputs_are_errors_or_no_ops(oracle):
+    """Empty column sets / forcing are rejected (ValueError from MC_ERR_ARG), an empty step range is a no-op that leaves the state
+    untouched, and out-of-range step ranges or sample indices never reach the device."""
+    from microclimc_b200._lib import Context, MicroclimcError
+    inp = transient_inputs(oracle, ncol=9, T=12)
+    ctx = Context(M, SM)
+    with pytest.raises((ValueError, MicroclimcError)):
+        ctx.run_transient(0, 1)                                                   # nothing set yet
+    with pytest.raises((ValueError, MicroclimcError, AssertionError)):
+        ctx.set_columns(inp["veg"][:, :0], inp["soil"][:, :0], inp["lat"][:0], inp["lon"][:0])
+    ctx.set_columns(inp["veg"], inp["soil"], inp["lat"], inp["lon"])
+    with pytest.raises((ValueError, MicroclimcError)):
+        ctx.set_forcing(inp["f"][:0])
+    ctx.set_forcing(inp["f"], inp["fs"], inp["fo"]); ctx.set_config(make_cfg(spin_steps=0))
+    with pytest.raises((ValueError, MicroclimcError)):
+        ctx.run_transient(0, 4)                                                   # no spin-up and no state
+    ctx.set_config(make_cfg(spin_steps=10))
+    ctx.run_transient(0, 4)
+    st = ctx.get_state()
+    r = ctx.run_transient(4, 4, samp_idx=np.arange(9))                            # empty range
+    assert r["series"].shape == (0, 8, 9)
+    np.testing.assert_array_equal(ctx.get_state(), st)
+    for t0, t1 in ((-1, 3), (5, 4), (0, 13)):
+        with pytest.raises((ValueError, MicroclimcError)):
+            ctx.run_transient(t0, t1)
+    with pytest.raises((ValueError, MicroclimcError)):
+        ctx.run_transient(4, 6, samp_idx=np.array([0, 9]))
+    np.testing.assert_array_equal(ctx.get_state(), st)
+    # and the context still works afterwards
+    ctx.run_transient(4, 12)
+    assert np.all(np.isfinite(ctx.get_state()[L.state_rows(M, SM)["tc"]]))
