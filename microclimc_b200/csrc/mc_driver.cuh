@@ -21,6 +21,7 @@ struct TransientArgs {
   const double* lat;         // [ncol]
   const double* lon;         // [ncol]
   const double* forcing;     // [T][F_N]
+  const double* fsol;        // [T][3] date-only solar terms of each forcing row (sol_day: eot, sin / cos of the declination) or null
   const double* fscale;      // [8][ncol] or null
   const double* foffset;     // [8][ncol] or null
   const double* tsoil;       // [ncol] or null (NaN entries -> mean of the column's air temperature)

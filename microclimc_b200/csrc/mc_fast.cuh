@@ -33,7 +33,7 @@ enum { P0_HGT, P0_LA, P0_LNREF, P0_LZU, P0_LZUH, P0_LZOH, P0_LNHD, P0_D, P0_GLNH
        P0_A0CAP, P0_GXC0, P0_CGCAP, P0_RDZCAP, P0_A0G, P0_GXG1, P0_CGG, P0_RZG,
        P0_X, P0_KDEN, P0_CLUMP, P0_REFG, P0_SM, P0_TRDM, P0_EMV, P0_VEGEM, P0_TRLWSUM, P0_REFM, P0_LAT, P0_LON,
        P0_GSMAX, P0_Q50, P0_LWD, P0_SMAX, P0_SOILB, P0_PSIE, P0_SKA, P0_SKB, P0_SKC, P0_SKAD, P0_CVDRY, P0_Z1,
-       P0_SELG, P0_SELH, P0_SELS, P0_ZABOVE, P0_FAST, P0_NFIX };          // then 1/DZK[sm], DZC[sm], Z[m]
+       P0_SELG, P0_SELH, P0_SELS, P0_ZABOVE, P0_FAST, P0_K5, P0_SLAT, P0_CLAT, P0_NFIX };          // then 1/DZK[sm], DZC[sm], Z[m]
 enum { PA_A0I, PA_A0O, PA_EX1, PA_EX2, PA_GLO, PA_GLI, PA_EDO, PA_EDI, PA_GX0, PA_GX1, PA_CG, PA_RDZ, PA_DZ, PA_N };
 enum { PB_REF, PB_PC, PB_SPC, PB_SGC, PB_TRDC, PB_TRDG, PB_TRLW, PB_PAI, PB_IZTH, PB_IZL, PB_IZRF, PB_IZP, PB_MAC, PB_MZ,
        PB_VDEN, PB_DZ, PB_N };
@@ -98,6 +98,8 @@ MC_HD void geom_column(const FastArgs& a, const RunCfg& cfg, long long c, long l
   }
   put(P0_A0CAP, col.a0_cap); put(P0_GXC0, col.gxc0); put(P0_CGCAP, (col.lm_cap * col.iw[m]) / hgt); put(P0_RDZCAP, 1 / fabs(hgt - col.z[m]));
   put(P0_A0G, col.a0_g); put(P0_GXG1, col.gxg1); put(P0_CGG, (col.lm_g * col.iwmean) / hgt); put(P0_RZG, 1 / fabs(col.zg - 0));
+  put(P0_K5, cank(col.x, 5.0, col.kden));
+  { double sl, cl; sol_site(col.lat, sl, cl); put(P0_SLAT, sl); put(P0_CLAT, cl); }
   put(P0_X, col.x); put(P0_KDEN, col.kden); put(P0_CLUMP, col.clump); put(P0_REFG, col.refg); put(P0_SM, col.s_m); put(P0_TRDM, col.trd_m);
   put(P0_EMV, col.emv); put(P0_VEGEM, col.vegem); put(P0_TRLWSUM, col.trlw_sum);
   put(P0_REFM, col.pLAI[m] * col.refls + (1 - col.pLAI[m]) * col.refw); put(P0_LAT, col.lat); put(P0_LON, col.lon);
@@ -532,7 +534,7 @@ MC_HD void fast_park_constants(Mem& mem) {
 // `run` false (a column that takes this step through the general path) only suppresses the stores into the state rows.
 // Returns false when the column left the fast envelope (nothing of the state has been modified then).
 template <class Mem, int MS>
-MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-uniform fields only */, double surfwet, bool run, bool emit,
+MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunCfg& cfg /* launch-uniform fields only */, double surfwet, bool run, bool emit,
                      double reqhgt, int charmode,
                      double relhum0, double rsw0, double skyem0, StepOut& out) {
   const FastLayout L = mem.L;
@@ -681,11 +683,11 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const RunCfg& cfg /* launch-un
     const double ppk = x1[X_PPK - X_PPK], ps1 = x1[X_PS1 - X_PPK], tet_tcan = x1[X_TET_TCAN - X_PPK];
     const double clump = mem.unpark(KR_CLUMP), refg = mem.unpark(KU_REFG), emv = mem.unpark(KG_EMV);   // launch-resident (fast_park_constants)
     double dp = fc.dp;
-    const double sa = solalt(fc.lt, p0(P0_LAT), p0(P0_LON), fc.jd, cfg.merid, cfg.dst);
+    const double sa = solalt_pre(fc.lt, p0(P0_LON), cfg.merid, cfg.dst, sday, p0(P0_SLAT), p0(P0_CLAT));
     if (dp != dp) dp = difprop(Rsw, sa);
     const double xx = p0(P0_X), kden = p0(P0_KDEN);
-    const double K = (sa > 0) ? cank(xx, sa, kden) : 0.0;
-    const double mul = cank(xx, sa < 5 ? 5.0 : sa, kden);
+    double K, mul;
+    cank2(xx, sa, kden, p0(P0_K5), K, mul);
     const double aG0 = refg * cansw_k(Rsw, dp, sa, p0(P0_SUMPAI), p0(P0_SM), p0(P0_TRDM), K, clump);
     const double lwout = kSb * pow4(tairn + 273.15);
     day = sa > 0;
@@ -1330,7 +1332,10 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
     const bool emit = live && (it == nsteps - 1 || (slot >= 0 && t.full));
     const bool gen_first = zdiff && it == 0;
     const bool runf = live && fastcol && !gen_first;
-    const bool ok = fast_step<Mem, MS>(mem, fc, t.cfg, surfwet, runf, emit, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
+    SolDay sday;                                          // date-only solar terms: from the per-row table when the library made one
+    if (t.fsol) { sday.eot = t.fsol[tt * 3]; sday.sdec = t.fsol[tt * 3 + 1]; sday.cdec = t.fsol[tt * 3 + 2]; }
+    else sday = sol_day(f[F_JD]);
+    const bool ok = fast_step<Mem, MS>(mem, fc, sday, t.cfg, surfwet, runf, emit, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
     if (live && (!runf || !ok)) {
       if (spin) {
         double zreg[MM + 1];                                  // previn$z of paraminit (regular grid) for the general path

@@ -99,11 +99,12 @@ __global__ void __launch_bounds__(kBlock, MC_STEADY_CTAS) k_steady(SteadyArgs a)
   const bool live = c < a.ncol;
   steady_column<MM>(a, live ? c : a.ncol - 1, blockIdx.y, gridDim.y, live);
 }
-// date-only part of the solar geometry, once per hour of the series instead of once per (column, hour)
-__global__ void k_steady_sol(long long T, const double* clim, double* sol) {
+// date-only part of the solar geometry, once per row of the series instead of once per (column, row); `stride` doubles per row,
+// Julian day at `jdcol`
+__global__ void k_sol_rows(long long T, const double* rows, int stride, int jdcol, double* sol) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
-  const SolDay d = sol_day(clim[t * 9 + 7]);
+  const SolDay d = sol_day(rows[t * stride + jdcol]);
   sol[t * 3] = d.eot; sol[t * 3 + 1] = d.sdec; sol[t * 3 + 2] = d.cdec;
 }
 __global__ void k_steady_reduce(long long ncol, int nchunk, long long T, const double* part, double* stats) {
@@ -171,7 +172,7 @@ struct Shard {
   int dev = 0; long long c0 = 0, nc = 0;
   cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
   DBuf vegp, soilp, lat, lon, state, state_bak, fscale, foffset, forcing, season, tsoil, stats, series, full, samp_of, flags,
-      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fP, fS, fW, dbg;
+      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fsol, fP, fS, fW, dbg;
   bool fast_attr = false;
   bool has_pert = false, has_season = false, has_state = false;
   float ms = 0; long long launches = 0;
@@ -290,7 +291,7 @@ int launch_transient(Shard& s, const TransientArgs& a) {
 }
 int launch_steady(Shard& s, const SteadyArgs& a, int nchunk) {
   if (a.sol) {
-    k_steady_sol<<<nblocks(a.T), kBlock, 0, s.st>>>(a.T, a.clim, const_cast<double*>(a.sol));
+    k_sol_rows<<<nblocks(a.T), kBlock, 0, s.st>>>(a.T, a.clim, 9, 7, const_cast<double*>(a.sol));
     s.launches++;
   }
   dim3 grid(nblocks(a.ncol), nchunk);
@@ -352,7 +353,7 @@ void mc_destroy(mc_ctx* ctx) {
     cudaSetDevice(s.dev);
     DBuf* bufs[] = {&s.vegp, &s.soilp, &s.lat, &s.lon, &s.state, &s.state_bak, &s.fscale, &s.foffset, &s.forcing, &s.season, &s.tsoil,
                     &s.stats, &s.series, &s.full, &s.samp_of, &s.flags, &s.args6, &s.clim8, &s.theta, &s.thetap, &s.nmerged,
-                    &s.sclim, &s.snmr, &s.sseason, &s.sout, &s.spart, &s.ssol, &s.fP, &s.fS, &s.fW, &s.dbg};
+                    &s.sclim, &s.snmr, &s.sseason, &s.sout, &s.spart, &s.ssol, &s.fsol, &s.fP, &s.fS, &s.fW, &s.dbg};
     for (DBuf* b : bufs) b->release();
     if (s.e0) cudaEventDestroy(s.e0);
     if (s.e1) cudaEventDestroy(s.e1);
@@ -396,6 +397,9 @@ int mc_set_forcing(mc_ctx* ctx, int64_t T, const double* forcing, const double* 
     if (s.nc == 0) return 0;
     CU(s.forcing.need(sizeof(double) * T * MC_F_N));
     CU(cudaMemcpyAsync(s.forcing.p, forcing, sizeof(double) * T * MC_F_N, cudaMemcpyHostToDevice, s.st));
+    CU(s.fsol.need(sizeof(double) * T * 3));
+    k_sol_rows<<<nblocks(T), kBlock, 0, s.st>>>(T, s.forcing.as<double>(), MC_F_N, F_JD, s.fsol.as<double>());
+    CU(cudaGetLastError());
     s.has_pert = fscale != nullptr;
     if (fscale) {
       CU(s.fscale.need(sizeof(double) * MC_NPERT * s.nc)); CU(s.foffset.need(sizeof(double) * MC_NPERT * s.nc));
@@ -538,7 +542,7 @@ static int run_transient_impl(mc_ctx* ctx, int64_t t0, int64_t t1, int spin_step
     TransientArgs a{};
     a.ncol = s.nc; a.m = m; a.sm = sm; a.T = ctx->T; a.t0 = t0; a.t1 = t1;
     a.vegp = s.vegp.as<double>(); a.soilp = s.soilp.as<double>(); a.lat = s.lat.as<double>(); a.lon = s.lon.as<double>();
-    a.forcing = s.forcing.as<double>();
+    a.forcing = s.forcing.as<double>(); a.fsol = s.fsol.as<double>();
     a.fscale = s.has_pert ? s.fscale.as<double>() : nullptr; a.foffset = s.has_pert ? s.foffset.as<double>() : nullptr;
     a.season = s.has_season ? s.season.as<double>() : nullptr;
     a.state = s.state.as<double>(); a.cfg = cfg; a.spin_steps = spin_steps; a.charmode = charmode; a.spin_standalone = standalone;

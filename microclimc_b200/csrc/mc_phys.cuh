@@ -342,6 +342,13 @@ MC_HD double cank(double x, double sa, double den) {
 MC_HD double clumptr(double tr, double clump) { return clump + (1 - clump) * tr; }
 // shortwave under plant area l: `s` = sqrt(1 - ref), `trd` = clumped diffuse transmission exp(-s*l),
 // `K` = beam extinction (unused when sa <= 0)
+// cank for sa (0 when the sun is down) and for max(sa, 5 degrees) with ONE tangent: the second equals the first whenever
+// sa >= 5 and is the column constant K5 = cank(x, 5, den) otherwise.  Values identical to two separate calls.
+MC_HD void cank2(double x, double sa, double den, double K5, double& K, double& Kc) {
+  const double Kf = cank(x, sa, den);
+  K = (sa > 0) ? Kf : 0.0;
+  Kc = (sa < 5) ? K5 : Kf;
+}
 MC_HD double cansw_k(double globrad, double dp, double sa, double l, double s, double trd, double K, double clump) {
   double trb = (sa > 0) ? clumptr(fexp(-s * K * l), clump) : clumptr(0.0, clump);
   return globrad * (dp * trd + (1 - dp) * trb);

@@ -38,7 +38,7 @@ struct SteadyCol {
   double wA, wB, wE;            // .windprofile factors: ln(zi), ln(zo or hgt), exp term
   double gt_lnu, gt_lnh, gtc_lnh;   // gturb pieces for z1 = hgt+2 and z1 = reqhgt
   double gc_top_den, gc_c_den, gc_0_den;   // hgt*(e0-e1) of the three gcanopy calls
-  double ref, sref, kden, emv, slw, trd_u, trd_t, trlw_u;
+  double ref, sref, kden, k5, emv, slw, trd_u, trd_t, trlw_u;
   double s02, trd02, sls, trdls, cdif;     // PAR (ref 0.2) and Rsw (ref refls) transmissions, cantransdif
   double merid_def;
   // snow variants
@@ -100,6 +100,7 @@ struct SteadyCol {
     ref = pl * refls + (1 - pl) * refw;
     sref = sqrt(1 - ref);
     kden = cank_den(x);
+    k5 = cank(x, 5.0, kden);
     emv = 1 - (1 - vegem);
     slw = sqrt(emv);
     trd_u = clumptr(exp(-sref * PAIu), 0.0);            // Q15: clump lands in `merid`; cansw/canlw see clump = 0
@@ -262,8 +263,8 @@ struct SteadyCol {
     const double ph = phair(tair, pk);
     double gtt = gturb_apply(u2, gt_lnu, gt_lnh, ph, psi_m, psi_h);
     const double sa_l = solalt_pre(cr[8], lon, /*merid <- clump (Q15)*/ clump, 0, sd, slat, clat);
-    const double K_l = (sa_l > 0) ? cank(x, sa_l, kden) : 0.0;
-    const double mul = cank(x, sa_l < 5 ? 5.0 : sa_l, kden);
+    double K_l, mul;
+    cank2(x, sa_l, kden, k5, K_l, mul);
     const double ph0 = phair(tair, 101.3);
     double tz, tleaf, rh, Rsw;
     if (reqhgt >= hgt) {
@@ -361,8 +362,8 @@ struct SteadyCol {
     const double ph = phair(tair, pk), ph0 = phair(tair, 101.3);
     double gtt = gturb_apply(u2, gts_lnu, gts_lnh, ph, 0, 0);
     const double sa_l = solalt_pre(cr[8], lon, clump, 0, sd, slat, clat);
-    const double K_l = (sa_l > 0) ? cank(x, sa_l, kden) : 0.0;
-    const double mul = cank(x, sa_l < 5 ? 5.0 : sa_l, kden);
+    double K_l, mul;
+    cank2(x, sa_l, kden, k5, K_l, mul);
     const double emv85 = 1 - (1 - 0.85);
     const double tk = tair + 273.15;
     double tz, tleaf, rh, Rsw, Rlw;
