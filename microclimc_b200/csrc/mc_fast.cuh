@@ -683,11 +683,12 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     const double ppk = x1[X_PPK - X_PPK], ps1 = x1[X_PS1 - X_PPK], tet_tcan = x1[X_TET_TCAN - X_PPK];
     const double clump = mem.unpark(KR_CLUMP), refg = mem.unpark(KU_REFG), emv = mem.unpark(KG_EMV);   // launch-resident (fast_park_constants)
     double dp = fc.dp;
-    const double sa = solalt_pre(fc.lt, p0(P0_LON), cfg.merid, cfg.dst, sday, p0(P0_SLAT), p0(P0_CLAT));
-    if (dp != dp) dp = difprop(Rsw, sa);
+    // `sa` is sin(solar altitude) from here on: only its sign, the 5-degree test, sin and cot of the angle are used (mc_phys.cuh)
+    const double sa = solsin_pre(fc.lt, p0(P0_LON), cfg.merid, cfg.dst, sday, p0(P0_SLAT), p0(P0_CLAT));
+    if (dp != dp) dp = difprop_sh(Rsw, sa);
     const double xx = p0(P0_X), kden = p0(P0_KDEN);
     double K, mul;
-    cank2(xx, sa, kden, p0(P0_K5), K, mul);
+    cank2_sh(xx, sa, kden, p0(P0_K5), K, mul);
     const double aG0 = refg * cansw_k(Rsw, dp, sa, p0(P0_SUMPAI), p0(P0_SM), p0(P0_TRDM), K, clump);
     const double lwout = kSb * pow4(tairn + 273.15);
     day = sa > 0;

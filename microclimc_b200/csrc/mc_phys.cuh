@@ -321,6 +321,28 @@ MC_HD double solalt_pre(double lt, double lon, double merid, double dst, const S
   double sh = d.sdec * slat + d.cdec * clat * cos(tt);
   return fdiv(180 * atan(fdiv(sh, fsqrt(1 - sh * sh))), kPi);
 }
+// The streaming and steady kernels never need the ANGLE: everything downstream of solalt is either a sign test, the 5-degree
+// test, sin(sa) (difprop) or tan(90 - sa) (cank) — all functions of sh = sin(sa), which is what the formula produces before its
+// atan.  Working on sh removes the atan -> degrees -> radians -> tan / sin round trips (two libm calls of ~70 serial instructions
+// each per use; algebraically identical, numerically within a few ulp of the round trip, far inside the parity tolerance).
+// The general column (mc_step.cuh) and the oracle keep the literal form.
+constexpr double kSin5 = 0.08715574274765817;          // sin(5 degrees)
+MC_HD double solsin_pre(double lt, double lon, double merid, double dst, const SolDay& d, double slat, double clat) {
+  double st = lt + fdiv(4 * (lon - merid) + d.eot, 60) - dst;
+  double tt = 0.261799 * (st - 12);
+  return d.sdec * slat + d.cdec * clat * cos(tt);
+}
+// cank2 on sh: tan(90 deg - sa) = cos(sa) / sin(sa)
+MC_HD void cank2_sh(double x, double sh, double den, double K5, double& K, double& Kc) {
+  const double cot = fdiv(fsqrt(1 - sh * sh), sh);
+  const double Kf = fdiv(fsqrt(x * x + cot * cot), den);
+  K = (sh > 0) ? Kf : 0.0;
+  Kc = (sh < kSin5) ? K5 : Kf;
+}
+MC_HD double cank_sh(double x, double sh, double den) {
+  const double cot = fdiv(fsqrt(1 - sh * sh), sh);
+  return fdiv(fsqrt(x * x + cot * cot), den);
+}
 MC_HD double solalt(double lt, double lat, double lon, double jd, double merid, double dst) {
   double sl, cl;
   sol_site(lat, sl, cl);
@@ -329,6 +351,14 @@ MC_HD double solalt(double lt, double lat, double lon, double jd, double merid, 
 MC_HD double difprop(double Rsw, double sa) {
   if (!(sa > 0) || !(Rsw > 0)) return 1.0;
   double kt = fdiv(Rsw, 1352.0 * sin(fdiv(sa * kPi, 180)));
+  if (kt > 1) kt = 1;
+  if (kt <= 0.22) return 1 - 0.09 * kt;
+  if (kt <= 0.8) return 0.9511 - 0.1604 * kt + 4.388 * kt * kt - 16.638 * kt * kt * kt + 12.336 * kt * kt * kt * kt;
+  return 0.165;
+}
+MC_HD double difprop_sh(double Rsw, double sh) {          // difprop with sin(sa) given
+  if (!(sh > 0) || !(Rsw > 0)) return 1.0;
+  double kt = fdiv(Rsw, 1352.0 * sh);
   if (kt > 1) kt = 1;
   if (kt <= 0.22) return 1 - 0.09 * kt;
   if (kt <= 0.8) return 0.9511 - 0.1604 * kt + 4.388 * kt * kt - 16.638 * kt * kt * kt + 12.336 * kt * kt * kt * kt;

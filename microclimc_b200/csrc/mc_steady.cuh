@@ -262,9 +262,9 @@ struct SteadyCol {
     if (dp > 1) dp = 1;
     const double ph = phair(tair, pk);
     double gtt = gturb_apply(u2, gt_lnu, gt_lnh, ph, psi_m, psi_h);
-    const double sa_l = solalt_pre(cr[8], lon, /*merid <- clump (Q15)*/ clump, 0, sd, slat, clat);
+    const double sa_l = solsin_pre(cr[8], lon, /*merid <- clump (Q15)*/ clump, 0, sd, slat, clat);
     double K_l, mul;
-    cank2(x, sa_l, kden, k5, K_l, mul);
+    cank2_sh(x, sa_l, kden, k5, K_l, mul);       // sa_l, sa: sin(solar altitude), see mc_phys.cuh
     const double ph0 = phair(tair, 101.3);
     double tz, tleaf, rh, Rsw;
     if (reqhgt >= hgt) {
@@ -293,8 +293,8 @@ struct SteadyCol {
       gtt = hpar(gtt, gtc);
       double gt0 = gcan_apply(l_m, iwmean, ph, uh, a, gc_0_den);
       double gha = 1.41 * gforcedfree(lw * 0.71, uz, tair, 5, pk, 5);
-      double sa = solalt_pre(cr[8], lon, merid_def, 0, sd, slat, clat);
-      double K = (sa > 0) ? cank(x, sa, kden) : 0.0;
+      double sa = solsin_pre(cr[8], lon, merid_def, 0, sd, slat, clat);
+      double K = (sa > 0) ? cank_sh(x, sa, kden) : 0.0;
       double PAR = cansw_k(swrad, dp, sa, PAIu, s02, trd02, K, 0.0);
       double gC = layercond(PAR, gsmax, q50);
       double gv = hpar(gC, gha);
@@ -361,9 +361,9 @@ struct SteadyCol {
     if (dp > 1) dp = 1;
     const double ph = phair(tair, pk), ph0 = phair(tair, 101.3);
     double gtt = gturb_apply(u2, gts_lnu, gts_lnh, ph, 0, 0);
-    const double sa_l = solalt_pre(cr[8], lon, clump, 0, sd, slat, clat);
+    const double sa_l = solsin_pre(cr[8], lon, clump, 0, sd, slat, clat);
     double K_l, mul;
-    cank2(x, sa_l, kden, k5, K_l, mul);
+    cank2_sh(x, sa_l, kden, k5, K_l, mul);       // sa_l, sa: sin(solar altitude), see mc_phys.cuh
     const double emv85 = 1 - (1 - 0.85);
     const double tk = tair + 273.15;
     double tz, tleaf, rh, Rsw, Rlw;
@@ -394,8 +394,8 @@ struct SteadyCol {
       gtt = hpar(gtt, gtc);
       double gt0 = gcan_apply(l_m_s, iwmean, ph, uh, a1, gcs_0_den);
       double gha = 1.41 * gforcedfree(lw * 0.71 * 2, uz, tair, 5, pk, 5);
-      double sa = solalt_pre(cr[8], lon, merid_def, 0, sd, slat, clat);
-      double K = (sa > 0) ? cank(x, sa, kden) : 0.0;
+      double sa = solsin_pre(cr[8], lon, merid_def, 0, sd, slat, clat);
+      double K = (sa > 0) ? cank_sh(x, sa, kden) : 0.0;
       double PAR = cansw_k(swrad, dp, sa, PAIu, s06, trd06, K, 0.0);
       double gC = layercond(PAR, gsmax, q50);
       double gv = hpar(gC, gha);
