@@ -175,7 +175,7 @@ struct Shard {
       args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fsol, fP, fS, fW, dbg;
   bool fast_attr = false;
   bool has_pert = false, has_season = false, has_state = false;
-  float ms = 0; long long launches = 0;
+  float ms = 0; long long launches = 0, pending_launches = 0;   // pending: kernels of mc_set_forcing, reported with the next run
   // replay info for mc_bench_resident
   int last_kind = 0;   // 0 none, 1 transient, 2 steady
   TransientArgs last_t; SteadyArgs last_s; int last_nchunk = 1;
@@ -400,6 +400,7 @@ int mc_set_forcing(mc_ctx* ctx, int64_t T, const double* forcing, const double* 
     CU(s.fsol.need(sizeof(double) * T * 3));
     k_sol_rows<<<nblocks(T), kBlock, 0, s.st>>>(T, s.forcing.as<double>(), MC_F_N, F_JD, s.fsol.as<double>());
     CU(cudaGetLastError());
+    s.pending_launches++;
     s.has_pert = fscale != nullptr;
     if (fscale) {
       CU(s.fscale.need(sizeof(double) * MC_NPERT * s.nc)); CU(s.foffset.need(sizeof(double) * MC_NPERT * s.nc));
@@ -527,7 +528,7 @@ static int run_transient_impl(mc_ctx* ctx, int64_t t0, int64_t t1, int spin_step
   RunCfg cfg = mk_cfg(ctx->cfg);
   const int charmode = ctx->cfg[MC_C_HARVEST_CHAR] != 0;
   int rc = for_shards(ctx, [&](Shard& s) -> int {
-    s.ms = 0; s.launches = 0;
+    s.ms = 0; s.launches = s.pending_launches; s.pending_launches = 0;
     if (s.nc == 0) return 0;
     // sample slots owned by this shard
     std::vector<long long> samp_of; std::vector<int64_t> slots;
