@@ -88,3 +88,49 @@ def test_steady_large_batch_matches_small_batches(oracle):
     np.testing.assert_array_equal(big[:, :, sel], small)
     want = oracle.run_steady(veg[:, sel], soil[:, sel], clim, nmr, np.full(sel.size, 50.0), np.full(sel.size, -5.0), scfg, M, SM)
     _check(small, want["out"])
+
+
+def test_config2_full_size_statistics_against_oracle(oracle):
+    """BASELINE config 2 in full (10^4-column ensemble x the bundled year, 8.76e7 column-hours): per-column statistics of every
+    column finite, and the statistics of a 64-column sample equal to the oracle's over the whole year."""
+    ncol, T = 10_000, 8760
+    veg, soil, clim, nmr = _steady_inputs(oracle, ncol, T, snow=False)
+    scfg = np.array([1.0, 1, 2, 1, 0.95])
+    st = _ctx(veg, soil).run_steady(clim, nmr, scfg, want_out=False)["stats"]
+    assert st.shape == (6, ncol) and np.all(np.isfinite(st))
+    sel = np.linspace(0, ncol - 1, 64).astype(int)
+    want = oracle.run_steady(veg[:, sel], soil[:, sel], clim, nmr, np.full(64, 50.0), np.full(64, -5.0), scfg, M, SM)["out"]   # [T][7][64]
+    for k, col in ((0, 0), (3, 1)):                         # mean / min / max of Tloc, then of tleaf
+        np.testing.assert_allclose(st[k, sel], want[:, col].mean(axis=0), rtol=0, atol=1e-6)
+        np.testing.assert_allclose(st[k + 1, sel], want[:, col].min(axis=0), rtol=0, atol=1e-6)
+        np.testing.assert_allclose(st[k + 2, sel], want[:, col].max(axis=0), rtol=0, atol=1e-6)
+
+
+def test_config4_full_size_mixed_habitats_with_snow(oracle):
+    """BASELINE config 4 size (4 x 10^6 columns, four habitat classes, snow pack and bucket soil moisture from dailyprecip): columns
+    of the same class agree bit for bit wherever they sit in the grid, everything is finite, a sample matches the oracle."""
+    T, t0, nbase, rep = 36, 516, 4000, 1000
+    ncol = nbase * rep
+    veg1, soil1 = S.ensemble(S.vegp_deciduous(), loam(oracle), nbase, M, SM, seed=11)
+    cls = np.arange(nbase) % 4                               # habitat classes: scale height and plant area of the template
+    veg1[L.VEG_SCALARS.index("hgt")] *= (0.4 + 0.4 * cls)
+    veg1[len(L.VEG_SCALARS):len(L.VEG_SCALARS) + M] *= (0.5 + 0.35 * cls)
+    w = S.load_weather(); sp = S.load_soilparams(); i = sp["Soil.type"].index("Loam")
+    lo = {k: sp[k][i] for k in L.SOIL_SCALARS}
+    clim = S.steady_clim_from_climdata(w)[t0:t0 + T].copy(); clim[:, 0] -= 6.0
+    th = S.theta_from_dailyprecip(S.load_dailyprecip(), lo, w["temp"] - 6.0, w["swrad"])
+    dep, sn = S.snow_from_forcing(S.load_dailyprecip() * 4.0, w["temp"] - 6.0)
+    nmr = np.zeros((T, 11))
+    nmr[:, 1] = th[t0:t0 + T]; nmr[:, 2] = dep[t0:t0 + T]; nmr[:, 3:] = sn[t0:t0 + T]
+    nmr[:, 0] = np.minimum(clim[:, 0] + 0.5, 0.0)
+    assert nmr[:, 2].min() > 0 and nmr[:, 2].min() < 100 < nmr[:, 2].max()          # the pack grows through the 1 m output height
+    veg = np.ascontiguousarray(np.tile(veg1, (1, rep))); soil = np.ascontiguousarray(np.tile(soil1, (1, rep)))
+    scfg = np.array([1.0, 1, 2, 1, 0.95])
+    st = _ctx(veg, soil).run_steady(clim, nmr, scfg, want_out=False)["stats"]
+    assert np.all(np.isfinite(st))
+    s3 = st.reshape(6, rep, nbase)
+    assert np.all(s3 == s3[:, :1, :])
+    sel = np.arange(0, nbase, 125)
+    want = oracle.run_steady(veg1[:, sel], soil1[:, sel], clim, nmr, np.full(sel.size, 50.0), np.full(sel.size, -5.0), scfg, M, SM)["out"]
+    np.testing.assert_allclose(st[0, sel], want[:, 0].mean(axis=0), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(st[5, sel], want[:, 1].max(axis=0), rtol=0, atol=1e-6)
