@@ -139,7 +139,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_threads()
-    ncol_s = args.cpu_sample_cols or max(64, 24 * cores)
+    ncol_s = args.cpu_sample_cols or max(256, 256 * cores)
     val, ms = oracle_rate(cores, ncol_s, args.hours, args.steps, args.warmup)
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -294,7 +294,7 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "nonfinite_columns": nonfinite}
         if not args.no_cpu_baseline and world == 1:
             cores = host_threads()
-            ncs = args.cpu_sample_cols or max(64, 24 * cores)
+            ncs = args.cpu_sample_cols or max(256, 256 * cores)
             cv, cms = oracle_rate(cores, ncs, hours, 2, 1)
             line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d columns x %d hourly steps x 2, OpenMP over columns; C++ restatement of the R path"
