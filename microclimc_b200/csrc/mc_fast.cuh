@@ -1204,8 +1204,8 @@ MC_NI void general_step(const FastArgs& a, const RunCfg& cfg, const FastLayout& 
 }
 
 // ABI state rows of one column from the working rows (state layout of include/microclimc_b200.h)
-MC_HD void abi_state_from_ws(const FastLayout& L, const double* P, const double* S, const double* W, const double* soilz /* soilp z rows */,
-                             long long soil_ld, double* st, long long ld) {
+MC_HD void abi_state_from_ws(const FastLayout& L, const double* __restrict__ P, const double* __restrict__ S, const double* __restrict__ W,
+                             const double* __restrict__ soilz /* soilp z rows */, long long soil_ld, double* __restrict__ st, long long ld) {
   const int m = L.m, sm = L.sm;
   auto g = [&](int r) { return S[(long long)r * kTile]; };
   auto w = [&](int r, double v) { st[(long long)r * ld] = v; };
@@ -1293,7 +1293,9 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
     // paraminit's z is the regular grid; a snapped node (reqhgt) makes the first step's previn$z differ (code.R:573, 719)
     for (int i = 1; i <= m; ++i) if ((i - 0.5) / m * hgt != P[(long long)L.pz(i) * kTile]) zdiff = true;
   } else {
-    auto st = [&](int r) { return t.state[(long long)r * t.ncol + c]; };
+    // (loads of the ABI state and stores of the working rows never alias: tell the compiler, so that it batches the loads)
+    const double* __restrict__ const stp = t.state + c;
+    auto st = [&](int r) { return stp[(long long)r * t.ncol]; };
     sput(S0_TABOVE, st(P_TABOVE)); sput(S0_RELHUM, st(P_RELHUM)); sput(S0_TAIR, st(P_TAIR)); sput(S0_TSOIL, st(P_TSOIL)); sput(S0_PK, st(P_PK));
     sput(S0_H, st(P_H)); sput(S0_PSIM, st(P_PSIM)); sput(S0_G, st(P_G));
     double tcs = 0;
