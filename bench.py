@@ -221,7 +221,9 @@ def main():
     # ---- e2e leg: same K steps through the C-ABI with host buffers (H2D forcing tile + perturbation, D2H stats/flags) ----
     ctx.spinup(args.spin)
     ctx.set_config(cfg0)
-    stats = np.zeros((6, ncol)); flags = np.zeros(ncol, dtype=np.int32)
+    # result buffers of the e2e leg: pinned host memory owned by the caller and reused every step, as a grid driver would
+    stats_p = torch.empty((6, ncol), dtype=torch.float64, pin_memory=True)
+    flags_p = torch.empty((ncol,), dtype=torch.int32, pin_memory=True)
     e2e_t = []
     for k in range(nsteps):
         if k == W:
@@ -230,7 +232,8 @@ def main():
         tile = f_p.numpy()[k * hours:(k + 1) * hours]
         ctx.set_forcing(tile, fs_p.numpy(), fo_p.numpy())
         # the tile is a window of the year: the column's mean air temperature (deep-soil boundary) is passed explicitly
-        rr = ctx.run_transient(0, hours, tsoil=tsoil_p.numpy(), want_series=False, want_stats=True, want_flags=True)
+        rr = ctx.run_transient(0, hours, tsoil=tsoil_p.numpy(), want_series=False, want_stats=True, want_flags=True,
+                               out_stats=stats_p.numpy(), out_flags=flags_p.numpy())
         torch.cuda.synchronize()
         if k >= W:
             e2e_t.append(time.perf_counter() - t0); launches += ctx.last_kernel_launches()

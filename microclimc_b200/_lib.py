@@ -134,7 +134,9 @@ class Context:
         self._chk(lib().mc_spinup(self._h, int(steps)))
 
     def run_transient(self, t0=0, t1=None, tsoil=None, samp_idx=None, want_series=True, want_full=False, want_stats=True,
-                      want_flags=True):
+                      want_flags=True, out_stats=None, out_flags=None):
+        """Steps [t0, t1) of the runmodel loop.  `out_stats` ([6][ncol] float64) / `out_flags` ([ncol] int32): caller-owned result
+        buffers to fill instead of fresh arrays (e.g. pinned memory reused across calls)."""
         t1 = self.T if t1 is None else t1
         nt = t1 - t0
         tsoil = _f(tsoil)
@@ -143,8 +145,12 @@ class Context:
             samp = np.ascontiguousarray(samp_idx, dtype=np.int64); ns = samp.size
         series = np.zeros((nt, 8, ns)) if (want_series and ns) else None
         full = np.zeros((nt, self.nstate, ns)) if (want_full and ns) else None
-        stats = np.zeros((6, self.ncol)) if want_stats else None
-        flags = np.zeros(self.ncol, dtype=np.int32) if want_flags else None
+        stats = (out_stats if out_stats is not None else np.zeros((6, self.ncol))) if want_stats else None
+        flags = (out_flags if out_flags is not None else np.zeros(self.ncol, dtype=np.int32)) if want_flags else None
+        if stats is not None:
+            assert stats.dtype == np.float64 and stats.shape == (6, self.ncol) and stats.flags["C_CONTIGUOUS"]
+        if flags is not None:
+            assert flags.dtype == np.int32 and flags.shape == (self.ncol,) and flags.flags["C_CONTIGUOUS"]
         self._chk(lib().mc_run_transient(self._h, t0, t1, _p(tsoil), _p(samp, PI64), ns, _p(series), _p(full), _p(stats),
                                          _p(flags, PI32)))
         return dict(series=series, full=full, stats=stats, flags=flags)
