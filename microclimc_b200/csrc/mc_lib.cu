@@ -107,6 +107,14 @@ __global__ void k_sol_rows(long long T, const double* rows, int stride, int jdco
   const SolDay d = sol_day(rows[t * stride + jdcol]);
   sol[t * 3] = d.eot; sol[t * 3 + 1] = d.sdec; sol[t * 3 + 2] = d.cdec;
 }
+// hour-only quantities of the steady path, once per hour instead of once per (column, hour)
+__global__ void k_steady_hour(long long T, const double* clim, double* out) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const HourPre h = hour_pre(clim + t * 9);
+  double* o = out + t * 6;
+  o[0] = h.sd.eot; o[1] = h.sd.sdec; o[2] = h.sd.cdec; o[3] = h.dp; o[4] = h.ph; o[5] = h.ph0;
+}
 __global__ void k_steady_reduce(long long ncol, int nchunk, long long T, const double* part, double* stats) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncol) return;
@@ -291,7 +299,7 @@ int launch_transient(Shard& s, const TransientArgs& a) {
 }
 int launch_steady(Shard& s, const SteadyArgs& a, int nchunk) {
   if (a.sol) {
-    k_sol_rows<<<nblocks(a.T), kBlock, 0, s.st>>>(a.T, a.clim, 9, 7, const_cast<double*>(a.sol));
+    k_steady_hour<<<nblocks(a.T), kBlock, 0, s.st>>>(a.T, a.clim, const_cast<double*>(a.sol));
     s.launches++;
   }
   dim3 grid(nblocks(a.ncol), nchunk);
@@ -642,7 +650,7 @@ int mc_run_steady(mc_ctx* ctx, int64_t T, const double* clim, const double* nmr,
     }
     CU(s.flags.need(sizeof(int) * s.nc)); a.flags = s.flags.as<int>();
     CU(cudaMemsetAsync(s.flags.p, 0, sizeof(int) * s.nc, s.st));
-    CU(s.ssol.need(sizeof(double) * T * 3)); a.sol = s.ssol.as<double>();
+    CU(s.ssol.need(sizeof(double) * T * 6)); a.sol = s.ssol.as<double>();
     CU(cudaEventRecord(s.e0, s.st));
     launch_steady(s, a, nchunk);
     CU(cudaEventRecord(s.e1, s.st));

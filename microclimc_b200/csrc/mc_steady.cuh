@@ -20,13 +20,28 @@ struct SteadyArgs {
   const double* nmr;         // [T][11] or [T][11][ncol]: D0cm, WC0cm, SNOWDEP(cm), SN1..SN8
   int nmr_percol;
   const double* season;      // [T] or null
-  const double* sol;         // [T][3] eot, sin(declination), cos(declination) per hour (k_steady_sol), or null: computed in place
+  const double* sol;         // [T][6] eot, sin / cos of the declination, dp, ph, ph0 per hour (k_steady_hour), or null: computed in place
   double reqhgt; int metopen; double windhgt, surfwet;
   double* out;               // [T][7][ncol] or null
   double* stats;             // [6][ncol] (written by the reduce kernel)
   double* part;              // [nchunk][6][ncol] partial sums/min/max, or null
   int* flags;                // [ncol]; bit 2: snow-layer lookup out of range
 };
+
+// What an hour's forcing row determines for every column: the date-only solar terms, the diffuse fraction and the molar
+// densities of air at the forcing pressure and at 101.3 kPa (k_steady_hour writes them once per hour; the same expressions
+// run in place when there is no table).
+struct HourPre { SolDay sd; double dp, ph, ph0; };
+MC_HD HourPre hour_pre(const double* cr) {
+  HourPre h;
+  h.sd = sol_day(cr[7]);
+  double dp = cr[5] / cr[4];                                   // difrad / swrad (IEEE division: 0/0 and x/0 are meaningful)
+  if (dp != dp) dp = 0.5;
+  if (isinf(dp)) dp = 0.5;
+  if (dp > 1) dp = 1;
+  h.dp = dp; h.ph = phair(cr[0], cr[2]); h.ph0 = phair(cr[0], 101.3);
+  return h;
+}
 
 template <int MM>
 struct SteadyCol {
@@ -240,7 +255,7 @@ struct SteadyCol {
   }
 
   // one hour without snow (runmodelS body, NMR.R:761-865); o[7] = Tloc, tleaf, RHloc, RSWloc, RLWloc, windspeed, dp
-  MC_HD void point(const SteadyArgs& A, const double* cr, const SolDay& sd, double tground, double theta, double* o) const {
+  MC_HD void point(const SteadyArgs& A, const double* cr, const HourPre& hp, double tground, double theta, double* o) const {
     const double reqhgt = A.reqhgt;
     const double tair = cr[0], relhum = cr[1], pk = cr[2], swrad = cr[4], skyem = cr[6];
     const double u2 = wind2m(A, cr[3], PAIt);
@@ -256,16 +271,14 @@ struct SteadyCol {
     if (psi_h < -2.5) psi_h = -2.5;
     const double uz = wind_apply(u2, wA, wB, wE);
     const double uh = fdiv(uf, 0.4) * lnh3;
-    double dp = cr[5] / swrad;
-    if (dp != dp) dp = 0.5;
-    if (isinf(dp)) dp = 0.5;
-    if (dp > 1) dp = 1;
-    const double ph = phair(tair, pk);
+    double dp = hp.dp;
+    const SolDay& sd = hp.sd;
+    const double ph = hp.ph;
     double gtt = gturb_apply(u2, gt_lnu, gt_lnh, ph, psi_m, psi_h);
     const double sa_l = solsin_pre(cr[8], lon, /*merid <- clump (Q15)*/ clump, 0, sd, slat, clat);
     double K_l, mul;
     cank2_sh(x, sa_l, kden, k5, K_l, mul);       // sa_l, sa: sin(solar altitude), see mc_phys.cuh
-    const double ph0 = phair(tair, 101.3);
+    const double ph0 = hp.ph0;
     double tz, tleaf, rh, Rsw;
     if (reqhgt >= hgt) {
       double gt0 = gcan_apply(l_m, iwmean, ph, uh, a, gc_top_den);
@@ -331,7 +344,7 @@ struct SteadyCol {
     return true;
   }
   // one hour with snow on the ground (.runmodelsnow body, NMR.R:514-677)
-  MC_HD bool point_snow(const SteadyArgs& A, const double* cr, const SolDay& sd, double snowdep_cm, const double* SN, double* o) const {
+  MC_HD bool point_snow(const SteadyArgs& A, const double* cr, const HourPre& hp, double snowdep_cm, const double* SN, double* o) const {
     const double reqhgt = A.reqhgt;
     const double snowtemp = SN[0];
     const double snowdep = snowdep_cm / 100;
@@ -355,11 +368,9 @@ struct SteadyCol {
     const bool below = reqhgt < snowdep;
     double tz2 = 0;
     if (below && !snowtempf(snowdep, SN, reqhgt, tz2)) return false;
-    double dp = cr[5] / swrad;
-    if (dp != dp) dp = 0.5;
-    if (isinf(dp)) dp = 0.5;
-    if (dp > 1) dp = 1;
-    const double ph = phair(tair, pk), ph0 = phair(tair, 101.3);
+    double dp = hp.dp;
+    const SolDay& sd = hp.sd;
+    const double ph = hp.ph, ph0 = hp.ph0;
     double gtt = gturb_apply(u2, gts_lnu, gts_lnh, ph, 0, 0);
     const double sa_l = solsin_pre(cr[8], lon, clump, 0, sd, slat, clat);
     double K_l, mul;
@@ -441,13 +452,15 @@ MC_HD void steady_column(const SteadyArgs& A, long long c, int chunk, int nchunk
     double nm[11];
     if (A.nmr_percol) { for (int q = 0; q < 11; ++q) nm[q] = A.nmr[(t * 11 + q) * A.ncol + c]; }
     else { for (int q = 0; q < 11; ++q) nm[q] = A.nmr[t * 11 + q]; }
-    SolDay sd;
-    if (A.sol) { sd.eot = A.sol[t * 3]; sd.sdec = A.sol[t * 3 + 1]; sd.cdec = A.sol[t * 3 + 2]; }
-    else sd = sol_day(cr[7]);
+    HourPre hp;
+    if (A.sol) {
+      const double* h = A.sol + t * 6;
+      hp.sd.eot = h[0]; hp.sd.sdec = h[1]; hp.sd.cdec = h[2]; hp.dp = h[3]; hp.ph = h[4]; hp.ph0 = h[5];
+    } else hp = hour_pre(cr);
     double o[7];
     if (nm[2] > 0) {                                             // NMR.R:873-883: snow rows come from .runmodelsnow
-      if (!col.point_snow(A, cr, sd, nm[2], nm + 3, o)) { flag |= 4; for (int q = 0; q < 7; ++q) o[q] = NAN; }
-    } else col.point(A, cr, sd, nm[0], nm[1], o);
+      if (!col.point_snow(A, cr, hp, nm[2], nm + 3, o)) { flag |= 4; for (int q = 0; q < 7; ++q) o[q] = NAN; }
+    } else col.point(A, cr, hp, nm[0], nm[1], o);
     if (A.out && live) for (int q = 0; q < 7; ++q) A.out[(t * 7 + q) * A.ncol + c] = o[q];
     st[0] += o[0]; if (o[0] < st[1]) st[1] = o[0]; if (o[0] > st[2]) st[2] = o[0];
     st[3] += o[1]; if (o[1] < st[4]) st[4] = o[1]; if (o[1] > st[5]) st[5] = o[1];
