@@ -20,7 +20,7 @@ struct SteadyArgs {
   const double* nmr;         // [T][11] or [T][11][ncol]: D0cm, WC0cm, SNOWDEP(cm), SN1..SN8
   int nmr_percol;
   const double* season;      // [T] or null
-  const double* sol;         // [T][6] eot, sin / cos of the declination, dp, ph, ph0 per hour (k_steady_hour), or null: computed in place
+  const double* sol;         // [T][10] eot, sin / cos of the declination, dp, ph, ph0, es, eref, cp, (tair + 273.15)^4 per hour (k_steady_hour), or null: computed in place
   double reqhgt; int metopen; double windhgt, surfwet;
   double* out;               // [T][7][ncol] or null
   double* stats;             // [6][ncol] (written by the reduce kernel)
@@ -31,7 +31,7 @@ struct SteadyArgs {
 // What an hour's forcing row determines for every column: the date-only solar terms, the diffuse fraction and the molar
 // densities of air at the forcing pressure and at 101.3 kPa (k_steady_hour writes them once per hour; the same expressions
 // run in place when there is no table).
-struct HourPre { SolDay sd; double dp, ph, ph0; };
+struct HourPre { SolDay sd; double dp, ph, ph0, es, eref, cp, p4; };   // es = satvap(tair), eref = relhum/100 * es, cp = cpair(tair), p4 = (tair + 273.15)^4
 MC_HD HourPre hour_pre(const double* cr) {
   HourPre h;
   h.sd = sol_day(cr[7]);
@@ -40,6 +40,7 @@ MC_HD HourPre hour_pre(const double* cr) {
   if (isinf(dp)) dp = 0.5;
   if (dp > 1) dp = 1;
   h.dp = dp; h.ph = phair(cr[0], cr[2]); h.ph0 = phair(cr[0], 101.3);
+  h.es = satvap(cr[0]); h.eref = fdiv(cr[1], 100) * h.es; h.cp = cpair(cr[0]); h.p4 = pow4(cr[0] + 273.15);
   return h;
 }
 
@@ -179,13 +180,13 @@ struct SteadyCol {
   }
   // .leafabs2 (NMR.R:361-376) with merid <- clump (Q15), clump = 0
   MC_HD double leafabs2(double Rsw, double sa, double K, double mul, double tair, double PAIt_, double PAIu_, double refv, double srefv,
-                        double trdu, double trdt, double refgv, double emvv, double trlwu, double skyem, double dp) const {
+                        double trdu, double trdt, double refgv, double emvv, double trlwu, double skyem, double dp, double p4) const {
     double sunl = psunlit_k(PAIu_, sa, K, 0.0);
     double aRsw = (1 - refv) * cansw_k(Rsw, dp, sa, PAIu_, srefv, trdu, K, 0.0);
     double aGround = refgv * cansw_k(Rsw, dp, sa, PAIt_, srefv, trdt, K, 0.0);
     aGround = (1 - refv) * cansw_k(aGround, dp, sa, PAIt_, srefv, trdt, K, 0.0);
     aRsw = sunl * mul * aRsw + (1 - sunl) * aRsw + aGround;
-    double lwout = kSb * pow4(tair + 273.15);
+    double lwout = kSb * p4;
     double lwin = trlwu * skyem * lwout + (1 - trlwu) * emvv * lwout;
     return aRsw + emvv * lwin;
   }
@@ -194,17 +195,17 @@ struct SteadyCol {
   // tleafS (NMR.R:432-493)
   MC_HD static void tleafS(double tair, double tground, double relhum, double pk, double theta, double gtt, double gt0, double gha,
                            double gv, double gL, double Rabs, double vegemv, double soilbv, double Psie, double Smaxv, double surfwet,
-                           double leafd, double& tleaf, double& tn, double& rh) {
-    double cp = cpair(tair);
+                           double leafd, const HourPre& hp, double& tleaf, double& tn, double& rh) {
+    double cp = hp.cp;
     double gs = gtt + gt0;
     const double igs = frcp(gs);
     double aL = (gtt * (tair + 273.15) + gt0 * (tground + 273.15)) * igs;
     double bL = (leafd * gL) * igs;
-    double es = satvap(tair);
-    double eref = fdiv(relhum, 100) * es;
+    double es = hp.es;
+    double eref = hp.eref;
     double esoil = soilrh(theta, soilbv, Psie, Smaxv, tground) * satvap(tground);
     double tk = tair + 273.15;
-    double Rnet = Rabs - 0.97 * kSb * pow4(tk);
+    double Rnet = Rabs - 0.97 * kSb * hp.p4;
     double tle = tair + fdiv(0.5 * Rnet, cp * gha);
     double wgt1 = leafd < 1 ? leafd / 2 : 1 - fdiv(0.5, leafd);
     double tapprox = wgt1 * tle + (1 - wgt1) * tair;
@@ -261,7 +262,7 @@ struct SteadyCol {
     const double u2 = wind2m(A, cr[3], PAIt);
     const double uf = fdiv(0.4 * u2, lnuf);
     const double tk = tair + 273.15;
-    double Rlw = (1 - skyem) * kSb * vegem * pow4(tk);
+    double Rlw = (1 - skyem) * kSb * vegem * hp.p4;
     const double Hh = 0.2 * ((1 - 0.23) * swrad - Rlw);
     double psi_m, psi_h;
     diabatic_cor(tair, pk, Hh, uf, hgt + 2, d, psi_m, psi_h);
@@ -286,14 +287,14 @@ struct SteadyCol {
       double gC = layercond(swrad, gsmax, q50);
       double gv = hpar(gC, gha);
       double gL = hpar(gha, ph0 * uh);
-      double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt, 0.0, ref, sref, 1.0, trd_t, refg, emv, 1.0, skyem, dp);
+      double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt, 0.0, ref, sref, 1.0, trd_t, refg, emv, 1.0, skyem, dp, hp.p4);
       double tn, rhn;
-      tleafS(tair, tground, relhum, pk, theta, gtt, gt0, gha, gv, gL, Rabs, vegem, soilb, psi_e, Smax, A.surfwet, leafdens, tleaf, tn, rhn);
+      tleafS(tair, tground, relhum, pk, theta, gtt, gt0, gha, gv, gL, Rabs, vegem, soilb, psi_e, Smax, A.surfwet, leafdens, hp, tleaf, tn, rhn);
       if (reqhgt == hgt) { tz = tn; rh = rhn; }
       else {
         double gtc = gturb_apply(u2, gt_lnu, gtc_lnh, ph, psi_m, psi_h);
         double gt2 = 1 / (1 / gtt - 1 / gtc);
-        double eref = fdiv(relhum, 100) * satvap(tair);
+        double eref = hp.eref;
         double ecan = fdiv(rhn, 100) * satvap(tn);
         double ea = (gt2 * eref + gtc * ecan) / (gt2 + gtc);          // (gt2 may be +-Inf when gtt == gtc: IEEE division kept)
         tz = (gt2 * tair + gtc * tn) / (gt2 + gtc);
@@ -312,8 +313,8 @@ struct SteadyCol {
       double gC = layercond(PAR, gsmax, q50);
       double gv = hpar(gC, gha);
       double gL = hpar(gha, ph0 * uz);
-      double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt, PAIu, ref, sref, trd_u, trd_t, refg, emv, trlw_u, skyem, dp);
-      tleafS(tair, tground, relhum, pk, theta, gtt, gt0, gha, gv, gL, Rabs, vegem, soilb, psi_e, Smax, A.surfwet, leafdens, tleaf, tz, rh);
+      double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt, PAIu, ref, sref, trd_u, trd_t, refg, emv, trlw_u, skyem, dp, hp.p4);
+      tleafS(tair, tground, relhum, pk, theta, gtt, gt0, gha, gv, gL, Rabs, vegem, soilb, psi_e, Smax, A.surfwet, leafdens, hp, tleaf, tz, rh);
       Rsw = cansw_k(swrad, dp, sa, PAIu, sls, trdls, K, 0.0);
       double Rdif = cdif * swrad * dp;
       dp = Rdif / Rsw;
@@ -322,7 +323,7 @@ struct SteadyCol {
       if (dp < 0) dp = 0;
       if (dp > 1) dp = 1;
       double tr = clumptr(fexp(-slw * PAIu), clump);
-      double lwout = kSb * pow4(tk);
+      double lwout = kSb * hp.p4;
       Rlw = tr * skyem * lwout + (1 - tr) * emv * lwout;
     }
     o[0] = tz; o[1] = tleaf; o[2] = rh; o[3] = Rsw; o[4] = Rlw; o[5] = uz; o[6] = dp;
@@ -384,14 +385,14 @@ struct SteadyCol {
       double gC = layercond(swrad, gsmax, q50);
       double gv = hpar(gC, gha);
       double gL = hpar(gha, ph0 * uh);
-      double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt_s, 0.0, ref_s, sref_s, 1.0, trds_t, 0.95, emv85, 1.0, skyem, dp);
+      double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt_s, 0.0, ref_s, sref_s, 1.0, trds_t, 0.95, emv85, 1.0, skyem, dp, hp.p4);
       double tn, rhn;
-      tleafS(tair, snowtemp, relhum, pk, 0.5, gtt, gt0, gha, gv, gL, Rabs, 0.85, soilb, psi_e, Smax, 1, leafdens_s, tleaf, tn, rhn);
+      tleafS(tair, snowtemp, relhum, pk, 0.5, gtt, gt0, gha, gv, gL, Rabs, 0.85, soilb, psi_e, Smax, 1, leafdens_s, hp, tleaf, tn, rhn);
       if (reqhgt == hgt) { tz = tn; rh = rhn; }
       else {
         double gtc = gturb_apply(u2, gts_lnu, gtcs_lnh, ph, 0, 0);
         double gt2 = 1 / (1 / gtt - 1 / gtc);
-        double eref = fdiv(relhum, 100) * satvap(tair);
+        double eref = hp.eref;
         double ecan = fdiv(rhn, 100) * satvap(tn);
         double ea = (gt2 * eref + gtc * ecan) / (gt2 + gtc);          // (gt2 may be +-Inf when gtt == gtc: IEEE division kept)
         tz = (gt2 * tair + gtc * tn) / (gt2 + gtc);
@@ -412,8 +413,8 @@ struct SteadyCol {
       double gv = hpar(gC, gha);
       double gL = hpar(gha, ph0 * uz);
       double trlw = clumptr(fexp(-fsqrt(emv85) * PAIu), 0.0);
-      double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt_s, PAIu, ref_s, sref_s, trds_u, trds_t, 0.95, emv85, trlw, skyem, dp);
-      tleafS(tair, snowtemp, relhum, pk, 0.5, gtt, gt0, gha, gv, gL, Rabs, vegem, soilb, psi_e, Smax, 1, leafdens_s, tleaf, tz, rh);
+      double Rabs = leafabs2(swrad, sa_l, K_l, mul, tair, PAIt_s, PAIu, ref_s, sref_s, trds_u, trds_t, 0.95, emv85, trlw, skyem, dp, hp.p4);
+      tleafS(tair, snowtemp, relhum, pk, 0.5, gtt, gt0, gha, gv, gL, Rabs, vegem, soilb, psi_e, Smax, 1, leafdens_s, hp, tleaf, tz, rh);
       Rsw = cansw_k(swrad, dp, sa, PAIu, s95, trd95, K, 0.0);
       double Rdif = cdif95 * swrad * dp;
       dp = Rdif / Rsw;
@@ -421,7 +422,7 @@ struct SteadyCol {
       if (isinf(dp)) dp = 1;
       if (dp < 0) dp = 0;
       if (dp > 1) dp = 1;
-      double lwout = kSb * pow4(tk);
+      double lwout = kSb * hp.p4;
       Rlw = trlw85_u * skyem * lwout + (1 - trlw85_u) * (1 - 0.85) * lwout;     // canlw(tair, PAIu, 0.85, ...): 0.85 passed as `ref`
     }
     if (below) { tz = tz2; tleaf = tz2; rh = 100; uz = 0; Rsw = 0; Rlw = kSb * 0.85 * pow4(tz2 + 273.15); }
@@ -454,8 +455,9 @@ MC_HD void steady_column(const SteadyArgs& A, long long c, int chunk, int nchunk
     else { for (int q = 0; q < 11; ++q) nm[q] = A.nmr[t * 11 + q]; }
     HourPre hp;
     if (A.sol) {
-      const double* h = A.sol + t * 6;
+      const double* h = A.sol + t * 10;
       hp.sd.eot = h[0]; hp.sd.sdec = h[1]; hp.sd.cdec = h[2]; hp.dp = h[3]; hp.ph = h[4]; hp.ph0 = h[5];
+      hp.es = h[6]; hp.eref = h[7]; hp.cp = h[8]; hp.p4 = h[9];
     } else hp = hour_pre(cr);
     double o[7];
     if (nm[2] > 0) {                                             // NMR.R:873-883: snow rows come from .runmodelsnow
