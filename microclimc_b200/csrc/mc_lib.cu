@@ -113,9 +113,9 @@ __global__ void k_steady_hour(long long T, const double* clim, double* out) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   const HourPre h = hour_pre(clim + t * 9);
-  double* o = out + t * 10;
+  double* o = out + t * 13;
   o[0] = h.sd.eot; o[1] = h.sd.sdec; o[2] = h.sd.cdec; o[3] = h.dp; o[4] = h.ph; o[5] = h.ph0;
-  o[6] = h.es; o[7] = h.eref; o[8] = h.cp; o[9] = h.p4;
+  o[6] = h.es; o[7] = h.eref; o[8] = h.cp; o[9] = h.p4; o[10] = h.gDh; o[11] = h.ginu; o[12] = h.ggq;
 }
 __global__ void k_steady_reduce(long long ncol, int nchunk, long long T, const double* part, double* stats) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -652,7 +652,7 @@ int mc_run_steady(mc_ctx* ctx, int64_t T, const double* clim, const double* nmr,
     }
     CU(s.flags.need(sizeof(int) * s.nc)); a.flags = s.flags.as<int>();
     CU(cudaMemsetAsync(s.flags.p, 0, sizeof(int) * s.nc, s.st));
-    CU(s.ssol.need(sizeof(double) * T * 10)); a.sol = s.ssol.as<double>();
+    CU(s.ssol.need(sizeof(double) * T * 13)); a.sol = s.ssol.as<double>();
     CU(cudaEventRecord(s.e0, s.st));
     launch_steady(s, a, nchunk);
     CU(cudaEventRecord(s.e1, s.st));

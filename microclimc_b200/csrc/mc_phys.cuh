@@ -271,6 +271,8 @@ MC_HD double gturb(double u, double zu, double z1, double z0, double hgt, double
   if (den < 0.25 * lnh) den = 0.25 * lnh;
   return (0.4 * phair(tc, pk) * uf) / den;
 }
+// Prandtl number of air in gforcedfree: nu / Dh = 13.3 / 18.9 exactly (both carry the same temperature / pressure factor)
+constexpr double kPrAir = 0.7037037037037037, kCbrtPrAir = 0.8894672162406483;
 MC_HD double gforcedfree(double d, double u, double tc, double dtc, double pk, double dtmin) {
   double Tk = tc + 273.15;
   double ph = phair(tc, pk);

@@ -20,7 +20,7 @@ struct SteadyArgs {
   const double* nmr;         // [T][11] or [T][11][ncol]: D0cm, WC0cm, SNOWDEP(cm), SN1..SN8
   int nmr_percol;
   const double* season;      // [T] or null
-  const double* sol;         // [T][10] eot, sin / cos of the declination, dp, ph, ph0, es, eref, cp, (tair + 273.15)^4 per hour (k_steady_hour), or null: computed in place
+  const double* sol;         // [T][13] eot, sin / cos of the declination, dp, ph, ph0, es, eref, cp, (tair + 273.15)^4, gDh, ginu, ggq per hour (k_steady_hour), or null: computed in place
   double reqhgt; int metopen; double windhgt, surfwet;
   double* out;               // [T][7][ncol] or null
   double* stats;             // [6][ncol] (written by the reduce kernel)
@@ -31,7 +31,7 @@ struct SteadyArgs {
 // What an hour's forcing row determines for every column: the date-only solar terms, the diffuse fraction and the molar
 // densities of air at the forcing pressure and at 101.3 kPa (k_steady_hour writes them once per hour; the same expressions
 // run in place when there is no table).
-struct HourPre { SolDay sd; double dp, ph, ph0, es, eref, cp, p4; };   // es = satvap(tair), eref = relhum/100 * es, cp = cpair(tair), p4 = (tair + 273.15)^4
+struct HourPre { SolDay sd; double dp, ph, ph0, es, eref, cp, p4, gDh, ginu, ggq; };   // es = satvap(tair), eref = relhum/100 * es, cp = cpair(tair), p4 = (tair + 273.15)^4
 MC_HD HourPre hour_pre(const double* cr) {
   HourPre h;
   h.sd = sol_day(cr[7]);
@@ -41,6 +41,13 @@ MC_HD HourPre hour_pre(const double* cr) {
   if (dp > 1) dp = 1;
   h.dp = dp; h.ph = phair(cr[0], cr[2]); h.ph0 = phair(cr[0], 101.3);
   h.es = satvap(cr[0]); h.eref = fdiv(cr[1], 100) * h.es; h.cp = cpair(cr[0]); h.p4 = pow4(cr[0] + 273.15);
+  {                                                            // hour-only pieces of gforcedfree (leaf boundary-layer conductance)
+    const double Tk = cr[0] + 273.15;
+    const double sc = pow175(Tk * (1 / 273.15)) * fdiv(101.3, cr[2]);
+    h.gDh = 18.9e-6 * sc;
+    h.ginu = frcp(13.3e-6 * sc);
+    h.ggq = frcp(Tk) * (h.ginu * h.ginu);
+  }
   return h;
 }
 
@@ -54,6 +61,7 @@ struct SteadyCol {
   double wA, wB, wE;            // .windprofile factors: ln(zi), ln(zo or hgt), exp term
   double gt_lnu, gt_lnh, gtc_lnh;   // gturb pieces for z1 = hgt+2 and z1 = reqhgt
   double gc_top_den, gc_c_den, gc_0_den;   // hgt*(e0-e1) of the three gcanopy calls
+  double gd, gid, gd3a, gd_s, gid_s, gd3a_s;   // leaf dimension d = 0.71 lw (twice that under snow), 1/d, 9.81 d^3 * 5
   double ref, sref, kden, k5, emv, slw, trd_u, trd_t, trlw_u;
   double s02, trd02, sls, trdls, cdif;     // PAR (ref 0.2) and Rsw (ref refls) transmissions, cantransdif
   double merid_def;
@@ -117,6 +125,8 @@ struct SteadyCol {
     sref = sqrt(1 - ref);
     kden = cank_den(x);
     k5 = cank(x, 5.0, kden);
+    gd = lw * 0.71; gid = 1 / gd; gd3a = (9.81 * (gd * gd * gd)) * 5;
+    gd_s = lw * 2 * 0.71; gid_s = 1 / gd_s; gd3a_s = (9.81 * (gd_s * gd_s * gd_s)) * 5;
     emv = 1 - (1 - vegem);
     slw = sqrt(emv);
     trd_u = clumptr(exp(-sref * PAIu), 0.0);            // Q15: clump lands in `merid`; cansw/canlw see clump = 0
@@ -189,6 +199,15 @@ struct SteadyCol {
     double lwout = kSb * p4;
     double lwin = trlwu * skyem * lwout + (1 - trlwu) * emvv * lwout;
     return aRsw + emvv * lwin;
+  }
+  // 1.41 * gforcedfree(d, u, tair, 5, pk, 5) with its hour-only pieces from HourPre and its column-only pieces (d, 1/d,
+  // 9.81 d^3 * 5) from prep(): same formula as mc_phys.cuh gforcedfree in product form (as gha_fast of the streaming kernel)
+  MC_HD static double gha_hour(double d, double id, double d3a, double u, const HourPre& hp) {
+    const double Re = (u * d) * hp.ginu;
+    const double Gr = d3a * hp.ggq;
+    const double gforced = (0.664 * hp.gDh * hp.ph * fsqrt(Re) * kCbrtPrAir) * id;
+    const double gfree = (0.54 * hp.gDh * hp.ph * qroot(Gr * kPrAir)) * id;
+    return 1.41 * ((gforced > gfree) ? gforced : gfree);
   }
   // 1 / (1/a + 1/b) as a*b / (a+b): one division; a == 0 (closed stomata at night) still gives 0 as the IEEE form does
   MC_HD static double hpar(double a, double b) { return fdiv(a * b, a + b); }
@@ -283,7 +302,7 @@ struct SteadyCol {
     double tz, tleaf, rh, Rsw;
     if (reqhgt >= hgt) {
       double gt0 = gcan_apply(l_m, iwmean, ph, uh, a, gc_top_den);
-      double gha = 1.41 * gforcedfree(lw * 0.71, uh, tair, 5, pk, 5);
+      double gha = gha_hour(gd, gid, gd3a, uh, hp);
       double gC = layercond(swrad, gsmax, q50);
       double gv = hpar(gC, gha);
       double gL = hpar(gha, ph0 * uh);
@@ -306,7 +325,7 @@ struct SteadyCol {
       double gtc = gcan_apply(l_m, iwmean, ph, uh, a, gc_c_den);
       gtt = hpar(gtt, gtc);
       double gt0 = gcan_apply(l_m, iwmean, ph, uh, a, gc_0_den);
-      double gha = 1.41 * gforcedfree(lw * 0.71, uz, tair, 5, pk, 5);
+      double gha = gha_hour(gd, gid, gd3a, uz, hp);
       double sa = solsin_pre(cr[8], lon, merid_def, 0, sd, slat, clat);
       double K = (sa > 0) ? cank_sh(x, sa, kden) : 0.0;
       double PAR = cansw_k(swrad, dp, sa, PAIu, s02, trd02, K, 0.0);
@@ -381,7 +400,7 @@ struct SteadyCol {
     double tz, tleaf, rh, Rsw, Rlw;
     if (reqhgt >= hgt) {
       double gt0 = gcan_apply(l_m_s, iwmean, ph, uh, a1, gcs_top_den);
-      double gha = 1.41 * gforcedfree(lw * 2 * 0.71, uh, tair, 5, pk, 5);
+      double gha = gha_hour(gd_s, gid_s, gd3a_s, uh, hp);
       double gC = layercond(swrad, gsmax, q50);
       double gv = hpar(gC, gha);
       double gL = hpar(gha, ph0 * uh);
@@ -405,7 +424,7 @@ struct SteadyCol {
       double gtc = gcan_apply(l_m_s, iwmean, ph, uh, a1, gcs_c_den);
       gtt = hpar(gtt, gtc);
       double gt0 = gcan_apply(l_m_s, iwmean, ph, uh, a1, gcs_0_den);
-      double gha = 1.41 * gforcedfree(lw * 0.71 * 2, uz, tair, 5, pk, 5);
+      double gha = gha_hour(gd_s, gid_s, gd3a_s, uz, hp);
       double sa = solsin_pre(cr[8], lon, merid_def, 0, sd, slat, clat);
       double K = (sa > 0) ? cank_sh(x, sa, kden) : 0.0;
       double PAR = cansw_k(swrad, dp, sa, PAIu, s06, trd06, K, 0.0);
@@ -455,9 +474,9 @@ MC_HD void steady_column(const SteadyArgs& A, long long c, int chunk, int nchunk
     else { for (int q = 0; q < 11; ++q) nm[q] = A.nmr[t * 11 + q]; }
     HourPre hp;
     if (A.sol) {
-      const double* h = A.sol + t * 10;
+      const double* h = A.sol + t * 13;
       hp.sd.eot = h[0]; hp.sd.sdec = h[1]; hp.sd.cdec = h[2]; hp.dp = h[3]; hp.ph = h[4]; hp.ph0 = h[5];
-      hp.es = h[6]; hp.eref = h[7]; hp.cp = h[8]; hp.p4 = h[9];
+      hp.es = h[6]; hp.eref = h[7]; hp.cp = h[8]; hp.p4 = h[9]; hp.gDh = h[10]; hp.ginu = h[11]; hp.ggq = h[12];
     } else hp = hour_pre(cr);
     double o[7];
     if (nm[2] > 0) {                                             // NMR.R:873-883: snow rows come from .runmodelsnow
