@@ -65,6 +65,7 @@ struct SteadyCol {
   double ref, sref, kden, k5, emv, slw, trd_u, trd_t, trlw_u;
   double s02, trd02, sls, trdls, cdif;     // PAR (ref 0.2) and Rsw (ref refls) transmissions, cantransdif
   double merid_def;
+  bool same_merid;
   // snow variants
   double a1, a2, PAIt_s, pLAI_s, zm3_s, d_s, wA1, wB1, wE1, wB2, leafdens_s, gts_lnu, gts_lnh, gtcs_lnh, gcs_top_den, gcs_c_den,
       gcs_0_den, l_m_s, trds_u, trds_t, s06, trd06, s95, trd95, cdif95, trlw85_u, sref_s, ref_s;
@@ -136,6 +137,7 @@ struct SteadyCol {
     sls = sqrt(1 - refls); trdls = exp(-sls * PAIu);
     cdif = exp(-sqrt(1 - refls) * PAIu);
     merid_def = nearbyint(lon / 15) * 15;
+    same_merid = (lon - merid_def) == (lon - clump);       // what solsin_pre sees of the meridian
     // ---- snow-surface variants (.runmodelsnow, NMR.R:514-677) ----
     PAIt_s = PAIt < 0.001 ? 0.001 : PAIt;
     pLAI_s = LAI / PAIt_s; if (pLAI_s != pLAI_s) pLAI_s = 0.8;
@@ -326,8 +328,13 @@ struct SteadyCol {
       gtt = hpar(gtt, gtc);
       double gt0 = gcan_apply(l_m, iwmean, ph, uh, a, gc_0_den);
       double gha = gha_hour(gd, gid, gd3a, uz, hp);
-      double sa = solsin_pre(cr[8], lon, merid_def, 0, sd, slat, clat);
-      double K = (sa > 0) ? cank_sh(x, sa, kden) : 0.0;
+      // second solar position (default meridian; the first one carries quirk Q15): the same numbers whenever the two meridians
+      // coincide (clump = 0 and |long| < 7.5 degrees, e.g.), then reused instead of recomputed
+      double sa = sa_l, K = K_l;
+      if (!same_merid) {
+        sa = solsin_pre(cr[8], lon, merid_def, 0, sd, slat, clat);
+        K = (sa > 0) ? cank_sh(x, sa, kden) : 0.0;
+      }
       double PAR = cansw_k(swrad, dp, sa, PAIu, s02, trd02, K, 0.0);
       double gC = layercond(PAR, gsmax, q50);
       double gv = hpar(gC, gha);
@@ -425,8 +432,13 @@ struct SteadyCol {
       gtt = hpar(gtt, gtc);
       double gt0 = gcan_apply(l_m_s, iwmean, ph, uh, a1, gcs_0_den);
       double gha = gha_hour(gd_s, gid_s, gd3a_s, uz, hp);
-      double sa = solsin_pre(cr[8], lon, merid_def, 0, sd, slat, clat);
-      double K = (sa > 0) ? cank_sh(x, sa, kden) : 0.0;
+      // second solar position (default meridian; the first one carries quirk Q15): the same numbers whenever the two meridians
+      // coincide (clump = 0 and |long| < 7.5 degrees, e.g.), then reused instead of recomputed
+      double sa = sa_l, K = K_l;
+      if (!same_merid) {
+        sa = solsin_pre(cr[8], lon, merid_def, 0, sd, slat, clat);
+        K = (sa > 0) ? cank_sh(x, sa, kden) : 0.0;
+      }
       double PAR = cansw_k(swrad, dp, sa, PAIu, s06, trd06, K, 0.0);
       double gC = layercond(PAR, gsmax, q50);
       double gv = hpar(gC, gha);

@@ -139,6 +139,10 @@ STEADY_VARIANTS = {
     "above_canopy": dict(reqhgt=17.0),
     "met_station_above_canopy": dict(metopen=0.0, windhgt=19.0),
     "dry_surface_low_emissivity": dict(surfwet=0.2, groundem=0.9),
+    # site keys (not run-description keys): the two solar positions of runmodelS differ when the default meridian differs from
+    # `clump` (quirk Q15 puts clump where merid belongs)
+    "other_longitude_and_latitude": dict(lon=18.0, lat=-33.0),
+    "clumped_canopy": dict(clump=0.35),
 }
 
 
@@ -146,9 +150,9 @@ STEADY_VARIANTS = {
 @pytest.mark.parametrize("snow", [False, True])
 def test_steady_variants(oracle, name, snow):
     from microclimc_b200._lib import Context
-    kw = dict(reqhgt=1.0, metopen=1.0, windhgt=2.0, surfwet=1.0, groundem=0.95); kw.update(STEADY_VARIANTS[name])
+    kw = dict(reqhgt=1.0, metopen=1.0, windhgt=2.0, surfwet=1.0, groundem=0.95, lon=-5.0, lat=50.0, clump=0.0); kw.update(STEADY_VARIANTS[name])
     scfg = np.array([kw[k] for k in L.STEADY_CFG], float)
-    veg, so = S.ensemble(S.vegp_deciduous(), loam(oracle), NCOL, M, SM, seed=5)
+    veg, so = S.ensemble(dict(S.vegp_deciduous(), clump=kw["clump"]), loam(oracle), NCOL, M, SM, seed=5)
     w = S.load_weather()
     clim = S.steady_clim_from_climdata(w)[:240]
     rng = np.random.default_rng(2)
@@ -156,7 +160,7 @@ def test_steady_variants(oracle, name, snow):
     if snow:
         nmr[:, 2] = np.where(clim[:, 0] < 6, rng.uniform(1, 250, 240), 0.0)       # cm; some hours bury the output height
         nmr[:, 3:] = rng.uniform(-9, 0, (240, 8))
-    lat = np.full(NCOL, 50.0); lon = np.full(NCOL, -5.0)
+    lat = np.full(NCOL, kw["lat"]); lon = np.full(NCOL, kw["lon"])
     want = oracle.run_steady(veg, so, clim, nmr, lat, lon, scfg, M, SM)["out"]
     ctx = Context(M, SM)
     ctx.set_columns(veg, so, lat, lon)
