@@ -6,7 +6,7 @@ The year is run the way a grid user would run it: one `run_transient` call per w
 per-column statistics reduced on the device per call and combined over the year on the host), the hourly series of a sample of columns read back, and that sample compared
 with the CPU oracle over the whole year (tolerances of the north_star: 1e-6 K, 1e-8 relative).  Prints one JSON line.
 
-  python tools/bench_year.py [--columns 1000000] [--hours 8760] [--chunk 168] [--check 32]
+  python tools/bench_year.py [--columns 1000000] [--hours 8760] [--chunk 168] [--check 32] [--gpus 1]
 """
 import argparse
 import json
@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=168)
     ap.add_argument("--spin", type=int, default=200)
     ap.add_argument("--check", type=int, default=32, help="columns compared with the CPU oracle over the whole year")
+    ap.add_argument("--gpus", type=int, default=1, help="GPUs of this box used IN PROCESS (static column split, one host thread per GPU)")
     a = ap.parse_args()
     from microclimc_b200._lib import Context
     M, SM = B.M, B.SM
@@ -35,7 +36,7 @@ def main():
     cfg = B.make_cfg(w["ts"], a.spin)
     nchk = min(a.check, a.columns)
     samp = np.unique(np.linspace(0, a.columns - 1, nchk).astype(np.int64))
-    ctx = Context(M, SM, 1, [0])
+    ctx = Context(M, SM, a.gpus, list(range(a.gpus)))
     t_wall0 = time.perf_counter()
     ctx.set_columns(w["veg"], w["soil"], w["lat"], w["lon"])
     ctx.set_forcing(w["f"], w["fs"], w["fo"])
@@ -62,7 +63,7 @@ def main():
     stats[[0, 3]] /= a.hours
     flags = r["flags"]
     colsteps = float(a.columns) * (a.hours + a.spin)
-    out = {"workload": "C3 full year", "columns": a.columns, "hours": a.hours, "spin_steps": a.spin, "chunk_hours": a.chunk,
+    out = {"workload": "C3 full year", "n_gpus_in_process": a.gpus, "columns": a.columns, "hours": a.hours, "spin_steps": a.spin, "chunk_hours": a.chunk,
            "device_s": dev_ms * 1e-3, "wall_s_incl_upload_and_readback": wall, "first_call_ms_incl_spinup": spin_ms,
            "column_timesteps": colsteps, "column_timesteps_per_s_device": colsteps / (dev_ms * 1e-3),
            "column_timesteps_per_s_wall": colsteps / wall, "kernel_launches": launches,
