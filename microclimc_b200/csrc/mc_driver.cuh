@@ -37,6 +37,12 @@ struct TransientArgs {
   int spin_steps;            // > 0: paraminit + spinup before the loop (state input ignored)
   int charmode;              // reqhgt "all"/"allclim"
   int spin_standalone;       // spin-up called as spinup() itself: keeps reqhgt, zlafact, surfwet (no Q22 / spinhgt mapping)
+  int flag_or;               // OR-ed into every flags[] entry this launch writes (8: the column left the streaming form)
+  // general time-varying vegetation (.vegpsort, code.R:904-916): per step PAI[m], pLAI[m], zm0, shared by all columns (nvt == 1)
+  // or per column (nvt == ncol); null: time-invariant (or `season`)
+  const double* vegt;        // [T][2m+1][nvt]
+  long long nvt;
+  const double* thetaz;      // [T][sm] soil moisture by depth (theta matrix of runmodel, code.R:1146-1154) or null
 };
 
 MC_HD void forcing_at(const TransientArgs& a, long long t, long long c, double* f) {
@@ -133,7 +139,7 @@ MC_HD void run_column(const TransientArgs& a, long long c, bool live = true) {
     a.stats[0 * a.ncol + c] = st[0] / n; a.stats[1 * a.ncol + c] = st[1]; a.stats[2 * a.ncol + c] = st[2];
     a.stats[3 * a.ncol + c] = st[3] / n; a.stats[4 * a.ncol + c] = st[4]; a.stats[5 * a.ncol + c] = st[5];
   }
-  if (a.flags) a.flags[c] = flag;
+  if (a.flags) a.flags[c] = flag | a.flag_or;
   col.store_state(a.state, a.ncol, c);
 }
 

@@ -1,7 +1,12 @@
 // Streaming form of the transient step (runonestep, R/code.R:687-902) for the configuration the BASELINE workloads run:
 // time-invariant PAI, at most kNG merged canopy air layers (hourly steps give 1-5), regular wind edge profile.
-// Columns that leave that envelope at some step (many merged layers at very short time steps, state whose node
-// heights differ from the current geometry) take that step through the general `Column::step` (mc_step.cuh).
+// A column that leaves that envelope at some step (many merged layers at very short time steps, lowest nodes under 0.12 m with
+// the edge profile) is dropped from the streaming launch: the kernel records it in a fail list, stops storing for it, and the
+// library re-runs the listed columns from the launch's initial state through the general kernel (k_transient, mc_step.cuh)
+// right after — the general column is NOT part of this kernel (it used to be: 14 KB stack frame, and its call boundary pinned
+// the register allocation of the hot loop).  A state whose node heights differ from the current geometry (first step after
+// paraminit when reqhgt snaps a node, code.R:573 vs 719) stays in the streaming form: the leaf-geometry rows are built from
+// previn$z for the first step and rebuilt in place from the current heights after it (fast_regeom).
 //
 // Why a second form: the general column keeps ~16 KB of thread-private state + hoisted geometry + work arrays and is
 // bound by local-memory latency (profiles/README.md r01b: long_scoreboard 64 % of stalls, FP64 pipe 13 % busy).
@@ -25,7 +30,7 @@ namespace mc {
 
 constexpr int kTile = 128;   // columns per CTA == columns per workspace tile
 #if !defined(__CUDACC__)
-static long long g_mc_general_steps = 0;
+static long long g_mc_general_steps = 0;     // host (test) build: columns that left the streaming form (launch-level count)
 #endif
 
 // ---- workspace rows -----------------------------------------------------------------------------------------------
@@ -33,7 +38,7 @@ enum { P0_HGT, P0_LA, P0_LNREF, P0_LZU, P0_LZUH, P0_LZOH, P0_LNHD, P0_D, P0_GLNH
        P0_A0CAP, P0_GXC0, P0_CGCAP, P0_RDZCAP, P0_A0G, P0_GXG1, P0_CGG, P0_RZG,
        P0_X, P0_KDEN, P0_CLUMP, P0_REFG, P0_SM, P0_TRDM, P0_EMV, P0_VEGEM, P0_TRLWSUM, P0_REFM, P0_LAT, P0_LON,
        P0_GSMAX, P0_Q50, P0_LWD, P0_SMAX, P0_SOILB, P0_PSIE, P0_SKA, P0_SKB, P0_SKC, P0_SKAD, P0_CVDRY, P0_Z1,
-       P0_SELG, P0_SELH, P0_SELS, P0_ZABOVE, P0_FAST, P0_K5, P0_SLAT, P0_CLAT, P0_NFIX };          // then 1/DZK[sm], DZC[sm], Z[m]
+       P0_SELG, P0_SELH, P0_SELS, P0_ZABOVE, P0_FAST, P0_K5, P0_SLAT, P0_CLAT, P0_CPW, P0_PHW, P0_ZDIFF, P0_NFIX };          // then 1/DZK[sm], DZC[sm], Z[m]
 enum { PA_A0I, PA_A0O, PA_EX1, PA_EX2, PA_GLO, PA_GLI, PA_EDO, PA_EDI, PA_GX0, PA_GX1, PA_CG, PA_RDZ, PA_DZ, PA_N };
 enum { PB_REF, PB_PC, PB_SPC, PB_SGC, PB_TRDC, PB_TRDG, PB_TRLW, PB_PAI, PB_IZTH, PB_IZL, PB_IZRF, PB_IZP, PB_MAC, PB_MZ,
        PB_VDEN, PB_DZ, PB_N };
@@ -74,7 +79,23 @@ struct FastArgs {
   double* W;                // [ntile][nW][128]  inter-pass work rows
   unsigned long long* dbgbuf;   // [8] phase cycle counters (MC_DBG_SKIP bit 16) or null
   int spin_mode;            // 1: paraminit + t.spin_steps steps on forcing row 0 with the running mean of H (spinup, code.R:982-1013)
+  // columns that left the streaming form: fail[c] = 1 (during the spin-up launch) or 2 (during the run launch), appended to
+  // flist[0][..] / flist[1][..] with counts fcount[0] / fcount[1]; re-run by the general kernel after the streaming launches
+  int* fail;                // [ncol], zeroed before the first launch of a call
+  long long* flist;         // [2][ncol]
+  unsigned* fcount;         // [2]
 };
+
+// The six leaftemp rows of a layer that depend on previn$z (code.R:387-392): 1/zth, 1/zla, 1/zref, 1/z, the two time-step factors.
+struct LeafGeom { double izth, izl, izrf, izp, mac, mz; };
+MC_HD LeafGeom leafgeom_rows(double hgt, double zp, double zth, double zl, double PAIi, double vden, double cpw, double phw, double timestep) {
+  const double PAIm = 2 * PAIi / zth;
+  LeafGeom g;
+  g.izth = 1 / zth; g.izl = 1 / zl; g.izrf = 1 / ((hgt + 2) - zp); g.izp = 1 / zp;
+  g.mac = (timestep * PAIm * 2) / (1 - vden);
+  g.mz = ((timestep * PAIm) / (vden * cpw * phw)) / zl;
+  return g;
+}
 
 // ---- geometry: one thread per column, once per launch (uses the general column's precompute) -------------------------
 template <int MM, int MS>
@@ -84,7 +105,13 @@ MC_HD void geom_column(const FastArgs& a, const RunCfg& cfg, long long c, long l
   col.load_params(t.vegp, t.soilp, t.lat, t.lon, t.ncol, cl, t.m, t.sm);
   col.precompute(cfg, 1.0);
   const int m = t.m, sm = t.sm;
-  for (int i = 1; i <= m; ++i) col.zprev[i] = col.z[i];
+  // previn$z of the launch's first step: paraminit's regular grid (code.R:573) for the spin-up launch, the z rows of the incoming
+  // state otherwise.  When it differs from the current heights, the kernel rebuilds the leaf-geometry rows after that step.
+  bool zdiff = false;
+  for (int i = 1; i <= m; ++i) {
+    col.zprev[i] = a.spin_mode ? (i - 0.5) / m * col.hgt : t.state[(long long)(P_NSCAL + 3 * m + i - 1) * t.ncol + cl];
+    if (col.zprev[i] != col.z[i]) zdiff = true;
+  }
   col.precompute_leafgeom(cfg);
   FastLayout L{m, sm};
   double* P = a.P + (c / kTile) * (long long)L.nP() * kTile + (c % kTile);
@@ -127,6 +154,7 @@ MC_HD void geom_column(const FastArgs& a, const RunCfg& cfg, long long c, long l
     put(P0_SELH, (double)selh); put(P0_SELS, (double)sels);
   }
   put(P0_ZABOVE, col.zabove_g);
+  put(P0_CPW, col.cpw); put(P0_PHW, col.phw); put(P0_ZDIFF, zdiff ? 1.0 : 0.0);
   bool fast = true;
   if (cfg.edgedist == cfg.edgedist) for (int i = 1; i <= m; ++i) if (col.zi_[i] == 0.0) fast = false;
   put(P0_FAST, fast ? 1.0 : 0.0);
@@ -147,14 +175,13 @@ MC_HD void geom_column(const FastArgs& a, const RunCfg& cfg, long long c, long l
   for (int i = 1; i <= m; ++i) {
     const double ref = col.pLAI[i] * col.refls + (1 - col.pLAI[i]) * col.refw;
     const double pc = col.PAIg[m + 1 - i];
-    const double zth = col.zthp[i], zl = col.zla[i];
-    const double PAIm = 2 * col.PAI[i] / zth;
     const double vden = col.thickw[i] * col.PAI[i];
+    const LeafGeom lg = leafgeom_rows(hgt, col.zprev[i], col.zthp[i], col.zla[i], col.PAI[i], vden, col.cpw, col.phw, cfg.timestep);
     put(L.pb(i, PB_REF), ref); put(L.pb(i, PB_PC), pc); put(L.pb(i, PB_SPC), col.sref[i] * pc); put(L.pb(i, PB_SGC), col.sref[i] * col.PAIg[i]);
     put(L.pb(i, PB_TRDC), col.trdc[i]); put(L.pb(i, PB_TRDG), col.trdg[i]); put(L.pb(i, PB_TRLW), col.trlw[i]); put(L.pb(i, PB_PAI), col.PAI[i]);
-    put(L.pb(i, PB_IZTH), 1 / zth); put(L.pb(i, PB_IZL), 1 / zl); put(L.pb(i, PB_IZRF), 1 / ((hgt + 2) - col.z[i]));
-    put(L.pb(i, PB_IZP), 1 / col.z[i]); put(L.pb(i, PB_MAC), (cfg.timestep * PAIm * 2) / (1 - vden));
-    put(L.pb(i, PB_MZ), ((cfg.timestep * PAIm) / (vden * col.cpw * col.phw)) / zl); put(L.pb(i, PB_VDEN), vden);
+    put(L.pb(i, PB_IZTH), lg.izth); put(L.pb(i, PB_IZL), lg.izl); put(L.pb(i, PB_IZRF), lg.izrf);
+    put(L.pb(i, PB_IZP), lg.izp); put(L.pb(i, PB_MAC), lg.mac);
+    put(L.pb(i, PB_MZ), lg.mz); put(L.pb(i, PB_VDEN), vden);
     put(L.pb(i, PB_DZ), col.z[i] - (i > 1 ? col.z[i - 1] : 0.0));
   }
 }
@@ -549,14 +576,14 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   mem.step_begin();
   bool fastok = run;
   // ======================= phase 0: scalars of the step (code.R:700-745) =======================
-  double uh, sqphi, iphi, ugr, cpk, cppk, ps1a, tcu;
+  double uh, sqphi, iphi, ugr, cpk, ps1a, tcu;
   const bool edge = cfg.edgedist == cfg.edgedist;
   {
     const double tairn = fc.tair, pkn = fc.pk;
     double relhumn = fc.relhum, u = fc.u;
     const double ppk = s0(S0_PK), Hprev = s0(S0_H), ps1 = s0(L.soiltc(1));
     const double hgt = p0(P0_HGT);
-    cpk = 44.6 * fdiv(pkn, 101.3); cppk = 44.6 * fdiv(ppk, 101.3);                  // phair(t, pk) = c * 273.15 / (t + 273.15)
+    cpk = 44.6 * fdiv(pkn, 101.3);                                                  // phair(t, pk) = c * 273.15 / (t + 273.15)
     const double pha = phair(tairn, pkn);
     double u2;
     if (cfg.metopen) {
@@ -627,7 +654,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   MC_TICK(0);
   // ======================= sweep A: wind and turbulent conductances, top -> bottom (code.R:747-770) =======================
   {
-    double sfx = 0, Rtot = 0, Ctot = 0, cs = 0;
+    double sfx = 0, cs = 0;
     const int half = (int)nearbyint(m / 2.0);
     for (int i = m; i >= 1; --i) {
       mem.stageA(i);
@@ -647,12 +674,11 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double gtn = (g > gfree) ? g : gfree;
       const double rn = frcp(gtn);
       const double rg = frcp(0.5 * gtn + 0.5 * mem.a_gto());
-      const double phz = phair_c(cppk, tcu) * mem.a_p(PA_DZ);
       double* Wl = W + (long long)L.wl(i, 0) * kTile;
       mem.st_keep(Wl + WL_GTN * kTile, gtn); mem.st_keep(Wl + WL_UZN * kTile, uzn);
       // phz is rebuilt in sweep B from rows it stages anyway (old tc of the layer, dz); rg and its sum above each layer are not handed to sweep B through memory: B recomputes rg from gtn and the old gt row
       // and rebuilds the sum above layer i as (total - sum up to i)
-      sfx += rg; Rtot += rn; Ctot += phz;
+      sfx += rg;
       if (i <= half) cs += rn;
       tcu = tcl;
     }
@@ -665,9 +691,6 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     const double gfree = 0.0012 * ph * qroot(fabs(tcan - tc1) * p0(P0_RDZCAP));
     const double gtncap = (g > gfree) ? g : gfree;
     const double rgcap = frcp(0.5 * gtncap + 0.5 * s0(S0_GTCAP));
-    // layermerge (code.R:772) closes a group when timestep / sum(1/gt) <= sum(ph*zth); k closed groups need
-    // sum(1/gt) * sum(ph*zth) >= k^2 * timestep (Cauchy-Schwarz), so below (kNG+1)^2 * timestep at most kNG groups exist.
-    if (!(Rtot * Ctot < (double)((kNG + 1) * (kNG + 1)) * cfg.timestep * (1 - 1e-9))) fastok = false;
     mem.park(X_UH, uh); mem.park(X_SQPHI, sqphi); mem.park(X_CS, cs); mem.park(X_GTNCAP, gtncap); mem.park(X_RGCAP, rgcap);
     mem.park(KT_TNS1, sfx);                            // sum of rg over all layers (the slot is free until the solve)
   }
@@ -716,7 +739,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   // layermerge / layeraverage bookkeeping (code.R:772, 814): closed groups 1..ng and the open one
   int ng = 0, glo[kNG + 2], ghi[kNG + 2];
   double gw[kNG + 2], gtc[kNG + 2], gVo[kNG + 2], gea[kNG + 2], gX[kNG + 2], gvd[kNG + 2];
-  const bool runB = run && fastok;
+  const bool runB = run;
   {
     const int selHb = (int)p0(P0_SELH);
     const double its = 1 / cfg.timestep;              // launch-uniform
@@ -879,10 +902,11 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         oR += rn; oC += phz; open = true;
         ow += wi; otc += wi * ptc; oVo += wi * (eaj * ku[KU_IPPK - KU_LAMBDA]); oea += wi * ean; oX += wi * (tnl - ptc); ovd += wi * mem.b_p(PB_VDEN);
         if (timestep <= oC * oR) {                                               // timestep / sum(1/gt) <= sum(ph*zth)
-          if (ng < kNG) {            // (lanes outside the envelope compute too, but never beyond the solver's storage)
+          if (ng < kNG) {
             ++ng;
             glo[ng] = olo; ghi[ng] = i; gw[ng] = ow; gtc[ng] = otc; gVo[ng] = oVo; gea[ng] = oea; gX[ng] = oX; gvd[ng] = ovd;
-          }
+          } else fastok = false;     // more merged layers than the solve holds: the column leaves the streaming form (the rest of
+                                     // this step only writes its own, now dead, rows; never beyond the solver's storage)
           olo = i + 1; oR = 0; oC = 0; ow = 0; otc = 0; oVo = 0; oea = 0; oX = 0; ovd = 0; open = false;
         }
       }
@@ -1095,7 +1119,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   const double Lt = mem.unpark(X_LT), stl = mem.unpark(X_STL), ssw = mem.unpark(X_SSW);
   const double sqphi_e = mem.unpark(X_SQPHI), uh_e = mem.unpark(X_UH), cp1_e = mem.unpark(X_CP1), gtncap_e = mem.unpark(X_GTNCAP);
   const double tns1_in = mem.unpark(KT_TNS1), tsel_in = mem.unpark(KT_TSEL);
-  if (!runB) return !run || fastok;               // (after the last warp-collective tensor-memory access of the step)
+  if (!runB) return !run;                         // (after the last warp-collective tensor-memory access of the step)
   const double tairn = x0[X_TAIRN], pkn = x0[X_PKN], Rsw = x0[X_RSW], tcan = x0[X_TCAN];
   const double ps1 = x1[X_PS1 - X_PPK], tet_tair = x1[X_TET_TAIR - X_PPK], tet_tcan = x1[X_TET_TCAN - X_PPK], tfrost = x1[X_TFROST - X_PPK];
   const double phi_m = x1[X_PHIM - X_PPK];
@@ -1130,7 +1154,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   double* o = out.o;
   out.ng = ng;
   o[6] = Hn; o[7] = Gn;
-  if (charmode || reqhgt != reqhgt) { o[0] = stc / m; o[1] = stl / m; o[2] = srh / m; o[3] = ssw / m; o[4] = slw / m; o[5] = Lt; return true; }
+  if (charmode || reqhgt != reqhgt) { o[0] = stc / m; o[1] = stl / m; o[2] = srh / m; o[3] = ssw / m; o[4] = slw / m; o[5] = Lt; return fastok; }
   o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0;
   if (reqhgt >= hgt) {                                                         // Q13
     o[0] = tcan; o[1] = stl / m;
@@ -1145,62 +1169,27 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     } else { for (int q = 0; q < 6; ++q) o[q] = NAN; }
   }
   if (reqhgt <= 0) { const int ss = (int)p0(P0_SELS); o[0] = (ss == 1) ? tns1 : tsel_in; o[1] = stl / m; o[2] = srh / m; o[3] = ssw / m; o[4] = slw / m; o[5] = Lt; }
-  return true;
+  return fastok;
 }
 
-// ---- moving one column between the ABI state array and the working rows ------------------------------------------------
-template <int MM, int MS>
-MC_HD void ws_from_column(const Column<MM, MS>& col, const FastLayout& L, double* S) {
-  auto put = [&](int r, double v) { S[(long long)r * kTile] = v; };
-  const int m = L.m, sm = L.sm;
-  put(S0_TABOVE, col.tabove); put(S0_RELHUM, col.relhum); put(S0_TAIR, col.tair); put(S0_TSOIL, col.tsoil); put(S0_PK, col.pk);
-  put(S0_H, col.H); put(S0_PSIM, col.psi_m); put(S0_G, col.G);
-  double s = 0;
+// ---- leaf-geometry rows after a first step whose previn$z differed from the current heights ---------------------------------
+// leaftemp takes its layer geometry from previn$z (code.R:387-392); runonestep returns z = the current heights (code.R:719, 898),
+// so from the second step on the rows follow the current heights.  One thread rewrites the six rows of its own column lane.
+MC_NI void fast_regeom(double* P /* lane-adjusted */, int m, int sm, double timestep, double zlafact) {
+  const FastLayout L{m, sm};
+  auto g = [&](int r) { return P[(long long)r * kTile]; };
+  const double hgt = g(P0_HGT), cpw = g(P0_CPW), phw = g(P0_PHW);
+#pragma unroll 1
   for (int i = 1; i <= m; ++i) {
-    s += col.tc[i];
-    put(L.sl(i, SL_TC), col.tc[i]); put(L.sl(i, SL_TLEAF), col.tleaf[i]); put(L.sl(i, SL_RH), col.rh[i]); put(L.sl(i, SL_RABS), col.Rabs[i]);
-    put(L.sl(i, SL_GV), col.gv[i]); put(L.sl(i, SL_GHA), col.gha[i]); put(L.uz(i), col.uz[i]); put(L.gt(i), col.gt[i]);
+    const double zi = g(L.pz(i));
+    const double zth = (i < m) ? g(L.pz(i + 1)) - zi : hgt - (zi + g(L.pz(m - 1))) / 2;
+    const double PAIi = g(L.pb(i, PB_PAI));
+    const double zl = mixinglength(zth, PAIi) * 0.5 * zlafact;
+    const LeafGeom lg = leafgeom_rows(hgt, zi, zth, zl, PAIi, g(L.pb(i, PB_VDEN)), cpw, phw, timestep);
+    P[(long long)L.pb(i, PB_IZTH) * kTile] = lg.izth; P[(long long)L.pb(i, PB_IZL) * kTile] = lg.izl;
+    P[(long long)L.pb(i, PB_IZRF) * kTile] = lg.izrf; P[(long long)L.pb(i, PB_IZP) * kTile] = lg.izp;
+    P[(long long)L.pb(i, PB_MAC) * kTile] = lg.mac; P[(long long)L.pb(i, PB_MZ) * kTile] = lg.mz;
   }
-  put(S0_TCSUM, s); put(S0_GTCAP, col.gt[m + 1]); put(L.gt(m + 1), col.gt[m + 1]);
-  for (int j = 1; j <= sm; ++j) put(L.soiltc(j), col.soiltc[j]);
-}
-template <int MM, int MS>
-MC_HD void column_from_ws(Column<MM, MS>& col, const FastLayout& L, const double* S) {
-  auto get = [&](int r) { return S[(long long)r * kTile]; };
-  const int m = L.m, sm = L.sm;
-  col.tabove = get(S0_TABOVE); col.relhum = get(S0_RELHUM); col.tair = get(S0_TAIR); col.tsoil = get(S0_TSOIL); col.pk = get(S0_PK);
-  col.H = get(S0_H); col.psi_m = get(S0_PSIM); col.G = get(S0_G);
-  for (int i = 1; i <= m; ++i) {
-    col.tc[i] = get(L.sl(i, SL_TC)); col.tleaf[i] = get(L.sl(i, SL_TLEAF)); col.rh[i] = get(L.sl(i, SL_RH)); col.Rabs[i] = get(L.sl(i, SL_RABS));
-    col.gv[i] = get(L.sl(i, SL_GV)); col.gha[i] = get(L.sl(i, SL_GHA)); col.uz[i] = get(L.uz(i)); col.gt[i] = get(L.gt(i));
-  }
-  col.gt[m + 1] = get(S0_GTCAP);
-  for (int j = 1; j <= sm; ++j) col.soiltc[j] = get(L.soiltc(j));
-}
-
-// One step of one column through the general path (several merged air layers, or node heights of the incoming state that
-// differ from the current geometry).  `zprev` null: previous heights equal the current ones.
-template <int MM, int MS>
-MC_NI void general_step(const FastArgs& a, const RunCfg& cfg, const FastLayout& L, long long c, double* S, double* W, const double* zprev,
-                        long long zld, const Forcing& fc, bool emit, double reqhgt, int charmode, double temp_i, double relhum0, double rsw0,
-                        double skyem0, StepOut& out) {
-#if !defined(__CUDACC__)
-  ++g_mc_general_steps;                     // host (test) build only: how often columns leave the streaming envelope
-#endif
-  Column<MM, MS> col;
-  const TransientArgs& t = a.t;
-  col.load_params(t.vegp, t.soilp, t.lat, t.lon, t.ncol, c, t.m, t.sm);
-  col.precompute(cfg, 1.0);
-  column_from_ws(col, L, S);
-  for (int i = 1; i <= L.m; ++i) { col.zprev[i] = zprev ? zprev[(long long)(i - 1) * zld] : col.z[i]; col.L[i] = 0; col.Rswin[i] = 0; col.Rlwin[i] = 0; }
-  col.zabove = col.zabove_g;
-  col.precompute_leafgeom(cfg);
-  out.ng = col.step(fc, cfg);
-  ws_from_column(col, L, S);
-  if (emit) for (int i = 1; i <= L.m; ++i) {
-    W[(long long)L.wl(i, WL_L) * kTile] = col.L[i]; W[(long long)L.wl(i, WL_RSWIN) * kTile] = col.Rswin[i]; W[(long long)L.wl(i, WL_RLWIN) * kTile] = col.Rlwin[i];
-  }
-  col.harvest(reqhgt, charmode, temp_i, relhum0, rsw0, skyem0, out.o);
 }
 
 // ABI state rows of one column from the working rows (state layout of include/microclimc_b200.h)
@@ -1266,12 +1255,12 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
   const double hgt = P[(long long)P0_HGT * kTile];
   const RunCfg cfg = effective_cfg(t, hgt, a.spin_mode != 0);
   const bool fastcol = P[(long long)P0_FAST * kTile] != 0.0;
+  const bool zdiff = P[(long long)P0_ZDIFF * kTile] != 0.0;
   double f0[F_N], f[F_N];
   forcing_at(t, 0, c, f0);
   const bool have_tsoil = t.tsoil && t.tsoil[c] == t.tsoil[c];
   const double tmean = (a.spin_mode || !have_tsoil) ? column_tmean(t, c) : 0.0;
   const int NS = nstate_rows(m, sm);
-  bool zdiff = false;
   if (a.spin_mode) {
     // paraminit (code.R:566-585) straight into the working rows
     const double tair_ = f0[F_TAIR], u_ = f0[F_U], relhum_ = f0[F_RELHUM], tsoil_ = tmean, Rsw_ = f0[F_RSW];
@@ -1290,8 +1279,6 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
     for (int j = 1; j <= sm; ++j) sput(L.soiltc(j), lin2(tsoil_, tair_, sm + 1 - j, m + sm));
     sput(S0_TABOVE, tair_); sput(S0_RELHUM, relhum_); sput(S0_TAIR, tair_); sput(S0_TSOIL, tsoil_); sput(S0_PK, 101.3); sput(S0_H, 0.0);
     sput(S0_PSIM, 0.0); sput(S0_G, 0.0);
-    // paraminit's z is the regular grid; a snapped node (reqhgt) makes the first step's previn$z differ (code.R:573, 719)
-    for (int i = 1; i <= m; ++i) if ((i - 0.5) / m * hgt != P[(long long)L.pz(i) * kTile]) zdiff = true;
   } else {
     // (loads of the ABI state and stores of the working rows never alias: tell the compiler, so that it batches the loads)
     const double* __restrict__ const stp = t.state + c;
@@ -1303,7 +1290,6 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
       const double tci = st(P_NSCAL + i - 1);
       tcs += tci;
       sput(L.sl(i, SL_TC), tci); sput(L.sl(i, SL_TLEAF), st(P_NSCAL + m + i - 1)); sput(L.uz(i), st(P_NSCAL + 2 * m + i - 1));
-      if (st(P_NSCAL + 3 * m + i - 1) != P[(long long)L.pz(i) * kTile]) zdiff = true;
       sput(L.sl(i, SL_RH), st(P_NSCAL + 4 * m + i - 1)); sput(L.sl(i, SL_RABS), st(P_NSCAL + 5 * m + i - 1));
       sput(L.sl(i, SL_GV), st(P_NSCAL + 6 * m + i - 1)); sput(L.sl(i, SL_GHA), st(P_NSCAL + 7 * m + i - 1));
       sput(L.gt(i), st(P_NSCAL + 11 * m + i - 1));
@@ -1326,31 +1312,37 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
   double Hsum = 0;
   int flag = 0;
   const long long slot = (!spin && t.nsamp > 0 && t.samp_of) ? t.samp_of[c] : -1;
+  // `dead`: padding lane, or a column that left the streaming form (now or in the spin-up launch of the same call): it keeps
+  // computing with its stores suppressed (tensor-memory accesses and barriers are collective) and the general kernel redoes it.
+  bool dead = !live || a.fail[c] != 0;
+  auto drop = [&]() {
+    dead = true;
+    a.fail[c] = spin ? 1 : 2;
+#if defined(__CUDA_ARCH__)
+    const unsigned k = atomicAdd(a.fcount + (spin ? 0 : 1), 1u);
+#elif !defined(__CUDACC__)
+    const unsigned k = a.fcount[spin ? 0 : 1]++;
+    ++g_mc_general_steps;
+#else
+    const unsigned k = 0;                               // (nvcc's host pass of a device-only path)
+#endif
+    a.flist[(spin ? 0 : t.ncol) + k] = c;
+  };
+  if (!dead && !fastcol) drop();
   fast_park_constants(mem);
   for (long long it = 0; it < nsteps; ++it) {
     const long long tt = spin ? 0 : t.t0 + it;
     forcing_at(t, tt, c, f);
     const Forcing fc = {f[F_TAIR], f[F_RELHUM], f[F_PK], f[F_U], tsoil, f[F_SKYEM], f[F_RSW], f[F_DP], f[F_JD], f[F_LT], f[F_THETA],
                         /*Q2*/ f0[F_THETA]};
-    const bool emit = live && (it == nsteps - 1 || (slot >= 0 && t.full));
-    const bool gen_first = zdiff && it == 0;
-    const bool runf = live && fastcol && !gen_first;
+    const bool emit = !dead && (it == nsteps - 1 || (slot >= 0 && t.full));
     SolDay sday;                                          // date-only solar terms: from the per-row table when the library made one
     if (t.fsol) { sday.eot = t.fsol[tt * 3]; sday.sdec = t.fsol[tt * 3 + 1]; sday.cdec = t.fsol[tt * 3 + 2]; }
     else sday = sol_day(f[F_JD]);
-    const bool ok = fast_step<Mem, MS>(mem, fc, sday, t.cfg, surfwet, runf, emit, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
-    if (live && (!runf || !ok)) {
-      if (spin) {
-        double zreg[MM + 1];                                  // previn$z of paraminit (regular grid) for the general path
-        for (int q = 1; q <= m; ++q) zreg[q - 1] = (q - 0.5) / m * hgt;
-        general_step<MM, MS>(a, cfg, L, c, S, W, gen_first ? zreg : nullptr, 1, fc, emit, reqhgt, t.charmode, fc.tair, f0[F_RELHUM], f0[F_RSW],
-                             f0[F_SKYEM], so);
-      } else {
-        general_step<MM, MS>(a, cfg, L, c, S, W, gen_first ? t.state + (long long)(P_NSCAL + 3 * m) * t.ncol + c : nullptr, t.ncol, fc, emit,
-                             reqhgt, t.charmode, fc.tair, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
-      }
-    }
-    if (!live) continue;
+    const bool ok = fast_step<Mem, MS>(mem, fc, sday, t.cfg, surfwet, !dead, emit, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
+    if (!dead && !ok) drop();
+    if (it == 0 && zdiff) fast_regeom(const_cast<double*>(P), m, sm, cfg.timestep, cfg.zlafact);   // (ordered before the next step's bulk copies by step_begin's fence + barrier)
+    if (dead) continue;
     if (spin) { Hsum += S[(long long)S0_H * kTile]; sput(S0_H, Hsum / (double)(it + 1)); continue; }   // previn$H <- mean(H)
     if (so.ng > 1) flag |= 2;
     const double* o = so.o;
@@ -1362,7 +1354,7 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
       if (t.full) abi_state_from_ws(L, P, S, W, t.soilp + (long long)S_NSCAL * t.ncol + c, t.ncol, t.full + it * NS * t.nsamp + slot, t.nsamp);
     }
   }
-  if (live && !spin) {
+  if (!dead && !spin) {
     if (t.stats) {
       const double n = (double)(t.t1 - t.t0);
       t.stats[0 * t.ncol + c] = stt[0] / n; t.stats[1 * t.ncol + c] = stt[1]; t.stats[2 * t.ncol + c] = stt[2];
@@ -1370,7 +1362,7 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
     }
     if (t.flags) t.flags[c] = flag;
   }
-  if (live) abi_state_from_ws(L, P, S, W, t.soilp + (long long)S_NSCAL * t.ncol + c, t.ncol, t.state + c, t.ncol);
+  if (!dead) abi_state_from_ws(L, P, S, W, t.soilp + (long long)S_NSCAL * t.ncol + c, t.ncol, t.state + c, t.ncol);
 }
 
 }  // namespace mc

@@ -21,12 +21,17 @@ using namespace mc;
 // ---------------------------------------------------------------------------------------------------
 constexpr int kBlock = 128;
 
+// `list` null: every column of the shard.  Otherwise the columns list[0 .. *count) — the ones that left the streaming form
+// (mc_fast.cuh); blocks beyond the count exit at once, the last block's spare threads shadow its last column.
 template <int MM, int MS>
-__global__ void __launch_bounds__(kBlock) k_transient(TransientArgs a) {
+__global__ void __launch_bounds__(kBlock) k_transient(TransientArgs a, const long long* __restrict__ list, const unsigned* __restrict__ count) {
+  long long n = a.ncol;
+  if (list) { n = *count; if ((long long)blockIdx.x * kBlock >= n) return; }
   exp_tab_init();
-  long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
-  const bool live = c < a.ncol;
-  run_column<MM, MS>(a, live ? c : a.ncol - 1, live);
+  const long long j = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const bool live = j < n;
+  const long long jj = live ? j : n - 1;
+  run_column<MM, MS>(a, list ? list[jj] : jj, live);
 }
 // Streaming form of the transient run (mc_fast.cuh): geometry once per launch, then the time loop with TMA-staged layers.
 template <int MM, int MS>
@@ -182,7 +187,7 @@ struct Shard {
   int dev = 0; long long c0 = 0, nc = 0;
   cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
   DBuf vegp, soilp, lat, lon, state, state_bak, fscale, foffset, forcing, season, tsoil, stats, series, full, samp_of, flags,
-      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fsol, fP, fS, fW, dbg;
+      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fsol, fP, fS, fW, dbg, ffail, flist, fcount;
   bool fast_attr = false;
   bool has_pert = false, has_season = false, has_state = false;
   float ms = 0; long long launches = 0, pending_launches = 0;   // pending: kernels of mc_set_forcing, reported with the next run
@@ -242,8 +247,11 @@ RunCfg mk_cfg(const double* c) {
   r.timestep = c[MC_C_TIMESTEP]; r.edgedist = c[MC_C_EDGEDIST]; r.reqhgt = c[MC_C_REQHGT]; r.zu = c[MC_C_ZU];
   r.merid = c[MC_C_MERID]; r.dst = c[MC_C_DST]; r.n = c[MC_C_N]; r.metopen = c[MC_C_METOPEN] != 0; r.windhgt = c[MC_C_WINDHGT];
   r.zlafact = c[MC_C_ZLAFACT]; r.surfwet = c[MC_C_SURFWET];
+  r.dbg = 0;
+#ifdef MC_ABLATE                                   // measurement builds only (make ABLATE=1): section-skip / phase-timer knobs
   const char* e = getenv("MC_DBG_SKIP");
   r.dbg = e ? atoi(e) : 0;
+#endif
   return r;
 }
 
@@ -253,16 +261,20 @@ template <class F> int dispatch_ms(int m, int sm, F&& f) {
 }
 inline unsigned nblocks(long long n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
-// The streaming kernels cover time-invariant PAI and the small template (m <= 20, sm <= 10); everything else, or
-// MC_FORCE_GENERAL=1 in the environment (A/B tests), runs the general one-column-per-thread kernel.
+// The streaming kernels cover time-invariant PAI, the small template (m <= 20, sm <= 10) and time steps of 5 min and more (below
+// that most column-steps have more merged air layers than the streaming solve holds); everything else runs the general
+// one-column-per-thread kernel.  Measurement builds (make ABLATE=1) can force the general kernel with MC_FORCE_GENERAL=1.
 bool fast_eligible(const TransientArgs& a) {
+#ifdef MC_ABLATE
   const char* e = getenv("MC_FORCE_GENERAL");
-  return !a.season && a.m <= 20 && a.m > kNG && a.sm <= 10 && !(e && e[0] == '1');
+  if (e && e[0] == '1') return false;
+#endif
+  return !a.season && !a.vegt && !a.thetaz && a.m <= 20 && a.m > kNG && a.sm <= 10 && a.cfg.timestep >= 300.0;
 }
 int launch_transient(Shard& s, const TransientArgs& a) {
   if (!fast_eligible(a))
     return dispatch_ms(a.m, a.sm, [&](auto MM, auto MS) {
-      k_transient<decltype(MM)::value, decltype(MS)::value><<<nblocks(a.ncol), kBlock, 0, s.st>>>(a);
+      k_transient<decltype(MM)::value, decltype(MS)::value><<<nblocks(a.ncol), kBlock, 0, s.st>>>(a, nullptr, nullptr);
       s.launches++;
       return 0;
     });
@@ -270,17 +282,22 @@ int launch_transient(Shard& s, const TransientArgs& a) {
   const long long ntile = (a.ncol + kTile - 1) / kTile;
   CU(s.fP.need(sizeof(double) * ntile * L.nP() * kTile)); CU(s.fS.need(sizeof(double) * ntile * L.nS() * kTile));
   CU(s.fW.need(sizeof(double) * ntile * L.nW() * kTile));
+  CU(s.ffail.need(sizeof(int) * a.ncol)); CU(s.flist.need(sizeof(long long) * 2 * a.ncol)); CU(s.fcount.need(sizeof(unsigned) * 2));
+  CU(cudaMemsetAsync(s.ffail.p, 0, sizeof(int) * a.ncol, s.st)); CU(cudaMemsetAsync(s.fcount.p, 0, sizeof(unsigned) * 2, s.st));
   if (!s.fast_attr) {
     CU(cudaFuncSetAttribute(k_transient_fast<20, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
     CU(cudaFuncSetAttribute(k_transient_fast<20, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
     s.fast_attr = true;
   }
-  FastArgs fa{a, s.fP.as<double>(), s.fS.as<double>(), s.fW.as<double>(), nullptr, 0};
+  FastArgs fa{a, s.fP.as<double>(), s.fS.as<double>(), s.fW.as<double>(), nullptr, 0, s.ffail.as<int>(), s.flist.as<long long>(),
+              s.fcount.as<unsigned>()};
+#ifdef MC_ABLATE
   if (a.cfg.dbg & 16) {
     CU(s.dbg.need(sizeof(unsigned long long) * 8));
     CU(cudaMemsetAsync(s.dbg.p, 0, sizeof(unsigned long long) * 8, s.st));
     fa.dbgbuf = s.dbg.as<unsigned long long>();
   }
+#endif
   for (int spin = 1; spin >= 0; --spin) {
     if (spin ? a.spin_steps <= 0 : a.t1 <= a.t0) continue;
     fa.spin_mode = spin;
@@ -289,6 +306,18 @@ int launch_transient(Shard& s, const TransientArgs& a) {
     else k_transient_fast<20, 10, false><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
     s.launches += 2;
   }
+  // Columns that left the streaming form are redone by the general kernel from the call's initial state: list 0 (left during the
+  // spin-up launch) with the spin-up, list 1 (left during the run launch) from the state the spin-up launch stored.  Both launches
+  // cover the worst case and their blocks beyond the list length exit at once (no host round trip for the count).
+  for (int q = 0; q < 2; ++q) {
+    if (q == 0 ? a.spin_steps <= 0 : a.t1 <= a.t0) continue;
+    TransientArgs g = a;
+    if (q == 1) g.spin_steps = 0;
+    g.flag_or = 8;
+    k_transient<20, 10><<<nblocks(a.ncol), kBlock, 0, s.st>>>(g, s.flist.as<long long>() + (q ? a.ncol : 0), s.fcount.as<unsigned>() + q);
+    s.launches++;
+  }
+#ifdef MC_ABLATE
   if (fa.dbgbuf) {
     unsigned long long h[8];
     CU(cudaMemcpyAsync(h, fa.dbgbuf, sizeof(h), cudaMemcpyDeviceToHost, s.st));
@@ -297,6 +326,7 @@ int launch_transient(Shard& s, const TransientArgs& a) {
     const char* nm[8] = {"phase0", "sweepA+cap", "Bprep", "sweepB", "solve", "sweepC", "end", "between-steps"};
     for (int q = 0; q < 8; ++q) fprintf(stderr, "[mc phase] %-14s %6.2f %%\n", nm[q], 100.0 * (double)h[q] / (double)(tot ? tot : 1));
   }
+#endif
   return 0;
 }
 int launch_steady(Shard& s, const SteadyArgs& a, int nchunk) {
@@ -363,7 +393,8 @@ void mc_destroy(mc_ctx* ctx) {
     cudaSetDevice(s.dev);
     DBuf* bufs[] = {&s.vegp, &s.soilp, &s.lat, &s.lon, &s.state, &s.state_bak, &s.fscale, &s.foffset, &s.forcing, &s.season, &s.tsoil,
                     &s.stats, &s.series, &s.full, &s.samp_of, &s.flags, &s.args6, &s.clim8, &s.theta, &s.thetap, &s.nmerged,
-                    &s.sclim, &s.snmr, &s.sseason, &s.sout, &s.spart, &s.ssol, &s.fsol, &s.fP, &s.fS, &s.fW, &s.dbg};
+                    &s.sclim, &s.snmr, &s.sseason, &s.sout, &s.spart, &s.ssol, &s.fsol, &s.fP, &s.fS, &s.fW, &s.dbg, &s.ffail, &s.flist,
+                    &s.fcount};
     for (DBuf* b : bufs) b->release();
     if (s.e0) cudaEventDestroy(s.e0);
     if (s.e1) cudaEventDestroy(s.e1);

@@ -51,7 +51,8 @@ extern "C" int dbg_run_transient_fast(int64_t ncol, int m, int sm, int64_t T, co
   FastLayout L{m, sm};
   const long long ntile = (ncol + kTile - 1) / kTile;
   std::vector<double> P(ntile * L.nP() * kTile), S(ntile * L.nS() * kTile), W(ntile * L.nW() * kTile);
-  FastArgs a{t, P.data(), S.data(), W.data(), nullptr, 0};
+  std::vector<int> fail(ncol, 0); std::vector<long long> flist(2 * ncol, 0); unsigned fcount[2] = {0, 0};
+  FastArgs a{t, P.data(), S.data(), W.data(), nullptr, 0, fail.data(), flist.data(), fcount};
   for (int spin = 1; spin >= 0; --spin) {
     if (spin ? t.spin_steps <= 0 : T <= 0) continue;
     a.spin_mode = spin;
@@ -68,6 +69,14 @@ extern "C" int dbg_run_transient_fast(int64_t ncol, int m, int sm, int64_t T, co
       mem.ia = mem.ib = 1;
       fast_run_column<DirectMem, 20, 10>(a, mem, c, true);
     }
+  }
+  // columns that left the streaming form: redone by the general column from the call's initial state, as mc_lib.cu sequences it
+  for (int q = 0; q < 2; ++q) {
+    if (q == 0 ? t.spin_steps <= 0 : T <= 0) continue;
+    TransientArgs g = t;
+    if (q == 1) g.spin_steps = 0;
+    g.flag_or = 8;
+    for (unsigned k = 0; k < fcount[q]; ++k) run_column<20, 10>(g, flist[(q ? ncol : 0) + k]);
   }
   return 0;
 }

@@ -216,8 +216,11 @@ def test_streaming_form_equals_oracle(oracle, hostdbg, timestep, charmode, reqhg
     assert np.array_equal(got["flags"] & 1, want["flags"] & 1)
     for t in (0, 50, 95):
         assert_state_close(got["full"][t], want["full"][t], what="streaming full table t=%d" % t)
-    if timestep >= 1800.0 and np.all(np.isfinite(want["state"])):
-        assert ngen <= 0.01 * 7 * (96 + 80) + 7, "hourly columns should stay in the streaming envelope (general steps: %d)" % ngen
+    if timestep >= 1800.0 and np.all(np.isfinite(want["state"])) and edgedist == edgedist:      # (without the edge term the calm lower canopy can exceed the streaming solve's 6 merged layers)
+        assert ngen == 0, "hourly columns should stay in the streaming form (columns dropped: %d)" % ngen
+        assert not np.any(got["flags"] & 8)
+    if timestep <= 20.0:
+        assert ngen > 0 and np.any(got["flags"] & 8), "20 s steps have more merged layers than the streaming solve holds" 
 
 
 def test_streaming_form_merged_layers_occur_at_hourly_steps(oracle, hostdbg):
@@ -227,7 +230,7 @@ def test_streaming_form_merged_layers_occur_at_hourly_steps(oracle, hostdbg):
     fl = _FastLib(hostdbg)
     fl.dbg_general_steps(1)
     got = dbg_run_transient(fl, inp, cfg)
-    assert fl.dbg_general_steps(1) <= 8
+    assert fl.dbg_general_steps(1) == 0
     assert np.any(got["flags"] & 2), "no merged-layer step seen"
     want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"])
     assert_series_close(got["series"], want["series"], "bench-like")
@@ -278,6 +281,6 @@ def test_streaming_form_over_the_variant_tables(oracle, hostdbg, kind, name, mon
     assert_series_close(got["series"], want["series"], name)
     assert_state_close(got["state"], want["state"], what=name)
     if name == "short_grass_general_path":
-        assert ngen >= 5 * (V.T + V.SPIN) - 5, "nodes under 0.12 m must take the general path (%d)" % ngen
-    elif kw.get("timestep", 3600.0) >= 3600.0 and "reqhgt" not in kw:
-        assert ngen <= 5, "hourly columns should stay in the streaming envelope (general steps: %d)" % ngen
+        assert ngen >= 5, "nodes under 0.12 m must take the general path (%d)" % ngen
+    elif kw.get("timestep", 3600.0) >= 3600.0:
+        assert ngen == 0, "hourly columns should stay in the streaming form (columns dropped: %d)" % ngen
