@@ -18,6 +18,7 @@
 #ifndef MICROCLIMC_B200_H
 #define MICROCLIMC_B200_H
 #include <stdint.h>
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -87,7 +88,8 @@ int mc_run_onestep(mc_ctx* ctx, const double* climvars, double jd, double lt, co
  *  samp_idx [nsamp] columns whose hourly outputs are returned: series [t1-t0][MC_O_N][nsamp],
  *  fullseries [t1-t0][NSTATE][nsamp] (reqhgt "all"/"allclim" tables); either may be NULL;
  *  stats [6][ncol] = mean,min,max of tout then of tleaf (NULL to skip); flags [ncol] bit0 non-finite output,
- *  bit1 merged-layer branch taken (NULL to skip). */
+ *  bit1 merged-layer branch taken, bit3 the column left the streaming kernel and was redone by the general kernel inside the
+ *  same call (NULL to skip).  samp_idx must not hold a column twice (MC_ERR_ARG). */
 int mc_run_transient(mc_ctx* ctx, int64_t t0, int64_t t1, const double* tsoil, const int64_t* samp_idx, int64_t nsamp,
                      double* series, double* fullseries, double* stats, int32_t* flags);
 /* spinup (R/code.R:982-1013) as a call of its own: paraminit + `steps` iterations on forcing row 0. */
@@ -99,12 +101,19 @@ int mc_spinup(mc_ctx* ctx, int steps);
 int mc_run_steady(mc_ctx* ctx, int64_t T, const double* clim, const double* nmr, int nmr_percol, const double* scfg,
                   const double* pai_season, double* out, double* stats);
 
+/* Page-locked host memory for callers that want true asynchronous copies (the library accepts any host pointer; pinned
+ * input / result buffers remove the driver's staging copy: bench.py's e2e legs, microclimc_b200.gridrun).  NULL on failure. */
+void* mc_host_alloc(size_t bytes);
+void mc_host_free(void* p);
+
 /* Device time (ms, CUDA events on the launching streams, max over GPUs) of the kernels of the last mc_run_* /
  * mc_spinup call, and the number of kernel launches it made. */
 double mc_last_kernel_ms(const mc_ctx* ctx);
 int64_t mc_last_kernel_launches(const mc_ctx* ctx);
 /* Re-run the last mc_run_transient / mc_run_steady kernels on the device-resident inputs `reps` times without any
- * host<->device copy (state is restored before each repetition); returns the mean device ms per repetition. */
+ * host<->device copy (state is restored before each repetition); returns the mean device ms per repetition.
+ * The state copy a transient replay needs is kept only once this entry has been called on the context: the first call after a
+ * transient run without spin-up arms it and returns -1 (MC_ERR_STATE in mc_last_error); repeat the run, then call again. */
 double mc_bench_resident(mc_ctx* ctx, int reps);
 /* Measured FP64 (non-tensor DFMA) peak of the context's first GPU in TFLOP/s: the roofline denominator of this
  * FP64-bound path (the driver's MEASURED_PEAKS.json carries no FP64 figure). */

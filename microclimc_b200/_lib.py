@@ -34,6 +34,8 @@ SYMBOLS = {
     "mc_bench_resident": (D, [C.c_void_p, C.c_int]),
     "mc_fp64_peak_tflops": (D, [C.c_void_p]),
     "mc_eval_primitive": (C.c_int, [C.c_void_p, C.c_int, I64, PD, PD, PD]),
+    "mc_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "mc_host_free": (None, [C.c_void_p]),
 }
 
 
@@ -55,6 +57,40 @@ def lib():
             f.restype = res; f.argtypes = args
         _LIB = L
     return _LIB
+
+
+class _Pinned:
+    """Owner of one mc_host_alloc block; numpy views keep it alive through their .base chain."""
+
+    def __init__(self, nbytes):
+        self.ptr = lib().mc_host_alloc(max(int(nbytes), 8))
+        if not self.ptr:
+            raise MicroclimcError("mc_host_alloc(%d) failed" % nbytes)
+        self.buf = (C.c_byte * max(int(nbytes), 8)).from_address(self.ptr)
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and _LIB is not None:
+            _LIB.mc_host_free(self.ptr); self.ptr = None
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array in page-locked host memory (mc_host_alloc): copies to / from it are true asynchronous DMA."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    own = _Pinned(n)
+    a = np.frombuffer(own.buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    a.flags.writeable = True
+    _PINNED_OWNERS[id(own)] = own          # (np.frombuffer keeps `own.buf`, not `own`: hold the owner until the module goes away)
+    return a
+
+
+_PINNED_OWNERS = {}
+
+
+def pinned_copy(a, dtype=np.float64):
+    out = pinned_empty(np.shape(a), dtype)
+    out[...] = a
+    return out
 
 
 def _p(a, typ=PD):
@@ -155,12 +191,16 @@ class Context:
                                          _p(flags, PI32)))
         return dict(series=series, full=full, stats=stats, flags=flags)
 
-    def run_steady(self, clim, nmr, scfg, pai_season=None, want_out=True, want_stats=True):
+    def run_steady(self, clim, nmr, scfg, pai_season=None, want_out=True, want_stats=True, out_stats=None, out_out=None):
+        """runmodelS over T hours.  `out_stats` ([6][ncol]) / `out_out` ([T][7][ncol]): caller-owned (e.g. pinned) result buffers."""
         clim, nmr, scfg, pai_season = map(_f, (clim, nmr, scfg, pai_season))
         T = clim.shape[0]
         percol = 1 if nmr.ndim == 3 else 0
-        out = np.zeros((T, 7, self.ncol)) if want_out else None
-        stats = np.zeros((6, self.ncol)) if want_stats else None
+        out = (out_out if out_out is not None else np.zeros((T, 7, self.ncol))) if want_out else None
+        stats = (out_stats if out_stats is not None else np.zeros((6, self.ncol))) if want_stats else None
+        for a_, shp in ((out, (T, 7, self.ncol)), (stats, (6, self.ncol))):
+            if a_ is not None:
+                assert a_.dtype == np.float64 and a_.shape == shp and a_.flags["C_CONTIGUOUS"]
         self._chk(lib().mc_run_steady(self._h, T, _p(clim), _p(nmr), percol, _p(scfg), _p(pai_season), _p(out), _p(stats)))
         return dict(out=out, stats=stats)
 

@@ -6,8 +6,11 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <mutex>
+#include <condition_variable>
 #include <vector>
 #include <functional>
+#include <algorithm>
 #include "../../include/microclimc_b200.h"
 #include "mc_driver.cuh"
 #include "mc_fast.cuh"
@@ -104,6 +107,10 @@ __global__ void __launch_bounds__(kBlock, MC_STEADY_CTAS) k_steady(SteadyArgs a)
   const bool live = c < a.ncol;
   steady_column<MM>(a, live ? c : a.ncol - 1, blockIdx.y, gridDim.y, live);
 }
+__global__ void k_samp_scatter(long long ns, const long long* __restrict__ cols, long long* __restrict__ samp_of) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < ns) samp_of[cols[k]] = k;
+}
 // date-only part of the solar geometry, once per row of the series instead of once per (column, row); `stride` doubles per row,
 // Julian day at `jdcol`
 __global__ void k_sol_rows(long long T, const double* rows, int stride, int jdcol, double* sol) {
@@ -183,13 +190,41 @@ struct DBuf {
   template <class T> T* as() const { return (T*)p; }
 };
 
+// One persistent host thread per GPU of a multi-GPU context (created in mc_create, joined in mc_destroy): the calling thread posts
+// the same job to every worker and waits for all of them, so no thread is spawned per API call and each worker keeps its device
+// current.  The library's entry points are not re-entrant per context (one caller at a time), which is all the hand-off assumes.
+// pinned host staging (sampled series travel through it before they are scattered into the caller's arrays)
+struct HBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t need(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+struct Worker {
+  std::thread th; std::mutex mu; std::condition_variable cv;
+  const std::function<int(struct Shard&)>* job = nullptr;
+  int rc = 0; bool busy = false, quit = false;
+};
+
 struct Shard {
   int dev = 0; long long c0 = 0, nc = 0;
+  Worker* worker = nullptr;
+  std::vector<int64_t> samp_cached;            // sample columns whose slots the device-side samp_of currently holds
+  bool samp_valid = false;
+  HBuf hser, hfull;
   cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
   DBuf vegp, soilp, lat, lon, state, state_bak, fscale, foffset, forcing, season, tsoil, stats, series, full, samp_of, flags,
-      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fsol, fP, fS, fW, dbg, ffail, flist, fcount;
+      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fsol, fP, fS, fW, dbg, ffail, flist, fcount, samp_cols;
   bool fast_attr = false;
-  bool has_pert = false, has_season = false, has_state = false;
+  bool has_pert = false, has_season = false, has_state = false, bak_valid = false;
   float ms = 0; long long launches = 0, pending_launches = 0;   // pending: kernels of mc_set_forcing, reported with the next run
   // replay info for mc_bench_resident
   int last_kind = 0;   // 0 none, 1 transient, 2 steady
@@ -207,6 +242,7 @@ struct mc_ctx {
   bool has_cfg = false;
   std::string err;
   double last_ms = 0; long long last_launches = 0;
+  bool keep_replay_state = false;   // set by the first mc_bench_resident call: transient runs then keep a copy of their incoming state
 };
 
 namespace {
@@ -215,17 +251,38 @@ int fail(mc_ctx* ctx, int code, const std::string& msg) { if (ctx) ctx->err = ms
 
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { s.err = std::string(#call) + ": " + cudaGetErrorString(e_); return MC_ERR_CUDA; } } while (0)
 
-// run fn on every shard, one host thread per GPU, joined before return
+void worker_main(Shard* s) {
+  cudaSetDevice(s->dev);
+  Worker& w = *s->worker;
+  std::unique_lock<std::mutex> lk(w.mu);
+  for (;;) {
+    w.cv.wait(lk, [&] { return w.busy || w.quit; });
+    if (w.quit) return;
+    lk.unlock();
+    const int rc = (*w.job)(*s);
+    lk.lock();
+    w.rc = rc; w.busy = false;
+    w.cv.notify_all();
+  }
+}
+// run fn on every shard — inline for one GPU, on the per-GPU worker threads otherwise — and return when all are done
 int for_shards(mc_ctx* ctx, const std::function<int(Shard&)>& fn) {
   std::vector<int> rc(ctx->shards.size(), 0);
   if (ctx->shards.size() == 1) {
     cudaSetDevice(ctx->shards[0].dev);
     rc[0] = fn(ctx->shards[0]);
   } else {
-    std::vector<std::thread> th;
-    for (size_t i = 0; i < ctx->shards.size(); ++i)
-      th.emplace_back([&, i] { cudaSetDevice(ctx->shards[i].dev); rc[i] = fn(ctx->shards[i]); });
-    for (auto& t : th) t.join();
+    for (auto& s : ctx->shards) {
+      std::lock_guard<std::mutex> lk(s.worker->mu);
+      s.worker->job = &fn; s.worker->busy = true;
+      s.worker->cv.notify_all();
+    }
+    for (size_t i = 0; i < ctx->shards.size(); ++i) {
+      Worker& w = *ctx->shards[i].worker;
+      std::unique_lock<std::mutex> lk(w.mu);
+      w.cv.wait(lk, [&] { return !w.busy; });
+      rc[i] = w.rc;
+    }
   }
   for (size_t i = 0; i < rc.size(); ++i)
     if (rc[i]) { ctx->err = "gpu " + std::to_string(ctx->shards[i].dev) + ": " + ctx->shards[i].err; return rc[i]; }
@@ -261,15 +318,16 @@ template <class F> int dispatch_ms(int m, int sm, F&& f) {
 }
 inline unsigned nblocks(long long n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
-// The streaming kernels cover time-invariant PAI, the small template (m <= 20, sm <= 10) and time steps of 5 min and more (below
-// that most column-steps have more merged air layers than the streaming solve holds); everything else runs the general
-// one-column-per-thread kernel.  Measurement builds (make ABLATE=1) can force the general kernel with MC_FORCE_GENERAL=1.
+// The streaming kernels cover time-invariant PAI, the small template (m <= 20, sm <= 10) and hourly or coarser time steps (the
+// reference's use: hourly climdata).  With shorter steps column-steps with more merged air layers than the streaming solve holds
+// become common (host build, 96 steps of 64 columns: 11 % of the columns at 1800 s, all of them at 900 s), and a column that meets
+// one is redone from the start; everything else runs the general one-column-per-thread kernel.  Measurement builds (make ABLATE=1) can force the general kernel with MC_FORCE_GENERAL=1.
 bool fast_eligible(const TransientArgs& a) {
 #ifdef MC_ABLATE
   const char* e = getenv("MC_FORCE_GENERAL");
   if (e && e[0] == '1') return false;
 #endif
-  return !a.season && !a.vegt && !a.thetaz && a.m <= 20 && a.m > kNG && a.sm <= 10 && a.cfg.timestep >= 300.0;
+  return !a.season && !a.vegt && !a.thetaz && a.m <= 20 && a.m > kNG && a.sm <= 10 && a.cfg.timestep >= 3600.0;
 }
 int launch_transient(Shard& s, const TransientArgs& a) {
   if (!fast_eligible(a))
@@ -384,18 +442,26 @@ mc_ctx* mc_create(int m, int sm, int n_gpus, const int* gpu_ids) {
       delete ctx; return nullptr;
     }
   }
+  if (n_gpus > 1)
+    for (auto& s : ctx->shards) { s.worker = new Worker(); s.worker->th = std::thread(worker_main, &s); }
   std::memset(ctx->cfg, 0, sizeof(ctx->cfg));
   return ctx;
 }
 void mc_destroy(mc_ctx* ctx) {
   if (!ctx) return;
   for (auto& s : ctx->shards) {
+    if (s.worker) {
+      { std::lock_guard<std::mutex> lk(s.worker->mu); s.worker->quit = true; s.worker->cv.notify_all(); }
+      s.worker->th.join();
+      delete s.worker; s.worker = nullptr;
+    }
     cudaSetDevice(s.dev);
     DBuf* bufs[] = {&s.vegp, &s.soilp, &s.lat, &s.lon, &s.state, &s.state_bak, &s.fscale, &s.foffset, &s.forcing, &s.season, &s.tsoil,
                     &s.stats, &s.series, &s.full, &s.samp_of, &s.flags, &s.args6, &s.clim8, &s.theta, &s.thetap, &s.nmerged,
                     &s.sclim, &s.snmr, &s.sseason, &s.sout, &s.spart, &s.ssol, &s.fsol, &s.fP, &s.fS, &s.fW, &s.dbg, &s.ffail, &s.flist,
-                    &s.fcount};
+                    &s.fcount, &s.samp_cols};
     for (DBuf* b : bufs) b->release();
+    s.hser.release(); s.hfull.release();
     if (s.e0) cudaEventDestroy(s.e0);
     if (s.e1) cudaEventDestroy(s.e1);
     if (s.st) cudaStreamDestroy(s.st);
@@ -412,7 +478,7 @@ int mc_set_columns(mc_ctx* ctx, int64_t ncol, const double* vegp, const double* 
     Shard& s = ctx->shards[i];
     s.c0 = std::min<long long>((long long)i * per, ncol);
     s.nc = std::min<long long>(per, ncol - s.c0);
-    s.has_state = false; s.has_pert = false; s.last_kind = 0;
+    s.has_state = false; s.has_pert = false; s.last_kind = 0; s.samp_valid = false;
   }
   const int NV = mc_nveg(ctx->m), NSo = mc_nsoil(ctx->sm), NSt = mc_nstate(ctx->m, ctx->sm);
   return for_shards(ctx, [&](Shard& s) -> int {
@@ -563,6 +629,11 @@ static int run_transient_impl(mc_ctx* ctx, int64_t t0, int64_t t1, int spin_step
   if (spin_steps <= 0) for (auto& s : ctx->shards) if (s.nc && !s.has_state)
     return fail(ctx, MC_ERR_STATE, "mc_run_transient: no state on the device (spin-up disabled and no mc_set_state / mc_paraminit)");
   for (int64_t j = 0; j < nsamp; ++j) if (samp_idx[j] < 0 || samp_idx[j] >= ctx->ncol) return fail(ctx, MC_ERR_ARG, "mc_run_transient: samp_idx out of range");
+  if (nsamp > 1 && (series || fullseries)) {          // a column may be sampled once: its device slot is written once
+    std::vector<int64_t> srt(samp_idx, samp_idx + nsamp);
+    std::sort(srt.begin(), srt.end());
+    if (std::adjacent_find(srt.begin(), srt.end()) != srt.end()) return fail(ctx, MC_ERR_ARG, "mc_run_transient: duplicate entries in samp_idx");
+  }
   const long long ncol = ctx->ncol;
   const int m = ctx->m, sm = ctx->sm, NSt = mc_nstate(m, sm);
   const long long nt = t1 - t0;
@@ -571,15 +642,13 @@ static int run_transient_impl(mc_ctx* ctx, int64_t t0, int64_t t1, int spin_step
   int rc = for_shards(ctx, [&](Shard& s) -> int {
     s.ms = 0; s.launches = s.pending_launches; s.pending_launches = 0;
     if (s.nc == 0) return 0;
-    // sample slots owned by this shard
-    std::vector<long long> samp_of; std::vector<int64_t> slots;
-    if (nsamp > 0 && (series || fullseries)) {
-      samp_of.assign(s.nc, -1);
+    // sample slots owned by this shard: slot k of the shard <-> entry slots[k] of samp_idx <-> local column cols[k]
+    std::vector<int64_t> slots, cols;
+    if (nsamp > 0 && (series || fullseries))
       for (int64_t j = 0; j < nsamp; ++j) {
         long long c = samp_idx[j] - s.c0;
-        if (c >= 0 && c < s.nc) { samp_of[c] = (long long)slots.size(); slots.push_back(j); }
+        if (c >= 0 && c < s.nc) { slots.push_back(j); cols.push_back(c); }
       }
-    }
     const long long ns = (long long)slots.size();
     TransientArgs a{};
     a.ncol = s.nc; a.m = m; a.sm = sm; a.T = ctx->T; a.t0 = t0; a.t1 = t1;
@@ -594,28 +663,45 @@ static int run_transient_impl(mc_ctx* ctx, int64_t t0, int64_t t1, int spin_step
       a.tsoil = s.tsoil.as<double>();
     }
     if (ns > 0) {
-      CU(s.samp_of.need(sizeof(long long) * s.nc));
-      CU(cudaMemcpyAsync(s.samp_of.p, samp_of.data(), sizeof(long long) * s.nc, cudaMemcpyHostToDevice, s.st));
+      // column -> slot map on the device: filled with -1 and scattered from the short column list by a small kernel, and kept as long
+      // as the sample set does not change (a weekly-chunked year re-uses it 52 times) — no per-call upload proportional to ncol
+      if (!s.samp_valid || s.samp_cached != cols) {
+        CU(s.samp_of.need(sizeof(long long) * s.nc)); CU(s.samp_cols.need(sizeof(long long) * ns));
+        CU(cudaMemsetAsync(s.samp_of.p, 0xFF, sizeof(long long) * s.nc, s.st));
+        CU(cudaMemcpyAsync(s.samp_cols.p, cols.data(), sizeof(long long) * ns, cudaMemcpyHostToDevice, s.st));
+        k_samp_scatter<<<nblocks(ns), kBlock, 0, s.st>>>(ns, s.samp_cols.as<long long>(), s.samp_of.as<long long>());
+        CU(cudaGetLastError());
+        s.launches++;
+        CU(cudaStreamSynchronize(s.st));                 // (cols is a local: the copy must have read it before it goes away)
+        s.samp_cached = cols; s.samp_valid = true;
+      }
       a.samp_of = s.samp_of.as<long long>(); a.nsamp = ns;
       if (series) { CU(s.series.need(sizeof(double) * nt * MC_O_N * ns)); a.series = s.series.as<double>(); }
       if (fullseries) { CU(s.full.need(sizeof(double) * nt * NSt * ns)); a.full = s.full.as<double>(); }
     }
     if (stats) { CU(s.stats.need(sizeof(double) * 6 * s.nc)); a.stats = s.stats.as<double>(); }
     if (flags) { CU(s.flags.need(sizeof(int) * s.nc)); a.flags = s.flags.as<int>(); }
-    if (spin_steps <= 0) {   // keep a copy so mc_bench_resident can replay from the same state
+    if (spin_steps <= 0 && ctx->keep_replay_state) {   // opt-in (mc_bench_resident): a copy of the incoming state to replay from
       CU(s.state_bak.need(sizeof(double) * NSt * s.nc));
       CU(cudaMemcpyAsync(s.state_bak.p, s.state.p, sizeof(double) * NSt * s.nc, cudaMemcpyDeviceToDevice, s.st));
-    }
+      s.bak_valid = true;
+    } else s.bak_valid = false;
     CU(cudaEventRecord(s.e0, s.st));
-    launch_transient(s, a);
+    { int lrc = launch_transient(s, a); if (lrc) return lrc; }
     CU(cudaEventRecord(s.e1, s.st));
     CU(cudaGetLastError());
     s.last_kind = 1; s.last_t = a;
     if (stats) CU(d2h_rows(stats, s.stats.as<double>(), 6, ncol, s.c0, s.nc, s.st));
     if (flags) CU(cudaMemcpyAsync(flags + s.c0, s.flags.p, sizeof(int) * s.nc, cudaMemcpyDeviceToHost, s.st));
-    std::vector<double> hser, hfull;
-    if (ns > 0 && series) { hser.resize((size_t)nt * MC_O_N * ns); CU(cudaMemcpyAsync(hser.data(), s.series.p, sizeof(double) * hser.size(), cudaMemcpyDeviceToHost, s.st)); }
-    if (ns > 0 && fullseries) { hfull.resize((size_t)nt * NSt * ns); CU(cudaMemcpyAsync(hfull.data(), s.full.p, sizeof(double) * hfull.size(), cudaMemcpyDeviceToHost, s.st)); }
+    const double *hser = nullptr, *hfull = nullptr;
+    if (ns > 0 && series) {
+      const size_t b = sizeof(double) * (size_t)nt * MC_O_N * ns;
+      CU(s.hser.need(b)); CU(cudaMemcpyAsync(s.hser.p, s.series.p, b, cudaMemcpyDeviceToHost, s.st)); hser = s.hser.as<double>();
+    }
+    if (ns > 0 && fullseries) {
+      const size_t b = sizeof(double) * (size_t)nt * NSt * ns;
+      CU(s.hfull.need(b)); CU(cudaMemcpyAsync(s.hfull.p, s.full.p, b, cudaMemcpyDeviceToHost, s.st)); hfull = s.hfull.as<double>();
+    }
     CU(cudaStreamSynchronize(s.st));
     CU(cudaEventElapsedTime(&s.ms, s.e0, s.e1));
     s.has_state = true;
@@ -685,7 +771,7 @@ int mc_run_steady(mc_ctx* ctx, int64_t T, const double* clim, const double* nmr,
     CU(cudaMemsetAsync(s.flags.p, 0, sizeof(int) * s.nc, s.st));
     CU(s.ssol.need(sizeof(double) * T * 13)); a.sol = s.ssol.as<double>();
     CU(cudaEventRecord(s.e0, s.st));
-    launch_steady(s, a, nchunk);
+    { int lrc = launch_steady(s, a, nchunk); if (lrc) return lrc; }
     CU(cudaEventRecord(s.e1, s.st));
     CU(cudaGetLastError());
     s.last_kind = 2; s.last_s = a; s.last_nchunk = nchunk;
@@ -747,12 +833,29 @@ int mc_eval_primitive(mc_ctx* ctx, int op, int64_t n, const double* x, const dou
   return 0;
 }
 
+void* mc_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void mc_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 double mc_last_kernel_ms(const mc_ctx* ctx) { return ctx ? ctx->last_ms : -1.0; }
 int64_t mc_last_kernel_launches(const mc_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
 
 double mc_bench_resident(mc_ctx* ctx, int reps) {
   if (!ctx || reps <= 0) return -1.0;
   const int NSt = mc_nstate(ctx->m, ctx->sm);
+  if (!ctx->keep_replay_state) {
+    // The state copy a replay needs is not kept by default (it doubles the resident state).  The first call arms it: a transient run
+    // without spin-up issued after this call can be replayed; one issued before cannot (its incoming state is gone).
+    ctx->keep_replay_state = true;
+    for (auto& s : ctx->shards)
+      if (s.nc && s.last_kind == 1 && s.last_t.spin_steps <= 0 && !s.bak_valid) {
+        fail(ctx, MC_ERR_STATE, "mc_bench_resident: replay armed; repeat the mc_run_transient call, then call mc_bench_resident again");
+        return -1.0;
+      }
+  }
   int rc = for_shards(ctx, [&](Shard& s) -> int {
     s.ms = 0; s.launches = 0;
     if (s.nc == 0 || s.last_kind == 0) return 0;
@@ -761,7 +864,7 @@ double mc_bench_resident(mc_ctx* ctx, int reps) {
       if (s.last_kind == 1 && s.last_t.spin_steps <= 0)
         CU(cudaMemcpyAsync(s.state.p, s.state_bak.p, sizeof(double) * NSt * s.nc, cudaMemcpyDeviceToDevice, s.st));
       CU(cudaEventRecord(s.e0, s.st));
-      if (s.last_kind == 1) launch_transient(s, s.last_t); else launch_steady(s, s.last_s, s.last_nchunk);
+      { int lrc = (s.last_kind == 1) ? launch_transient(s, s.last_t) : launch_steady(s, s.last_s, s.last_nchunk); if (lrc) return lrc; }
       CU(cudaEventRecord(s.e1, s.st));
       CU(cudaGetLastError());
       CU(cudaStreamSynchronize(s.st));

@@ -1,0 +1,135 @@
+"""GPU parity cases added in round 2 ("untested on the GPU"): transient output above the canopy (code.R:722-725,
+quirk Q13 at 1235-1240), `runmodel(snow = 1)` end to end (code.R:918-933: a very different operating point of the step), the
+bench workload itself (BASELINE config 3 shapes) over a fortnight with sampled columns against the oracle, columns that leave
+the streaming form, and the in-process multi-GPU split."""
+import numpy as np
+import pytest
+
+from tests.common import M, SM, make_cfg, transient_inputs, assert_state_close, assert_series_close, loam
+from microclimc_b200 import layout as L, synth as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(inp, cfg, n_gpus=1):
+    from microclimc_b200._lib import Context
+    ctx = Context(M, SM, n_gpus)
+    ctx.set_columns(inp["veg"], inp["soil"], inp["lat"], inp["lon"])
+    ctx.set_forcing(inp["f"], inp["fs"], inp["fo"])
+    ctx.set_config(cfg)
+    return ctx
+
+
+@pytest.mark.parametrize("reqhgt", [17.0, 25.0])
+def test_transient_output_above_canopy(oracle, reqhgt):
+    """reqhgt > hgt: zabove <- reqhgt (code.R:722-725) changes the canopy-top temperature's reference height, and the harvest takes
+    tabove / the first row's relhum, Rsw, skyem (quirk Q13, code.R:1235-1240)."""
+    inp = transient_inputs(oracle, ncol=48, T=120)
+    hg = L.veg_rows(M)["hgt"]
+    inp["veg"][hg] = np.minimum(inp["veg"][hg], 16.0)                      # every canopy below the output height
+    cfg = make_cfg(reqhgt=reqhgt, spin_steps=60)
+    want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"])
+    ctx = _ctx(inp, cfg)
+    got = ctx.run_transient(samp_idx=np.arange(48))
+    st = ctx.get_state()
+    assert np.all(st[L.state_rows(M, SM)["zabove"]] == reqhgt)
+    assert_series_close(got["series"], want["series"], "reqhgt %g above canopy" % reqhgt)
+    assert_state_close(st, want["state"], what="reqhgt above canopy")
+    assert np.count_nonzero(got["flags"] & 8) <= 2, "hourly columns stay in the streaming form (a node snapped above a short canopy may not)"
+
+
+def test_transient_runmodel_with_snow_on_the_canopy(oracle):
+    """runmodel(snow = 1): .snowsort (code.R:918-933) swaps in lw*1.5, zm0 0.024, refls 0.85, refg 0.8, refw 0.7, gsmax 10, q50 1 for the
+    whole run (quirk Q3) — through the public host mirror (api.runmodel_batch) against the oracle fed the swapped parameters."""
+    from microclimc_b200 import api
+    w = S.load_weather()
+    T = 96
+    clim = {k: (np.asarray(v)[300:300 + T]) for k, v in w.items()}          # midwinter
+    soil = loam(oracle)
+    base = S.vegp_deciduous()
+    vl = []
+    rng = np.random.default_rng(4)
+    for c in range(24):
+        v = dict(base); v["PAI"] = np.asarray(base["PAI"]) * rng.uniform(0.7, 1.3); v["hgt"] = base["hgt"] * rng.uniform(0.8, 1.2)
+        vl.append(v)
+    r = api.runmodel_batch(clim, vl, [soil] * 24, 50.0, -5.0, reqhgt=1.0, steps=40, snow=1, sample=np.arange(24))
+    snowed = [api._snowsort(v, 1, 0) for v in vl]
+    veg = S.pack_vegp(snowed, M); so = S.pack_soilp([soil] * 24, SM)
+    f, ts = S.forcing_from_climdata(clim, theta=0.3)
+    cfg = make_cfg(timestep=ts, reqhgt=1.0, spin_steps=40)
+    want = oracle.run_transient(veg, so, f, np.full(24, 50.0), np.full(24, -5.0), cfg, M, SM)
+    assert veg[L.veg_rows(M)["gsmax"]][0, 0] == 10.0 and veg[L.veg_rows(M)["refls"]][0, 0] == 0.85
+    assert_series_close(r["series"], want["series"], "snow = 1")
+    assert_state_close(r["state"], want["state"], what="snow = 1")
+
+
+def test_bench_workload_fortnight_sampled_columns(oracle):
+    """BASELINE config 3 as bench.py / tools/bench_year.py run it (same generator, same seeds), 2 x 10^5 columns x (200 spin-up +
+    336 hourly steps) in two weekly calls; 32 columns spread over the grid against the oracle, statistics combined as the year run does."""
+    import bench as B
+    ncol, hours = 200_000, 336
+    w = B.workload(ncol, hours, seed=1234)
+    cfg = B.make_cfg(w["ts"], 200)
+    samp = np.unique(np.linspace(0, ncol - 1, 32).astype(np.int64))
+    from microclimc_b200._lib import Context
+    ctx = Context(M, SM)
+    ctx.set_columns(w["veg"], w["soil"], w["lat"], w["lon"]); ctx.set_forcing(w["f"], w["fs"], w["fo"]); ctx.set_config(cfg)
+    ser = []; dropped = 0
+    for t0 in (0, 168):
+        r = ctx.run_transient(t0, t0 + 168, samp_idx=samp)
+        ser.append(r["series"]); dropped += int(np.count_nonzero(r["flags"] & 8))
+        assert not np.any(r["flags"] & 1)
+    got = np.concatenate(ser)
+    want = oracle.run_transient(w["veg"][:, samp], w["soil"][:, samp], w["f"], w["lat"][samp], w["lon"][samp], cfg, M, SM,
+                                fscale=w["fs"][:, samp], foffset=w["fo"][:, samp])
+    assert_series_close(got, want["series"], "C3 fortnight")
+    assert_state_close(ctx.get_state()[:, samp], want["state"], what="C3 fortnight state")
+    assert dropped <= ncol // 1000, "the bench workload should stay in the streaming form (%d columns dropped)" % dropped
+
+
+def test_columns_leaving_the_streaming_form_are_redone_by_the_general_kernel(oracle):
+    """A mixed grid: forest columns stay in the streaming form, short-grass columns (nodes under 0.12 m need the generic edge-wind
+    profile) leave it at once; those are flagged (bit 3), redone by the general kernel inside the same call — spin-up launch and run
+    launch each with its own list — and agree with the oracle like the rest.  A ragged count, so padding lanes are in play."""
+    ncol = 300 + 21
+    inp = transient_inputs(oracle, ncol=ncol, T=72)
+    g = S.vegp_deciduous(hgt=0.4, PAIt=1.5); g.update(x=0.4, lw=0.01, gsmax=0.4, hgtg=0.02)
+    vg, _ = S.ensemble(g, loam(oracle), ncol, M, SM, seed=77)
+    grass = np.zeros(ncol, bool); grass[::3] = True; grass[-5:] = True
+    inp["veg"][:, grass] = vg[:, grass]
+    cfg = make_cfg(spin_steps=40)
+    want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"])
+    ctx = _ctx(inp, cfg)
+    got = ctx.run_transient(samp_idx=np.arange(ncol))
+    assert np.array_equal((got["flags"] & 8) != 0, grass)
+    assert_series_close(got["series"], want["series"], "mixed grid")
+    assert_state_close(ctx.get_state(), want["state"], what="mixed grid")
+    np.testing.assert_allclose(got["stats"], want["stats"], rtol=0, atol=1e-6)
+    assert np.array_equal(got["flags"] & 1, want["flags"] & 1)
+    # a second call continues from the device state: the run launch's list alone
+    r2 = ctx.run_transient(40, 72, samp_idx=np.arange(ncol))
+    assert np.array_equal((r2["flags"] & 8) != 0, grass)
+
+
+def test_duplicate_sample_columns_are_rejected(oracle):
+    from microclimc_b200._lib import MicroclimcError
+    inp = transient_inputs(oracle, ncol=9, T=6)
+    ctx = _ctx(inp, make_cfg(spin_steps=5))
+    with pytest.raises((ValueError, MicroclimcError), match="duplicate"):
+        ctx.run_transient(samp_idx=np.array([1, 3, 3]))
+
+
+def test_in_process_split_over_all_visible_gpus_equals_one_gpu(oracle):
+    """The product's own multi-GPU path (mc_create(n_gpus): static contiguous column split, one worker thread per GPU, gathered into
+    the caller's arrays) must reproduce the single-GPU run bit for bit — on one GPU the split degenerates to one shard and the
+    test still drives the gather path with a ragged column count."""
+    from microclimc_b200._lib import lib
+    ng = max(1, min(8, lib().mc_device_count()))
+    inp = transient_inputs(oracle, ncol=1000 + 37, T=48)
+    cfg = make_cfg(spin_steps=30)
+    samp = np.array([0, 5, 517, 518, 1036])
+    a = _ctx(inp, cfg, 1); ra = a.run_transient(samp_idx=samp)
+    b = _ctx(inp, cfg, ng); rb = b.run_transient(samp_idx=samp)
+    np.testing.assert_array_equal(a.get_state(), b.get_state())
+    for k in ("series", "stats", "flags"):
+        np.testing.assert_array_equal(ra[k], rb[k])
