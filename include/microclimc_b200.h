@@ -72,6 +72,17 @@ int mc_set_columns(mc_ctx* ctx, int64_t ncol, const double* vegp, const double* 
  * (PAI(t) = PAI * pai_season[t], the batched form of .vegpsort, R/code.R:904-916). */
 int mc_set_forcing(mc_ctx* ctx, int64_t T, const double* forcing, const double* fscale, const double* foffset,
                    const double* pai_season);
+/* General time-varying vegetation (.vegpsort, R/code.R:904-916: vegp$PAI / vegp$pLAI as m x T matrices, vegp$zm0 of length T, what
+ * microctools::habitatvars returns): vegt [T][2m+1][nvt] = PAI[m], pLAI[m], zm0 of every forcing row, one series shared by all
+ * columns (nvt == 1) or one per column (nvt == ncol); T must equal the rows of the run that uses it (the forcing rows of
+ * mc_run_transient, the T of mc_run_steady: checked there, MC_ERR_ARG); NULL clears.  Transient runs with it take the general kernel
+ * (the streaming kernel hoists the geometry once per launch); mc_run_steady reads PAI and pLAI from it (NMR.R:730-735). */
+int mc_set_vegt(mc_ctx* ctx, int64_t T, int64_t nvt, const double* vegt);
+/* Soil moisture by depth (theta matrix of runmodel, R/code.R:1146-1154, consumed by soilk at code.R:790): thetaz [T][sm], shared by
+ * all columns (the per-column perturbation of the theta forcing row applies to every depth).  The forcing's theta column is then
+ * ignored.  R recycles the soil vector over the canopy layers inside leaftemp (code.R:416-437; canopy layer i sees soil node
+ * (i-1) mod sm), which is reproduced; sm > m is rejected.  T must equal the forcing rows of the run; NULL clears.  General kernel. */
+int mc_set_thetaz(mc_ctx* ctx, int64_t T, const double* thetaz);
 int mc_set_config(mc_ctx* ctx, const double* cfg /* [MC_C_N_] */);
 int mc_set_state(mc_ctx* ctx, const double* state /* [NSTATE][ncol] */);
 int mc_get_state(mc_ctx* ctx, double* state);

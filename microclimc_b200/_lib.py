@@ -21,6 +21,8 @@ SYMBOLS = {
     "mc_destroy": (None, [C.c_void_p]),
     "mc_set_columns": (C.c_int, [C.c_void_p, I64, PD, PD, PD, PD]),
     "mc_set_forcing": (C.c_int, [C.c_void_p, I64, PD, PD, PD, PD]),
+    "mc_set_vegt": (C.c_int, [C.c_void_p, I64, I64, PD]),
+    "mc_set_thetaz": (C.c_int, [C.c_void_p, I64, PD]),
     "mc_set_config": (C.c_int, [C.c_void_p, PD]),
     "mc_set_state": (C.c_int, [C.c_void_p, PD]),
     "mc_get_state": (C.c_int, [C.c_void_p, PD]),
@@ -142,6 +144,22 @@ class Context:
         forcing, fscale, foffset, pai_season = map(_f, (forcing, fscale, foffset, pai_season))
         self.T = forcing.shape[0]
         self._chk(lib().mc_set_forcing(self._h, self.T, _p(forcing), _p(fscale), _p(foffset), _p(pai_season)))
+
+    def set_vegt(self, vegt):
+        """vegt [T][2m+1][1 or ncol]: PAI[m], pLAI[m], zm0 per forcing row (.vegpsort); None clears."""
+        if vegt is None:
+            self._chk(lib().mc_set_vegt(self._h, 0, 0, None)); return
+        vegt = _f(vegt)
+        assert vegt.ndim == 3 and vegt.shape[1] == 2 * self.m + 1, vegt.shape
+        self._chk(lib().mc_set_vegt(self._h, vegt.shape[0], vegt.shape[2], _p(vegt)))
+
+    def set_thetaz(self, thetaz):
+        """thetaz [T][sm]: soil moisture by depth per forcing row; None clears."""
+        if thetaz is None:
+            self._chk(lib().mc_set_thetaz(self._h, 0, None)); return
+        thetaz = _f(thetaz)
+        assert thetaz.ndim == 2 and thetaz.shape[1] == self.sm, thetaz.shape
+        self._chk(lib().mc_set_thetaz(self._h, thetaz.shape[0], _p(thetaz)))
 
     def set_config(self, cfg):
         cfg = _f(cfg); assert cfg.size == 13

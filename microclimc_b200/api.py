@@ -85,27 +85,63 @@ def _snowsort(vegp, snow, i=0):
 
 
 def _season_of(vegp):
-    """Time-varying PAI matrix m x T -> (static vegp, season[T]) when PAI[:, t] = PAI[:, 0] * s[t]; else error."""
+    """Time-varying vegp (PAI / pLAI as m x T matrices, zm0 of length T; what .vegpsort indexes, R/code.R:904-916) ->
+    (static vegp, season[T] or None, vegt [T][2m+1] or None).
+
+    When only PAI varies and PAI[:, t] = PAI[:, 0] * s[t] exactly, the cheap separable form (pai_season) is used; any other
+    time dependence is passed through in full as `vegt` rows (PAI[m], pLAI[m], zm0 per time step)."""
     P = np.asarray(vegp["PAI"], float)
-    if P.ndim == 1:
-        return vegp, None
-    base = P[:, 0]
-    with np.errstate(divide="ignore", invalid="ignore"):
-        s = np.nanmean(np.where(base[:, None] > 0, P / base[:, None], np.nan), axis=0)
-    if not np.allclose(base[:, None] * s[None, :], P, rtol=1e-12, atol=0):
-        raise NotImplementedError("time-varying PAI must be separable (profile x seasonal factor) for the batched GPU path")
-    v = dict(vegp); v["PAI"] = base.copy()
     pl = np.asarray(vegp["pLAI"], float)
-    if pl.ndim == 2:
-        if not np.allclose(pl, pl[:, :1]):
-            raise NotImplementedError("time-varying pLAI is not supported by the batched GPU path")
-        v["pLAI"] = pl[:, 0].copy()
-    if np.size(vegp["zm0"]) > 1:
-        z = np.asarray(vegp["zm0"], float)
-        if not np.allclose(z, z[0]):
-            raise NotImplementedError("time-varying zm0 is not supported by the batched GPU path")
-        v["zm0"] = float(z[0])
-    return v, np.ascontiguousarray(s)
+    z0 = np.atleast_1d(np.asarray(vegp["zm0"], float))
+    if P.ndim == 1 and pl.ndim == 1 and z0.size == 1:
+        return vegp, None, None
+    T = P.shape[1] if P.ndim == 2 else (pl.shape[1] if pl.ndim == 2 else z0.size)
+    v = dict(vegp)
+    v["PAI"] = P[:, 0].copy() if P.ndim == 2 else P
+    v["pLAI"] = pl[:, 0].copy() if pl.ndim == 2 else pl
+    v["zm0"] = float(z0[0])
+    pl_static = pl.ndim == 1 or np.array_equal(pl, np.repeat(pl[:, :1], pl.shape[1], axis=1))
+    z_static = z0.size == 1 or np.all(z0 == z0[0])
+    if P.ndim == 2 and pl_static and z_static:
+        base = P[:, 0]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            s = np.nanmean(np.where(base[:, None] > 0, P / base[:, None], np.nan), axis=0)
+        if np.all(np.isfinite(s)) and np.allclose(base[:, None] * s[None, :], P, rtol=1e-12, atol=0):
+            return v, np.ascontiguousarray(s), None
+    m = P.shape[0]
+    vt = np.empty((T, 2 * m + 1))
+    vt[:, :m] = P.T if P.ndim == 2 else P[None, :]
+    vt[:, m:2 * m] = pl.T if pl.ndim == 2 else pl[None, :]
+    vt[:, 2 * m] = z0 if z0.size > 1 else z0[0]
+    return v, None, vt
+
+
+def _veg_time(vl, snow=None):
+    """Per-column vegp lists -> (static lists, shared season or None, vegt [T][2m+1][1 or ncol] or None)."""
+    out, seasons, vts = [], [], []
+    for v in vl:
+        v2, s, vt = _season_of(v)
+        out.append(v2); seasons.append(s); vts.append(vt)
+    if all(s is None for s in seasons) and all(vt is None for vt in vts):
+        return out, None, None
+    same_season = all(s is not None for s in seasons) and all(np.array_equal(s, seasons[0]) for s in seasons)
+    if same_season:
+        return out, seasons[0], None
+    # general form: every column gets its rows (columns given in separable form are expanded)
+    T = next((vt.shape[0] for vt in vts if vt is not None), None) or next(s.size for s in seasons if s is not None)
+    m = len(np.asarray(out[0]["PAI"]))
+    full = np.empty((T, 2 * m + 1, len(vl)))
+    for c, (v2, s, vt) in enumerate(zip(out, seasons, vts)):
+        if vt is None:
+            f = np.ones(T) if s is None else s
+            full[:, :m, c] = np.asarray(v2["PAI"], float)[None, :] * f[:, None]
+            full[:, m:2 * m, c] = np.asarray(v2["pLAI"], float)[None, :]
+            full[:, 2 * m, c] = v2["zm0"]
+        else:
+            full[:, :, c] = vt
+    if len(vl) > 1 and all(np.array_equal(full[:, :, c], full[:, :, 0]) for c in range(1, len(vl))):
+        full = full[:, :, :1]
+    return out, None, np.ascontiguousarray(full)
 
 
 def _state_to_list(st, m, sm, c=0):
@@ -212,26 +248,29 @@ def _transient_ctx(climdata, veg, soil, m, sm, lat, long, cfg, theta, fscale, fo
 
 
 def _theta_series(theta, T, sm):
+    """runmodel's theta argument (R/code.R:1093-1100, 1146-1154) -> (theta for the forcing column, thetaz [T][sm] or None)."""
     th = np.asarray(theta, float)
     if th.ndim == 0:
-        return float(th)
+        return float(th), None
     if th.ndim == 2:
-        if th.shape[0] != 1 and not np.allclose(th, th[:1]):
-            raise NotImplementedError("depth-varying soil moisture is not supported by the batched GPU path")
-        return th[0]
+        if th.shape[0] == 1:
+            return th[0], None
+        if th.shape != (sm, T):
+            raise ValueError("theta matrix must have one row per soil layer and one column per time step")
+        return th[0], np.ascontiguousarray(th.T)
+    if th.size == 1:
+        return float(th[0]), None
+    if th.size == sm:                       # code.R:1151-1153 (tested before the time-series reading, as R does when sm == T)
+        return float(th[0]), np.ascontiguousarray(np.repeat(th[None, :], T, axis=0))
     if th.size == T:
-        return th
-    if th.size == sm:
-        if not np.allclose(th, th[0]):
-            raise NotImplementedError("depth-varying soil moisture is not supported by the batched GPU path")
-        return float(th[0])
-    raise ValueError("theta must be a scalar, a vector over time or a 1-row matrix")
+        return th, None
+    raise ValueError("theta must be a scalar, a vector over time or soil layers, or a matrix [soil layers x time]")
 
 
 def spinup(climdata, vegp, soilp, lat, long, edgedist=100, reqhgt=None, sdepth=2, zu=2, theta=0.3, thetap=0.3, merid=0, dst=0,
            n=0.6, plotout=False, steps=200, metopen=True, windhgt=2, zlafact=1, surfwet=1):
     """R/code.R:982-1013 (plotout is accepted and ignored: graphics are out of scope)."""
-    if np.atleast_1d(theta)[0] != np.atleast_1d(thetap)[0]:
+    if not np.array_equal(np.atleast_1d(theta), np.atleast_1d(thetap)):
         raise NotImplementedError("spinup with thetap != theta")
     vegp1 = _vegpsort(vegp, 0)
     veg, soil, m, sm = _pack(vegp1, soilp)
@@ -240,6 +279,10 @@ def spinup(climdata, vegp, soilp, lat, long, edgedist=100, reqhgt=None, sdepth=2
     ctx = Context(m, sm)
     ctx.set_columns(veg, soil, np.array([lat], float), np.array([long], float))
     ctx.set_forcing(f)
+    if np.size(theta) > 1:                                     # theta by soil layer (runmodel passes theta[, 1], code.R:1158)
+        if np.size(theta) != sm:
+            raise ValueError("theta must be a scalar or one value per soil layer")
+        ctx.set_thetaz(np.repeat(np.asarray(theta, float)[None, :], f.shape[0], axis=0))
     ctx.set_config(_cfg(ts, edgedist, reqhgt, zu, merid, dst, n, metopen, windhgt, zlafact, surfwet, steps))
     ctx.spinup(steps)
     return _state_to_list(ctx.get_state(), m, sm)
@@ -251,19 +294,13 @@ def _prepare_transient(climdata, vegp, soilp, lat, long, edgedist, reqhgt, zu, t
     char = isinstance(reqhgt, str)
     if char and reqhgt not in ("all", "allclim"):
         raise ValueError("input reqhgt no recognised\n")                                     # code.R:1136-1139
-    season = None
+    season = vegt = None
     if not isinstance(vegp, np.ndarray):
         vl = list(vegp) if isinstance(vegp, (list, tuple)) else [vegp]
-        vl2 = []
-        for v in vl:
-            v = _snowsort(v, snow, 0)                                                       # Q3: snow[1] decides for the whole run
-            v, s = _season_of(v)
-            if s is not None:
-                if season is not None and not np.array_equal(s, season):
-                    raise NotImplementedError("all columns must share the seasonal PAI factor")
-                season = s
-            vl2.append(v)
-        vegp = vl2
+        vl = [_snowsort(v, snow, 0) for v in vl]                                             # Q3: snow[1] decides for the whole run
+        vegp, season, vegt = _veg_time(vl)
+        if vegt is not None and snow is not None and not (np.ndim(snow) == 0 and _isna(snow)) and np.atleast_1d(snow)[0] == 1:
+            vegt[:, -1, :] = 0.024                                                          # .snowsort after .vegpsort (code.R:1196-1197)
     veg, soil, m, sm = _pack(vegp, soilp)
     ncol = veg.shape[1]
     _check_pai(veg, m)
@@ -281,9 +318,15 @@ def _prepare_transient(climdata, vegp, soilp, lat, long, edgedist, reqhgt, zu, t
     if (not metopen) and np.any(windhgt < hg):
         raise ValueError("When metopen is FALSE, windhgt must be above canopy\n")            # code.R:1141-1143
     T = len(climdata["temp"])
-    th = _theta_series(theta, T, sm)
+    th, thetaz = _theta_series(theta, T, sm)
     spin = steps if previn is None else 0
     ctx, f, ts = _transient_ctx(climdata, veg, soil, m, sm, lat, long, None, th, fscale, foffset, season, n_gpus)
+    if vegt is not None:
+        if vegt.shape[0] != T:
+            raise ValueError("time-varying vegp must have one column per time step of climdata")
+        ctx.set_vegt(vegt)
+    if thetaz is not None:
+        ctx.set_thetaz(thetaz)
     ctx.set_config(_cfg(ts, edgedist, rq, zu, merid, dst, n, metopen, windhgt, zlafact, surfwet, spin, 1 if char else 0))
     if previn is not None:
         st = previn if isinstance(previn, np.ndarray) else np.concatenate([_list_to_state(p, m, sm) for p in
@@ -391,15 +434,10 @@ def runmodelS_batch(climdata, vegp, soilp, nmrout, reqhgt, lat, long, metopen=Tr
                     want_out=True):
     """Batched `runmodelS` (R/NicheMapRcode.R:717-885, incl. the .runmodelsnow overlay). nmrout: the reference's list
     (shared by all columns) or a packed array [T][11] / [T][11][ncol] (layout.STEADY_NMR)."""
-    season = None
+    season = vegt = None
     if not isinstance(vegp, np.ndarray):
         vl = list(vegp) if isinstance(vegp, (list, tuple)) else [vegp]
-        vl2 = []
-        for v in vl:
-            v, s = _season_of(v)
-            season = s if s is not None else season
-            vl2.append(v)
-        vegp = vl2
+        vegp, season, vegt = _veg_time(vl)
     veg, soil, m, sm = _pack(vegp, soilp)
     ncol = veg.shape[1]
     hg = veg[L.veg_rows(m)["hgt"]][0]
@@ -411,6 +449,10 @@ def runmodelS_batch(climdata, vegp, soilp, nmrout, reqhgt, lat, long, metopen=Tr
     ctx = Context(m, sm, n_gpus)
     ctx.set_columns(veg, soil, np.broadcast_to(np.asarray(lat, float), (ncol,)).copy(),
                     np.broadcast_to(np.asarray(long, float), (ncol,)).copy())
+    if vegt is not None:
+        if vegt.shape[0] != T:
+            raise ValueError("time-varying vegp must have one column per time step of climdata")
+        ctx.set_vegt(vegt)
     r = ctx.run_steady(clim, nmr, np.array([reqhgt, 1.0 if metopen else 0.0, windhgt, surfwet, groundem], float), season, want_out=want_out)
     r["nmr"] = nmr; r["kernel_ms"] = ctx.last_kernel_ms()
     return r

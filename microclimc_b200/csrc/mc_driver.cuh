@@ -84,6 +84,23 @@ MC_HD void run_column(const TransientArgs& a, long long c, bool live = true) {
     for (long long t = 0; t < a.T; ++t) s += a.forcing[t * F_N + F_TAIR];
     tmean = s / (double)a.T;
   }
+  // .vegpsort(vegp, t + 1) (code.R:904-916): PAI, pLAI and zm0 of forcing row t
+  auto vegpsort = [&](long long t) {
+    const long long cc = (a.nvt == 1) ? 0 : c;
+    const double* row = a.vegt + t * (2 * m + 1) * a.nvt + cc;
+    for (int i = 1; i <= m; ++i) { col.PAIbase[i] = row[(long long)(i - 1) * a.nvt]; col.pLAI[i] = row[(long long)(m + i - 1) * a.nvt]; }
+    col.zm0 = row[(long long)(2 * m) * a.nvt];
+  };
+  // theta[, t + 1] of this column (code.R:1202): the per-column perturbation of the theta row applies to every depth
+  double thz[MS + 1], thz0[MS + 1];
+  auto theta_at = [&](long long t, double* o) {
+    for (int j = 0; j < a.sm; ++j) {
+      double th = a.thetaz[t * a.sm + j];
+      if (a.fscale && a.foffset) { th = th * a.fscale[(long long)F_THETA * a.ncol + c] + a.foffset[(long long)F_THETA * a.ncol + c]; if (th < 0.001) th = 0.001; }
+      o[j] = th;
+    }
+  };
+  if (a.thetaz) theta_at(0, thz0);
   const double reqhgt = a.cfg.reqhgt;
   const double spinhgt = a.charmode ? col.hgt / 2 : ((reqhgt == reqhgt && reqhgt > 0) ? reqhgt : NAN);   // code.R:1136-1140
   RunCfg cl = a.cfg;
@@ -91,11 +108,13 @@ MC_HD void run_column(const TransientArgs& a, long long c, bool live = true) {
   if (a.spin_steps > 0) {
     RunCfg cs = a.cfg;
     if (!a.spin_standalone) { cs.reqhgt = spinhgt; cs.zlafact = 1; cs.surfwet = 1; }                     // Q22
+    if (a.vegt) vegpsort(0);
     col.precompute(cs, a.season ? a.season[0] : 1.0);
     col.paraminit(col.hgt, f0[F_TAIR], f0[F_U], f0[F_RELHUM], tmean, f0[F_RSW]);
     col.precompute_leafgeom(cs);
     Forcing fc = {f0[F_TAIR], f0[F_RELHUM], f0[F_PK], f0[F_U], tmean, f0[F_SKYEM], f0[F_RSW], f0[F_DP], f0[F_JD], f0[F_LT],
                   f0[F_THETA], f0[F_THETA]};
+    if (a.thetaz) { fc.theta = thz0[0]; fc.thetap = thz0[0]; fc.thz = thz0; }                             // theta[,1], theta[,1] (code.R:1158)
     double Hsum = 0;
     for (int i = 1; i <= a.spin_steps; ++i) {
       MC_CTA_SYNC();
@@ -104,9 +123,11 @@ MC_HD void run_column(const TransientArgs& a, long long c, bool live = true) {
       col.H = Hsum / i;                                                                                   // previn$H <- mean(H)
     }
     bool same = (cs.reqhgt == cl.reqhgt) || (cs.reqhgt != cs.reqhgt && cl.reqhgt != cl.reqhgt);
-    if (!same || a.season || cs.zlafact != cl.zlafact) { col.precompute(cl, a.season ? a.season[a.t0] : 1.0); col.precompute_leafgeom(cl); }
+    if (a.vegt) vegpsort(a.t0);
+    if (!same || a.season || a.vegt || cs.zlafact != cl.zlafact) { col.precompute(cl, a.season ? a.season[a.t0] : 1.0); col.precompute_leafgeom(cl); }
   } else {
     col.load_state(a.state, a.ncol, c);
+    if (a.vegt) vegpsort(a.t0);
     col.precompute(cl, a.season ? a.season[a.t0] : 1.0);
     col.precompute_leafgeom(cl);
   }
@@ -118,9 +139,11 @@ MC_HD void run_column(const TransientArgs& a, long long c, bool live = true) {
   for (long long t = a.t0; t < a.t1; ++t) {
     MC_CTA_SYNC();
     forcing_at(a, t, c, f);
-    if (a.season && t > a.t0) { col.precompute(cl, a.season[t]); col.precompute_leafgeom(cl); }
+    if (a.vegt && t > a.t0) vegpsort(t);
+    if ((a.season || a.vegt) && t > a.t0) { col.precompute(cl, a.season ? a.season[t] : 1.0); col.precompute_leafgeom(cl); }
     Forcing fc = {f[F_TAIR], f[F_RELHUM], f[F_PK], f[F_U], tsoil, f[F_SKYEM], f[F_RSW], f[F_DP], f[F_JD], f[F_LT], f[F_THETA],
                   /*Q2*/ f0[F_THETA]};
+    if (a.thetaz) { theta_at(t, thz); fc.theta = thz[0]; fc.thetap = thz0[0]; fc.thz = thz; }             // thetap: theta[1, 1] (Q2)
     int ng = col.step(fc, cl);
     if (ng > 1) flag |= 2;
     double o[8];

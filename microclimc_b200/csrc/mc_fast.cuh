@@ -203,6 +203,7 @@ struct DirectMem {
   MC_HD int warp_max(int v) const { return v; }
   MC_HD void st_stream(double* p, double v) const { *p = v; }
   MC_HD void st_keep(double* p, double v) const { *p = v; }
+  MC_HD double ld_keep(const double* p) const { return *p; }
   MC_HD void discard_AB() {}
   MC_HD void discard_C() {}
   MC_HD void step_begin() {}
@@ -274,6 +275,11 @@ MC_D unsigned long long l2_evict_last_policy() {
 MC_D void st_hint(double* p, double v, unsigned long long pol) {
   asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
 }
+MC_D double ld_hint(const double* p, unsigned long long pol) {
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
 MC_D void discard_line(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
 
 struct PipeMem {
@@ -296,6 +302,10 @@ struct PipeMem {
   MC_D void st_stream(double* p, double v) const { *p = v; }
   MC_D void st_keep(double* p, double v) const { *p = v; }
 #endif
+#ifndef MC_KEEP
+#define MC_KEEP 0          // bit 0: per-column forcing perturbation rows, bit 1: the state's scalar rows — loaded / stored with the L2 evict-last policy
+#endif
+  MC_D double ld_keep(const double* p) const { return ld_hint(p, pol_keep); }
   // all lines of the A->B rows (GTN, UZN of every layer) / of the B->C rows (TT, EAL, contiguous) of this tile
   MC_D void discard_AB() {
 #if MC_L2HINT >= 2
@@ -568,8 +578,13 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   const int m = L.m, sm = L.sm;
   const double* const P = mem.P; double* const S = mem.S; double* const W = mem.W;
   auto p0 = [=](int r) { return P[(long long)r * kTile]; };
+#if defined(__CUDA_ARCH__) && (MC_KEEP & 2)
+  auto s0 = [&](int r) { return mem.ld_keep(S + (long long)r * kTile); };
+  auto sput = [&](int r, double v) { mem.st_keep(S + (long long)r * kTile, v); };
+#else
   auto s0 = [=](int r) { return S[(long long)r * kTile]; };
   auto sput = [=](int r, double v) { S[(long long)r * kTile] = v; };
+#endif
   auto wput = [=](int i, int r, double v) { W[(long long)L.wl(i, r) * kTile] = v; };
   auto wget = [=](int i, int r) { return W[(long long)L.wl(i, r) * kTile]; };
   MC_TICK(7);
@@ -1242,6 +1257,33 @@ MC_HD double column_tmean(const TransientArgs& a, long long c) {
   return s / (double)a.T;
 }
 
+// forcing_at (mc_driver.cuh) with the per-column perturbation rows read through the accessor (L2 evict-last when MC_KEEP bit 0: the
+// same 16 values are read every step, but 10 KB of streamed rows per column-step would push them out of L2 in between)
+template <class Mem>
+MC_HD void fast_forcing_at(const Mem& mem, const TransientArgs& a, long long t, long long c, double* f) {
+#if defined(__CUDA_ARCH__) && (MC_KEEP & 1)
+  const double* row = a.forcing + t * F_N;
+#pragma unroll
+  for (int v = 0; v < F_N; ++v) f[v] = row[v];
+  if (a.fscale && a.foffset) {
+    double sc[kNPert], of[kNPert];
+#pragma unroll
+    for (int v = 0; v < kNPert; ++v) { sc[v] = mem.ld_keep(a.fscale + (long long)v * a.ncol + c); of[v] = mem.ld_keep(a.foffset + (long long)v * a.ncol + c); }
+#pragma unroll
+    for (int v = 0; v < kNPert; ++v) f[v] = row[v] * sc[v] + of[v];
+    if (f[F_RELHUM] > 100) f[F_RELHUM] = 100;
+    if (f[F_RELHUM] < 1) f[F_RELHUM] = 1;
+    if (f[F_U] < 0) f[F_U] = 0;
+    if (f[F_SKYEM] > 1) f[F_SKYEM] = 1;
+    if (f[F_SKYEM] < 0) f[F_SKYEM] = 0;
+    if (f[F_RSW] < 0) f[F_RSW] = 0;
+    if (f[F_THETA] < 0.001) f[F_THETA] = 0.001;
+  }
+#else
+  forcing_at(a, t, c, f);
+#endif
+}
+
 // The whole launch for one column: spin_mode 1 = paraminit + spin-up steps on forcing row 0 (code.R:982-1013);
 // spin_mode 0 = steps [t0, t1) of runmodel's loop with the output harvest (code.R:1193-1266).
 // `c` is the source column (clamped for padding lanes), `live` false for padding lanes.
@@ -1332,7 +1374,7 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
   fast_park_constants(mem);
   for (long long it = 0; it < nsteps; ++it) {
     const long long tt = spin ? 0 : t.t0 + it;
-    forcing_at(t, tt, c, f);
+    fast_forcing_at(mem, t, tt, c, f);
     const Forcing fc = {f[F_TAIR], f[F_RELHUM], f[F_PK], f[F_U], tsoil, f[F_SKYEM], f[F_RSW], f[F_DP], f[F_JD], f[F_LT], f[F_THETA],
                         /*Q2*/ f0[F_THETA]};
     const bool emit = !dead && (it == nsteps - 1 || (slot >= 0 && t.full));

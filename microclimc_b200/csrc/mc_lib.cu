@@ -222,9 +222,10 @@ struct Shard {
   HBuf hser, hfull;
   cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
   DBuf vegp, soilp, lat, lon, state, state_bak, fscale, foffset, forcing, season, tsoil, stats, series, full, samp_of, flags,
-      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fsol, fP, fS, fW, dbg, ffail, flist, fcount, samp_cols;
+      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fsol, fP, fS, fW, dbg, ffail, flist, fcount, samp_cols, vegt, thetaz;
   bool fast_attr = false;
   bool has_pert = false, has_season = false, has_state = false, bak_valid = false;
+  long long nvt = 0, vegt_T = 0, thetaz_T = 0; bool has_thetaz = false;       // time-varying vegetation / soil moisture by depth loaded (mc_set_vegt, mc_set_thetaz)
   float ms = 0; long long launches = 0, pending_launches = 0;   // pending: kernels of mc_set_forcing, reported with the next run
   // replay info for mc_bench_resident
   int last_kind = 0;   // 0 none, 1 transient, 2 steady
@@ -459,7 +460,7 @@ void mc_destroy(mc_ctx* ctx) {
     DBuf* bufs[] = {&s.vegp, &s.soilp, &s.lat, &s.lon, &s.state, &s.state_bak, &s.fscale, &s.foffset, &s.forcing, &s.season, &s.tsoil,
                     &s.stats, &s.series, &s.full, &s.samp_of, &s.flags, &s.args6, &s.clim8, &s.theta, &s.thetap, &s.nmerged,
                     &s.sclim, &s.snmr, &s.sseason, &s.sout, &s.spart, &s.ssol, &s.fsol, &s.fP, &s.fS, &s.fW, &s.dbg, &s.ffail, &s.flist,
-                    &s.fcount, &s.samp_cols};
+                    &s.fcount, &s.samp_cols, &s.vegt, &s.thetaz};
     for (DBuf* b : bufs) b->release();
     s.hser.release(); s.hfull.release();
     if (s.e0) cudaEventDestroy(s.e0);
@@ -478,7 +479,7 @@ int mc_set_columns(mc_ctx* ctx, int64_t ncol, const double* vegp, const double* 
     Shard& s = ctx->shards[i];
     s.c0 = std::min<long long>((long long)i * per, ncol);
     s.nc = std::min<long long>(per, ncol - s.c0);
-    s.has_state = false; s.has_pert = false; s.last_kind = 0; s.samp_valid = false;
+    s.has_state = false; s.has_pert = false; s.last_kind = 0; s.samp_valid = false; s.nvt = 0; s.has_thetaz = false;
   }
   const int NV = mc_nveg(ctx->m), NSo = mc_nsoil(ctx->sm), NSt = mc_nstate(ctx->m, ctx->sm);
   return for_shards(ctx, [&](Shard& s) -> int {
@@ -520,6 +521,39 @@ int mc_set_forcing(mc_ctx* ctx, int64_t T, const double* forcing, const double* 
       CU(cudaMemcpyAsync(s.season.p, pai_season, sizeof(double) * T, cudaMemcpyHostToDevice, s.st));
     }
     CU(cudaStreamSynchronize(s.st));
+    return 0;
+  });
+}
+
+int mc_set_vegt(mc_ctx* ctx, int64_t T, int64_t nvt, const double* vegt) {
+  if (!ctx || ctx->ncol <= 0) return fail(ctx, MC_ERR_ARG, "mc_set_vegt: set columns first");
+  if (!vegt) { for (auto& s : ctx->shards) s.nvt = 0; return 0; }
+  if (T <= 0) return fail(ctx, MC_ERR_ARG, "mc_set_vegt: T must be positive");
+  if (nvt != 1 && nvt != ctx->ncol) return fail(ctx, MC_ERR_ARG, "mc_set_vegt: nvt must be 1 (shared series) or ncol");
+  const long long rows = T * (2 * ctx->m + 1), ncol = ctx->ncol;
+  return for_shards(ctx, [&](Shard& s) -> int {
+    if (s.nc == 0) return 0;
+    const long long n = (nvt == 1) ? 1 : s.nc;
+    CU(s.vegt.need(sizeof(double) * rows * n));
+    if (nvt == 1) CU(cudaMemcpyAsync(s.vegt.p, vegt, sizeof(double) * rows, cudaMemcpyHostToDevice, s.st));
+    else CU(h2d_rows(s.vegt.as<double>(), vegt, rows, ncol, s.c0, s.nc, s.st));
+    CU(cudaStreamSynchronize(s.st));
+    s.nvt = n; s.vegt_T = T;
+    return 0;
+  });
+}
+int mc_set_thetaz(mc_ctx* ctx, int64_t T, const double* thetaz) {
+  if (!ctx || ctx->ncol <= 0) return fail(ctx, MC_ERR_ARG, "mc_set_thetaz: set columns first");
+  if (!thetaz) { for (auto& s : ctx->shards) s.has_thetaz = false; return 0; }
+  if (T <= 0) return fail(ctx, MC_ERR_ARG, "mc_set_thetaz: T must be positive");
+  if (ctx->sm > ctx->m) return fail(ctx, MC_ERR_ARG, "mc_set_thetaz: soil moisture by depth needs sm <= m (R recycles the soil vector over the canopy layers)");
+  const int sm = ctx->sm;
+  return for_shards(ctx, [&](Shard& s) -> int {
+    if (s.nc == 0) return 0;
+    CU(s.thetaz.need(sizeof(double) * T * sm));
+    CU(cudaMemcpyAsync(s.thetaz.p, thetaz, sizeof(double) * T * sm, cudaMemcpyHostToDevice, s.st));
+    CU(cudaStreamSynchronize(s.st));
+    s.has_thetaz = true; s.thetaz_T = T;
     return 0;
   });
 }
@@ -629,6 +663,10 @@ static int run_transient_impl(mc_ctx* ctx, int64_t t0, int64_t t1, int spin_step
   if (spin_steps <= 0) for (auto& s : ctx->shards) if (s.nc && !s.has_state)
     return fail(ctx, MC_ERR_STATE, "mc_run_transient: no state on the device (spin-up disabled and no mc_set_state / mc_paraminit)");
   for (int64_t j = 0; j < nsamp; ++j) if (samp_idx[j] < 0 || samp_idx[j] >= ctx->ncol) return fail(ctx, MC_ERR_ARG, "mc_run_transient: samp_idx out of range");
+  for (auto& s : ctx->shards) {
+    if (s.nc && s.nvt && s.vegt_T != ctx->T) return fail(ctx, MC_ERR_ARG, "mc_run_transient: mc_set_vegt rows differ from the forcing rows");
+    if (s.nc && s.has_thetaz && s.thetaz_T != ctx->T) return fail(ctx, MC_ERR_ARG, "mc_run_transient: mc_set_thetaz rows differ from the forcing rows");
+  }
   if (nsamp > 1 && (series || fullseries)) {          // a column may be sampled once: its device slot is written once
     std::vector<int64_t> srt(samp_idx, samp_idx + nsamp);
     std::sort(srt.begin(), srt.end());
@@ -656,6 +694,8 @@ static int run_transient_impl(mc_ctx* ctx, int64_t t0, int64_t t1, int spin_step
     a.forcing = s.forcing.as<double>(); a.fsol = s.fsol.as<double>();
     a.fscale = s.has_pert ? s.fscale.as<double>() : nullptr; a.foffset = s.has_pert ? s.foffset.as<double>() : nullptr;
     a.season = s.has_season ? s.season.as<double>() : nullptr;
+    a.vegt = s.nvt ? s.vegt.as<double>() : nullptr; a.nvt = s.nvt;
+    a.thetaz = s.has_thetaz ? s.thetaz.as<double>() : nullptr;
     a.state = s.state.as<double>(); a.cfg = cfg; a.spin_steps = spin_steps; a.charmode = charmode; a.spin_standalone = standalone;
     if (tsoil) {
       CU(s.tsoil.need(sizeof(double) * s.nc));
@@ -761,6 +801,10 @@ int mc_run_steady(mc_ctx* ctx, int64_t T, const double* clim, const double* nmr,
     a.ncol = s.nc; a.m = m; a.sm = sm; a.T = T; a.vegp = s.vegp.as<double>(); a.soilp = s.soilp.as<double>();
     a.lat = s.lat.as<double>(); a.lon = s.lon.as<double>(); a.clim = s.sclim.as<double>(); a.nmr = s.snmr.as<double>();
     a.nmr_percol = nmr_percol; a.season = pai_season ? s.sseason.as<double>() : nullptr;
+    if (s.nvt) {
+      if (s.vegt_T != T) { s.err = "mc_run_steady: mc_set_vegt rows differ from T"; return MC_ERR_ARG; }
+      a.vegt = s.vegt.as<double>(); a.nvt = s.nvt;
+    }
     a.reqhgt = reqhgt; a.metopen = scfg[MC_SG_METOPEN] != 0; a.windhgt = scfg[MC_SG_WINDHGT]; a.surfwet = scfg[MC_SG_SURFWET];
     if (out) { CU(s.sout.need(sizeof(double) * T * MC_SO_N * s.nc)); a.out = s.sout.as<double>(); }
     if (stats) {

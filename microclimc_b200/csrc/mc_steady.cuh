@@ -20,6 +20,8 @@ struct SteadyArgs {
   const double* nmr;         // [T][11] or [T][11][ncol]: D0cm, WC0cm, SNOWDEP(cm), SN1..SN8
   int nmr_percol;
   const double* season;      // [T] or null
+  const double* vegt;        // [T][2m+1][nvt] or null: PAI[m], pLAI[m] (zm0 unused here) per hour (vegp$PAI as m x T matrix, NMR.R:730-735)
+  long long nvt;             // 1: shared by all columns, ncol: per column
   const double* sol;         // [T][13] eot, sin / cos of the declination, dp, ph, ph0, es, eref, cp, (tair + 273.15)^4, gDh, ginu, ggq per hour (k_steady_hour), or null: computed in place
   double reqhgt; int metopen; double windhgt, surfwet;
   double* out;               // [T][7][ncol] or null
@@ -466,7 +468,7 @@ template <int MM>
 MC_HD void steady_column(const SteadyArgs& A, long long c, int chunk, int nchunk, bool live = true) {
   SteadyCol<MM> col;
   col.load(A, c);
-  if (!A.season) col.prep(A, 1.0);
+  if (!A.season && !A.vegt) col.prep(A, 1.0);
   const long long per = (A.T + nchunk - 1) / nchunk;
   const long long tb = (long long)chunk * per;
   const long long te = (tb + per < A.T) ? tb + per : A.T;
@@ -479,7 +481,11 @@ MC_HD void steady_column(const SteadyArgs& A, long long c, int chunk, int nchunk
     // +4.5 % on config 2, +3 % on config 4; a second rendezvous in the middle of the hour costs 2.5 % instead.
     __syncthreads();
 #endif
-    if (A.season) col.prep(A, A.season[t]);
+    if (A.vegt) {
+      const double* row = A.vegt + t * (2 * A.m + 1) * A.nvt + (A.nvt == 1 ? 0 : c);
+      for (int i = 1; i <= A.m; ++i) { col.PAIb[i] = row[(long long)(i - 1) * A.nvt]; col.pLAIb[i] = row[(long long)(A.m + i - 1) * A.nvt]; }
+      col.prep(A, 1.0);
+    } else if (A.season) col.prep(A, A.season[t]);
     const double* cr = A.clim + t * 9;
     double nm[11];
     if (A.nmr_percol) { for (int q = 0; q < 11; ++q) nm[q] = A.nmr[(t * 11 + q) * A.ncol + c]; }

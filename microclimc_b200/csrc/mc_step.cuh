@@ -24,7 +24,8 @@ struct RunCfg {          // runonestep / runmodel scalar arguments (code.R:687-6
   int metopen;
   int dbg;                 // timing ablations of the streaming kernel (MC_DBG_SKIP; results are meaningless when non-zero)
 };
-struct Forcing { double tair, relhum, pk, u, tsoil, skyem, Rsw, dp, jd, lt, theta, thetap; };
+// thz: soil moisture by soil node of this step (theta[, i] of runmodel's theta matrix, code.R:1146-1154, 1202) or null; theta == thz[0] then
+struct Forcing { double tair, relhum, pk, u, tsoil, skyem, Rsw, dp, jd, lt, theta, thetap; const double* thz = nullptr; };
 
 // state / vegp / soilp row indices of the column-interleaved arrays (include/microclimc_b200.h)
 enum { V_HGT, V_X, V_LW, V_CD, V_HGTG, V_ZM0, V_REFLS, V_REFG, V_REFW, V_REFLP, V_VEGEM, V_GSMAX, V_Q50, V_CPW, V_PHW,
@@ -294,9 +295,9 @@ struct Column {
     for (int i = 1; i <= m; ++i) if (zprev[i] != z[i]) zprev_is_z = false;
   }
 
-  MC_NI void soilk(double timestep, double theta) {
-    if (theta == th_cache) return;
-    th_cache = theta;
+  MC_NI void soilk(double timestep, double theta, const double* thz = nullptr) {
+    if (!thz && theta == th_cache) return;
+    th_cache = thz ? -1e300 : theta;
     double A = 0.65 - 0.78 * rho + 0.6 * rho * rho;
     double B = 1.06 * rho;
     double C = 1 + 2.6 / sqrt(Mc);
@@ -305,6 +306,11 @@ struct Column {
     double lam = A + B * theta - (A - D) * exp(-((ct * ct) * (ct * ct)));
     double Cv = (2.128 * Vq + 2.385 * Vm + 2.496 * Vo_s + 4.18 * theta) * 1e6;
     for (int i = 1; i <= sm; ++i) {
+      if (thz) {                                   // moisture by depth: node i from its own theta
+        ct = C * thz[i - 1];
+        lam = A + B * thz[i - 1] - (A - D) * exp(-((ct * ct) * (ct * ct)));
+        Cv = (2.128 * Vq + 2.385 * Vm + 2.496 * Vo_s + 4.18 * thz[i - 1]) * 1e6;
+      }
       double dzk = (i < sm) ? (zs[i + 1] - zs[i]) : (zs[sm] - zs[sm - 1]);
       ksoil[i] = lam / dzk;
       double zlo = (i > 1) ? zs[i - 1] : 0.0;
@@ -498,11 +504,15 @@ struct Column {
     const double mrh = 0.5 * relhumn + 0.5 * relhum;
     const double mpk = 0.5 * ppk + 0.5 * pkn;
     const double eref = (mrh / 100) * satvap(mtref);
-    const double esoil = soilrh(fc.theta, soilb, -psi_e, Smax, ps1) * satvap(ps1);            // Q7
+    const double esoil1 = soilrh(fc.theta, soilb, -psi_e, Smax, ps1) * satvap(ps1);           // Q7
+    // with moisture by depth esoil is a vector over the soil nodes that R recycles over the canopy layers (quirk Q24)
+    double esoilv[MS + 2];
+    if (fc.thz) { const double sv = satvap(ps1); for (int j = 1; j <= sm; ++j) esoilv[j] = soilrh(fc.thz[j - 1], soilb, -psi_e, Smax, ps1) * sv; }
     const double eamn = (relhumn / 100) * tet_tcan;
     double tnl[MM + 2], tleafn[MM + 2], eal[MM + 2];
     for (int i = 1; i <= m; ++i) {
       if (cta_sync) MC_CTA_SYNC();
+      const double esoil = fc.thz ? esoilv[(i - 1) % sm + 1] : esoil1;
       const double ptc = tc[i], ptl = tleaf[i];
       const double zp = zprev[i], zth = zthp[i], zl = zla[i];
       const double zrf = (hgt + 2) - zp;
@@ -597,7 +607,8 @@ struct Column {
     }
     // ---- soil conductances and surface forcing (code.R:789-811) ----
     if (cta_sync) MC_CTA_SYNC();
-    soilk(timestep, fc.theta);
+    soilk(timestep, fc.theta, fc.thz);
+    const double esoil = esoil1;                                 // tln$esoil[1] (code.R:799-805)
     double TT[MM + 2];
     { double s = 0; for (int i = 1; i <= m; ++i) { s += (phair(tc[i], ppk) / gtn[i]) * (z[i] - (i > 1 ? z[i - 1] : 0.0)); TT[i] = s; } }
     double Xs;
@@ -721,7 +732,7 @@ struct Column {
       for (int i = 1; i <= m; ++i) {
         double wgt = TT[i] / TX;
         tnn[i] = (1 - wgt) * tnsoil[1] + wgt * tcan;
-        ean2[i] = (1 - wgt) * esoil + wgt * eair;
+        ean2[i] = (1 - wgt) * (fc.thz ? esoilv[(i - 1) % sm + 1] : esoil) + wgt * eair;
       }
     }
     // ---- limits, humidity, fluxes (code.R:868-897) ----

@@ -180,9 +180,11 @@ inline double soilrh(double theta, double b, double Psie, double Smax, double tc
   return std::exp((0.018 * matric) / (8.31 * (tc + 273.15)));
 }
 // [V vig.md:852-854]+[R Campbell 1985] soil conductances k (W m^-2 K^-1; node i <-> i+1, last <-> deep
-// boundary) and heat storage cd (W m^-2 K^-1). Call site: code.R:790. theta is a scalar here.
+// boundary) and heat storage cd (W m^-2 K^-1). Call site: code.R:790.  theta is a scalar (thz null) or, when runmodel was given
+// soil moisture by depth (code.R:1146-1154: theta[, i] is then a vector over the soil nodes), the vector thz[0..sm): [D] node i takes
+// its conductivity and heat capacity from its own moisture.
 inline void soilk(double timestep, double theta, double Vq, double Vm, double Vo, double Mc, double rho,
-                  const double* z, int sm, double* k, double* cd) {
+                  const double* z, int sm, double* k, double* cd, const double* thz = nullptr) {
   double A = 0.65 - 0.78 * rho + 0.6 * rho * rho;
   double B = 1.06 * rho;
   double C = 1 + 2.6 / std::sqrt(Mc);
@@ -191,6 +193,11 @@ inline void soilk(double timestep, double theta, double Vq, double Vm, double Vo
   double lam = A + B * theta - (A - D) * std::exp(-((ct * ct) * (ct * ct)));
   double Cv = (2.128 * Vq + 2.385 * Vm + 2.496 * Vo + 4.18 * theta) * 1e6;
   for (int i = 0; i < sm; ++i) {
+    if (thz) {
+      ct = C * thz[i];
+      lam = A + B * thz[i] - (A - D) * std::exp(-((ct * ct) * (ct * ct)));
+      Cv = (2.128 * Vq + 2.385 * Vm + 2.496 * Vo + 4.18 * thz[i]) * 1e6;
+    }
     double dzk = (i < sm - 1) ? (z[i + 1] - z[i]) : (z[sm - 1] - z[sm - 2]);
     k[i] = lam / dzk;
     double zlo = (i > 0) ? z[i - 1] : 0.0;

@@ -213,7 +213,10 @@ inline LeafAbs leafabs(double Rsw, Tme tme, double tair, double /*tground*/, dou
 }
 
 // leaftemp  (code.R:378-512)
-struct LeafTemp { Vec tn, tleaf, ea, gtt, Rem, H, L; double esoil; };
+// esoilv: with soil moisture by depth `theta` is a vector over the soil nodes, so esoil is one too and R recycles it over the canopy
+// layers in every element-wise expression it meets (code.R:416-417, 424-437, 865): layer i sees esoilv[(i-1) %% length] (quirk Q24);
+// `esoil` is its first element (tln$esoil[1], code.R:799-805).
+struct LeafTemp { Vec tn, tleaf, ea, gtt, Rem, H, L; double esoil; Vec esoilv; };
 inline double edf(double ea1, double ea2, double tc) {   // code.R:380-386
   double es = 0.6108 * std::exp(17.27 * tc / (tc + 237.3));
   double y = ea1 > ea2 ? ea1 - ea2 : 0;
@@ -222,7 +225,7 @@ inline double edf(double ea1, double ea2, double tc) {   // code.R:380-386
 }
 inline LeafTemp leaftemp(double tair, double relhum, double pk, double timestep, Vec gt, Vec gha, Vec gv, Vec Rabs,
                          const State& previn, const Vegp& vegp, const Soilp& soilp, double theta,
-                         double zlafact = 1, double surfwet = 1) {
+                         double zlafact = 1, double surfwet = 1, const double* thz = nullptr, int nthz = 0) {
   const Vec& z = previn.z;
   double lambda = (-42.575 * tair + 44994) * surfwet;
   int m = gt.n - 1;
@@ -251,10 +254,17 @@ inline LeafTemp leaftemp(double tair, double relhum, double pk, double timestep,
   double eref = (mrh / 100) * esref;
   double rhsoil = soilrh(theta, soilp.b, -soilp.psi_e, soilp.Smax, previn.soiltc(1));   // Q7
   double esoil = rhsoil * satvap(previn.soiltc(1));
-  LeafTemp o; o.tn = Vec(m); o.tleaf = Vec(m); o.ea = Vec(m); o.gtt = gtt; o.Rem = Vec(m); o.H = Vec(m); o.L = Vec(m);
-  o.esoil = esoil;
+  Vec esoilv(thz ? nthz : 1, esoil);
+  if (thz) {
+    for (int j = 1; j <= nthz; ++j) esoilv(j) = soilrh(thz[j - 1], soilp.b, -soilp.psi_e, soilp.Smax, previn.soiltc(1)) * satvap(previn.soiltc(1));
+    esoil = esoilv(1);
+  }
+  const double esoil1 = esoil;
+  LeafTemp o; o.esoilv = esoilv; o.tn = Vec(m); o.tleaf = Vec(m); o.ea = Vec(m); o.gtt = gtt; o.Rem = Vec(m); o.H = Vec(m); o.L = Vec(m);
+  o.esoil = esoil1;
   double sb = 5.67 * 1e-8;
   for (int i = 1; i <= m; ++i) {
+    esoil = esoilv((i - 1) % esoilv.n + 1);                                   // R recycling (Q24); the scalar case has length 1
     double ptc = previn.tc(i), ptl = previn.tleaf(i);
     double esj = 0.6108 * std::exp(17.27 * ptc / (ptc + 237.3));
     double eaj = (previn.rh(i) / 100) * esj;
@@ -470,7 +480,8 @@ struct StepCfg {   // runonestep's scalar arguments (code.R:687-689)
 
 // runonestep  (code.R:687-902).  Returns 0, or -1 when m < 3 (stop at code.R:699).
 inline int runonestep(const Climvars& cv, const State& previn, Vegp vegp, const Soilp& soilp, const StepCfg& cfg,
-                      Tme tme, double theta, double thetap, State& out, int* nmerged = nullptr) {
+                      Tme tme, double theta, double thetap, State& out, int* nmerged = nullptr,
+                      const double* thz = nullptr /* theta by soil node (then theta == thz[0]) */) {
   const double timestep = cfg.timestep, edgedist = cfg.edgedist, reqhgt = cfg.reqhgt, zu = cfg.zu;
   for (int i = 1; i <= vegp.PAI.n; ++i) if (vegp.PAI(i) == 0) vegp.PAI(i) = 0.0001;     // code.R:691-696
   int m = previn.m;
@@ -550,12 +561,12 @@ inline int runonestep(const Climvars& cv, const State& previn, Vegp vegp, const 
     double dtc = previn.tleaf(i) - previn.tc(i);
     gha(i) = 1.41 * gforcedfree(vegp.lw * 0.71, uz(i), tc(i), dtc, pk);
   }
-  LeafTemp tln = leaftemp(tcan, relhum, pk, timestep, gt, gha, gv, Rabs, previn, vegp, soilp, theta, cfg.zlafact, cfg.surfwet);
+  LeafTemp tln = leaftemp(tcan, relhum, pk, timestep, gt, gha, gv, Rabs, previn, vegp, soilp, theta, cfg.zlafact, cfg.surfwet, thz, previn.sm);
   Vec Vo(m);
   for (int i = 1; i <= m; ++i) Vo(i) = (0.6108 * std::exp(17.27 * tc(i) / (tc(i) + 237.3)) * (previn.rh(i) / 100)) / previn.pk;
   int sm = previn.sm;
   Vec ksoil(sm), cdsoil(sm);
-  soilk(timestep, theta, soilp.Vq, soilp.Vm, soilp.Vo, soilp.Mc, soilp.rho, &soilp.z.a[1], sm, &ksoil.a[1], &cdsoil.a[1]);
+  soilk(timestep, theta, soilp.Vq, soilp.Vm, soilp.Vo, soilp.Mc, soilp.rho, &soilp.z.a[1], sm, &ksoil.a[1], &cdsoil.a[1], thz);
   Vec sz = soilp.z;
   Vec vden(m), X(m), TT(m);
   for (int i = 1; i <= m; ++i) { vden(i) = vegp.PAI(i) * vegp.thickw(i); X(i) = tln.tn(i) - tc(i); }
@@ -637,7 +648,7 @@ inline int runonestep(const Climvars& cv, const State& previn, Vegp vegp, const 
     for (int i = 1; i <= m; ++i) {
       double wgt = TT(i) / TX;
       tn(i) = (1 - wgt) * tnsoil(1) + wgt * tcan;
-      ea(i) = (1 - wgt) * tln.esoil + wgt * eair;
+      ea(i) = (1 - wgt) * tln.esoilv((i - 1) % tln.esoilv.n + 1) + wgt * eair;      // tln$esoil recycled (Q24)
     }
   }
   if (tnsoil(1) < tfrost) tnsoil(1) = tfrost;

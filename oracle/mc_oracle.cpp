@@ -231,11 +231,28 @@ int orc_runonestep(int64_t ncol, int m, int sm, const double* vegp, const double
 //  pai_season [T] or NULL (PAI(t) = PAI * season[t]); state [NSTATE][ncol] in (when spin_steps == 0) / out;
 //  series [T][8][nsamp] for columns samp_idx[]; stats [6][ncol] = mean,min,max of tout then of tleaf;
 //  fullseries [T][NSTATE][nsamp]; flags [ncol] (bit0: non-finite tout/tleaf seen).
+//  vegt [T][2m+1][nvt] or NULL: PAI[m], pLAI[m], zm0 of each forcing row (.vegpsort, code.R:904-916), one series shared by all columns
+//  (nvt == 1) or one per column (nvt == ncol); thetaz [T][sm] or NULL: soil moisture by depth (theta matrix, code.R:1146-1154), the
+//  per-column perturbation of the theta row applies to every depth.
+int orc_run_transient2(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* forcing,
+                       const double* fscale, const double* foffset, const double* tsoil_in, const double* lat,
+                       const double* lon, const double* cfg, const double* pai_season, double* state, double* series,
+                       const int64_t* samp_idx, int64_t nsamp, double* stats, double* fullseries, int32_t* flags, int nthreads,
+                       const double* vegt, int64_t nvt, const double* thetaz);
 int orc_run_transient(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* forcing,
                       const double* fscale, const double* foffset, const double* tsoil_in, const double* lat,
                       const double* lon, const double* cfg, const double* pai_season, double* state, double* series,
                       const int64_t* samp_idx, int64_t nsamp, double* stats, double* fullseries, int32_t* flags, int nthreads) {
+  return orc_run_transient2(ncol, m, sm, T, vegp, soilp, forcing, fscale, foffset, tsoil_in, lat, lon, cfg, pai_season, state, series,
+                            samp_idx, nsamp, stats, fullseries, flags, nthreads, nullptr, 0, nullptr);
+}
+int orc_run_transient2(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* forcing,
+                       const double* fscale, const double* foffset, const double* tsoil_in, const double* lat,
+                       const double* lon, const double* cfg, const double* pai_season, double* state, double* series,
+                       const int64_t* samp_idx, int64_t nsamp, double* stats, double* fullseries, int32_t* flags, int nthreads,
+                       const double* vegt, int64_t nvt, const double* thetaz) {
   if (m < 3) return -1;
+  if (thetaz && sm > m) return -3;          // R would recycle the canopy vectors over the longer soil vector: not a defined run
   const int NS = nstate(m, sm);
   const int spin = (int)cfg[C_SPINSTEPS];
   const int charmode = (int)cfg[C_HARVEST];
@@ -258,14 +275,33 @@ int orc_run_transient(int64_t ncol, int m, int sm, int64_t T, const double* vegp
     double reqhgt = sc.reqhgt;
     double spinhgt = charmode ? vbase.hgt / 2 : ((!is_na(reqhgt) && reqhgt > 0) ? reqhgt : NA);   // code.R:1136-1140
     State p, q;
+    auto vegpsort = [&](int64_t t) {                             // .vegpsort(vegp, t + 1), code.R:904-916
+      const int64_t cc = (nvt == 1) ? 0 : c;
+      for (int i = 1; i <= m; ++i) {
+        v.PAI(i) = vegt[(t * (2 * m + 1) + (i - 1)) * nvt + cc];
+        v.pLAI(i) = vegt[(t * (2 * m + 1) + m + (i - 1)) * nvt + cc];
+      }
+      v.zm0 = vegt[(t * (2 * m + 1) + 2 * m) * nvt + cc];
+    };
+    double thz[MAXN + 2], thz0[MAXN + 2];
+    auto theta_at = [&](int64_t t, double* o) {                  // theta[, t + 1] of this column
+      for (int j = 0; j < sm; ++j) {
+        double th = thetaz[t * sm + j];
+        if (fscale && foffset) { th = th * fscale[(int64_t)F_THETA * ncol + c] + foffset[(int64_t)F_THETA * ncol + c]; if (th < 0.001) th = 0.001; }
+        o[j] = th;
+      }
+    };
+    if (thetaz) theta_at(0, thz0);
     if (spin > 0) {                                              // spinup (code.R:982-1013)
       if (pai_season) apply_season(v, vbase, pai_season[0]);
+      if (vegt) vegpsort(0);
       p = paraminit(m, sm, v.hgt, f0[F_TAIR], f0[F_U], f0[F_RELHUM], tmean, f0[F_RSW]);
       Climvars cv = {f0[F_TAIR], f0[F_RELHUM], f0[F_PK], f0[F_U], tmean, f0[F_SKYEM], f0[F_RSW], f0[F_DP]};
       StepCfg ss = sc; ss.reqhgt = spinhgt; ss.zlafact = 1; ss.surfwet = 1;    // Q22
       double Hsum = 0;
       for (int i = 1; i <= spin; ++i) {
-        runonestep(cv, p, v, s, ss, Tme{f0[F_JD], f0[F_LT]}, f0[F_THETA], f0[F_THETA], q);
+        if (thetaz) runonestep(cv, p, v, s, ss, Tme{f0[F_JD], f0[F_LT]}, thz0[0], thz0[0], q, nullptr, thz0);   // theta[,1], theta[,1] (code.R:1158)
+        else runonestep(cv, p, v, s, ss, Tme{f0[F_JD], f0[F_LT]}, f0[F_THETA], f0[F_THETA], q);
         Hsum += q.H;
         q.H = Hsum / i;                                          // previn$H <- mean(H)
         p = q;
@@ -280,8 +316,10 @@ int orc_run_transient(int64_t ncol, int m, int sm, int64_t T, const double* vegp
     for (int64_t t = 0; t < T; ++t) {
       forcing_at(forcing, t, fscale, foffset, ncol, c, f);
       if (pai_season) apply_season(v, vbase, pai_season[t]);
+      if (vegt) vegpsort(t);
       Climvars cv = {f[F_TAIR], f[F_RELHUM], f[F_PK], f[F_U], tsoil, f[F_SKYEM], f[F_RSW], f[F_DP]};
-      runonestep(cv, p, v, s, sl, Tme{f[F_JD], f[F_LT]}, f[F_THETA], /*Q2*/ f0[F_THETA], q);
+      if (thetaz) { theta_at(t, thz); runonestep(cv, p, v, s, sl, Tme{f[F_JD], f[F_LT]}, thz[0], /*Q2: theta[1,1]*/ thz0[0], q, nullptr, thz); }
+      else runonestep(cv, p, v, s, sl, Tme{f[F_JD], f[F_LT]}, f[F_THETA], /*Q2*/ f0[F_THETA], q);
       p = q;
       double o[8];
       harvest(p, v, s, reqhgt, charmode, f[F_TAIR], f0, o);
@@ -310,9 +348,19 @@ int orc_run_transient(int64_t ncol, int m, int sm, int64_t T, const double* vegp
 //  nmr  [T][3 + 8]: D0cm, WC0cm, SNOWDEP(cm), SN1..SN8   (shared across columns) -- or per column when
 //  nmr_percol != 0: [T][11][ncol];  scfg: reqhgt, metopen, windhgt, surfwet, groundem
 //  out [T][7][ncol]: Tloc, tleaf, RHloc, RSWloc, RLWloc, windspeed, dp;   stats [6][ncol] (Tloc, tleaf)
+//  vegt [T][2m+1][nvt] or NULL: PAI[m], pLAI[m] (and zm0, unused on this path) per hour — runmodelS takes vegp$PAI as an m x T matrix
+//  (NMR.R:730-735: apply(vegp$PAI, 2, sum)); nvt == 1 shared by all columns, nvt == ncol one per column.
+int orc_run_steady2(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* clim,
+                    const double* nmr, int nmr_percol, const double* lat, const double* lon, const double* scfg,
+                    const double* pai_season, double* out, double* stats, int nthreads, const double* vegt, int64_t nvt);
 int orc_run_steady(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* clim,
                    const double* nmr, int nmr_percol, const double* lat, const double* lon, const double* scfg,
                    const double* pai_season, double* out, double* stats, int nthreads) {
+  return orc_run_steady2(ncol, m, sm, T, vegp, soilp, clim, nmr, nmr_percol, lat, lon, scfg, pai_season, out, stats, nthreads, nullptr, 0);
+}
+int orc_run_steady2(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* clim,
+                    const double* nmr, int nmr_percol, const double* lat, const double* lon, const double* scfg,
+                    const double* pai_season, double* out, double* stats, int nthreads, const double* vegt, int64_t nvt) {
   int rc_all = 0;
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -329,6 +377,10 @@ int orc_run_steady(int64_t ncol, int m, int sm, int64_t T, const double* vegp, c
       const double* cr = clim + t * 9;
       double season = pai_season ? pai_season[t] : 1.0;
       for (int i = 0; i < m; ++i) { pai[i] = v.PAI(i + 1) * season; plai[i] = v.pLAI(i + 1); }
+      if (vegt) {
+        const int64_t cc = (nvt == 1) ? 0 : c;
+        for (int i = 0; i < m; ++i) { pai[i] = vegt[(t * (2 * m + 1) + i) * nvt + cc]; plai[i] = vegt[(t * (2 * m + 1) + m + i) * nvt + cc]; }
+      }
       SteadyVeg sv;
       sv.hgt = v.hgt; sv.x = v.x; sv.lw = v.lw; sv.cd = v.cd; sv.iwmean = vmean(v.iw); sv.refls = v.refls; sv.refw = v.refw;
       sv.refg = v.refg; sv.vegem = v.vegem; sv.gsmax = v.gsmax; sv.q50 = v.q50; sv.clump = v.clump;

@@ -41,8 +41,12 @@ def lib():
                                        C.POINTER(C.c_int)])
         sig("orc_run_transient", C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, PD, PD, PD, PD, PD, PD, PD, PD, PD, PD,
                                           PD, PD, C.POINTER(C.c_int64), C.c_int64, PD, PD, C.POINTER(C.c_int32), C.c_int])
+        sig("orc_run_transient2", C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, PD, PD, PD, PD, PD, PD, PD, PD, PD, PD,
+                                           PD, PD, C.POINTER(C.c_int64), C.c_int64, PD, PD, C.POINTER(C.c_int32), C.c_int, PD, C.c_int64, PD])
         sig("orc_run_steady", C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, PD, PD, PD, PD, C.c_int, PD, PD, PD, PD,
                                        PD, PD, C.c_int])
+        sig("orc_run_steady2", C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, PD, PD, PD, PD, C.c_int, PD, PD, PD, PD,
+                                        PD, PD, C.c_int, PD, C.c_int64])
         sig("orc_tleafS", None, [PD, PD]); sig("orc_snowtempf", C.c_int, [D, PD, D, PD])
         for n in ["orc_nveg", "orc_nsoil", "orc_nforc", "orc_ncfg"]:
             pass
@@ -95,9 +99,10 @@ def runonestep(vegp, soilp, climvars, lat, lon, cfg, jd, lt, theta, thetap, stat
 
 
 def run_transient(vegp, soilp, forcing, lat, lon, cfg, m, sm, state=None, fscale=None, foffset=None, tsoil=None,
-                  pai_season=None, samp_idx=None, want_full=False, nthreads=0):
+                  pai_season=None, samp_idx=None, want_full=False, nthreads=0, vegt=None, thetaz=None):
+    """vegt [T][2m+1][1 or ncol]: PAI, pLAI, zm0 per forcing row (.vegpsort); thetaz [T][sm]: soil moisture by depth."""
     vegp, soilp, forcing, lat, lon, cfg = map(_f, (vegp, soilp, forcing, lat, lon, cfg))
-    fscale, foffset, tsoil, pai_season = map(_f, (fscale, foffset, tsoil, pai_season))
+    fscale, foffset, tsoil, pai_season, vegt, thetaz = map(_f, (fscale, foffset, tsoil, pai_season, vegt, thetaz))
     ncol = vegp.shape[1]; T = forcing.shape[0]
     NS = lib().orc_nstate(m, sm)
     st = np.zeros((NS, ncol)) if state is None else np.array(state, dtype=np.float64, order="C", copy=True)
@@ -105,21 +110,27 @@ def run_transient(vegp, soilp, forcing, lat, lon, cfg, m, sm, state=None, fscale
     ns = samp.size
     series = np.zeros((T, 8, ns)); stats = np.zeros((6, ncol)); flags = np.zeros(ncol, dtype=np.int32)
     full = np.zeros((T, NS, ns)) if want_full else None
-    rc = lib().orc_run_transient(ncol, m, sm, T, _p(vegp), _p(soilp), _p(forcing), _p(fscale), _p(foffset), _p(tsoil),
-                                 _p(lat), _p(lon), _p(cfg), _p(pai_season), _p(st), _p(series),
-                                 samp.ctypes.data_as(C.POINTER(C.c_int64)), ns, _p(stats), _p(full),
-                                 flags.ctypes.data_as(C.POINTER(C.c_int32)), nthreads)
+    nvt = 0
+    if vegt is not None:
+        assert vegt.ndim == 3 and vegt.shape[0] == T and vegt.shape[1] == 2 * m + 1 and vegt.shape[2] in (1, ncol), vegt.shape
+        nvt = vegt.shape[2]
+    if thetaz is not None:
+        assert thetaz.shape == (T, sm), thetaz.shape
+    rc = lib().orc_run_transient2(ncol, m, sm, T, _p(vegp), _p(soilp), _p(forcing), _p(fscale), _p(foffset), _p(tsoil),
+                                  _p(lat), _p(lon), _p(cfg), _p(pai_season), _p(st), _p(series),
+                                  samp.ctypes.data_as(C.POINTER(C.c_int64)), ns, _p(stats), _p(full),
+                                  flags.ctypes.data_as(C.POINTER(C.c_int32)), nthreads, _p(vegt), nvt, _p(thetaz))
     if rc:
         raise ValueError("oracle run_transient rc=%d" % rc)
     return dict(state=st, series=series, stats=stats, flags=flags, full=full)
 
 
-def run_steady(vegp, soilp, clim, nmr, lat, lon, scfg, m, sm, pai_season=None, want_out=True, nthreads=0):
-    vegp, soilp, clim, nmr, lat, lon, scfg, pai_season = map(_f, (vegp, soilp, clim, nmr, lat, lon, scfg, pai_season))
+def run_steady(vegp, soilp, clim, nmr, lat, lon, scfg, m, sm, pai_season=None, want_out=True, nthreads=0, vegt=None):
+    vegp, soilp, clim, nmr, lat, lon, scfg, pai_season, vegt = map(_f, (vegp, soilp, clim, nmr, lat, lon, scfg, pai_season, vegt))
     ncol = vegp.shape[1]; T = clim.shape[0]
     percol = 1 if nmr.ndim == 3 else 0
     out = np.zeros((T, 7, ncol)) if want_out else None
     stats = np.zeros((6, ncol))
-    rc = lib().orc_run_steady(ncol, m, sm, T, _p(vegp), _p(soilp), _p(clim), _p(nmr), percol, _p(lat), _p(lon), _p(scfg),
-                              _p(pai_season), _p(out), _p(stats), nthreads)
+    rc = lib().orc_run_steady2(ncol, m, sm, T, _p(vegp), _p(soilp), _p(clim), _p(nmr), percol, _p(lat), _p(lon), _p(scfg),
+                               _p(pai_season), _p(out), _p(stats), nthreads, _p(vegt), 0 if vegt is None else vegt.shape[2])
     return dict(out=out, stats=stats, rc=rc)

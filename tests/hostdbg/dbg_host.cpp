@@ -14,11 +14,25 @@ static RunCfg mkcfg(const double* c) {
   r.metopen = c[7] != 0; r.windhgt = c[8]; r.zlafact = c[9]; r.surfwet = c[10]; r.dbg = 0;
   return r;
 }
+extern "C" int dbg_run_transient2(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* forcing,
+                      const double* fscale, const double* foffset, const double* tsoil_in, const double* lat,
+                      const double* lon, const double* cfg, const double* pai_season, double* state, double* series,
+                      const int64_t* samp_idx, int64_t nsamp, double* stats, double* fullseries, int32_t* flags, int,
+                      const double* vegt, int64_t nvt, const double* thetaz);
 extern "C" int dbg_run_transient(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* forcing,
                       const double* fscale, const double* foffset, const double* tsoil_in, const double* lat,
                       const double* lon, const double* cfg, const double* pai_season, double* state, double* series,
                       const int64_t* samp_idx, int64_t nsamp, double* stats, double* fullseries, int32_t* flags, int) {
+  return dbg_run_transient2(ncol, m, sm, T, vegp, soilp, forcing, fscale, foffset, tsoil_in, lat, lon, cfg, pai_season, state, series, samp_idx,
+                            nsamp, stats, fullseries, flags, 0, nullptr, 0, nullptr);
+}
+extern "C" int dbg_run_transient2(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* forcing,
+                      const double* fscale, const double* foffset, const double* tsoil_in, const double* lat,
+                      const double* lon, const double* cfg, const double* pai_season, double* state, double* series,
+                      const int64_t* samp_idx, int64_t nsamp, double* stats, double* fullseries, int32_t* flags, int,
+                      const double* vegt, int64_t nvt, const double* thetaz) {
   TransientArgs a{};
+  a.vegt = vegt; a.nvt = nvt; a.thetaz = thetaz;
   a.ncol = ncol; a.m = m; a.sm = sm; a.T = T; a.t0 = 0; a.t1 = T; a.vegp = vegp; a.soilp = soilp; a.lat = lat; a.lon = lon;
   a.forcing = forcing; a.fscale = fscale; a.foffset = foffset; a.tsoil = tsoil_in; a.season = pai_season; a.state = state;
   a.series = series; a.full = fullseries; a.nsamp = nsamp; a.stats = stats; a.flags = flags; a.cfg = mkcfg(cfg);
@@ -90,10 +104,19 @@ extern "C" int dbg_runonestep(int64_t ncol, int m, int sm, const double* vegp, c
   return 0;
 }
 
+extern "C" int dbg_run_steady2(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* clim,
+                   const double* nmr, int nmr_percol, const double* lat, const double* lon, const double* scfg,
+                   const double* pai_season, double* out, double* stats, int, const double* vegt, int64_t nvt);
 extern "C" int dbg_run_steady(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* clim,
                    const double* nmr, int nmr_percol, const double* lat, const double* lon, const double* scfg,
                    const double* pai_season, double* out, double* stats, int) {
-  SteadyArgs a{}; a.ncol = ncol; a.m = m; a.sm = sm; a.T = T; a.vegp = vegp; a.soilp = soilp; a.lat = lat; a.lon = lon; a.clim = clim;
+  return dbg_run_steady2(ncol, m, sm, T, vegp, soilp, clim, nmr, nmr_percol, lat, lon, scfg, pai_season, out, stats, 0, nullptr, 0);
+}
+extern "C" int dbg_run_steady2(int64_t ncol, int m, int sm, int64_t T, const double* vegp, const double* soilp, const double* clim,
+                   const double* nmr, int nmr_percol, const double* lat, const double* lon, const double* scfg,
+                   const double* pai_season, double* out, double* stats, int, const double* vegt, int64_t nvt) {
+  SteadyArgs a{};
+  a.vegt = vegt; a.nvt = nvt; a.ncol = ncol; a.m = m; a.sm = sm; a.T = T; a.vegp = vegp; a.soilp = soilp; a.lat = lat; a.lon = lon; a.clim = clim;
   a.nmr = nmr; a.nmr_percol = nmr_percol; a.season = pai_season; a.reqhgt = scfg[0]; a.metopen = scfg[1] != 0; a.windhgt = scfg[2];
   a.surfwet = scfg[3]; a.out = out;
   int* flags = new int[ncol](); a.flags = flags;

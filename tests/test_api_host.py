@@ -35,21 +35,36 @@ def test_seasonal_pai_factorisation():
     v = S.vegp_deciduous()
     season = 0.6 + 0.4 * np.sin(np.linspace(0, np.pi, 12)) ** 2
     v2 = dict(v, PAI=np.outer(v["PAI"], season))
-    base, s = api._season_of(v2)
+    base, s, vt = api._season_of(v2)
+    assert vt is None
     np.testing.assert_allclose(np.outer(base["PAI"], s), v2["PAI"], rtol=1e-13)
+    # anything that is not profile x seasonal factor travels in full: PAI[m], pLAI[m], zm0 per time step (.vegpsort, code.R:904-916)
     bad = dict(v, PAI=np.outer(v["PAI"], season)); bad["PAI"][3, 4] *= 1.3
-    with pytest.raises(NotImplementedError):
-        api._season_of(bad)
-    assert api._season_of(v)[1] is None
+    base, s, vt = api._season_of(bad)
+    assert s is None and vt.shape == (12, 41)
+    np.testing.assert_array_equal(vt[:, :20], bad["PAI"].T); np.testing.assert_array_equal(vt[4, 20:40], v["pLAI"]); assert np.all(vt[:, 40] == v["zm0"])
+    np.testing.assert_array_equal(base["PAI"], bad["PAI"][:, 0])
+    tv = dict(v, pLAI=np.outer(v["pLAI"], np.linspace(1, 0.8, 12)), zm0=np.linspace(0.004, 0.006, 12))
+    base, s, vt = api._season_of(tv)
+    assert s is None and vt[7, 40] == tv["zm0"][7]; np.testing.assert_array_equal(vt[7, 20:40], tv["pLAI"][:, 7]); np.testing.assert_array_equal(vt[7, :20], v["PAI"])
+    assert api._season_of(v)[1] is None and api._season_of(v)[2] is None
+    # columns: shared season stays a season; differing columns become per-column rows; identical general columns collapse to one series
+    _, se, vt = api._veg_time([v2, v2]); assert vt is None and se.shape == (12,)
+    _, se, vt = api._veg_time([v2, bad]); assert se is None and vt.shape == (12, 41, 2); np.testing.assert_allclose(vt[:, :20, 0], v2["PAI"].T, rtol=1e-13)
+    _, se, vt = api._veg_time([bad, bad]); assert vt.shape == (12, 41, 1)
 
 
 def test_theta_forms():
-    assert api._theta_series(0.3, 10, 4) == 0.3
-    np.testing.assert_array_equal(api._theta_series(np.full((1, 10), 0.25), 10, 4), np.full(10, 0.25))
-    np.testing.assert_array_equal(api._theta_series(np.linspace(0.2, 0.3, 10), 10, 4), np.linspace(0.2, 0.3, 10))
-    assert api._theta_series(np.full(4, 0.27), 10, 4) == 0.27
-    with pytest.raises(NotImplementedError):
-        api._theta_series(np.array([0.2, 0.25, 0.3, 0.35]), 10, 4)
+    assert api._theta_series(0.3, 10, 4) == (0.3, None)
+    th, tz = api._theta_series(np.full((1, 10), 0.25), 10, 4); np.testing.assert_array_equal(th, np.full(10, 0.25)); assert tz is None
+    th, tz = api._theta_series(np.linspace(0.2, 0.3, 10), 10, 4); np.testing.assert_array_equal(th, np.linspace(0.2, 0.3, 10)); assert tz is None
+    # soil moisture by depth (code.R:1151-1153 and the matrix form): thetaz [T][sm]
+    th, tz = api._theta_series(np.array([0.2, 0.25, 0.3, 0.35]), 10, 4)
+    assert th == 0.2 and tz.shape == (10, 4) and np.all(tz == np.array([0.2, 0.25, 0.3, 0.35]))
+    mat = np.linspace(0.1, 0.4, 40).reshape(4, 10)
+    th, tz = api._theta_series(mat, 10, 4); np.testing.assert_array_equal(tz, mat.T); np.testing.assert_array_equal(th, mat[0])
+    with pytest.raises(ValueError):
+        api._theta_series(np.zeros((3, 10)), 10, 4)
 
 
 def test_pack_roundtrip_and_state_list():

@@ -133,3 +133,83 @@ def test_in_process_split_over_all_visible_gpus_equals_one_gpu(oracle):
     np.testing.assert_array_equal(a.get_state(), b.get_state())
     for k in ("series", "stats", "flags"):
         np.testing.assert_array_equal(ra[k], rb[k])
+
+
+# ---- general time-varying vegetation (.vegpsort) and soil moisture by depth, through the C-ABI and the host mirror ----------------------
+def _vegt(ncol, T, percol):
+    from tests.test_host_logic import _vegt_case
+    return _vegt_case(ncol, T, M, percol)
+
+
+@pytest.mark.parametrize("percol", [False, True])
+def test_general_time_varying_vegetation_on_the_gpu(oracle, percol):
+    """vegp$PAI / vegp$pLAI as m x T matrices that are not profile x seasonal factor, vegp$zm0 of length T (code.R:904-916): mc_set_vegt."""
+    ncol, T = 70, 96
+    inp = transient_inputs(oracle, ncol=ncol, T=T)
+    vegt = _vegt(ncol, T, percol)
+    cfg = make_cfg(spin_steps=40, reqhgt=2.0)
+    want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"], vegt=vegt)
+    ctx = _ctx(inp, cfg)
+    ctx.set_vegt(vegt)
+    got = ctx.run_transient(samp_idx=np.arange(ncol))
+    assert_series_close(got["series"], want["series"], "vegt"); assert_state_close(ctx.get_state(), want["state"], what="vegt")
+    # chunked continuation picks the right rows
+    ctx2 = _ctx(inp, cfg); ctx2.set_vegt(vegt)
+    a = ctx2.run_transient(0, 50, samp_idx=np.arange(ncol)); b = ctx2.run_transient(50, T, samp_idx=np.arange(ncol))
+    np.testing.assert_array_equal(np.concatenate([a["series"], b["series"]]), got["series"])
+
+
+def test_soil_moisture_by_depth_on_the_gpu(oracle):
+    """theta as a [soil layers x time] matrix (code.R:1146-1154): soilk per node, esoil recycled over the canopy layers (quirk Q24)."""
+    from microclimc_b200._lib import MicroclimcError
+    ncol, T = 70, 96
+    inp = transient_inputs(oracle, ncol=ncol, T=T)
+    rng = np.random.default_rng(8)
+    thetaz = np.clip(0.18 + 0.15 * np.linspace(0, 1, SM)[None, :] + 0.05 * np.sin(np.arange(T) / 7.0)[:, None] + rng.normal(0, 0.01, (T, SM)), 0.05, 0.42)
+    cfg = make_cfg(spin_steps=40)
+    want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"], thetaz=thetaz)
+    ctx = _ctx(inp, cfg)
+    ctx.set_thetaz(thetaz)
+    got = ctx.run_transient(samp_idx=np.arange(ncol))
+    assert_series_close(got["series"], want["series"], "thetaz"); assert_state_close(ctx.get_state(), want["state"], what="thetaz")
+    with pytest.raises((ValueError, MicroclimcError)):
+        ctx.set_thetaz(thetaz[:10]); ctx.run_transient()                      # rows must match the forcing
+
+
+def test_runmodel_with_matrix_vegp_and_theta_matrix_through_the_host_mirror(oracle):
+    """The reference's own call shape: runmodel(climdata, vegp with PAI m x T, soilp, ..., theta = matrix) for one column."""
+    from microclimc_b200 import api
+    w = S.load_weather(); T = 72
+    clim = {k: np.asarray(v)[2000:2000 + T] for k, v in w.items()}
+    vt = _vegt(1, T, False)[:, :, 0]
+    v = dict(S.vegp_deciduous(), PAI=vt[:, :M].T.copy(), pLAI=vt[:, M:2 * M].T.copy(), zm0=vt[:, 2 * M].copy())
+    soil = loam(oracle)
+    theta = np.clip(0.2 + 0.1 * np.linspace(0, 1, SM)[:, None] + 0.03 * np.cos(np.arange(T) / 5.0)[None, :], 0.05, 0.4)
+    df = api.runmodel(clim, v, soil, 50.0, -5.0, reqhgt=1.0, steps=30, theta=theta)
+    v0 = dict(v, PAI=v["PAI"][:, 0], pLAI=v["pLAI"][:, 0], zm0=float(v["zm0"][0]))
+    veg = S.pack_vegp([v0], M); so = S.pack_soilp([soil], SM)
+    f, ts = S.forcing_from_climdata(clim, theta=theta[0])
+    want = oracle.run_transient(veg, so, f, np.array([50.0]), np.array([-5.0]), make_cfg(timestep=ts, reqhgt=1.0, spin_steps=30), M, SM,
+                                vegt=vt[:, :, None], thetaz=theta.T.copy())
+    assert np.max(np.abs(df["tout"].to_numpy() - want["series"][:, 0, 0])) <= 1e-6
+    assert np.max(np.abs(df["tleaf"].to_numpy() - want["series"][:, 1, 0])) <= 1e-6
+
+
+def test_steady_path_with_matrix_vegp_on_the_gpu(oracle):
+    from microclimc_b200._lib import Context
+    ncol, T = 40, 120
+    veg, so = S.ensemble(S.vegp_deciduous(), loam(oracle), ncol, M, SM, seed=5)
+    clim = S.steady_clim_from_climdata(S.load_weather())[600:600 + T]
+    rng = np.random.default_rng(2)
+    nmr = np.zeros((T, 11)); nmr[:, 0] = clim[:, 0] + rng.normal(0, 1.5, T); nmr[:, 1] = rng.uniform(0.1, 0.4, T)
+    nmr[:, 2] = np.where(clim[:, 0] < 6, rng.uniform(1, 60, T), 0.0); nmr[:, 3:] = rng.uniform(-9, 0, (T, 8))
+    lat = np.full(ncol, 50.0); lon = np.full(ncol, -5.0); scfg = np.array([1.0, 1, 2, 1, 0.95])
+    for percol in (False, True):
+        vegt = _vegt(ncol, T, percol)
+        want = oracle.run_steady(veg, so, clim, nmr, lat, lon, scfg, M, SM, vegt=vegt)["out"]
+        ctx = Context(M, SM); ctx.set_columns(veg, so, lat, lon); ctx.set_vegt(vegt)
+        got = ctx.run_steady(clim, nmr, scfg)["out"]
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        g = np.nan_to_num(got); w_ = np.nan_to_num(want)
+        assert np.max(np.abs(g[:, :2] - w_[:, :2])) <= 1e-6
+        assert np.max(np.abs(g[:, 2:] - w_[:, 2:]) / np.maximum(np.abs(w_[:, 2:]), 1.0)) <= 1e-8

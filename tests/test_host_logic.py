@@ -23,7 +23,7 @@ def _f(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
 
 
-def dbg_run_transient(lib, inp, cfg, m=M, sm=SM, state=None, pai_season=None, want_full=False):
+def dbg_run_transient(lib, inp, cfg, m=M, sm=SM, state=None, pai_season=None, want_full=False, vegt=None, thetaz=None):
     veg, soil, f, lat, lon, fs, fo = map(_f, (inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], inp["fs"], inp["fo"]))
     ncol, T = veg.shape[1], f.shape[0]
     NS = L.nstate(m, sm)
@@ -31,6 +31,15 @@ def dbg_run_transient(lib, inp, cfg, m=M, sm=SM, state=None, pai_season=None, wa
     samp = np.arange(ncol, dtype=np.int64)
     series = np.zeros((T, 8, ncol)); stats = np.zeros((6, ncol)); flags = np.zeros(ncol, dtype=np.int32)
     full = np.zeros((T, NS, ncol)) if want_full else None
+    if vegt is not None or thetaz is not None:
+        vegt, thetaz = _f(vegt), _f(thetaz)
+        lib.dbg_run_transient2.restype = C.c_int
+        rc = lib.dbg_run_transient2(C.c_int64(ncol), m, sm, C.c_int64(T), _p(veg), _p(soil), _p(f), _p(fs), _p(fo), None, _p(lat), _p(lon),
+                                    _p(_f(cfg)), _p(_f(pai_season)), _p(st), _p(series), samp.ctypes.data_as(C.POINTER(C.c_int64)),
+                                    C.c_int64(ncol), _p(stats), _p(full), flags.ctypes.data_as(C.POINTER(C.c_int32)), 0,
+                                    _p(vegt), C.c_int64(0 if vegt is None else vegt.shape[2]), _p(thetaz))
+        assert rc == 0
+        return dict(state=st, series=series, stats=stats, flags=flags, full=full)
     lib.dbg_run_transient.restype = C.c_int
     rc = lib.dbg_run_transient(C.c_int64(ncol), m, sm, C.c_int64(T), _p(veg), _p(soil), _p(f), _p(fs), _p(fo), None, _p(lat), _p(lon),
                                _p(_f(cfg)), _p(_f(pai_season)), _p(st), _p(series), samp.ctypes.data_as(C.POINTER(C.c_int64)),
@@ -144,10 +153,15 @@ def _steady_inputs(oracle, ncol, T, t0=0, snow=False, percol=False, seed=2):
     return veg, soil, clim, nmr
 
 
-def dbg_run_steady(lib, veg, soil, clim, nmr, lat, lon, scfg, m=M, sm=SM, pai_season=None):
+def dbg_run_steady(lib, veg, soil, clim, nmr, lat, lon, scfg, m=M, sm=SM, pai_season=None, vegt=None):
     veg, soil, clim, nmr, lat, lon, scfg = map(_f, (veg, soil, clim, nmr, lat, lon, scfg))
     ncol, T = veg.shape[1], clim.shape[0]
     out = np.zeros((T, 7, ncol)); stats = np.zeros((6, ncol))
+    if vegt is not None:
+        vegt = _f(vegt)
+        rc = lib.dbg_run_steady2(C.c_int64(ncol), m, sm, C.c_int64(T), _p(veg), _p(soil), _p(clim), _p(nmr), 1 if nmr.ndim == 3 else 0, _p(lat),
+                                 _p(lon), _p(scfg), None, _p(out), _p(stats), 0, _p(vegt), C.c_int64(vegt.shape[2]))
+        return dict(out=out, stats=stats, rc=rc)
     rc = lib.dbg_run_steady(C.c_int64(ncol), m, sm, C.c_int64(T), _p(veg), _p(soil), _p(clim), _p(nmr), 1 if nmr.ndim == 3 else 0, _p(lat),
                             _p(lon), _p(scfg), _p(_f(pai_season)), _p(out), _p(stats), 0)
     return dict(out=out, stats=stats, rc=rc)
@@ -284,3 +298,77 @@ def test_streaming_form_over_the_variant_tables(oracle, hostdbg, kind, name, mon
         assert ngen >= 5, "nodes under 0.12 m must take the general path (%d)" % ngen
     elif kw.get("timestep", 3600.0) >= 3600.0:
         assert ngen == 0, "hourly columns should stay in the streaming form (columns dropped: %d)" % ngen
+
+
+# ---- general time-varying vegetation (.vegpsort) and soil moisture by depth (theta matrix) ---------------------------------
+def _vegt_case(ncol, T, m, percol, seed=3):
+    """PAI / pLAI as m x T matrices that are NOT profile x seasonal factor (the profile's shape moves through the season) and a
+    zm0 series, as habitatvars-style inputs have them."""
+    rng = np.random.default_rng(seed)
+    base = S.vegp_deciduous(m=m)
+    n = ncol if percol else 1
+    vegt = np.empty((T, 2 * m + 1, n))
+    zc = (np.arange(m) + 0.5) / m
+    for t in range(T):
+        ph = t / max(T - 1, 1)
+        for c in range(n):
+            peak = 0.55 + 0.25 * ph + 0.05 * (c % 3)
+            prof = np.exp(-((zc - peak) / (0.18 + 0.1 * ph)) ** 2)
+            vegt[t, :m, c] = prof / prof.sum() * (2.0 + 2.5 * ph + 0.1 * c)
+            vegt[t, m:2 * m, c] = np.clip(0.6 + 0.3 * ph * zc, 0, 1)
+            vegt[t, 2 * m, c] = 0.004 + 0.002 * ph
+    vegt[T // 2, 2, :] = 0.0                                                # a zero-PAI layer at one step (floored to 0.0001, code.R:691-696)
+    return vegt
+
+
+@pytest.mark.parametrize("percol", [False, True])
+def test_general_time_varying_vegetation_equals_oracle(oracle, hostdbg, percol):
+    inp = transient_inputs(oracle, ncol=5, T=60)
+    vegt = _vegt_case(5, 60, M, percol)
+    cfg = make_cfg(spin_steps=30, reqhgt=2.0)
+    want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"],
+                                vegt=vegt)
+    got = dbg_run_transient(hostdbg, inp, cfg, vegt=vegt)
+    assert_series_close(got["series"], want["series"], "vegt"); assert_state_close(got["state"], want["state"], what="vegt")
+    # and it matters: the run with the first row's vegetation held fixed differs
+    fixed = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"],
+                                 vegt=np.repeat(vegt[:1], 60, axis=0))
+    assert np.max(np.abs(fixed["series"][-1, 0] - want["series"][-1, 0])) > 1e-3
+
+
+def test_soil_moisture_by_depth_equals_oracle_and_recycles(oracle, hostdbg):
+    inp = transient_inputs(oracle, ncol=5, T=60)
+    rng = np.random.default_rng(8)
+    thetaz = np.clip(0.18 + 0.15 * np.linspace(0, 1, SM)[None, :] + 0.05 * np.sin(np.arange(60) / 7.0)[:, None] + rng.normal(0, 0.01, (60, SM)),
+                     0.05, 0.42)
+    cfg = make_cfg(spin_steps=30)
+    want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"],
+                                thetaz=thetaz)
+    got = dbg_run_transient(hostdbg, inp, cfg, thetaz=thetaz)
+    assert_series_close(got["series"], want["series"], "thetaz"); assert_state_close(got["state"], want["state"], what="thetaz")
+    # a depth-constant matrix is the scalar-theta run bit for bit (no recycling effect, same soilk)
+    flat = np.repeat(thetaz[:, :1], SM, axis=1)
+    inp2 = dict(inp, f=inp["f"].copy()); inp2["f"][:, L.FORCING.index("theta")] = thetaz[:, 0]
+    a = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"], thetaz=flat)
+    b = oracle.run_transient(inp2["veg"], inp2["soil"], inp2["f"], inp2["lat"], inp2["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"])
+    np.testing.assert_array_equal(a["series"], b["series"])
+    # Q24: the moisture of the deeper nodes reaches the canopy air through the recycled esoil
+    deep = thetaz.copy(); deep[:, 1:] = 0.08
+    c = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"], thetaz=deep)
+    assert np.max(np.abs(c["series"][:, 2] - want["series"][:, 2])) > 1e-6
+
+
+@pytest.mark.parametrize("percol,snow", [(False, False), (True, True)])
+def test_steady_general_time_varying_vegetation_equals_oracle(oracle, hostdbg, percol, snow):
+    """runmodelS takes vegp$PAI / vegp$pLAI as m x T matrices (NMR.R:730-735); any matrix, not only profile x seasonal factor."""
+    ncol, T = 5, 72
+    veg, soil, clim, nmr = _steady_inputs(oracle, ncol, T, t0=600, snow=snow, percol=False)
+    vegt = _vegt_case(ncol, T, M, percol)
+    lat = np.full(ncol, 50.0); lon = np.full(ncol, -5.0)
+    scfg = np.array([1.0, 1, 2, 1, 0.95])
+    want = oracle.run_steady(veg, soil, clim, nmr, lat, lon, scfg, M, SM, vegt=vegt)
+    got = dbg_run_steady(hostdbg, veg, soil, clim, nmr, lat, lon, scfg, vegt=vegt)
+    assert np.array_equal(np.isnan(got["out"]), np.isnan(want["out"]))
+    np.testing.assert_allclose(np.nan_to_num(got["out"]), np.nan_to_num(want["out"]), rtol=1e-9, atol=1e-9)
+    base = oracle.run_steady(veg, soil, clim, nmr, lat, lon, scfg, M, SM)
+    assert np.nanmax(np.abs(base["out"][:, 0] - want["out"][:, 0])) > 1e-3
