@@ -241,7 +241,11 @@ inline double difprop(double Rsw, double jd, double lt, double lat, double lon, 
 }
 
 // ---- canopy radiation -----------------------------------------------------------------------
-// [V vig.md:415, Campbell 1986] ellipsoidal extinction coefficient for solar altitude sa (deg).
+// [R] ellipsoidal extinction coefficient for solar altitude sa (deg): Campbell's (1986) PUBLISHED form
+// K = sqrt(x^2 + tan^2(zenith)) / (x + 1.774 (x + 1.182)^-0.733) — exponent -0.733, the square root over the numerator only.  The
+// vignette prints a different-looking formula at vig.md:415 (exponent 0.773 under one root); that typesetting is taken to be a slip and
+// is NOT what is implemented here: the tag is [R] (recollection of the published equation), not [V].  mt_cansw / mt_psunlit traces of
+// tools/r_parity/dump_reference.R are what would settle it.
 inline double cank(double x, double sa) {
   double zen = (90 - sa) * PI / 180;
   double t = std::tan(zen);

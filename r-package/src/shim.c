@@ -68,20 +68,36 @@ SEXP mcb_run_onestep(SEXP ptr, SEXP climvars, SEXP jd, SEXP lt, SEXP theta, SEXP
   check(ctx, mc_run_onestep(ctx, REAL(climvars), Rf_asReal(jd), Rf_asReal(lt), REAL(theta), REAL(thetap), NULL));
   return R_NilValue;
 }
-/* returns list(series = [nsamp x 8 x nt], stats = [ncol x 6], flags = int[ncol]) */
-SEXP mcb_run_transient(SEXP ptr, SEXP t0, SEXP t1, SEXP tsoil, SEXP samp, SEXP ncol_) {
+/* vegt: array c(nvt, 2m+1, T) (== [T][2m+1][nvt]); .vegpsort for every time step (R/code.R:904-916) */
+SEXP mcb_set_vegt(SEXP ptr, SEXP vegt, SEXP T, SEXP nvt) {
+  mc_ctx* ctx = get_ctx(ptr);
+  check(ctx, mc_set_vegt(ctx, (int64_t)Rf_asReal(T), (int64_t)Rf_asReal(nvt), opt(vegt)));
+  return R_NilValue;
+}
+/* thetaz: matrix sm x T (== [T][sm]): runmodel's theta matrix as the user passes it (R/code.R:1146-1154) */
+SEXP mcb_set_thetaz(SEXP ptr, SEXP thetaz, SEXP T) {
+  mc_ctx* ctx = get_ctx(ptr);
+  check(ctx, mc_set_thetaz(ctx, (int64_t)Rf_asReal(T), opt(thetaz)));
+  return R_NilValue;
+}
+/* returns list(series = [nsamp x 8 x nt], stats = [ncol x 6], flags = int[ncol], full = [nsamp x NSTATE x nt] or NULL);
+ * `full` holds the whole state of the sampled columns at every step: the reqhgt "all" / "allclim" tables (R/code.R:1267-1322) */
+SEXP mcb_run_transient(SEXP ptr, SEXP t0, SEXP t1, SEXP tsoil, SEXP samp, SEXP ncol_, SEXP want_full, SEXP nstate) {
   mc_ctx* ctx = get_ctx(ptr);
   const int64_t a = (int64_t)Rf_asReal(t0), b = (int64_t)Rf_asReal(t1), ncol = (int64_t)Rf_asReal(ncol_);
   const int64_t ns = XLENGTH(samp), nt = b - a;
+  const int wf = Rf_asInteger(want_full) != 0 && ns > 0;
   int64_t* idx = (int64_t*)R_alloc(ns > 0 ? ns : 1, sizeof(int64_t));
   for (int64_t j = 0; j < ns; ++j) idx[j] = (int64_t)REAL(samp)[j] - 1;          /* R is 1-based */
   SEXP series = PROTECT(Rf_allocVector(REALSXP, nt * MC_O_N * ns));
   SEXP stats = PROTECT(Rf_allocMatrix(REALSXP, (int)ncol, 6));
   SEXP flags = PROTECT(Rf_allocVector(INTSXP, ncol));
-  check(ctx, mc_run_transient(ctx, a, b, opt(tsoil), idx, ns, ns ? REAL(series) : NULL, NULL, REAL(stats), (int32_t*)INTEGER(flags)));
-  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
-  SET_VECTOR_ELT(out, 0, series); SET_VECTOR_ELT(out, 1, stats); SET_VECTOR_ELT(out, 2, flags);
-  UNPROTECT(4);
+  SEXP full = PROTECT(wf ? Rf_allocVector(REALSXP, nt * (int64_t)Rf_asInteger(nstate) * ns) : R_NilValue);
+  check(ctx, mc_run_transient(ctx, a, b, opt(tsoil), idx, ns, ns ? REAL(series) : NULL, wf ? REAL(full) : NULL, REAL(stats),
+                              (int32_t*)INTEGER(flags)));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+  SET_VECTOR_ELT(out, 0, series); SET_VECTOR_ELT(out, 1, stats); SET_VECTOR_ELT(out, 2, flags); SET_VECTOR_ELT(out, 3, full);
+  UNPROTECT(5);
   return out;
 }
 /* clim: MC_SC_N x T; nmr: MC_SN_N x T (shared); returns [ncol x MC_SO_N x T] */
@@ -99,6 +115,7 @@ static const R_CallMethodDef call_methods[] = {
   {"mcb_set_forcing", (DL_FUNC)&mcb_set_forcing, 5}, {"mcb_set_config", (DL_FUNC)&mcb_set_config, 2},
   {"mcb_set_state", (DL_FUNC)&mcb_set_state, 2}, {"mcb_get_state", (DL_FUNC)&mcb_get_state, 3},
   {"mcb_paraminit", (DL_FUNC)&mcb_paraminit, 2}, {"mcb_spinup", (DL_FUNC)&mcb_spinup, 2},
-  {"mcb_run_onestep", (DL_FUNC)&mcb_run_onestep, 6}, {"mcb_run_transient", (DL_FUNC)&mcb_run_transient, 6},
+  {"mcb_run_onestep", (DL_FUNC)&mcb_run_onestep, 6}, {"mcb_run_transient", (DL_FUNC)&mcb_run_transient, 8},
+  {"mcb_set_vegt", (DL_FUNC)&mcb_set_vegt, 4}, {"mcb_set_thetaz", (DL_FUNC)&mcb_set_thetaz, 3},
   {"mcb_run_steady", (DL_FUNC)&mcb_run_steady, 6}, {NULL, NULL, 0}};
 void R_init_microclimcB200(DllInfo* dll) { R_registerRoutines(dll, NULL, call_methods, NULL, NULL); R_useDynamicSymbols(dll, FALSE); }
