@@ -34,11 +34,22 @@ static long long g_mc_general_steps = 0;     // host (test) build: columns that 
 #endif
 
 // ---- workspace rows -----------------------------------------------------------------------------------------------
-enum { P0_HGT, P0_LA, P0_LNREF, P0_LZU, P0_LZUH, P0_LZOH, P0_LNHD, P0_D, P0_GLNH, P0_DZTB, P0_SUMPAI, P0_WL1, P0_WL2,
-       P0_A0CAP, P0_GXC0, P0_CGCAP, P0_RDZCAP, P0_A0G, P0_GXG1, P0_CGG, P0_RZG,
-       P0_X, P0_KDEN, P0_CLUMP, P0_REFG, P0_SM, P0_TRDM, P0_EMV, P0_VEGEM, P0_TRLWSUM, P0_REFM, P0_LAT, P0_LON,
-       P0_GSMAX, P0_Q50, P0_LWD, P0_SMAX, P0_SOILB, P0_PSIE, P0_SKA, P0_SKB, P0_SKC, P0_SKAD, P0_CVDRY, P0_Z1,
-       P0_SELG, P0_SELH, P0_SELS, P0_ZABOVE, P0_FAST, P0_K5, P0_SLAT, P0_CLAT, P0_CPW, P0_PHW, P0_ZDIFF, P0_NFIX };          // then 1/DZK[sm], DZC[sm], Z[m]
+// Scalar rows of a column.  The first 47 are grouped by the phase that reads them, each group contiguous, so that ONE TMA bulk copy
+// brings a group into stage-buffer rows that are idle at that time, a phase ahead of its use (the reads used to be ~20 exposed L2 / DRAM
+// round trips per step):
+//   G0  (26 rows) forcing perturbation scale / offset [8 + 8] and the phase-0 constants: fetched during the end of the previous step;
+//   G1a ( 9 rows) canopy-top conductance and soil-conductivity constants: fetched during sweep A, read right after it;
+//   G1b (12 rows) radiation geometry and soil-humidity constants of the sweep-B scalars: fetched during sweep A.
+enum { P0_FS0, P0_FO0 = P0_FS0 + 8,
+       P0_HGT = P0_FO0 + 8, P0_LA, P0_LNREF, P0_D, P0_DZTB, P0_LZU, P0_LZUH, P0_LZOH, P0_GLNH, P0_LNHD, P0_G0END,
+       P0_A0CAP = P0_G0END, P0_GXC0, P0_CGCAP, P0_RDZCAP, P0_SKC, P0_SKA, P0_SKB, P0_SKAD, P0_CVDRY, P0_G1AEND,
+       P0_LON = P0_G1AEND, P0_SLAT, P0_CLAT, P0_X, P0_KDEN, P0_K5, P0_SUMPAI, P0_SM, P0_TRDM, P0_SOILB, P0_PSIE, P0_SMAX, P0_G1BEND,
+       P0_WL1 = P0_G1BEND, P0_WL2, P0_A0G, P0_GXG1, P0_CGG, P0_RZG,
+       P0_CLUMP, P0_REFG, P0_EMV, P0_VEGEM, P0_TRLWSUM, P0_REFM, P0_LAT,
+       P0_GSMAX, P0_Q50, P0_LWD, P0_Z1,
+       P0_SELG, P0_SELH, P0_SELS, P0_ZABOVE, P0_FAST, P0_CPW, P0_PHW, P0_ZDIFF, P0_NFIX };          // then 1/DZK[sm], DZC[sm], Z[m]
+constexpr int kG0Rows = P0_G0END, kG1aRows = P0_G1AEND - P0_G0END, kG1bRows = P0_G1BEND - P0_G1AEND;
+constexpr int kGRow0 = 15;                        // G1a / G1b land in rows 15.. of a stage buffer (sweep-A stages use rows 0..14)
 enum { PA_A0I, PA_A0O, PA_EX1, PA_EX2, PA_GLO, PA_GLI, PA_EDO, PA_EDI, PA_GX0, PA_GX1, PA_CG, PA_RDZ, PA_DZ, PA_N };
 enum { PB_REF, PB_PC, PB_SPC, PB_SGC, PB_TRDC, PB_TRDG, PB_TRLW, PB_PAI, PB_IZTH, PB_IZL, PB_IZRF, PB_IZP, PB_MAC, PB_MZ,
        PB_VDEN, PB_DZ, PB_N };
@@ -51,6 +62,7 @@ constexpr int kCL = 5;                            // layers per sweep-C stage (t
 constexpr int kStageRowsB = PB_N + SL_N + kWLiveB + 1;   // sweep-B stage: geometry, state, work rows and the old gt row = 25 rows
 constexpr int kStageRows = 27;                    // rows of 128 doubles per stage buffer (the solver scratch needs 2 x 27)
 static_assert(kStageRowsB <= kStageRows, "sweep-B stage exceeds the stage buffer");
+static_assert(kG0Rows <= kStageRows && kGRow0 + kG1aRows <= kStageRows && kGRow0 + kG1bRows <= kStageRows && PA_N + 2 <= kGRow0, "scalar groups do not fit the idle stage rows");
 constexpr int kNG = 6;                            // merged air layers handled in the streaming form (more: general path)
 
 struct FastLayout {
@@ -117,6 +129,10 @@ MC_HD void geom_column(const FastArgs& a, const RunCfg& cfg, long long c, long l
   double* P = a.P + (c / kTile) * (long long)L.nP() * kTile + (c % kTile);
   auto put = [&](int row, double v) { P[(long long)row * kTile] = v; };
   const double hgt = col.hgt;
+  for (int v = 0; v < kNPert; ++v) {              // forcing perturbation of the column (identity when the run has none)
+    put(P0_FS0 + v, (t.fscale && t.foffset) ? t.fscale[(long long)v * t.ncol + cl] : 1.0);
+    put(P0_FO0 + v, (t.fscale && t.foffset) ? t.foffset[(long long)v * t.ncol + cl] : 0.0);
+  }
   put(P0_HGT, hgt); put(P0_LA, col.La); put(P0_LNREF, col.lnref); put(P0_LZU, col.lzu); put(P0_LZUH, col.lzuh); put(P0_LZOH, col.lzoh);
   put(P0_LNHD, col.lnhd); put(P0_D, col.d); put(P0_GLNH, col.g_lnh); put(P0_DZTB, col.z[m] - col.z[1]); put(P0_SUMPAI, col.sumPAI);
   {
@@ -206,6 +222,13 @@ struct DirectMem {
   MC_HD double ld_keep(const double* p) const { return *p; }
   MC_HD void discard_AB() {}
   MC_HD void discard_C() {}
+  MC_HD void g0_issue() {}
+  MC_HD void g0_wait() {}
+  MC_HD void g1_wait() {}
+  MC_HD void end_begin(bool) {}
+  MC_HD double g0(int r) const { return P[(long long)r * kTile]; }
+  MC_HD double g1a(int r) const { return P[(long long)r * kTile]; }
+  MC_HD double g1b(int r) const { return P[(long long)r * kTile]; }
   MC_HD void step_begin() {}
   MC_HD void sweepB_begin() {}
   MC_HD void sweepC_begin() {}
@@ -213,6 +236,7 @@ struct DirectMem {
   MC_HD void stageB(int i) { ib = i; }
   MC_HD void stageC(int i) { ib = i; }
   MC_HD double c_w(int r) const { return W[(long long)L.wl(ib, WL_TT + r) * kTile]; }
+  MC_HD double c_wq(int q, int r) const { return W[(long long)L.wl(ib + q, WL_TT + r) * kTile]; }   // layer ib + q of the current sweep-C stage
   MC_HD double a_p(int r) const { return P[(long long)L.pa(ia, r) * kTile]; }
   MC_HD double a_tcl() const { return S[(long long)L.sl(ia - 1, SL_TC) * kTile]; }          // only for ia > 1
   MC_HD double a_gto() const { return S[(long long)L.gt(ia) * kTile]; }
@@ -355,6 +379,30 @@ struct PipeMem {
 #pragma unroll
     for (int q = 0; q < 8; ++q) v[q] = __hiloint2double(r[2 * q + 1], r[2 * q]);
   }
+  // ---- scalar groups (see the P0 enum): one more mbarrier (bar[2]), used strictly in turn: G0 of a step, then its G1, then the next G0
+  unsigned gk;                                 // completed group waits (parity of bar[2])
+  const double* g0p; const double* g1ap; const double* g1bp;   // lane-adjusted smem rows of the current groups
+  MC_D void g_issue(unsigned dst32, int row0, int nrows) { bulk_g2s_stream(dst32, Pt + (long long)row0 * kTile, nrows * kTile * 8, bar32 + 16, pol); }
+  // G0 for the coming step goes to the buffer its first sweep-A stage does NOT use (stage k lands in buffer k & 1)
+  MC_D void g0_issue() {
+    if (lane == 0) {
+      mbar_expect_tx(bar32 + 16, kG0Rows * kTile * 8);
+      g_issue(buf32 + ((k + 1) & 1) * (kStageRows * kTile * 8), 0, kG0Rows);
+    }
+    g0p = buf + ((k + 1) & 1) * (kStageRows * kTile) + lane;
+  }
+  MC_D void g_wait() { mbar_wait(bar32 + 16, gk & 1); ++gk; }
+  MC_D void g0_wait() { g_wait(); }
+  MC_D void g1_wait() { g_wait(); }
+  // after sweep C: every lane is done with the stage rows and the node arrays; fetch the next step's G0 behind the end of this one
+  MC_D void end_begin(bool more) {
+    fence_proxy_async();
+    __syncthreads();
+    if (more) g0_issue();
+  }
+  MC_D double g0(int r) const { return g0p[r * kTile]; }
+  MC_D double g1a(int r) const { return g1ap[(kGRow0 + r - P0_A0CAP) * kTile]; }
+  MC_D double g1b(int r) const { return g1bp[(kGRow0 + r - P0_LON) * kTile]; }
   MC_D void issueA(int i, unsigned kk) {
     const unsigned b = buf32 + (kk & 1) * (kStageRows * kTile * 8);
     const unsigned mb = bar32 + (kk & 1) * 8;
@@ -417,6 +465,17 @@ struct PipeMem {
   }
   MC_D void stageA(int i) {
     __syncthreads();                                   // everybody has left the buffer the next stage will fill
+    if (i == L.m) {
+      // sweep B's first stage will land in buffer (k + m) & 1: G1b (read after that copy has been issued) goes to the other one,
+      // G1a (read before it) to that one; both in rows 15.., which the sweep-A stages leave alone
+      const unsigned ba = (k + L.m) & 1, bb = ba ^ 1;
+      if (lane == 0) {
+        mbar_expect_tx(bar32 + 16, (kG1aRows + kG1bRows) * kTile * 8);
+        g_issue(buf32 + (ba * kStageRows + kGRow0) * (kTile * 8), P0_A0CAP, kG1aRows);
+        g_issue(buf32 + (bb * kStageRows + kGRow0) * (kTile * 8), P0_LON, kG1bRows);
+      }
+      g1ap = buf + ba * (kStageRows * kTile) + lane; g1bp = buf + bb * (kStageRows * kTile) + lane;
+    }
     if (lane == 0 && i > 1) issueA(i - 1, k + 1);
     mbar_wait(bar32 + (k & 1) * 8, (k >> 1) & 1);
     cur = buf + (k & 1) * (kStageRows * kTile) + lane;
@@ -437,6 +496,7 @@ struct PipeMem {
   MC_D double b_w(int r) const { return cur[(PB_N + SL_N + r) * kTile]; }
   MC_D double b_gto() const { return cur[(PB_N + SL_N + kWLiveB) * kTile]; }
   MC_D double c_w(int r) const { return cur[r * kTile]; }
+  MC_D double c_wq(int q, int r) const { return cbase[(q * kWLiveC + r) * kTile]; }
 };
 #endif
 
@@ -571,7 +631,7 @@ MC_HD void fast_park_constants(Mem& mem) {
 // `run` false (a column that takes this step through the general path) only suppresses the stores into the state rows.
 // Returns false when the column left the fast envelope (nothing of the state has been modified then).
 template <class Mem, int MS>
-MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunCfg& cfg /* launch-uniform fields only */, double surfwet, bool run, bool emit,
+MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunCfg& cfg /* launch-uniform fields only */, double surfwet, bool run, bool emit, bool more /* another step follows in this launch */,
                      double reqhgt, int charmode,
                      double relhum0, double rsw0, double skyem0, StepOut& out) {
   const FastLayout L = mem.L;
@@ -597,13 +657,13 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     const double tairn = fc.tair, pkn = fc.pk;
     double relhumn = fc.relhum, u = fc.u;
     const double ppk = s0(S0_PK), Hprev = s0(S0_H), ps1 = s0(L.soiltc(1));
-    const double hgt = p0(P0_HGT);
+    const double hgt = mem.g0(P0_HGT);
     cpk = 44.6 * fdiv(pkn, 101.3);                                                  // phair(t, pk) = c * 273.15 / (t + 273.15)
     const double pha = phair(tairn, pkn);
     double u2;
     if (cfg.metopen) {
       if (cfg.windhgt != 2) u = fdiv(u * 4.87, flog(67.8 * cfg.windhgt - 5.42));
-      u2 = fdiv(u * p0(P0_LA), log(67.8 * 2 - 5.42));
+      u2 = fdiv(u * mem.g0(P0_LA), log(67.8 * 2 - 5.42));
     } else {
       u2 = u;
       if (cfg.windhgt != (2 + hgt)) {                                        // windprofile(u, windhgt, hgt+2, ...) with zo above the canopy
@@ -614,14 +674,14 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       }
     }
     if (u2 < 0.5) u2 = 0.5;
-    const double lnref = p0(P0_LNREF);
+    const double lnref = mem.g0(P0_LNREF);
     const double uf = fdiv(0.4 * u2, lnref);
     double psi_mn, psi_h;
-    diabatic_cor(tairn, pkn, Hprev, uf, hgt + 2, p0(P0_D), psi_mn, psi_h);
+    diabatic_cor(tairn, pkn, Hprev, uf, hgt + 2, mem.g0(P0_D), psi_mn, psi_h);
     const double tcm = s0(L.sl(m, SL_TC)), tc1 = s0(L.sl(1, SL_TC));
     double phi_m;
     {
-      const double dz = p0(P0_DZTB);
+      const double dz = mem.g0(P0_DZTB);
       const double idz = frcp(dz);
       const double dtdz = (tcm - tc1) * idz;
       double dudz = (s0(L.uz(m)) - s0(L.uz(1))) * idz;
@@ -635,10 +695,10 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     }
     double tcan;
     {
-      const double ufh = fdiv(0.4 * u2, p0(P0_LZU) + psi_h);
+      const double ufh = fdiv(0.4 * u2, mem.g0(P0_LZU) + psi_h);
       const double mm = fdiv(Hprev, 0.4 * pha * cpair(tairn) * ufh);
-      const double tref = tairn + mm * (p0(P0_LZUH) + psi_h);
-      tcan = tref - mm * (p0(P0_LZOH) + psi_h);
+      const double tref = tairn + mm * (mem.g0(P0_LZUH) + psi_h);
+      tcan = tref - mm * (mem.g0(P0_LZOH) + psi_h);
     }
     const double tfrost = dewpoint(fdiv(relhumn, 100) * satvap(tairn), tairn);
     if (tcan < tfrost) tcan = tfrost;
@@ -651,10 +711,10 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       if (relhumn > 100) relhumn = 100;
     }
     sqphi = fsqrt(phi_m); iphi = frcp(phi_m);
-    ugr = fdiv(0.4 * fdiv(u, p0(P0_GLNH)), 0.4);                                    // grass-profile ur = ugr * gl (uref = u, zref = zu)
+    ugr = fdiv(0.4 * fdiv(u, mem.g0(P0_GLNH)), 0.4);                                    // grass-profile ur = ugr * gl (uref = u, zref = zu)
     {
       const double ufw = 0.4 * fdiv(u2, lnref + psi_mn);
-      double ln2 = p0(P0_LNHD) + psi_mn;
+      double ln2 = mem.g0(P0_LNHD) + psi_mn;
       if (ln2 < 0.55) ln2 = 0.55;
       uh = fdiv(ufw, 0.4) * ln2;
     }
@@ -699,11 +759,17 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     }
     // canopy top <-> reference (code.R:769), Q8: leftover uh, lowest air node
     const double tcan = mem.unpark(X_TCAN), tc1 = mem.unpark(X_TC1);
-    const double a = p0(P0_A0CAP) * sqphi;
+    mem.g1_wait();                                     // the G1 rows were fetched behind the sweep
+    const double a = mem.g1a(P0_A0CAP) * sqphi;
     const double ph = phair_c(cpk, (tcan + tc1) / 2);
-    const double e0 = fexp(-a * p0(P0_GXC0));
-    const double g = fdiv(p0(P0_CGCAP) * ph * uh * a, e0 - 1.0) * iphi;
-    const double gfree = 0.0012 * ph * qroot(fabs(tcan - tc1) * p0(P0_RDZCAP));
+    const double e0 = fexp(-a * mem.g1a(P0_GXC0));
+    const double g = fdiv(mem.g1a(P0_CGCAP) * ph * uh * a, e0 - 1.0) * iphi;
+    const double gfree = 0.0012 * ph * qroot(fabs(tcan - tc1) * mem.g1a(P0_RDZCAP));
+    {                                                  // soilk (microctools; Column::soilk) for this step's theta
+      const double ct = mem.g1a(P0_SKC) * fc.theta;
+      mem.park(X_LAM, mem.g1a(P0_SKA) + mem.g1a(P0_SKB) * fc.theta - mem.g1a(P0_SKAD) * fexp(-((ct * ct) * (ct * ct))));
+      mem.park(X_CV, (mem.g1a(P0_CVDRY) + 4.18 * fc.theta) * 1e6);
+    }
     const double gtncap = (g > gfree) ? g : gfree;
     const double rgcap = frcp(0.5 * gtncap + 0.5 * s0(S0_GTCAP));
     mem.park(X_UH, uh); mem.park(X_SQPHI, sqphi); mem.park(X_CS, cs); mem.park(X_GTNCAP, gtncap); mem.park(X_RGCAP, rgcap);
@@ -722,12 +788,12 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     const double clump = mem.unpark(KR_CLUMP), refg = mem.unpark(KU_REFG), emv = mem.unpark(KG_EMV);   // launch-resident (fast_park_constants)
     double dp = fc.dp;
     // `sa` is sin(solar altitude) from here on: only its sign, the 5-degree test, sin and cot of the angle are used (mc_phys.cuh)
-    const double sa = solsin_pre(fc.lt, p0(P0_LON), cfg.merid, cfg.dst, sday, p0(P0_SLAT), p0(P0_CLAT));
+    const double sa = solsin_pre(fc.lt, mem.g1b(P0_LON), cfg.merid, cfg.dst, sday, mem.g1b(P0_SLAT), mem.g1b(P0_CLAT));
     if (dp != dp) dp = difprop_sh(Rsw, sa);
-    const double xx = p0(P0_X), kden = p0(P0_KDEN);
+    const double xx = mem.g1b(P0_X), kden = mem.g1b(P0_KDEN);
     double K, mul;
-    cank2_sh(xx, sa, kden, p0(P0_K5), K, mul);
-    const double aG0 = refg * cansw_k(Rsw, dp, sa, p0(P0_SUMPAI), p0(P0_SM), p0(P0_TRDM), K, clump);
+    cank2_sh(xx, sa, kden, mem.g1b(P0_K5), K, mul);
+    const double aG0 = refg * cansw_k(Rsw, dp, sa, mem.g1b(P0_SUMPAI), mem.g1b(P0_SM), mem.g1b(P0_TRDM), K, clump);
     const double lwout = kSb * pow4(tairn + 273.15);
     day = sa > 0;
     mem.park(KR_K, K); mem.park(KR_MUL, mul); mem.park(KR_DP, dp); mem.park(KR_RSW, Rsw); mem.park(KR_AG0, aG0);
@@ -737,16 +803,12 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     const double mrh = 0.5 * relhumn + 0.5 * x0[X_RELHUMP];
     const double mpk = 0.5 * ppk + 0.5 * pkn;
     const double eref = fdiv(mrh, 100) * satvap(mtref);
-    const double esoil = soilrh(fc.theta, p0(P0_SOILB), -p0(P0_PSIE), p0(P0_SMAX), ps1) * satvap(ps1);     // Q7
+    const double esoil = soilrh(fc.theta, mem.g1b(P0_SOILB), -mem.g1b(P0_PSIE), mem.g1b(P0_SMAX), ps1) * satvap(ps1);     // Q7
     const double eamn = fdiv(relhumn, 100) * tet_tcan;
     mem.park(KT_EREF, eref); mem.park(KT_ESOIL, esoil); mem.park(KT_MTREF, mtref); mem.park(KT_PS1, ps1); mem.park(KT_RGCAP, mem.unpark(X_RGCAP));
     mem.park(KT_CPPK, (44.6 * fdiv(ppk, 101.3)) * 273.15);
     mem.park(KU_LAMBDA, (-42.575 * tcan + 44994) * surfwet); mem.park(KU_IMPK, frcp(mpk));
     mem.park(KU_TCAN, tcan); mem.park(KU_EAMN, eamn); mem.park(KU_IPPK, frcp(ppk)); mem.park(KU_PKN, pkn);
-    // soilk (microctools; Column::soilk) for this step's theta
-    const double ct = p0(P0_SKC) * fc.theta;
-    mem.park(X_LAM, p0(P0_SKA) + p0(P0_SKB) * fc.theta - p0(P0_SKAD) * fexp(-((ct * ct) * (ct * ct))));
-    mem.park(X_CV, (p0(P0_CVDRY) + 4.18 * fc.theta) * 1e6);
     mem.park_done();
   }
   MC_TICK(2);
@@ -1084,6 +1146,8 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     const double skyem = mem.unpark(X_SKYEM), pkn = mem.unpark(X_PKN);
     const int selG = (int)p0(P0_SELG), selH = (int)p0(P0_SELH);
     const double iTX = frcp(TX);
+    // (Unrolling the kCL layers of a stage so that their branch-free tails interleave was tried and LOST 6-15 %: the sweep grows from 0.5 k to
+    // 1.4 k instructions and the step no longer fits the instruction cache as well — tools/abv.sh cil1..cil5, profiles/README.md r02e.)
     for (int i = 1; i <= m; ++i) {
       mem.stageC(i);
       if (MC_SKIP(8)) continue;
@@ -1128,6 +1192,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   }
   MC_TICK(5);
   mem.discard_C();
+  mem.end_begin(more);
   // ======================= soil limits and fluxes (code.R:868-891), output harvest (code.R:1222-1265) =======================
   double x0[8], x1[8];
   mem.unpark8(X_TAIRN, x0); mem.unpark8(X_PPK, x1);
@@ -1257,20 +1322,16 @@ MC_HD double column_tmean(const TransientArgs& a, long long c) {
   return s / (double)a.T;
 }
 
-// forcing_at (mc_driver.cuh) with the per-column perturbation rows read through the accessor (L2 evict-last when MC_KEEP bit 0: the
-// same 16 values are read every step, but 10 KB of streamed rows per column-step would push them out of L2 in between)
+// forcing_at (mc_driver.cuh) with the column's perturbation taken from the G0 rows (scale / offset were copied into the geometry rows by
+// k_geom and fetched behind the end of the previous step: the 16 loads used to be a DRAM round trip at the start of every step)
 template <class Mem>
 MC_HD void fast_forcing_at(const Mem& mem, const TransientArgs& a, long long t, long long c, double* f) {
-#if defined(__CUDA_ARCH__) && (MC_KEEP & 1)
   const double* row = a.forcing + t * F_N;
 #pragma unroll
   for (int v = 0; v < F_N; ++v) f[v] = row[v];
   if (a.fscale && a.foffset) {
-    double sc[kNPert], of[kNPert];
 #pragma unroll
-    for (int v = 0; v < kNPert; ++v) { sc[v] = mem.ld_keep(a.fscale + (long long)v * a.ncol + c); of[v] = mem.ld_keep(a.foffset + (long long)v * a.ncol + c); }
-#pragma unroll
-    for (int v = 0; v < kNPert; ++v) f[v] = row[v] * sc[v] + of[v];
+    for (int v = 0; v < kNPert; ++v) f[v] = row[v] * mem.g0(P0_FS0 + v) + mem.g0(P0_FO0 + v);
     if (f[F_RELHUM] > 100) f[F_RELHUM] = 100;
     if (f[F_RELHUM] < 1) f[F_RELHUM] = 1;
     if (f[F_U] < 0) f[F_U] = 0;
@@ -1279,9 +1340,6 @@ MC_HD void fast_forcing_at(const Mem& mem, const TransientArgs& a, long long t, 
     if (f[F_RSW] < 0) f[F_RSW] = 0;
     if (f[F_THETA] < 0.001) f[F_THETA] = 0.001;
   }
-#else
-  forcing_at(a, t, c, f);
-#endif
 }
 
 // The whole launch for one column: spin_mode 1 = paraminit + spin-up steps on forcing row 0 (code.R:982-1013);
@@ -1372,8 +1430,10 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
   };
   if (!dead && !fastcol) drop();
   fast_park_constants(mem);
+  if (nsteps > 0) mem.g0_issue();
   for (long long it = 0; it < nsteps; ++it) {
     const long long tt = spin ? 0 : t.t0 + it;
+    mem.g0_wait();
     fast_forcing_at(mem, t, tt, c, f);
     const Forcing fc = {f[F_TAIR], f[F_RELHUM], f[F_PK], f[F_U], tsoil, f[F_SKYEM], f[F_RSW], f[F_DP], f[F_JD], f[F_LT], f[F_THETA],
                         /*Q2*/ f0[F_THETA]};
@@ -1381,7 +1441,7 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
     SolDay sday;                                          // date-only solar terms: from the per-row table when the library made one
     if (t.fsol) { sday.eot = t.fsol[tt * 3]; sday.sdec = t.fsol[tt * 3 + 1]; sday.cdec = t.fsol[tt * 3 + 2]; }
     else sday = sol_day(f[F_JD]);
-    const bool ok = fast_step<Mem, MS>(mem, fc, sday, t.cfg, surfwet, !dead, emit, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
+    const bool ok = fast_step<Mem, MS>(mem, fc, sday, t.cfg, surfwet, !dead, emit, it + 1 < nsteps, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
     if (!dead && !ok) drop();
     if (it == 0 && zdiff) fast_regeom(const_cast<double*>(P), m, sm, cfg.timestep, cfg.zlafact);   // (ordered before the next step's bulk copies by step_begin's fence + barrier)
     if (dead) continue;

@@ -54,9 +54,9 @@ __global__ void __launch_bounds__(kTile, 4) k_transient_fast(const __grid_consta
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* buf = reinterpret_cast<double*>(smem_raw);
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + 2 * kStageRows * kTile * 8);
-  unsigned* tmem_base_s = reinterpret_cast<unsigned*>(bar + 2);
+  unsigned* tmem_base_s = reinterpret_cast<unsigned*>(bar + 3);
   if (threadIdx.x == 0) {
-    mbar_init(bar, 1); mbar_init(bar + 1, 1);
+    mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1);       // two stage barriers, one for the scalar groups
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 32) {         // one warp allocates the block's 128 tensor-memory columns (64 doubles per thread of scratch)
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kTile, 4) k_transient_fast(const __grid_consta
   mem.Pt = a.P + (long long)blockIdx.x * L.nP() * kTile; mem.St = a.S + (long long)blockIdx.x * L.nS() * kTile;
   mem.Wt = a.W + (long long)blockIdx.x * L.nW() * kTile;
   mem.P = mem.Pt + threadIdx.x; mem.S = const_cast<double*>(mem.St) + threadIdx.x; mem.W = const_cast<double*>(mem.Wt) + threadIdx.x;
-  mem.buf = buf; mem.bar = bar; mem.bar32 = smem_u32(bar); mem.buf32 = smem_u32(buf); mem.lane = threadIdx.x; mem.k = 0; mem.cur = buf; mem.pol = l2_evict_first_policy(); mem.pol_keep = l2_evict_last_policy();
+  mem.buf = buf; mem.bar = bar; mem.bar32 = smem_u32(bar); mem.buf32 = smem_u32(buf); mem.lane = threadIdx.x; mem.k = 0; mem.gk = 0; mem.g0p = mem.g1ap = mem.g1bp = buf; mem.cur = buf; mem.pol = l2_evict_first_policy(); mem.pol_keep = l2_evict_last_policy();
   mem.tbase = *tmem_base_s + ((unsigned)((threadIdx.x >> 5) * 32) << 16);
   for (int q = 0; q < 8; ++q) mem.tcyc[q] = 0;
   mem.tlast = clock64();

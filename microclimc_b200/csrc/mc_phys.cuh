@@ -154,6 +154,37 @@ MC_HD double flog(double x) {
 #endif
 }
 
+// flog without its out-of-line branch (a straight-line body lets the scheduler interleave several calls): same polynomial; the special
+// operands are patched in by selects — NaN and negative -> NaN, 0 -> -Inf, +Inf -> +Inf.  Subnormal operands (never a vapour pressure)
+// are treated as 0.
+MC_HD double flog_nb(double x) {
+#if defined(__CUDA_ARCH__)
+  int hi = __double2hiint(x);
+  const bool bad = hi < 0x00100000 || hi >= 0x7ff00000;
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;
+  double m = __hiloint2double(hi, __double2loint(x));          // [1, 2)
+  const bool big = m > 1.4142135623730951;
+  m = big ? m * 0.5 : m; e = big ? e + 1 : e;
+  const double sn = m - 1.0, sd = m + 1.0;
+  const double s1 = fdiv(sn, sd);
+  const double z = s1 * s1, z2 = z * z, z4 = z2 * z2;
+  const double p01 = fma(c_log_poly[1], z, c_log_poly[0]), p23 = fma(c_log_poly[3], z, c_log_poly[2]);
+  const double p45 = fma(c_log_poly[5], z, c_log_poly[4]), p67 = fma(c_log_poly[7], z, c_log_poly[6]);
+  const double q03 = fma(p23, z2, p01), q47 = fma(p67, z2, p45);
+  const double P = fma(fma(c_log_poly[8], z4, q47), z4, q03);
+  const double ed = (double)e;
+  const double r = fma(-s1, sd, sn) * frcp(sd);
+  const double lo = fma(s1 * z, P, fma(ed, 1.90821492927058770002e-10, 2.0 * r));
+  const double res = fma(ed, 6.93147180369123816490e-01, fma(2.0, s1, lo));
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  const double special = (x != x || x < 0.0) ? __longlong_as_double(0x7ff8000000000000LL) : ((x == inf) ? inf : -inf);
+  return bad ? special : res;
+#else
+  return log(x);
+#endif
+}
+
 MC_HD double dmin(double a, double b) { return a < b ? a : b; }
 MC_HD double dmax(double a, double b) { return a > b ? a : b; }
 MC_HD double sq(double x) { return x * x; }

@@ -8,7 +8,7 @@ kern = sys.argv[2] if len(sys.argv) > 2 else "k_transient_fastILi20ELi10ELb1"
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 blocks = re.split(r"\n\s*Function : ", txt)
 body = [b for b in blocks if b.startswith("_Z") and kern in b.split("\n")[0]][0]
-names = {0x80: "between-steps/init", 0x1: "phase0", 0x2: "sweepA+cap", 0x4: "Bprep", 0x8: "sweepB", 0x10: "solve", 0x20: "sweepC", 0x40: "end"}
+names = {0x80: "phase0", 0x1: "sweepA+cap", 0x2: "Bprep", 0x4: "sweepB (per layer)", 0x8: "solve", 0x10: "sweepC", 0x20: "end", 0x40: "between steps + epilogue"}   # the code AFTER each marker
 segs = []; cur = ["prologue", Counter()]; segs.append(cur)
 for line in body.split("\n"):
     m = re.match(r"\s*/\*([0-9a-f]+)\*/\s+(.*?);", line)
@@ -17,7 +17,7 @@ for line in body.split("\n"):
     ops = ins.split()
     op = ops[1] if ops[0].startswith("@") else ops[0]
     if op == "PMTRIG":
-        v = int(ops[-1], 16); cur = ["after tick -> " + names.get(v, hex(v)), Counter()]; segs.append(cur); continue
+        v = int(ops[-1], 16); cur = [names.get(v, hex(v)), Counter()]; segs.append(cur); continue
     c = cur[1]; c["n"] += 1
     base = op.split(".")[0]
     if base in ("DFMA", "DMUL", "DADD", "DSETP", "DMNMX"): c["fp64"] += 1
