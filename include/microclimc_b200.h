@@ -83,6 +83,10 @@ int mc_set_vegt(mc_ctx* ctx, int64_t T, int64_t nvt, const double* vegt);
  * ignored.  R recycles the soil vector over the canopy layers inside leaftemp (code.R:416-437; canopy layer i sees soil node
  * (i-1) mod sm), which is reproduced; sm > m is rejected.  T must equal the forcing rows of the run; NULL clears.  General kernel. */
 int mc_set_thetaz(mc_ctx* ctx, int64_t T, const double* thetaz);
+/* Statistics across calls: on != 0 starts (or restarts) an accumulation — the mean / min / max (and the flag bits) that mc_run_transient
+ * returns then cover every step run since this call, carried on the device between calls, so a year run week by week needs no host-side
+ * combining and can skip the read-back (stats = NULL) until its last call; on == 0 returns to per-call statistics. */
+int mc_set_stats_accumulate(mc_ctx* ctx, int on);
 int mc_set_config(mc_ctx* ctx, const double* cfg /* [MC_C_N_] */);
 int mc_set_state(mc_ctx* ctx, const double* state /* [NSTATE][ncol] */);
 int mc_get_state(mc_ctx* ctx, double* state);

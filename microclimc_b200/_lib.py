@@ -23,6 +23,7 @@ SYMBOLS = {
     "mc_set_forcing": (C.c_int, [C.c_void_p, I64, PD, PD, PD, PD]),
     "mc_set_vegt": (C.c_int, [C.c_void_p, I64, I64, PD]),
     "mc_set_thetaz": (C.c_int, [C.c_void_p, I64, PD]),
+    "mc_set_stats_accumulate": (C.c_int, [C.c_void_p, C.c_int]),
     "mc_set_config": (C.c_int, [C.c_void_p, PD]),
     "mc_set_state": (C.c_int, [C.c_void_p, PD]),
     "mc_get_state": (C.c_int, [C.c_void_p, PD]),
@@ -160,6 +161,10 @@ class Context:
         thetaz = _f(thetaz)
         assert thetaz.ndim == 2 and thetaz.shape[1] == self.sm, thetaz.shape
         self._chk(lib().mc_set_thetaz(self._h, thetaz.shape[0], _p(thetaz)))
+
+    def set_stats_accumulate(self, on=True):
+        """Carry the per-column statistics and flags across run_transient calls (on the device); (re)starts the accumulation."""
+        self._chk(lib().mc_set_stats_accumulate(self._h, 1 if on else 0))
 
     def set_config(self, cfg):
         cfg = _f(cfg); assert cfg.size == 13

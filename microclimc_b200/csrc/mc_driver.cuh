@@ -43,7 +43,32 @@ struct TransientArgs {
   const double* vegt;        // [T][2m+1][nvt]
   long long nvt;
   const double* thetaz;      // [T][sm] soil moisture by depth (theta matrix of runmodel, code.R:1146-1154) or null
+  // statistics carried across calls (mc_set_stats_accumulate): raw sums / minima / maxima and the flag bits live in stats_raw / flags_raw
+  // between calls; `stats_prev_n` > 0: continue from them (steps already in them), else start afresh.  stats (when given) always receives
+  // the statistics over all accumulated steps.
+  double* stats_raw;         // [6][ncol] or null
+  int* flags_raw;            // [ncol] or null
+  long long stats_prev_n;
 };
+// statistics of a column at the start / end of a launch (shared by both kernels, so that a column redone by the general kernel continues
+// from the same partial sums the streaming kernel would have used)
+MC_HD void stats_begin(const TransientArgs& a, long long c, double* st, int& flag) {
+  st[0] = 0; st[1] = 1e300; st[2] = -1e300; st[3] = 0; st[4] = 1e300; st[5] = -1e300; flag = 0;
+  if (a.stats_raw && a.stats_prev_n > 0) {
+    for (int q = 0; q < 6; ++q) st[q] = a.stats_raw[(long long)q * a.ncol + c];
+    if (a.flags_raw) flag = a.flags_raw[c];
+  }
+}
+MC_HD void stats_end(const TransientArgs& a, long long c, const double* st, int flag) {
+  if (a.stats_raw) for (int q = 0; q < 6; ++q) a.stats_raw[(long long)q * a.ncol + c] = st[q];
+  if (a.flags_raw) a.flags_raw[c] = flag;
+  if (a.stats) {
+    const double n = (double)((a.stats_raw ? a.stats_prev_n : 0) + (a.t1 - a.t0));
+    a.stats[0 * a.ncol + c] = st[0] / n; a.stats[1 * a.ncol + c] = st[1]; a.stats[2 * a.ncol + c] = st[2];
+    a.stats[3 * a.ncol + c] = st[3] / n; a.stats[4 * a.ncol + c] = st[4]; a.stats[5 * a.ncol + c] = st[5];
+  }
+  if (a.flags) a.flags[c] = flag;
+}
 
 MC_HD void forcing_at(const TransientArgs& a, long long t, long long c, double* f) {
   const double* row = a.forcing + t * F_N;
@@ -132,8 +157,10 @@ MC_HD void run_column(const TransientArgs& a, long long c, bool live = true) {
     col.precompute_leafgeom(cl);
   }
   const double tsoil = (a.tsoil && a.tsoil[c] == a.tsoil[c]) ? a.tsoil[c] : tmean;
-  double st[6] = {0, 1e300, -1e300, 0, 1e300, -1e300};
-  int flag = 0;
+  double st[6];
+  int flag;
+  stats_begin(a, c, st, flag);
+  flag |= a.flag_or;
   const long long slot = (a.nsamp > 0 && a.samp_of) ? a.samp_of[c] : -1;
   const int NS = nstate_rows(m, a.sm);
   for (long long t = a.t0; t < a.t1; ++t) {
@@ -157,12 +184,7 @@ MC_HD void run_column(const TransientArgs& a, long long c, bool live = true) {
     }
   }
   if (!live) return;
-  if (a.stats) {
-    const double n = (double)(a.t1 - a.t0);
-    a.stats[0 * a.ncol + c] = st[0] / n; a.stats[1 * a.ncol + c] = st[1]; a.stats[2 * a.ncol + c] = st[2];
-    a.stats[3 * a.ncol + c] = st[3] / n; a.stats[4 * a.ncol + c] = st[4]; a.stats[5 * a.ncol + c] = st[5];
-  }
-  if (a.flags) a.flags[c] = flag | a.flag_or;
+  stats_end(a, c, st, flag);
   col.store_state(a.state, a.ncol, c);
 }
 

@@ -1408,9 +1408,10 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
   const long long nsteps = spin ? (long long)t.spin_steps : t.t1 - t.t0;
   const double tsoil = spin ? tmean : (have_tsoil ? t.tsoil[c] : tmean);
   const double surfwet = cfg.surfwet;
-  double stt[6] = {0, 1e300, -1e300, 0, 1e300, -1e300};
+  double stt[6];
   double Hsum = 0;
-  int flag = 0;
+  int flag;
+  stats_begin(t, c, stt, flag);
   const long long slot = (!spin && t.nsamp > 0 && t.samp_of) ? t.samp_of[c] : -1;
   // `dead`: padding lane, or a column that left the streaming form (now or in the spin-up launch of the same call): it keeps
   // computing with its stores suppressed (tensor-memory accesses and barriers are collective) and the general kernel redoes it.
@@ -1456,14 +1457,7 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
       if (t.full) abi_state_from_ws(L, P, S, W, t.soilp + (long long)S_NSCAL * t.ncol + c, t.ncol, t.full + it * NS * t.nsamp + slot, t.nsamp);
     }
   }
-  if (!dead && !spin) {
-    if (t.stats) {
-      const double n = (double)(t.t1 - t.t0);
-      t.stats[0 * t.ncol + c] = stt[0] / n; t.stats[1 * t.ncol + c] = stt[1]; t.stats[2 * t.ncol + c] = stt[2];
-      t.stats[3 * t.ncol + c] = stt[3] / n; t.stats[4 * t.ncol + c] = stt[4]; t.stats[5 * t.ncol + c] = stt[5];
-    }
-    if (t.flags) t.flags[c] = flag;
-  }
+  if (!dead && !spin) stats_end(t, c, stt, flag);
   if (!dead) abi_state_from_ws(L, P, S, W, t.soilp + (long long)S_NSCAL * t.ncol + c, t.ncol, t.state + c, t.ncol);
 }
 

@@ -222,7 +222,7 @@ struct Shard {
   HBuf hser, hfull;
   cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
   DBuf vegp, soilp, lat, lon, state, state_bak, fscale, foffset, forcing, season, tsoil, stats, series, full, samp_of, flags,
-      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fsol, fP, fS, fW, dbg, ffail, flist, fcount, samp_cols, vegt, thetaz;
+      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fsol, fP, fS, fW, dbg, ffail, flist, fcount, samp_cols, vegt, thetaz, stats_raw, flags_raw;
   bool fast_attr = false;
   bool has_pert = false, has_season = false, has_state = false, bak_valid = false;
   long long nvt = 0, vegt_T = 0, thetaz_T = 0; bool has_thetaz = false;       // time-varying vegetation / soil moisture by depth loaded (mc_set_vegt, mc_set_thetaz)
@@ -243,6 +243,7 @@ struct mc_ctx {
   bool has_cfg = false;
   std::string err;
   double last_ms = 0; long long last_launches = 0;
+  bool stats_accum = false; long long stats_n = 0;   // mc_set_stats_accumulate: statistics carried across mc_run_transient calls, steps in them
   bool keep_replay_state = false;   // set by the first mc_bench_resident call: transient runs then keep a copy of their incoming state
 };
 
@@ -460,7 +461,7 @@ void mc_destroy(mc_ctx* ctx) {
     DBuf* bufs[] = {&s.vegp, &s.soilp, &s.lat, &s.lon, &s.state, &s.state_bak, &s.fscale, &s.foffset, &s.forcing, &s.season, &s.tsoil,
                     &s.stats, &s.series, &s.full, &s.samp_of, &s.flags, &s.args6, &s.clim8, &s.theta, &s.thetap, &s.nmerged,
                     &s.sclim, &s.snmr, &s.sseason, &s.sout, &s.spart, &s.ssol, &s.fsol, &s.fP, &s.fS, &s.fW, &s.dbg, &s.ffail, &s.flist,
-                    &s.fcount, &s.samp_cols, &s.vegt, &s.thetaz};
+                    &s.fcount, &s.samp_cols, &s.vegt, &s.thetaz, &s.stats_raw, &s.flags_raw};
     for (DBuf* b : bufs) b->release();
     s.hser.release(); s.hfull.release();
     if (s.e0) cudaEventDestroy(s.e0);
@@ -558,6 +559,11 @@ int mc_set_thetaz(mc_ctx* ctx, int64_t T, const double* thetaz) {
   });
 }
 
+int mc_set_stats_accumulate(mc_ctx* ctx, int on) {
+  if (!ctx) return MC_ERR_ARG;
+  ctx->stats_accum = on != 0; ctx->stats_n = 0;
+  return 0;
+}
 int mc_set_config(mc_ctx* ctx, const double* cfg) {
   if (!ctx || !cfg) return fail(ctx, MC_ERR_ARG, "mc_set_config: bad argument");
   std::memcpy(ctx->cfg, cfg, sizeof(ctx->cfg));
@@ -721,6 +727,10 @@ static int run_transient_impl(mc_ctx* ctx, int64_t t0, int64_t t1, int spin_step
     }
     if (stats) { CU(s.stats.need(sizeof(double) * 6 * s.nc)); a.stats = s.stats.as<double>(); }
     if (flags) { CU(s.flags.need(sizeof(int) * s.nc)); a.flags = s.flags.as<int>(); }
+    if (ctx->stats_accum && nt > 0) {
+      CU(s.stats_raw.need(sizeof(double) * 6 * s.nc)); CU(s.flags_raw.need(sizeof(int) * s.nc));
+      a.stats_raw = s.stats_raw.as<double>(); a.flags_raw = s.flags_raw.as<int>(); a.stats_prev_n = ctx->stats_n;
+    }
     if (spin_steps <= 0 && ctx->keep_replay_state) {   // opt-in (mc_bench_resident): a copy of the incoming state to replay from
       CU(s.state_bak.need(sizeof(double) * NSt * s.nc));
       CU(cudaMemcpyAsync(s.state_bak.p, s.state.p, sizeof(double) * NSt * s.nc, cudaMemcpyDeviceToDevice, s.st));
@@ -754,6 +764,7 @@ static int run_transient_impl(mc_ctx* ctx, int64_t t0, int64_t t1, int spin_step
     return 0;
   });
   collect_timing(ctx);
+  if (rc == 0 && ctx->stats_accum) ctx->stats_n += nt;
   return rc;
 }
 

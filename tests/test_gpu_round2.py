@@ -213,3 +213,25 @@ def test_steady_path_with_matrix_vegp_on_the_gpu(oracle):
         g = np.nan_to_num(got); w_ = np.nan_to_num(want)
         assert np.max(np.abs(g[:, :2] - w_[:, :2])) <= 1e-6
         assert np.max(np.abs(g[:, 2:] - w_[:, 2:]) / np.maximum(np.abs(w_[:, 2:]), 1.0)) <= 1e-8
+
+
+def test_statistics_accumulated_across_calls_equal_one_call(oracle):
+    """mc_set_stats_accumulate: mean / min / max and flags carried on the device over chunked calls are bit-identical to one call over the
+    whole range (same summation order), including for columns redone by the general kernel; turning it off restores per-call statistics."""
+    ncol = 200
+    inp = transient_inputs(oracle, ncol=ncol, T=96)
+    g = S.vegp_deciduous(hgt=0.4, PAIt=1.5); g.update(x=0.4, lw=0.01, gsmax=0.4, hgtg=0.02)
+    vg, _ = S.ensemble(g, loam(oracle), ncol, M, SM, seed=7)
+    inp["veg"][:, ::7] = vg[:, ::7]                                        # some columns take the general kernel
+    cfg = make_cfg(spin_steps=30)
+    one = _ctx(inp, cfg).run_transient(want_series=False)
+    ctx = _ctx(inp, cfg)
+    ctx.set_stats_accumulate(True)
+    ctx.run_transient(0, 40, want_series=False, want_stats=False, want_flags=False)
+    ctx.run_transient(40, 41, want_series=False, want_stats=False, want_flags=False)
+    r = ctx.run_transient(41, 96, want_series=False)
+    np.testing.assert_array_equal(r["stats"], one["stats"])
+    np.testing.assert_array_equal(r["flags"], one["flags"])
+    ctx.set_stats_accumulate(False)
+    r2 = ctx.run_transient(90, 96, want_series=False)
+    assert np.all(r2["stats"][1] >= one["stats"][1]) and not np.array_equal(r2["stats"], one["stats"])

@@ -3,7 +3,7 @@
 forcing (8760 steps) after a 200-step spin-up, on one B200 through the C-ABI — 8.76e9 column-timesteps.
 
 The year is run the way a grid user would run it: one `run_transient` call per week of forcing (state resident on the GPU,
-per-column statistics reduced on the device per call and combined over the year on the host), the hourly series of a sample of columns read back, and that sample compared
+per-column statistics reduced on the device and carried there across the calls: mc_set_stats_accumulate), the hourly series of a sample of columns read back, and that sample compared
 with the CPU oracle over the whole year (tolerances of the north_star: 1e-6 K, 1e-8 relative).  Prints one JSON line.
 
   python tools/bench_year.py [--columns 1000000] [--hours 8760] [--chunk 168] [--check 32] [--gpus 1]
@@ -25,46 +25,46 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--columns", type=int, default=1_000_000)
     ap.add_argument("--hours", type=int, default=8760)
-    ap.add_argument("--chunk", type=int, default=168)
+    ap.add_argument("--chunk", type=int, default=168, help="hours per run_transient call (0: the whole year in ONE call / launch)")
     ap.add_argument("--spin", type=int, default=200)
     ap.add_argument("--check", type=int, default=32, help="columns compared with the CPU oracle over the whole year")
     ap.add_argument("--gpus", type=int, default=1, help="GPUs of this box used IN PROCESS (static column split, one host thread per GPU)")
     a = ap.parse_args()
-    from microclimc_b200._lib import Context
+    from microclimc_b200._lib import Context, pinned_empty
     M, SM = B.M, B.SM
+    if a.chunk <= 0:
+        a.chunk = a.hours
     w = B.workload(a.columns, a.hours, seed=1234)
     cfg = B.make_cfg(w["ts"], a.spin)
     nchk = min(a.check, a.columns)
     samp = np.unique(np.linspace(0, a.columns - 1, nchk).astype(np.int64))
     ctx = Context(M, SM, a.gpus, list(range(a.gpus)))
+    # caller-owned result buffers in page-locked memory (mc_host_alloc), reused by every call, as a grid driver would keep them
+    st = pinned_empty((6, a.columns)); fl = pinned_empty((a.columns,), np.int32)
     t_wall0 = time.perf_counter()
     ctx.set_columns(w["veg"], w["soil"], w["lat"], w["lon"])
     ctx.set_forcing(w["f"], w["fs"], w["fo"])
     ctx.set_config(cfg)
+    ctx.set_stats_accumulate(True)        # statistics and flags carried on the device across the weekly calls, read back with the last one
+    t_upload = time.perf_counter() - t_wall0
     dev_ms, launches, series = 0.0, 0, []
-    stats = None                                             # per-call statistics cover [t0, t1): combined over the year here
     spin_ms = None
     for t0 in range(0, a.hours, a.chunk):
         t1 = min(a.hours, t0 + a.chunk)
-        r = ctx.run_transient(t0, t1, samp_idx=samp, want_series=True, want_stats=True, want_flags=True)
+        last = t1 == a.hours
+        r = ctx.run_transient(t0, t1, samp_idx=samp, want_series=True, want_stats=last, want_flags=last, out_stats=st, out_flags=fl)
         ms = ctx.last_kernel_ms()
         if t0 == 0:
             spin_ms = ms                                      # first call holds the spin-up launch as well
         dev_ms += ms; launches += ctx.last_kernel_launches()
         series.append(r["series"])
-        st = r["stats"]; n = t1 - t0
-        if stats is None:
-            stats = st.copy(); stats[[0, 3]] *= n
-        else:
-            stats[[0, 3]] += st[[0, 3]] * n
-            stats[[1, 4]] = np.minimum(stats[[1, 4]], st[[1, 4]]); stats[[2, 5]] = np.maximum(stats[[2, 5]], st[[2, 5]])
     wall = time.perf_counter() - t_wall0
     series = np.concatenate(series)
-    stats[[0, 3]] /= a.hours
-    flags = r["flags"]
+    stats, flags = st, fl
     colsteps = float(a.columns) * (a.hours + a.spin)
     out = {"workload": "C3 full year", "n_gpus_in_process": a.gpus, "columns": a.columns, "hours": a.hours, "spin_steps": a.spin, "chunk_hours": a.chunk,
-           "device_s": dev_ms * 1e-3, "wall_s_incl_upload_and_readback": wall, "first_call_ms_incl_spinup": spin_ms,
+           "device_s": dev_ms * 1e-3, "wall_s_incl_upload_and_readback": wall, "upload_s": t_upload,
+           "first_call_ms_incl_spinup": spin_ms, "columns_left_streaming_form": int(np.count_nonzero(flags & 8)),
            "column_timesteps": colsteps, "column_timesteps_per_s_device": colsteps / (dev_ms * 1e-3),
            "column_timesteps_per_s_wall": colsteps / wall, "kernel_launches": launches,
            "nonfinite_columns": int(np.count_nonzero(flags & 1)),
