@@ -246,6 +246,14 @@ struct DirectMem {
   MC_HD double b_gto() const { return S[(long long)L.gt(ib) * kTile]; }                     // read before the layer stores its new gt
 };
 
+// make BOUNDS=1: every computed index into the stage buffers, the tensor-memory scratch and the tile workspaces is range-checked on the
+// device (printf + trap).  compute-sanitizer is not available on the GPU pool (profiles/r02a_compute_sanitizer_refused.txt); this build is
+// what the memory-safety record of profiles/ was produced with.  Never the shipped build (the checks cost ~15 %).
+#if defined(MC_BOUNDS) && defined(__CUDA_ARCH__)
+#define MC_CHK(cond, what, v) do { if (!(cond)) { printf("[mc bounds] %s = %lld out of range (block %d thread %d)\n", what, (long long)(v), blockIdx.x, threadIdx.x); __trap(); } } while (0)
+#else
+#define MC_CHK(cond, what, v) ((void)0)
+#endif
 #if defined(__CUDACC__)
 #define MC_D __device__ __forceinline__
 // PipeMem: per-stage rows arrive in shared memory through TMA bulk copies; two buffers, one mbarrier each.
@@ -353,15 +361,17 @@ struct PipeMem {
   unsigned tbase;                              // TMEM address of this warp's lane quarter, column 0 of the allocation
   long long tcyc[8], tlast;                    // phase timing (MC_DBG_SKIP bit 16)
   MC_D void park(int slot, double v) {
+    MC_CHK(slot >= 0 && slot < 64, "tensor-memory slot (park)", slot);
     __syncwarp();
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(tbase + 2 * slot), "r"(__double2loint(v)), "r"(__double2hiint(v)));
   }
   MC_D void park_done() { asm volatile("tcgen05.wait::st.sync.aligned;"); }
   // per-thread scratch in the stage buffers while no stage is in flight (54 doubles: row idx of the two buffers, own lane)
-  MC_D double scr_get(int idx) const { return buf[idx * kTile + lane]; }
-  MC_D void scr_put(int idx, double v) { buf[idx * kTile + lane] = v; }
+  MC_D double scr_get(int idx) const { MC_CHK(idx >= 0 && idx < 2 * kStageRows, "solver scratch row (get)", idx); return buf[idx * kTile + lane]; }
+  MC_D void scr_put(int idx, double v) { MC_CHK(idx >= 0 && idx < 2 * kStageRows, "solver scratch row (put)", idx); buf[idx * kTile + lane] = v; }
   MC_D int warp_max(int v) const { __syncwarp(); return __reduce_max_sync(0xffffffffu, v); }
   MC_D double unpark(int slot) {
+    MC_CHK(slot >= 0 && slot < 64, "tensor-memory slot (unpark)", slot);
     unsigned lo, hi;
     __syncwarp();
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(tbase + 2 * slot));
@@ -369,6 +379,7 @@ struct PipeMem {
     return __hiloint2double(hi, lo);
   }
   MC_D void unpark8(int slot0, double* v) {
+    MC_CHK(slot0 >= 0 && slot0 + 8 <= 64, "tensor-memory slot (unpark8)", slot0);
     unsigned r[16];
     __syncwarp();
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -400,9 +411,9 @@ struct PipeMem {
     __syncthreads();
     if (more) g0_issue();
   }
-  MC_D double g0(int r) const { return g0p[r * kTile]; }
-  MC_D double g1a(int r) const { return g1ap[(kGRow0 + r - P0_A0CAP) * kTile]; }
-  MC_D double g1b(int r) const { return g1bp[(kGRow0 + r - P0_LON) * kTile]; }
+  MC_D double g0(int r) const { MC_CHK(r >= 0 && r < kG0Rows, "G0 row", r); return g0p[r * kTile]; }
+  MC_D double g1a(int r) const { MC_CHK(r >= P0_A0CAP && r < P0_G1AEND, "G1a row", r); return g1ap[(kGRow0 + r - P0_A0CAP) * kTile]; }
+  MC_D double g1b(int r) const { MC_CHK(r >= P0_LON && r < P0_G1BEND, "G1b row", r); return g1bp[(kGRow0 + r - P0_LON) * kTile]; }
   MC_D void issueA(int i, unsigned kk) {
     const unsigned b = buf32 + (kk & 1) * (kStageRows * kTile * 8);
     const unsigned mb = bar32 + (kk & 1) * 8;
@@ -488,12 +499,12 @@ struct PipeMem {
     cur = buf + (k & 1) * (kStageRows * kTile) + lane;
     ++k;
   }
-  MC_D double a_p(int r) const { return cur[r * kTile]; }
+  MC_D double a_p(int r) const { MC_CHK(r >= 0 && r < PA_N, "sweep-A stage row", r); return cur[r * kTile]; }
   MC_D double a_tcl() const { return cur[PA_N * kTile]; }
   MC_D double a_gto() const { return cur[(PA_N + 1) * kTile]; }
-  MC_D double b_p(int r) const { return cur[r * kTile]; }
-  MC_D double b_s(int r) const { return cur[(PB_N + r) * kTile]; }
-  MC_D double b_w(int r) const { return cur[(PB_N + SL_N + r) * kTile]; }
+  MC_D double b_p(int r) const { MC_CHK(r >= 0 && r < PB_N, "sweep-B geometry row", r); return cur[r * kTile]; }
+  MC_D double b_s(int r) const { MC_CHK(r >= 0 && r < SL_N, "sweep-B state row", r); return cur[(PB_N + r) * kTile]; }
+  MC_D double b_w(int r) const { MC_CHK(r >= 0 && r < kWLiveB, "sweep-B work row", r); return cur[(PB_N + SL_N + r) * kTile]; }
   MC_D double b_gto() const { return cur[(PB_N + SL_N + kWLiveB) * kTile]; }
   MC_D double c_w(int r) const { return cur[r * kTile]; }
   MC_D double c_wq(int q, int r) const { return cbase[(q * kWLiveC + r) * kTile]; }
@@ -637,16 +648,16 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   const FastLayout L = mem.L;
   const int m = L.m, sm = L.sm;
   const double* const P = mem.P; double* const S = mem.S; double* const W = mem.W;
-  auto p0 = [=](int r) { return P[(long long)r * kTile]; };
+  auto p0 = [=](int r) { MC_CHK(r >= 0 && r < L.nP(), "geometry row", r); return P[(long long)r * kTile]; };
 #if defined(__CUDA_ARCH__) && (MC_KEEP & 2)
   auto s0 = [&](int r) { return mem.ld_keep(S + (long long)r * kTile); };
   auto sput = [&](int r, double v) { mem.st_keep(S + (long long)r * kTile, v); };
 #else
-  auto s0 = [=](int r) { return S[(long long)r * kTile]; };
-  auto sput = [=](int r, double v) { S[(long long)r * kTile] = v; };
+  auto s0 = [=](int r) { MC_CHK(r >= 0 && r < L.nS(), "state row (read)", r); return S[(long long)r * kTile]; };
+  auto sput = [=](int r, double v) { MC_CHK(r >= 0 && r < L.nS(), "state row (write)", r); S[(long long)r * kTile] = v; };
 #endif
-  auto wput = [=](int i, int r, double v) { W[(long long)L.wl(i, r) * kTile] = v; };
-  auto wget = [=](int i, int r) { return W[(long long)L.wl(i, r) * kTile]; };
+  auto wput = [=](int i, int r, double v) { MC_CHK(i >= 1 && i <= L.m && r >= 0 && r < WL_N, "work row (write), layer", i); W[(long long)L.wl(i, r) * kTile] = v; };
+  auto wget = [=](int i, int r) { MC_CHK(i >= 1 && i <= L.m && r >= 0 && r < WL_N, "work row (read), layer", i); return W[(long long)L.wl(i, r) * kTile]; };
   MC_TICK(7);
   mem.step_begin();
   bool fastok = run;
