@@ -83,6 +83,13 @@ int mc_set_vegt(mc_ctx* ctx, int64_t T, int64_t nvt, const double* vegt);
  * ignored.  R recycles the soil vector over the canopy layers inside leaftemp (code.R:416-437; canopy layer i sees soil node
  * (i-1) mod sm), which is reproduced; sm > m is rejected.  T must equal the forcing rows of the run; NULL clears.  General kernel. */
 int mc_set_thetaz(mc_ctx* ctx, int64_t T, const double* thetaz);
+/* Parameter classes (grids with K << ncol distinct vegetation / soil parameter sets, e.g. habitat maps): class_of [ncol], the caller's
+ * promise that columns with the same id >= 0 have identical vegp AND soilp columns (lat / lon / forcing perturbation may differ; a
+ * negative id marks a column of its own).  Tiles of 128 consecutive columns that belong to one class then share their per-layer geometry
+ * rows, which are read from L2 instead of DRAM (the streamed geometry is 5.3 of the 8.7 KB the streaming kernel moves per column-step);
+ * results are bit-identical to a run without classes.  Order the columns by class for it to take effect.  Call after mc_set_columns
+ * (which clears it); NULL clears. */
+int mc_set_classes(mc_ctx* ctx, const int32_t* class_of);
 /* Statistics across calls: on != 0 starts (or restarts) an accumulation — the mean / min / max (and the flag bits) that mc_run_transient
  * returns then cover every step run since this call, carried on the device between calls, so a year run week by week needs no host-side
  * combining and can skip the read-back (stats = NULL) until its last call; on == 0 returns to per-call statistics. */

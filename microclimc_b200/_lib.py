@@ -23,6 +23,7 @@ SYMBOLS = {
     "mc_set_forcing": (C.c_int, [C.c_void_p, I64, PD, PD, PD, PD]),
     "mc_set_vegt": (C.c_int, [C.c_void_p, I64, I64, PD]),
     "mc_set_thetaz": (C.c_int, [C.c_void_p, I64, PD]),
+    "mc_set_classes": (C.c_int, [C.c_void_p, PI32]),
     "mc_set_stats_accumulate": (C.c_int, [C.c_void_p, C.c_int]),
     "mc_set_config": (C.c_int, [C.c_void_p, PD]),
     "mc_set_state": (C.c_int, [C.c_void_p, PD]),
@@ -161,6 +162,13 @@ class Context:
         thetaz = _f(thetaz)
         assert thetaz.ndim == 2 and thetaz.shape[1] == self.sm, thetaz.shape
         self._chk(lib().mc_set_thetaz(self._h, thetaz.shape[0], _p(thetaz)))
+
+    def set_classes(self, class_of):
+        """class_of [ncol] int32: columns with the same id >= 0 have identical vegp and soilp (the caller's promise); None clears."""
+        if class_of is None:
+            self._chk(lib().mc_set_classes(self._h, None)); return
+        c = np.ascontiguousarray(class_of, dtype=np.int32); assert c.shape == (self.ncol,)
+        self._chk(lib().mc_set_classes(self._h, _p(c, PI32)))
 
     def set_stats_accumulate(self, on=True):
         """Carry the per-column statistics and flags across run_transient calls (on the device); (re)starts the accumulation."""

@@ -335,13 +335,49 @@ def _prepare_transient(climdata, vegp, soilp, lat, long, edgedist, reqhgt, zu, t
     return ctx, dict(m=m, sm=sm, ncol=ncol, T=T, char=char, timestep=ts)
 
 
+def _runmodel_batch_by_class(classes, climdata, vegp, soilp, lat, long, kw):
+    """Columns ordered by parameter class for the run (tiles of one class share their geometry rows, mc_set_classes) and the results
+    put back in the caller's order.  vegp / soilp must be packed arrays here; columns of a class must be identical (checked)."""
+    classes = np.asarray(classes)
+    veg = np.ascontiguousarray(vegp, float); soil = np.ascontiguousarray(soilp, float)
+    ncol = veg.shape[1]
+    if soil.shape[1] == 1:
+        soil = np.repeat(soil, ncol, axis=1)
+    order = np.argsort(classes, kind="stable"); inv = np.empty(ncol, np.int64); inv[order] = np.arange(ncol)
+    ids = classes[order].astype(np.int32)
+    first = np.r_[0, np.flatnonzero(np.diff(ids)) + 1]
+    rep = np.repeat(first, np.diff(np.r_[first, ncol]))
+    if not (np.array_equal(veg[:, order], veg[:, order][:, rep]) and np.array_equal(soil[:, order], soil[:, order][:, rep])):
+        raise ValueError("columns of one class must have identical vegp and soilp")
+    per = lambda a: None if a is None else np.ascontiguousarray(np.broadcast_to(np.asarray(a, float), (ncol,))[order])
+    per2 = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a, float)[:, order])
+    kw = dict(kw)
+    sample = kw.pop("sample", None)
+    samp = np.arange(ncol) if sample is None else np.asarray(sample, dtype=np.int64)
+    kw["fscale"], kw["foffset"] = per2(kw.get("fscale")), per2(kw.get("foffset"))
+    if kw.get("previn") is not None:
+        kw["previn"] = per2(kw["previn"])
+    if kw.get("tsoil") is not None and np.ndim(kw["tsoil"]) > 0:
+        kw["tsoil"] = per(kw["tsoil"])
+    r = runmodel_batch(climdata, veg[:, order].copy(), soil[:, order].copy(), per(lat), per(long), sample=inv[samp], _class_ids=ids, **kw)
+    r["stats"] = r["stats"][:, inv]; r["flags"] = r["flags"][inv]; r["state"] = r["state"][:, inv]; r["sample"] = samp
+    return r
+
+
 def runmodel_batch(climdata, vegp, soilp, lat, long, edgedist=100, reqhgt=None, sdepth=2, zu=2, theta=0.3, merid=0, dst=0, n=0.6,
                    steps=200, tsoil=None, metopen=True, windhgt=2, zlafact=1, surfwet=1, previn=None, snow=None, fscale=None,
-                   foffset=None, sample=None, full=False, n_gpus=1):
+                   foffset=None, sample=None, full=False, n_gpus=1, classes=None, _class_ids=None):
     """Batched `runmodel` (R/code.R:1125-1328) over stacked columns.
 
     vegp / soilp: lists of the reference's lists (one per column) or packed [row][column] arrays.
+    classes: optional parameter-class id per column (habitat maps: K << ncol distinct vegp / soilp sets; packed arrays only) — the
+    columns are run ordered by class so that the streamed geometry is shared (mc_set_classes), results come back in the given order.
     Returns dict(series [T][8][nsample] (layout.SERIES), stats [6][ncol], flags, state [NSTATE][ncol], full, sample, obs_time)."""
+    if classes is not None:
+        return _runmodel_batch_by_class(classes, climdata, vegp, soilp, lat, long, dict(
+            edgedist=edgedist, reqhgt=reqhgt, sdepth=sdepth, zu=zu, theta=theta, merid=merid, dst=dst, n=n, steps=steps, tsoil=tsoil,
+            metopen=metopen, windhgt=windhgt, zlafact=zlafact, surfwet=surfwet, previn=previn, snow=snow, fscale=fscale, foffset=foffset,
+            sample=sample, full=full, n_gpus=n_gpus))
     ctx, info = _prepare_transient(climdata, vegp, soilp, lat, long, edgedist, reqhgt, zu, theta, merid, dst, n, steps, metopen, windhgt,
                                    zlafact, surfwet, previn, snow, fscale, foffset, n_gpus)
     m, sm, ncol, char = info["m"], info["sm"], info["ncol"], info["char"]
@@ -349,6 +385,8 @@ def runmodel_batch(climdata, vegp, soilp, lat, long, edgedist=100, reqhgt=None, 
     if not _isna(tsoil):
         ts_arr = np.broadcast_to(np.asarray(tsoil, float), (ncol,)).copy()
     samp = np.arange(ncol) if sample is None else np.asarray(sample, dtype=np.int64)
+    if _class_ids is not None:
+        ctx.set_classes(_class_ids)
     r = ctx.run_transient(tsoil=ts_arr, samp_idx=samp, want_series=True, want_full=bool(full or char))
     r["state"] = ctx.get_state(); r["sample"] = samp; r["obs_time"] = np.asarray(climdata["obs_time"])
     r["m"], r["sm"], r["kernel_ms"] = m, sm, ctx.last_kernel_ms()

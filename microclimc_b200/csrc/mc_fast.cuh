@@ -93,6 +93,10 @@ struct FastArgs {
   int spin_mode;            // 1: paraminit + t.spin_steps steps on forcing row 0 with the running mean of H (spinup, code.R:982-1013)
   // columns that left the streaming form: fail[c] = 1 (during the spin-up launch) or 2 (during the run launch), appended to
   // flist[0][..] / flist[1][..] with counts fcount[0] / fcount[1]; re-run by the general kernel after the streaming launches
+  // Parameter classes (mc_set_classes): tile t takes its per-LAYER geometry rows from tile tile_src[t] — the first tile of the launch whose
+  // 128 columns all belong to the same class as t's (itself when its columns are mixed) — so a grid with K << ncol distinct vegetation /
+  // soil parameter sets streams those 4.6 KB per column-step from L2 instead of DRAM.  Null: every tile reads its own rows.
+  const int* tile_src;
   int* fail;                // [ncol], zeroed before the first launch of a call
   long long* flist;         // [2][ncol]
   unsigned* fcount;         // [2]
@@ -317,6 +321,7 @@ MC_D void discard_line(const void* p) { asm volatile("discard.global.L2 [%0], 12
 struct PipeMem {
   const double* P; double* S; double* W;      // lane-adjusted tile bases (for stores and the few direct reads)
   const double* Pt; const double* St; const double* Wt;   // tile bases (lane 0), for the bulk copies
+  const double* Pl;                            // tile whose per-layer geometry rows this tile reads (Pt, or its class's first tile)
   FastLayout L;
   double* buf;                                 // [2][kStageRows][kTile] in shared memory
   unsigned long long* bar;                     // [2]
@@ -419,7 +424,7 @@ struct PipeMem {
     const unsigned mb = bar32 + (kk & 1) * 8;
     const unsigned bytes = (PA_N + (i > 1 ? 1 : 0) + 1) * kTile * 8;
     mbar_expect_tx(mb, bytes);
-    bulk_g2s_stream(b, Pt + (long long)L.pa(i, 0) * kTile, PA_N * kTile * 8, mb, pol);
+    bulk_g2s_stream(b, Pl + (long long)L.pa(i, 0) * kTile, PA_N * kTile * 8, mb, Pl == Pt ? pol : pol_keep);
     if (i > 1) bulk_g2s_stream(b + PA_N * kTile * 8, St + (long long)L.sl(i - 1, SL_TC) * kTile, kTile * 8, mb, pol);
     bulk_g2s_stream(b + (PA_N + 1) * kTile * 8, St + (long long)L.gt(i) * kTile, kTile * 8, mb, pol);
   }
@@ -427,7 +432,7 @@ struct PipeMem {
     const unsigned b = buf32 + (kk & 1) * (kStageRows * kTile * 8);
     const unsigned mb = bar32 + (kk & 1) * 8;
     mbar_expect_tx(mb, kStageRowsB * kTile * 8);
-    bulk_g2s_stream(b, Pt + (long long)L.pb(i, 0) * kTile, PB_N * kTile * 8, mb, pol);
+    bulk_g2s_stream(b, Pl + (long long)L.pb(i, 0) * kTile, PB_N * kTile * 8, mb, Pl == Pt ? pol : pol_keep);
     bulk_g2s_stream(b + PB_N * kTile * 8, St + (long long)L.sl(i, 0) * kTile, SL_N * kTile * 8, mb, pol);
 #if MC_L2HINT
     bulk_g2s_stream(b + (PB_N + SL_N) * kTile * 8, Wt + (long long)L.wl(i, 0) * kTile, kWLiveB * kTile * 8, mb, pol_keep);
@@ -1441,6 +1446,9 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
     a.flist[(spin ? 0 : t.ncol) + k] = c;
   };
   if (!dead && !fastcol) drop();
+  // with shared per-layer rows (parameter classes) a tile cannot rebuild its leaf-geometry rows after the first step: such a column
+  // (incoming node heights differ from the current geometry) goes to the general kernel
+  if (!dead && zdiff && a.tile_src) drop();
   fast_park_constants(mem);
   if (nsteps > 0) mem.g0_issue();
   for (long long it = 0; it < nsteps; ++it) {
@@ -1455,7 +1463,7 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
     else sday = sol_day(f[F_JD]);
     const bool ok = fast_step<Mem, MS>(mem, fc, sday, t.cfg, surfwet, !dead, emit, it + 1 < nsteps, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
     if (!dead && !ok) drop();
-    if (it == 0 && zdiff) fast_regeom(const_cast<double*>(P), m, sm, cfg.timestep, cfg.zlafact);   // (ordered before the next step's bulk copies by step_begin's fence + barrier)
+    if (it == 0 && zdiff && !a.tile_src) fast_regeom(const_cast<double*>(P), m, sm, cfg.timestep, cfg.zlafact);   // (ordered before the next step's bulk copies by step_begin's fence + barrier)
     if (dead) continue;
     if (spin) { Hsum += S[(long long)S0_H * kTile]; sput(S0_H, Hsum / (double)(it + 1)); continue; }   // previn$H <- mean(H)
     if (so.ng > 1) flag |= 2;

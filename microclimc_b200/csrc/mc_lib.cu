@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(kTile, 4) k_transient_fast(const __grid_consta
   mem.L = L;
   mem.Pt = a.P + (long long)blockIdx.x * L.nP() * kTile; mem.St = a.S + (long long)blockIdx.x * L.nS() * kTile;
   mem.Wt = a.W + (long long)blockIdx.x * L.nW() * kTile;
+  mem.Pl = a.tile_src ? a.P + (long long)a.tile_src[blockIdx.x] * L.nP() * kTile : mem.Pt;
   mem.P = mem.Pt + threadIdx.x; mem.S = const_cast<double*>(mem.St) + threadIdx.x; mem.W = const_cast<double*>(mem.Wt) + threadIdx.x;
   mem.buf = buf; mem.bar = bar; mem.bar32 = smem_u32(bar); mem.buf32 = smem_u32(buf); mem.lane = threadIdx.x; mem.k = 0; mem.gk = 0; mem.g0p = mem.g1ap = mem.g1bp = buf; mem.cur = buf; mem.pol = l2_evict_first_policy(); mem.pol_keep = l2_evict_last_policy();
   mem.tbase = *tmem_base_s + ((unsigned)((threadIdx.x >> 5) * 32) << 16);
@@ -224,10 +225,11 @@ struct Shard {
   HBuf hser, hfull;
   cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
   DBuf vegp, soilp, lat, lon, state, state_bak, fscale, foffset, forcing, season, tsoil, stats, series, full, samp_of, flags,
-      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fsol, fP, fS, fW, dbg, ffail, flist, fcount, samp_cols, vegt, thetaz, stats_raw, flags_raw;
+      args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fsol, fP, fS, fW, dbg, ffail, flist, fcount, samp_cols, vegt, thetaz, stats_raw, flags_raw, tile_src;
   bool fast_attr = false;
   bool has_pert = false, has_season = false, has_state = false, bak_valid = false;
-  long long nvt = 0, vegt_T = 0, thetaz_T = 0; bool has_thetaz = false;       // time-varying vegetation / soil moisture by depth loaded (mc_set_vegt, mc_set_thetaz)
+  long long nvt = 0, vegt_T = 0, thetaz_T = 0; bool has_thetaz = false;
+  bool has_classes = false; long long class_tiles_shared = 0;   // mc_set_classes: tile_src loaded; tiles that read another tile's rows       // time-varying vegetation / soil moisture by depth loaded (mc_set_vegt, mc_set_thetaz)
   float ms = 0; long long launches = 0, pending_launches = 0;   // pending: kernels of mc_set_forcing, reported with the next run
   // replay info for mc_bench_resident
   int last_kind = 0;   // 0 none, 1 transient, 2 steady
@@ -351,8 +353,11 @@ int launch_transient(Shard& s, const TransientArgs& a) {
     CU(cudaFuncSetAttribute(k_transient_fast<20, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
     s.fast_attr = true;
   }
-  FastArgs fa{a, s.fP.as<double>(), s.fS.as<double>(), s.fW.as<double>(), nullptr, 0, s.ffail.as<int>(), s.flist.as<long long>(),
+  FastArgs fa{a, s.fP.as<double>(), s.fS.as<double>(), s.fW.as<double>(), nullptr, 0, nullptr, s.ffail.as<int>(), s.flist.as<long long>(),
               s.fcount.as<unsigned>()};
+  // parameter classes: shared per-layer rows only in launches whose incoming node heights equal the geometry's (the spin-up launch
+  // starts from paraminit's regular grid, which differs whenever reqhgt snaps a node: code.R:573 vs 719)
+  const bool classes_ok_spin = !(a.cfg.reqhgt == a.cfg.reqhgt) && !a.charmode;
 #ifdef MC_ABLATE
   if (a.cfg.dbg & 16) {
     CU(s.dbg.need(sizeof(unsigned long long) * 8));
@@ -363,6 +368,7 @@ int launch_transient(Shard& s, const TransientArgs& a) {
   for (int spin = 1; spin >= 0; --spin) {
     if (spin ? a.spin_steps <= 0 : a.t1 <= a.t0) continue;
     fa.spin_mode = spin;
+    fa.tile_src = (s.has_classes && (spin == 0 || classes_ok_spin)) ? s.tile_src.as<int>() : nullptr;
     k_geom<20, 10><<<(unsigned)ntile, kTile, 0, s.st>>>(fa);
     if (a.m == 20 && a.sm == 10) k_transient_fast<20, 10, true><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
     else k_transient_fast<20, 10, false><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
@@ -463,7 +469,7 @@ void mc_destroy(mc_ctx* ctx) {
     DBuf* bufs[] = {&s.vegp, &s.soilp, &s.lat, &s.lon, &s.state, &s.state_bak, &s.fscale, &s.foffset, &s.forcing, &s.season, &s.tsoil,
                     &s.stats, &s.series, &s.full, &s.samp_of, &s.flags, &s.args6, &s.clim8, &s.theta, &s.thetap, &s.nmerged,
                     &s.sclim, &s.snmr, &s.sseason, &s.sout, &s.spart, &s.ssol, &s.fsol, &s.fP, &s.fS, &s.fW, &s.dbg, &s.ffail, &s.flist,
-                    &s.fcount, &s.samp_cols, &s.vegt, &s.thetaz, &s.stats_raw, &s.flags_raw};
+                    &s.fcount, &s.samp_cols, &s.vegt, &s.thetaz, &s.stats_raw, &s.flags_raw, &s.tile_src};
     for (DBuf* b : bufs) b->release();
     s.hser.release(); s.hfull.release();
     if (s.e0) cudaEventDestroy(s.e0);
@@ -482,7 +488,7 @@ int mc_set_columns(mc_ctx* ctx, int64_t ncol, const double* vegp, const double* 
     Shard& s = ctx->shards[i];
     s.c0 = std::min<long long>((long long)i * per, ncol);
     s.nc = std::min<long long>(per, ncol - s.c0);
-    s.has_state = false; s.has_pert = false; s.last_kind = 0; s.samp_valid = false; s.nvt = 0; s.has_thetaz = false;
+    s.has_state = false; s.has_pert = false; s.last_kind = 0; s.samp_valid = false; s.nvt = 0; s.has_thetaz = false; s.has_classes = false;
   }
   const int NV = mc_nveg(ctx->m), NSo = mc_nsoil(ctx->sm), NSt = mc_nstate(ctx->m, ctx->sm);
   return for_shards(ctx, [&](Shard& s) -> int {
@@ -561,6 +567,33 @@ int mc_set_thetaz(mc_ctx* ctx, int64_t T, const double* thetaz) {
   });
 }
 
+int mc_set_classes(mc_ctx* ctx, const int32_t* class_of) {
+  if (!ctx || ctx->ncol <= 0) return fail(ctx, MC_ERR_ARG, "mc_set_classes: set columns first");
+  if (!class_of) { for (auto& s : ctx->shards) s.has_classes = false; return 0; }
+  return for_shards(ctx, [&](Shard& s) -> int {
+    if (s.nc == 0) return 0;
+    const long long ntile = (s.nc + kTile - 1) / kTile;
+    std::vector<int> src(ntile);
+    std::vector<std::pair<int32_t, int>> first;              // class id -> first class-uniform tile of this shard
+    long long shared = 0;
+    for (long long t = 0; t < ntile; ++t) {
+      const long long c0 = s.c0 + t * kTile, c1 = std::min<long long>(c0 + kTile, s.c0 + s.nc);
+      const int32_t id = class_of[c0];
+      bool uniform = id >= 0;
+      for (long long c = c0 + 1; c < c1 && uniform; ++c) uniform = class_of[c] == id;
+      src[t] = (int)t;
+      if (!uniform) continue;
+      auto it = std::find_if(first.begin(), first.end(), [&](const std::pair<int32_t, int>& p) { return p.first == id; });
+      if (it == first.end()) first.emplace_back(id, (int)t);
+      else { src[t] = it->second; ++shared; }
+    }
+    CU(s.tile_src.need(sizeof(int) * ntile));
+    CU(cudaMemcpyAsync(s.tile_src.p, src.data(), sizeof(int) * ntile, cudaMemcpyHostToDevice, s.st));
+    CU(cudaStreamSynchronize(s.st));
+    s.has_classes = true; s.class_tiles_shared = shared;
+    return 0;
+  });
+}
 int mc_set_stats_accumulate(mc_ctx* ctx, int on) {
   if (!ctx) return MC_ERR_ARG;
   ctx->stats_accum = on != 0; ctx->stats_n = 0;

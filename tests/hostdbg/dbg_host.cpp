@@ -66,7 +66,7 @@ extern "C" int dbg_run_transient_fast(int64_t ncol, int m, int sm, int64_t T, co
   const long long ntile = (ncol + kTile - 1) / kTile;
   std::vector<double> P(ntile * L.nP() * kTile), S(ntile * L.nS() * kTile), W(ntile * L.nW() * kTile);
   std::vector<int> fail(ncol, 0); std::vector<long long> flist(2 * ncol, 0); unsigned fcount[2] = {0, 0};
-  FastArgs a{t, P.data(), S.data(), W.data(), nullptr, 0, fail.data(), flist.data(), fcount};
+  FastArgs a{t, P.data(), S.data(), W.data(), nullptr, 0, nullptr, fail.data(), flist.data(), fcount};
   for (int spin = 1; spin >= 0; --spin) {
     if (spin ? t.spin_steps <= 0 : T <= 0) continue;
     a.spin_mode = spin;

@@ -235,3 +235,46 @@ def test_statistics_accumulated_across_calls_equal_one_call(oracle):
     ctx.set_stats_accumulate(False)
     r2 = ctx.run_transient(90, 96, want_series=False)
     assert np.all(r2["stats"][1] >= one["stats"][1]) and not np.array_equal(r2["stats"], one["stats"])
+
+
+def _classed_grid(oracle, ncol, K=4, seed=3):
+    """A grid of K habitat classes (identical vegp / soilp within a class), per-column lat / forcing perturbation."""
+    inp = transient_inputs(oracle, ncol=K, T=60, seed=seed)
+    rng = np.random.default_rng(seed)
+    cls = rng.integers(0, K, ncol)
+    veg = inp["veg"][:, cls].copy(); soil = inp["soil"][:, cls].copy()
+    fs, fo = S.forcing_perturbation(ncol, seed=seed + 1)
+    return dict(veg=veg, soil=soil, f=inp["f"], ts=inp["ts"], lat=rng.uniform(45, 55, ncol), lon=np.full(ncol, -5.0), fs=fs, fo=fo), cls
+
+
+def test_parameter_classes_share_geometry_rows_bit_identically(oracle):
+    """mc_set_classes: tiles of one class read their per-layer geometry rows from the class's first tile; the results must not change by
+    a single bit, whether the columns are ordered by class (sharing takes effect) or not (mixed tiles keep their own rows)."""
+    ncol = 4 * 256 + 77
+    inp, cls = _classed_grid(oracle, ncol)
+    order = np.argsort(cls, kind="stable")
+    srt = {k: (v[..., order] if isinstance(v, np.ndarray) and v.shape[-1] == ncol else v) for k, v in inp.items()}
+    for case, ids in ((srt, cls[order]), (inp, cls)):
+        for cfg in (make_cfg(spin_steps=30), make_cfg(spin_steps=30, reqhgt=2.0)):           # (reqhgt: the spin-up launch cannot share)
+            a = _ctx(case, cfg); ra = a.run_transient(want_series=False)
+            b = _ctx(case, cfg); b.set_classes(ids); rb = b.run_transient(want_series=False)
+            np.testing.assert_array_equal(a.get_state(), b.get_state())
+            np.testing.assert_array_equal(ra["stats"], rb["stats"]); np.testing.assert_array_equal(ra["flags"], rb["flags"])
+    want = oracle.run_transient(srt["veg"], srt["soil"], srt["f"], srt["lat"], srt["lon"], make_cfg(spin_steps=30), M, SM, fscale=srt["fs"], foffset=srt["fo"])
+    b = _ctx(srt, make_cfg(spin_steps=30)); b.set_classes(cls[order]); b.run_transient(want_series=False)
+    assert_state_close(b.get_state(), want["state"], what="classes vs oracle")
+
+
+def test_runmodel_batch_by_class_returns_the_callers_order(oracle):
+    from microclimc_b200 import api
+    ncol = 300
+    inp, cls = _classed_grid(oracle, ncol, K=3, seed=9)
+    w = S.load_weather(); clim = {k: np.asarray(v)[1000:1048] for k, v in w.items()}
+    kw = dict(steps=20, fscale=inp["fs"], foffset=inp["fo"], sample=np.array([5, 250, 17]))
+    a = api.runmodel_batch(clim, inp["veg"], inp["soil"], inp["lat"], inp["lon"], **kw)
+    b = api.runmodel_batch(clim, inp["veg"], inp["soil"], inp["lat"], inp["lon"], classes=cls, **kw)
+    for k in ("series", "stats", "flags", "state"):
+        np.testing.assert_array_equal(a[k], b[k])
+    bad = inp["veg"].copy(); bad[3, 7] *= 1.01
+    with pytest.raises(ValueError, match="identical"):
+        api.runmodel_batch(clim, bad, inp["soil"], inp["lat"], inp["lon"], classes=cls, **kw)
