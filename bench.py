@@ -362,6 +362,16 @@ def main():
                 other["C5_shard"] = c5_shard(local, hours, args.spin)
             except Exception as e:
                 other["C5_shard"] = {"error": str(e)}
+        if world == 1 and not args.no_extra and args.workload == "C3":
+            # a habitat-class grid in transient mode (4 parameter sets, columns ordered by class): with mc_set_classes the per-layer geometry
+            # rows are shared per class and come from L2; bit-identical results (tools/bench_classes.py; DRAM bytes per column-step measured
+            # with ncu: profiles/r02k_parameter_classes_ncu_dram.csv, 8.44 KB -> 3.69 KB)
+            try:
+                out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_classes.py"), "--reps", "2"], capture_output=True, text=True,
+                                     timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=str(local))).stdout.strip().splitlines()
+                other["habitat_class_grid_transient"] = json.loads(out[-1])
+            except Exception as e:
+                other["habitat_class_grid_transient"] = {"error": str(e)}
         if not args.no_steady and world == 1:
             # BASELINE configs 2 and 4 beside the headline (not bench lines of their own): steady-state runmodelS, k_steady timed with CUDA
             # events inside the library, with the same FP64 roofline view (tools/bench_steady.py)

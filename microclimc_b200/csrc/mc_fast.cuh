@@ -398,7 +398,10 @@ struct PipeMem {
   // ---- scalar groups (see the P0 enum): one more mbarrier (bar[2]), used strictly in turn: G0 of a step, then its G1, then the next G0
   unsigned gk;                                 // completed group waits (parity of bar[2])
   const double* g0p; const double* g1ap; const double* g1bp;   // lane-adjusted smem rows of the current groups
-  MC_D void g_issue(unsigned dst32, int row0, int nrows) { bulk_g2s_stream(dst32, Pt + (long long)row0 * kTile, nrows * kTile * 8, bar32 + 16, pol); }
+#ifndef MC_GKEEP
+#define MC_GKEEP 0
+#endif
+  MC_D void g_issue(unsigned dst32, int row0, int nrows) { bulk_g2s_stream(dst32, Pt + (long long)row0 * kTile, nrows * kTile * 8, bar32 + 16, MC_GKEEP ? pol_keep : pol); }
   // G0 for the coming step goes to the buffer its first sweep-A stage does NOT use (stage k lands in buffer k & 1)
   MC_D void g0_issue() {
     if (lane == 0) {
