@@ -521,9 +521,9 @@ struct PipeMem {
 
 // windcanopy (code.R:279-294) with hoisted pieces: uzv = uh * exp(a*ex); edge term ur * exp(a*ed), ur = ugr * gl
 MC_HD double wc_fast(double uh, double a, double ex, double gl, double ed, double ugr, bool edge) {
-  double uzv = uh * fexp(a * ex);
+  double uzv = uh * fexp_b(a * ex);                 // (a = O(1-30), |ex| <= O(1): bounded; the edge term below is not)
   if (edge) {
-    double uhr = (ugr * gl) * fexp(a * ed);
+    double uhr = (ugr * gl) * fexp_neg(a * ed);       // (ed = -edgedist / (uwr * htop) <= 0, unbounded below)
     if (uzv != uzv) uzv = uhr;
     else if (uhr == uhr && uhr > uzv) uzv = uhr;
   }
@@ -762,7 +762,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         uzn = wc_fast(uh, mem.a_p(PA_A0O) * sqphi, mem.a_p(PA_EX2), mem.a_p(PA_GLI), mem.a_p(PA_EDI), ugr, edge);      // Q9
       }
       const double ph = phair_c(cpk, (tcu + tcl) / 2);
-      const double e0 = fexp(-ai * mem.a_p(PA_GX0)), e1 = fexp(-ai * mem.a_p(PA_GX1));
+      const double e0 = fexp_b(-ai * mem.a_p(PA_GX0)), e1 = fexp_b(-ai * mem.a_p(PA_GX1));      // (gx in [-1, 0])
       const double g = fdiv(mem.a_p(PA_CG) * ph * uh * ai, e0 - e1) * iphi;
       const double gfree = 0.0012 * ph * qroot(fabs(tcu - tcl) * mem.a_p(PA_RDZ));
       const double gtn = (g > gfree) ? g : gfree;
@@ -781,7 +781,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     mem.g1_wait();                                     // the G1 rows were fetched behind the sweep
     const double a = mem.g1a(P0_A0CAP) * sqphi;
     const double ph = phair_c(cpk, (tcan + tc1) / 2);
-    const double e0 = fexp(-a * mem.g1a(P0_GXC0));
+    const double e0 = fexp_b(-a * mem.g1a(P0_GXC0));
     const double g = fdiv(mem.g1a(P0_CGCAP) * ph * uh * a, e0 - 1.0) * iphi;
     const double gfree = 0.0012 * ph * qroot(fabs(tcan - tc1) * mem.g1a(P0_RDZCAP));
     {                                                  // soilk (microctools; Column::soilk) for this step's theta
@@ -856,9 +856,9 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         double kr[8];
         mem.unpark8(KR_K, kr);
         const double K = kr[KR_K - KR_K], clump = kr[KR_CLUMP - KR_K], dp = kr[KR_DP - KR_K];
-        const double trbc = day ? clumptr(fexp(-(mem.b_p(PB_SPC) * K)), clump) : clumptr(0.0, clump);
-        const double trbg = day ? clumptr(fexp(-(mem.b_p(PB_SGC) * K)), clump) : clumptr(0.0, clump);
-        const double sunl = day ? clumptr(fexp(-K * mem.b_p(PB_PC)), clump) : clumptr(0.0, clump);
+        const double trbc = day ? clumptr(fexp_neg(-(mem.b_p(PB_SPC) * K)), clump) : clumptr(0.0, clump);
+        const double trbg = day ? clumptr(fexp_neg(-(mem.b_p(PB_SGC) * K)), clump) : clumptr(0.0, clump);
+        const double sunl = day ? clumptr(fexp_neg(-K * mem.b_p(PB_PC)), clump) : clumptr(0.0, clump);
         // code.R:43-46 per unit (1 - ref): Rswin = aRsw / (1 - ref) (code.R:895) is formed first, aRsw = (1 - ref) * Rswin
         const double xR = kr[KR_RSW - KR_K] * (dp * mem.b_p(PB_TRDC) + (1 - dp) * trbc);
         const double xG = kr[KR_AG0 - KR_K] * (dp * mem.b_p(PB_TRDG) + (1 - dp) * trbg);
@@ -888,11 +888,11 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double gtt2 = frcp(acc2);
       const double izl = mem.b_p(PB_IZL), izrf = mem.b_p(PB_IZRF), izp = mem.b_p(PB_IZP), izth = mem.b_p(PB_IZTH), PAIi = mem.b_p(PB_PAI);
       const double PAIm = 2 * PAIi * izth;
-      const double esj = 0.6108 * fexp((17.27 * ptc) * frcp(ptc + 237.3));      // Tetens, code.R:410
+      const double esj = 0.6108 * fexp_b((17.27 * ptc) * frcp(ptc + 237.3));    // Tetens, code.R:410
       const double eaj = (mem.b_s(SL_RH) * 0.01) * esj;
       const double estl = satvap(ptl);
       const double r237l = frcp(ptl + 237.3);
-      const double tetl = 0.6108 * fexp((17.27 * ptl) * r237l);
+      const double tetl = 0.6108 * fexp_b((17.27 * ptl) * r237l);
       const double delta = (4098 * tetl) * (r237l * r237l);                      // code.R:415
       const double gvo = mem.b_s(SL_GV), ghao = mem.b_s(SL_GHA);
       // 1/(1/a + 1/b) = a*b/(a+b): one division; a = 0 (closed stomata at night) still gives 0
@@ -1190,7 +1190,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
           ea2 = (Yea + (Yeb - Yea) * w) * pkn;                                     // ea <- vn * pk (code.R:852)
         }
       }
-      double r = fdiv(ea2, 0.6108 * fexp((17.27 * tnn) * frcp(tnn + 237.3))) * 100;
+      double r = fdiv(ea2, 0.6108 * fexp_b((17.27 * tnn) * frcp(tnn + 237.3))) * 100;
       if (r > 100) r = 100;
       if (r < 0) r = 0;
       double tdws;                                                               // dewpoint(tln$ea, tn), Q12

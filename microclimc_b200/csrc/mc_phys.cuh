@@ -89,11 +89,20 @@ MC_HD double frcp(double b) {
   return 1.0 / b;
 #endif
 }
+#ifndef MC_FASTDIV
+#define MC_FASTDIV 1
+#endif
 MC_HD double fdiv(double a, double b) {
 #if defined(__CUDA_ARCH__)
   double r = frcp(b);
   double q = a * r;
+#if MC_FASTDIV
+  // q = a * (1/b) with the 0.5-ulp reciprocal: <= 1.5 ulp.  The exact-residual step fma(fma(-q, b, a), r, q) that made it 0.5 ulp is
+  // two more dependent FP64 operations on a chain whose latency is what bounds the kernels (+3.3 % on the bench without it, r02n).
+  return q;
+#else
   return fma(fma(-q, b, a), r, q);
+#endif
 #else
   return a / b;
 #endif
@@ -120,6 +129,40 @@ MC_HD double fexp(double x) {
   return res;
 #else
   return exp(x);
+#endif
+}
+
+// fexp for arguments that are bounded by construction (|x| < 700: the Tetens / Clausius-Clapeyron exponents of physical temperatures,
+// attenuation exponents of O(10)): the two range guards of fexp (a compare and two selects at the head of the dependent chain, another
+// pair at its end) are dropped.  NaN still comes out as NaN (n = 0).  MC_EXPB 0 maps it back to fexp.
+#ifndef MC_EXPB
+#define MC_EXPB 1
+#endif
+MC_HD double fexp_b(double x) {
+#if defined(__CUDA_ARCH__) && MC_EXPB
+  double t = fma(x, 9.233248261689366e+01, 6755399441055744.0);
+  const int n = __double2loint(t);
+  const double kd = t - 6755399441055744.0;
+  double r = fma(kd, -0x1.62e42feep-7, x);
+  r = fma(kd, -0x1.a39ef35793c76p-39, r);
+  const double T = s_exp_tab[n & 63];
+  const double r2 = r * r;
+  const double a = fma(8.3333333333333332e-03, r, 4.1666666666666664e-02), b = fma(1.6666666666666666e-01, r, 0.5);
+  const double d = fma(fma(a, r2, b), r2, r);
+  const double p = fma(T, d, T);
+  return __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
+#else
+  return fexp(x);
+#endif
+}
+
+// fexp for arguments that are never positive (attenuation exponents -K * PAI, which can be very negative when the sun is at the
+// horizon): only the lower clamp is kept.
+MC_HD double fexp_neg(double x) {
+#if defined(__CUDA_ARCH__) && MC_EXPB
+  return fexp_b((x < -708.0) ? -708.0 : x);
+#else
+  return fexp(x);
 #endif
 }
 
@@ -206,7 +249,14 @@ MC_HD double fsqrt(double x) {
   const double e = fma(-t, y, 1.0);
   const double q = e * fma(0.375, e, 0.5);
   const double s0 = fma(t, q, t);
+#ifndef MC_SQRT_HERON
+#define MC_SQRT_HERON 0
+#endif
+#if MC_SQRT_HERON
   const double s = fma(0.5 * y, fma(-s0, s0, x), s0);
+#else
+  const double s = s0;                   // <= 1.5 ulp without the Heron correction (3 operations, 2 chain levels less; r02n)
+#endif
   return (x == 0.0) ? 0.0 : s;
 #else
   const double hx = 0.5 * x;
@@ -226,12 +276,12 @@ MC_HD double pow175(double x) { double r = fsqrt(x); return x * r * fsqrt(r); } 
 // ---- thermodynamics ---------------------------------------------------------------------------
 MC_HD double phair(double tc, double pk) { return 44.6 * fdiv(pk, 101.3) * fdiv(273.15, tc + 273.15); }
 MC_HD double cpair(double tc) { return 2e-05 * tc * tc + 0.0002 * tc + 29.119; }
-MC_HD double tetens(double tc) { return 0.6108 * fexp(fdiv(17.27 * tc, tc + 237.3)); }   // code.R:156,382,410,...
+MC_HD double tetens(double tc) { return 0.6108 * fexp_b(fdiv(17.27 * tc, tc + 237.3)); }   // code.R:156,382,410,...
 MC_HD double phair_c(double c, double tc) { return c * fdiv(273.15, tc + 273.15); }     // c = 44.6 * (pk / 101.3)
 MC_HD double satvap(double tc) {                                   // ice = TRUE
   double e0, L;
   if (tc < 0) { e0 = 610.78 / 1000; L = 2.834e6; } else { e0 = 611.2 / 1000; L = 2.501e6 - 2340 * tc; }
-  return e0 * fexp((L * (1 / 461.5)) * (1 / 273.15 - frcp(tc + 273.15)));
+  return e0 * fexp_b((L * (1 / 461.5)) * (1 / 273.15 - frcp(tc + 273.15)));
 }
 MC_HD double dewpoint(double ea, double tc) {
   double e0, L;

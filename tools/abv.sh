@@ -7,7 +7,7 @@ cd "$(dirname "$0")/.."
 mkdir -p build/ab
 if [ "$1" = build ]; then
   N=$2; shift 2
-  (cd microclimc_b200/csrc && nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v "$@" -shared -o ../../build/ab/$N.so mc_lib.cu -lcudart 2> ../../build/ab/$N.ptxas)
+  (cd microclimc_b200/csrc && nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v $@ -shared -o ../../build/ab/$N.so mc_lib.cu -lcudart 2> ../../build/ab/$N.ptxas)
   grep -A3 "k_transient_fastILi20ELi10ELb1" build/ab/$N.ptxas | sed -n 3,4p | tr '\n' ' '; echo
 else
   shift
