@@ -322,6 +322,9 @@ def main():
         roof = {"bound": "fp64", "unit": "TFLOP/s", "achieved": ach, "peak": peak_fp64,
                 "peak_source": "of measured: mc_fp64_peak_tflops DFMA probe in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "frac": (ach / peak_fp64) if (ach and peak_fp64 > 0) else None,
+                # the same rate against a FIXED unit of work (the round-1 kernel's FP64-pipe instruction count): comparable across rounds,
+                # unlike `frac`, which falls whenever instructions are removed from the kernel
+                "frac_fixed_work": (2.0 * cost.get("fixed_work_fp64_slots_per_colstep", 15166.0) * per_gpu_rate / 1e12 / peak_fp64) if peak_fp64 > 0 else None,
                 "traffic": (traffic_per * ncol * hours) if traffic_per else None,
                 "traffic_per_colstep": traffic_per,
                 "traffic_over_algorithmic": {"vs_152B_state_on_chip": (traffic_per / 152.0) if traffic_per else None,

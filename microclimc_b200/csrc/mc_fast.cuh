@@ -415,7 +415,8 @@ struct PipeMem {
   MC_D void g1_wait() { g_wait(); }
   // after sweep C: every lane is done with the stage rows and the node arrays; fetch the next step's G0 behind the end of this one
   MC_D void end_begin(bool more) {
-    fence_proxy_async();
+    // (no proxy fence: sweep C only READ the stage rows and the node arrays; the generic-proxy writes to them — the solve's scratch — were
+    // fenced by sweepC_begin.  The barrier orders every lane's last read before the copy overwrites the rows.)
     __syncthreads();
     if (more) g0_issue();
   }
