@@ -310,26 +310,31 @@ def main():
             pass
         per_gpu_rate = value / world
         # Roofline of the dominant kernel (k_transient_fast): this path is FP64-pipe bound (DESIGN.md "Measurement").
-        #  achieved = FP64-pipe instructions the shipped kernel executes per column-timestep (ncu, profiles/cost_per_colstep.json), 2 flop
-        #             each, x column-timesteps of the timed launches / their CUDA-event time — pipe utilisation, not algorithmic efficiency;
         #  peak     = DFMA probe measured in this run (MEASURED_PEAKS.json carries HBM and bf16 only, no FP64 figure).
         # The HBM view is reported next to it: measured DRAM traffic per column-timestep (ncu) x rate against the measured copy peak, with
         # its ratio to the algorithmic bytes (152 B with the state resident on chip, 3.3 KB with the state streamed).
-        flop_per = cost.get("fp64_flop_per_colstep")
+        # `achieved` = ALGORITHMIC FP64 work per column-timestep x column-timesteps/s, the work unit FIXED at 30 332 flop = 2 x the 15 166
+        # FP64-pipe instructions the round-1 kernel executed per column-timestep (profiles/r01s; SURVEY.md 8d estimates 3.7e4
+        # flop-equivalents, band 3-6e4, so the unit is at the conservative end).  It does not move when instructions are removed from the
+        # kernel, so rounds are comparable.  `pipe_utilisation` is the other view: the instructions the SHIPPED kernel executes (ncu,
+        # tools/ncu_fp64_count.py) x 2 flop x rate / peak, i.e. how busy the FP64 pipe is — it falls whenever work is removed.
+        unit_flop = 2.0 * cost.get("fixed_work_fp64_slots_per_colstep", 15166.0)
+        exec_flop = cost.get("fp64_flop_per_colstep")
         bytes_per = cost.get("algorithmic_bytes_per_colstep", 152.0)
         traffic_per = cost.get("dram_bytes_per_colstep")
-        ach = (flop_per * per_gpu_rate / 1e12) if flop_per else None
+        ach = unit_flop * per_gpu_rate / 1e12
         roof = {"bound": "fp64", "unit": "TFLOP/s", "achieved": ach, "peak": peak_fp64,
                 "peak_source": "of measured: mc_fp64_peak_tflops DFMA probe in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                "frac": (ach / peak_fp64) if (ach and peak_fp64 > 0) else None,
-                # the same rate against a FIXED unit of work (the round-1 kernel's FP64-pipe instruction count): comparable across rounds,
-                # unlike `frac`, which falls whenever instructions are removed from the kernel
-                "frac_fixed_work": (2.0 * cost.get("fixed_work_fp64_slots_per_colstep", 15166.0) * per_gpu_rate / 1e12 / peak_fp64) if peak_fp64 > 0 else None,
+                "frac": (ach / peak_fp64) if peak_fp64 > 0 else None,
+                "flop_per_colstep": unit_flop,
+                "flop_source": "fixed algorithmic unit: 2 flop x 15 166 FP64-pipe instructions per column-timestep (the round-1 kernel's executed count, "
+                               "profiles/r01s; SURVEY.md 8d estimate 3.7e4 flop-equivalents); DESIGN.md section 6",
+                "pipe_utilisation": {"frac": (exec_flop * per_gpu_rate / 1e12 / peak_fp64) if (exec_flop and peak_fp64 > 0) else None,
+                                     "executed_flop_per_colstep": exec_flop, "source": cost.get("fp64_flop_source")},
                 "traffic": (traffic_per * ncol * hours) if traffic_per else None,
                 "traffic_per_colstep": traffic_per,
                 "traffic_over_algorithmic": {"vs_152B_state_on_chip": (traffic_per / 152.0) if traffic_per else None,
                                              "vs_3.3KB_state_streamed": (traffic_per / 3300.0) if traffic_per else None},
-                "flop_per_colstep": flop_per, "flop_source": cost.get("fp64_flop_source", "tools/opcount: shipped streaming algorithm, 2 x FP64 issue slots"),
                 "hbm": {"achieved": (traffic_per or bytes_per) * per_gpu_rate / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": (traffic_per or bytes_per) * per_gpu_rate / 1e9 / hbm_peak,
                         "peak_source": "of measured: MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "of fallback 6650",

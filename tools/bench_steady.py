@@ -70,8 +70,11 @@ def run(name, ncol, T, t0, snow, reqhgt, reps, habitats=1, gpu=0, quiet=False, p
     fl = st.get("fp64_flop_per_column_hour")
     if fl and peak_fp64:
         ach = fl * rate / 1e12
+        ex = st.get("executed_fp64_flop_per_column_hour")
         out["roofline"] = {"bound": "fp64", "unit": "TFLOP/s", "achieved": ach, "peak": peak_fp64, "frac": ach / peak_fp64,
                            "flop_per_column_hour": fl, "flop_source": st.get("source"),
+                           "pipe_utilisation": {"frac": (ex * rate / 1e12 / peak_fp64) if ex else None, "executed_flop_per_column_hour": ex,
+                                                "source": st.get("executed_source")},
                            "algorithmic_bytes_per_column_hour": st.get("algorithmic_bytes_per_column_hour"),
                            "traffic_per_column_hour": st.get("dram_bytes_per_column_hour")}
     if not quiet:
