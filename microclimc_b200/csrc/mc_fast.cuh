@@ -1016,7 +1016,8 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         if (emit || i == 1 || i == m) sput(L.uz(i), uzn);
         mem.st_stream(S + (long long)L.gt(i) * kTile, gtn);
       }
-      mem.st_keep(W + (long long)L.wl(i, WL_TT) * kTile, TT); mem.st_keep(W + (long long)L.wl(i, WL_EAL) * kTile, ean);
+      // (the EAL row carries log(ean / 0.6108), which this sweep has anyway: sweep C needs ean only inside dewpoint()'s logarithm)
+      mem.st_keep(W + (long long)L.wl(i, WL_TT) * kTile, TT); mem.st_keep(W + (long long)L.wl(i, WL_EAL) * kTile, al);
       if (emit || i == selHb) { wput(i, WL_L, Lp); wput(i, WL_RSWIN, rsw); }
       Lt += Lp; stl += tleafn; ssw += rsw;
     }
@@ -1171,7 +1172,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     for (int i = 1; i <= m; ++i) {
       mem.stageC(i);
       if (MC_SKIP(8)) continue;
-      const double v = mem.c_w(0), ean = mem.c_w(1);
+      const double v = mem.c_w(0), lal = mem.c_w(1);             // lal = log(ean / 0.6108) from sweep B
       double tnn, ea2;
       if (nn == 2) {
         const double wgt = v * iTX;
@@ -1197,9 +1198,10 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       double tdws;                                                               // dewpoint(tln$ea, tn), Q12
       {
         const bool ice = tnn < 0;
-        const double ie0 = ice ? (1 / (610.78 / 1000)) : (1 / (611.2 / 1000));
+        // log(ean / e0) = log(ean / 0.6108) + log(0.6108 / e0), e0 = 0.61078 over ice, 0.6112 over water
+        const double le0 = ice ? 3.27444784653359042e-05 : -6.54664507833277280e-04;
         const double iLv = ice ? (461.5 / 2.834e6) : fdiv(461.5, 2.501e6 - 2340 * tnn);
-        tdws = frcp(1 / 273.15 - iLv * flog(ean * ie0)) - 273.15;
+        tdws = frcp(1 / 273.15 - iLv * (lal + le0)) - 273.15;
       }
       const double tn = (tnn < tdws) ? tdws : tnn;
       const double lwt = kSb * pow4(tn + 273.15);
