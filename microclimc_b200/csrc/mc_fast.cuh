@@ -817,7 +817,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     const double lwout = kSb * pow4(tairn + 273.15);
     day = sa > 0;
     mem.park(KR_K, K); mem.park(KR_MUL, mul); mem.park(KR_DP, dp); mem.park(KR_RSW, Rsw); mem.park(KR_AG0, aG0);
-    mem.park(KR_SKLW, skyem * lwout); mem.park(KR_EMLW, emv * lwout);
+    mem.park(KR_SKLW, emv * (skyem * lwout - emv * lwout)); mem.park(KR_EMLW, emv * (emv * lwout));   // slope and intercept of lwabs in trlw
     mem.park(KG_C101, fdiv(101.3, pkn)); mem.park(KG_CPK, (44.6 * fdiv(pkn, 101.3)) * 273.15);
     const double mtref = 0.5 * tcan + 0.5 * x0[X_TAIRP];
     const double mrh = 0.5 * relhumn + 0.5 * x0[X_RELHUMP];
@@ -863,12 +863,12 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         // code.R:43-46 per unit (1 - ref): Rswin = aRsw / (1 - ref) (code.R:895) is formed first, aRsw = (1 - ref) * Rswin
         const double xR = kr[KR_RSW - KR_K] * (dp * mem.b_p(PB_TRDC) + (1 - dp) * trbc);
         const double xG = kr[KR_AG0 - KR_K] * (dp * mem.b_p(PB_TRDG) + (1 - dp) * trbg);
-        rsw = sunl * kr[KR_MUL - KR_K] * xR + (1 - sunl) * xR + xG;
+        rsw = xR * (sunl * kr[KR_MUL - KR_K] + (1 - sunl)) + xG;
         aRsw = omr * rsw;
         const double trl = mem.b_p(PB_TRLW);
         double kg[8];
         mem.unpark8(KG_EMV, kg);
-        const double aRlw = kg[KG_EMV - KG_EMV] * (trl * kr[KR_SKLW - KR_K] + (1 - trl) * kr[KR_EMLW - KR_K]);       // canlw()$lwabs, code.R:47
+        const double aRlw = kr[KR_EMLW - KR_K] + trl * kr[KR_SKLW - KR_K];       // canlw()$lwabs, code.R:47: emv * (trl * sky + (1 - trl) * canopy)
         Rabsn = aRsw + aRlw;
         const double Qa = 4.6 * rsw;
         gvn = fdiv(kg[KG_GSMAX - KG_EMV] * Qa, Qa + kg[KG_Q50 - KG_EMV]);       // layercond
@@ -921,10 +921,10 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double phc = kt[KT_CPPK - KT_EREF] * iTkc;
       double aL, bL;
       if (timestep * dmax(dmax(g1, g3h), g2) > 1) {
-        const double K1 = gtt * cp, K2 = gtt2 * cp, K3 = gham * cp;
-        const double iden = frcp(K1 + K2 + K3);
-        aL = (K1 * mtref + K2 * ps1 + K3 * ptl) * iden;
-        bL = (0.5 * K3) * iden;
+        // code.R:447-449 with the common factor cp of K1, K2, K3 cancelled between numerator and denominator
+        const double iden = frcp(gtt + gtt2 + gham);
+        aL = (gtt * mtref + gtt2 * ps1 + gham * ptl) * iden;
+        bL = (0.5 * gham) * iden;
       } else {
         const double ma = fdiv(mem.b_p(PB_MAC), cp * phc);
         const double K1 = g1 * cp, K2 = g2 * cp, K3 = g3h * cp * PAIm;
@@ -948,13 +948,13 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double bRe = ku[KU_VSB - KU_LAMBDA] * 2 * (tk * tk * tk);
       const double mz = mem.b_p(PB_MZ);                                          // ml / zla
       const double num = Ra - aRe - aX - aH, bsum = bRe + bX + bH;
-      double dTL = fdiv(mz * num, 1 + mz * bsum);                                // (ml*num) / (zla + ml*bsum)
-      const double dTL2 = fdiv(num, bsum);
-      if (fabs(dTL2) < fabs(dTL)) dTL = dTL2;
+      // (ml*num) / (zla + ml*bsum).  Two pieces of the reference are dead arithmetic and are not evaluated: dTL2 = num / bsum replaces dTL only
+      // when it is SMALLER in magnitude (code.R:467-469), and |num| / bsum >= |num| / (bsum + zla/ml) for every bsum > 0, ml/zla > 0 (bsum holds
+      // 2 eps sigma T^3 > 0; both are NaN together); the limits of tn against max(tair + 15, tleaf) / min(tair - 5, tleaf) (code.R:472-477) can
+      // never bind, since they are applied only where tleaf is already beyond tn on that side.  The general column keeps both literally.
+      double dTL = fdiv(mz * num, 1 + mz * bsum);
       double tnl = aL + bL * dTL;
       double tlf = ptl + dTL;
-      if (tlf > tnl) { const double tmx = dmax(tcan + 15, tlf); if (tnl > tmx) tnl = tmx; }
-      if (tlf < tnl) { const double tmn = dmin(tcan - 5, tlf); if (tnl < tmn) tnl = tmn; }
       const double eam = ae + be * dTL;
       double ean = eaj + 2 * (eam - eaj);
       const double es = tetens(tnl);
@@ -964,10 +964,14 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double Tdew = -fdiv(237.3 * al, al - 17.27);
       double dT1 = -(ptl + dTL - Tdew);
       if (dT1 < 0) dT1 = 0;
-      const double Lc = lambda_l * gvm * (tetens(tlf) - ean) * impk;
-      double dT2 = -mz * Lc;
-      if (dT2 < 0) dT2 = 0;
-      tlf = tlf + dmin(dT1, dT2);
+      // dew on the leaf (code.R:497-503): min(dT1, dT2) with dT2 >= 0 is 0 whenever the leaf is not below the dew point (dT1 == 0), so the
+      // second Tetens evaluation is only made for lanes that need it (a NaN dT1 still takes the branch and propagates as before)
+      if (!(dT1 <= 0)) {
+        const double Lc = lambda_l * gvm * (tetens(tlf) - ean) * impk;
+        double dT2 = -mz * Lc;
+        if (dT2 < 0) dT2 = 0;
+        tlf = tlf + dmin(dT1, dT2);
+      }
       dTL = tlf - ptl;
       const double dTmx = ptc + 20.2 - ptl, dTmn = ptc - 4.5 - ptl;
       if (dTL > dTmx) dTL = dTmx;
@@ -1167,6 +1171,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     const double skyem = mem.unpark(X_SKYEM), pkn = mem.unpark(X_PKN);
     const int selG = (int)p0(P0_SELG), selH = (int)p0(P0_SELH);
     const double iTX = frcp(TX);
+    const double clw = trlw_sum * skyem + (1 - trlw_sum) * emv;
     // (Unrolling the kCL layers of a stage so that their branch-free tails interleave was tried and LOST 6-15 %: the sweep grows from 0.5 k to
     // 1.4 k instructions and the step no longer fits the instruction cache as well — tools/abv.sh cil1..cil5, profiles/README.md r02e.)
     for (int i = 1; i <= m; ++i) {
@@ -1200,12 +1205,13 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         const bool ice = tnn < 0;
         // log(ean / e0) = log(ean / 0.6108) + log(0.6108 / e0), e0 = 0.61078 over ice, 0.6112 over water
         const double le0 = ice ? 3.27444784653359042e-05 : -6.54664507833277280e-04;
-        const double iLv = ice ? (461.5 / 2.834e6) : fdiv(461.5, 2.501e6 - 2340 * tnn);
-        tdws = frcp(1 / 273.15 - iLv * (lal + le0)) - 273.15;
+        // 1 / (1/273.15 - (461.5 / Lv) * L) = Lv / (Lv/273.15 - 461.5 L): one division instead of two
+        const double Lv = ice ? 2.834e6 : 2.501e6 - 2340 * tnn;
+        tdws = fdiv(Lv, Lv * (1 / 273.15) - 461.5 * (lal + le0)) - 273.15;
       }
       const double tn = (tnn < tdws) ? tdws : tnn;
       const double lwt = kSb * pow4(tn + 273.15);
-      const double Rlwin = trlw_sum * skyem * lwt + (1 - trlw_sum) * emv * lwt;
+      const double Rlwin = clw * lwt;                                             // (trlw_sum skyem + (1 - trlw_sum) emv) lwt
       if (i == selG) tnselG = tnn;
       if (runB) { mem.st_stream(S + (long long)L.sl(i, SL_TC) * kTile, tn); mem.st_stream(S + (long long)L.sl(i, SL_RH) * kTile, r); }
       if (emit || i == selH) wput(i, WL_RLWIN, Rlwin);
