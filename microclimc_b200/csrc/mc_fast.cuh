@@ -840,7 +840,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   {
     const int selHb = (int)p0(P0_SELH);
     const double its = 1 / cfg.timestep;              // launch-uniform
-    double acc2 = 0, TT = 0, Lt = 0, stl = 0, ssw = 0, Xs = 0, cp1 = 0;
+    double acc2 = 0, TT = 0, Lt = 0, stl = 0, ssw = 0;
     double oR = 0, oC = 0, ow = 0, otc = 0, oVo = 0, oea = 0, oX = 0, ovd = 0;
     int olo = 1;
     bool open = false;
@@ -981,10 +981,10 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double Lp = (aX + bX * dTL) * PAIi;                                   // code.R:880 (Q1)
       if (i == 1) {                                                               // soil-surface forcing (code.R:799-811)
         const double refg = ku[KU_REFG - KU_LAMBDA], pkn = ku[KU_PKN - KU_LAMBDA];
-        cp1 = cp;
         const double cd1 = (mem.unpark(X_CV) * p0(P0_NFIX + sm)) * (0.5 * its);
         const double icd1 = frcp(cd1);
         const double a1 = (1 - refg) * (aRsw * icd1);
+        double Xs;
         if (esoil - ean > 0) {
           const double mm = fdiv((-42.575 * ptc + 44994) * phc * p0(P0_Z1), pkn);
           const double dl = 4098 * tetens(ps1) / sq(ps1 + 237.3);
@@ -995,6 +995,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         const double Xsmx = fdiv((1 - refg) * aRsw, ghan * cp) + (tnl - ps1);
         if (fabs(Xs) > fabs(Xsmx)) Xs = Xsmx;
         Xs = fabs(Xs) * sgn;
+        mem.park(X_XS, Xs); mem.park(X_CP1, cp);        // parked here: nothing of it stays live over the other layers
       }
       // layermerge (code.R:772) greedy grouping with the layeraverage sums (code.R:814) of the open group
       {
@@ -1029,7 +1030,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       if (ng > 0) { ghi[ng] = m; gw[ng] += ow; gtc[ng] += otc; gVo[ng] += oVo; gea[ng] += oea; gX[ng] += oX; gvd[ng] += ovd; }
       else { ng = 1; glo[1] = 1; ghi[1] = m; }
     }
-    mem.park(X_XS, Xs); mem.park(X_CP1, cp1); mem.park(X_TT, TT); mem.park(X_LT, Lt); mem.park(X_STL, stl); mem.park(X_SSW, ssw);
+    mem.park(X_TT, TT); mem.park(X_LT, Lt); mem.park(X_STL, stl); mem.park(X_SSW, ssw);
     mem.park_done();
   }
   MC_TICK(3);
