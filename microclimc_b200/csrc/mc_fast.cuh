@@ -827,7 +827,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     const double eamn = fdiv(relhumn, 100) * tet_tcan;
     mem.park(KT_EREF, eref); mem.park(KT_ESOIL, esoil); mem.park(KT_MTREF, mtref); mem.park(KT_PS1, ps1); mem.park(KT_RGCAP, mem.unpark(X_RGCAP));
     mem.park(KT_CPPK, (44.6 * fdiv(ppk, 101.3)) * 273.15);
-    mem.park(KU_LAMBDA, (-42.575 * tcan + 44994) * surfwet); mem.park(KU_IMPK, frcp(mpk));
+    mem.park(KU_LAMBDA, fdiv((-42.575 * tcan + 44994) * surfwet, mpk));     // lambda / mpk: the only form sweep B uses
     mem.park(KU_TCAN, tcan); mem.park(KU_EAMN, eamn); mem.park(KU_IPPK, frcp(ppk)); mem.park(KU_PKN, pkn);
     mem.park_done();
   }
@@ -851,7 +851,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double uzn = mem.b_w(WL_UZN), gtn = mem.b_w(WL_GTN);
       // leafabs (code.R:31-49) of this layer
       const double omr = 1 - mem.b_p(PB_REF);
-      double aRsw, rsw, Rabsn, gvn, ghan;
+      double rsw, Rabsn, gvn, ghan;
       const double Tkc = ptc + 273.15, iTkc = frcp(Tkc);
       {
         double kr[8];
@@ -864,7 +864,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         const double xR = kr[KR_RSW - KR_K] * (dp * mem.b_p(PB_TRDC) + (1 - dp) * trbc);
         const double xG = kr[KR_AG0 - KR_K] * (dp * mem.b_p(PB_TRDG) + (1 - dp) * trbg);
         rsw = xR * (sunl * kr[KR_MUL - KR_K] + (1 - sunl)) + xG;
-        aRsw = omr * rsw;
+        const double aRsw = omr * rsw;
         const double trl = mem.b_p(PB_TRLW);
         double kg[8];
         mem.unpark8(KG_EMV, kg);
@@ -875,12 +875,10 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         ghan = gha_fast(kg[KG_LWD - KG_EMV], kg[KG_ILWD - KG_EMV], kg[KG_LWD3 - KG_EMV], uzn, Tkc, iTkc, kg[KG_CPK - KG_EMV] * iTkc, ptl - ptc,
                         kg[KG_C101 - KG_EMV]);
       }
-      double kt[8], ku[8];
+      double kt[8];
       mem.unpark8(KT_EREF, kt);
-      mem.unpark8(KU_LAMBDA, ku);
       const double eref = kt[KT_EREF - KT_EREF], esoil = kt[KT_ESOIL - KT_EREF], mtref = kt[KT_MTREF - KT_EREF], ps1 = kt[KT_PS1 - KT_EREF];
       const double timestep = cfg.timestep;
-      const double lambda_l = ku[KU_LAMBDA - KU_LAMBDA], impk = ku[KU_IMPK - KU_LAMBDA], tcan = ku[KU_TCAN - KU_LAMBDA], eamn = ku[KU_EAMN - KU_LAMBDA];
       // leaftemp (code.R:378-512)
       const double rg = frcp(0.5 * gtn + 0.5 * mem.b_gto());                     // as in sweep A
       acc2 += rg;
@@ -936,7 +934,11 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double aH = cp * gham * (ptl - aL);
       double bH = cp * gham * (0.5 - 0.5 * bL);
       if (bH < 0) bH = 0;
-      const double lg = lambda_l * gvm * impk;
+      // (the second group of step scalars is fetched here, after the vapour / heat balances, so that it does not occupy registers over them)
+      double ku[8];
+      mem.unpark8(KU_LAMBDA, ku);
+      const double eamn = ku[KU_EAMN - KU_LAMBDA];
+      const double lg = ku[KU_LAMBDA - KU_LAMBDA] * gvm;                           // (lambda / mpk) * gv, code.R:456
       double edf_l = (estl > ae ? estl - ae : 0.0);
       if (ae > esj) edf_l = 0;
       const double aX = lg * edf_l;
@@ -967,7 +969,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       // dew on the leaf (code.R:497-503): min(dT1, dT2) with dT2 >= 0 is 0 whenever the leaf is not below the dew point (dT1 == 0), so the
       // second Tetens evaluation is only made for lanes that need it (a NaN dT1 still takes the branch and propagates as before)
       if (!(dT1 <= 0)) {
-        const double Lc = lambda_l * gvm * (tetens(tlf) - ean) * impk;
+        const double Lc = lg * (tetens(tlf) - ean);
         double dT2 = -mz * Lc;
         if (dT2 < 0) dT2 = 0;
         tlf = tlf + dmin(dT1, dT2);
@@ -978,16 +980,18 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       if (dTL < dTmn) dTL = dTmn;
       tnl = aL + bL * dTL;
       const double tleafn = ptl + dTL;
-      const double Lp = (aX + bX * dTL) * PAIi;                                   // code.R:880 (Q1)
+      const double Lp = (aX + bX * dTL) * mem.b_p(PB_PAI);                                   // code.R:880 (Q1)
       if (i == 1) {                                                               // soil-surface forcing (code.R:799-811)
         const double refg = ku[KU_REFG - KU_LAMBDA], pkn = ku[KU_PKN - KU_LAMBDA];
+        const double esoil = mem.unpark(KT_ESOIL), ps1 = mem.unpark(KT_PS1);   // (fetched again: not carried over the leaf balance of every layer)
         const double cd1 = (mem.unpark(X_CV) * p0(P0_NFIX + sm)) * (0.5 * its);
         const double icd1 = frcp(cd1);
+        const double aRsw = (1 - mem.b_p(PB_REF)) * rsw;                          // (1 - ref) * Rswin, as formed for Rabs above
         const double a1 = (1 - refg) * (aRsw * icd1);
         double Xs;
         if (esoil - ean > 0) {
           const double mm = fdiv((-42.575 * ptc + 44994) * phc * p0(P0_Z1), pkn);
-          const double dl = 4098 * tetens(ps1) / sq(ps1 + 237.3);
+          const double dl = fdiv(4098 * tetens(ps1), sq(ps1 + 237.3));
           const double btm = 1 + 0.5 * (mm * icd1) * dl;
           Xs = fdiv(a1 - (mm * icd1) * (esoil - ean), btm);
         } else Xs = a1;
@@ -999,7 +1003,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       }
       // layermerge (code.R:772) greedy grouping with the layeraverage sums (code.R:814) of the open group
       {
-        const double wi = mem.b_p(PB_DZ), phz = phc * wi, rn = frcp(gtn);       // phair(previn$tc, previn$pk) * dz as in sweep A
+        const double wi = mem.b_p(PB_DZ), phz = phc * wi, rn = frcp(mem.b_w(WL_GTN));       // phair(previn$tc, previn$pk) * dz as in sweep A
         TT += phz * rn;                                                           // cumsum((ph/gt) * dz), code.R:797
         oR += rn; oC += phz; open = true;
         ow += wi; otc += wi * ptc; oVo += wi * (eaj * ku[KU_IPPK - KU_LAMBDA]); oea += wi * ean; oX += wi * (tnl - ptc); ovd += wi * mem.b_p(PB_VDEN);
@@ -1018,8 +1022,9 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         mem.st_stream(Sl + SL_GHA * kTile, ghan);
         // previn$uz is only read at the lowest and highest node (code.R:731), so the other rows are written when the state is
         // harvested (emit) and not on every step
-        if (emit || i == 1 || i == m) sput(L.uz(i), uzn);
-        mem.st_stream(S + (long long)L.gt(i) * kTile, gtn);
+        // (stage rows are read again here rather than held in registers since the top of the layer)
+        if (emit || i == 1 || i == m) sput(L.uz(i), mem.b_w(WL_UZN));
+        mem.st_stream(S + (long long)L.gt(i) * kTile, mem.b_w(WL_GTN));
       }
       // (the EAL row carries log(ean / 0.6108), which this sweep has anyway: sweep C needs ean only inside dewpoint()'s logarithm)
       mem.st_keep(W + (long long)L.wl(i, WL_TT) * kTile, TT); mem.st_keep(W + (long long)L.wl(i, WL_EAL) * kTile, al);

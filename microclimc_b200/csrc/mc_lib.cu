@@ -49,7 +49,10 @@ constexpr int kFastSmem = 2 * kStageRows * kTile * 8 + 64;
 // EXACT: the layer counts equal the template bounds (m = MM, sm = MS, all BASELINE configs), so every row offset is a
 // compile-time constant; otherwise they are read from the arguments (6 < m <= MM, sm <= MS).
 template <int MM, int MS, bool EXACT>
-__global__ void __launch_bounds__(kTile, 4) k_transient_fast(const __grid_constant__ FastArgs a) {
+#ifndef MC_FAST_CTAS
+#define MC_FAST_CTAS 4
+#endif
+__global__ void __launch_bounds__(kTile, MC_FAST_CTAS) k_transient_fast(const __grid_constant__ FastArgs a) {
   exp_tab_init();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* buf = reinterpret_cast<double*>(smem_raw);
