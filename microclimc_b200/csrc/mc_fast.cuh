@@ -286,11 +286,10 @@ MC_D void bulk_g2s(unsigned dst32, const void* src, unsigned bytes, unsigned bar
 }
 // streamed rows (geometry, state) are read once per step with a reuse distance far beyond L2: mark them evict-first so
 // that the short-lived work rows and the threads' local scratch stay resident
-MC_D unsigned long long l2_evict_first_policy() {
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
+// (The descriptors createpolicy.fractional.L2::evict_first / evict_last return for fraction 1.0 are fixed encodings — the same constants
+// CUTLASS passes as TMA cache hints, cute/arch/copy_sm90_desc.hpp — so they are immediates here and occupy no registers between uses.)
+constexpr unsigned long long kL2EvictFirst = 0x12F0000000000000ull, kL2EvictLast = 0x14F0000000000000ull;
+MC_D unsigned long long l2_evict_first_policy() { return kL2EvictFirst; }
 MC_D void bulk_g2s_stream(unsigned dst32, const void* src, unsigned bytes, unsigned bar32, unsigned long long pol) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst32), "l"(src),
                "r"(bytes), "r"(bar32), "l"(pol)
@@ -303,11 +302,7 @@ MC_D void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory");
 #ifndef MC_L2HINT
 #define MC_L2HINT 2
 #endif
-MC_D unsigned long long l2_evict_last_policy() {
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
+MC_D unsigned long long l2_evict_last_policy() { return kL2EvictLast; }
 MC_D void st_hint(double* p, double v, unsigned long long pol) {
   asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
 }
@@ -330,8 +325,8 @@ struct PipeMem {
   unsigned k;                                  // stages issued so far (uniform over the block)
   const double* cur;                           // current stage buffer + lane
   const double* cbase;                         // sweep C: start of the current group's rows
-  unsigned long long pol;                      // L2 evict-first policy for the streamed rows
-  unsigned long long pol_keep;                 // L2 evict-last policy for the work rows
+  static constexpr unsigned long long pol = kL2EvictFirst;        // L2 evict-first policy for the streamed rows
+  static constexpr unsigned long long pol_keep = kL2EvictLast;    // L2 evict-last policy for the work rows
 #if MC_L2HINT
   MC_D void st_stream(double* p, double v) const { st_hint(p, v, pol); }
   MC_D void st_keep(double* p, double v) const { st_hint(p, v, pol_keep); }

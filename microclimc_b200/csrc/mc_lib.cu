@@ -49,6 +49,10 @@ constexpr int kFastSmem = 2 * kStageRows * kTile * 8 + 64;
 // EXACT: the layer counts equal the template bounds (m = MM, sm = MS, all BASELINE configs), so every row offset is a
 // compile-time constant; otherwise they are read from the arguments (6 < m <= MM, sm <= MS).
 template <int MM, int MS, bool EXACT>
+// CTAs per SM the register allocation is bounded for.  4 (128 registers) is what shared memory (55 KB per CTA) and tensor memory (128 columns
+// per CTA) allow as well.  Measured around it on the same box (tools/abv.sh, profiles/README.md r02s): 5 (96 registers, still 4 resident) runs
+// 12 % slower, 3 (168 registers, no spills, 3 resident) 4 % slower — each warp is 28 % faster with the registers, which does not make up for
+// a quarter fewer warps.
 #ifndef MC_FAST_CTAS
 #define MC_FAST_CTAS 4
 #endif
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(kTile, MC_FAST_CTAS) k_transient_fast(const __
   mem.Wt = a.W + (long long)blockIdx.x * L.nW() * kTile;
   mem.Pl = a.tile_src ? a.P + (long long)a.tile_src[blockIdx.x] * L.nP() * kTile : mem.Pt;
   mem.P = mem.Pt + threadIdx.x; mem.S = const_cast<double*>(mem.St) + threadIdx.x; mem.W = const_cast<double*>(mem.Wt) + threadIdx.x;
-  mem.buf = buf; mem.bar = bar; mem.bar32 = smem_u32(bar); mem.buf32 = smem_u32(buf); mem.lane = threadIdx.x; mem.k = 0; mem.gk = 0; mem.g0p = mem.g1ap = mem.g1bp = buf; mem.cur = buf; mem.pol = l2_evict_first_policy(); mem.pol_keep = l2_evict_last_policy();
+  mem.buf = buf; mem.bar = bar; mem.bar32 = smem_u32(bar); mem.buf32 = smem_u32(buf); mem.lane = threadIdx.x; mem.k = 0; mem.gk = 0; mem.g0p = mem.g1ap = mem.g1bp = buf; mem.cur = buf;
   mem.tbase = *tmem_base_s + ((unsigned)((threadIdx.x >> 5) * 32) << 16);
   for (int q = 0; q < 8; ++q) mem.tcyc[q] = 0;
   mem.tlast = clock64();
