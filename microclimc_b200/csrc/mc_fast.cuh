@@ -49,8 +49,8 @@ enum { P0_FS0, P0_FO0 = P0_FS0 + 8,
        P0_GSMAX, P0_Q50, P0_LWD, P0_Z1,
        P0_SELG, P0_SELH, P0_SELS, P0_ZABOVE, P0_FAST, P0_CPW, P0_PHW, P0_ZDIFF, P0_NFIX };          // then 1/DZK[sm], DZC[sm], Z[m]
 constexpr int kG0Rows = P0_G0END, kG1aRows = P0_G1AEND - P0_G0END, kG1bRows = P0_G1BEND - P0_G1AEND;
-constexpr int kGRow0 = 15;                        // G1a / G1b land in rows 15.. of a stage buffer (sweep-A stages use rows 0..14)
-enum { PA_A0I, PA_A0O, PA_EX1, PA_EX2, PA_GLO, PA_GLI, PA_EDO, PA_EDI, PA_GX0, PA_GX1, PA_CG, PA_RDZ, PA_DZ, PA_N };
+constexpr int kGRow0 = 15;                        // G1a / G1b land in rows 15.. of a stage buffer (sweep-A stages use rows 0..13)
+enum { PA_A0I, PA_A0O, PA_EX1, PA_EX2, PA_GLO, PA_GLI, PA_EDO, PA_EDI, PA_GX0, PA_GX1, PA_CG, PA_RDZ, PA_N };
 enum { PB_REF, PB_PC, PB_SPC, PB_SGC, PB_TRDC, PB_TRDG, PB_TRLW, PB_PAI, PB_IZTH, PB_IZL, PB_IZRF, PB_IZP, PB_MAC, PB_MZ,
        PB_VDEN, PB_DZ, PB_N };
 enum { S0_TABOVE, S0_RELHUM, S0_TAIR, S0_TSOIL, S0_PK, S0_H, S0_PSIM, S0_G, S0_TCSUM, S0_GTCAP, S0_N };   // then soiltc[sm]
@@ -182,14 +182,14 @@ MC_HD void geom_column(const FastArgs& a, const RunCfg& cfg, long long c, long l
   put(L.pa(m, PA_A0I), col.a0_top); put(L.pa(m, PA_A0O), col.a0_top); put(L.pa(m, PA_EX1), col.ex_top); put(L.pa(m, PA_EX2), col.ex_top);
   put(L.pa(m, PA_GLO), col.gl_top); put(L.pa(m, PA_GLI), col.gl_top); put(L.pa(m, PA_EDO), col.ed_top); put(L.pa(m, PA_EDI), col.ed_top);
   put(L.pa(m, PA_GX0), col.gx0_top); put(L.pa(m, PA_GX1), col.gx1_top); put(L.pa(m, PA_CG), (col.lm_top * col.iw[m]) / hgt);
-  put(L.pa(m, PA_RDZ), 1 / fabs(col.z[m] - col.z[m - 1])); put(L.pa(m, PA_DZ), col.z[m] - col.z[m - 1]);
+  put(L.pa(m, PA_RDZ), 1 / fabs(col.z[m] - col.z[m - 1]));
   for (int i = m - 1; i >= 1; --i) {
     const double zt = col.z[i + 1] - col.z[i], zi = col.z[i + 1] + 0.5 * zt;
     const double z0 = (i > 1) ? col.z[i - 1] : 0;
     put(L.pa(i, PA_A0I), col.a0i[i]); put(L.pa(i, PA_A0O), col.a0o[i]); put(L.pa(i, PA_EX1), col.ex1[i]); put(L.pa(i, PA_EX2), col.ex2[i]);
     put(L.pa(i, PA_GLO), col.gl_o[i]); put(L.pa(i, PA_GLI), col.gl_i[i]); put(L.pa(i, PA_EDO), col.ed_o[i]); put(L.pa(i, PA_EDI), col.ed_i[i]);
     put(L.pa(i, PA_GX0), col.gx0[i]); put(L.pa(i, PA_GX1), col.gx1[i]); put(L.pa(i, PA_CG), (col.lmi[i] * col.iw[i]) / zi);
-    put(L.pa(i, PA_RDZ), 1 / fabs(col.z[i] - z0)); put(L.pa(i, PA_DZ), col.z[i] - z0);
+    put(L.pa(i, PA_RDZ), 1 / fabs(col.z[i] - z0));
   }
   // sweep B rows: leafabs (code.R:31-49) and leaftemp (code.R:378-512) constants of the layer
   for (int i = 1; i <= m; ++i) {
