@@ -798,11 +798,19 @@ static int run_transient_impl(mc_ctx* ctx, int64_t t0, int64_t t1, int spin_step
     CU(cudaEventElapsedTime(&s.ms, s.e0, s.e1));
     s.has_state = true;
     // scatter this shard's sample slots into the caller's arrays (disjoint slots per shard)
-    for (long long k = 0; k < ns; ++k) {
-      const int64_t j = slots[k];
-      if (series) for (long long r = 0; r < nt * MC_O_N; ++r) series[r * nsamp + j] = hser[r * ns + k];
-      if (fullseries) for (long long r = 0; r < nt * NSt; ++r) fullseries[r * nsamp + j] = hfull[r * ns + k];
-    }
+    // (row by row: both sides are walked contiguously — column by column this was 1.4 M cache-missing element copies, ~5 ms per call for
+    // 1 024 sampled columns x 168 h; with one shard owning every slot in order the rows are identical and copied whole)
+    bool whole = ns == (long long)nsamp;
+    for (long long k = 0; whole && k < ns; ++k) whole = slots[k] == k;
+    auto scatter = [&](double* dst, const double* src, long long rows) {
+      if (whole) { memcpy(dst, src, sizeof(double) * (size_t)rows * (size_t)ns); return; }
+      for (long long r = 0; r < rows; ++r) {
+        double* d = dst + r * nsamp; const double* h = src + r * ns;
+        for (long long k = 0; k < ns; ++k) d[slots[k]] = h[k];
+      }
+    };
+    if (ns > 0 && series) scatter(series, hser, nt * MC_O_N);
+    if (ns > 0 && fullseries) scatter(fullseries, hfull, nt * NSt);
     return 0;
   });
   collect_timing(ctx);
