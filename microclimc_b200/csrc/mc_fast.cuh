@@ -29,6 +29,27 @@
 namespace mc {
 
 constexpr int kTile = 128;   // columns per CTA == columns per workspace tile
+// Algebraic forms of round 2's last step (each removes transcendental work from the per-layer chains; 0 restores the earlier form):
+//   MC_LOGWIND  sweep A carries log(uh): windcanopy's two products uh * exp(a ex), ur * exp(a ed) and their maximum become two sums and
+//               a maximum, the gcanopy quotient uh / (e0 - e1) becomes 1 / (exp(-a gx0 - lu) - exp(-a gx1 - lu)): 3 exponentials per
+//               layer instead of 6 (the gl rows hold log(gl));
+//   MC_GHA2     leaf boundary-layer conductance with the common factor ph / d * sqrt(sc) of the forced and free branches taken out
+//               of the maximum: 4 square roots and no reciprocal instead of 5 and one;
+//   MC_GVC      the working state keeps the series conductance gv gha / (gv + gha) of the previous step (all that leaftemp reads of
+//               previn$gv) instead of gv; gv itself is written with the harvest rows when the state is emitted;
+//   MC_MQ       leaftemp's transient air balance with cp cancelled (ma * K_i = mac * g_i / ph, 1 / ph = Tk / (cpk 273.15)): one division less.
+#ifndef MC_LOGWIND
+#define MC_LOGWIND 1
+#endif
+#ifndef MC_GHA2
+#define MC_GHA2 1
+#endif
+#ifndef MC_GVC
+#define MC_GVC 1
+#endif
+#ifndef MC_MQ
+#define MC_MQ 1
+#endif
 #if !defined(__CUDACC__)
 static long long g_mc_general_steps = 0;     // host (test) build: columns that left the streaming form (launch-level count)
 #endif
@@ -55,10 +76,11 @@ enum { PB_REF, PB_PC, PB_SPC, PB_SGC, PB_TRDC, PB_TRDG, PB_TRLW, PB_PAI, PB_IZTH
        PB_VDEN, PB_DZ, PB_N };
 enum { S0_TABOVE, S0_RELHUM, S0_TAIR, S0_TSOIL, S0_PK, S0_H, S0_PSIM, S0_G, S0_TCSUM, S0_GTCAP, S0_N };   // then soiltc[sm]
 enum { SL_TC, SL_TLEAF, SL_RH, SL_RABS, SL_GV, SL_GHA, SL_N };
-enum { WL_GTN, WL_UZN, WL_TT, WL_EAL, WL_L, WL_RSWIN, WL_RLWIN, WL_N };
+enum { WL_GTN, WL_UZN, WL_TT, WL_EAL, WL_L, WL_RSWIN, WL_RLWIN, WL_GVN, WL_N };   // GVN: previn$gv, written with the harvest rows (MC_GVC)
 constexpr int kWLiveB = 2;                        // W rows sweep B reads back from sweep A (GTN, UZN)
 constexpr int kWLiveC = 2;                        // W rows sweep C reads back from sweep B (TT, EAL)
 constexpr int kCL = 5;                            // layers per sweep-C stage (their TT/EAL rows are contiguous: 10 rows)
+static_assert(WL_GTN == 0 && WL_UZN == 1, "sweep B stages the first kWLiveB rows of a layer's block");
 constexpr int kStageRowsB = PB_N + SL_N + kWLiveB + 1;   // sweep-B stage: geometry, state, work rows and the old gt row = 25 rows
 constexpr int kStageRows = 27;                    // rows of 128 doubles per stage buffer (the solver scratch needs 2 x 27)
 static_assert(kStageRowsB <= kStageRows, "sweep-B stage exceeds the stage buffer");
@@ -77,7 +99,7 @@ struct FastLayout {
   MC_HD int uz(int i) const { return S0_N + sm + m * SL_N + (i - 1); }
   MC_HD int gt(int i) const { return S0_N + sm + m * SL_N + m + (i - 1); }          // i = 1..m+1
   MC_HD int nS() const { return S0_N + sm + m * SL_N + m + (m + 1); }
-  // per-layer blocks of 5 rows (GTN, UZN, L, RSWIN, RLWIN), then the sweep-C rows (TT, EAL) of all layers contiguously
+  // per-layer blocks of 6 rows (GTN, UZN, L, RSWIN, RLWIN, GVN), then the sweep-C rows (TT, EAL) of all layers contiguously
   MC_HD int wl(int i, int r) const {
     return (r == WL_TT || r == WL_EAL) ? m * (WL_N - 2) + (i - 1) * 2 + (r - WL_TT) : (i - 1) * (WL_N - 2) + (r < WL_TT ? r : r - 2);
   }
@@ -180,14 +202,14 @@ MC_HD void geom_column(const FastArgs& a, const RunCfg& cfg, long long c, long l
   put(P0_FAST, fast ? 1.0 : 0.0);
   // sweep A rows: layer m (canopy top, code.R:749-753) then the recurrence layers (code.R:756-767)
   put(L.pa(m, PA_A0I), col.a0_top); put(L.pa(m, PA_A0O), col.a0_top); put(L.pa(m, PA_EX1), col.ex_top); put(L.pa(m, PA_EX2), col.ex_top);
-  put(L.pa(m, PA_GLO), col.gl_top); put(L.pa(m, PA_GLI), col.gl_top); put(L.pa(m, PA_EDO), col.ed_top); put(L.pa(m, PA_EDI), col.ed_top);
+  put(L.pa(m, PA_GLO), MC_LOGWIND ? log(col.gl_top) : col.gl_top); put(L.pa(m, PA_GLI), MC_LOGWIND ? log(col.gl_top) : col.gl_top); put(L.pa(m, PA_EDO), col.ed_top); put(L.pa(m, PA_EDI), col.ed_top);
   put(L.pa(m, PA_GX0), col.gx0_top); put(L.pa(m, PA_GX1), col.gx1_top); put(L.pa(m, PA_CG), (col.lm_top * col.iw[m]) / hgt);
   put(L.pa(m, PA_RDZ), 1 / fabs(col.z[m] - col.z[m - 1]));
   for (int i = m - 1; i >= 1; --i) {
     const double zt = col.z[i + 1] - col.z[i], zi = col.z[i + 1] + 0.5 * zt;
     const double z0 = (i > 1) ? col.z[i - 1] : 0;
     put(L.pa(i, PA_A0I), col.a0i[i]); put(L.pa(i, PA_A0O), col.a0o[i]); put(L.pa(i, PA_EX1), col.ex1[i]); put(L.pa(i, PA_EX2), col.ex2[i]);
-    put(L.pa(i, PA_GLO), col.gl_o[i]); put(L.pa(i, PA_GLI), col.gl_i[i]); put(L.pa(i, PA_EDO), col.ed_o[i]); put(L.pa(i, PA_EDI), col.ed_i[i]);
+    put(L.pa(i, PA_GLO), MC_LOGWIND ? log(col.gl_o[i]) : col.gl_o[i]); put(L.pa(i, PA_GLI), MC_LOGWIND ? log(col.gl_i[i]) : col.gl_i[i]); put(L.pa(i, PA_EDO), col.ed_o[i]); put(L.pa(i, PA_EDI), col.ed_i[i]);
     put(L.pa(i, PA_GX0), col.gx0[i]); put(L.pa(i, PA_GX1), col.gx1[i]); put(L.pa(i, PA_CG), (col.lmi[i] * col.iw[i]) / zi);
     put(L.pa(i, PA_RDZ), 1 / fabs(col.z[i] - z0));
   }
@@ -542,6 +564,24 @@ MC_HD double gha_fast(double d, double id, double d3, double u, double Tk, doubl
   return 1.41 * ((gforced > gfree) ? gforced : gfree);
 }
 
+// The same conductance with what the forced and the free branch share taken out of the maximum.  With Dh = 18.9e-6 sc, nu = 13.3e-6 sc:
+//   gforced = Cf (ph / d) sqrt(sc) sqrt(u d),  gfree = Cr (ph / d) sqrt(sc) (9.81 d^3 |dT| / Tk)^(1/4)
+//   => 1.41 max(gforced, gfree) = (1.41 / d) ph sqrt(sc max(Cf^2 d u, sqrt(Cr^4 9.81 d^3 |dT| / Tk)))
+// with Cf = 0.664 * 18.9e-6 * Pr^(1/3) / sqrt(13.3e-6), Cr = 0.54 * 18.9e-6 * Pr^(1/4) / sqrt(13.3e-6).  kA = Cf^2 d, kB = Cr^4 9.81 d^3 and
+// kI = 1.41 / d are column constants (fast_park_constants).  Four square roots on two independent chains and no reciprocal, instead of
+// five and one in a row.  A negative or NaN wind speed loses the comparison as the NaN of sqrt(Re) did.
+constexpr double kGhaCf2 = 9.3684559114155109e-06, kGhaCr4 = 4.3162720585010526e-11;
+MC_HD double gha_fast2(double kA, double kB, double kI, double u, double Tk, double iTk, double ph, double dtc, double c101) {
+  const double x = Tk * (1 / 273.15);
+  const double r = fsqrt_nz(x);
+  const double sc = (x * r) * (fsqrt_nz(r) * c101);               // (Tk / 273.15)^1.75 * 101.3 / pk
+  double adt = fabs(dtc);
+  if (adt < 1.0) adt = 1.0;
+  const double A = u * kA, B = fsqrt_nz((kB * adt) * iTk);
+  const double M = (A > B) ? A : B;
+  return (kI * ph) * fsqrt_nz(sc * M);
+}
+
 // Scratch map of the solves (indices into Mem::scr_*; the C stages later overwrite rows 0, 1, 27, 28 only):
 //   heat   : K(i) at SK0+i (i = 1..17), CD(i) at SCD0+i (1..16), TC(i) at STC0+i (1..18; holds the solution afterwards)
 //   vapour : K, CD, TC in the (then dead) heat K/CD rows;  node arrays for sweep C: T2, Yt, Ye (1..8 each)
@@ -636,8 +676,13 @@ MC_HD void fast_park_constants(Mem& mem) {
   auto p0 = [=](int r) { return P[(long long)r * kTile]; };
   const double lwd = p0(P0_LWD);
   mem.park(KR_CLUMP, p0(P0_CLUMP));
-  mem.park(KG_EMV, p0(P0_EMV)); mem.park(KG_GSMAX, p0(P0_GSMAX)); mem.park(KG_Q50, p0(P0_Q50)); mem.park(KG_LWD, lwd); mem.park(KG_ILWD, 1 / lwd);
+  mem.park(KG_EMV, p0(P0_EMV)); mem.park(KG_GSMAX, p0(P0_GSMAX)); mem.park(KG_Q50, p0(P0_Q50));
+#if MC_GHA2
+  mem.park(KG_LWD, kGhaCf2 * lwd); mem.park(KG_ILWD, 1.41 / lwd); mem.park(KG_LWD3, kGhaCr4 * (9.81 * (lwd * lwd * lwd)));   // kA, kI, kB of gha_fast2
+#else
+  mem.park(KG_LWD, lwd); mem.park(KG_ILWD, 1 / lwd);
   mem.park(KG_LWD3, 9.81 * (lwd * lwd * lwd));
+#endif
   mem.park(KU_VSB, p0(P0_VEGEM) * kSb); mem.park(KU_REFG, p0(P0_REFG));
   mem.park_done();
 }
@@ -667,6 +712,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   bool fastok = run;
   // ======================= phase 0: scalars of the step (code.R:700-745) =======================
   double uh, sqphi, iphi, ugr, cpk, ps1a, tcu;
+  double lu = 0, lugr = 0;                            // MC_LOGWIND: log(uh), log(ugr)
   const bool edge = cfg.edgedist == cfg.edgedist;
   {
     const double tairn = fc.tair, pkn = fc.pk;
@@ -734,6 +780,9 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       uh = fdiv(ufw, 0.4) * ln2;
     }
     ps1a = ps1; tcu = tcm;
+#if MC_LOGWIND
+    lu = flog(uh); lugr = flog(ugr);                   // (uh >= 0.5 * ... > 0; ugr = 0 in a calm hour gives -Inf, which loses every maximum)
+#endif
     mem.park(X_TAIRN, tairn); mem.park(X_PKN, pkn); mem.park(X_SKYEM, fc.skyem); mem.park(X_RSW, fc.Rsw); mem.park(X_RELHUMN, relhumn);
     mem.park(X_TCAN, tcan); mem.park(X_TAIRP, s0(S0_TAIR)); mem.park(X_RELHUMP, s0(S0_RELHUM));
     mem.park(X_PPK, ppk); mem.park(X_PS1, ps1); mem.park(X_TET_TAIR, tet_tair); mem.park(X_TET_TCAN, tet_tcan); mem.park(X_TFROST, tfrost);
@@ -752,14 +801,38 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double tcl = (i > 1) ? mem.a_tcl() : ps1a;
       const double ai = mem.a_p(PA_A0I) * sqphi;
       double uzn;
+      const double ph = phair_c(cpk, (tcu + tcl) / 2);
+#if MC_LOGWIND
+      // windcanopy (code.R:279-294) on logarithms: log(uh exp(a ex)) = lu + a ex, log(ur exp(a ed)) = log(ugr) + log(gl) + a ed; the same
+      // NaN-aware maximum; only the wind speed that is stored is exponentiated.  gcanopy's uh / (e0 - e1) takes lu into the exponents.
+      auto wcl = [&](double l, double a, double ex, double lgl, double ed) {
+        double t = fma(a, ex, l);
+        if (edge) {
+          const double r = fma(a, ed, lugr + lgl);
+          if (t != t) t = r;
+          else if (r == r && r > t) t = r;
+        }
+        return t;
+      };
+      double lz;
+      if (i == m) lz = wcl(lu, ai, mem.a_p(PA_EX1), mem.a_p(PA_GLO), mem.a_p(PA_EDO));
+      else {
+        lu = wcl(lu, ai, mem.a_p(PA_EX1), mem.a_p(PA_GLO), mem.a_p(PA_EDO));
+        lz = wcl(lu, mem.a_p(PA_A0O) * sqphi, mem.a_p(PA_EX2), mem.a_p(PA_GLI), mem.a_p(PA_EDI));                           // Q9
+      }
+      uzn = fexp_neg(lz);                               // (clamped below only: lz <= log of the wind above the canopy)
+      const double nlu = (lu < -600.0) ? 600.0 : -lu;   // (without the edge term the product can underflow; the exponents stay finite)
+      const double e0 = fexp_b(fma(-ai, mem.a_p(PA_GX0), nlu)), e1 = fexp_b(fma(-ai, mem.a_p(PA_GX1), nlu));      // (gx in [-1, 0])
+      const double g = fdiv(mem.a_p(PA_CG) * ph * ai, e0 - e1) * iphi;
+#else
       if (i == m) uzn = wc_fast(uh, ai, mem.a_p(PA_EX1), mem.a_p(PA_GLO), mem.a_p(PA_EDO), ugr, edge);
       else {
         uh = wc_fast(uh, ai, mem.a_p(PA_EX1), mem.a_p(PA_GLO), mem.a_p(PA_EDO), ugr, edge);
         uzn = wc_fast(uh, mem.a_p(PA_A0O) * sqphi, mem.a_p(PA_EX2), mem.a_p(PA_GLI), mem.a_p(PA_EDI), ugr, edge);      // Q9
       }
-      const double ph = phair_c(cpk, (tcu + tcl) / 2);
       const double e0 = fexp_b(-ai * mem.a_p(PA_GX0)), e1 = fexp_b(-ai * mem.a_p(PA_GX1));      // (gx in [-1, 0])
       const double g = fdiv(mem.a_p(PA_CG) * ph * uh * ai, e0 - e1) * iphi;
+#endif
       const double gfree = 0.0012 * ph * qroot(fabs(tcu - tcl) * mem.a_p(PA_RDZ));
       const double gtn = (g > gfree) ? g : gfree;
       const double rn = frcp(gtn);
@@ -773,6 +846,9 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       tcu = tcl;
     }
     // canopy top <-> reference (code.R:769), Q8: leftover uh, lowest air node
+#if MC_LOGWIND
+    uh = fexp_neg(lu);
+#endif
     const double tcan = mem.unpark(X_TCAN), tc1 = mem.unpark(X_TC1);
     mem.g1_wait();                                     // the G1 rows were fetched behind the sweep
     const double a = mem.g1a(P0_A0CAP) * sqphi;
@@ -822,6 +898,9 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     const double eamn = fdiv(relhumn, 100) * tet_tcan;
     mem.park(KT_EREF, eref); mem.park(KT_ESOIL, esoil); mem.park(KT_MTREF, mtref); mem.park(KT_PS1, ps1); mem.park(KT_RGCAP, mem.unpark(X_RGCAP));
     mem.park(KT_CPPK, (44.6 * fdiv(ppk, 101.3)) * 273.15);
+#if MC_MQ
+    mem.park(KT_TSEL, fdiv(101.3 / (44.6 * 273.15), ppk));            // 1 / (cpk 273.15) of the previous pressure (the slot is free until the solve parks tsel)
+#endif
     mem.park(KU_LAMBDA, fdiv((-42.575 * tcan + 44994) * surfwet, mpk));     // lambda / mpk: the only form sweep B uses
     mem.park(KU_TCAN, tcan); mem.park(KU_EAMN, eamn); mem.park(KU_IPPK, frcp(ppk)); mem.park(KU_PKN, pkn);
     mem.park_done();
@@ -867,8 +946,13 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         Rabsn = aRsw + aRlw;
         const double Qa = 4.6 * rsw;
         gvn = fdiv(kg[KG_GSMAX - KG_EMV] * Qa, Qa + kg[KG_Q50 - KG_EMV]);       // layercond
+#if MC_GHA2
+        ghan = gha_fast2(kg[KG_LWD - KG_EMV], kg[KG_LWD3 - KG_EMV], kg[KG_ILWD - KG_EMV], uzn, Tkc, iTkc, kg[KG_CPK - KG_EMV] * iTkc, ptl - ptc,
+                         kg[KG_C101 - KG_EMV]);
+#else
         ghan = gha_fast(kg[KG_LWD - KG_EMV], kg[KG_ILWD - KG_EMV], kg[KG_LWD3 - KG_EMV], uzn, Tkc, iTkc, kg[KG_CPK - KG_EMV] * iTkc, ptl - ptc,
                         kg[KG_C101 - KG_EMV]);
+#endif
       }
       double kt[8];
       mem.unpark8(KT_EREF, kt);
@@ -890,7 +974,11 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double delta = (4098 * tetl) * (r237l * r237l);                      // code.R:415
       const double gvo = mem.b_s(SL_GV), ghao = mem.b_s(SL_GHA);
       // 1/(1/a + 1/b) = a*b/(a+b): one division; a = 0 (closed stomata at night) still gives 0
+#if MC_GVC
+      const double gvp = gvo;                                                    // the working row holds the previous step's gvc (fast_run_column converts previn$gv)
+#else
       const double gvp = fdiv(gvo * ghao, gvo + ghao);
+#endif
       const double gvc = fdiv(gvn * ghan, gvn + ghan);
       const double gvm = 0.5 * gvp + 0.5 * gvc;
       const double gham = 0.5 * ghan + 0.5 * ghao;
@@ -919,8 +1007,14 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         aL = (gtt * mtref + gtt2 * ps1 + gham * ptl) * iden;
         bL = (0.5 * gham) * iden;
       } else {
+#if MC_MQ
+        // ma K_i = (mac / (cp ph)) (g_i cp) = mac g_i / ph and 1 / ph = Tk / (cpk 273.15): no division, cp cancels
+        const double ma = mem.b_p(PB_MAC) * (Tkc * kt[KT_TSEL - KT_EREF]);
+        const double K1 = g1, K2 = g2, K3 = g3h * PAIm;
+#else
         const double ma = fdiv(mem.b_p(PB_MAC), cp * phc);
         const double K1 = g1 * cp, K2 = g2 * cp, K3 = g3h * cp * PAIm;
+#endif
         const double ibtm = frcp(1 + 0.5 * ma * (K1 + K2 + K3));
         aL = (ptc + 0.5 * ma * (K1 * mtref + K2 * ps1 + K3 * ptl)) * ibtm;
         bL = (0.25 * ma * K3) * ibtm;
@@ -1013,7 +1107,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       }
       if (runB) {
         double* Sl = S + (long long)L.sl(i, 0) * kTile;
-        mem.st_stream(Sl + SL_TLEAF * kTile, tleafn); mem.st_stream(Sl + SL_RABS * kTile, Rabsn); mem.st_stream(Sl + SL_GV * kTile, gvn);
+        mem.st_stream(Sl + SL_TLEAF * kTile, tleafn); mem.st_stream(Sl + SL_RABS * kTile, Rabsn); mem.st_stream(Sl + SL_GV * kTile, MC_GVC ? gvc : gvn);
         mem.st_stream(Sl + SL_GHA * kTile, ghan);
         // previn$uz is only read at the lowest and highest node (code.R:731), so the other rows are written when the state is
         // harvested (emit) and not on every step
@@ -1024,6 +1118,9 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       // (the EAL row carries log(ean / 0.6108), which this sweep has anyway: sweep C needs ean only inside dewpoint()'s logarithm)
       mem.st_keep(W + (long long)L.wl(i, WL_TT) * kTile, TT); mem.st_keep(W + (long long)L.wl(i, WL_EAL) * kTile, al);
       if (emit || i == selHb) { wput(i, WL_L, Lp); wput(i, WL_RSWIN, rsw); }
+#if MC_GVC
+      if (emit) wput(i, WL_GVN, gvn);
+#endif
       Lt += Lp; stl += tleafn; ssw += rsw;
     }
     if (open) {                                     // trailing group joins the last closed one
@@ -1316,7 +1413,7 @@ MC_HD void abi_state_from_ws(const FastLayout& L, const double* __restrict__ P, 
   r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, P[(long long)L.pz(i) * kTile]);
   r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, g(L.sl(i, SL_RH)));
   r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, g(L.sl(i, SL_RABS)));
-  r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, g(L.sl(i, SL_GV)));
+  r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, MC_GVC ? W[(long long)L.wl(i, WL_GVN) * kTile] : g(L.sl(i, SL_GV)));
   r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, g(L.sl(i, SL_GHA)));
   r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, W[(long long)L.wl(i, WL_L) * kTile]);
   r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, W[(long long)L.wl(i, WL_RSWIN) * kTile]);
@@ -1400,7 +1497,9 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
       const double tci = lin2(tsoil_, tair_, sm + i, m + sm), Ra = lin2(0.2 * Rsw_ + 20, Rsw_ + 20, i, m);
       tcs += tci;
       sput(L.sl(i, SL_TC), tci); sput(L.sl(i, SL_TLEAF), tci + 0.01 * Ra); sput(L.sl(i, SL_RH), relhum_); sput(L.sl(i, SL_RABS), Ra);
-      sput(L.sl(i, SL_GV), lin2(0.25, 0.32, i, m)); sput(L.sl(i, SL_GHA), lin2(0.13, 0.19, i, m)); sput(L.uz(i), ((double)i / m) * u_);
+      { const double gv = lin2(0.25, 0.32, i, m), gha = lin2(0.13, 0.19, i, m);
+        sput(L.sl(i, SL_GV), MC_GVC ? fdiv(gv * gha, gv + gha) : gv); sput(L.sl(i, SL_GHA), gha); }
+      sput(L.uz(i), ((double)i / m) * u_);
       sput(L.gt(i), i == 1 ? 2 * g0 : g0);
     }
     const double gcap = g0 * (hgt / m) * 0.5;
@@ -1420,7 +1519,8 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
       tcs += tci;
       sput(L.sl(i, SL_TC), tci); sput(L.sl(i, SL_TLEAF), st(P_NSCAL + m + i - 1)); sput(L.uz(i), st(P_NSCAL + 2 * m + i - 1));
       sput(L.sl(i, SL_RH), st(P_NSCAL + 4 * m + i - 1)); sput(L.sl(i, SL_RABS), st(P_NSCAL + 5 * m + i - 1));
-      sput(L.sl(i, SL_GV), st(P_NSCAL + 6 * m + i - 1)); sput(L.sl(i, SL_GHA), st(P_NSCAL + 7 * m + i - 1));
+      { const double gv = st(P_NSCAL + 6 * m + i - 1), gha = st(P_NSCAL + 7 * m + i - 1);      // (the same quotient the step forms: restarts stay bit-identical)
+        sput(L.sl(i, SL_GV), MC_GVC ? fdiv(gv * gha, gv + gha) : gv); sput(L.sl(i, SL_GHA), gha); }
       sput(L.gt(i), st(P_NSCAL + 11 * m + i - 1));
       W[(long long)L.wl(i, WL_L) * kTile] = st(P_NSCAL + 8 * m + i - 1); W[(long long)L.wl(i, WL_RSWIN) * kTile] = st(P_NSCAL + 9 * m + i - 1);
       W[(long long)L.wl(i, WL_RLWIN) * kTile] = st(P_NSCAL + 10 * m + i - 1);

@@ -270,6 +270,20 @@ MC_HD double fsqrt(double x) {
   return sqrt(x);
 #endif
 }
+// fsqrt for operands that are never zero (a product of strictly positive factors): without the x == 0 patch (a compare and a select pair).
+// NaN and negative operands still give NaN; +0 would give NaN instead of 0.
+MC_HD double fsqrt_nz(double x) {
+#if defined(__CUDA_ARCH__) && MC_SQRT_CUBIC && !MC_SQRT_HERON
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double t = x * y;
+  const double e = fma(-t, y, 1.0);
+  const double q = e * fma(0.375, e, 0.5);
+  return fma(t, q, t);
+#else
+  return fsqrt(x);
+#endif
+}
 MC_HD double qroot(double x) { return fsqrt(fsqrt(x)); }           // x^0.25
 MC_HD double pow175(double x) { double r = fsqrt(x); return x * r * fsqrt(r); }   // x^1.75
 

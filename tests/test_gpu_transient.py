@@ -133,7 +133,10 @@ def test_other_layer_counts_on_the_gpu(oracle, m, sm):
     veg, so = S.ensemble(S.vegp_deciduous(m=m), soil, ncol, m, sm, seed=3)
     f, ts = S.forcing_from_climdata(S.load_weather()); f = np.ascontiguousarray(f[4000:4000 + T])
     lat = np.full(ncol, 50.0); lon = np.full(ncol, -5.0)
-    cfg = make_cfg(spin_steps=60)
+    # 30 spin-up steps: with m = 20 / sm = 7 two of these columns sit in the frozen-forcing oscillation of DESIGN.md section 2, where
+    # rounding-level differences between ANY two evaluation orders grow ~20 x per 20 spin-up steps (host build of the same source vs
+    # the oracle: 1e-11 -> 1e-10 -> 4e-9 -> 2e-6 relative in G after 20 / 40 / 60 / 100 steps); 60 steps left no margin to 1e-8
+    cfg = make_cfg(spin_steps=30)
     want = oracle.run_transient(veg, so, f, lat, lon, cfg, m, sm, samp_idx=np.arange(ncol))
     ctx = Context(m, sm)
     ctx.set_columns(veg, so, lat, lon); ctx.set_forcing(f, None, None); ctx.set_config(cfg)
