@@ -29,27 +29,16 @@
 namespace mc {
 
 constexpr int kTile = 128;   // columns per CTA == columns per workspace tile
-// Algebraic forms of round 2's last step (each removes transcendental work from the per-layer chains; 0 restores the earlier form):
-//   MC_LOGWIND  sweep A carries log(uh): windcanopy's two products uh * exp(a ex), ur * exp(a ed) and their maximum become two sums and
-//               a maximum, the gcanopy quotient uh / (e0 - e1) becomes 1 / (exp(-a gx0 - lu) - exp(-a gx1 - lu)): 3 exponentials per
-//               layer instead of 6 (the gl rows hold log(gl));
-//   MC_GHA2     leaf boundary-layer conductance with the common factor ph / d * sqrt(sc) of the forced and free branches taken out
-//               of the maximum: 4 square roots and no reciprocal instead of 5 and one;
-//   MC_GVC      the working state keeps the series conductance gv gha / (gv + gha) of the previous step (all that leaftemp reads of
-//               previn$gv) instead of gv; gv itself is written with the harvest rows when the state is emitted;
-//   MC_MQ       leaftemp's transient air balance with cp cancelled (ma * K_i = mac * g_i / ph, 1 / ph = Tk / (cpk 273.15)): one division less.
-#ifndef MC_LOGWIND
-#define MC_LOGWIND 1
-#endif
-#ifndef MC_GHA2
-#define MC_GHA2 1
-#endif
-#ifndef MC_GVC
-#define MC_GVC 1
-#endif
-#ifndef MC_MQ
-#define MC_MQ 1
-#endif
+// Algebraic forms that keep transcendental work off the per-layer chains (each changes results at rounding level only):
+//   * sweep A carries log(uh): windcanopy's two products uh * exp(a ex), ur * exp(a ed) and their maximum become two sums and a maximum,
+//     the gcanopy quotient uh / (e0 - e1) becomes 1 / (exp(-a gx0 - lu) - exp(-a gx1 - lu)): 3 exponentials per layer instead of 6 (the gl
+//     rows hold log(gl));
+//   * leaf boundary-layer conductance with the common factor (ph / d) sqrt(sc) of the forced and free branches taken out of the maximum
+//     (gha_fast2): 4 square roots and no reciprocal instead of 5 and one;
+//   * the working state keeps the series conductance gv gha / (gv + gha) of the previous step (all that leaftemp reads of previn$gv)
+//     instead of gv; gv itself is written with the harvest rows when the state is emitted;
+//   * leaftemp's transient air balance with cp cancelled (ma K_i = mac g_i / ph): one division less.
+// Same-box A/B of the four together: 589-594 -> 613-614 M column-steps/s.
 #if !defined(__CUDACC__)
 static long long g_mc_general_steps = 0;     // host (test) build: columns that left the streaming form (launch-level count)
 #endif
@@ -71,17 +60,38 @@ enum { P0_FS0, P0_FO0 = P0_FS0 + 8,
        P0_SELG, P0_SELH, P0_SELS, P0_ZABOVE, P0_FAST, P0_CPW, P0_PHW, P0_ZDIFF, P0_NFIX };          // then 1/DZK[sm], DZC[sm], Z[m]
 constexpr int kG0Rows = P0_G0END, kG1aRows = P0_G1AEND - P0_G0END, kG1bRows = P0_G1BEND - P0_G1AEND;
 constexpr int kGRow0 = 15;                        // G1a / G1b land in rows 15.. of a stage buffer (sweep-A stages use rows 0..13)
-enum { PA_A0I, PA_A0O, PA_EX1, PA_EX2, PA_GLO, PA_GLI, PA_EDO, PA_EDI, PA_GX0, PA_GX1, PA_CG, PA_RDZ, PA_N };
-enum { PB_REF, PB_PC, PB_SPC, PB_SGC, PB_TRDC, PB_TRDG, PB_TRLW, PB_PAI, PB_IZTH, PB_IZL, PB_IZRF, PB_IZP, PB_MAC, PB_MZ,
-       PB_VDEN, PB_DZ, PB_N };
+// Per-layer rows.  The first PA_NREG / PB_NREG of a block are staged in every launch.  The next ones are pure functions of the node grid
+// z: on the REGULAR grid z[i] = (i - 0.5) hgt / m that paraminit builds (code.R:573) and runonestep keeps whenever reqhgt is NA (code.R:719
+// replaces one node otherwise) they depend on the column through hgt alone, and a launch whose columns all have that grid (template
+// parameter REG of the kernel) forms them from m / hgt and small-integer reciprocals instead of streaming them: 5 + 4 rows of 8 bytes per
+// layer and step less, 1.44 of the 8.4 KB the kernel moves per column-step.  PB_MAC (read only in leaftemp's transient air balance, which
+// hourly steps practically never take) and PB_CVD (the cumulative sum of dz * vden, read at the merged-layer group boundaries by the solve)
+// are never staged: direct reads where needed.
+enum { PA_A0I, PA_A0O, PA_GLO, PA_GLI, PA_EDO, PA_EDI, PA_CG, PA_NREG, PA_EX1 = PA_NREG, PA_EX2, PA_GX0, PA_GX1, PA_RDZ, PA_N };
+enum { PB_REF, PB_PC, PB_SPC, PB_SGC, PB_TRDC, PB_TRDG, PB_TRLW, PB_PAI, PB_IZL, PB_MZ, PB_NREG, PB_IZTH = PB_NREG, PB_IZP, PB_IZRF, PB_DZ,
+       PB_NSTG, PB_MAC = PB_NSTG, PB_CVD, PB_VDEN, PB_N };
+// 1 / k for the small integers the regular grid needs (k <= 2 m - 1, m <= 20 in the streaming form)
+#if defined(__CUDACC__)
+__constant__ double c_rinv[40] = {0.0,     1.0 / 1,  1.0 / 2,  1.0 / 3,  1.0 / 4,  1.0 / 5,  1.0 / 6,  1.0 / 7,  1.0 / 8,  1.0 / 9,
+                                  1.0 / 10, 1.0 / 11, 1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19,
+                                  1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29,
+                                  1.0 / 30, 1.0 / 31, 1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37, 1.0 / 38, 1.0 / 39};
+#endif
+MC_HD double rinv_small(int k) {
+#if defined(__CUDA_ARCH__)
+  return c_rinv[k];
+#else
+  return 1.0 / (double)k;
+#endif
+}
 enum { S0_TABOVE, S0_RELHUM, S0_TAIR, S0_TSOIL, S0_PK, S0_H, S0_PSIM, S0_G, S0_TCSUM, S0_GTCAP, S0_N };   // then soiltc[sm]
 enum { SL_TC, SL_TLEAF, SL_RH, SL_RABS, SL_GV, SL_GHA, SL_N };
-enum { WL_GTN, WL_UZN, WL_TT, WL_EAL, WL_L, WL_RSWIN, WL_RLWIN, WL_GVN, WL_N };   // GVN: previn$gv, written with the harvest rows (MC_GVC)
+enum { WL_GTN, WL_UZN, WL_TT, WL_EAL, WL_L, WL_RSWIN, WL_RLWIN, WL_GVN, WL_N };   // GVN: previn$gv, written with the harvest rows
 constexpr int kWLiveB = 2;                        // W rows sweep B reads back from sweep A (GTN, UZN)
 constexpr int kWLiveC = 2;                        // W rows sweep C reads back from sweep B (TT, EAL)
 constexpr int kCL = 5;                            // layers per sweep-C stage (their TT/EAL rows are contiguous: 10 rows)
 static_assert(WL_GTN == 0 && WL_UZN == 1, "sweep B stages the first kWLiveB rows of a layer's block");
-constexpr int kStageRowsB = PB_N + SL_N + kWLiveB + 1;   // sweep-B stage: geometry, state, work rows and the old gt row = 25 rows
+constexpr int kStageRowsB = PB_NSTG + SL_N + kWLiveB + 1;   // sweep-B stage: geometry, state, work rows and the old gt row = 23 rows (19 on the regular grid)
 constexpr int kStageRows = 27;                    // rows of 128 doubles per stage buffer (the solver scratch needs 2 x 27)
 static_assert(kStageRowsB <= kStageRows, "sweep-B stage exceeds the stage buffer");
 static_assert(kG0Rows <= kStageRows && kGRow0 + kG1aRows <= kStageRows && kGRow0 + kG1bRows <= kStageRows && PA_N + 2 <= kGRow0, "scalar groups do not fit the idle stage rows");
@@ -202,18 +212,19 @@ MC_HD void geom_column(const FastArgs& a, const RunCfg& cfg, long long c, long l
   put(P0_FAST, fast ? 1.0 : 0.0);
   // sweep A rows: layer m (canopy top, code.R:749-753) then the recurrence layers (code.R:756-767)
   put(L.pa(m, PA_A0I), col.a0_top); put(L.pa(m, PA_A0O), col.a0_top); put(L.pa(m, PA_EX1), col.ex_top); put(L.pa(m, PA_EX2), col.ex_top);
-  put(L.pa(m, PA_GLO), MC_LOGWIND ? log(col.gl_top) : col.gl_top); put(L.pa(m, PA_GLI), MC_LOGWIND ? log(col.gl_top) : col.gl_top); put(L.pa(m, PA_EDO), col.ed_top); put(L.pa(m, PA_EDI), col.ed_top);
+  put(L.pa(m, PA_GLO), log(col.gl_top)); put(L.pa(m, PA_GLI), log(col.gl_top)); put(L.pa(m, PA_EDO), col.ed_top); put(L.pa(m, PA_EDI), col.ed_top);
   put(L.pa(m, PA_GX0), col.gx0_top); put(L.pa(m, PA_GX1), col.gx1_top); put(L.pa(m, PA_CG), (col.lm_top * col.iw[m]) / hgt);
   put(L.pa(m, PA_RDZ), 1 / fabs(col.z[m] - col.z[m - 1]));
   for (int i = m - 1; i >= 1; --i) {
     const double zt = col.z[i + 1] - col.z[i], zi = col.z[i + 1] + 0.5 * zt;
     const double z0 = (i > 1) ? col.z[i - 1] : 0;
     put(L.pa(i, PA_A0I), col.a0i[i]); put(L.pa(i, PA_A0O), col.a0o[i]); put(L.pa(i, PA_EX1), col.ex1[i]); put(L.pa(i, PA_EX2), col.ex2[i]);
-    put(L.pa(i, PA_GLO), MC_LOGWIND ? log(col.gl_o[i]) : col.gl_o[i]); put(L.pa(i, PA_GLI), MC_LOGWIND ? log(col.gl_i[i]) : col.gl_i[i]); put(L.pa(i, PA_EDO), col.ed_o[i]); put(L.pa(i, PA_EDI), col.ed_i[i]);
+    put(L.pa(i, PA_GLO), log(col.gl_o[i])); put(L.pa(i, PA_GLI), log(col.gl_i[i])); put(L.pa(i, PA_EDO), col.ed_o[i]); put(L.pa(i, PA_EDI), col.ed_i[i]);
     put(L.pa(i, PA_GX0), col.gx0[i]); put(L.pa(i, PA_GX1), col.gx1[i]); put(L.pa(i, PA_CG), (col.lmi[i] * col.iw[i]) / zi);
     put(L.pa(i, PA_RDZ), 1 / fabs(col.z[i] - z0));
   }
   // sweep B rows: leafabs (code.R:31-49) and leaftemp (code.R:378-512) constants of the layer
+  double cvd = 0;
   for (int i = 1; i <= m; ++i) {
     const double ref = col.pLAI[i] * col.refls + (1 - col.pLAI[i]) * col.refw;
     const double pc = col.PAIg[m + 1 - i];
@@ -223,8 +234,10 @@ MC_HD void geom_column(const FastArgs& a, const RunCfg& cfg, long long c, long l
     put(L.pb(i, PB_TRDC), col.trdc[i]); put(L.pb(i, PB_TRDG), col.trdg[i]); put(L.pb(i, PB_TRLW), col.trlw[i]); put(L.pb(i, PB_PAI), col.PAI[i]);
     put(L.pb(i, PB_IZTH), lg.izth); put(L.pb(i, PB_IZL), lg.izl); put(L.pb(i, PB_IZRF), lg.izrf);
     put(L.pb(i, PB_IZP), lg.izp); put(L.pb(i, PB_MAC), lg.mac);
-    put(L.pb(i, PB_MZ), lg.mz); put(L.pb(i, PB_VDEN), vden);
-    put(L.pb(i, PB_DZ), col.z[i] - (i > 1 ? col.z[i - 1] : 0.0));
+    put(L.pb(i, PB_MZ), lg.mz);
+    const double dzi = col.z[i] - (i > 1 ? col.z[i - 1] : 0.0);
+    cvd += dzi * vden;                                                 // sum over the layers up to i of dz * vden (layeraverage's vden sum of a group = a difference of two)
+    put(L.pb(i, PB_DZ), dzi); put(L.pb(i, PB_CVD), cvd); put(L.pb(i, PB_VDEN), vden);
   }
 }
 
@@ -270,6 +283,8 @@ struct DirectMem {
   MC_HD double b_s(int r) const { return S[(long long)L.sl(ib, r) * kTile]; }
   MC_HD double b_w(int r) const { return W[(long long)L.wl(ib, r) * kTile]; }
   MC_HD double b_gto() const { return S[(long long)L.gt(ib) * kTile]; }                     // read before the layer stores its new gt
+  MC_HD double p_mac(int i) const { return P[(long long)L.pb(i, PB_MAC) * kTile]; }
+  MC_HD double p_cvd(int i) const { return P[(long long)L.pb(i, PB_CVD) * kTile]; }
 };
 
 // make BOUNDS=1: every computed index into the stage buffers, the tensor-memory scratch and the tile workspaces is range-checked on the
@@ -335,10 +350,15 @@ MC_D double ld_hint(const double* p, unsigned long long pol) {
 }
 MC_D void discard_line(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
 
-struct PipeMem {
+template <bool REG>
+struct PipeMemT {
+  static constexpr int PAS = REG ? PA_NREG : PA_N, PBS = REG ? PB_NREG : PB_NSTG;   // geometry rows of a sweep-A / sweep-B stage
   const double* P; double* S; double* W;      // lane-adjusted tile bases (for stores and the few direct reads)
   const double* Pt; const double* St; const double* Wt;   // tile bases (lane 0), for the bulk copies
   const double* Pl;                            // tile whose per-layer geometry rows this tile reads (Pt, or its class's first tile)
+  const double* Pll;                           // Pl + lane, for the two rows that are read directly
+  MC_D double p_mac(int i) const { return Pll[(long long)L.pb(i, PB_MAC) * kTile]; }
+  MC_D double p_cvd(int i) const { return Pll[(long long)L.pb(i, PB_CVD) * kTile]; }
   FastLayout L;
   double* buf;                                 // [2][kStageRows][kTile] in shared memory
   unsigned long long* bar;                     // [2]
@@ -443,24 +463,24 @@ struct PipeMem {
   MC_D void issueA(int i, unsigned kk) {
     const unsigned b = buf32 + (kk & 1) * (kStageRows * kTile * 8);
     const unsigned mb = bar32 + (kk & 1) * 8;
-    const unsigned bytes = (PA_N + (i > 1 ? 1 : 0) + 1) * kTile * 8;
+    const unsigned bytes = (PAS + (i > 1 ? 1 : 0) + 1) * kTile * 8;
     mbar_expect_tx(mb, bytes);
-    bulk_g2s_stream(b, Pl + (long long)L.pa(i, 0) * kTile, PA_N * kTile * 8, mb, Pl == Pt ? pol : pol_keep);
-    if (i > 1) bulk_g2s_stream(b + PA_N * kTile * 8, St + (long long)L.sl(i - 1, SL_TC) * kTile, kTile * 8, mb, pol);
-    bulk_g2s_stream(b + (PA_N + 1) * kTile * 8, St + (long long)L.gt(i) * kTile, kTile * 8, mb, pol);
+    bulk_g2s_stream(b, Pl + (long long)L.pa(i, 0) * kTile, PAS * kTile * 8, mb, Pl == Pt ? pol : pol_keep);
+    if (i > 1) bulk_g2s_stream(b + PAS * kTile * 8, St + (long long)L.sl(i - 1, SL_TC) * kTile, kTile * 8, mb, pol);
+    bulk_g2s_stream(b + (PAS + 1) * kTile * 8, St + (long long)L.gt(i) * kTile, kTile * 8, mb, pol);
   }
   MC_D void issueB(int i, unsigned kk) {
     const unsigned b = buf32 + (kk & 1) * (kStageRows * kTile * 8);
     const unsigned mb = bar32 + (kk & 1) * 8;
-    mbar_expect_tx(mb, kStageRowsB * kTile * 8);
-    bulk_g2s_stream(b, Pl + (long long)L.pb(i, 0) * kTile, PB_N * kTile * 8, mb, Pl == Pt ? pol : pol_keep);
-    bulk_g2s_stream(b + PB_N * kTile * 8, St + (long long)L.sl(i, 0) * kTile, SL_N * kTile * 8, mb, pol);
+    mbar_expect_tx(mb, (PBS + SL_N + kWLiveB + 1) * kTile * 8);
+    bulk_g2s_stream(b, Pl + (long long)L.pb(i, 0) * kTile, PBS * kTile * 8, mb, Pl == Pt ? pol : pol_keep);
+    bulk_g2s_stream(b + PBS * kTile * 8, St + (long long)L.sl(i, 0) * kTile, SL_N * kTile * 8, mb, pol);
 #if MC_L2HINT
-    bulk_g2s_stream(b + (PB_N + SL_N) * kTile * 8, Wt + (long long)L.wl(i, 0) * kTile, kWLiveB * kTile * 8, mb, pol_keep);
+    bulk_g2s_stream(b + (PBS + SL_N) * kTile * 8, Wt + (long long)L.wl(i, 0) * kTile, kWLiveB * kTile * 8, mb, pol_keep);
 #else
-    bulk_g2s(b + (PB_N + SL_N) * kTile * 8, Wt + (long long)L.wl(i, 0) * kTile, kWLiveB * kTile * 8, mb);
+    bulk_g2s(b + (PBS + SL_N) * kTile * 8, Wt + (long long)L.wl(i, 0) * kTile, kWLiveB * kTile * 8, mb);
 #endif
-    bulk_g2s_stream(b + (PB_N + SL_N + kWLiveB) * kTile * 8, St + (long long)L.gt(i) * kTile, kTile * 8, mb, pol);
+    bulk_g2s_stream(b + (PBS + SL_N + kWLiveB) * kTile * 8, St + (long long)L.gt(i) * kTile, kTile * 8, mb, pol);
   }
   MC_D void issueC(int i, unsigned kk) {                  // rows of layers i .. i+kCL-1 (or up to m)
     const unsigned b = buf32 + (kk & 1) * (kStageRows * kTile * 8);
@@ -525,46 +545,20 @@ struct PipeMem {
     cur = buf + (k & 1) * (kStageRows * kTile) + lane;
     ++k;
   }
-  MC_D double a_p(int r) const { MC_CHK(r >= 0 && r < PA_N, "sweep-A stage row", r); return cur[r * kTile]; }
-  MC_D double a_tcl() const { return cur[PA_N * kTile]; }
-  MC_D double a_gto() const { return cur[(PA_N + 1) * kTile]; }
-  MC_D double b_p(int r) const { MC_CHK(r >= 0 && r < PB_N, "sweep-B geometry row", r); return cur[r * kTile]; }
-  MC_D double b_s(int r) const { MC_CHK(r >= 0 && r < SL_N, "sweep-B state row", r); return cur[(PB_N + r) * kTile]; }
-  MC_D double b_w(int r) const { MC_CHK(r >= 0 && r < kWLiveB, "sweep-B work row", r); return cur[(PB_N + SL_N + r) * kTile]; }
-  MC_D double b_gto() const { return cur[(PB_N + SL_N + kWLiveB) * kTile]; }
+  MC_D double a_p(int r) const { MC_CHK(r >= 0 && r < PAS, "sweep-A stage row", r); return cur[r * kTile]; }
+  MC_D double a_tcl() const { return cur[PAS * kTile]; }
+  MC_D double a_gto() const { return cur[(PAS + 1) * kTile]; }
+  MC_D double b_p(int r) const { MC_CHK(r >= 0 && r < PBS, "sweep-B geometry row", r); return cur[r * kTile]; }
+  MC_D double b_s(int r) const { MC_CHK(r >= 0 && r < SL_N, "sweep-B state row", r); return cur[(PBS + r) * kTile]; }
+  MC_D double b_w(int r) const { MC_CHK(r >= 0 && r < kWLiveB, "sweep-B work row", r); return cur[(PBS + SL_N + r) * kTile]; }
+  MC_D double b_gto() const { return cur[(PBS + SL_N + kWLiveB) * kTile]; }
   MC_D double c_w(int r) const { return cur[r * kTile]; }
   MC_D double c_wq(int q, int r) const { return cbase[(q * kWLiveC + r) * kTile]; }
 };
 #endif
 
-// windcanopy (code.R:279-294) with hoisted pieces: uzv = uh * exp(a*ex); edge term ur * exp(a*ed), ur = ugr * gl
-MC_HD double wc_fast(double uh, double a, double ex, double gl, double ed, double ugr, bool edge) {
-  double uzv = uh * fexp_b(a * ex);                 // (a = O(1-30), |ex| <= O(1): bounded; the edge term below is not)
-  if (edge) {
-    double uhr = (ugr * gl) * fexp_neg(a * ed);       // (ed = -edgedist / (uwr * htop) <= 0, unbounded below)
-    if (uzv != uzv) uzv = uhr;
-    else if (uhr == uhr && uhr > uzv) uzv = uhr;
-  }
-  return uzv;
-}
-
-// 1.41 * gforcedfree(d, u, tc, dtc, pk, dtmin = 1) (microctools; mc_phys.cuh gforcedfree) with the reciprocals shared:
-// iTk = 1/(tc+273.15), c101 = 101.3/pk, ph = phair(tc, pk), id = 1/d, d3 = 9.81*d^3.  Pr = nu/Dh = 13.3/18.9 exactly.
-MC_HD double gha_fast(double d, double id, double d3, double u, double Tk, double iTk, double ph, double dtc, double c101) {
-  const double kPr = 0.7037037037037037, kCbrtPr = 0.8894672162406483;
-  const double sc = pow175(Tk * (1 / 273.15)) * c101;
-  const double Dh = 18.9e-6 * sc, nu = 13.3e-6 * sc;
-  const double inu = frcp(nu);
-  double adt = fabs(dtc);
-  if (adt < 1.0) adt = 1.0;
-  const double Re = (u * d) * inu;
-  const double Gr = (d3 * adt) * iTk * (inu * inu);
-  const double gforced = (0.664 * Dh * ph * fsqrt(Re) * kCbrtPr) * id;
-  const double gfree = (0.54 * Dh * ph * qroot(Gr * kPr)) * id;
-  return 1.41 * ((gforced > gfree) ? gforced : gfree);
-}
-
-// The same conductance with what the forced and the free branch share taken out of the maximum.  With Dh = 18.9e-6 sc, nu = 13.3e-6 sc:
+// 1.41 * gforcedfree(d, u, tc, dtc, pk, dtmin = 1) (microctools; mc_phys.cuh gforcedfree), Pr = nu / Dh = 13.3 / 18.9, with what the forced and
+// the free branch share taken out of the maximum.  With Dh = 18.9e-6 sc, nu = 13.3e-6 sc:
 //   gforced = Cf (ph / d) sqrt(sc) sqrt(u d),  gfree = Cr (ph / d) sqrt(sc) (9.81 d^3 |dT| / Tk)^(1/4)
 //   => 1.41 max(gforced, gfree) = (1.41 / d) ph sqrt(sc max(Cf^2 d u, sqrt(Cr^4 9.81 d^3 |dT| / Tk)))
 // with Cf = 0.664 * 18.9e-6 * Pr^(1/3) / sqrt(13.3e-6), Cr = 0.54 * 18.9e-6 * Pr^(1/4) / sqrt(13.3e-6).  kA = Cf^2 d, kB = Cr^4 9.81 d^3 and
@@ -664,7 +658,7 @@ enum { X_TAIRN, X_PKN, X_SKYEM, X_RSW, X_RELHUMN, X_TCAN, X_TAIRP, X_RELHUMP,
        X_XS, X_CP1, X_TT, X_LT, X_STL, X_SSW, X_LAM, X_CV,
        // sweep-B invariants, 8 per group, one LDTM each
        KR_K, KR_MUL, KR_DP, KR_RSW, KR_AG0, KR_CLUMP, KR_SKLW, KR_EMLW,
-       KG_EMV, KG_GSMAX, KG_Q50, KG_LWD, KG_ILWD, KG_LWD3, KG_C101, KG_CPK,
+       KG_IDZ, KG_GSMAX, KG_Q50, KG_LWD, KG_ILWD, KG_LWD3, KG_C101, KG_CPK,
        KT_EREF, KT_ESOIL, KT_MTREF, KT_PS1, KT_RGCAP, KT_TNS1, KT_TSEL, KT_CPPK,
        KU_LAMBDA, KU_IMPK, KU_VSB, KU_TCAN, KU_EAMN, KU_IPPK, KU_PKN, KU_REFG, K_NPARK };
 static_assert(K_NPARK <= 64, "64 doubles of tensor-memory scratch per thread");
@@ -676,13 +670,9 @@ MC_HD void fast_park_constants(Mem& mem) {
   auto p0 = [=](int r) { return P[(long long)r * kTile]; };
   const double lwd = p0(P0_LWD);
   mem.park(KR_CLUMP, p0(P0_CLUMP));
-  mem.park(KG_EMV, p0(P0_EMV)); mem.park(KG_GSMAX, p0(P0_GSMAX)); mem.park(KG_Q50, p0(P0_Q50));
-#if MC_GHA2
+  mem.park(KG_IDZ, (double)mem.L.m / p0(P0_HGT));                  // m / hgt: 1 / dz of the regular grid (used by the REG instantiation only)
+  mem.park(KG_GSMAX, p0(P0_GSMAX)); mem.park(KG_Q50, p0(P0_Q50));
   mem.park(KG_LWD, kGhaCf2 * lwd); mem.park(KG_ILWD, 1.41 / lwd); mem.park(KG_LWD3, kGhaCr4 * (9.81 * (lwd * lwd * lwd)));   // kA, kI, kB of gha_fast2
-#else
-  mem.park(KG_LWD, lwd); mem.park(KG_ILWD, 1 / lwd);
-  mem.park(KG_LWD3, 9.81 * (lwd * lwd * lwd));
-#endif
   mem.park(KU_VSB, p0(P0_VEGEM) * kSb); mem.park(KU_REFG, p0(P0_REFG));
   mem.park_done();
 }
@@ -690,7 +680,7 @@ MC_HD void fast_park_constants(Mem& mem) {
 // One time step of one column in streaming form.  Every lane computes (tensor-memory accesses are warp-collective);
 // `run` false (a column that takes this step through the general path) only suppresses the stores into the state rows.
 // Returns false when the column left the fast envelope (nothing of the state has been modified then).
-template <class Mem, int MS>
+template <class Mem, int MS, bool REG>
 MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunCfg& cfg /* launch-uniform fields only */, double surfwet, bool run, bool emit, bool more /* another step follows in this launch */,
                      double reqhgt, int charmode,
                      double relhum0, double rsw0, double skyem0, StepOut& out) {
@@ -712,7 +702,8 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   bool fastok = run;
   // ======================= phase 0: scalars of the step (code.R:700-745) =======================
   double uh, sqphi, iphi, ugr, cpk, ps1a, tcu;
-  double lu = 0, lugr = 0;                            // MC_LOGWIND: log(uh), log(ugr)
+  double lu = 0, lugr = 0;                            // log(uh), log(ugr): sweep A works on logarithms
+  double idz = 0;                                     // REG: m / hgt
   const bool edge = cfg.edgedist == cfg.edgedist;
   {
     const double tairn = fc.tair, pkn = fc.pk;
@@ -780,9 +771,8 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       uh = fdiv(ufw, 0.4) * ln2;
     }
     ps1a = ps1; tcu = tcm;
-#if MC_LOGWIND
+    if (REG) idz = (double)m * frcp(hgt);              // 1 / dz of the regular grid
     lu = flog(uh); lugr = flog(ugr);                   // (uh >= 0.5 * ... > 0; ugr = 0 in a calm hour gives -Inf, which loses every maximum)
-#endif
     mem.park(X_TAIRN, tairn); mem.park(X_PKN, pkn); mem.park(X_SKYEM, fc.skyem); mem.park(X_RSW, fc.Rsw); mem.park(X_RELHUMN, relhumn);
     mem.park(X_TCAN, tcan); mem.park(X_TAIRP, s0(S0_TAIR)); mem.park(X_RELHUMP, s0(S0_RELHUM));
     mem.park(X_PPK, ppk); mem.park(X_PS1, ps1); mem.park(X_TET_TAIR, tet_tair); mem.park(X_TET_TCAN, tet_tcan); mem.park(X_TFROST, tfrost);
@@ -802,7 +792,6 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double ai = mem.a_p(PA_A0I) * sqphi;
       double uzn;
       const double ph = phair_c(cpk, (tcu + tcl) / 2);
-#if MC_LOGWIND
       // windcanopy (code.R:279-294) on logarithms: log(uh exp(a ex)) = lu + a ex, log(ur exp(a ed)) = log(ugr) + log(gl) + a ed; the same
       // NaN-aware maximum; only the wind speed that is stored is exponentiated.  gcanopy's uh / (e0 - e1) takes lu into the exponents.
       auto wcl = [&](double l, double a, double ex, double lgl, double ed) {
@@ -814,26 +803,27 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         }
         return t;
       };
+      // the rows that depend on the node grid alone: on the regular grid zi = (i + 1) dz, zo = i dz, z[i] = (i - 0.5) dz, z0 = (i - 1.5) dz
+      // (0 under the lowest node), so ex1 = zo / zi - 1 = -1 / (i + 1), ex2 = zi / zo - 1 = 1 / i, gx0 = z0 / zi - 1, gx1 = z[i] / zi - 1;
+      // the top layer refers to hgt = m dz (Column::precompute)
+      double ex1, ex2, gx0, gx1, rdz;
+      if (REG) {
+        const double r1 = rinv_small(i == m ? m : i + 1);
+        ex1 = (i == m) ? -0.5 * r1 : -r1; ex2 = (i == m) ? ex1 : rinv_small(i);
+        gx0 = (i == m) ? -1.5 * r1 : (i > 1 ? -2.5 * r1 : -1.0); gx1 = (i == m) ? -0.5 * r1 : -1.5 * r1;
+        rdz = (i == 1) ? 2 * idz : idz;
+      } else { ex1 = mem.a_p(PA_EX1); ex2 = mem.a_p(PA_EX2); gx0 = mem.a_p(PA_GX0); gx1 = mem.a_p(PA_GX1); rdz = mem.a_p(PA_RDZ); }
       double lz;
-      if (i == m) lz = wcl(lu, ai, mem.a_p(PA_EX1), mem.a_p(PA_GLO), mem.a_p(PA_EDO));
+      if (i == m) lz = wcl(lu, ai, ex1, mem.a_p(PA_GLO), mem.a_p(PA_EDO));
       else {
-        lu = wcl(lu, ai, mem.a_p(PA_EX1), mem.a_p(PA_GLO), mem.a_p(PA_EDO));
-        lz = wcl(lu, mem.a_p(PA_A0O) * sqphi, mem.a_p(PA_EX2), mem.a_p(PA_GLI), mem.a_p(PA_EDI));                           // Q9
+        lu = wcl(lu, ai, ex1, mem.a_p(PA_GLO), mem.a_p(PA_EDO));
+        lz = wcl(lu, mem.a_p(PA_A0O) * sqphi, ex2, mem.a_p(PA_GLI), mem.a_p(PA_EDI));                           // Q9
       }
       uzn = fexp_neg(lz);                               // (clamped below only: lz <= log of the wind above the canopy)
       const double nlu = (lu < -600.0) ? 600.0 : -lu;   // (without the edge term the product can underflow; the exponents stay finite)
-      const double e0 = fexp_b(fma(-ai, mem.a_p(PA_GX0), nlu)), e1 = fexp_b(fma(-ai, mem.a_p(PA_GX1), nlu));      // (gx in [-1, 0])
+      const double e0 = fexp_b(fma(-ai, gx0, nlu)), e1 = fexp_b(fma(-ai, gx1, nlu));      // (gx in [-1, 0])
       const double g = fdiv(mem.a_p(PA_CG) * ph * ai, e0 - e1) * iphi;
-#else
-      if (i == m) uzn = wc_fast(uh, ai, mem.a_p(PA_EX1), mem.a_p(PA_GLO), mem.a_p(PA_EDO), ugr, edge);
-      else {
-        uh = wc_fast(uh, ai, mem.a_p(PA_EX1), mem.a_p(PA_GLO), mem.a_p(PA_EDO), ugr, edge);
-        uzn = wc_fast(uh, mem.a_p(PA_A0O) * sqphi, mem.a_p(PA_EX2), mem.a_p(PA_GLI), mem.a_p(PA_EDI), ugr, edge);      // Q9
-      }
-      const double e0 = fexp_b(-ai * mem.a_p(PA_GX0)), e1 = fexp_b(-ai * mem.a_p(PA_GX1));      // (gx in [-1, 0])
-      const double g = fdiv(mem.a_p(PA_CG) * ph * uh * ai, e0 - e1) * iphi;
-#endif
-      const double gfree = 0.0012 * ph * qroot(fabs(tcu - tcl) * mem.a_p(PA_RDZ));
+      const double gfree = 0.0012 * ph * qroot(fabs(tcu - tcl) * rdz);
       const double gtn = (g > gfree) ? g : gfree;
       const double rn = frcp(gtn);
       const double rg = frcp(0.5 * gtn + 0.5 * mem.a_gto());
@@ -846,9 +836,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       tcu = tcl;
     }
     // canopy top <-> reference (code.R:769), Q8: leftover uh, lowest air node
-#if MC_LOGWIND
     uh = fexp_neg(lu);
-#endif
     const double tcan = mem.unpark(X_TCAN), tc1 = mem.unpark(X_TC1);
     mem.g1_wait();                                     // the G1 rows were fetched behind the sweep
     const double a = mem.g1a(P0_A0CAP) * sqphi;
@@ -876,7 +864,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     mem.unpark8(X_TAIRN, x0); mem.unpark8(X_PPK, x1);
     const double tairn = x0[X_TAIRN], pkn = x0[X_PKN], skyem = x0[X_SKYEM], Rsw = x0[X_RSW], relhumn = x0[X_RELHUMN], tcan = x0[X_TCAN];
     const double ppk = x1[X_PPK - X_PPK], ps1 = x1[X_PS1 - X_PPK], tet_tcan = x1[X_TET_TCAN - X_PPK];
-    const double clump = mem.unpark(KR_CLUMP), refg = mem.unpark(KU_REFG), emv = mem.unpark(KG_EMV);   // launch-resident (fast_park_constants)
+    const double clump = mem.unpark(KR_CLUMP), refg = mem.unpark(KU_REFG), emv = p0(P0_EMV);   // launch-resident (fast_park_constants)
     double dp = fc.dp;
     // `sa` is sin(solar altitude) from here on: only its sign, the 5-degree test, sin and cot of the angle are used (mc_phys.cuh)
     const double sa = solsin_pre(fc.lt, mem.g1b(P0_LON), cfg.merid, cfg.dst, sday, mem.g1b(P0_SLAT), mem.g1b(P0_CLAT));
@@ -898,9 +886,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     const double eamn = fdiv(relhumn, 100) * tet_tcan;
     mem.park(KT_EREF, eref); mem.park(KT_ESOIL, esoil); mem.park(KT_MTREF, mtref); mem.park(KT_PS1, ps1); mem.park(KT_RGCAP, mem.unpark(X_RGCAP));
     mem.park(KT_CPPK, (44.6 * fdiv(ppk, 101.3)) * 273.15);
-#if MC_MQ
-    mem.park(KT_TSEL, fdiv(101.3 / (44.6 * 273.15), ppk));            // 1 / (cpk 273.15) of the previous pressure (the slot is free until the solve parks tsel)
-#endif
+    if (REG) mem.park(KT_TSEL, frcp(mem.unpark(KG_IDZ)));             // dz = hgt / m of the regular grid (the slot is free until the solve parks tsel)
     mem.park(KU_LAMBDA, fdiv((-42.575 * tcan + 44994) * surfwet, mpk));     // lambda / mpk: the only form sweep B uses
     mem.park(KU_TCAN, tcan); mem.park(KU_EAMN, eamn); mem.park(KU_IPPK, frcp(ppk)); mem.park(KU_PKN, pkn);
     mem.park_done();
@@ -909,13 +895,13 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   // ======================= sweep B: leafabs + leaftemp, bottom -> top, with the merged-layer sums =======================
   // layermerge / layeraverage bookkeeping (code.R:772, 814): closed groups 1..ng and the open one
   int ng = 0, glo[kNG + 2], ghi[kNG + 2];
-  double gw[kNG + 2], gtc[kNG + 2], gVo[kNG + 2], gea[kNG + 2], gX[kNG + 2], gvd[kNG + 2];
+  double gw[kNG + 2], gtc[kNG + 2], gVo[kNG + 2], gea[kNG + 2], gX[kNG + 2];
   const bool runB = run;
   {
     const int selHb = (int)p0(P0_SELH);
     const double its = 1 / cfg.timestep;              // launch-uniform
     double acc2 = 0, TT = 0, Lt = 0, stl = 0, ssw = 0;
-    double oR = 0, oC = 0, ow = 0, otc = 0, oVo = 0, oea = 0, oX = 0, ovd = 0;
+    double oR = 0, oC = 0, ow = 0, otc = 0, oVo = 0, oea = 0, oX = 0;
     int olo = 1;
     bool open = false;
     for (int i = 1; i <= m; ++i) {
@@ -925,7 +911,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double uzn = mem.b_w(WL_UZN), gtn = mem.b_w(WL_GTN);
       // leafabs (code.R:31-49) of this layer
       const double omr = 1 - mem.b_p(PB_REF);
-      double rsw, Rabsn, gvn, ghan;
+      double rsw, Rabsn, gvn, ghan, idzb = 0;
       const double Tkc = ptc + 273.15, iTkc = frcp(Tkc);
       {
         double kr[8];
@@ -941,18 +927,14 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         const double aRsw = omr * rsw;
         const double trl = mem.b_p(PB_TRLW);
         double kg[8];
-        mem.unpark8(KG_EMV, kg);
+        mem.unpark8(KG_IDZ, kg);
         const double aRlw = kr[KR_EMLW - KR_K] + trl * kr[KR_SKLW - KR_K];       // canlw()$lwabs, code.R:47: emv * (trl * sky + (1 - trl) * canopy)
         Rabsn = aRsw + aRlw;
         const double Qa = 4.6 * rsw;
-        gvn = fdiv(kg[KG_GSMAX - KG_EMV] * Qa, Qa + kg[KG_Q50 - KG_EMV]);       // layercond
-#if MC_GHA2
-        ghan = gha_fast2(kg[KG_LWD - KG_EMV], kg[KG_LWD3 - KG_EMV], kg[KG_ILWD - KG_EMV], uzn, Tkc, iTkc, kg[KG_CPK - KG_EMV] * iTkc, ptl - ptc,
-                         kg[KG_C101 - KG_EMV]);
-#else
-        ghan = gha_fast(kg[KG_LWD - KG_EMV], kg[KG_ILWD - KG_EMV], kg[KG_LWD3 - KG_EMV], uzn, Tkc, iTkc, kg[KG_CPK - KG_EMV] * iTkc, ptl - ptc,
-                        kg[KG_C101 - KG_EMV]);
-#endif
+        idzb = kg[KG_IDZ - KG_IDZ];
+        gvn = fdiv(kg[KG_GSMAX - KG_IDZ] * Qa, Qa + kg[KG_Q50 - KG_IDZ]);       // layercond
+        ghan = gha_fast2(kg[KG_LWD - KG_IDZ], kg[KG_LWD3 - KG_IDZ], kg[KG_ILWD - KG_IDZ], uzn, Tkc, iTkc, kg[KG_CPK - KG_IDZ] * iTkc, ptl - ptc,
+                         kg[KG_C101 - KG_IDZ]);
       }
       double kt[8];
       mem.unpark8(KT_EREF, kt);
@@ -964,7 +946,13 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double sfxi = (i == m) ? 0.0 : kt[KT_TNS1 - KT_EREF] - acc2;            // sum of rg above this layer
       const double gtt = frcp(kt[KT_RGCAP - KT_EREF] + sfxi);
       const double gtt2 = frcp(acc2);
-      const double izl = mem.b_p(PB_IZL), izrf = mem.b_p(PB_IZRF), izp = mem.b_p(PB_IZP), izth = mem.b_p(PB_IZTH), PAIi = mem.b_p(PB_PAI);
+      // previn$z geometry of the layer (code.R:387-392): rows, or on the regular grid zp = (i - 0.5) dz, zth = dz, zref = hgt + 2 - zp
+      const double izl = mem.b_p(PB_IZL), PAIi = mem.b_p(PB_PAI);
+      double izrf, izp, izth;
+      if (REG) {
+        izth = idzb; izp = idzb * (2 * rinv_small(2 * i - 1));
+        izrf = frcp(fma(kt[KT_TSEL - KT_EREF], (double)m - ((double)i - 0.5), 2.0));
+      } else { izrf = mem.b_p(PB_IZRF); izp = mem.b_p(PB_IZP); izth = mem.b_p(PB_IZTH); }
       const double PAIm = 2 * PAIi * izth;
       const double esj = 0.6108 * fexp_b((17.27 * ptc) * frcp(ptc + 237.3));    // Tetens, code.R:410
       const double eaj = (mem.b_s(SL_RH) * 0.01) * esj;
@@ -974,11 +962,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double delta = (4098 * tetl) * (r237l * r237l);                      // code.R:415
       const double gvo = mem.b_s(SL_GV), ghao = mem.b_s(SL_GHA);
       // 1/(1/a + 1/b) = a*b/(a+b): one division; a = 0 (closed stomata at night) still gives 0
-#if MC_GVC
       const double gvp = gvo;                                                    // the working row holds the previous step's gvc (fast_run_column converts previn$gv)
-#else
-      const double gvp = fdiv(gvo * ghao, gvo + ghao);
-#endif
       const double gvc = fdiv(gvn * ghan, gvn + ghan);
       const double gvm = 0.5 * gvp + 0.5 * gvc;
       const double gham = 0.5 * ghan + 0.5 * ghao;
@@ -1007,14 +991,9 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         aL = (gtt * mtref + gtt2 * ps1 + gham * ptl) * iden;
         bL = (0.5 * gham) * iden;
       } else {
-#if MC_MQ
         // ma K_i = (mac / (cp ph)) (g_i cp) = mac g_i / ph and 1 / ph = Tk / (cpk 273.15): no division, cp cancels
-        const double ma = mem.b_p(PB_MAC) * (Tkc * kt[KT_TSEL - KT_EREF]);
+        const double ma = mem.p_mac(i) * (Tkc * frcp(kt[KT_CPPK - KT_EREF]));   // (PB_MAC is not staged: hourly steps practically never come here)
         const double K1 = g1, K2 = g2, K3 = g3h * PAIm;
-#else
-        const double ma = fdiv(mem.b_p(PB_MAC), cp * phc);
-        const double K1 = g1 * cp, K2 = g2 * cp, K3 = g3h * cp * PAIm;
-#endif
         const double ibtm = frcp(1 + 0.5 * ma * (K1 + K2 + K3));
         aL = (ptc + 0.5 * ma * (K1 * mtref + K2 * ps1 + K3 * ptl)) * ibtm;
         bL = (0.25 * ma * K3) * ibtm;
@@ -1092,22 +1071,23 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       }
       // layermerge (code.R:772) greedy grouping with the layeraverage sums (code.R:814) of the open group
       {
-        const double wi = mem.b_p(PB_DZ), phz = phc * wi, rn = frcp(mem.b_w(WL_GTN));       // phair(previn$tc, previn$pk) * dz as in sweep A
+        const double wi = REG ? ((i == 1) ? 0.5 * kt[KT_TSEL - KT_EREF] : kt[KT_TSEL - KT_EREF]) : mem.b_p(PB_DZ);   // z[i] - z[i-1]
+        const double phz = phc * wi, rn = frcp(mem.b_w(WL_GTN));       // phair(previn$tc, previn$pk) * dz as in sweep A
         TT += phz * rn;                                                           // cumsum((ph/gt) * dz), code.R:797
         oR += rn; oC += phz; open = true;
-        ow += wi; otc += wi * ptc; oVo += wi * (eaj * ku[KU_IPPK - KU_LAMBDA]); oea += wi * ean; oX += wi * (tnl - ptc); ovd += wi * mem.b_p(PB_VDEN);
+        ow += wi; otc += wi * ptc; oVo += wi * (eaj * ku[KU_IPPK - KU_LAMBDA]); oea += wi * ean; oX += wi * (tnl - ptc);
         if (timestep <= oC * oR) {                                               // timestep / sum(1/gt) <= sum(ph*zth)
           if (ng < kNG) {
             ++ng;
-            glo[ng] = olo; ghi[ng] = i; gw[ng] = ow; gtc[ng] = otc; gVo[ng] = oVo; gea[ng] = oea; gX[ng] = oX; gvd[ng] = ovd;
+            glo[ng] = olo; ghi[ng] = i; gw[ng] = ow; gtc[ng] = otc; gVo[ng] = oVo; gea[ng] = oea; gX[ng] = oX;
           } else fastok = false;     // more merged layers than the solve holds: the column leaves the streaming form (the rest of
                                      // this step only writes its own, now dead, rows; never beyond the solver's storage)
-          olo = i + 1; oR = 0; oC = 0; ow = 0; otc = 0; oVo = 0; oea = 0; oX = 0; ovd = 0; open = false;
+          olo = i + 1; oR = 0; oC = 0; ow = 0; otc = 0; oVo = 0; oea = 0; oX = 0; open = false;
         }
       }
       if (runB) {
         double* Sl = S + (long long)L.sl(i, 0) * kTile;
-        mem.st_stream(Sl + SL_TLEAF * kTile, tleafn); mem.st_stream(Sl + SL_RABS * kTile, Rabsn); mem.st_stream(Sl + SL_GV * kTile, MC_GVC ? gvc : gvn);
+        mem.st_stream(Sl + SL_TLEAF * kTile, tleafn); mem.st_stream(Sl + SL_RABS * kTile, Rabsn); mem.st_stream(Sl + SL_GV * kTile, gvc);
         mem.st_stream(Sl + SL_GHA * kTile, ghan);
         // previn$uz is only read at the lowest and highest node (code.R:731), so the other rows are written when the state is
         // harvested (emit) and not on every step
@@ -1118,13 +1098,11 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       // (the EAL row carries log(ean / 0.6108), which this sweep has anyway: sweep C needs ean only inside dewpoint()'s logarithm)
       mem.st_keep(W + (long long)L.wl(i, WL_TT) * kTile, TT); mem.st_keep(W + (long long)L.wl(i, WL_EAL) * kTile, al);
       if (emit || i == selHb) { wput(i, WL_L, Lp); wput(i, WL_RSWIN, rsw); }
-#if MC_GVC
       if (emit) wput(i, WL_GVN, gvn);
-#endif
       Lt += Lp; stl += tleafn; ssw += rsw;
     }
     if (open) {                                     // trailing group joins the last closed one
-      if (ng > 0) { ghi[ng] = m; gw[ng] += ow; gtc[ng] += otc; gVo[ng] += oVo; gea[ng] += oea; gX[ng] += oX; gvd[ng] += ovd; }
+      if (ng > 0) { ghi[ng] = m; gw[ng] += ow; gtc[ng] += otc; gVo[ng] += oVo; gea[ng] += oea; gX[ng] += oX; }
       else { ng = 1; glo[1] = 1; ghi[1] = m; }
     }
     mem.park(X_TT, TT); mem.park(X_LT, Lt); mem.park(X_STL, stl); mem.park(X_SSW, ssw);
@@ -1180,7 +1158,9 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         lz[mg + 2] = p0(P0_HGT);
 #pragma unroll 1
         for (int g = 1; g <= mg; ++g) {
-          const double lcp = cpair(ltc[g]), lvd = gvd[g] * frcp(gw[g]);
+          // sum of dz * vden over the group from the cumulative row (two direct reads per group, only on steps with merged layers)
+          const double gvd = mem.p_cvd(ghi[g]) - (glo[g] > 1 ? mem.p_cvd(glo[g] - 1) : 0.0);
+          const double lcp = cpair(ltc[g]), lvd = gvd * frcp(gw[g]);
           const double cda = lcp * lph[g] * (1 - lvd) * (lz[g + 2] - lz[g]) / 2 * timestep;       // Q10
           double ka = lgt[g] * lcp;
           if (ka > cda) ka = cda;
@@ -1413,7 +1393,7 @@ MC_HD void abi_state_from_ws(const FastLayout& L, const double* __restrict__ P, 
   r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, P[(long long)L.pz(i) * kTile]);
   r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, g(L.sl(i, SL_RH)));
   r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, g(L.sl(i, SL_RABS)));
-  r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, MC_GVC ? W[(long long)L.wl(i, WL_GVN) * kTile] : g(L.sl(i, SL_GV)));
+  r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, W[(long long)L.wl(i, WL_GVN) * kTile]);
   r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, g(L.sl(i, SL_GHA)));
   r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, W[(long long)L.wl(i, WL_L) * kTile]);
   r += m; for (int i = 1; i <= m; ++i) w(r + i - 1, W[(long long)L.wl(i, WL_RSWIN) * kTile]);
@@ -1434,6 +1414,15 @@ MC_HD RunCfg effective_cfg(const TransientArgs& t, double hgt, bool spin) {
   if (spin) { if (!t.spin_standalone) { c.reqhgt = spinhgt; c.zlafact = 1; c.surfwet = 1; } }
   else c.reqhgt = t.charmode ? spinhgt : reqhgt;
   return c;
+}
+
+// The launch runs on the regular node grid (template parameter REG of the streaming kernel) when its effective reqhgt is NA for every
+// column: runonestep then keeps paraminit's z (code.R:573, 719).  `spin` selects the spin-up launch.  (With charmode the spin-up height
+// is hgt / 2 per column, never NA.)
+MC_HD bool fast_regular_grid(const TransientArgs& t, bool spin) {
+  if (t.charmode) return false;
+  const RunCfg c = effective_cfg(t, 1.0, spin);
+  return !(c.reqhgt == c.reqhgt);
 }
 
 // mean(climdata$temp) of one column (code.R:992, 1165), summed in time order
@@ -1471,7 +1460,7 @@ MC_HD void fast_forcing_at(const Mem& mem, const TransientArgs& a, long long t, 
 // The whole launch for one column: spin_mode 1 = paraminit + spin-up steps on forcing row 0 (code.R:982-1013);
 // spin_mode 0 = steps [t0, t1) of runmodel's loop with the output harvest (code.R:1193-1266).
 // `c` is the source column (clamped for padding lanes), `live` false for padding lanes.
-template <class Mem, int MM, int MS>
+template <class Mem, int MM, int MS, bool REG>
 MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) {
   const TransientArgs& t = a.t;
   const FastLayout L = mem.L;
@@ -1498,7 +1487,7 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
       tcs += tci;
       sput(L.sl(i, SL_TC), tci); sput(L.sl(i, SL_TLEAF), tci + 0.01 * Ra); sput(L.sl(i, SL_RH), relhum_); sput(L.sl(i, SL_RABS), Ra);
       { const double gv = lin2(0.25, 0.32, i, m), gha = lin2(0.13, 0.19, i, m);
-        sput(L.sl(i, SL_GV), MC_GVC ? fdiv(gv * gha, gv + gha) : gv); sput(L.sl(i, SL_GHA), gha); }
+        sput(L.sl(i, SL_GV), fdiv(gv * gha, gv + gha)); sput(L.sl(i, SL_GHA), gha); }
       sput(L.uz(i), ((double)i / m) * u_);
       sput(L.gt(i), i == 1 ? 2 * g0 : g0);
     }
@@ -1520,7 +1509,7 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
       sput(L.sl(i, SL_TC), tci); sput(L.sl(i, SL_TLEAF), st(P_NSCAL + m + i - 1)); sput(L.uz(i), st(P_NSCAL + 2 * m + i - 1));
       sput(L.sl(i, SL_RH), st(P_NSCAL + 4 * m + i - 1)); sput(L.sl(i, SL_RABS), st(P_NSCAL + 5 * m + i - 1));
       { const double gv = st(P_NSCAL + 6 * m + i - 1), gha = st(P_NSCAL + 7 * m + i - 1);      // (the same quotient the step forms: restarts stay bit-identical)
-        sput(L.sl(i, SL_GV), MC_GVC ? fdiv(gv * gha, gv + gha) : gv); sput(L.sl(i, SL_GHA), gha); }
+        sput(L.sl(i, SL_GV), fdiv(gv * gha, gv + gha)); sput(L.sl(i, SL_GHA), gha); }
       sput(L.gt(i), st(P_NSCAL + 11 * m + i - 1));
       W[(long long)L.wl(i, WL_L) * kTile] = st(P_NSCAL + 8 * m + i - 1); W[(long long)L.wl(i, WL_RSWIN) * kTile] = st(P_NSCAL + 9 * m + i - 1);
       W[(long long)L.wl(i, WL_RLWIN) * kTile] = st(P_NSCAL + 10 * m + i - 1);
@@ -1561,7 +1550,7 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
   if (!dead && !fastcol) drop();
   // with shared per-layer rows (parameter classes) a tile cannot rebuild its leaf-geometry rows after the first step: such a column
   // (incoming node heights differ from the current geometry) goes to the general kernel
-  if (!dead && zdiff && a.tile_src) drop();
+  if (!dead && zdiff && (a.tile_src || REG)) drop();       // (REG: the launch assumes the regular node grid in previn$z as well)
   fast_park_constants(mem);
   if (nsteps > 0) mem.g0_issue();
   for (long long it = 0; it < nsteps; ++it) {
@@ -1574,9 +1563,9 @@ MC_HD void fast_run_column(const FastArgs& a, Mem& mem, long long c, bool live) 
     SolDay sday;                                          // date-only solar terms: from the per-row table when the library made one
     if (t.fsol) { sday.eot = t.fsol[tt * 3]; sday.sdec = t.fsol[tt * 3 + 1]; sday.cdec = t.fsol[tt * 3 + 2]; }
     else sday = sol_day(f[F_JD]);
-    const bool ok = fast_step<Mem, MS>(mem, fc, sday, t.cfg, surfwet, !dead, emit, it + 1 < nsteps, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
+    const bool ok = fast_step<Mem, MS, REG>(mem, fc, sday, t.cfg, surfwet, !dead, emit, it + 1 < nsteps, reqhgt, t.charmode, f0[F_RELHUM], f0[F_RSW], f0[F_SKYEM], so);
     if (!dead && !ok) drop();
-    if (it == 0 && zdiff && !a.tile_src) fast_regeom(const_cast<double*>(P), m, sm, cfg.timestep, cfg.zlafact);   // (ordered before the next step's bulk copies by step_begin's fence + barrier)
+    if (!REG && it == 0 && zdiff && !a.tile_src) fast_regeom(const_cast<double*>(P), m, sm, cfg.timestep, cfg.zlafact);   // (ordered before the next step's bulk copies by step_begin's fence + barrier)
     if (dead) continue;
     if (spin) { Hsum += S[(long long)S0_H * kTile]; sput(S0_H, Hsum / (double)(it + 1)); continue; }   // previn$H <- mean(H)
     if (so.ng > 1) flag |= 2;

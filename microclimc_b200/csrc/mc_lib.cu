@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kTile) k_geom(const __grid_constant__ FastArgs
 constexpr int kFastSmem = 2 * kStageRows * kTile * 8 + 64;
 // EXACT: the layer counts equal the template bounds (m = MM, sm = MS, all BASELINE configs), so every row offset is a
 // compile-time constant; otherwise they are read from the arguments (6 < m <= MM, sm <= MS).
-template <int MM, int MS, bool EXACT>
+template <int MM, int MS, bool EXACT, bool REG>
 // CTAs per SM the register allocation is bounded for.  4 (128 registers) is what shared memory (55 KB per CTA) and tensor memory (128 columns
 // per CTA) allow as well.  Measured around it on the same box (tools/abv.sh, profiles/README.md r02s): 5 (96 registers, still 4 resident) runs
 // 12 % slower, 3 (168 registers, no spills, 3 resident) 4 % slower — each warp is 28 % faster with the registers, which does not make up for
@@ -77,17 +77,18 @@ __global__ void __launch_bounds__(kTile, MC_FAST_CTAS) k_transient_fast(const __
   const long long c = (long long)blockIdx.x * kTile + threadIdx.x;
   const bool live = c < a.t.ncol;
   FastLayout L{EXACT ? MM : a.t.m, EXACT ? MS : a.t.sm};
-  PipeMem mem;
+  PipeMemT<REG> mem;
   mem.L = L;
   mem.Pt = a.P + (long long)blockIdx.x * L.nP() * kTile; mem.St = a.S + (long long)blockIdx.x * L.nS() * kTile;
   mem.Wt = a.W + (long long)blockIdx.x * L.nW() * kTile;
   mem.Pl = a.tile_src ? a.P + (long long)a.tile_src[blockIdx.x] * L.nP() * kTile : mem.Pt;
+  mem.Pll = mem.Pl + threadIdx.x;
   mem.P = mem.Pt + threadIdx.x; mem.S = const_cast<double*>(mem.St) + threadIdx.x; mem.W = const_cast<double*>(mem.Wt) + threadIdx.x;
   mem.buf = buf; mem.bar = bar; mem.bar32 = smem_u32(bar); mem.buf32 = smem_u32(buf); mem.lane = threadIdx.x; mem.k = 0; mem.gk = 0; mem.g0p = mem.g1ap = mem.g1bp = buf; mem.cur = buf;
   mem.tbase = *tmem_base_s + ((unsigned)((threadIdx.x >> 5) * 32) << 16);
   for (int q = 0; q < 8; ++q) mem.tcyc[q] = 0;
   mem.tlast = clock64();
-  fast_run_column<PipeMem, MM, MS>(a, mem, live ? c : a.t.ncol - 1, live);
+  fast_run_column<PipeMemT<REG>, MM, MS, REG>(a, mem, live ? c : a.t.ncol - 1, live);
   if (a.dbgbuf && threadIdx.x == 0) for (int q = 0; q < 8; ++q) atomicAdd(a.dbgbuf + q, (unsigned long long)mem.tcyc[q]);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -356,8 +357,9 @@ int launch_transient(Shard& s, const TransientArgs& a) {
   CU(s.ffail.need(sizeof(int) * a.ncol)); CU(s.flist.need(sizeof(long long) * 2 * a.ncol)); CU(s.fcount.need(sizeof(unsigned) * 2));
   CU(cudaMemsetAsync(s.ffail.p, 0, sizeof(int) * a.ncol, s.st)); CU(cudaMemsetAsync(s.fcount.p, 0, sizeof(unsigned) * 2, s.st));
   if (!s.fast_attr) {
-    CU(cudaFuncSetAttribute(k_transient_fast<20, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
-    CU(cudaFuncSetAttribute(k_transient_fast<20, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
+    CU(cudaFuncSetAttribute(k_transient_fast<20, 10, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
+    CU(cudaFuncSetAttribute(k_transient_fast<20, 10, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
+    CU(cudaFuncSetAttribute(k_transient_fast<20, 10, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
     s.fast_attr = true;
   }
   FastArgs fa{a, s.fP.as<double>(), s.fS.as<double>(), s.fW.as<double>(), nullptr, 0, nullptr, s.ffail.as<int>(), s.flist.as<long long>(),
@@ -377,8 +379,10 @@ int launch_transient(Shard& s, const TransientArgs& a) {
     fa.spin_mode = spin;
     fa.tile_src = (s.has_classes && (spin == 0 || classes_ok_spin)) ? s.tile_src.as<int>() : nullptr;
     k_geom<20, 10><<<(unsigned)ntile, kTile, 0, s.st>>>(fa);
-    if (a.m == 20 && a.sm == 10) k_transient_fast<20, 10, true><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
-    else k_transient_fast<20, 10, false><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
+    // REG: every column of the launch is on paraminit's regular node grid (reqhgt NA): the rows that depend on the grid alone are not streamed
+    if (a.m == 20 && a.sm == 10 && fast_regular_grid(a, spin != 0)) k_transient_fast<20, 10, true, true><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
+    else if (a.m == 20 && a.sm == 10) k_transient_fast<20, 10, true, false><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
+    else k_transient_fast<20, 10, false, false><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
     s.launches += 2;
   }
   // Columns that left the streaming form are redone by the general kernel from the call's initial state: list 0 (left during the

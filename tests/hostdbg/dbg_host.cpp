@@ -81,7 +81,9 @@ extern "C" int dbg_run_transient_fast(int64_t ncol, int m, int sm, int64_t T, co
       mem.S = S.data() + (c / kTile) * L.nS() * kTile + (c % kTile);
       mem.W = W.data() + (c / kTile) * L.nW() * kTile + (c % kTile);
       mem.ia = mem.ib = 1;
-      fast_run_column<DirectMem, 20, 10>(a, mem, c, true);
+      // the instantiation mc_lib.cu would launch: REG (regular node grid, reqhgt NA) only with m = 20, sm = 10
+      if (m == 20 && sm == 10 && fast_regular_grid(t, spin != 0)) fast_run_column<DirectMem, 20, 10, true>(a, mem, c, true);
+      else fast_run_column<DirectMem, 20, 10, false>(a, mem, c, true);
     }
   }
   // columns that left the streaming form: redone by the general column from the call's initial state, as mc_lib.cu sequences it
