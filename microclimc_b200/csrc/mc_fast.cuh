@@ -36,9 +36,8 @@ constexpr int kTile = 128;   // columns per CTA == columns per workspace tile
 //   * leaf boundary-layer conductance with the common factor (ph / d) sqrt(sc) of the forced and free branches taken out of the maximum
 //     (gha_fast2): 4 square roots and no reciprocal instead of 5 and one;
 //   * the working state keeps the series conductance gv gha / (gv + gha) of the previous step (all that leaftemp reads of previn$gv)
-//     instead of gv; gv itself is written with the harvest rows when the state is emitted;
-//   * leaftemp's transient air balance with cp cancelled (ma K_i = mac g_i / ph): one division less.
-// Same-box A/B of the four together: 589-594 -> 613-614 M column-steps/s.
+//     instead of gv; gv itself is written with the harvest rows when the state is emitted.
+// Same-box A/B of the three together: 589-594 -> 613-614 M column-steps/s.
 #if !defined(__CUDACC__)
 static long long g_mc_general_steps = 0;     // host (test) build: columns that left the streaming form (launch-level count)
 #endif
@@ -64,12 +63,12 @@ constexpr int kGRow0 = 15;                        // G1a / G1b land in rows 15..
 // z: on the REGULAR grid z[i] = (i - 0.5) hgt / m that paraminit builds (code.R:573) and runonestep keeps whenever reqhgt is NA (code.R:719
 // replaces one node otherwise) they depend on the column through hgt alone, and a launch whose columns all have that grid (template
 // parameter REG of the kernel) forms them from m / hgt and small-integer reciprocals instead of streaming them: 5 + 4 rows of 8 bytes per
-// layer and step less, 1.44 of the 8.4 KB the kernel moves per column-step.  PB_MAC (read only in leaftemp's transient air balance, which
-// hourly steps practically never take) and PB_CVD (the cumulative sum of dz * vden, read at the merged-layer group boundaries by the solve)
-// are never staged: direct reads where needed.
+// layer and step less, 1.44 of the 8.4 KB the kernel moves per column-step.  PB_CVD (the cumulative sum of dz * vden, read at the merged-layer
+// group boundaries by the solve), PB_MAC (leaftemp's transient air balance, which only the non-regular instantiation evaluates, and hourly steps
+// take it only for a node moved above the canopy) and PB_VDEN (read by fast_regeom only) are never staged: direct reads where needed.
 enum { PA_A0I, PA_A0O, PA_GLO, PA_GLI, PA_EDO, PA_EDI, PA_CG, PA_NREG, PA_EX1 = PA_NREG, PA_EX2, PA_GX0, PA_GX1, PA_RDZ, PA_N };
 enum { PB_REF, PB_PC, PB_SPC, PB_SGC, PB_TRDC, PB_TRDG, PB_TRLW, PB_PAI, PB_IZL, PB_MZ, PB_NREG, PB_IZTH = PB_NREG, PB_IZP, PB_IZRF, PB_DZ,
-       PB_NSTG, PB_MAC = PB_NSTG, PB_CVD, PB_VDEN, PB_N };
+       PB_NSTG, PB_CVD = PB_NSTG, PB_MAC, PB_VDEN, PB_N };
 // 1 / k for the small integers the regular grid needs (k <= 2 m - 1, m <= 20 in the streaming form)
 #if defined(__CUDACC__)
 __constant__ double c_rinv[40] = {0.0,     1.0 / 1,  1.0 / 2,  1.0 / 3,  1.0 / 4,  1.0 / 5,  1.0 / 6,  1.0 / 7,  1.0 / 8,  1.0 / 9,
@@ -283,8 +282,8 @@ struct DirectMem {
   MC_HD double b_s(int r) const { return S[(long long)L.sl(ib, r) * kTile]; }
   MC_HD double b_w(int r) const { return W[(long long)L.wl(ib, r) * kTile]; }
   MC_HD double b_gto() const { return S[(long long)L.gt(ib) * kTile]; }                     // read before the layer stores its new gt
-  MC_HD double p_mac(int i) const { return P[(long long)L.pb(i, PB_MAC) * kTile]; }
   MC_HD double p_cvd(int i) const { return P[(long long)L.pb(i, PB_CVD) * kTile]; }
+  MC_HD double p_mac(int i) const { return P[(long long)L.pb(i, PB_MAC) * kTile]; }
 };
 
 // make BOUNDS=1: every computed index into the stage buffers, the tensor-memory scratch and the tile workspaces is range-checked on the
@@ -356,9 +355,9 @@ struct PipeMemT {
   const double* P; double* S; double* W;      // lane-adjusted tile bases (for stores and the few direct reads)
   const double* Pt; const double* St; const double* Wt;   // tile bases (lane 0), for the bulk copies
   const double* Pl;                            // tile whose per-layer geometry rows this tile reads (Pt, or its class's first tile)
-  const double* Pll;                           // Pl + lane, for the two rows that are read directly
-  MC_D double p_mac(int i) const { return Pll[(long long)L.pb(i, PB_MAC) * kTile]; }
+  const double* Pll;                           // Pl + lane, for the rows that are read directly
   MC_D double p_cvd(int i) const { return Pll[(long long)L.pb(i, PB_CVD) * kTile]; }
+  MC_D double p_mac(int i) const { return Pll[(long long)L.pb(i, PB_MAC) * kTile]; }
   FastLayout L;
   double* buf;                                 // [2][kStageRows][kTile] in shared memory
   unsigned long long* bar;                     // [2]
@@ -900,6 +899,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   {
     const int selHb = (int)p0(P0_SELH);
     const double its = 1 / cfg.timestep;              // launch-uniform
+    bool balances_ok = true;                            // every layer so far takes leaftemp's equilibrium balances
     double acc2 = 0, TT = 0, Lt = 0, stl = 0, ssw = 0;
     double oR = 0, oC = 0, ow = 0, otc = 0, oVo = 0, oea = 0, oX = 0;
     int olo = 1;
@@ -948,11 +948,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double gtt2 = frcp(acc2);
       // previn$z geometry of the layer (code.R:387-392): rows, or on the regular grid zp = (i - 0.5) dz, zth = dz, zref = hgt + 2 - zp
       const double izl = mem.b_p(PB_IZL), PAIi = mem.b_p(PB_PAI);
-      double izrf, izp, izth;
-      if (REG) {
-        izth = idzb; izp = idzb * (2 * rinv_small(2 * i - 1));
-        izrf = frcp(fma(kt[KT_TSEL - KT_EREF], (double)m - ((double)i - 0.5), 2.0));
-      } else { izrf = mem.b_p(PB_IZRF); izp = mem.b_p(PB_IZP); izth = mem.b_p(PB_IZTH); }
+      const double izth = REG ? idzb : mem.b_p(PB_IZTH);
       const double PAIm = 2 * PAIi * izth;
       const double esj = 0.6108 * fexp_b((17.27 * ptc) * frcp(ptc + 237.3));    // Tetens, code.R:410
       const double eaj = (mem.b_s(SL_RH) * 0.01) * esj;
@@ -966,9 +962,23 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double gvc = fdiv(gvn * ghan, gvn + ghan);
       const double gvm = 0.5 * gvp + 0.5 * gvc;
       const double gham = 0.5 * ghan + 0.5 * ghao;
-      const double g1 = gtt * izrf, g2 = gtt2 * izp, g3 = gvm * izl, g3h = gham * izl;
+      // leaftemp switches each balance between a transient form and an equilibrium form: equilibrium when timestep * max(g1, g3, g2) > 1,
+      // g1 = gtt / zref, g2 = gtt2 / z, g3 = gv / zla (gha / zla for heat) (code.R:419-449).  On the regular node grid every layer of every
+      // test and bench input is in the equilibrium form at the hourly or longer steps the streaming form runs with (the leaf term alone is
+      // 10^2-10^4): the REG instantiation does not carry the transient forms; a lane that would need one leaves the streaming form and is
+      // redone by the general kernel.  Its test avoids the reciprocals (gtt / zref > 1 / timestep <=> timestep gtt > zref; zref, z > 0 there).
+      // A node moved above the canopy (reqhgt > hgt) does take the transient forms at hourly steps: the general instantiation has both.
+      bool eqv = true, eqh = true;
+      if (REG) {
+        const double zp = kt[KT_TSEL - KT_EREF] * ((double)i - 0.5);                // (i - 0.5) dz;  zref = hgt + 2 - z
+        const bool big12 = (timestep * gtt > fma(kt[KT_TSEL - KT_EREF], (double)m - ((double)i - 0.5), 2.0)) || (timestep * gtt2 > zp);
+        const double tzl = timestep * izl;
+        if (!(big12 || tzl * gvm > 1) || !(big12 || tzl * gham > 1)) balances_ok = false;
+      }
+      const double g1 = REG ? 0.0 : gtt * mem.b_p(PB_IZRF), g2 = REG ? 0.0 : gtt2 * mem.b_p(PB_IZP), g3 = gvm * izl, g3h = gham * izl;
+      if (!REG) { eqv = timestep * dmax(dmax(g1, g3), g2) > 1; eqh = timestep * dmax(dmax(g1, g3h), g2) > 1; }
       double ae, be;
-      if (timestep * dmax(dmax(g1, g3), g2) > 1) {
+      if (REG || eqv) {
         const double gv2b = (PAIm * izth) * gvm;                                // Q21
         const double iden = frcp(gtt + gtt2 + gv2b);
         ae = (gtt * eref + gtt2 * esoil + gv2b * estl) * iden;
@@ -985,14 +995,14 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double cp = cpair(ptc);
       const double phc = kt[KT_CPPK - KT_EREF] * iTkc;
       double aL, bL;
-      if (timestep * dmax(dmax(g1, g3h), g2) > 1) {
+      if (REG || eqh) {
         // code.R:447-449 with the common factor cp of K1, K2, K3 cancelled between numerator and denominator
         const double iden = frcp(gtt + gtt2 + gham);
         aL = (gtt * mtref + gtt2 * ps1 + gham * ptl) * iden;
         bL = (0.5 * gham) * iden;
       } else {
         // ma K_i = (mac / (cp ph)) (g_i cp) = mac g_i / ph and 1 / ph = Tk / (cpk 273.15): no division, cp cancels
-        const double ma = mem.p_mac(i) * (Tkc * frcp(kt[KT_CPPK - KT_EREF]));   // (PB_MAC is not staged: hourly steps practically never come here)
+        const double ma = mem.p_mac(i) * (Tkc * frcp(kt[KT_CPPK - KT_EREF]));   // (PB_MAC is not staged)
         const double K1 = g1, K2 = g2, K3 = g3h * PAIm;
         const double ibtm = frcp(1 + 0.5 * ma * (K1 + K2 + K3));
         aL = (ptc + 0.5 * ma * (K1 * mtref + K2 * ps1 + K3 * ptl)) * ibtm;
@@ -1030,7 +1040,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double es = tetens(tnl);
       if (ean > es) ean = es;
       if (ean < eamn) ean = eamn;
-      const double al = flog(ean * (1 / 0.6108));
+      const double al = flog_nb(ean * (1 / 0.6108));          // (branch-free form: ean >= eamn > 0, and a straight-line body lets the scheduler interleave it)
       const double Tdew = -fdiv(237.3 * al, al - 17.27);
       double dT1 = -(ptl + dTL - Tdew);
       if (dT1 < 0) dT1 = 0;
@@ -1105,6 +1115,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       if (ng > 0) { ghi[ng] = m; gw[ng] += ow; gtc[ng] += otc; gVo[ng] += oVo; gea[ng] += oea; gX[ng] += oX; }
       else { ng = 1; glo[1] = 1; ghi[1] = m; }
     }
+    if (REG && !balances_ok) fastok = false;          // a transient balance somewhere in the column: general path
     mem.park(X_TT, TT); mem.park(X_LT, Lt); mem.park(X_STL, stl); mem.park(X_SSW, ssw);
     mem.park_done();
   }

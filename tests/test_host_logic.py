@@ -230,7 +230,9 @@ def test_streaming_form_equals_oracle(oracle, hostdbg, timestep, charmode, reqhg
     assert np.array_equal(got["flags"] & 1, want["flags"] & 1)
     for t in (0, 50, 95):
         assert_state_close(got["full"][t], want["full"][t], what="streaming full table t=%d" % t)
-    if timestep >= 1800.0 and np.all(np.isfinite(want["state"])) and edgedist == edgedist:      # (without the edge term the calm lower canopy can exceed the streaming solve's 6 merged layers)
+    # (the library runs the streaming form for hourly or longer steps only; with shorter steps on the regular node grid (reqhgt NA) lanes
+    # that reach leaftemp's transient balances are redone by the general column, as are those with more than 6 merged layers)
+    if timestep >= (3600.0 if reqhgt != reqhgt else 1800.0) and np.all(np.isfinite(want["state"])) and edgedist == edgedist:      # (without the edge term the calm lower canopy can exceed the streaming solve's 6 merged layers)
         assert ngen == 0, "hourly columns should stay in the streaming form (columns dropped: %d)" % ngen
         assert not np.any(got["flags"] & 8)
     if timestep <= 20.0:
