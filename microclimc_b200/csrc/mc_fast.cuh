@@ -94,6 +94,8 @@ constexpr int kStageRowsB = PB_NSTG + SL_N + kWLiveB + 1;   // sweep-B stage: ge
 constexpr int kStageRows = 27;                    // rows of 128 doubles per stage buffer (the solver scratch needs 2 x 27)
 static_assert(kStageRowsB <= kStageRows, "sweep-B stage exceeds the stage buffer");
 static_assert(kG0Rows <= kStageRows && kGRow0 + kG1aRows <= kStageRows && kGRow0 + kG1bRows <= kStageRows && PA_N + 2 <= kGRow0, "scalar groups do not fit the idle stage rows");
+constexpr int kG2Spill = kStageRowsB;              // first stage row no sweep-B stage uses
+static_assert(3 * 10 <= kStageRows + (kStageRows - kG2Spill), "the solve's soil rows do not fit the idle stage rows");
 constexpr int kNG = 6;                            // merged air layers handled in the streaming form (more: general path)
 
 struct FastLayout {
@@ -263,6 +265,8 @@ struct DirectMem {
   MC_HD void g0_issue() {}
   MC_HD void g0_wait() {}
   MC_HD void g1_wait() {}
+  MC_HD void g2_wait() {}
+  MC_HD double g2(int r) const { return r < 2 * L.sm ? P[(long long)(P0_NFIX + r) * kTile] : S[(long long)L.soiltc(r - 2 * L.sm + 1) * kTile]; }
   MC_HD void end_begin(bool) {}
   MC_HD double g0(int r) const { return P[(long long)r * kTile]; }
   MC_HD double g1a(int r) const { return P[(long long)r * kTile]; }
@@ -449,6 +453,13 @@ struct PipeMemT {
   MC_D void g_wait() { mbar_wait(bar32 + 16, gk & 1); ++gk; }
   MC_D void g0_wait() { g_wait(); }
   MC_D void g1_wait() { g_wait(); }
+  // G2: the solve's soil rows — 1 / dzk [sm], dzc [sm] of the geometry and the sm soil temperatures of the state — fetched behind the LAST
+  // sweep-B stage, which has no successor to prefetch: the other stage buffer is idle from that stage's barrier until sweep C's first
+  // copy.  Rows 0.. of that buffer, and what does not fit its kStageRows rows goes to the spare rows (kG2Spill..) of the current buffer.
+  // (They used to be 3 sm direct reads at the head of the solve: 42 % of its stall samples, r02t.)
+  const double* g2a; const double* g2b;
+  MC_D void g2_wait() { g_wait(); }
+  MC_D double g2(int r) const { return r < kStageRows ? g2a[r * kTile] : g2b[(kG2Spill + r - kStageRows) * kTile]; }
   // after sweep C: every lane is done with the stage rows and the node arrays; fetch the next step's G0 behind the end of this one
   MC_D void end_begin(bool more) {
     // (no proxy fence: sweep C only READ the stage rows and the node arrays; the generic-proxy writes to them — the solve's scratch — were
@@ -540,6 +551,18 @@ struct PipeMemT {
   MC_D void stageB(int i) {
     __syncthreads();
     if (lane == 0 && i < L.m) issueB(i + 1, k + 1);
+    if (i == L.m) {                                  // G2 behind the last stage (see g2)
+      const int ns = 3 * L.sm, na = ns < kStageRows ? ns : kStageRows;
+      const unsigned fb = (k + 1) & 1, cb = k & 1;
+      if (lane == 0) {
+        mbar_expect_tx(bar32 + 16, ns * kTile * 8);
+        const unsigned dst = buf32 + fb * (kStageRows * kTile * 8);
+        bulk_g2s_stream(dst, Pt + (long long)P0_NFIX * kTile, 2 * L.sm * kTile * 8, bar32 + 16, pol);
+        bulk_g2s_stream(dst + 2 * L.sm * kTile * 8, St + (long long)L.soiltc(1) * kTile, (na - 2 * L.sm) * kTile * 8, bar32 + 16, pol);
+        if (ns > na) bulk_g2s_stream(buf32 + (cb * kStageRows + kG2Spill) * (kTile * 8), St + (long long)L.soiltc(1 + na - 2 * L.sm) * kTile, (ns - na) * kTile * 8, bar32 + 16, pol);
+      }
+      g2a = buf + fb * (kStageRows * kTile) + lane; g2b = buf + cb * (kStageRows * kTile) + lane;
+    }
     mbar_wait(bar32 + (k & 1) * 8, (k >> 1) & 1);
     cur = buf + (k & 1) * (kStageRows * kTile) + lane;
     ++k;
@@ -1135,10 +1158,21 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     const double esoil = mem.unpark(KT_ESOIL), eamn = mem.unpark(KU_EAMN);          // (all tensor-memory reads before lanes diverge)
     const double timestep = cfg.timestep, i2ts = 1 / (2 * timestep);
     TX = TT + fdiv(pha, gtncap) * 2;
+    mem.g2_wait();                                     // the soil rows were fetched behind the last sweep-B stage
     if (!MC_SKIP(4)) {
       mgx = (ng > 1) ? ng : 0;
       const int mg = mgx, N = mg + sm;
       double ltc[kNG + 2], lgt[kNG + 3], lz[kNG + 4], lVo[kNG + 2], lea[kNG + 2], lph[kNG + 2], lTT[kNG + 2], xv[kNG + 3], vX[kNG + 2], Yt[kNG + 3];
+      {                                                  // soil nodes FIRST: their rows (G2) sit in stage rows the scratch stores below reuse;
+                                                         // all row loads, then the scratch stores (own lane only: no cross-lane hazard)
+        double rk[MS], rc[MS], rt[MS];
+#pragma unroll
+        for (int j = 1; j <= MS; ++j) if (j <= sm) { rk[j - 1] = mem.g2(j - 1); rc[j - 1] = mem.g2(sm + (j - 1)); rt[j - 1] = mem.g2(2 * sm + (j - 1)); }
+#pragma unroll
+        for (int j = 1; j <= MS; ++j) if (j <= sm) {
+          mem.scr_put(SK0 + mg + 1 + j, lam * rk[j - 1]); mem.scr_put(SCD0 + mg + j, (Cv * rc[j - 1]) * i2ts); mem.scr_put(STC0 + 1 + mg + j, rt[j - 1]);
+        }
+      }
       if (mg > 0) {                                   // layeraverage (code.R:814) and the air part of the system (code.R:815-826)
         int cprev = 0;
         lz[1] = 0;
@@ -1182,15 +1216,6 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         mem.scr_put(SK0 + 1, frcp(cs) * cpair(tabove));   // one lumped conductance for the lower half of the canopy (code.R:856-857)
       }
       xv[mg + 1] = Xs;
-      {                                                  // soil nodes: all row loads first (one latency), then the scratch stores
-        double rk[MS], rc[MS], rt[MS];
-#pragma unroll
-        for (int j = 1; j <= MS; ++j) if (j <= sm) { rk[j - 1] = p0(P0_NFIX + (j - 1)); rc[j - 1] = p0(P0_NFIX + sm + (j - 1)); rt[j - 1] = s0(L.soiltc(j)); }
-#pragma unroll
-        for (int j = 1; j <= MS; ++j) if (j <= sm) {
-          mem.scr_put(SK0 + mg + 1 + j, lam * rk[j - 1]); mem.scr_put(SCD0 + mg + j, (Cv * rc[j - 1]) * i2ts); mem.scr_put(STC0 + 1 + mg + j, rt[j - 1]);
-        }
-      }
       mem.scr_put(STC0 + 1, tabove); mem.scr_put(STC0 + N + 2, tsoilp);
       thomas_s(mem, SK0, SCD0, STC0, N, fc.tsoil, tcan, cfg.n, xv, mg + 1);
       // STC(2..N+1) now holds tn2 (code.R:829); tnsoil[j] = tn2[mg+1+j]
