@@ -794,7 +794,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     }
     ps1a = ps1; tcu = tcm;
     if (REG) idz = (double)m * frcp(hgt);              // 1 / dz of the regular grid
-    lu = flog(uh); lugr = flog(ugr);                   // (uh >= 0.5 * ... > 0; ugr = 0 in a calm hour gives -Inf, which loses every maximum)
+    lu = flog_nb(uh); lugr = flog_nb(ugr);                 // (uh >= 0.5 * ... > 0; ugr = 0 in a calm hour gives -Inf, which loses every maximum)
     mem.park(X_TAIRN, tairn); mem.park(X_PKN, pkn); mem.park(X_SKYEM, fc.skyem); mem.park(X_RSW, fc.Rsw); mem.park(X_RELHUMN, relhumn);
     mem.park(X_TCAN, tcan); mem.park(X_TAIRP, s0(S0_TAIR)); mem.park(X_RELHUMP, s0(S0_RELHUM));
     mem.park(X_PPK, ppk); mem.park(X_PS1, ps1); mem.park(X_TET_TAIR, tet_tair); mem.park(X_TET_TCAN, tet_tcan); mem.park(X_TFROST, tfrost);
