@@ -278,3 +278,28 @@ def test_runmodel_batch_by_class_returns_the_callers_order(oracle):
     bad = inp["veg"].copy(); bad[3, 7] *= 1.01
     with pytest.raises(ValueError, match="identical"):
         api.runmodel_batch(clim, bad, inp["soil"], inp["lat"], inp["lon"], classes=cls, **kw)
+
+
+def test_regular_grid_launch_from_a_state_with_a_moved_node(oracle):
+    """A launch with reqhgt NA runs the regular-grid instantiation of the streaming kernel, which assumes paraminit's
+    node heights in previn$z as well.  A state handed over from a run with reqhgt = 5 m has one node moved (code.R:719): those columns
+    must be redone by the general kernel (flags bit 3) and still match the oracle continuing from the same state."""
+    inp = transient_inputs(oracle, ncol=40, T=48)
+    first = make_cfg(reqhgt=5.0, spin_steps=30)
+    want0 = oracle.run_transient(inp["veg"], inp["soil"], inp["f"][:24], inp["lat"], inp["lon"], first, M, SM, fscale=inp["fs"], foffset=inp["fo"])
+    second = make_cfg(spin_steps=0)                                             # reqhgt NA from here on
+    tsoil = inp["f"][:, 0].mean() * inp["fs"][0] + inp["fo"][0]
+    want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"][24:], inp["lat"], inp["lon"], second, M, SM, state=want0["state"],
+                                fscale=inp["fs"], foffset=inp["fo"], tsoil=tsoil)
+    ctx = _ctx(dict(inp, f=inp["f"][24:]), second)
+    ctx.set_state(want0["state"])
+    got = ctx.run_transient(tsoil=tsoil, samp_idx=np.arange(40))
+    assert_series_close(got["series"], want["series"], "regular-grid launch from a moved-node state")
+    assert_state_close(ctx.get_state(), want["state"], what="regular-grid launch from a moved-node state")
+    assert np.all(got["flags"] & 8), "columns whose previn$z is not the regular grid leave the regular-grid instantiation"
+    # the next launch starts from the regular grid again (runonestep returned z = the current heights) and stays in the streaming form
+    got2 = ctx.run_transient(tsoil=tsoil, samp_idx=np.arange(40))
+    assert not np.any(got2["flags"] & 8)
+    want2 = oracle.run_transient(inp["veg"], inp["soil"], inp["f"][24:], inp["lat"], inp["lon"], second, M, SM, state=want["state"],
+                                 fscale=inp["fs"], foffset=inp["fo"], tsoil=tsoil)
+    assert_series_close(got2["series"], want2["series"], "second regular-grid launch")

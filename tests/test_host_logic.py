@@ -267,6 +267,46 @@ def test_streaming_restart_and_chunking(oracle, hostdbg):
     assert np.all(np.isfinite(a["state"]))
 
 
+def test_regular_grid_instantiation_redoes_columns_with_a_moved_node(oracle, hostdbg):
+    """reqhgt NA selects the regular-grid instantiation (REG) of the streaming step; a state whose previn$z has a node moved by an
+    earlier reqhgt = 5 m run (code.R:719) cannot use it: every such column is redone by the general column and matches the oracle."""
+    inp = transient_inputs(oracle, ncol=6, T=36)
+    first = make_cfg(reqhgt=5.0, spin_steps=30)
+    want0 = oracle.run_transient(inp["veg"], inp["soil"], inp["f"][:12], inp["lat"], inp["lon"], first, M, SM, fscale=inp["fs"], foffset=inp["fo"])
+    second = make_cfg(spin_steps=0)
+    rest = dict(inp, f=inp["f"][12:])
+    want = oracle.run_transient(inp["veg"], inp["soil"], rest["f"], inp["lat"], inp["lon"], second, M, SM, state=want0["state"],
+                                fscale=inp["fs"], foffset=inp["fo"])
+    fl = _FastLib(hostdbg)
+    fl.dbg_general_steps(1)
+    got = dbg_run_transient(fl, rest, second, state=want0["state"])
+    assert fl.dbg_general_steps(1) == 6 and np.all(got["flags"] & 8)
+    assert_series_close(got["series"], want["series"], "moved node, regular-grid launch")
+    assert_state_close(got["state"], want["state"], what="moved node, regular-grid launch")
+    fl.dbg_general_steps(1)
+    got2 = dbg_run_transient(fl, rest, second, state=got["state"])                 # z is the regular grid again: streaming form
+    assert fl.dbg_general_steps(1) == 0 and not np.any(got2["flags"] & 8)
+    want2 = oracle.run_transient(inp["veg"], inp["soil"], rest["f"], inp["lat"], inp["lon"], second, M, SM, state=want["state"],
+                                 fscale=inp["fs"], foffset=inp["fo"])
+    assert_series_close(got2["series"], want2["series"], "second regular-grid launch")
+
+
+def test_regular_grid_instantiation_leaves_transient_balances_to_the_general_column(oracle, hostdbg):
+    """leaftemp selects its transient balances when timestep * max(g1, g3, g2) <= 1 (code.R:419-449) — on the regular grid that needs
+    steps of a few seconds or less (host count over 8 columns x 44 steps: none of 7 040 layer-steps at 3600 / 300 / 60 / 20 s, a third at 5 s, all at 0.05 s).  The regular-grid instantiation
+    carries only the equilibrium forms: such lanes (here, at 0.05 s, all of them; they also exceed the six merged layers) are redone by the
+    general column and match the oracle."""
+    inp = transient_inputs(oracle, ncol=4, T=6)
+    cfg = make_cfg(timestep=0.05, spin_steps=5)
+    want = oracle.run_transient(inp["veg"], inp["soil"], inp["f"], inp["lat"], inp["lon"], cfg, M, SM, fscale=inp["fs"], foffset=inp["fo"])
+    fl = _FastLib(hostdbg)
+    fl.dbg_general_steps(1)
+    got = dbg_run_transient(fl, inp, cfg)
+    assert fl.dbg_general_steps(1) == 4 and np.all(got["flags"] & 8)
+    assert_series_close(got["series"], want["series"], "0.05 s steps")
+    assert_state_close(got["state"], want["state"], what="0.05 s steps")
+
+
 # ---- the variant tables of tests/test_gpu_variants.py through the host build of the streaming code -----------------------
 def _variant_cases():
     import tests.test_gpu_variants as V
