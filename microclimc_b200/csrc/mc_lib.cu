@@ -235,6 +235,17 @@ struct Shard {
   DBuf vegp, soilp, lat, lon, state, state_bak, fscale, foffset, forcing, season, tsoil, stats, series, full, samp_of, flags,
       args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fsol, fP, fS, fW, dbg, ffail, flist, fcount, samp_cols, vegt, thetaz, stats_raw, flags_raw, tile_src;
   bool fast_attr = false;
+  // Geometry cache of the streaming path.  k_geom's output (the P workspace: 3.9 ms per 10^6 columns and launch) depends on the column inputs
+  // (vegp, soilp, lat, lon, forcing perturbation: `inputs_epoch` counts their uploads), the run description, the launch kind (spin-up or run) and
+  // previn$z of the incoming state.  A run launch re-uses the rows of the previous run launch when all of that is unchanged AND both launches
+  // are "clean": the incoming node heights equal the launch's own heights, which holds when the state was last written by a launch with the same
+  // effective reqhgt (runonestep returns z = its current heights, code.R:898) — then no column has differing previn$z and the kernel does not
+  // rebuild rows in place.  A year run week by week computes the geometry once instead of 52 times.
+  struct GeomTag { double c[10]; int metopen, charmode, standalone, m, sm, pert; long long ncol; unsigned long long epoch; };
+  GeomTag geom_tag{}; bool geom_valid = false;
+  unsigned long long inputs_epoch = 1;
+  bool z_valid = false; double z_reqhgt = 0; int z_charmode = 0; unsigned long long z_epoch = 0;   // whose heights the state's z rows hold
+  bool bak_z_valid = false; double bak_z_reqhgt = 0; int bak_z_charmode = 0; unsigned long long bak_z_epoch = 0;   // the same for state_bak
   bool has_pert = false, has_season = false, has_state = false, bak_valid = false;
   long long nvt = 0, vegt_T = 0, thetaz_T = 0; bool has_thetaz = false;
   bool has_classes = false; long long class_tiles_shared = 0;   // mc_set_classes: tile_src loaded; tiles that read another tile's rows       // time-varying vegetation / soil moisture by depth loaded (mc_set_vegt, mc_set_thetaz)
@@ -343,13 +354,22 @@ bool fast_eligible(const TransientArgs& a) {
 #endif
   return !a.season && !a.vegt && !a.thetaz && a.m <= 20 && a.m > kNG && a.sm <= 10 && a.cfg.timestep >= 3600.0;
 }
+// whose node heights the state holds after this call: those of its last launch (the run launch, else the spin-up launch)
+static void note_state_heights(Shard& s, const TransientArgs& a) {
+  const bool spin_last = !(a.t1 > a.t0);
+  s.z_valid = true; s.z_reqhgt = effective_cfg(a, 1.0, spin_last).reqhgt; s.z_charmode = a.charmode; s.z_epoch = s.inputs_epoch;
+}
+static bool same_bits(double x, double y) { return std::memcmp(&x, &y, sizeof(double)) == 0; }
 int launch_transient(Shard& s, const TransientArgs& a) {
-  if (!fast_eligible(a))
-    return dispatch_ms(a.m, a.sm, [&](auto MM, auto MS) {
+  if (!fast_eligible(a)) {
+    int rc = dispatch_ms(a.m, a.sm, [&](auto MM, auto MS) {
       k_transient<decltype(MM)::value, decltype(MS)::value><<<nblocks(a.ncol), kBlock, 0, s.st>>>(a, nullptr, nullptr);
       s.launches++;
       return 0;
     });
+    note_state_heights(s, a);
+    return rc;
+  }
   const FastLayout L{a.m, a.sm};
   const long long ntile = (a.ncol + kTile - 1) / kTile;
   CU(s.fP.need(sizeof(double) * ntile * L.nP() * kTile)); CU(s.fS.need(sizeof(double) * ntile * L.nS() * kTile));
@@ -378,13 +398,35 @@ int launch_transient(Shard& s, const TransientArgs& a) {
     if (spin ? a.spin_steps <= 0 : a.t1 <= a.t0) continue;
     fa.spin_mode = spin;
     fa.tile_src = (s.has_classes && (spin == 0 || classes_ok_spin)) ? s.tile_src.as<int>() : nullptr;
-    k_geom<20, 10><<<(unsigned)ntile, kTile, 0, s.st>>>(fa);
+    // geometry: recomputed unless this is a run launch with the inputs, run description and (clean) node heights of the run launch that
+    // filled the workspace last (see Shard::GeomTag)
+    Shard::GeomTag tag{};
+    {
+      const RunCfg& c = a.cfg;
+      const double cv[10] = {c.timestep, c.edgedist, c.reqhgt, c.zu, c.merid, c.dst, c.n, c.windhgt, c.zlafact, c.surfwet};
+      std::memcpy(tag.c, cv, sizeof(cv));
+      tag.metopen = c.metopen; tag.charmode = a.charmode; tag.standalone = a.spin_standalone; tag.m = a.m; tag.sm = a.sm;
+      tag.pert = a.fscale != nullptr; tag.ncol = a.ncol; tag.epoch = s.inputs_epoch;
+    }
+    const double zreq = effective_cfg(a, 1.0, spin != 0).reqhgt;
+    // the state's z rows are this launch's heights: written by a launch of the same effective reqhgt (or, after this call's own spin-up
+    // launch, by that one)
+    const bool spun = spin == 0 && a.spin_steps > 0;
+    const double zprev_req = spun ? effective_cfg(a, 1.0, true).reqhgt : s.z_reqhgt;
+    const bool clean = spin == 0 && (spun || (s.z_valid && s.z_epoch == s.inputs_epoch && s.z_charmode == a.charmode)) && same_bits(zprev_req, zreq) && !a.charmode;
+    const bool reuse = clean && s.geom_valid && std::memcmp(&tag, &s.geom_tag, sizeof(tag)) == 0;
+    if (!reuse) {
+      k_geom<20, 10><<<(unsigned)ntile, kTile, 0, s.st>>>(fa);
+      s.launches++;
+      s.geom_valid = clean; s.geom_tag = tag;           // (a spin-up launch or one with differing previn$z leaves rows nobody may re-use)
+    }
     // REG: every column of the launch is on paraminit's regular node grid (reqhgt NA): the rows that depend on the grid alone are not streamed
     if (a.m == 20 && a.sm == 10 && fast_regular_grid(a, spin != 0)) k_transient_fast<20, 10, true, true><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
     else if (a.m == 20 && a.sm == 10) k_transient_fast<20, 10, true, false><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
     else k_transient_fast<20, 10, false, false><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
-    s.launches += 2;
+    s.launches++;
   }
+  note_state_heights(s, a);
   // Columns that left the streaming form are redone by the general kernel from the call's initial state: list 0 (left during the
   // spin-up launch) with the spin-up, list 1 (left during the run launch) from the state the spin-up launch stored.  Both launches
   // cover the worst case and their blocks beyond the list length exit at once (no host round trip for the count).
@@ -500,6 +542,7 @@ int mc_set_columns(mc_ctx* ctx, int64_t ncol, const double* vegp, const double* 
     s.c0 = std::min<long long>((long long)i * per, ncol);
     s.nc = std::min<long long>(per, ncol - s.c0);
     s.has_state = false; s.has_pert = false; s.last_kind = 0; s.samp_valid = false; s.nvt = 0; s.has_thetaz = false; s.has_classes = false;
+    s.inputs_epoch++; s.geom_valid = false; s.z_valid = false;
   }
   const int NV = mc_nveg(ctx->m), NSo = mc_nsoil(ctx->sm), NSt = mc_nstate(ctx->m, ctx->sm);
   return for_shards(ctx, [&](Shard& s) -> int {
@@ -530,6 +573,7 @@ int mc_set_forcing(mc_ctx* ctx, int64_t T, const double* forcing, const double* 
     CU(cudaGetLastError());
     s.pending_launches++;
     s.has_pert = fscale != nullptr;
+    s.inputs_epoch++; s.geom_valid = false;          // (the perturbation rows are copied into the geometry workspace)
     if (fscale) {
       CU(s.fscale.need(sizeof(double) * MC_NPERT * s.nc)); CU(s.foffset.need(sizeof(double) * MC_NPERT * s.nc));
       CU(h2d_rows(s.fscale.as<double>(), fscale, MC_NPERT, ncol, s.c0, s.nc, s.st));
@@ -625,7 +669,7 @@ int mc_set_state(mc_ctx* ctx, const double* state) {
     if (s.nc == 0) return 0;
     CU(h2d_rows(s.state.as<double>(), state, NSt, ncol, s.c0, s.nc, s.st));
     CU(cudaStreamSynchronize(s.st));
-    s.has_state = true;
+    s.has_state = true; s.z_valid = false;
     return 0;
   });
 }
@@ -661,7 +705,7 @@ int mc_paraminit(mc_ctx* ctx, const double* args) {
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s.st));
     CU(cudaEventElapsedTime(&s.ms, s.e0, s.e1));
-    s.has_state = true;
+    s.has_state = true; s.z_valid = false;
     return 0;
   });
   collect_timing(ctx);
@@ -698,6 +742,7 @@ int mc_run_onestep(mc_ctx* ctx, const double* climvars, double jd, double lt, co
     if (nmerged) CU(cudaMemcpyAsync(nmerged + s.c0, s.nmerged.p, sizeof(int) * s.nc, cudaMemcpyDeviceToHost, s.st));
     CU(cudaStreamSynchronize(s.st));
     CU(cudaEventElapsedTime(&s.ms, s.e0, s.e1));
+    s.z_valid = false;
     return 0;
   });
   collect_timing(ctx);
@@ -781,6 +826,7 @@ static int run_transient_impl(mc_ctx* ctx, int64_t t0, int64_t t1, int spin_step
       CU(s.state_bak.need(sizeof(double) * NSt * s.nc));
       CU(cudaMemcpyAsync(s.state_bak.p, s.state.p, sizeof(double) * NSt * s.nc, cudaMemcpyDeviceToDevice, s.st));
       s.bak_valid = true;
+      s.bak_z_valid = s.z_valid; s.bak_z_reqhgt = s.z_reqhgt; s.bak_z_charmode = s.z_charmode; s.bak_z_epoch = s.z_epoch;
     } else s.bak_valid = false;
     CU(cudaEventRecord(s.e0, s.st));
     { int lrc = launch_transient(s, a); if (lrc) return lrc; }
@@ -970,8 +1016,10 @@ double mc_bench_resident(mc_ctx* ctx, int reps) {
     if (s.nc == 0 || s.last_kind == 0) return 0;
     float total = 0;
     for (int r = 0; r < reps; ++r) {
-      if (s.last_kind == 1 && s.last_t.spin_steps <= 0)
+      if (s.last_kind == 1 && s.last_t.spin_steps <= 0) {
         CU(cudaMemcpyAsync(s.state.p, s.state_bak.p, sizeof(double) * NSt * s.nc, cudaMemcpyDeviceToDevice, s.st));
+        s.z_valid = s.bak_z_valid; s.z_reqhgt = s.bak_z_reqhgt; s.z_charmode = s.bak_z_charmode; s.z_epoch = s.bak_z_epoch;   // (the restored state's heights)
+      }
       CU(cudaEventRecord(s.e0, s.st));
       { int lrc = (s.last_kind == 1) ? launch_transient(s, s.last_t) : launch_steady(s, s.last_s, s.last_nchunk); if (lrc) return lrc; }
       CU(cudaEventRecord(s.e1, s.st));
