@@ -45,6 +45,18 @@ __global__ void __launch_bounds__(kTile) k_geom(const __grid_constant__ FastArgs
   const double hgt = a.t.vegp[(long long)V_HGT * a.t.ncol + cl];
   geom_column<MM, MS>(a, effective_cfg(a.t, hgt, a.spin_mode != 0), c, cl);
 }
+// Only the forcing-perturbation rows of the geometry workspace (16 of its ~670 rows): what a new mc_set_forcing changes.
+__global__ void __launch_bounds__(kTile) k_geom_pert(const __grid_constant__ FastArgs a) {
+  const long long c = (long long)blockIdx.x * kTile + threadIdx.x;
+  const long long cl = c < a.t.ncol ? c : a.t.ncol - 1;
+  const FastLayout L{a.t.m, a.t.sm};
+  double* P = a.P + (long long)blockIdx.x * L.nP() * kTile + threadIdx.x;
+  const bool pert = a.t.fscale && a.t.foffset;
+  for (int v = 0; v < kNPert; ++v) {
+    P[(long long)(P0_FS0 + v) * kTile] = pert ? a.t.fscale[(long long)v * a.t.ncol + cl] : 1.0;
+    P[(long long)(P0_FO0 + v) * kTile] = pert ? a.t.foffset[(long long)v * a.t.ncol + cl] : 0.0;
+  }
+}
 constexpr int kFastSmem = 2 * kStageRows * kTile * 8 + 64;
 // EXACT: the layer counts equal the template bounds (m = MM, sm = MS, all BASELINE configs), so every row offset is a
 // compile-time constant; otherwise they are read from the arguments (6 < m <= MM, sm <= MS).
@@ -236,14 +248,15 @@ struct Shard {
       args6, clim8, theta, thetap, nmerged, sclim, snmr, sseason, sout, spart, ssol, fsol, fP, fS, fW, dbg, ffail, flist, fcount, samp_cols, vegt, thetaz, stats_raw, flags_raw, tile_src;
   bool fast_attr = false;
   // Geometry cache of the streaming path.  k_geom's output (the P workspace: 3.9 ms per 10^6 columns and launch) depends on the column inputs
-  // (vegp, soilp, lat, lon, forcing perturbation: `inputs_epoch` counts their uploads), the run description, the launch kind (spin-up or run) and
+  // (vegp, soilp, lat, lon: `inputs_epoch` counts their uploads; the forcing perturbation: `pert_epoch`, and a launch after a new
+  // mc_set_forcing alone rewrites just those 16 rows, k_geom_pert), the run description, the launch kind (spin-up or run) and
   // previn$z of the incoming state.  A run launch re-uses the rows of the previous run launch when all of that is unchanged AND both launches
   // are "clean": the incoming node heights equal the launch's own heights, which holds when the state was last written by a launch with the same
   // effective reqhgt (runonestep returns z = its current heights, code.R:898) — then no column has differing previn$z and the kernel does not
   // rebuild rows in place.  A year run week by week computes the geometry once instead of 52 times.
-  struct GeomTag { double c[10]; int metopen, charmode, standalone, m, sm, pert; long long ncol; unsigned long long epoch; };
-  GeomTag geom_tag{}; bool geom_valid = false;
-  unsigned long long inputs_epoch = 1;
+  struct GeomTag { double c[10]; int metopen, charmode, standalone, m, sm; long long ncol; unsigned long long epoch; };
+  GeomTag geom_tag{}; bool geom_valid = false; unsigned long long geom_pert_epoch = 0;
+  unsigned long long inputs_epoch = 1, pert_epoch = 1;
   bool z_valid = false; double z_reqhgt = 0; int z_charmode = 0; unsigned long long z_epoch = 0;   // whose heights the state's z rows hold
   bool bak_z_valid = false; double bak_z_reqhgt = 0; int bak_z_charmode = 0; unsigned long long bak_z_epoch = 0;   // the same for state_bak
   bool has_pert = false, has_season = false, has_state = false, bak_valid = false;
@@ -406,7 +419,7 @@ int launch_transient(Shard& s, const TransientArgs& a) {
       const double cv[10] = {c.timestep, c.edgedist, c.reqhgt, c.zu, c.merid, c.dst, c.n, c.windhgt, c.zlafact, c.surfwet};
       std::memcpy(tag.c, cv, sizeof(cv));
       tag.metopen = c.metopen; tag.charmode = a.charmode; tag.standalone = a.spin_standalone; tag.m = a.m; tag.sm = a.sm;
-      tag.pert = a.fscale != nullptr; tag.ncol = a.ncol; tag.epoch = s.inputs_epoch;
+      tag.ncol = a.ncol; tag.epoch = s.inputs_epoch;
     }
     const double zreq = effective_cfg(a, 1.0, spin != 0).reqhgt;
     // the state's z rows are this launch's heights: written by a launch of the same effective reqhgt (or, after this call's own spin-up
@@ -418,7 +431,11 @@ int launch_transient(Shard& s, const TransientArgs& a) {
     if (!reuse) {
       k_geom<20, 10><<<(unsigned)ntile, kTile, 0, s.st>>>(fa);
       s.launches++;
-      s.geom_valid = clean; s.geom_tag = tag;           // (a spin-up launch or one with differing previn$z leaves rows nobody may re-use)
+      s.geom_valid = clean; s.geom_tag = tag; s.geom_pert_epoch = s.pert_epoch;   // (a spin-up launch or one with differing previn$z leaves rows nobody may re-use)
+    } else if (s.geom_pert_epoch != s.pert_epoch) {
+      k_geom_pert<<<(unsigned)ntile, kTile, 0, s.st>>>(fa);
+      s.launches++;
+      s.geom_pert_epoch = s.pert_epoch;
     }
     // REG: every column of the launch is on paraminit's regular node grid (reqhgt NA): the rows that depend on the grid alone are not streamed
     if (a.m == 20 && a.sm == 10 && fast_regular_grid(a, spin != 0)) k_transient_fast<20, 10, true, true><<<(unsigned)ntile, kTile, kFastSmem, s.st>>>(fa);
@@ -573,7 +590,7 @@ int mc_set_forcing(mc_ctx* ctx, int64_t T, const double* forcing, const double* 
     CU(cudaGetLastError());
     s.pending_launches++;
     s.has_pert = fscale != nullptr;
-    s.inputs_epoch++; s.geom_valid = false;          // (the perturbation rows are copied into the geometry workspace)
+    s.pert_epoch++;                                  // (the perturbation rows are copied into the geometry workspace)
     if (fscale) {
       CU(s.fscale.need(sizeof(double) * MC_NPERT * s.nc)); CU(s.foffset.need(sizeof(double) * MC_NPERT * s.nc));
       CU(h2d_rows(s.fscale.as<double>(), fscale, MC_NPERT, ncol, s.c0, s.nc, s.st));
