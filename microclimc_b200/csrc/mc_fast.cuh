@@ -66,8 +66,11 @@ constexpr int kGRow0 = 15;                        // G1a / G1b land in rows 15..
 // layer and step less, 1.44 of the 8.4 KB the kernel moves per column-step.  PB_CVD (the cumulative sum of dz * vden, read at the merged-layer
 // group boundaries by the solve), PB_MAC (leaftemp's transient air balance, which only the non-regular instantiation evaluates, and hourly steps
 // take it only for a node moved above the canopy) and PB_VDEN (read by fast_regeom only) are never staged: direct reads where needed.
-enum { PA_A0I, PA_A0O, PA_GLO, PA_GLI, PA_EDO, PA_EDI, PA_CG, PA_NREG, PA_EX1 = PA_NREG, PA_EX2, PA_GX0, PA_GX1, PA_RDZ, PA_N };
-enum { PB_REF, PB_PC, PB_SPC, PB_SGC, PB_TRDC, PB_TRDG, PB_TRLW, PB_PAI, PB_IZL, PB_MZ, PB_NREG, PB_IZTH = PB_NREG, PB_IZP, PB_IZRF, PB_DZ,
+// (On the regular grid the inner-node rows GLI, EDI of layer i are those of the outer node of layer i + 1 — the same height, zi(i) = zo(i + 1)
+// — up to the factor zi(i + 1) / zo(i) = (i + 2) / i in ed: sweep A, going down, carries them in registers and stages them only for
+// layer m - 1, which has no such neighbour.  SREF = sqrt(1 - ref) stands for three former rows: 1 - ref = SREF^2, sref * pc = SREF * PC.)
+enum { PA_A0I, PA_A0O, PA_GLO, PA_EDO, PA_CG, PA_NREG5, PA_GLI = PA_NREG5, PA_EDI, PA_NREG, PA_EX1 = PA_NREG, PA_EX2, PA_GX0, PA_GX1, PA_RDZ, PA_N };
+enum { PB_SREF, PB_PC, PB_SGC, PB_TRDC, PB_TRDG, PB_TRLW, PB_PAI, PB_IZL, PB_MZ, PB_NREG, PB_IZTH = PB_NREG, PB_IZP, PB_IZRF, PB_DZ,
        PB_NSTG, PB_CVD = PB_NSTG, PB_MAC, PB_VDEN, PB_N };
 // 1 / k for the small integers the regular grid needs (k <= 2 m - 1, m <= 20 in the streaming form)
 #if defined(__CUDACC__)
@@ -231,7 +234,7 @@ MC_HD void geom_column(const FastArgs& a, const RunCfg& cfg, long long c, long l
     const double pc = col.PAIg[m + 1 - i];
     const double vden = col.thickw[i] * col.PAI[i];
     const LeafGeom lg = leafgeom_rows(hgt, col.zprev[i], col.zthp[i], col.zla[i], col.PAI[i], vden, col.cpw, col.phw, cfg.timestep);
-    put(L.pb(i, PB_REF), ref); put(L.pb(i, PB_PC), pc); put(L.pb(i, PB_SPC), col.sref[i] * pc); put(L.pb(i, PB_SGC), col.sref[i] * col.PAIg[i]);
+    put(L.pb(i, PB_SREF), col.sref[i]); put(L.pb(i, PB_PC), pc); put(L.pb(i, PB_SGC), col.sref[i] * col.PAIg[i]);      // sref = sqrt(1 - ref)
     put(L.pb(i, PB_TRDC), col.trdc[i]); put(L.pb(i, PB_TRDG), col.trdg[i]); put(L.pb(i, PB_TRLW), col.trlw[i]); put(L.pb(i, PB_PAI), col.PAI[i]);
     put(L.pb(i, PB_IZTH), lg.izth); put(L.pb(i, PB_IZL), lg.izl); put(L.pb(i, PB_IZRF), lg.izrf);
     put(L.pb(i, PB_IZP), lg.izp); put(L.pb(i, PB_MAC), lg.mac);
@@ -355,7 +358,10 @@ MC_D void discard_line(const void* p) { asm volatile("discard.global.L2 [%0], 12
 
 template <bool REG>
 struct PipeMemT {
-  static constexpr int PAS = REG ? PA_NREG : PA_N, PBS = REG ? PB_NREG : PB_NSTG;   // geometry rows of a sweep-A / sweep-B stage
+  static constexpr int PBS = REG ? PB_NREG : PB_NSTG;   // geometry rows of a sweep-B stage
+  // geometry rows of the sweep-A stage of layer i: on the regular grid GLI / EDI are staged for layer m - 1 only (see the PA enum)
+  MC_D int pas(int i) const { return REG ? (i == L.m - 1 ? (int)PA_NREG : (int)PA_NREG5) : (int)PA_N; }
+  int an;                                      // pas() of the current sweep-A stage
   const double* P; double* S; double* W;      // lane-adjusted tile bases (for stores and the few direct reads)
   const double* Pt; const double* St; const double* Wt;   // tile bases (lane 0), for the bulk copies
   const double* Pl;                            // tile whose per-layer geometry rows this tile reads (Pt, or its class's first tile)
@@ -473,11 +479,15 @@ struct PipeMemT {
   MC_D void issueA(int i, unsigned kk) {
     const unsigned b = buf32 + (kk & 1) * (kStageRows * kTile * 8);
     const unsigned mb = bar32 + (kk & 1) * 8;
+    const int PAS = pas(i);
     const unsigned bytes = (PAS + (i > 1 ? 1 : 0) + 1) * kTile * 8;
     mbar_expect_tx(mb, bytes);
     bulk_g2s_stream(b, Pl + (long long)L.pa(i, 0) * kTile, PAS * kTile * 8, mb, Pl == Pt ? pol : pol_keep);
-    if (i > 1) bulk_g2s_stream(b + PAS * kTile * 8, St + (long long)L.sl(i - 1, SL_TC) * kTile, kTile * 8, mb, pol);
-    bulk_g2s_stream(b + (PAS + 1) * kTile * 8, St + (long long)L.gt(i) * kTile, kTile * 8, mb, pol);
+#ifndef MC_AKEEP
+#define MC_AKEEP 1      // 1: the tc / gt rows sweep A reads are kept in L2 (evict-last) for sweep B's read of the same rows half a step later
+#endif
+    if (i > 1) bulk_g2s_stream(b + PAS * kTile * 8, St + (long long)L.sl(i - 1, SL_TC) * kTile, kTile * 8, mb, MC_AKEEP ? pol_keep : pol);
+    bulk_g2s_stream(b + (PAS + 1) * kTile * 8, St + (long long)L.gt(i) * kTile, kTile * 8, mb, MC_AKEEP ? pol_keep : pol);
   }
   MC_D void issueB(int i, unsigned kk) {
     const unsigned b = buf32 + (kk & 1) * (kStageRows * kTile * 8);
@@ -546,6 +556,7 @@ struct PipeMemT {
     if (lane == 0 && i > 1) issueA(i - 1, k + 1);
     mbar_wait(bar32 + (k & 1) * 8, (k >> 1) & 1);
     cur = buf + (k & 1) * (kStageRows * kTile) + lane;
+    an = pas(i);
     ++k;
   }
   MC_D void stageB(int i) {
@@ -567,9 +578,9 @@ struct PipeMemT {
     cur = buf + (k & 1) * (kStageRows * kTile) + lane;
     ++k;
   }
-  MC_D double a_p(int r) const { MC_CHK(r >= 0 && r < PAS, "sweep-A stage row", r); return cur[r * kTile]; }
-  MC_D double a_tcl() const { return cur[PAS * kTile]; }
-  MC_D double a_gto() const { return cur[(PAS + 1) * kTile]; }
+  MC_D double a_p(int r) const { MC_CHK(r >= 0 && r < an, "sweep-A stage row", r); return cur[r * kTile]; }
+  MC_D double a_tcl() const { return cur[an * kTile]; }
+  MC_D double a_gto() const { return cur[(an + 1) * kTile]; }
   MC_D double b_p(int r) const { MC_CHK(r >= 0 && r < PBS, "sweep-B geometry row", r); return cur[r * kTile]; }
   MC_D double b_s(int r) const { MC_CHK(r >= 0 && r < SL_N, "sweep-B state row", r); return cur[(PBS + r) * kTile]; }
   MC_D double b_w(int r) const { MC_CHK(r >= 0 && r < kWLiveB, "sweep-B work row", r); return cur[(PBS + SL_N + r) * kTile]; }
@@ -806,6 +817,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   // ======================= sweep A: wind and turbulent conductances, top -> bottom (code.R:747-770) =======================
   {
     double sfx = 0, cs = 0;
+    double lglo_up = 0, edo_up = 0;                     // REG: log(gl), ed of the outer node of the layer above
     const int half = (int)nearbyint(m / 2.0);
     for (int i = m; i >= 1; --i) {
       mem.stageA(i);
@@ -836,11 +848,17 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         rdz = (i == 1) ? 2 * idz : idz;
       } else { ex1 = mem.a_p(PA_EX1); ex2 = mem.a_p(PA_EX2); gx0 = mem.a_p(PA_GX0); gx1 = mem.a_p(PA_GX1); rdz = mem.a_p(PA_RDZ); }
       double lz;
-      if (i == m) lz = wcl(lu, ai, ex1, mem.a_p(PA_GLO), mem.a_p(PA_EDO));
+      const double lglo = mem.a_p(PA_GLO), edo = mem.a_p(PA_EDO);
+      if (i == m) lz = wcl(lu, ai, ex1, lglo, edo);
       else {
-        lu = wcl(lu, ai, ex1, mem.a_p(PA_GLO), mem.a_p(PA_EDO));
-        lz = wcl(lu, mem.a_p(PA_A0O) * sqphi, ex2, mem.a_p(PA_GLI), mem.a_p(PA_EDI));                           // Q9
+        // inner node of the layer: its rows, or on the regular grid (below layer m - 1) the outer node of the layer above — the same
+        // height — with ed rescaled from that layer's top to this layer's outer node: zi(i + 1) / zo(i) = (i + 2) / i
+        const double lgli = (!REG || i == m - 1) ? mem.a_p(PA_GLI) : lglo_up;
+        const double edi = (!REG || i == m - 1) ? mem.a_p(PA_EDI) : edo_up * ((double)(i + 2) * rinv_small(i));
+        lu = wcl(lu, ai, ex1, lglo, edo);
+        lz = wcl(lu, mem.a_p(PA_A0O) * sqphi, ex2, lgli, edi);                           // Q9
       }
+      lglo_up = lglo; edo_up = edo;
       uzn = fexp_neg(lz);                               // (clamped below only: lz <= log of the wind above the canopy)
       const double nlu = (lu < -600.0) ? 600.0 : -lu;   // (without the edge term the product can underflow; the exponents stay finite)
       const double e0 = fexp_b(fma(-ai, gx0, nlu)), e1 = fexp_b(fma(-ai, gx1, nlu));      // (gx in [-1, 0])
@@ -933,14 +951,14 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       const double ptc = mem.b_s(SL_TC), ptl = mem.b_s(SL_TLEAF);
       const double uzn = mem.b_w(WL_UZN), gtn = mem.b_w(WL_GTN);
       // leafabs (code.R:31-49) of this layer
-      const double omr = 1 - mem.b_p(PB_REF);
+      const double sref = mem.b_p(PB_SREF), omr = sref * sref;                   // 1 - ref
       double rsw, Rabsn, gvn, ghan, idzb = 0;
       const double Tkc = ptc + 273.15, iTkc = frcp(Tkc);
       {
         double kr[8];
         mem.unpark8(KR_K, kr);
         const double K = kr[KR_K - KR_K], clump = kr[KR_CLUMP - KR_K], dp = kr[KR_DP - KR_K];
-        const double trbc = day ? clumptr(fexp_neg(-(mem.b_p(PB_SPC) * K)), clump) : clumptr(0.0, clump);
+        const double trbc = day ? clumptr(fexp_neg(-((sref * mem.b_p(PB_PC)) * K)), clump) : clumptr(0.0, clump);
         const double trbg = day ? clumptr(fexp_neg(-(mem.b_p(PB_SGC) * K)), clump) : clumptr(0.0, clump);
         const double sunl = day ? clumptr(fexp_neg(-K * mem.b_p(PB_PC)), clump) : clumptr(0.0, clump);
         // code.R:43-46 per unit (1 - ref): Rswin = aRsw / (1 - ref) (code.R:895) is formed first, aRsw = (1 - ref) * Rswin
@@ -1087,7 +1105,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         const double esoil = mem.unpark(KT_ESOIL), ps1 = mem.unpark(KT_PS1);   // (fetched again: not carried over the leaf balance of every layer)
         const double cd1 = (mem.unpark(X_CV) * p0(P0_NFIX + sm)) * (0.5 * its);
         const double icd1 = frcp(cd1);
-        const double aRsw = (1 - mem.b_p(PB_REF)) * rsw;                          // (1 - ref) * Rswin, as formed for Rabs above
+        const double aRsw = (mem.b_p(PB_SREF) * mem.b_p(PB_SREF)) * rsw;        // (1 - ref) * Rswin, as formed for Rabs above
         const double a1 = (1 - refg) * (aRsw * icd1);
         double Xs;
         if (esoil - ean > 0) {
