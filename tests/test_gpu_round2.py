@@ -303,3 +303,47 @@ def test_regular_grid_launch_from_a_state_with_a_moved_node(oracle):
     want2 = oracle.run_transient(inp["veg"], inp["soil"], inp["f"][24:], inp["lat"], inp["lon"], second, M, SM, state=want["state"],
                                  fscale=inp["fs"], foffset=inp["fo"], tsoil=tsoil)
     assert_series_close(got2["series"], want2["series"], "second regular-grid launch")
+
+
+def test_geometry_workspace_follows_new_inputs_between_launches(oracle):
+    """The library re-uses the geometry workspace of the streaming path across run launches (mc_lib.cu, Shard::GeomTag).  Every input it
+    depends on must invalidate it: a new forcing perturbation (only those rows are rewritten), a new run description, new columns.
+    Each continuation is compared with the oracle continuing from the same state with the same inputs."""
+    inp = transient_inputs(oracle, ncol=40, T=72)
+    cfg = make_cfg(spin_steps=30)
+    nospin = make_cfg(spin_steps=0)
+    f = inp["f"]
+
+    def tsoil_of(fs, fo):
+        return f[:, 0].mean() * fs[0] + fo[0]
+
+    ctx = _ctx(inp, cfg)
+    ts0 = tsoil_of(inp["fs"], inp["fo"])
+    ctx.run_transient(0, 24, tsoil=ts0, want_series=False)                       # spin-up + 24 h: fills the workspace
+    ctx.run_transient(24, 30, tsoil=ts0, want_series=False)                      # re-uses it
+    st = ctx.get_state()
+    # (1) a new perturbation between two launches
+    fs2, fo2 = S.forcing_perturbation(40, seed=77)
+    ctx.set_forcing(f, fs2, fo2)
+    got = ctx.run_transient(30, 48, tsoil=ts0, samp_idx=np.arange(40))
+    want = oracle.run_transient(inp["veg"], inp["soil"], f[30:48], inp["lat"], inp["lon"], nospin, M, SM, state=st, fscale=fs2, foffset=fo2,
+                                tsoil=ts0)
+    assert_series_close(got["series"], want["series"], "new perturbation")
+    assert_state_close(ctx.get_state(), want["state"], what="new perturbation")
+    # (2) a new run description (edge distance): the whole workspace is rebuilt
+    cfg2 = make_cfg(spin_steps=30, edgedist=25.0)
+    ctx.set_config(cfg2)
+    st = ctx.get_state()
+    got = ctx.run_transient(48, 60, tsoil=ts0, samp_idx=np.arange(40))
+    want = oracle.run_transient(inp["veg"], inp["soil"], f[48:60], inp["lat"], inp["lon"], make_cfg(spin_steps=0, edgedist=25.0), M, SM, state=st,
+                                fscale=fs2, foffset=fo2, tsoil=ts0)
+    assert_series_close(got["series"], want["series"], "new edge distance")
+    # (3) new columns (another ensemble) with the state carried over by the caller
+    veg2, soil2 = S.ensemble(S.vegp_deciduous(), loam(oracle), 40, M, SM, seed=99)
+    st = ctx.get_state()
+    ctx.set_columns(veg2, soil2, inp["lat"], inp["lon"]); ctx.set_forcing(f, fs2, fo2); ctx.set_state(st)
+    got = ctx.run_transient(60, 72, tsoil=ts0, samp_idx=np.arange(40))
+    want = oracle.run_transient(veg2, soil2, f[60:72], inp["lat"], inp["lon"], make_cfg(spin_steps=0, edgedist=25.0), M, SM, state=st,
+                                fscale=fs2, foffset=fo2, tsoil=ts0)
+    assert_series_close(got["series"], want["series"], "new columns")
+    assert_state_close(ctx.get_state(), want["state"], what="new columns")
