@@ -597,7 +597,6 @@ struct PipeMemT {
 // with Cf = 0.664 * 18.9e-6 * Pr^(1/3) / sqrt(13.3e-6), Cr = 0.54 * 18.9e-6 * Pr^(1/4) / sqrt(13.3e-6).  kA = Cf^2 d, kB = Cr^4 9.81 d^3 and
 // kI = 1.41 / d are column constants (fast_park_constants).  Four square roots on two independent chains and no reciprocal, instead of
 // five and one in a row.  A negative or NaN wind speed loses the comparison as the NaN of sqrt(Re) did.
-constexpr double kGhaCf2 = 9.3684559114155109e-06, kGhaCr4 = 4.3162720585010526e-11;
 MC_HD double gha_fast2(double kA, double kB, double kI, double u, double Tk, double iTk, double ph, double dtc, double c101) {
   const double x = Tk * (1 / 273.15);
   const double r = fsqrt_nz(x);

@@ -368,6 +368,9 @@ MC_HD double gturb(double u, double zu, double z1, double z0, double hgt, double
 }
 // Prandtl number of air in gforcedfree: nu / Dh = 13.3 / 18.9 exactly (both carry the same temperature / pressure factor)
 constexpr double kPrAir = 0.7037037037037037, kCbrtPrAir = 0.8894672162406483;
+// Cf^2 and Cr^4 of the product form of gforcedfree (gha_fast2 in mc_fast.cuh, gha_hour in mc_steady.cuh):
+// Cf = 0.664 * 18.9e-6 * Pr^(1/3) / sqrt(13.3e-6), Cr = 0.54 * 18.9e-6 * Pr^(1/4) / sqrt(13.3e-6)
+constexpr double kGhaCf2 = 9.3684559114155109e-06, kGhaCr4 = 4.3162720585010526e-11;
 MC_HD double gforcedfree(double d, double u, double tc, double dtc, double pk, double dtmin) {
   double Tk = tc + 273.15;
   double ph = phair(tc, pk);

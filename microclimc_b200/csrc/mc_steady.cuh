@@ -22,7 +22,7 @@ struct SteadyArgs {
   const double* season;      // [T] or null
   const double* vegt;        // [T][2m+1][nvt] or null: PAI[m], pLAI[m] (zm0 unused here) per hour (vegp$PAI as m x T matrix, NMR.R:730-735)
   long long nvt;             // 1: shared by all columns, ncol: per column
-  const double* sol;         // [T][13] eot, sin / cos of the declination, dp, ph, ph0, es, eref, cp, (tair + 273.15)^4, gDh, ginu, ggq per hour (k_steady_hour), or null: computed in place
+  const double* sol;         // [T][13] eot, sin / cos of the declination, dp, ph, ph0, es, eref, cp, (tair + 273.15)^4, gS, gT (+ one unused) per hour (k_steady_hour), or null: computed in place
   double reqhgt; int metopen; double windhgt, surfwet;
   double* out;               // [T][7][ncol] or null
   double* stats;             // [6][ncol] (written by the reduce kernel)
@@ -33,7 +33,7 @@ struct SteadyArgs {
 // What an hour's forcing row determines for every column: the date-only solar terms, the diffuse fraction and the molar
 // densities of air at the forcing pressure and at 101.3 kPa (k_steady_hour writes them once per hour; the same expressions
 // run in place when there is no table).
-struct HourPre { SolDay sd; double dp, ph, ph0, es, eref, cp, p4, gDh, ginu, ggq; };   // es = satvap(tair), eref = relhum/100 * es, cp = cpair(tair), p4 = (tair + 273.15)^4
+struct HourPre { SolDay sd; double dp, ph, ph0, es, eref, cp, p4, gS, gT; };   // es = satvap(tair), eref = relhum/100 * es, cp = cpair(tair), p4 = (tair + 273.15)^4
 MC_HD HourPre hour_pre(const double* cr) {
   HourPre h;
   h.sd = sol_day(cr[7]);
@@ -43,12 +43,11 @@ MC_HD HourPre hour_pre(const double* cr) {
   if (dp > 1) dp = 1;
   h.dp = dp; h.ph = phair(cr[0], cr[2]); h.ph0 = phair(cr[0], 101.3);
   h.es = satvap(cr[0]); h.eref = fdiv(cr[1], 100) * h.es; h.cp = cpair(cr[0]); h.p4 = pow4(cr[0] + 273.15);
-  {                                                            // hour-only pieces of gforcedfree (leaf boundary-layer conductance)
+  {                                                            // hour-only pieces of gforcedfree (leaf boundary-layer conductance), see gha_hour
     const double Tk = cr[0] + 273.15;
     const double sc = pow175(Tk * (1 / 273.15)) * fdiv(101.3, cr[2]);
-    h.gDh = 18.9e-6 * sc;
-    h.ginu = frcp(13.3e-6 * sc);
-    h.ggq = frcp(Tk) * (h.ginu * h.ginu);
+    h.gS = h.ph * fsqrt(sc);
+    h.gT = fsqrt(frcp(Tk));
   }
   return h;
 }
@@ -63,7 +62,7 @@ struct SteadyCol {
   double wA, wB, wE;            // .windprofile factors: ln(zi), ln(zo or hgt), exp term
   double gt_lnu, gt_lnh, gtc_lnh;   // gturb pieces for z1 = hgt+2 and z1 = reqhgt
   double gc_top_den, gc_c_den, gc_0_den;   // hgt*(e0-e1) of the three gcanopy calls
-  double gd, gid, gd3a, gd_s, gid_s, gd3a_s;   // leaf dimension d = 0.71 lw (twice that under snow), 1/d, 9.81 d^3 * 5
+  double gd, gid, gd3a, gd_s, gid_s, gd3a_s;   // column-only pieces of gha_hour for the leaf dimension d = 0.71 lw (twice that under snow): Cf^2 d, 1.41 / d, sqrt(Cr^4 9.81 d^3 * 5)
   double ref, sref, kden, k5, emv, slw, trd_u, trd_t, trlw_u;
   double s02, trd02, sls, trdls, cdif;     // PAR (ref 0.2) and Rsw (ref refls) transmissions, cantransdif
   double merid_def;
@@ -128,8 +127,8 @@ struct SteadyCol {
     sref = sqrt(1 - ref);
     kden = cank_den(x);
     k5 = cank(x, 5.0, kden);
-    gd = lw * 0.71; gid = 1 / gd; gd3a = (9.81 * (gd * gd * gd)) * 5;
-    gd_s = lw * 2 * 0.71; gid_s = 1 / gd_s; gd3a_s = (9.81 * (gd_s * gd_s * gd_s)) * 5;
+    { const double d = lw * 0.71; gd = kGhaCf2 * d; gid = 1.41 / d; gd3a = sqrt(kGhaCr4 * ((9.81 * (d * d * d)) * 5)); }
+    { const double d = lw * 2 * 0.71; gd_s = kGhaCf2 * d; gid_s = 1.41 / d; gd3a_s = sqrt(kGhaCr4 * ((9.81 * (d * d * d)) * 5)); }
     emv = 1 - (1 - vegem);
     slw = sqrt(emv);
     trd_u = clumptr(exp(-sref * PAIu), 0.0);            // Q15: clump lands in `merid`; cansw/canlw see clump = 0
@@ -204,14 +203,14 @@ struct SteadyCol {
     double lwin = trlwu * skyem * lwout + (1 - trlwu) * emvv * lwout;
     return aRsw + emvv * lwin;
   }
-  // 1.41 * gforcedfree(d, u, tair, 5, pk, 5) with its hour-only pieces from HourPre and its column-only pieces (d, 1/d,
-  // 9.81 d^3 * 5) from prep(): same formula as mc_phys.cuh gforcedfree in product form (as gha_fast of the streaming kernel)
-  MC_HD static double gha_hour(double d, double id, double d3a, double u, const HourPre& hp) {
-    const double Re = (u * d) * hp.ginu;
-    const double Gr = d3a * hp.ggq;
-    const double gforced = (0.664 * hp.gDh * hp.ph * fsqrt(Re) * kCbrtPrAir) * id;
-    const double gfree = (0.54 * hp.gDh * hp.ph * qroot(Gr * kPrAir)) * id;
-    return 1.41 * ((gforced > gfree) ? gforced : gfree);
+  // 1.41 * gforcedfree(d, u, tair, 5, pk, 5) (mc_phys.cuh gforcedfree) with what the forced and the free branch share taken out of the
+  // maximum, as gha_fast2 of the streaming kernel: with Dh = 18.9e-6 sc, nu = 13.3e-6 sc
+  //   1.41 max(gforced, gfree) = (1.41 / d) ph sqrt(sc) sqrt(max(Cf^2 d u, sqrt(Cr^4 9.81 d^3 5 / Tk)))
+  // and here |dT| = 5 is fixed, so the free-convection term is a column-only factor cB = sqrt(Cr^4 9.81 d^3 5) times an hour-only one
+  // gT = sqrt(1 / Tk): one square root per call instead of three.  cA = Cf^2 d, cI = 1.41 / d (prep()); gS = ph sqrt(sc) (HourPre).
+  MC_HD static double gha_hour(double cA, double cI, double cB, double u, const HourPre& hp) {
+    const double A = cA * u, B = cB * hp.gT;
+    return (cI * hp.gS) * fsqrt((A > B) ? A : B);
   }
   // 1 / (1/a + 1/b) as a*b / (a+b): one division; a == 0 (closed stomata at night) still gives 0 as the IEEE form does
   MC_HD static double hpar(double a, double b) { return fdiv(a * b, a + b); }
@@ -284,7 +283,6 @@ struct SteadyCol {
     const double tair = cr[0], relhum = cr[1], pk = cr[2], swrad = cr[4], skyem = cr[6];
     const double u2 = wind2m(A, cr[3], PAIt);
     const double uf = fdiv(0.4 * u2, lnuf);
-    const double tk = tair + 273.15;
     double Rlw = (1 - skyem) * kSb * vegem * hp.p4;
     const double Hh = 0.2 * ((1 - 0.23) * swrad - Rlw);
     double psi_m, psi_h;
@@ -405,7 +403,6 @@ struct SteadyCol {
     double K_l, mul;
     cank2_sh(x, sa_l, kden, k5, K_l, mul);       // sa_l, sa: sin(solar altitude), see mc_phys.cuh
     const double emv85 = 1 - (1 - 0.85);
-    const double tk = tair + 273.15;
     double tz, tleaf, rh, Rsw, Rlw;
     if (reqhgt >= hgt) {
       double gt0 = gcan_apply(l_m_s, iwmean, ph, uh, a1, gcs_top_den);
@@ -494,7 +491,7 @@ MC_HD void steady_column(const SteadyArgs& A, long long c, int chunk, int nchunk
     if (A.sol) {
       const double* h = A.sol + t * 13;
       hp.sd.eot = h[0]; hp.sd.sdec = h[1]; hp.sd.cdec = h[2]; hp.dp = h[3]; hp.ph = h[4]; hp.ph0 = h[5];
-      hp.es = h[6]; hp.eref = h[7]; hp.cp = h[8]; hp.p4 = h[9]; hp.gDh = h[10]; hp.ginu = h[11]; hp.ggq = h[12];
+      hp.es = h[6]; hp.eref = h[7]; hp.cp = h[8]; hp.p4 = h[9]; hp.gS = h[10]; hp.gT = h[11];
     } else hp = hour_pre(cr);
     double o[7];
     if (nm[2] > 0) {                                             // NMR.R:873-883: snow rows come from .runmodelsnow
