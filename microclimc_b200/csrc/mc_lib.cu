@@ -150,7 +150,7 @@ __global__ void k_steady_hour(long long T, const double* clim, double* out) {
   const HourPre h = hour_pre(clim + t * 9);
   double* o = out + t * 13;
   o[0] = h.sd.eot; o[1] = h.sd.sdec; o[2] = h.sd.cdec; o[3] = h.dp; o[4] = h.ph; o[5] = h.ph0;
-  o[6] = h.es; o[7] = h.eref; o[8] = h.cp; o[9] = h.p4; o[10] = h.gS; o[11] = h.gT; o[12] = 0.0;
+  o[6] = h.es; o[7] = h.eref; o[8] = h.cp; o[9] = h.p4; o[10] = h.gS; o[11] = h.gT; o[12] = h.lpk;
 }
 __global__ void k_steady_reduce(long long ncol, int nchunk, long long T, const double* part, double* stats) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;

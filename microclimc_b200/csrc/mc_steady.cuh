@@ -22,7 +22,7 @@ struct SteadyArgs {
   const double* season;      // [T] or null
   const double* vegt;        // [T][2m+1][nvt] or null: PAI[m], pLAI[m] (zm0 unused here) per hour (vegp$PAI as m x T matrix, NMR.R:730-735)
   long long nvt;             // 1: shared by all columns, ncol: per column
-  const double* sol;         // [T][13] eot, sin / cos of the declination, dp, ph, ph0, es, eref, cp, (tair + 273.15)^4, gS, gT (+ one unused) per hour (k_steady_hour), or null: computed in place
+  const double* sol;         // [T][13] eot, sin / cos of the declination, dp, ph, ph0, es, eref, cp, (tair + 273.15)^4, gS, gT, lpk per hour (k_steady_hour), or null: computed in place
   double reqhgt; int metopen; double windhgt, surfwet;
   double* out;               // [T][7][ncol] or null
   double* stats;             // [6][ncol] (written by the reduce kernel)
@@ -33,7 +33,7 @@ struct SteadyArgs {
 // What an hour's forcing row determines for every column: the date-only solar terms, the diffuse fraction and the molar
 // densities of air at the forcing pressure and at 101.3 kPa (k_steady_hour writes them once per hour; the same expressions
 // run in place when there is no table).
-struct HourPre { SolDay sd; double dp, ph, ph0, es, eref, cp, p4, gS, gT; };   // es = satvap(tair), eref = relhum/100 * es, cp = cpair(tair), p4 = (tair + 273.15)^4
+struct HourPre { SolDay sd; double dp, ph, ph0, es, eref, cp, p4, gS, gT, lpk; };   // lpk = latent heat of vaporisation (J / mol) / pk   // es = satvap(tair), eref = relhum/100 * es, cp = cpair(tair), p4 = (tair + 273.15)^4
 MC_HD HourPre hour_pre(const double* cr) {
   HourPre h;
   h.sd = sol_day(cr[7]);
@@ -49,6 +49,7 @@ MC_HD HourPre hour_pre(const double* cr) {
     h.gS = h.ph * fsqrt(sc);
     h.gT = fsqrt(frcp(Tk));
   }
+  h.lpk = fdiv(-42.575 * cr[0] + 44994, cr[2]);
   return h;
 }
 
@@ -58,8 +59,8 @@ struct SteadyCol {
   double hgt, x, lw, cd, refls, refw, refg, vegem, gsmax, q50, clump, iwmean, soilb, psi_e, Smax, lat, lon, slat, clat;
   double PAIb[MM + 2], pLAIb[MM + 2];
   // prepared (column + season)
-  double PAIt, LAI, PAIu, d, zm3, zm4, lnuf, lnh3, a, l_m, La, leafdens;
-  double wA, wB, wE;            // .windprofile factors: ln(zi), ln(zo or hgt), exp term
+  double PAIt, LAI, PAIu, d, zm3, zm4, lnuf, ilnuf, lnh3, a, l_m, La, leafdens;
+  double wA, wB, wE, iwA, iwA1; // .windprofile factors: ln(zi), ln(zo or hgt), exp term; 1 / ln(zi) (and of the snow-surface variant)
   double gt_lnu, gt_lnh, gtc_lnh;   // gturb pieces for z1 = hgt+2 and z1 = reqhgt
   double gc_top_den, gc_c_den, gc_0_den;   // hgt*(e0-e1) of the three gcanopy calls
   double gd, gid, gd3a, gd_s, gid_s, gd3a_s;   // column-only pieces of gha_hour for the leaf dimension d = 0.71 lw (twice that under snow): Cf^2 d, 1.41 / d, sqrt(Cr^4 9.81 d^3 * 5)
@@ -110,12 +111,12 @@ struct SteadyCol {
     d = zeroplanedis(hgt, PAIt);
     zm3 = roughlength_d(hgt, PAIt, d, 0.003);
     zm4 = roughlength_d(hgt, PAIt, d, 0.004);
-    lnuf = log((2 + hgt - d) / zm3);
+    lnuf = log((2 + hgt - d) / zm3); ilnuf = 1 / lnuf;
     lnh3 = log((hgt - d) / zm3); if (lnh3 < 0.55) lnh3 = 0.55;
     l_m = mixinglength(hgt, PAIt);
     a = attencoef_base(hgt, PAIt, cd, iwmean, l_m) * sqrt(1.0);
     leafdens = PAIt / hgt;
-    wind_factors(hgt + 2, reqhgt, a, hgt, d, zm4, wA, wB, wE);
+    wind_factors(hgt + 2, reqhgt, a, hgt, d, zm4, wA, wB, wE); iwA = 1 / wA;
     gturb_factors(hgt + 2, hgt + 2, hgt, d, zm4, gt_lnu, gt_lnh);
     { double dum; gturb_factors(hgt + 2, reqhgt, hgt, d, zm4, dum, gtc_lnh); }
     gc_top_den = gc_den(hgt, 0, a);
@@ -148,7 +149,7 @@ struct SteadyCol {
     a1 = attencoef_base(hgt, PAIt_s, cd, iwmean, l_m_s) * sqrt(1.0);
     { double lm0 = mixinglength(hgt, 0.0); a2 = attencoef_base(hgt, 0.0, cd, iwmean, lm0) * sqrt(1.0); }
     { double zm4s = roughlength_d(hgt, PAIt_s, d_s, 0.004);
-      wind_factors(hgt + 2, reqhgt, a1, hgt, d_s, zm4s, wA1, wB1, wE1);
+      wind_factors(hgt + 2, reqhgt, a1, hgt, d_s, zm4s, wA1, wB1, wE1); iwA1 = 1 / wA1;
       gturb_factors(hgt + 2, hgt + 2, hgt, d_s, zm4s, gts_lnu, gts_lnh);
       double dum; gturb_factors(hgt + 2, reqhgt, hgt, d_s, zm4s, dum, gtcs_lnh); }
     { double l2 = log((reqhgt - 0.0) / 0.004); if (l2 < 0.55) l2 = 0.55; wB2 = l2; }
@@ -169,6 +170,11 @@ struct SteadyCol {
     if (zo >= h) { double l2 = log((zo - dd) / zmm); if (l2 < 0.55) l2 = 0.55; fB = l2; fE = -1.0; }
     else { double l2 = log((h - dd) / zmm); if (l2 < 0.55) l2 = 0.55; fB = l2; fE = exp(av * (zo / h) - 1); }   // Q14
   }
+  // the same with the column-only reciprocal 1 / fA given: ((0.4 ui) / fA / 0.4) fB = ui (1 / fA) fB up to rounding
+  MC_HD static double wind_apply_r(double ui, double ifA, double fB, double fE) {
+    const double uo = (ui * ifA) * fB;
+    return fE < 0 ? uo : uo * fE;
+  }
   MC_HD static double wind_apply(double ui, double fA, double fB, double fE) {
     double uf = fdiv(0.4 * ui, fA);
     double uo = fdiv(uf, 0.4) * fB;
@@ -182,9 +188,8 @@ struct SteadyCol {
   }
   MC_HD static double gturb_apply(double u, double lnu, double lnh, double ph, double psi_m, double psi_h) {
     double ln = lnu + psi_m; if (!(ln >= 0.55)) ln = 0.55;
-    double uf = fdiv(0.4 * u, ln);
     double den = lnh + psi_h; if (den < 0.25 * lnh) den = 0.25 * lnh;
-    return fdiv(0.4 * ph * uf, den);
+    return fdiv((0.4 * 0.4) * ph * u, ln * den);                  // 0.4 ph uf / den with uf = 0.4 u / ln: one division
   }
   // gcanopy with tc1 == tc0 (free-convection floor is exactly 0)
   MC_HD static double gcan_apply(double lmix, double iw, double ph, double uh, double av, double den) {
@@ -231,13 +236,14 @@ struct SteadyCol {
     double tle = tair + fdiv(0.5 * Rnet, cp * gha);
     double wgt1 = leafd < 1 ? leafd / 2 : 1 - fdiv(0.5, leafd);
     double tapprox = wgt1 * tle + (1 - wgt1) * tair;
-    double delta = fdiv(4098 * tetens(tapprox), sq(tapprox + 237.3));
+    const double r237 = frcp(tapprox + 237.3);                    // Tetens and its slope share the reciprocal
+    double delta = (4098 * (0.6108 * fexp_b((17.27 * tapprox) * r237))) * (r237 * r237);
     double g3 = gs + gv;
     const double ig3 = frcp(g3);
     double ae = (gtt * eref + gt0 * esoil + gv * es) * ig3;
     double be = (gv * delta) * ig3;
     double bH = gha * cp;
-    double lg = fdiv((-42.575 * tair + 44994) * gv, pk);
+    double lg = hp.lpk * gv;
     double aX = lg * (surfwet * es - ae);
     double bX = lg * (surfwet * delta - be);
     if (aX < 0) aX = 0;
@@ -282,7 +288,7 @@ struct SteadyCol {
     const double reqhgt = A.reqhgt;
     const double tair = cr[0], relhum = cr[1], pk = cr[2], swrad = cr[4], skyem = cr[6];
     const double u2 = wind2m(A, cr[3], PAIt);
-    const double uf = fdiv(0.4 * u2, lnuf);
+    const double uf = (0.4 * u2) * ilnuf;
     double Rlw = (1 - skyem) * kSb * vegem * hp.p4;
     const double Hh = 0.2 * ((1 - 0.23) * swrad - Rlw);
     double psi_m, psi_h;
@@ -291,8 +297,8 @@ struct SteadyCol {
     if (psi_h > 2.5) psi_h = 2.5;
     if (psi_m < -2.5) psi_m = -2.5;
     if (psi_h < -2.5) psi_h = -2.5;
-    const double uz = wind_apply(u2, wA, wB, wE);
-    const double uh = fdiv(uf, 0.4) * lnh3;
+    const double uz = wind_apply_r(u2, iwA, wB, wE);
+    const double uh = (uf * 2.5) * lnh3;
     double dp = hp.dp;
     const SolDay& sd = hp.sd;
     const double ph = hp.ph;
@@ -382,7 +388,7 @@ struct SteadyCol {
     const double dd = above ? d_s : snowdep - 0.003;
     double hgt2 = above ? hgt : snowdep;
     double uz;
-    if (above) uz = wind_apply(u2, wA1, wB1, wE1);
+    if (above) uz = wind_apply_r(u2, iwA1, wB1, wE1);
     else {
       double l = flog(fdiv(snowdep + 2 - 0.0, 0.004)); if (l < 0.55) l = 0.55;
       uz = wind_apply(u2, l, wB2, -1.0);
@@ -491,7 +497,7 @@ MC_HD void steady_column(const SteadyArgs& A, long long c, int chunk, int nchunk
     if (A.sol) {
       const double* h = A.sol + t * 13;
       hp.sd.eot = h[0]; hp.sd.sdec = h[1]; hp.sd.cdec = h[2]; hp.dp = h[3]; hp.ph = h[4]; hp.ph0 = h[5];
-      hp.es = h[6]; hp.eref = h[7]; hp.cp = h[8]; hp.p4 = h[9]; hp.gS = h[10]; hp.gT = h[11];
+      hp.es = h[6]; hp.eref = h[7]; hp.cp = h[8]; hp.p4 = h[9]; hp.gS = h[10]; hp.gT = h[11]; hp.lpk = h[12];
     } else hp = hour_pre(cr);
     double o[7];
     if (nm[2] > 0) {                                             // NMR.R:873-883: snow rows come from .runmodelsnow
