@@ -434,8 +434,9 @@ MC_HD double solsin_pre(double lt, double lon, double merid, double dst, const S
 }
 // cank2 on sh: tan(90 deg - sa) = cos(sa) / sin(sa)
 MC_HD void cank2_sh(double x, double sh, double den, double K5, double& K, double& Kc) {
-  const double cot = fdiv(fsqrt(1 - sh * sh), sh);
-  const double Kf = fdiv(fsqrt(x * x + cot * cot), den);
+  // sqrt(x^2 + cot^2) with cot^2 = (1 - sh^2) / sh^2 is sqrt((x^2 - 1) sh^2 + 1) / sh for sh > 0 (the only case Kf is selected in):
+  // one square root and one division instead of two and two
+  const double Kf = fdiv(fsqrt(fma(x * x - 1, sh * sh, 1.0)), sh * den);
   K = (sh > 0) ? Kf : 0.0;
   Kc = (sh < kSin5) ? K5 : Kf;
 }
