@@ -24,6 +24,7 @@
 // The same code builds for the host (tests/hostdbg) with a direct-memory accessor, which is how its arithmetic is
 // checked against the CPU oracle without a GPU.
 #pragma once
+#include <type_traits>
 #include "mc_driver.cuh"
 
 namespace mc {
@@ -99,7 +100,8 @@ static_assert(kStageRowsB <= kStageRows, "sweep-B stage exceeds the stage buffer
 static_assert(kG0Rows <= kStageRows && kGRow0 + kG1aRows <= kStageRows && kGRow0 + kG1bRows <= kStageRows && PA_N + 2 <= kGRow0, "scalar groups do not fit the idle stage rows");
 constexpr int kG2Spill = kStageRowsB;              // first stage row no sweep-B stage uses
 static_assert(3 * 10 <= kStageRows + (kStageRows - kG2Spill), "the solve's soil rows do not fit the idle stage rows");
-constexpr int kNG = 6;                            // merged air layers handled in the streaming form (more: general path)
+constexpr int kNG = 6;                            // merged air layers the solve holds in the idle stage buffers (the common case: hourly steps give 1-5)
+constexpr int kNGW = 20;                          // ... and in the lane's own (thread-private) scratch when a step has more: the wide solve
 
 struct FastLayout {
   int m, sm;
@@ -616,6 +618,20 @@ MC_HD double gha_fast2(double kA, double kB, double kI, double u, double Tk, dou
 enum { SK0 = 0, SCD0 = 17, STC0 = 33, VK0 = 0, VCD0 = 8, VTC0 = 15, NT20 = 9, NYT0 = 17, NYE0 = 36 };
 static_assert(2 * kCL <= NT20 + 1 && NYE0 + 1 >= kStageRows + 2 * kCL, "sweep-C stage rows overlap the node arrays");
 static_assert(STC0 + kNG + 10 + 2 < 2 * kStageRows, "solver scratch exceeds the two stage buffers");
+struct ScrMapStage { static constexpr int K0 = SK0, CD0 = SCD0, TC0 = STC0, vK0 = VK0, vCD0 = VCD0, vTC0 = VTC0, T20 = NT20, YT0 = NYT0, YE0 = NYE0; };
+// The wide solve: a step in which a lane closes more than kNG merged layers (calm, stably stratified hours) used to drop the column to the
+// general kernel, whose redo launch costs 38 ms per 168-step launch whatever the number of such columns (one thread per column, serial).
+// Such a lane now runs the same solve code on arrays sized for up to m merged layers in thread-private memory (1.9 KB of stack, touched
+// only then); the warp's other lanes idle through it.  Same arithmetic, same order.
+struct ScrMapLane { static constexpr int K0 = 0, CD0 = 32, TC0 = 63, vK0 = 96, vCD0 = 118, vTC0 = 139, T20 = 162, YT0 = 185, YE0 = 208, N = 232; };
+static_assert(ScrMapLane::CD0 > kNGW + 10 + 1 && ScrMapLane::TC0 - ScrMapLane::CD0 > kNGW + 10 && ScrMapLane::vK0 - ScrMapLane::TC0 > kNGW + 10 + 2 &&
+              ScrMapLane::vCD0 - ScrMapLane::vK0 > kNGW + 1 && ScrMapLane::vTC0 - ScrMapLane::vCD0 > kNGW && ScrMapLane::T20 - ScrMapLane::vTC0 > kNGW + 2 &&
+              ScrMapLane::YT0 - ScrMapLane::T20 > kNGW + 2 && ScrMapLane::YE0 - ScrMapLane::YT0 > kNGW + 2 && ScrMapLane::N - ScrMapLane::YE0 > kNGW + 2, "lane scratch map");
+struct LaneScr {
+  double a[ScrMapLane::N];
+  MC_HD double scr_get(int idx) const { return a[idx]; }
+  MC_HD void scr_put(int idx, double v) { a[idx] = v; }
+};
 
 // Thomas (code.R:94-125) in fused form: one forward pass forms the right-hand side on the fly and eliminates, one backward
 // pass substitutes and applies the old-stencil limits (quirk Q11).  Coefficients come from the scratch rows and are replaced in
@@ -933,8 +949,8 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   MC_TICK(2);
   // ======================= sweep B: leafabs + leaftemp, bottom -> top, with the merged-layer sums =======================
   // layermerge / layeraverage bookkeeping (code.R:772, 814): closed groups 1..ng and the open one
-  int ng = 0, glo[kNG + 2], ghi[kNG + 2];
-  double gw[kNG + 2], gtc[kNG + 2], gVo[kNG + 2], gea[kNG + 2], gX[kNG + 2];
+  int ng = 0, glo[kNGW + 2], ghi[kNGW + 2];
+  double gw[kNGW + 2], gtc[kNGW + 2], gVo[kNGW + 2], gea[kNGW + 2], gX[kNGW + 2];
   const bool runB = run;
   {
     const int selHb = (int)p0(P0_SELH);
@@ -1127,11 +1143,10 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         oR += rn; oC += phz; open = true;
         ow += wi; otc += wi * ptc; oVo += wi * (eaj * ku[KU_IPPK - KU_LAMBDA]); oea += wi * ean; oX += wi * (tnl - ptc);
         if (timestep <= oC * oR) {                                               // timestep / sum(1/gt) <= sum(ph*zth)
-          if (ng < kNG) {
+          if (ng < kNGW) {             // (at most m <= kNGW groups can close)
             ++ng;
             glo[ng] = olo; ghi[ng] = i; gw[ng] = ow; gtc[ng] = otc; gVo[ng] = oVo; gea[ng] = oea; gX[ng] = oX;
-          } else fastok = false;     // more merged layers than the solve holds: the column leaves the streaming form (the rest of
-                                     // this step only writes its own, now dead, rows; never beyond the solver's storage)
+          }
           olo = i + 1; oR = 0; oC = 0; ow = 0; otc = 0; oVo = 0; oea = 0; oX = 0; open = false;
         }
       }
@@ -1165,6 +1180,8 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
   // per solve for both branches (equilibrium = no merged air node), so warps with mixed lanes do not run the solves twice.
   int nn = 2, mgx = 0;
   double TX, y1t = 0, y2t = 0, y1e = 0, y2e = 0, tns1_raw = 0, tsel_raw = 0;
+  const bool wide = ng > kNG;                         // this lane's step has more merged layers than the stage-buffer solve holds
+  LaneScr lscr;                                       // (thread-private; touched only by wide lanes; its node arrays are read by sweep C)
   {
     double x0[8], x1[8], x2[8];
     mem.unpark8(X_TAIRN, x0); mem.unpark8(X_PPK, x1); mem.unpark8(X_TSOILP, x2);
@@ -1177,9 +1194,13 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
     TX = TT + fdiv(pha, gtncap) * 2;
     mem.g2_wait();                                     // the soil rows were fetched behind the last sweep-B stage
     if (!MC_SKIP(4)) {
+      // the solve on storage `scr` (stage-buffer rows, or the lane's own arrays) with row map MAP and capacity CAP merged layers
+      auto solve = [&](auto& scr, auto map_tag, auto cap_tag) {
+      using MAP = decltype(map_tag);
+      constexpr int CAP = decltype(cap_tag)::value;
       mgx = (ng > 1) ? ng : 0;
       const int mg = mgx, N = mg + sm;
-      double ltc[kNG + 2], lgt[kNG + 3], lz[kNG + 4], lVo[kNG + 2], lea[kNG + 2], lph[kNG + 2], lTT[kNG + 2], xv[kNG + 3], vX[kNG + 2], Yt[kNG + 3];
+      double ltc[CAP + 2], lgt[CAP + 3], lz[CAP + 4], lVo[CAP + 2], lea[CAP + 2], lph[CAP + 2], lTT[CAP + 2], xv[CAP + 3], vX[CAP + 2], Yt[CAP + 3];
       {                                                  // soil nodes FIRST: their rows (G2) sit in stage rows the scratch stores below reuse;
                                                          // all row loads, then the scratch stores (own lane only: no cross-lane hazard)
         double rk[MS], rc[MS], rt[MS];
@@ -1187,7 +1208,7 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         for (int j = 1; j <= MS; ++j) if (j <= sm) { rk[j - 1] = mem.g2(j - 1); rc[j - 1] = mem.g2(sm + (j - 1)); rt[j - 1] = mem.g2(2 * sm + (j - 1)); }
 #pragma unroll
         for (int j = 1; j <= MS; ++j) if (j <= sm) {
-          mem.scr_put(SK0 + mg + 1 + j, lam * rk[j - 1]); mem.scr_put(SCD0 + mg + j, (Cv * rc[j - 1]) * i2ts); mem.scr_put(STC0 + 1 + mg + j, rt[j - 1]);
+          scr.scr_put(MAP::K0 + mg + 1 + j, lam * rk[j - 1]); scr.scr_put(MAP::CD0 + mg + j, (Cv * rc[j - 1]) * i2ts); scr.scr_put(MAP::TC0 + 1 + mg + j, rt[j - 1]);
         }
       }
       if (mg > 0) {                                   // layeraverage (code.R:814) and the air part of the system (code.R:815-826)
@@ -1226,23 +1247,23 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
           const double cda = lcp * lph[g] * (1 - lvd) * (lz[g + 2] - lz[g]) / 2 * timestep;       // Q10
           double ka = lgt[g] * lcp;
           if (ka > cda) ka = cda;
-          mem.scr_put(SK0 + mg + 2 - g, ka); mem.scr_put(SCD0 + mg + 1 - g, cda); mem.scr_put(STC0 + 1 + mg + 1 - g, ltc[g]);
+          scr.scr_put(MAP::K0 + mg + 2 - g, ka); scr.scr_put(MAP::CD0 + mg + 1 - g, cda); scr.scr_put(MAP::TC0 + 1 + mg + 1 - g, ltc[g]);
         }
-        mem.scr_put(SK0 + 1, lgt[mg + 1] * cpair(tabove));
+        scr.scr_put(MAP::K0 + 1, lgt[mg + 1] * cpair(tabove));
       } else {
-        mem.scr_put(SK0 + 1, frcp(cs) * cpair(tabove));   // one lumped conductance for the lower half of the canopy (code.R:856-857)
+        scr.scr_put(MAP::K0 + 1, frcp(cs) * cpair(tabove));   // one lumped conductance for the lower half of the canopy (code.R:856-857)
       }
       xv[mg + 1] = Xs;
-      mem.scr_put(STC0 + 1, tabove); mem.scr_put(STC0 + N + 2, tsoilp);
-      thomas_s(mem, SK0, SCD0, STC0, N, fc.tsoil, tcan, cfg.n, xv, mg + 1);
+      scr.scr_put(MAP::TC0 + 1, tabove); scr.scr_put(MAP::TC0 + N + 2, tsoilp);
+      thomas_s(scr, MAP::K0, MAP::CD0, MAP::TC0, N, fc.tsoil, tcan, cfg.n, xv, mg + 1);
       // STC(2..N+1) now holds tn2 (code.R:829); tnsoil[j] = tn2[mg+1+j]
-      const double tns1 = mem.scr_get(STC0 + mg + 2);
+      const double tns1 = scr.scr_get(MAP::TC0 + mg + 2);
       double Vsoil = 0, Vair = 0;
       if (mg > 0) {
         // tnair = rev(tn2[1:(mg+2)]) = (soil 1, air bottom..top, tcan); ThomasV (code.R:153-169) on reversed arrays
         nn = mg + 2;
         Yt[mg + 2] = tcan;
-        for (int g = 1; g <= mg + 1; ++g) Yt[g] = mem.scr_get(STC0 + mg + 3 - g);
+        for (int g = 1; g <= mg + 1; ++g) Yt[g] = scr.scr_get(MAP::TC0 + mg + 3 - g);
         double rhs = soilrh(fc.theta, p0(P0_SOILB), p0(P0_PSIE), p0(P0_SMAX), tns1); if (rhs > 1) rhs = 1;
         double rhsp = soilrh(fc.thetap, p0(P0_SOILB), p0(P0_PSIE), p0(P0_SMAX), ps1); if (rhsp > 1) rhsp = 1;
         const double ipkn = frcp(pkn), ippk = frcp(ppk);
@@ -1250,27 +1271,27 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         const double eap = tetens(tairp) * fdiv(relhump, 100);
         Vsoil = (tetens(tns1) * rhs) * ipkn;
         const double easp = tetens(tsoilp) * rhsp;                               // Q5
-        mem.scr_put(VTC0 + 1, eap * ippk); mem.scr_put(VTC0 + mg + 2, easp * ippk);
-        for (int g = 1; g <= mg; ++g) mem.scr_put(VTC0 + 1 + g, lVo[mg + 1 - g]);
+        scr.scr_put(MAP::vTC0 + 1, eap * ippk); scr.scr_put(MAP::vTC0 + mg + 2, easp * ippk);
+        for (int g = 1; g <= mg; ++g) scr.scr_put(MAP::vTC0 + 1 + g, lVo[mg + 1 - g]);
         for (int g = 1; g <= mg + 1; ++g) {
           double gt2 = lgt[g];
           if (g <= mg) { const double gtmx = fdiv(lph[g], lz[g + 1] - lz[g]) * (2 * timestep); if (gt2 > gtmx) gt2 = gtmx; }
-          mem.scr_put(VK0 + mg + 2 - g, gt2);
+          scr.scr_put(MAP::vK0 + mg + 2 - g, gt2);
         }
         for (int g = 1; g <= mg; ++g) {
-          mem.scr_put(VCD0 + mg + 1 - g, phair(Yt[g + 1], pkn));
+          scr.scr_put(MAP::vCD0 + mg + 1 - g, phair(Yt[g + 1], pkn));
           double vf = (lea[g] * ipkn) - lVo[g]; if (vf < 0) vf = 0;
           vX[g] = vf;                                                            // Q6: not reversed
         }
       }
-      thomas_s(mem, VK0, VCD0, VTC0, mg, Vsoil, Vair, cfg.n, vX, mg);           // (lanes without merged layers idle through it)
+      thomas_s(scr, MAP::vK0, MAP::vCD0, MAP::vTC0, mg, Vsoil, Vair, cfg.n, vX, mg);           // (lanes without merged layers idle through it)
       // tnsoil (code.R:830, 859): nodes 2..sm go straight to the state rows (before the node arrays below reuse their scratch
       // rows); node 1 passes the limits at the end of the step first.  The node nearest to -reqhgt is kept for the harvest.
       {
         const int ss = (int)p0(P0_SELS);
         double tsel = tns1;
         for (int j = 2; j <= sm; ++j) {
-          const double v = mem.scr_get(STC0 + mg + 1 + j);
+          const double v = scr.scr_get(MAP::TC0 + mg + 1 + j);
           if (runB) sput(L.soiltc(j), v);
           if (j == ss) tsel = v;
         }
@@ -1278,17 +1299,20 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
       }
       if (mg > 0) {
         // Vn = rev(vn): Ye[g] = vn[mg+3-g] with vn[1] = Vair, vn[mg+2] = Vsoil; mole fractions, scaled by pk after the interpolation
-        double Ye[kNG + 3];
+        double Ye[CAP + 3];
         Ye[1] = Vsoil; Ye[mg + 2] = Vair;
-        for (int g = 2; g <= mg + 1; ++g) Ye[g] = mem.scr_get(VTC0 + mg + 3 - g);
+        for (int g = 2; g <= mg + 1; ++g) Ye[g] = scr.scr_get(MAP::vTC0 + mg + 3 - g);
         // node arrays for sweep C, in scratch rows the C stages do not touch
-        for (int g = 1; g <= mg + 2; ++g) { mem.scr_put(NYT0 + g, Yt[g]); mem.scr_put(NYE0 + g, Ye[g]); }
-        mem.scr_put(NT20 + 1, 0.0);
-        for (int g = 1; g <= mg; ++g) mem.scr_put(NT20 + g + 1, lTT[g]);
-        mem.scr_put(NT20 + mg + 2, TX);
+        for (int g = 1; g <= mg + 2; ++g) { scr.scr_put(MAP::YT0 + g, Yt[g]); scr.scr_put(MAP::YE0 + g, Ye[g]); }
+        scr.scr_put(MAP::T20 + 1, 0.0);
+        for (int g = 1; g <= mg; ++g) scr.scr_put(MAP::T20 + g + 1, lTT[g]);
+        scr.scr_put(MAP::T20 + mg + 2, TX);
       } else {
         y1t = tns1; y2t = tcan; y1e = esoil; y2e = eamn;                           // eair = (relhum/100)*tetens(tcan), code.R:863
       }
+      };
+      if (!wide) solve(mem, ScrMapStage{}, std::integral_constant<int, kNG>{});
+      else solve(lscr, ScrMapLane{}, std::integral_constant<int, kNGW>{});
     }
   }
   mem.park(KT_TNS1, tns1_raw); mem.park(KT_TSEL, tsel_raw); mem.park_done();
@@ -1316,10 +1340,12 @@ MC_HD bool fast_step(Mem& mem, const Forcing& fc, const SolDay& sday, const RunC
         ea2 = (1 - wgt) * y1e + wgt * y2e;
       } else if (!(v >= 0.0) || !(v <= TX)) { tnn = NAN; ea2 = NAN; }
       else {                                            // layerinterp: R approx(), bisection + linear (code.R:846-847)
+        auto node = [&](int fast0, int wide0, int idx) { return wide ? lscr.a[wide0 + idx] : mem.scr_get(fast0 + idx); };
         int a = 1, b = nn;
-        while (a < b - 1) { const int ab = (a + b) / 2; if (v < mem.scr_get(NT20 + ab)) b = ab; else a = ab; }
-        const double T2a = mem.scr_get(NT20 + a), T2b = mem.scr_get(NT20 + b);
-        const double Yta = mem.scr_get(NYT0 + a), Ytb = mem.scr_get(NYT0 + b), Yea = mem.scr_get(NYE0 + a), Yeb = mem.scr_get(NYE0 + b);
+        while (a < b - 1) { const int ab = (a + b) / 2; if (v < node(NT20, ScrMapLane::T20, ab)) b = ab; else a = ab; }
+        const double T2a = node(NT20, ScrMapLane::T20, a), T2b = node(NT20, ScrMapLane::T20, b);
+        const double Yta = node(NYT0, ScrMapLane::YT0, a), Ytb = node(NYT0, ScrMapLane::YT0, b);
+        const double Yea = node(NYE0, ScrMapLane::YE0, a), Yeb = node(NYE0, ScrMapLane::YE0, b);
         if (v == T2b) { tnn = Ytb; ea2 = Yeb * pkn; }
         else if (v == T2a) { tnn = Yta; ea2 = Yea * pkn; }
         else {
