@@ -1500,6 +1500,7 @@ MC_HD RunCfg effective_cfg(const TransientArgs& t, double hgt, bool spin) {
 // is hgt / 2 per column, never NA.)
 MC_HD bool fast_regular_grid(const TransientArgs& t, bool spin) {
   if (t.charmode) return false;
+  if (!(t.cfg.timestep >= 3600.0)) return false;      // (shorter steps reach leaftemp's transient balances, which only the general instantiation has)
   const RunCfg c = effective_cfg(t, 1.0, spin);
   return !(c.reqhgt == c.reqhgt);
 }

@@ -356,16 +356,17 @@ template <class F> int dispatch_ms(int m, int sm, F&& f) {
 }
 inline unsigned nblocks(long long n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
-// The streaming kernels cover time-invariant PAI, the small template (m <= 20, sm <= 10) and hourly or coarser time steps (the
-// reference's use: hourly climdata).  With shorter steps column-steps with more merged air layers than the streaming solve holds
-// become common (host build, 96 steps of 64 columns: 11 % of the columns at 1800 s, all of them at 900 s), and a column that meets
-// one is redone from the start; everything else runs the general one-column-per-thread kernel.  Measurement builds (make ABLATE=1) can force the general kernel with MC_FORCE_GENERAL=1.
+// The streaming kernels cover time-invariant PAI, depth-uniform soil moisture and the small template (6 < m <= 20, sm <= 10), at any time
+// step: hourly or longer steps without an output height run the regular-grid instantiation, everything else the general instantiation
+// (all per-layer rows staged, leaftemp's transient balances included); steps with more than six merged air layers (the rule at short
+// steps) are solved by the wide solve.  The rest runs the general one-column-per-thread kernel.  Measurement builds (make ABLATE=1) can
+// force the general kernel with MC_FORCE_GENERAL=1.
 bool fast_eligible(const TransientArgs& a) {
 #ifdef MC_ABLATE
   const char* e = getenv("MC_FORCE_GENERAL");
   if (e && e[0] == '1') return false;
 #endif
-  return !a.season && !a.vegt && !a.thetaz && a.m <= 20 && a.m > kNG && a.sm <= 10 && a.cfg.timestep >= 3600.0;
+  return !a.season && !a.vegt && !a.thetaz && a.m <= 20 && a.m > kNG && a.sm <= 10;
 }
 // whose node heights the state holds after this call: those of its last launch (the run launch, else the spin-up launch)
 static void note_state_heights(Shard& s, const TransientArgs& a) {

@@ -2,6 +2,7 @@
 // Lets the CPU-only test suite check the product's fused step logic against the oracle without a GPU.
 // It is NOT part of the product library, is never loaded by microclimc_b200/, and is not a CPU fallback.
 #include <cmath>
+#include <cstdlib>
 #include <cstdint>
 #include "../../microclimc_b200/csrc/mc_driver.cuh"
 #include "../../microclimc_b200/csrc/mc_fast.cuh"
@@ -82,7 +83,10 @@ extern "C" int dbg_run_transient_fast(int64_t ncol, int m, int sm, int64_t T, co
       mem.W = W.data() + (c / kTile) * L.nW() * kTile + (c % kTile);
       mem.ia = mem.ib = 1;
       // the instantiation mc_lib.cu would launch: REG (regular node grid, reqhgt NA) only with m = 20, sm = 10
-      if (m == 20 && sm == 10 && fast_regular_grid(t, spin != 0)) fast_run_column<DirectMem, 20, 10, true>(a, mem, c, true);
+      // (MC_HOST_FORCE_REG=1: the regular-grid instantiation at any time step, to exercise its fallback for leaftemp's transient balances)
+      const char* fr = getenv("MC_HOST_FORCE_REG");
+      TransientArgs tq = t; if (fr && fr[0] == '1') tq.cfg.timestep = 3600.0;
+      if (m == 20 && sm == 10 && fast_regular_grid(tq, spin != 0)) fast_run_column<DirectMem, 20, 10, true>(a, mem, c, true);
       else fast_run_column<DirectMem, 20, 10, false>(a, mem, c, true);
     }
   }
