@@ -1,12 +1,13 @@
-// Streaming form of the transient step (runonestep, R/code.R:687-902) for the configuration the BASELINE workloads run:
-// time-invariant PAI, at most kNG merged canopy air layers (hourly steps give 1-5), regular wind edge profile.
-// A column that leaves that envelope at some step (many merged layers at very short time steps, lowest nodes under 0.12 m with
-// the edge profile) is dropped from the streaming launch: the kernel records it in a fail list, stops storing for it, and the
-// library re-runs the listed columns from the launch's initial state through the general kernel (k_transient, mc_step.cuh)
-// right after — the general column is NOT part of this kernel (it used to be: 14 KB stack frame, and its call boundary pinned
-// the register allocation of the hot loop).  A state whose node heights differ from the current geometry (first step after
-// paraminit when reqhgt snaps a node, code.R:573 vs 719) stays in the streaming form: the leaf-geometry rows are built from
-// previn$z for the first step and rebuilt in place from the current heights after it (fast_regeom).
+// Streaming form of the transient step (runonestep, R/code.R:687-902): time-invariant PAI, depth-uniform soil moisture, any time step.
+// Steps with up to kNG merged canopy air layers (hourly steps give 1-5) are solved in the idle stage buffers, steps with more in the
+// lane's own arrays (the wide solve).  A column that leaves the envelope (lowest nodes under 0.12 m with the edge profile; a state whose
+// previn$z is not the launch's node grid in a regular-grid or parameter-class launch; a transient leaf balance on the regular grid) is
+// dropped from the streaming launch: the kernel records it in a fail list, stops storing for it, and the library re-runs the listed
+// columns from the launch's initial state through the general kernel (k_transient, mc_step.cuh) right after — the general column is NOT
+// part of this kernel (it used to be: 14 KB stack frame, and its call boundary pinned the register allocation of the hot loop).
+// Otherwise a state whose node heights differ from the current geometry (first step after paraminit when reqhgt snaps a node,
+// code.R:573 vs 719) stays in the streaming form: the leaf-geometry rows are built from previn$z for the first step and rebuilt in
+// place from the current heights after it (fast_regeom).
 //
 // Why a second form: the general column keeps ~16 KB of thread-private state + hoisted geometry + work arrays and is
 // bound by local-memory latency (profiles/README.md r01b: long_scoreboard 64 % of stalls, FP64 pipe 13 % busy).
